@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the auv_particle_filter measurement cycle (BASELINE.json metric:
+particle-beam likelihood evaluations/s and filter-cycle latency).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port)
+
+A "step" is one filter cycle on one ping: P=5 predicts (50 Hz odometry between
+10 Hz pings) + MBES update (raycast + beam likelihood) + normalise + systematic
+resample + gather with fused roughening.  Workload at 1 GPU = BASELINE config C3
+(1,048,576 particles x 512 beams, 0.5 m DEM over 4 km^2); with N GPUs every rank
+holds that many particles of ONE filter (weak scaling; `--workload C4` gives the
+16M x 512 target configuration at 8 GPUs).
+
+Prints ONE JSON line (rank 0).  `value` = whole-job evals/s with the pings already
+resident in HBM, timed with CUDA events on the library's stream per step (L2 flushed
+between steps), max over ranks; `e2e` = the same through the public Python API with
+pinned HOST buffers (ping H2D, estimate D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from smarc_navigation_b200 import world  # noqa: E402
+
+METRIC = "particle_beam_evals_per_s"
+UNIT = "evals/s"
+P_PREDICTS = 5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4"])
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work per reference step / baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args, n_gpus):
+    name = args.workload
+    if name == "auto":
+        name = "C3"
+    c = dict(world.CONFIGS[name])
+    if name == "C4":
+        per_gpu = c["particles"] // 8
+    else:
+        per_gpu = c["particles"]
+    c["name"] = name
+    c["per_gpu"] = per_gpu
+    c["total"] = per_gpu * n_gpus
+    return c
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.idx = gpu_index
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_cycle_setup(cfg, seed_particles=4):
+    from oracle import c_oracle
+    dem = world.make_dem(cfg["dem_n"], cfg["res"])
+    beams = world.make_beams(cfg["beams"])
+    ext = cfg["dem_n"] * cfg["res"]
+    traj = world.Trajectory(ext)
+    return c_oracle, dem, beams, traj
+
+
+def cpu_run(cfg, n_sample, steps, warmup):
+    """The oracle port of the cycle (C/OpenMP float64 raycast + likelihood + motion model,
+    NumPy/C normalise + systematic resample + gather + roughen) on n_sample particles."""
+    from oracle import pf_oracle as o
+    c_oracle, dem, beams, traj = cpu_cycle_setup(cfg)
+    P = world.MBES_PARAMS
+    B = cfg["beams"]
+    rng = np.random.default_rng(4)
+    poses = o.add_noise(np.tile(traj.truth, (n_sample, 1)), P["init_covariance"], rng.normal(size=(n_sample, 6)))
+    times = []
+    for s in range(warmup + steps):
+        odoms, truth = traj.cycle()
+        r_true = c_oracle.update_mbes(dem, truth[None, :], np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX,
+                                      want_ranges=True)["ranges"][0]
+        meas = r_true + world.ping_noise(B, s)
+        pn = [rng.normal(size=(n_sample, 6)) for _ in odoms]
+        rn = rng.normal(size=(n_sample, 6))
+        u = float(rng.uniform())
+        t0 = time.perf_counter()
+        for od, nz in zip(odoms, pn):
+            roll, pitch = o.odom_roll_pitch(od.quat)
+            poses = c_oracle.motion_pred(poses, od.v, od.wz, roll, pitch, od.z, od.dt, P["motion_covariance"], nz)
+        logw = c_oracle.update_mbes(dem, poses, np.eye(4), beams, meas, P["measurement_std"], world.RANGE_MIN,
+                                    world.RANGE_MAX)["logw"].astype(np.float32)
+        qq, m, A = c_oracle.quantise_logw(logw)
+        anc = c_oracle.systematic(o.weights_from_q(qq), u)
+        poses = o.add_noise(poses[anc], P["resampling_noise_covariance"], rn)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), c_oracle.num_threads()
+
+
+def cpu_sample_size(cfg, seconds):
+    """Size the bounded sample so that one CPU cycle is about `seconds` of work."""
+    t, cores = cpu_run(cfg, 512, 1, 1)          # one untimed warm-up cycle (thread pool, page faults)
+    per_particle = t / 512.0
+    n = int(max(256, min(cfg["per_gpu"], seconds / max(per_particle, 1e-9))))
+    return n, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = workload(args, args.gpus)
+    n, cores = cpu_sample_size(cfg, args.cpu_seconds)
+    t, cores = cpu_run(cfg, n, args.steps, min(args.warmup, 1))
+    v = n * cfg["beams"] / t
+    sample = "%d of %d particles x %d beams per step, C/OpenMP float64 oracle port, %d threads" % (
+        n, cfg["total"], cfg["beams"], cores)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t * cfg["total"] / n, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %d particles x %d beams, %.1f m DEM %dx%d" % (
+                cfg["name"], cfg["total"], cfg["beams"], cfg["res"], cfg["dem_n"], cfg["dem_n"]),
+                "predicts_per_cycle": P_PREDICTS},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    G = world_size
+    cfg = workload(args, G)
+    M, B = cfg["per_gpu"], cfg["beams"]
+    K, W = args.steps, max(args.warmup, 3)
+    P = world.MBES_PARAMS
+    ext = cfg["dem_n"] * cfg["res"]
+    dem = world.make_dem(cfg["dem_n"], cfg["res"])
+    beams = world.make_beams(B)
+    traj = world.Trajectory(ext)
+
+    from smarc_navigation_b200 import ParticleFilter
+    common = dict(init_covariance=P["init_covariance"], motion_covariance=P["motion_covariance"],
+                  resampling_noise_covariance=P["resampling_noise_covariance"],
+                  measurement_std=P["measurement_std"], range_min=world.RANGE_MIN, range_max=world.RANGE_MAX,
+                  init_mean=traj.truth, seed=4)
+    if G == 1:
+        pf = ParticleFilter(particle_count=M, device=local_rank, **common)
+        filt = pf
+    else:
+        from smarc_navigation_b200.sharded import ShardedParticleFilter
+        filt = ShardedParticleFilter(M, dist, device=local_rank, **common)
+        pf = filt.pf
+    filt.set_dem(dem)
+    filt.set_beams(beams)
+
+    # synthetic ping sequence: ground-truth ranges raycast on the GPU (the product path), + noise
+    n_steps = 2 * (K + W) + 2
+    cycles = []
+    for s in range(n_steps):
+        odoms, truth = traj.cycle()
+        r_true = pf.raycast(truth[None, :])[0]
+        cycles.append((odoms, (r_true + world.ping_noise(B, s)).astype(np.float32), truth))
+    pings_dev = torch.from_numpy(np.stack([c[1] for c in cycles])).cuda()
+    pings_pin = torch.from_numpy(np.stack([c[1] for c in cycles])).pin_memory()
+    stream = torch.cuda.ExternalStream(pf.stream_ptr)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    import ctypes as C
+    from smarc_navigation_b200 import _lib
+    L = _lib.load()
+
+    def cycle_device(s):
+        odoms = cycles[s][0]
+        for od in odoms:
+            filt.predict(od)
+        _lib.check(L.auvpf_update_mbes(pf._h, C.c_void_p(pings_dev[s].data_ptr()), None))
+        filt.resample()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    # ---- device-resident timing --------------------------------------------------------------
+    for s in range(W):
+        cycle_device(s)
+    pf.sync()
+    pf.profile(True)
+    pf.profile_read(reset=True)
+    clocks = ClockSampler(local_rank)
+    barrier()
+    evs = []
+    for s in range(W, W + K):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        cycle_device(s)
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    clk = clocks.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(np.sum(step_ms))
+    prof = pf.profile_read(reset=True)
+    pf.profile(False)
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = M * G * B / (ms_per_step * 1e-3)
+    mean, cov = filt.mean_cov()
+    mean = np.asarray(mean).reshape(-1)
+    track_err = float(np.hypot(mean[0] - cycles[W + K - 1][2][0], mean[1] - cycles[W + K - 1][2][1]))
+
+    # ---- end to end through the public API, host buffers ----------------------------------------
+    base = W + K
+    for s in range(base, base + W):
+        for od in cycles[s][0]:
+            filt.predict(od)
+        filt.update_mbes(pings_pin[s].numpy()) if G > 1 else pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
+        filt.resample()
+        filt.mean_cov()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(base + W, base + W + K):
+        for od in cycles[s][0]:
+            filt.predict(od)
+        if G > 1:
+            filt.update_mbes(pings_pin[s].numpy())
+        else:
+            pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
+        filt.resample()
+        est = filt.mean_cov()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = M * G * B * K / e2e_s
+    h2d = B * 4 + P_PREDICTS * 0 + 8            # ping ranges + the resample uniform (odometry travels as kernel arguments)
+    d2h = 16 * 8 + 4                            # pose sums/moments + the degenerate-weights flag
+
+    # ---- roofline of the dominant kernel + the HBM-bound resample path ----------------------------
+    peak, peak_src = peaks()
+    dem_bytes = dem["z"].size * 4
+    mbes_ms, mbes_n = prof["update_mbes"]
+    alg_mbes = M * (32 + 4) + dem_bytes + 16 * B            # state read + logw write, DEM once, beam table
+    ach = alg_mbes / (mbes_ms / max(mbes_n, 1) * 1e-3) / 1e9 if mbes_n else 0.0
+    rs_ms = prof["normalise"][0] + prof["scan"][0] + prof["select_gather"][0]
+    rs_n = max(prof["scan"][1], 1)
+    alg_rs = M * (4 + 4 + 12 + 12 + 4 + 32 + 32)            # max, sum, scan r/w, select r/w, gather r/w
+    ach_rs = alg_rs / (rs_ms / rs_n * 1e-3) / 1e9 if rs_ms > 0 else 0.0
+    prop_ms, prop_n = prof["propagate"]
+    ach_prop = M * 52 / (prop_ms / max(prop_n, 1) * 1e-3) / 1e9 if prop_n else 0.0
+    launches = int(sum(v[1] for v in prof.values()))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %d particles/GPU x %d beams (%d total), %.1f m DEM %dx%d, %d predicts per cycle" % (
+            cfg["name"], M, B, M * G, cfg["res"], cfg["dem_n"], cfg["dem_n"], P_PREDICTS),
+            "parallelism": "particle-sharded x%d" % G, "l2": "flushed between steps (256 MiB memset)",
+            "resampler": "systematic", "cycle_hz": 1e3 / ms_per_step},
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / K},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "k_update_mbes (fused raycast + beam likelihood)",
+                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "peak_source": peak_src, "ms_per_launch": mbes_ms / max(mbes_n, 1),
+                     "evals_per_s": M * B / (mbes_ms / max(mbes_n, 1) * 1e-3) if mbes_n else None,
+                     "note": "dominant kernel is issue/latency-bound on an L1/L2-resident DEM footprint, not "
+                             "HBM-bound (SURVEY 8d); the HBM-bound path is roofline_resample"},
+        "roofline_resample": {"bound": "hbm", "kernel": "normalise + k_scan_q + k_select_gather",
+                              "achieved": ach_rs, "peak": peak, "unit": "GB/s", "frac": ach_rs / peak,
+                              "ms_per_cycle": rs_ms / rs_n, "bytes_per_particle": 100},
+        "roofline_propagate": {"bound": "hbm", "achieved": ach_prop, "peak": peak, "unit": "GB/s",
+                               "frac": ach_prop / peak, "ms_per_launch": prop_ms / max(prop_n, 1)},
+        "kernel_ms_per_cycle": {k: v[0] / K for k, v in prof.items() if v[1]},
+        "track_error_m": track_err,
+    }
+    if rank == 0 and G == 1 and not args.no_cpu_baseline:
+        n, cores = cpu_sample_size(cfg, args.cpu_seconds)
+        t, cores = cpu_run(cfg, n, 1, 0)
+        line["cpu_baseline"] = {"value": n * B / t, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d of %d particles x %d beams, 1 cycle, C/OpenMP float64 oracle port" % (
+                                    n, M, B)}
+    if rank == 0:
+        print(json.dumps(line))
+    filt.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

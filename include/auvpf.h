@@ -1,0 +1,200 @@
+/* auvpf.h -- C ABI of the B200-native auv_particle_filter measurement cycle.
+ *
+ * This is the drop-in boundary for the ONE hot path of smarc_navigation that
+ * this repo replaces: the particle-filter cycle of
+ * auv_particle_filter/scripts/{auv_pf,auv_particle,resampling}.py.  The
+ * reference has no FFI for this path (it is three Python methods on one
+ * object); every entry point below names the reference
+ * lines it replaces.  A maintainer binds these with ctypes from the ROS node
+ * (INTEGRATION.md shows the stub); smarc_navigation_b200/filter.py is that
+ * binding plus a class with the reference's predict/update/resample methods.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no C++/torch types.
+ *  - Every function returns an int status (AUVPF_OK == 0, negative = error);
+ *    auvpf_last_error() returns a thread-local message for the last failure.
+ *  - Every data pointer may be a HOST pointer or a CUDA DEVICE pointer of the
+ *    handle's device (detected with cudaPointerGetAttributes), so torch tensors
+ *    can be passed zero-copy through data_ptr().
+ *  - All work of a handle is enqueued on the handle's own CUDA stream in call
+ *    order.  Calls that copy results to host memory synchronise that stream;
+ *    the others return after enqueueing (auvpf_sync() waits).  A handle is not
+ *    re-entrant: serialise calls per handle (the Python facade holds a lock).
+ *  - Pose layout across the ABI: row-major (n, 6) float64
+ *    [x, y, z, roll, pitch, yaw] in the odom frame, exactly Particle.p_pose
+ *    (auv_particle.py:24,36).  Covariance arguments are the reference's
+ *    6-vectors of VARIANCES in that order (auv_pf.launch:15-19).
+ *  - F independent filters of M particles each live in one handle (F = 1 for
+ *    the reference's single filter); particle i of filter f is row f*M + i.
+ */
+#ifndef AUVPF_H
+#define AUVPF_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUVPF_VERSION 100
+
+/* status codes */
+#define AUVPF_OK 0
+#define AUVPF_ERR_BADARG (-1)
+#define AUVPF_ERR_CUDA (-2)
+#define AUVPF_ERR_STATE (-3)      /* e.g. update_mbes before set_dem/set_beams */
+#define AUVPF_ERR_DEGENERATE (-4) /* all weights zero / -inf / NaN: resample skipped */
+#define AUVPF_ERR_NOMEM (-5)
+
+/* resampler selection for auvpf_resample* */
+#define AUVPF_SYSTEMATIC 0 /* resampling.py:135-168 systematic_resample            */
+#define AUVPF_RESIDUAL 1   /* resampling.py:27-76 residual_resample (deterministic
+                              floor(N w) copies bit-exact; residual draw: see DESIGN.md) */
+
+/* flags for auvpf_resample* */
+#define AUVPF_RS_SORTED 0      /* new[i] = old[ancestor[i]] (ancestors ascending)    */
+#define AUVPF_RS_INPLACE_REF 1 /* reference slot map, auv_pf.py:183-198: survivors keep
+                                  their slot, pose[lost[r]] <- pose[dupes[r]]        */
+
+/* kernel classes for auvpf_profile_read */
+enum {
+    AUVPF_K_PROPAGATE = 0,
+    AUVPF_K_UPDATE_MBES = 1,
+    AUVPF_K_UPDATE_GPS = 2,
+    AUVPF_K_NORMALISE = 3,   /* max + fixed-point sum                                */
+    AUVPF_K_SCAN = 4,        /* decoupled-lookback prefix scan of quantised weights  */
+    AUVPF_K_SELECT_GATHER = 5, /* ancestor select + particle gather (+ roughening)   */
+    AUVPF_K_ROUGHEN = 6,
+    AUVPF_K_ESTIMATE = 7,
+    AUVPF_K_OTHER = 8,
+    AUVPF_K_COUNT = 9
+};
+
+typedef struct auvpf_handle auvpf_handle;
+
+/* Constructor parameters: the ROS params of auv_pf.__init__ (auv_pf.py:27-56,
+ * auv_pf.launch:15-20) plus what the GPU path adds. */
+typedef struct auvpf_config {
+    int32_t struct_size;     /* sizeof(auvpf_config), for forward compatibility      */
+    int32_t device;          /* CUDA device ordinal                                  */
+    int64_t particle_count;  /* M, ~particle_count (auv_pf.py:27)                    */
+    int32_t n_filters;       /* F independent filters sharing map/beams (default 1)  */
+    int32_t coarse_level;    /* max-mip level used for ray skipping; -1 = automatic  */
+    int64_t global_offset;   /* id of this shard's first particle (multi-GPU), else 0 */
+    int64_t global_count;    /* particles per filter over all shards; 0 = M          */
+    double motion_cov[6];    /* ~motion_covariance (auv_pf.py:40-44)                 */
+    double meas_std;         /* ~measurement_std (auv_pf.py:39)                      */
+    double m2o[16];          /* map<-odom 4x4 row-major (auv_pf.py:79-81)            */
+    uint64_t seed;           /* Philox key                                           */
+    double range_min;        /* measured beams outside [range_min, range_max] or     */
+    double range_max;        /*   non-finite are skipped; a raycast MISS = range_max */
+} auvpf_config;
+
+/* -- lifecycle ------------------------------------------------------------ */
+int auvpf_version(void);
+const char *auvpf_last_error(void);
+/* auv_pf.__init__ (auv_pf.py:25-119) minus ROS; particles start at pose 0 and
+ * are spread by auvpf_init_particles. */
+int auvpf_create(const auvpf_config *cfg, auvpf_handle **out);
+int auvpf_destroy(auvpf_handle *h);
+int auvpf_sync(auvpf_handle *h);
+/* the handle's cudaStream_t, for torch.cuda.ExternalStream interop */
+void *auvpf_stream(auvpf_handle *h);
+int64_t auvpf_particle_count(auvpf_handle *h); /* F*M rows held by this handle */
+
+/* -- map and sensor model (no reference counterpart: SURVEY.md section 0) --- */
+/* H x W float32 vertex heights, row i at y0 + i*res, column j at x0 + j*res;
+ * builds the max-mip pyramid on the device. */
+int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double x0, double y0, double res);
+/* B unit beam directions in the sensor (= particle body) frame, (B,3) float32 */
+int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B);
+
+/* -- particle state --------------------------------------------------------- */
+/* Particle.__init__ -> add_noise(init_cov) (auv_particle.py:24,30,32-36):
+ * pose = mean + sqrt(var) * n.  noise: (F*M, 6) float32 standard normals in
+ * the reference's draw order, or NULL for the library's Philox stream. */
+int auvpf_init_particles(auvpf_handle *h, const double mean[6], const double var[6], const float *noise);
+int auvpf_set_poses(auvpf_handle *h, const double *poses);   /* (F*M, 6) */
+int auvpf_get_poses(auvpf_handle *h, double *poses);         /* (F*M, 6) */
+int auvpf_get_logw(auvpf_handle *h, float *logw);            /* (F*M)    */
+int auvpf_set_logw(auvpf_handle *h, const float *logw);      /* (F*M)    */
+
+/* -- predict: auv_pf.predict (auv_pf.py:213-216) -> Particle.motion_pred
+ * (auv_particle.py:38-70).  odom: (F, 11) float64 rows
+ * [vx, vy, vz, wz, qx, qy, qz, qw, z, dt, unused]; n_odom == 1 broadcasts one
+ * row to every filter.  noise: (F*M, 6) float32 normals (columns 0, 1, 5 are
+ * consumed, like the reference) or NULL for Philox. */
+int auvpf_predict(auvpf_handle *h, const double *odom, int32_t n_odom, const float *noise);
+
+/* -- update ----------------------------------------------------------------- */
+/* auv_pf.update (auv_pf.py:135-167) -> Particle.compute_weight
+ * (auv_particle.py:100-106): log N2(gps; p_map[0:2], std^2 I).  gps_xy: (F, 2)
+ * in the map frame.  logw_out: (F*M) float32 or NULL (kept on the device). */
+int auvpf_update_gps(auvpf_handle *h, const double *gps_xy, float *logw_out);
+/* North-star form of compute_weight: raycast every beam from every particle
+ * pose (get_p_pose, auv_particle.py:72-83) into the DEM and score
+ * logw = -1/(2 std^2) sum_b (r_b - rhat_b)^2 - B_valid log(std sqrt(2 pi)).
+ * ranges: (F, B) float32 measured ranges (a LaserScan's ranges[]). */
+int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out);
+/* Parity probe: expected ranges (n, B) float32 for n explicit poses (n, 6). */
+int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges_out);
+
+/* -- normalise + resample: auv_pf.resample (auv_pf.py:169-192) --------------- */
+/* Uses the device-resident log-weights of the last update.  u: F uniforms in
+ * [0,1) replacing resampling.py's random() (:157), or NULL for Philox.
+ * ancestors_out: (F*M) int32 (filter-local ids) or NULL.  rough_var: 6
+ * variances of the post-resample add_noise (auv_pf.py:191-192) fused into the
+ * gather, or NULL for none; rough_noise as in auvpf_init_particles.
+ * Returns AUVPF_ERR_DEGENERATE (state untouched) when a filter has no finite
+ * weight. */
+int auvpf_resample(auvpf_handle *h, int32_t mode, int32_t flags, const double *u, int32_t *ancestors_out,
+                   const double *rough_var, const float *rough_noise);
+/* Same, from caller-supplied LINEAR float64 weights (F*M) -- the literal
+ * resample(weights) of the reference (normalisation auv_pf.py:172 included). */
+int auvpf_resample_weights(auvpf_handle *h, const double *weights, int32_t mode, int32_t flags, const double *u,
+                           int32_t *ancestors_out, const double *rough_var, const float *rough_noise);
+/* The fixed-point normalised weights of the last resample: (F*M) uint64,
+ * w_i = q_i * 2^-52, sum_i q_i == 2^52 exactly per filter. */
+int auvpf_get_weights_q(auvpf_handle *h, uint64_t *q);
+/* Apply caller-supplied ancestor indices with the reference's in-place slot
+ * map (auv_pf.py:183-189 keep/lost/dupes + reassign_poses :195-198). */
+int auvpf_apply_indices(auvpf_handle *h, const int32_t *indices, int32_t flags);
+/* Particle.add_noise on every particle (auv_pf.py:191-192). */
+int auvpf_roughen(auvpf_handle *h, const double var[6], const float *noise);
+
+/* -- estimate: auv_pf.update_loc_pose (auv_pf.py:218-252) -------------------- */
+/* mean: (F, 6) [x y z roll pitch yaw_mean_of_wrapped]; cov: (F, 9) row-major
+ * 3x3 with the reference's fill pattern ([2,0], [2,1] left 0). */
+int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov);
+/* effective sample size 1 / sum w^2 of the last normalisation, (F) */
+int auvpf_neff(auvpf_handle *h, double *neff);
+
+/* -- multi-GPU staging (particle-sharded single filter) - */
+/* stage 1: local max of logw (F floats) */
+int auvpf_shard_max(auvpf_handle *h, float *m_out);
+/* stage 2: given the GLOBAL max, local fixed-point sums: (F, 2) uint64 limbs
+ * [sum of low 32 bits, sum of high bits]; A = lo + (hi << 32). */
+int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *limbs_out);
+/* stage 3: given global max and global A (F,2: lo64, hi64), quantise and scan
+ * locally; returns the local total Q (F). */
+int auvpf_shard_scan(auvpf_handle *h, const float *m_global, const uint64_t *A_global, uint64_t *Q_out);
+/* stage 4: emit the n_out = out_hi - out_lo offspring whose ancestors live in
+ * this shard: global output slots [out_lo, out_hi) as 32-byte records
+ * {double x, y; float z, roll, pitch, yaw} into `records` (device or host) and,
+ * optionally, their GLOBAL ancestor ids.  q_offset = sum of Q of lower shards,
+ * deficit = 2^52 - sum of all Q. */
+int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t deficit, int64_t out_lo,
+                     int64_t out_hi, void *records, int64_t *ancestors_out);
+/* stage 5: replace the local state by M records received from the exchange */
+int auvpf_shard_load(auvpf_handle *h, const void *records, int64_t n);
+
+/* -- measurement support ----------------------------------------------------- */
+int auvpf_profile_enable(auvpf_handle *h, int32_t on);
+/* accumulated CUDA-event time [ms] and launch count per kernel class since the
+ * last reset; synchronises the stream. */
+int auvpf_profile_read(auvpf_handle *h, double ms[AUVPF_K_COUNT], int64_t launches[AUVPF_K_COUNT], int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUVPF_H */

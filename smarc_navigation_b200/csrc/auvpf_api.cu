@@ -1,0 +1,1157 @@
+// auvpf_api.cu -- C ABI (include/auvpf.h) over the sm_100a kernels.
+//
+// One handle = one CUDA device, one stream, F filters x M particles.  The handle owns every
+// device buffer; callers own what they pass.  No CPU fallback exists: every entry point either
+// enqueues kernels on the handle's stream or fails with an error code.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/auvpf.h"
+#include "auvpf_kernels.cuh"
+
+using namespace auvpf;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? AUVPF_ERR_NOMEM : AUVPF_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e_), __FILE__, __LINE__);                              \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+enum Slot { S_IN0 = 0, S_IN1, S_IN2, S_OUT0, S_OUT1, S_COUNT };
+
+struct ProfEvent {
+    cudaEvent_t a, b;
+    int klass;
+};
+
+}   // namespace
+
+struct auvpf_handle {
+    auvpf_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t M = 0, N = 0;   // per filter, total rows
+    int F = 1;
+    int64_t global_offset = 0, global_count = 0;
+
+    // state (double-buffered SoA)
+    StateView st[2];
+    int cur = 0;
+    float *logw = nullptr;
+    unsigned long long *cdf = nullptr;
+
+    // per-filter scalars
+    long long *wmax_ordered = nullptr;
+    double *wmax = nullptr;
+    unsigned long long *limbs = nullptr, *A = nullptr, *Q = nullptr, *deficit = nullptr;
+    double *u = nullptr, *sumsq = nullptr, *sums = nullptr, *mom = nullptr, *gps = nullptr;
+    PredictParams *pparams = nullptr;
+    int *degenerate = nullptr;
+
+    // scan machinery
+    unsigned long long *status = nullptr;
+    unsigned int *tile_counter = nullptr;
+    int tiles_per_filter = 0;
+
+    // resampling extras
+    int32_t *anc = nullptr;
+    int *first = nullptr;
+    unsigned long long *scan2 = nullptr, *totals2 = nullptr;
+    int32_t *lost = nullptr, *dupes = nullptr;
+    const double *lin_weights = nullptr;   // device pointer of the last linear weight source
+    int last_src_kind = 0;
+    bool have_norm = false;
+
+    // map / sensor
+    float *dem_z = nullptr, *mip = nullptr, *beams = nullptr, *meas = nullptr;
+    DemView dem{};
+    bool have_dem = false;
+    int B = 0;
+    FrameParams frame{};
+
+    // step counters for the Philox streams
+    uint32_t step_predict = 0, step_rough = 0, step_resample = 0;
+
+    DevBuf slots[S_COUNT];
+    void *pinned = nullptr;   // small pinned staging ring
+    size_t pinned_cap = 1 << 16, pinned_off = 0;
+
+    // profiling
+    bool prof = false;
+    std::vector<ProfEvent> prof_events;
+    std::vector<ProfEvent> prof_pool;
+    double prof_ms[AUVPF_K_COUNT] = {0};
+    int64_t prof_launches[AUVPF_K_COUNT] = {0};
+};
+
+namespace {
+
+struct Guard {   // make the handle's device current for the duration of a call
+    int prev = -1;
+    explicit Guard(auvpf_handle *h)
+    {
+        cudaGetDevice(&prev);
+        if (prev != h->device) cudaSetDevice(h->device);
+    }
+    ~Guard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct Prof {   // CUDA-event bracket around the kernels of one class
+    auvpf_handle *h;
+    ProfEvent ev{};
+    bool on;
+    Prof(auvpf_handle *h_, int klass) : h(h_), on(h_->prof)
+    {
+        if (!on) return;
+        if (!h->prof_pool.empty()) {
+            ev = h->prof_pool.back();
+            h->prof_pool.pop_back();
+        } else {
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+        }
+        ev.klass = klass;
+        cudaEventRecord(ev.a, h->stream);
+    }
+    ~Prof()
+    {
+        if (!on) return;
+        cudaEventRecord(ev.b, h->stream);
+        h->prof_events.push_back(ev);
+    }
+};
+
+#define LAUNCHED(h, klass, n) ((h)->prof_launches[klass] += (n))
+
+bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int slot_reserve(auvpf_handle *h, int slot, size_t bytes, void **out)
+{
+    DevBuf &b = h->slots[slot];
+    if (b.cap < bytes) {
+        if (b.p) {
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaFree(b.p));
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t cap = bytes + bytes / 4 + 256;
+        CU(cudaMalloc(&b.p, cap));
+        b.cap = cap;
+    }
+    *out = b.p;
+    return AUVPF_OK;
+}
+
+// device view of an input that may live on the host
+template <class T>
+int stage_in(auvpf_handle *h, int slot, const T *src, size_t count, const T **dev)
+{
+    if (is_device_ptr(src)) {
+        *dev = src;
+        return AUVPF_OK;
+    }
+    void *d = nullptr;
+    int rc = slot_reserve(h, slot, count * sizeof(T), &d);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    *dev = static_cast<const T *>(d);
+    return AUVPF_OK;
+}
+
+// device buffer a kernel writes an output into; finish_out copies back when dst is host memory
+template <class T>
+int stage_out(auvpf_handle *h, int slot, T *dst, size_t count, T **dev)
+{
+    if (is_device_ptr(dst)) {
+        *dev = dst;
+        return AUVPF_OK;
+    }
+    void *d = nullptr;
+    int rc = slot_reserve(h, slot, count * sizeof(T), &d);
+    if (rc) return rc;
+    *dev = static_cast<T *>(d);
+    return AUVPF_OK;
+}
+
+template <class T>
+int finish_out(auvpf_handle *h, T *dst, const T *dev, size_t count)
+{
+    if (static_cast<const void *>(dst) == static_cast<const void *>(dev)) return AUVPF_OK;
+    CU(cudaMemcpyAsync(dst, dev, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
+// tiny host->device upload through the pinned ring (fully asynchronous)
+int tiny_upload(auvpf_handle *h, void *dst_dev, const void *src_host, size_t bytes)
+{
+    if (bytes > h->pinned_cap / 4) {
+        CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, h->stream));
+        return AUVPF_OK;
+    }
+    size_t off = (h->pinned_off + 15) & ~size_t(15);
+    if (off + bytes > h->pinned_cap) {
+        CU(cudaStreamSynchronize(h->stream));   // wrap: make sure earlier copies have drained
+        off = 0;
+    }
+    memcpy(static_cast<char *>(h->pinned) + off, src_host, bytes);
+    CU(cudaMemcpyAsync(dst_dev, static_cast<char *>(h->pinned) + off, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->pinned_off = off + bytes;
+    return AUVPF_OK;
+}
+
+inline dim3 grid1(int64_t n, int per_block, int F) { return dim3((unsigned)((n + per_block - 1) / per_block), (unsigned)F); }
+
+// tf.transformations.euler_from_quaternion(q)[0:2] with 'sxyz' (auv_particle.py:50-56): host, float64.
+void roll_pitch_from_quat(const double q_in[4], double &roll, double &pitch)
+{
+    double q[4] = {q_in[0], q_in[1], q_in[2], q_in[3]};
+    double nq = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const double eps = 2.220446049250313e-16 * 4.0;
+    double Mm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (nq >= eps) {
+        double s = std::sqrt(2.0 / nq);
+        for (double &c : q) c *= s;
+        double o[4][4];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) o[i][j] = q[i] * q[j];
+        Mm[0][0] = 1.0 - o[1][1] - o[2][2];
+        Mm[1][0] = o[0][1] + o[2][3];
+        Mm[2][0] = o[0][2] - o[1][3];
+        Mm[1][1] = 1.0 - o[0][0] - o[2][2];
+        Mm[1][2] = o[1][2] - o[0][3];
+        Mm[2][1] = o[1][2] + o[0][3];
+        Mm[2][2] = 1.0 - o[0][0] - o[1][1];
+    }
+    double cy = std::sqrt(Mm[0][0] * Mm[0][0] + Mm[1][0] * Mm[1][0]);
+    if (cy > eps) {
+        roll = std::atan2(Mm[2][1], Mm[2][2]);
+        pitch = std::atan2(-Mm[2][0], cy);
+    } else {
+        roll = std::atan2(-Mm[1][2], Mm[1][1]);
+        pitch = std::atan2(-Mm[2][0], cy);
+    }
+}
+
+PredictParams make_predict(const double *od, const double motion_cov[6])
+{
+    // od = [vx vy vz wz qx qy qz qw z dt]
+    double roll, pitch;
+    roll_pitch_from_quat(od + 4, roll, pitch);
+    const double dt = od[9];
+    const double vx = od[0] * dt, vy = od[1] * dt, vz = od[2] * dt;
+    const double cr = std::cos(roll), sr = std::sin(roll), cp = std::cos(pitch), sp = std::sin(pitch);
+    PredictParams p;
+    p.a = (float)(cp * vx + sp * sr * vy + sp * cr * vz);
+    p.b = (float)(cr * vy - sr * vz);
+    p.wzdt = (float)(od[3] * dt);
+    p.roll = (float)roll;
+    p.pitch = (float)pitch;
+    p.z = (float)od[8];
+    p.sx = (float)std::sqrt(motion_cov[0]);
+    p.sy = (float)std::sqrt(motion_cov[1]);
+    p.syaw = (float)std::sqrt(motion_cov[5]);
+    p.pad = 0.f;
+    return p;
+}
+
+NoiseParams make_noise(auvpf_handle *h, const double var[6], const double *mean, int mode, uint32_t step,
+                       uint32_t stream)
+{
+    NoiseParams n{};
+    for (int c = 0; c < 6; ++c) {
+        n.sigma[c] = var ? (float)std::sqrt(var[c]) : 0.f;
+        n.mean[c] = mean ? mean[c] : 0.0;
+    }
+    n.mode = mode;
+    n.seed = h->cfg.seed;
+    n.step = step;
+    n.stream = stream;
+    n.global_offset = h->global_offset;
+    n.global_stride = h->global_count;
+    return n;
+}
+
+int alloc_state(StateView &s, int64_t n)
+{
+    CU(cudaMalloc(&s.x, n * sizeof(double)));
+    CU(cudaMalloc(&s.y, n * sizeof(double)));
+    CU(cudaMalloc(&s.z, n * sizeof(float)));
+    CU(cudaMalloc(&s.roll, n * sizeof(float)));
+    CU(cudaMalloc(&s.pitch, n * sizeof(float)));
+    CU(cudaMalloc(&s.yaw, n * sizeof(float)));
+    return AUVPF_OK;
+}
+
+void free_state(StateView &s)
+{
+    cudaFree(s.x);
+    cudaFree(s.y);
+    cudaFree(s.z);
+    cudaFree(s.roll);
+    cudaFree(s.pitch);
+    cudaFree(s.yaw);
+}
+
+__global__ void k_reset_scalars(long long *wmax_ordered, unsigned long long *limbs, double *sumsq,
+                                unsigned int *tile_counter, int F)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f == 0) *tile_counter = 0;
+    if (f >= F) return;
+    wmax_ordered[f] = double_to_ordered(-INFINITY);
+    limbs[2 * f] = 0;
+    limbs[2 * f + 1] = 0;
+    sumsq[f] = 0.0;
+}
+
+// ordered max -> double, and the degenerate flag (no finite / positive weight)
+__global__ void k_finish_max(const long long *wmax_ordered, double *wmax, int *degenerate, int kind, int F)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    double m = ordered_to_double(wmax_ordered[f]);
+    wmax[f] = m;
+    bool bad = !isfinite(m) || (kind == 1 && !(m > 0.0));
+    degenerate[f] = bad ? 1 : 0;
+}
+
+__global__ void k_zero_f64(double *p, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 0.0;
+}
+
+// ---- normalisation + scan on the handle's stream ---------------------------------------------
+int run_max(auvpf_handle *h, const WeightSrc &src)
+{
+    Prof pr(h, AUVPF_K_NORMALISE);
+    k_reset_scalars<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->wmax_ordered, h->limbs, h->sumsq, h->tile_counter,
+                                                               h->F);
+    int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
+    k_weight_max<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax_ordered);
+    k_finish_max<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->wmax_ordered, h->wmax, h->degenerate, src.kind, h->F);
+    LAUNCHED(h, AUVPF_K_NORMALISE, 3);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+int run_sum(auvpf_handle *h, const WeightSrc &src)
+{
+    Prof pr(h, AUVPF_K_NORMALISE);
+    int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
+    k_weight_sum<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->limbs);
+    LAUNCHED(h, AUVPF_K_NORMALISE, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+int run_scan(auvpf_handle *h, const WeightSrc &src)
+{
+    Prof pr(h, AUVPF_K_SCAN);
+    CU(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * h->F, h->stream));
+    CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+    k_scan_q<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->A, h->cdf, h->status,
+                                                                     h->tile_counter, h->tiles_per_filter, h->Q,
+                                                                     h->sumsq);
+    LAUNCHED(h, AUVPF_K_SCAN, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+int check_degenerate(auvpf_handle *h)
+{
+    std::vector<int> deg(h->F);
+    CU(cudaMemcpyAsync(deg.data(), h->degenerate, sizeof(int) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < h->F; ++f)
+        if (deg[f]) return fail(AUVPF_ERR_DEGENERATE, "filter %d: no finite positive weight; resample skipped", f);
+    return AUVPF_OK;
+}
+
+int ensure_inplace_buffers(auvpf_handle *h)
+{
+    if (h->first) return AUVPF_OK;
+    CU(cudaMalloc(&h->first, sizeof(int) * h->N));
+    CU(cudaMalloc(&h->scan2, sizeof(unsigned long long) * h->N));
+    CU(cudaMalloc(&h->totals2, sizeof(unsigned long long) * 2 * h->F));
+    CU(cudaMalloc(&h->lost, sizeof(int32_t) * h->N));
+    CU(cudaMalloc(&h->dupes, sizeof(int32_t) * h->N));
+    return AUVPF_OK;
+}
+
+// reference slot map on device-resident indices (auv_pf.py:183-198)
+int apply_indices_dev(auvpf_handle *h, const int32_t *idx)
+{
+    int rc = ensure_inplace_buffers(h);
+    if (rc) return rc;
+    Prof pr(h, AUVPF_K_SELECT_GATHER);
+    const dim3 g = grid1(h->M, kThreads, h->F);
+    CU(cudaMemsetAsync(h->first, 0x7f, sizeof(int) * h->N, h->stream));
+    k_first_occurrence<<<g, kThreads, 0, h->stream>>>(idx, h->M, h->first);
+    const size_t st_bytes = sizeof(unsigned long long) * (size_t)h->tiles_per_filter * h->F;
+    CU(cudaMemsetAsync(h->status, 0, st_bytes, h->stream));
+    CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+    k_scan_lost<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(h->first, h->M, h->cdf, h->status,
+                                                                        h->tile_counter, h->tiles_per_filter,
+                                                                        h->totals2);
+    CU(cudaMemsetAsync(h->status, 0, st_bytes, h->stream));
+    CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+    k_scan_dupes<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(h->first, idx, h->M, h->scan2, h->status,
+                                                                         h->tile_counter, h->tiles_per_filter,
+                                                                         h->totals2 + h->F);
+    k_compact_lost_dupes<<<g, kThreads, 0, h->stream>>>(h->first, idx, h->M, h->cdf, h->scan2, h->lost, h->dupes);
+    k_reassign<<<g, kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->lost, h->dupes, h->totals2, h->totals2 + h->F);
+    LAUNCHED(h, AUVPF_K_SELECT_GATHER, 6);
+    CU(cudaGetLastError());
+    h->have_norm = false;   // cdf buffer was reused
+    return AUVPF_OK;
+}
+
+int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t flags, const double *u,
+                int32_t *ancestors_out, const double *rough_var, const float *rough_noise)
+{
+    if (mode != AUVPF_SYSTEMATIC)
+        return fail(AUVPF_ERR_BADARG, "resample mode %d not available in this build (systematic only)", mode);
+    int rc;
+    if ((rc = run_max(h, src))) return rc;
+    if ((rc = check_degenerate(h))) return rc;
+    if ((rc = run_sum(h, src))) return rc;
+    k_combine_limbs<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->limbs, h->A, h->F);
+    if ((rc = run_scan(h, src))) return rc;
+    k_deficit<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->Q, h->deficit, h->F);
+    LAUNCHED(h, AUVPF_K_NORMALISE, 3);
+    h->have_norm = true;
+    h->last_src_kind = src.kind;
+    h->lin_weights = src.lin;
+
+    // uniforms: resampling.py:157 random()
+    std::vector<double> uh(h->F);
+    if (u) {
+        if (is_device_ptr(u)) CU(cudaMemcpyAsync(h->u, u, sizeof(double) * h->F, cudaMemcpyDeviceToDevice, h->stream));
+        else if ((rc = tiny_upload(h, h->u, u, sizeof(double) * h->F))) return rc;
+    } else {
+        for (int f = 0; f < h->F; ++f)
+            uh[f] = uniform53(philox_for(h->cfg.seed, f, h->step_resample, kStreamResample, 0));
+        if ((rc = tiny_upload(h, h->u, uh.data(), sizeof(double) * h->F))) return rc;
+    }
+    h->step_resample++;
+
+    const bool inplace = (flags & AUVPF_RS_INPLACE_REF) != 0;
+    const float *rn = nullptr;
+    if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
+    NoiseParams rough = make_noise(h, rough_var, nullptr, (rough_var && !inplace) ? 1 : 0, h->step_rough, kStreamRoughen);
+    int32_t *anc_dev = nullptr;
+    if (ancestors_out || inplace) {
+        if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
+        anc_dev = h->anc;
+        if (ancestors_out && is_device_ptr(ancestors_out) && !inplace) anc_dev = ancestors_out;
+    }
+    SelectParams sp;
+    sp.M = h->M;
+    sp.n_global = h->M;
+    sp.j_global0 = 0;
+    sp.out_lo = 0;
+    sp.n_out = h->M;
+    sp.q_offset = 0;
+    {
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        StateView dst = h->st[1 - h->cur];
+        if (inplace) dst.x = nullptr;   // ancestors only
+        k_select_gather<false><<<grid1(h->M, kSelTile, h->F), kThreads, 0, h->stream>>>(
+            h->cdf, sp, h->u, h->deficit, h->st[h->cur], dst, nullptr, anc_dev, nullptr, rough, rn);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+        CU(cudaGetLastError());
+    }
+    if (!inplace) {
+        h->cur = 1 - h->cur;
+        if (rough_var) h->step_rough++;
+    }
+    if (ancestors_out && anc_dev != ancestors_out) {
+        if (is_device_ptr(ancestors_out))
+            CU(cudaMemcpyAsync(ancestors_out, anc_dev, sizeof(int32_t) * h->N, cudaMemcpyDeviceToDevice, h->stream));
+        else if ((rc = finish_out(h, ancestors_out, (const int32_t *)anc_dev, (size_t)h->N)))
+            return rc;
+    }
+    if (inplace) {
+        if ((rc = apply_indices_dev(h, anc_dev))) return rc;
+        if (rough_var && (rc = auvpf_roughen(h, rough_var, rough_noise))) return rc;
+    }
+    return AUVPF_OK;
+}
+
+}   // namespace
+
+// ================================================================================================
+extern "C" {
+
+int auvpf_version(void) { return AUVPF_VERSION; }
+
+const char *auvpf_last_error(void) { return g_err.c_str(); }
+
+int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
+{
+    if (!cfg || !out) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (cfg->struct_size != (int32_t)sizeof(auvpf_config))
+        return fail(AUVPF_ERR_BADARG, "auvpf_config.struct_size %d != %zu", cfg->struct_size, sizeof(auvpf_config));
+    if (cfg->particle_count <= 0 || cfg->particle_count > (1ll << 30))
+        return fail(AUVPF_ERR_BADARG, "particle_count %lld out of range", (long long)cfg->particle_count);
+    const int F = cfg->n_filters <= 0 ? 1 : cfg->n_filters;
+    if (!(cfg->meas_std > 0.0)) return fail(AUVPF_ERR_BADARG, "measurement_std must be > 0");
+    if (!(cfg->range_max > 0.0)) return fail(AUVPF_ERR_BADARG, "range_max must be > 0");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(AUVPF_ERR_BADARG, "device %d of %d", cfg->device, ndev);
+
+    auvpf_handle *h = new (std::nothrow) auvpf_handle();
+    if (!h) return fail(AUVPF_ERR_NOMEM, "host allocation failed");
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    h->M = cfg->particle_count;
+    h->F = F;
+    h->N = h->M * F;
+    h->global_offset = cfg->global_offset;
+    h->global_count = cfg->global_count > 0 ? cfg->global_count : h->M;
+    Guard g(h);
+    int rc = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        int rc2;
+        if ((rc2 = alloc_state(h->st[0], h->N)) || (rc2 = alloc_state(h->st[1], h->N))) return rc2;
+        CU(cudaMalloc(&h->logw, sizeof(float) * h->N));
+        CU(cudaMalloc(&h->cdf, sizeof(unsigned long long) * h->N));
+        CU(cudaMalloc(&h->wmax_ordered, sizeof(long long) * F));
+        CU(cudaMalloc(&h->wmax, sizeof(double) * F));
+        CU(cudaMalloc(&h->limbs, sizeof(unsigned long long) * 2 * F));
+        CU(cudaMalloc(&h->A, sizeof(unsigned long long) * 2 * F));
+        CU(cudaMalloc(&h->Q, sizeof(unsigned long long) * F));
+        CU(cudaMalloc(&h->deficit, sizeof(unsigned long long) * F));
+        CU(cudaMalloc(&h->u, sizeof(double) * F));
+        CU(cudaMalloc(&h->sumsq, sizeof(double) * F));
+        CU(cudaMalloc(&h->sums, sizeof(double) * 16 * F));
+        h->mom = h->sums + 8 * F;
+        CU(cudaMalloc(&h->gps, sizeof(double) * 2 * F));
+        CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F));
+        CU(cudaMalloc(&h->degenerate, sizeof(int) * F));
+        h->tiles_per_filter = (int)((h->M + kScanTile - 1) / kScanTile);
+        CU(cudaMalloc(&h->status, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * F));
+        CU(cudaMalloc(&h->tile_counter, sizeof(unsigned int)));
+        CU(cudaMallocHost(&h->pinned, h->pinned_cap));
+        for (int b = 0; b < 2; ++b) {
+            CU(cudaMemsetAsync(h->st[b].x, 0, sizeof(double) * h->N, h->stream));
+            CU(cudaMemsetAsync(h->st[b].y, 0, sizeof(double) * h->N, h->stream));
+            CU(cudaMemsetAsync(h->st[b].z, 0, sizeof(float) * h->N, h->stream));
+            CU(cudaMemsetAsync(h->st[b].roll, 0, sizeof(float) * h->N, h->stream));
+            CU(cudaMemsetAsync(h->st[b].pitch, 0, sizeof(float) * h->N, h->stream));
+            CU(cudaMemsetAsync(h->st[b].yaw, 0, sizeof(float) * h->N, h->stream));
+        }
+        CU(cudaMemsetAsync(h->logw, 0, sizeof(float) * h->N, h->stream));
+        return AUVPF_OK;
+    }();
+    if (rc) {
+        auvpf_destroy(h);
+        return rc;
+    }
+    // map <- odom transform (auv_pf.py:79-81)
+    bool ident = true;
+    for (int a = 0; a < 3; ++a) {
+        h->frame.m2o_t[a] = cfg->m2o[4 * a + 3];
+        for (int b = 0; b < 3; ++b) {
+            double v = cfg->m2o[4 * a + b];
+            h->frame.m2o_r[3 * a + b] = v;
+            if (v != (a == b ? 1.0 : 0.0)) ident = false;
+        }
+    }
+    h->frame.m2o_identity_r = ident ? 1 : 0;
+    *out = h;
+    return AUVPF_OK;
+}
+
+int auvpf_destroy(auvpf_handle *h)
+{
+    if (!h) return AUVPF_OK;
+    Guard g(h);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_state(h->st[0]);
+    free_state(h->st[1]);
+    void *bufs[] = {h->logw,    h->cdf,   h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
+                    h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
+                    h->status,  h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas};
+    for (void *b : bufs) cudaFree(b);
+    for (auto &s : h->slots) cudaFree(s.p);
+    if (h->pinned) cudaFreeHost(h->pinned);
+    for (auto &e : h->prof_events) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    for (auto &e : h->prof_pool) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    cudaGetLastError();
+    delete h;
+    return AUVPF_OK;
+}
+
+int auvpf_sync(auvpf_handle *h)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
+void *auvpf_stream(auvpf_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int64_t auvpf_particle_count(auvpf_handle *h) { return h ? h->N : 0; }
+
+// ------------------------------------------------------------------------------------------------
+int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double x0, double y0, double res)
+{
+    if (!h || !z) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (H < 2 || W < 2 || !(res > 0.0)) return fail(AUVPF_ERR_BADARG, "DEM must be at least 2x2 with res > 0");
+    Guard g(h);
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->dem_z);
+    cudaFree(h->mip);
+    h->dem_z = h->mip = nullptr;
+    h->have_dem = false;
+    const size_t n = (size_t)H * W;
+    CU(cudaMalloc(&h->dem_z, n * sizeof(float)));
+    CU(cudaMemcpyAsync(h->dem_z, z, n * sizeof(float), is_device_ptr(z) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       h->stream));
+    // coarse level: blocks of about 4 m unless the caller chose
+    int shift = h->cfg.coarse_level;
+    if (shift < 0) {
+        shift = (int)std::lround(std::log2(4.0 / res));
+    }
+    if (shift < 1) shift = 1;
+    if (shift > 8) shift = 8;
+    // build levels 1..shift
+    float *prev = nullptr;
+    int pH = 0, pW = 0;
+    dim3 tb(32, 8);
+    for (int L = 1; L <= shift; ++L) {
+        int S = 1 << L;
+        int oH = (H - 1 + S - 1) / S, oW = (W - 1 + S - 1) / S;
+        if (oH < 1) oH = 1;
+        if (oW < 1) oW = 1;
+        float *lvl;
+        CU(cudaMalloc(&lvl, (size_t)oH * oW * sizeof(float)));
+        dim3 gr((oW + tb.x - 1) / tb.x, (oH + tb.y - 1) / tb.y);
+        if (L == 1) k_mip_level1<<<gr, tb, 0, h->stream>>>(h->dem_z, H, W, lvl, oH, oW);
+        else k_mip_down<<<gr, tb, 0, h->stream>>>(prev, pH, pW, lvl, oH, oW);
+        CU(cudaGetLastError());
+        if (prev) {
+            CU(cudaStreamSynchronize(h->stream));
+            cudaFree(prev);
+        }
+        prev = lvl;
+        pH = oH;
+        pW = oW;
+    }
+    h->mip = prev;
+    // global maximum height
+    int *d_max;
+    void *tmp;
+    int rc = slot_reserve(h, S_OUT0, sizeof(int), &tmp);
+    if (rc) return rc;
+    d_max = static_cast<int *>(tmp);
+    int init = 0x80000000;   // ordered encoding below every float
+    CU(cudaMemcpyAsync(d_max, &init, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    k_max_f32<<<296, 256, 0, h->stream>>>(h->dem_z, (int64_t)n, d_max);
+    int mx;
+    CU(cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    mx = mx >= 0 ? mx : mx ^ 0x7FFFFFFF;
+    float zmax;
+    memcpy(&zmax, &mx, sizeof zmax);
+
+    DemView &d = h->dem;
+    d.z = h->dem_z;
+    d.mip = h->mip;
+    d.W = W;
+    d.H = H;
+    d.mipW = pW;
+    d.mipH = pH;
+    d.shift = shift;
+    d.inv_res = (float)(1.0 / res);
+    d.range_max = (float)h->cfg.range_max;
+    d.zmax = zmax;
+    d.x0 = x0;
+    d.y0 = y0;
+    d.inv_res_d = 1.0 / res;
+    h->have_dem = true;
+
+    // Keep the DEM resident in L2 across kernels where the part allows it (best effort).
+    int persist_max = 0, win_max = 0;
+    cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+    cudaDeviceGetAttribute(&win_max, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
+    if (persist_max > 0 && win_max > 0) {
+        size_t bytes = std::min(n * sizeof(float), (size_t)win_max);
+        size_t carve = std::min(bytes, (size_t)persist_max);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+        cudaStreamAttrValue at{};
+        at.accessPolicyWindow.base_ptr = h->dem_z;
+        at.accessPolicyWindow.num_bytes = bytes;
+        at.accessPolicyWindow.hitRatio = bytes ? (float)std::min(1.0, (double)carve / (double)bytes) : 0.f;
+        at.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &at);
+        cudaGetLastError();
+    }
+    return AUVPF_OK;
+}
+
+int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
+{
+    if (!h || !dirs_xyz || B <= 0 || B > 8192) return fail(AUVPF_ERR_BADARG, "bad beam table");
+    Guard g(h);
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(h->beams);
+    cudaFree(h->meas);
+    h->beams = h->meas = nullptr;
+    CU(cudaMalloc(&h->beams, sizeof(float) * 3 * B));
+    CU(cudaMalloc(&h->meas, sizeof(float) * (size_t)B * h->F));
+    CU(cudaMemcpyAsync(h->beams, dirs_xyz, sizeof(float) * 3 * B,
+                       is_device_ptr(dirs_xyz) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->B = B;
+    return AUVPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int auvpf_init_particles(auvpf_handle *h, const double mean[6], const double var[6], const float *noise)
+{
+    if (!h || !mean || !var) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    const float *nd = nullptr;
+    int rc;
+    if (noise && (rc = stage_in(h, S_IN0, noise, (size_t)h->N * 6, &nd))) return rc;
+    NoiseParams p = make_noise(h, var, mean, 2, 0, kStreamInit);
+    Prof pr(h, AUVPF_K_OTHER);
+    k_add_noise<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, p, nd);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+int auvpf_roughen(auvpf_handle *h, const double var[6], const float *noise)
+{
+    if (!h || !var) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    const float *nd = nullptr;
+    int rc;
+    if (noise && (rc = stage_in(h, S_IN0, noise, (size_t)h->N * 6, &nd))) return rc;
+    NoiseParams p = make_noise(h, var, nullptr, 1, h->step_rough++, kStreamRoughen);
+    Prof pr(h, AUVPF_K_ROUGHEN);
+    k_add_noise<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, p, nd);
+    LAUNCHED(h, AUVPF_K_ROUGHEN, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+int auvpf_set_poses(auvpf_handle *h, const double *poses)
+{
+    if (!h || !poses) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    const double *pd;
+    int rc = stage_in(h, S_IN0, poses, (size_t)h->N * 6, &pd);
+    if (rc) return rc;
+    k_set_poses<<<grid1(h->N, kThreads, 1), kThreads, 0, h->stream>>>(pd, h->N, h->st[h->cur]);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+int auvpf_get_poses(auvpf_handle *h, double *poses)
+{
+    if (!h || !poses) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    double *pd;
+    int rc = stage_out(h, S_OUT0, poses, (size_t)h->N * 6, &pd);
+    if (rc) return rc;
+    k_get_poses<<<grid1(h->N, kThreads, 1), kThreads, 0, h->stream>>>(h->st[h->cur], h->N, pd);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    return finish_out(h, poses, (const double *)pd, (size_t)h->N * 6);
+}
+
+int auvpf_get_logw(auvpf_handle *h, float *logw)
+{
+    if (!h || !logw) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    CU(cudaMemcpyAsync(logw, h->logw, sizeof(float) * h->N,
+                       is_device_ptr(logw) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
+int auvpf_set_logw(auvpf_handle *h, const float *logw)
+{
+    if (!h || !logw) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    CU(cudaMemcpyAsync(h->logw, logw, sizeof(float) * h->N,
+                       is_device_ptr(logw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    return AUVPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int auvpf_predict(auvpf_handle *h, const double *odom, int32_t n_odom, const float *noise)
+{
+    if (!h || !odom) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (n_odom != 1 && n_odom != h->F) return fail(AUVPF_ERR_BADARG, "n_odom must be 1 or n_filters");
+    if (is_device_ptr(odom)) return fail(AUVPF_ERR_BADARG, "odom must be host memory (11 scalars per filter)");
+    Guard g(h);
+    int rc;
+    const float *nd = nullptr;
+    if (noise && (rc = stage_in(h, S_IN0, noise, (size_t)h->N * 6, &nd))) return rc;
+    PredictParams p0 = make_predict(odom, h->cfg.motion_cov);
+    const PredictParams *pp = nullptr;
+    if (n_odom > 1) {
+        std::vector<PredictParams> all(h->F);
+        for (int f = 0; f < h->F; ++f) all[f] = make_predict(odom + 11 * f, h->cfg.motion_cov);
+        if ((rc = tiny_upload(h, h->pparams, all.data(), sizeof(PredictParams) * h->F))) return rc;
+        pp = h->pparams;
+    }
+    Prof pr(h, AUVPF_K_PROPAGATE);
+    k_propagate<<<grid1(h->M, kThreads * 4, h->F), kThreads, 0, h->stream>>>(
+        h->st[h->cur], h->M, p0, pp, h->cfg.seed, h->step_predict++, h->global_offset, h->global_count, nd);
+    LAUNCHED(h, AUVPF_K_PROPAGATE, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+int auvpf_update_gps(auvpf_handle *h, const double *gps_xy, float *logw_out)
+{
+    if (!h || !gps_xy) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    int rc;
+    if (is_device_ptr(gps_xy)) CU(cudaMemcpyAsync(h->gps, gps_xy, sizeof(double) * 2 * h->F, cudaMemcpyDeviceToDevice, h->stream));
+    else if ((rc = tiny_upload(h, h->gps, gps_xy, sizeof(double) * 2 * h->F))) return rc;
+    const double var = h->cfg.meas_std * h->cfg.meas_std;
+    {
+        Prof pr(h, AUVPF_K_UPDATE_GPS);
+        k_update_gps<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(
+            h->st[h->cur], h->M, h->frame, h->gps, (float)(0.5 / var), (float)(-std::log(2.0 * kPi * var)), h->logw);
+        LAUNCHED(h, AUVPF_K_UPDATE_GPS, 1);
+        CU(cudaGetLastError());
+    }
+    if (logw_out) return auvpf_get_logw(h, logw_out);
+    return AUVPF_OK;
+}
+
+int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
+{
+    if (!h || !ranges) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!h->have_dem || h->B <= 0) return fail(AUVPF_ERR_STATE, "update_mbes needs set_dem and set_beams first");
+    Guard g(h);
+    CU(cudaMemcpyAsync(h->meas, ranges, sizeof(float) * (size_t)h->B * h->F,
+                       is_device_ptr(ranges) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    const double var = h->cfg.meas_std * h->cfg.meas_std;
+    {
+        Prof pr(h, AUVPF_K_UPDATE_MBES);
+        const size_t smem = sizeof(float) * 4 * h->B;
+        k_update_mbes<<<grid1(h->M, kMbesWarps, h->F), kMbesWarps * 32, smem, h->stream>>>(
+            h->st[h->cur], h->M, h->frame, h->dem, h->beams, h->meas, h->B, (float)h->cfg.range_min,
+            (float)(-0.5 / var), (float)std::log(h->cfg.meas_std * std::sqrt(2.0 * kPi)), h->logw);
+        LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
+        CU(cudaGetLastError());
+    }
+    if (logw_out) return auvpf_get_logw(h, logw_out);
+    return AUVPF_OK;
+}
+
+int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges_out)
+{
+    if (!h || !poses || !ranges_out || n <= 0) return fail(AUVPF_ERR_BADARG, "bad argument");
+    if (!h->have_dem || h->B <= 0) return fail(AUVPF_ERR_STATE, "raycast needs set_dem and set_beams first");
+    Guard g(h);
+    const double *pd;
+    float *od;
+    int rc;
+    if ((rc = stage_in(h, S_IN0, poses, (size_t)n * 6, &pd))) return rc;
+    if ((rc = stage_out(h, S_OUT0, ranges_out, (size_t)n * h->B, &od))) return rc;
+    {
+        Prof pr(h, AUVPF_K_OTHER);
+        k_raycast_poses<<<grid1(n, kMbesWarps, 1), kMbesWarps * 32, 0, h->stream>>>(pd, n, h->frame, h->dem, h->beams,
+                                                                                   h->B, od);
+        LAUNCHED(h, AUVPF_K_OTHER, 1);
+        CU(cudaGetLastError());
+    }
+    return finish_out(h, ranges_out, (const float *)od, (size_t)n * h->B);
+}
+
+// ------------------------------------------------------------------------------------------------
+int auvpf_resample(auvpf_handle *h, int32_t mode, int32_t flags, const double *u, int32_t *ancestors_out,
+                   const double *rough_var, const float *rough_noise)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    WeightSrc src{h->logw, nullptr, 0};
+    return do_resample(h, src, mode, flags, u, ancestors_out, rough_var, rough_noise);
+}
+
+int auvpf_resample_weights(auvpf_handle *h, const double *weights, int32_t mode, int32_t flags, const double *u,
+                           int32_t *ancestors_out, const double *rough_var, const float *rough_noise)
+{
+    if (!h || !weights) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    const double *wd;
+    int rc = stage_in(h, S_IN2, weights, (size_t)h->N, &wd);
+    if (rc) return rc;
+    WeightSrc src{nullptr, wd, 1};
+    return do_resample(h, src, mode, flags, u, ancestors_out, rough_var, rough_noise);
+}
+
+int auvpf_get_weights_q(auvpf_handle *h, uint64_t *q)
+{
+    if (!h || !q) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!h->have_norm) return fail(AUVPF_ERR_STATE, "no normalisation available: call auvpf_resample first");
+    Guard g(h);
+    unsigned long long *qd;
+    int rc = stage_out(h, S_OUT0, reinterpret_cast<unsigned long long *>(q), (size_t)h->N, &qd);
+    if (rc) return rc;
+    WeightSrc src{h->logw, h->lin_weights, h->last_src_kind};
+    k_emit_q<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->A, h->deficit,
+                                                                     h->global_offset, qd);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    return finish_out(h, reinterpret_cast<unsigned long long *>(q), (const unsigned long long *)qd, (size_t)h->N);
+}
+
+int auvpf_apply_indices(auvpf_handle *h, const int32_t *indices, int32_t flags)
+{
+    if (!h || !indices) return fail(AUVPF_ERR_BADARG, "null argument");
+    (void)flags;
+    Guard g(h);
+    const int32_t *id = nullptr;
+    int rc = stage_in(h, S_IN0, indices, (size_t)h->N, &id);
+    if (rc) return rc;
+    return apply_indices_dev(h, id);
+}
+
+// ------------------------------------------------------------------------------------------------
+int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov)
+{
+    if (!h || !mean || !cov) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    std::vector<double> host(16 * h->F);
+    {
+        Prof pr(h, AUVPF_K_ESTIMATE);
+        k_zero_f64<<<(16 * h->F + 127) / 128, 128, 0, h->stream>>>(h->sums, 16 * h->F);
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 592);
+        k_pose_sums<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
+        k_pose_moments<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums, h->mom);
+        LAUNCHED(h, AUVPF_K_ESTIMATE, 3);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(host.data(), h->sums, sizeof(double) * 16 * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const double inv = 1.0 / (double)h->M;
+    for (int f = 0; f < h->F; ++f) {
+        const double *s = host.data() + 8 * f, *m = host.data() + 8 * h->F + 8 * f;
+        for (int c = 0; c < 5; ++c) mean[6 * f + c] = s[c] * inv;
+        mean[6 * f + 5] = s[6] * inv;   // mean of the wrapped yaws (auv_pf.py:229-231)
+        double *C = cov + 9 * f;
+        C[0] = m[0] * inv;
+        C[4] = m[1] * inv;
+        C[8] = m[2] * inv;
+        C[1] = m[3] * inv;
+        C[2] = m[4] * inv;
+        C[5] = m[5] * inv;
+        C[3] = C[1];          // only [1,0] is mirrored (auv_pf.py:246)
+        C[6] = 0.0;
+        C[7] = 0.0;
+    }
+    return AUVPF_OK;
+}
+
+int auvpf_neff(auvpf_handle *h, double *neff)
+{
+    if (!h || !neff) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!h->have_norm) return fail(AUVPF_ERR_STATE, "no normalisation available: call auvpf_resample first");
+    Guard g(h);
+    std::vector<double> s(h->F);
+    CU(cudaMemcpyAsync(s.data(), h->sumsq, sizeof(double) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < h->F; ++f) neff[f] = s[f] > 0.0 ? 1.0 / s[f] : 0.0;
+    return AUVPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU staging (particle-sharded single filter)
+int auvpf_shard_max(auvpf_handle *h, float *m_out)
+{
+    if (!h || !m_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    WeightSrc src{h->logw, nullptr, 0};
+    int rc = run_max(h, src);
+    if (rc) return rc;
+    std::vector<double> m(h->F);
+    CU(cudaMemcpyAsync(m.data(), h->wmax, sizeof(double) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < h->F; ++f) m_out[f] = (float)m[f];
+    return AUVPF_OK;
+}
+
+int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *limbs_out)
+{
+    if (!h || !m_global || !limbs_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    std::vector<double> m(h->F);
+    for (int f = 0; f < h->F; ++f) m[f] = (double)m_global[f];
+    int rc = tiny_upload(h, h->wmax, m.data(), sizeof(double) * h->F);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(h->limbs, 0, sizeof(unsigned long long) * 2 * h->F, h->stream));
+    CU(cudaMemsetAsync(h->sumsq, 0, sizeof(double) * h->F, h->stream));
+    WeightSrc src{h->logw, nullptr, 0};
+    if ((rc = run_sum(h, src))) return rc;
+    CU(cudaMemcpyAsync(limbs_out, h->limbs, sizeof(unsigned long long) * 2 * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
+int auvpf_shard_scan(auvpf_handle *h, const float *m_global, const uint64_t *A_global, uint64_t *Q_out)
+{
+    if (!h || !m_global || !A_global || !Q_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    int rc = tiny_upload(h, h->A, A_global, sizeof(unsigned long long) * 2 * h->F);
+    if (rc) return rc;
+    WeightSrc src{h->logw, nullptr, 0};
+    if ((rc = run_scan(h, src))) return rc;
+    h->have_norm = true;
+    h->last_src_kind = 0;
+    CU(cudaMemcpyAsync(Q_out, h->Q, sizeof(unsigned long long) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
+int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t deficit, int64_t out_lo, int64_t out_hi,
+                     void *records, int64_t *ancestors_out)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    if (h->F != 1) return fail(AUVPF_ERR_BADARG, "particle sharding is for a single filter (n_filters == 1)");
+    const int64_t n_out = out_hi - out_lo;
+    if (n_out < 0) return fail(AUVPF_ERR_BADARG, "out_hi < out_lo");
+    Guard g(h);
+    int rc;
+    unsigned long long d = deficit;
+    if ((rc = tiny_upload(h, h->deficit, &d, sizeof d))) return rc;
+    if ((rc = tiny_upload(h, h->u, &u, sizeof u))) return rc;
+    if (n_out == 0) return AUVPF_OK;
+    if (!records) return fail(AUVPF_ERR_BADARG, "null records");
+    Record *rd = nullptr;
+    int64_t *ad = nullptr;
+    if ((rc = stage_out(h, S_OUT0, static_cast<Record *>(records), (size_t)n_out, &rd))) return rc;
+    if (ancestors_out && (rc = stage_out(h, S_OUT1, ancestors_out, (size_t)n_out, &ad))) return rc;
+    SelectParams sp;
+    sp.M = h->M;
+    sp.n_global = h->global_count;
+    sp.j_global0 = h->global_offset;
+    sp.out_lo = out_lo;
+    sp.n_out = n_out;
+    sp.q_offset = q_offset;
+    NoiseParams none = make_noise(h, nullptr, nullptr, 0, 0, kStreamRoughen);
+    {
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        StateView nodst{};
+        k_select_gather<true><<<grid1(n_out, kSelTile, 1), kThreads, 0, h->stream>>>(
+            h->cdf, sp, h->u, h->deficit, h->st[h->cur], nodst, rd, nullptr, ad, none, nullptr);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+        CU(cudaGetLastError());
+    }
+    if ((rc = finish_out(h, static_cast<Record *>(records), (const Record *)rd, (size_t)n_out))) return rc;
+    if (ancestors_out && (rc = finish_out(h, ancestors_out, (const int64_t *)ad, (size_t)n_out))) return rc;
+    return AUVPF_OK;
+}
+
+int auvpf_shard_load(auvpf_handle *h, const void *records, int64_t n)
+{
+    if (!h || !records) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (n != h->N) return fail(AUVPF_ERR_BADARG, "expected %lld records, got %lld", (long long)h->N, (long long)n);
+    Guard g(h);
+    const Record *rd = nullptr;
+    int rc = stage_in(h, S_IN0, static_cast<const Record *>(records), (size_t)n, &rd);
+    if (rc) return rc;
+    k_load_records<<<grid1(n, kThreads, 1), kThreads, 0, h->stream>>>(rd, n, h->st[1 - h->cur]);
+    LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+    CU(cudaGetLastError());
+    h->cur = 1 - h->cur;
+    return AUVPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int auvpf_profile_enable(auvpf_handle *h, int32_t on)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    h->prof = on != 0;
+    return AUVPF_OK;
+}
+
+int auvpf_profile_read(auvpf_handle *h, double ms[AUVPF_K_COUNT], int64_t launches[AUVPF_K_COUNT], int32_t reset)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    CU(cudaStreamSynchronize(h->stream));
+    for (auto &e : h->prof_events) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) h->prof_ms[e.klass] += (double)t;
+        h->prof_pool.push_back(e);
+    }
+    h->prof_events.clear();
+    cudaGetLastError();
+    for (int k = 0; k < AUVPF_K_COUNT; ++k) {
+        if (ms) ms[k] = h->prof_ms[k];
+        if (launches) launches[k] = h->prof_launches[k];
+        if (reset) {
+            h->prof_ms[k] = 0.0;
+            h->prof_launches[k] = 0;
+        }
+    }
+    return AUVPF_OK;
+}
+
+}   // extern "C"

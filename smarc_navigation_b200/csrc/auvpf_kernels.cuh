@@ -1,0 +1,808 @@
+// auvpf_kernels.cuh -- sm_100a kernels of the particle-filter cycle.
+//
+// Layout in HBM: structure-of-arrays particle state,
+// x,y float64 (so a 2 km map keeps 1e-4 m), z,roll,pitch,yaw float32 = 32 B per
+// particle, double-buffered for the resampling gather; float32 log-weights;
+// uint64 integer CDF.  F filters x M particles, row f*M + i; grids are
+// (tiles over M, F) so no block straddles two filters.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "auvpf_math.cuh"
+
+namespace auvpf {
+
+struct StateView {
+    double *x, *y;
+    float *z, *roll, *pitch, *yaw;
+};
+
+struct Record {   // 32-byte exchange record of the multi-GPU ancestor exchange
+    double x, y;
+    float z, roll, pitch, yaw;
+};
+
+constexpr int kThreads = 256;
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int float_to_ordered(float f)
+{
+    int b = __float_as_int(f);
+    return b >= 0 ? b : b ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_to_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+__device__ __forceinline__ long long double_to_ordered(double d)
+{
+    long long b = __double_as_longlong(d);
+    return b >= 0 ? b : b ^ 0x7FFFFFFFFFFFFFFFll;
+}
+__device__ __forceinline__ double ordered_to_double(long long k)
+{
+    return __longlong_as_double(k >= 0 ? k : k ^ 0x7FFFFFFFFFFFFFFFll);
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// add_noise (auv_particle.py:32-36): pose = base + sigma * n.  `set_mean` != nullptr makes it the
+// particle initialiser (pose = mean + sigma n); otherwise roughening of the current state.
+struct NoiseParams {
+    float sigma[6];
+    double mean[6];
+    int mode;                // 0 = none, 1 = pose += sigma n, 2 = pose = mean + sigma n
+    uint64_t seed;
+    uint32_t step;
+    uint32_t stream;
+    int64_t global_offset;   // global id of local particle 0
+    int64_t global_stride;   // global particles per filter (ids: f * global_stride + global_offset + i)
+};
+
+__device__ __forceinline__ void six_normals(const NoiseParams &p, int64_t gid, const float *noise, int64_t row,
+                                            float n[6])
+{
+    if (noise) {
+#pragma unroll
+        for (int c = 0; c < 6; ++c) n[c] = __ldg(noise + row * 6 + c);
+    } else {
+        U4 r0 = philox_for(p.seed, gid, p.step, p.stream, 0);
+        U4 r1 = philox_for(p.seed, gid, p.step, p.stream, 1);
+        box_muller(r0.x, r0.y, n[0], n[1]);
+        box_muller(r0.z, r0.w, n[2], n[3]);
+        box_muller(r1.x, r1.y, n[4], n[5]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_add_noise(StateView s, int64_t M, NoiseParams p, const float *noise)
+{
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= M) return;
+    int f = blockIdx.y;
+    int64_t row = (int64_t)f * M + i;
+    int64_t gid = (int64_t)f * p.global_stride + p.global_offset + i;
+    float n[6];
+    six_normals(p, gid, noise, row, n);
+    if (p.mode == 2) {
+        s.x[row] = p.mean[0] + (double)(p.sigma[0] * n[0]);
+        s.y[row] = p.mean[1] + (double)(p.sigma[1] * n[1]);
+        s.z[row] = (float)p.mean[2] + p.sigma[2] * n[2];
+        s.roll[row] = (float)p.mean[3] + p.sigma[3] * n[3];
+        s.pitch[row] = (float)p.mean[4] + p.sigma[4] * n[4];
+        s.yaw[row] = (float)p.mean[5] + p.sigma[5] * n[5];
+    } else {
+        s.x[row] += (double)(p.sigma[0] * n[0]);
+        s.y[row] += (double)(p.sigma[1] * n[1]);
+        s.z[row] += p.sigma[2] * n[2];
+        s.roll[row] += p.sigma[3] * n[3];
+        s.pitch[row] += p.sigma[4] * n[4];
+        s.yaw[row] += p.sigma[5] * n[5];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Propagate (a2).  4 particles per thread, 128-bit loads/stores; HBM-bound:
+// reads x,y,yaw (20 B), writes x,y,z,roll,pitch,yaw (32 B) per particle.
+__device__ __forceinline__ void predict_normals(uint64_t seed, int64_t gid, uint32_t step, const float *noise,
+                                                int64_t row, float &n0, float &n1, float &n5)
+{
+    if (noise) {
+        n0 = __ldg(noise + row * 6 + 0);
+        n1 = __ldg(noise + row * 6 + 1);
+        n5 = __ldg(noise + row * 6 + 5);
+    } else {
+        U4 r = philox_for(seed, gid, step, kStreamPredict, 0);
+        float unused;
+        box_muller(r.x, r.y, n0, n1);
+        box_muller(r.z, r.w, n5, unused);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_propagate(StateView s, int64_t M, PredictParams p0, const PredictParams *params, uint64_t seed, uint32_t step, int64_t global_offset,
+            int64_t global_stride, const float *noise)
+{
+    const int f = blockIdx.y;
+    const PredictParams p = params ? params[f] : p0;   // one odom broadcast to all filters travels by value
+    const int64_t base = (int64_t)f * M;
+    const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (i0 >= M) return;
+    const int64_t gid0 = (int64_t)f * global_stride + global_offset + i0;
+    if (i0 + 3 < M && ((base + i0) & 3) == 0) {
+        double2 xa = *reinterpret_cast<const double2 *>(s.x + base + i0);
+        double2 xb = *reinterpret_cast<const double2 *>(s.x + base + i0 + 2);
+        double2 ya = *reinterpret_cast<const double2 *>(s.y + base + i0);
+        double2 yb = *reinterpret_cast<const double2 *>(s.y + base + i0 + 2);
+        float4 yw = *reinterpret_cast<const float4 *>(s.yaw + base + i0);
+        double x[4] = {xa.x, xa.y, xb.x, xb.y}, y[4] = {ya.x, ya.y, yb.x, yb.y};
+        float w[4] = {yw.x, yw.y, yw.z, yw.w};
+        float z, r, pt;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float n0, n1, n5;
+            predict_normals(seed, gid0 + k, step, noise, base + i0 + k, n0, n1, n5);
+            propagate_one(p, x[k], y[k], z, r, pt, w[k], n0, n1, n5);
+        }
+        *reinterpret_cast<double2 *>(s.x + base + i0) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2 *>(s.x + base + i0 + 2) = make_double2(x[2], x[3]);
+        *reinterpret_cast<double2 *>(s.y + base + i0) = make_double2(y[0], y[1]);
+        *reinterpret_cast<double2 *>(s.y + base + i0 + 2) = make_double2(y[2], y[3]);
+        *reinterpret_cast<float4 *>(s.yaw + base + i0) = make_float4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<float4 *>(s.z + base + i0) = make_float4(p.z, p.z, p.z, p.z);
+        *reinterpret_cast<float4 *>(s.roll + base + i0) = make_float4(p.roll, p.roll, p.roll, p.roll);
+        *reinterpret_cast<float4 *>(s.pitch + base + i0) = make_float4(p.pitch, p.pitch, p.pitch, p.pitch);
+    } else {
+        for (int k = 0; k < 4 && i0 + k < M; ++k) {
+            int64_t row = base + i0 + k;
+            double x = s.x[row], y = s.y[row];
+            float z, r, pt, w = s.yaw[row];
+            float n0, n1, n5;
+            predict_normals(seed, gid0 + k, step, noise, row, n0, n1, n5);
+            propagate_one(p, x, y, z, r, pt, w, n0, n1, n5);
+            s.x[row] = x;
+            s.y[row] = y;
+            s.z[row] = z;
+            s.roll[row] = r;
+            s.pitch[row] = pt;
+            s.yaw[row] = w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GPS update (a3, reference form): logw = -d^2 / (2 std^2) - log(2 pi std^2)
+__global__ void __launch_bounds__(kThreads)
+k_update_gps(StateView s, int64_t M, FrameParams fp, const double *gps_xy, float inv_2var, float lognorm,
+             float *logw)
+{
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= M) return;
+    int f = blockIdx.y;
+    int64_t row = (int64_t)f * M + i;
+    double x = s.x[row], y = s.y[row], z = (double)s.z[row];
+    double px, py;
+    if (fp.m2o_identity_r) {
+        px = x + fp.m2o_t[0];
+        py = y + fp.m2o_t[1];
+    } else {
+        px = fp.m2o_r[0] * x + fp.m2o_r[1] * y + fp.m2o_r[2] * z + fp.m2o_t[0];
+        py = fp.m2o_r[3] * x + fp.m2o_r[4] * y + fp.m2o_r[5] * z + fp.m2o_t[1];
+    }
+    double dx = gps_xy[2 * f] - px, dy = gps_xy[2 * f + 1] - py;
+    logw[row] = (float)(-(dx * dx + dy * dy) * (double)inv_2var + (double)lognorm);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused raycast + beam-range log-likelihood (a3 + a4).  One warp per particle, lanes over
+// beams, warp-shuffle reduction; beams (dir + measured range) staged in shared memory.
+// The DEM is read through the read-only path; at the benchmark configs the footprint of a
+// particle cloud is L1/L2 resident.
+constexpr int kMbesWarps = 8;
+
+__global__ void __launch_bounds__(kMbesWarps * 32)
+k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, const float *__restrict__ beam_dirs,
+              const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,
+              float log_norm_per_beam, float *__restrict__ logw)
+{
+    extern __shared__ float sm[];   // [4*B]: dx, dy, dz, measured range (NaN = skip)
+    __shared__ int s_valid;
+    const int f = blockIdx.y;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    int nv = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        sm[b] = beam_dirs[3 * b];
+        sm[B + b] = beam_dirs[3 * b + 1];
+        sm[2 * B + b] = beam_dirs[3 * b + 2];
+        float r = meas[(size_t)f * B + b];
+        bool ok = isfinite(r) && r >= range_min && r <= dem.range_max;
+        sm[3 * B + b] = ok ? r : __int_as_float(0x7fc00000);
+        nv += ok ? 1 : 0;
+    }
+    if (nv) atomicAdd(&s_valid, nv);
+    __syncthreads();
+    const float lognorm = -(float)s_valid * log_norm_per_beam;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * kMbesWarps + warp;
+    if (i >= M) return;
+    const int64_t row = (int64_t)f * M + i;
+    double p[3];
+    double R[9];
+    particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
+    int ix0, iy0;
+    float lx0, ly0;
+    origin_cell(dem, p, ix0, iy0, lx0, ly0);
+    float acc = 0.f;
+    for (int b = lane; b < B; b += 32) {
+        float rm = sm[3 * B + b];
+        if (rm != rm) continue;     // invalid measured beam: skipped, no raycast needed
+        Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, sm[b], sm[B + b], sm[2 * B + b]);
+        float e = rm - raycast_one(dem, ray);
+        acc = fmaf(e, e, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) logw[row] = fmaf(neg_half_inv_var, acc, lognorm);
+}
+
+// Parity probe: expected ranges for explicit poses, (n, B) float32.
+__global__ void __launch_bounds__(kMbesWarps * 32)
+k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, DemView dem,
+                const float *__restrict__ beam_dirs, int B, float *__restrict__ out)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * kMbesWarps + warp;
+    if (i >= n) return;
+    const double *ps = poses + 6 * i;
+    double p[3];
+    double R[9];
+    particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
+    int ix0, iy0;
+    float lx0, ly0;
+    origin_cell(dem, p, ix0, iy0, lx0, ly0);
+    for (int b = lane; b < B; b += 32) {
+        Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, beam_dirs[3 * b], beam_dirs[3 * b + 1], beam_dirs[3 * b + 2]);
+        out[(size_t)i * B + b] = raycast_one(dem, ray);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Max-mip pyramid.  Level 1 block (bi,bj) = max over vertices [2bi, 2bi+2] x [2bj, 2bj+2] (closed
+// footprint of a 2x2-cell block); level L+1 = max of 2x2 children.
+__global__ void k_mip_level1(const float *z, int H, int W, float *out, int oH, int oW)
+{
+    int bj = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y * blockDim.y + threadIdx.y;
+    if (bj >= oW || bi >= oH) return;
+    float m = -INFINITY;
+    for (int di = 0; di <= 2; ++di)
+        for (int dj = 0; dj <= 2; ++dj) {
+            int i = min(2 * bi + di, H - 1), j = min(2 * bj + dj, W - 1);
+            m = fmaxf(m, z[(size_t)i * W + j]);
+        }
+    out[(size_t)bi * oW + bj] = m;
+}
+
+__global__ void k_mip_down(const float *in, int iH, int iW, float *out, int oH, int oW)
+{
+    int bj = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y * blockDim.y + threadIdx.y;
+    if (bj >= oW || bi >= oH) return;
+    float m = -INFINITY;
+    for (int di = 0; di < 2; ++di)
+        for (int dj = 0; dj < 2; ++dj) {
+            int i = 2 * bi + di, j = 2 * bj + dj;
+            if (i < iH && j < iW) m = fmaxf(m, in[(size_t)i * iW + j]);
+        }
+    out[(size_t)bi * oW + bj] = m;
+}
+
+__global__ void k_max_f32(const float *in, int64_t n, int *out_ordered)
+{
+    float m = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, in[i]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out_ordered, float_to_ordered(m));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Normalisation, stage 1: per-filter maximum of the weight source.
+//   kind 0: float32 log-weights  -> wmax[f] = max logw (as double, ordered-int atomics)
+//   kind 1: float64 linear weights (the reference's resample(weights) argument)
+struct WeightSrc {
+    const float *logw;
+    const double *lin;
+    int kind;
+};
+
+__device__ __forceinline__ double src_value(const WeightSrc &w, int64_t row)
+{
+    return w.kind == 0 ? (double)w.logw[row] : w.lin[row];
+}
+
+__global__ void __launch_bounds__(kThreads) k_weight_max(WeightSrc w, int64_t M, long long *wmax_ordered)
+{
+    const int f = blockIdx.y;
+    double m = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        double v = src_value(w, (int64_t)f * M + i);
+        if (v == v) m = fmax(m, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(wmax_ordered + f, double_to_ordered(m));
+}
+
+__device__ __forceinline__ uint64_t src_a(const WeightSrc &w, int64_t row, double wmax)
+{
+    return w.kind == 0 ? a_from_logw(w.logw[row], (float)wmax) : a_from_linear(w.lin[row], wmax);
+}
+
+// stage 2: A = sum_i a_i exactly, as two limb sums (low 32 bits, high bits) per filter
+__global__ void __launch_bounds__(kThreads)
+k_weight_sum(WeightSrc w, int64_t M, const double *wmax, unsigned long long *limbs)
+{
+    const int f = blockIdx.y;
+    const double m = wmax[f];
+    unsigned long long lo = 0, hi = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        uint64_t a = src_a(w, (int64_t)f * M + i, m);
+        lo += a & 0xFFFFFFFFull;
+        hi += a >> 32;
+    }
+    lo = warp_sum_u64(lo);
+    hi = warp_sum_u64(hi);
+    __shared__ unsigned long long slo[kThreads / 32], shi[kThreads / 32];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        slo[warp] = lo;
+        shi[warp] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kThreads / 32; ++k) {
+            lo += slo[k];
+            hi += shi[k];
+        }
+        atomicAdd(limbs + 2 * f, lo);
+        atomicAdd(limbs + 2 * f + 1, hi);
+    }
+}
+
+// limbs -> 128-bit A as (lo64, hi64)
+__global__ void k_combine_limbs(const unsigned long long *limbs, unsigned long long *A, int F)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    unsigned __int128 a = (unsigned __int128)limbs[2 * f] + ((unsigned __int128)limbs[2 * f + 1] << 32);
+    A[2 * f] = (unsigned long long)a;
+    A[2 * f + 1] = (unsigned long long)(a >> 64);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-pass decoupled-lookback inclusive scan (Merrill & Garland) of uint64 values.
+// One 64-bit status word per tile: [63:62] flag (1 = tile aggregate, 2 = inclusive prefix),
+// [61:0] value, so value and flag travel in one store and no fence is needed.
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kThreads * kScanItems;
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (1ull << 62) - 1;
+
+template <class ValueFn>
+__device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigned long long *__restrict__ out,
+                                               volatile unsigned long long *status, unsigned int *tile_counter,
+                                               int tiles_per_filter, unsigned long long *totals,
+                                               double *sumsq /* optional: sum of (v 2^-52)^2 */)
+{
+    __shared__ unsigned int s_tile;
+    __shared__ unsigned long long s_warp[kThreads / 32];
+    __shared__ unsigned long long s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const unsigned int gtile = s_tile;
+    const int f = gtile / tiles_per_filter, tile = gtile % tiles_per_filter;
+    const int64_t base = (int64_t)f * M;
+    const int64_t i0 = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+
+    unsigned long long v[kScanItems];
+    unsigned long long tsum = 0;
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (i0 + k < M) ? value(base + i0 + k, f) : 0ull;
+        tsum += v[k];
+        if (sumsq) {
+            double w = (double)v[k] * 2.220446049250313e-16;
+            sq += w * w;
+        }
+    }
+    // block exclusive scan of per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long warp_off = 0, block_total = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) {
+        unsigned long long wv = s_warp[k];
+        if (k < warp) warp_off += wv;
+        block_total += wv;
+    }
+    unsigned long long excl = warp_off + incl - tsum;
+
+    // publish aggregate / look back (warp 0)
+    if (warp == 0) {
+        volatile unsigned long long *st = status + (size_t)f * tiles_per_filter;
+        if (tile == 0) {
+            if (lane == 0) {
+                st[0] = kFlagPrefix | block_total;
+                s_prefix = 0;
+            }
+        } else {
+            if (lane == 0) st[tile] = kFlagAgg | block_total;
+            unsigned long long run = 0;
+            int idx = tile - 1;
+            while (true) {
+                int j = idx - lane;
+                unsigned long long wd = kFlagPrefix;      // before the filter's first tile: prefix 0
+                if (j >= 0) {
+                    do {
+                        wd = st[j];
+                    } while ((wd >> 62) == 0);
+                }
+                unsigned pm = __ballot_sync(0xffffffffu, (wd >> 62) == 2);
+                unsigned long long val = wd & kValMask;
+                if (pm) {
+                    int L = __ffs(pm) - 1;                 // nearest tile that already has a prefix
+                    unsigned long long c = lane <= L ? val : 0ull;
+                    run += warp_sum_u64(c);
+                    break;
+                }
+                run += warp_sum_u64(val);
+                idx -= 32;
+            }
+            if (lane == 0) {
+                st[tile] = kFlagPrefix | (run + block_total);
+                s_prefix = run;
+            }
+        }
+    }
+    __syncthreads();
+    unsigned long long acc = s_prefix + excl;
+    if (totals && threadIdx.x == 0 && tile == tiles_per_filter - 1) totals[f] = s_prefix + block_total;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        acc += v[k];
+        if (i0 + k < M) out[base + i0 + k] = acc;
+    }
+    if (sumsq) {
+        sq = warp_sum_f64(sq);
+        if (lane == 0) atomicAdd(sumsq + f, sq);
+    }
+}
+
+// stage 3: q_i = floor(a_i 2^52 / A); inclusive integer CDF (raw: before the deficit units)
+__global__ void __launch_bounds__(kThreads)
+k_scan_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A, unsigned long long *cdf,
+         unsigned long long *status, unsigned int *tile_counter, int tiles_per_filter, unsigned long long *Q,
+         double *sumsq)
+{
+    auto value = [&](int64_t row, int f) -> unsigned long long {
+        return q_from_a(src_a(w, row, wmax[f]), A[2 * f], A[2 * f + 1]);
+    };
+    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq);
+}
+
+// q_i itself (parity read-back): q_i + (i_global < D)
+__global__ void __launch_bounds__(kThreads)
+k_emit_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A, const unsigned long long *deficit,
+         int64_t global_offset, unsigned long long *q_out)
+{
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= M) return;
+    int f = blockIdx.y;
+    int64_t row = (int64_t)f * M + i;
+    unsigned long long q = q_from_a(src_a(w, row, wmax[f]), A[2 * f], A[2 * f + 1]);
+    q_out[row] = q + (((unsigned long long)(global_offset + i) < deficit[f]) ? 1ull : 0ull);
+}
+
+__global__ void k_deficit(const unsigned long long *Q, unsigned long long *deficit, int F)
+{
+    int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < F) deficit[f] = (1ull << kQBits) - Q[f];
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage 4: systematic ancestor select (a7) + particle gather (a8, sorted form) + roughening (a9).
+// Output slot i (global) finds the first particle j with positions[i] < cdf[j]
+// (resampling.py:161-167).  A block owns kSelTile consecutive outputs; their ancestors form a
+// contiguous CDF interval that is staged in shared memory and searched there.
+constexpr int kSelItems = 4;
+constexpr int kSelTile = kThreads * kSelItems;
+constexpr int kSelSpan = 3072;   // CDF entries staged per block (24 KB)
+
+struct SelectParams {
+    int64_t M;             // local particles per filter (CDF length)
+    int64_t n_global;      // N of positions = (u + i) / N
+    int64_t j_global0;     // global id of local particle 0
+    int64_t out_lo;        // first global output slot emitted by this launch
+    int64_t n_out;         // outputs per filter emitted by this launch
+    unsigned long long q_offset;   // integer CDF mass of lower shards
+};
+
+__device__ __forceinline__ double full_cdf(const unsigned long long *cdf, int64_t j, const SelectParams &p,
+                                           unsigned long long D)
+{
+    unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
+    return cdf_value(p.q_offset + cdf[j] + (jg1 < D ? jg1 : D));
+}
+
+// first j in [lo, hi) with pos < cdf(j); hi if none
+__device__ __forceinline__ int64_t search_cdf(const unsigned long long *cdf, int64_t lo, int64_t hi, double pos,
+                                              const SelectParams &p, unsigned long long D)
+{
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (pos < full_cdf(cdf, mid, p, D)) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+template <bool kRecords>
+__global__ void __launch_bounds__(kThreads)
+k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, const double *__restrict__ u_all,
+                const unsigned long long *__restrict__ deficit, StateView src, StateView dst, Record *records,
+                int32_t *anc32, int64_t *anc64, NoiseParams rough, const float *rough_noise)
+{
+    __shared__ double s_cdf[kSelSpan];
+    __shared__ int64_t s_j[2];
+    const int f = blockIdx.y;
+    const unsigned long long *cdf = cdf_all + (size_t)f * p.M;
+    const unsigned long long D = deficit[f];
+    const double u = u_all[f], n = (double)p.n_global;
+    const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
+    if (k0 >= p.n_out) return;
+    const int64_t k1 = min(k0 + (int64_t)kSelTile, p.n_out) - 1;
+    if (threadIdx.x == 0) s_j[0] = search_cdf(cdf, 0, p.M, sys_position(u, p.out_lo + k0, n), p, D);
+    if (threadIdx.x == 32) s_j[1] = search_cdf(cdf, 0, p.M, sys_position(u, p.out_lo + k1, n), p, D);
+    __syncthreads();
+    const int64_t j_lo = min(s_j[0], p.M - 1), j_hi = min(s_j[1], p.M - 1);
+    const int64_t span = j_hi - j_lo + 1;
+    const bool staged = span <= kSelSpan;
+    if (staged)
+        for (int64_t t = threadIdx.x; t < span; t += kThreads) s_cdf[t] = full_cdf(cdf, j_lo + t, p, D);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSelItems; ++r) {
+        const int64_t k = k0 + threadIdx.x + (int64_t)r * kThreads;
+        if (k > k1) break;
+        const int64_t i = p.out_lo + k;
+        const double pos = sys_position(u, i, n);
+        int64_t j;
+        if (staged) {
+            int lo = 0, hi = (int)span;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (pos < s_cdf[mid]) hi = mid;
+                else lo = mid + 1;
+            }
+            j = j_lo + lo;
+        } else {
+            j = search_cdf(cdf, j_lo, j_hi + 1, pos, p, D);
+        }
+        j = min(j, p.M - 1);            // reference would run off the end (IndexError); clamp
+        const int64_t srow = (int64_t)f * p.M + j;
+        const int64_t orow = (int64_t)f * p.n_out + k;
+        double x = src.x[srow], y = src.y[srow];
+        float z = src.z[srow], ro = src.roll[srow], pi = src.pitch[srow], ya = src.yaw[srow];
+        if (anc32) anc32[orow] = (int32_t)j;
+        if (anc64) anc64[orow] = p.j_global0 + j;
+        if (kRecords) {
+            Record rec = {x, y, z, ro, pi, ya};
+            records[orow] = rec;
+        } else if (dst.x != nullptr) {
+            if (rough.mode == 1) {       // fused add_noise (auv_pf.py:191-192)
+                float nn[6];
+                six_normals(rough, (int64_t)f * rough.global_stride + i, rough_noise, orow, nn);
+                x += (double)(rough.sigma[0] * nn[0]);
+                y += (double)(rough.sigma[1] * nn[1]);
+                z += rough.sigma[2] * nn[2];
+                ro += rough.sigma[3] * nn[3];
+                pi += rough.sigma[4] * nn[4];
+                ya += rough.sigma[5] * nn[5];
+            }
+            dst.x[orow] = x;
+            dst.y[orow] = y;
+            dst.z[orow] = z;
+            dst.roll[orow] = ro;
+            dst.pitch[orow] = pi;
+            dst.yaw[orow] = ya;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_load_records(const Record *__restrict__ rec, int64_t n, StateView dst)
+{
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    Record r = rec[i];
+    dst.x[i] = r.x;
+    dst.y[i] = r.y;
+    dst.z[i] = r.z;
+    dst.roll[i] = r.roll;
+    dst.pitch[i] = r.pitch;
+    dst.yaw[i] = r.yaw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference in-place slot map (a8): auv_pf.py:183-189 keep/lost/dupes + reassign_poses :195-198.
+constexpr int kNoFirst = 0x7f7f7f7f;
+
+__global__ void __launch_bounds__(kThreads) k_first_occurrence(const int32_t *idx, int64_t M, int *first)
+{
+    int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= M) return;
+    int64_t base = (int64_t)blockIdx.y * M;
+    int j = idx[base + k];
+    if (j >= 0 && j < M) atomicMin(first + base + j, (int)k);
+}
+
+// scans of the "lost" flag over slots j and of the "dupe" flag over draws k
+__global__ void __launch_bounds__(kThreads)
+k_scan_lost(const int *first, int64_t M, unsigned long long *out, unsigned long long *status,
+            unsigned int *tile_counter, int tiles_per_filter, unsigned long long *totals)
+{
+    auto value = [&](int64_t row, int) -> unsigned long long { return first[row] == kNoFirst ? 1ull : 0ull; };
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_scan_dupes(const int *first, const int32_t *idx, int64_t M, unsigned long long *out, unsigned long long *status,
+             unsigned int *tile_counter, int tiles_per_filter, unsigned long long *totals)
+{
+    auto value = [&](int64_t row, int f) -> unsigned long long {
+        int64_t base = (int64_t)f * M;
+        int j = idx[row];
+        return first[base + j] != (int)(row - base) ? 1ull : 0ull;
+    };
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_compact_lost_dupes(const int *first, const int32_t *idx, int64_t M, const unsigned long long *scan_lost,
+                     const unsigned long long *scan_dupes, int32_t *lost, int32_t *dupes)
+{
+    int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= M) return;
+    int64_t base = (int64_t)blockIdx.y * M, row = base + k;
+    if (first[row] == kNoFirst) lost[base + scan_lost[row] - 1] = (int32_t)k;
+    int j = idx[row];
+    if (first[base + j] != (int)k) dupes[base + scan_dupes[row] - 1] = j;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_reassign(StateView s, int64_t M, const int32_t *lost, const int32_t *dupes, const unsigned long long *n_lost,
+           const unsigned long long *n_dupes)
+{
+    int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    int f = blockIdx.y;
+    unsigned long long n = n_lost[f] < n_dupes[f] ? n_lost[f] : n_dupes[f];
+    if (r >= (int64_t)n) return;
+    int64_t base = (int64_t)f * M;
+    int64_t d = base + lost[base + r], sidx = base + dupes[base + r];
+    s.x[d] = s.x[sidx];
+    s.y[d] = s.y[sidx];
+    s.z[d] = s.z[sidx];
+    s.roll[d] = s.roll[sidx];
+    s.pitch[d] = s.pitch[sidx];
+    s.yaw[d] = s.yaw[sidx];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Estimate (a10): auv_pf.update_loc_pose (auv_pf.py:218-252).  Pass 1: sums of the six pose
+// components with yaw wrapped (:229-231); pass 2: centred second moments of x,y,z.
+__device__ __forceinline__ double wrap_pi_d(double a)
+{
+    double t = fmod(a + kPi, 2.0 * kPi);
+    if (t < 0.0) t += 2.0 * kPi;
+    return t - kPi;
+}
+
+__global__ void __launch_bounds__(kThreads) k_pose_sums(StateView s, int64_t M, double *sums /* F x 8 */)
+{
+    const int f = blockIdx.y;
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        int64_t row = (int64_t)f * M + i;
+        a[0] += s.x[row];
+        a[1] += s.y[row];
+        a[2] += (double)s.z[row];
+        a[3] += (double)s.roll[row];
+        a[4] += (double)s.pitch[row];
+        double yw = (double)s.yaw[row];
+        a[5] += yw;
+        a[6] += wrap_pi_d(yw);
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        double v = warp_sum_f64(a[c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(sums + 8 * f + c, v);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_pose_moments(StateView s, int64_t M, const double *sums, double *mom /* F x 8: xx yy zz xy xz yz */)
+{
+    const int f = blockIdx.y;
+    const double inv = 1.0 / (double)M;
+    const double mx = sums[8 * f] * inv, my = sums[8 * f + 1] * inv, mz = sums[8 * f + 2] * inv;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        int64_t row = (int64_t)f * M + i;
+        double dx = s.x[row] - mx, dy = s.y[row] - my, dz = (double)s.z[row] - mz;
+        a[0] += dx * dx;
+        a[1] += dy * dy;
+        a[2] += dz * dz;
+        a[3] += dx * dy;
+        a[4] += dx * dz;
+        a[5] += dy * dz;
+    }
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        double v = warp_sum_f64(a[c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(mom + 8 * f + c, v);
+    }
+}
+
+// pack / unpack between the ABI's (n,6) float64 rows and the SoA state
+__global__ void __launch_bounds__(kThreads) k_set_poses(const double *poses, int64_t n, StateView s)
+{
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    const double *p = poses + 6 * i;
+    s.x[i] = p[0];
+    s.y[i] = p[1];
+    s.z[i] = (float)p[2];
+    s.roll[i] = (float)p[3];
+    s.pitch[i] = (float)p[4];
+    s.yaw[i] = (float)p[5];
+}
+
+__global__ void __launch_bounds__(kThreads) k_get_poses(StateView s, int64_t n, double *poses)
+{
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    double *p = poses + 6 * i;
+    p[0] = s.x[i];
+    p[1] = s.y[i];
+    p[2] = (double)s.z[i];
+    p[3] = (double)s.roll[i];
+    p[4] = (double)s.pitch[i];
+    p[5] = (double)s.yaw[i];
+}
+
+}   // namespace auvpf

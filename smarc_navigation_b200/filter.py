@@ -1,0 +1,321 @@
+"""Python facade: the reference filter API over the CUDA library.
+
+Mirrors ``auv_particle_filter/scripts/auv_pf.py`` (class ``auv_pf``): the same
+constructor parameters (the ROS params of ``auv_pf.py:27-56`` /
+``auv_pf.launch:15-20``, same names, same "list of VARIANCES in
+[x, y, z, roll, pitch, yaw] order" meaning, covariance strings accepted) and the
+same three methods ``predict(odom_t)``, ``update(meas) -> weights``,
+``resample(weights)``, plus ``update_loc_pose``'s numbers (``mean_cov``).  A ROS
+node keeps its callbacks and swaps the object.
+
+All arithmetic happens in ``libauvpf.so`` on the GPU; this file only marshals
+arguments.  There is no CPU path.
+"""
+import ctypes as C
+import math
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_TWO_PI = 2.0 * math.pi
+
+
+def parse_covariance(value):
+    """The reference's covariance parameters arrive as strings like
+    ``"[0.1, 0.1, 0.0, 0.0, 0.0, 0.0]"`` (auv_pf.py:40-56); lists pass through."""
+    if isinstance(value, str):
+        value = value.replace('[', '').replace(']', '')
+        value = list(map(float, value.split(",")))
+    v = [float(x) for x in value]
+    if len(v) != 6:
+        raise ValueError("covariance must have 6 entries [x, y, z, roll, pitch, yaw]")
+    return v
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _odom_row(odom_t, dt):
+    """Accept a ROS ``nav_msgs/Odometry``-shaped object (the attributes
+    ``Particle.motion_pred`` reads, auv_particle.py:43-70) or a plain object /
+    tuple ``(v[3], wz, quat_xyzw[4], z)``."""
+    if hasattr(odom_t, "twist"):
+        tw, po = odom_t.twist.twist, odom_t.pose.pose
+        return [tw.linear.x, tw.linear.y, tw.linear.z, tw.angular.z, po.orientation.x, po.orientation.y,
+                po.orientation.z, po.orientation.w, po.position.z, dt, 0.0]
+    if hasattr(odom_t, "v"):
+        v, wz, q, z = odom_t.v, odom_t.wz, odom_t.quat, odom_t.z
+        if dt is None:
+            dt = odom_t.dt
+    else:
+        v, wz, q, z = odom_t
+    return [v[0], v[1], v[2], wz, q[0], q[1], q[2], q[3], z, dt, 0.0]
+
+
+class ParticleFilter(object):
+    """Drop-in for the filter half of ``auv_pf`` (auv_pf.py:23-260).
+
+    Parameters (reference names, auv_pf.py:27-56): ``particle_count``,
+    ``init_covariance``, ``motion_covariance``, ``resampling_noise_covariance``,
+    ``measurement_std``, ``m2o_matrix`` (4x4 map<-odom, auv_pf.py:79-81).
+    GPU-side additions: ``n_filters``, ``seed``, ``device``, ``range_min``,
+    ``range_max``, ``resampler`` ("systematic"), ``inplace_reference`` (keep the
+    reference's survivors-stay-in-slot map, auv_pf.py:183-198).
+    """
+
+    def __init__(self, particle_count=10, init_covariance=(0.,) * 6, motion_covariance=(0.,) * 6,
+                 resampling_noise_covariance=(0.,) * 6, measurement_std=0.01, m2o_matrix=None,
+                 n_filters=1, seed=0, device=0, range_min=0.0, range_max=120.0, coarse_level=-1,
+                 resampler="systematic", inplace_reference=False, init_mean=None, init_noise=None,
+                 global_offset=0, global_count=0):
+        self._lib = _lib.load()
+        self.pc = int(particle_count)
+        self.n_filters = int(n_filters)
+        self.init_cov = parse_covariance(init_covariance)
+        self.motion_cov = parse_covariance(motion_covariance)
+        self.res_noise_cov = parse_covariance(resampling_noise_covariance)
+        self.meas_std = float(measurement_std)
+        self.m2o_mat = np.identity(4) if m2o_matrix is None else np.asarray(m2o_matrix, np.float64).reshape(4, 4)
+        self.resampler = {"systematic": _lib.SYSTEMATIC, "residual": _lib.RESIDUAL}[resampler]
+        self.inplace_reference = bool(inplace_reference)
+        self._lock = threading.Lock()      # the reference's callbacks race on self.particles
+        self.time = None
+        self.old_time = None
+        cfg = _lib.Config()
+        cfg.struct_size = C.sizeof(_lib.Config)
+        cfg.device = int(device)
+        cfg.particle_count = self.pc
+        cfg.n_filters = self.n_filters
+        cfg.coarse_level = int(coarse_level)
+        cfg.global_offset = int(global_offset)
+        cfg.global_count = int(global_count)
+        cfg.motion_cov[:] = self.motion_cov
+        cfg.meas_std = self.meas_std
+        cfg.m2o[:] = self.m2o_mat.reshape(16).tolist()
+        cfg.seed = int(seed)
+        cfg.range_min = float(range_min)
+        cfg.range_max = float(range_max)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.auvpf_create(C.byref(cfg), C.byref(self._h)))
+        self.n_rows = self.pc * self.n_filters
+        self.n_beams = 0
+        # Particle.__init__: zero pose + add_noise(init_cov) (auv_particle.py:24,30)
+        mean = np.zeros(6) if init_mean is None else np.asarray(init_mean, np.float64)
+        self.init_particles(mean, self.init_cov, init_noise)
+
+    # -- lifecycle -----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.auvpf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _lib.check(self._lib.auvpf_sync(self._h))
+
+    @property
+    def stream_ptr(self):
+        return self._lib.auvpf_stream(self._h)
+
+    # -- map / sensor --------------------------------------------------------------------
+    def set_dem(self, z, x0=0.0, y0=0.0, res=1.0):
+        if isinstance(z, dict):
+            z, x0, y0, res = z["z"], z["x0"], z["y0"], z["res"]
+        z = np.ascontiguousarray(z, np.float32)
+        with self._lock:
+            _lib.check(self._lib.auvpf_set_dem(self._h, _ptr(z), z.shape[0], z.shape[1], x0, y0, res))
+
+    def set_beams(self, dirs_xyz):
+        d = np.ascontiguousarray(dirs_xyz, np.float32).reshape(-1, 3)
+        with self._lock:
+            _lib.check(self._lib.auvpf_set_beams(self._h, _ptr(d), d.shape[0]))
+        self.n_beams = d.shape[0]
+
+    def set_scan_geometry(self, angle_min, angle_increment, n):
+        """Beam table of a ``sensor_msgs/LaserScan``-style fan in the sensor y-z plane
+        (the only MBES wire format in the reference,
+        mbes_processors/mbes_mapper/include/mbes_mapper/mbes_receptor.hpp:26,82)."""
+        th = angle_min + angle_increment * np.arange(n)
+        self.set_beams(np.stack([np.zeros(n), np.sin(th), -np.cos(th)], -1))
+
+    # -- state ---------------------------------------------------------------------------
+    def init_particles(self, mean, var, noise=None):
+        m = (C.c_double * 6)(*[float(x) for x in mean])
+        v = (C.c_double * 6)(*parse_covariance(var))
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(self.n_rows, 6)
+        with self._lock:
+            _lib.check(self._lib.auvpf_init_particles(self._h, m, v, _ptr(nz)))
+
+    def poses(self):
+        """(F*M, 6) float64 ``[x, y, z, roll, pitch, yaw]`` = every ``particles[i].p_pose``."""
+        out = np.empty((self.n_rows, 6), np.float64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_get_poses(self._h, _ptr(out)))
+        return out
+
+    def set_poses(self, poses):
+        p = np.ascontiguousarray(poses, np.float64).reshape(self.n_rows, 6)
+        with self._lock:
+            _lib.check(self._lib.auvpf_set_poses(self._h, _ptr(p)))
+
+    def log_weights(self):
+        out = np.empty(self.n_rows, np.float32)
+        with self._lock:
+            _lib.check(self._lib.auvpf_get_logw(self._h, _ptr(out)))
+        return out
+
+    def set_log_weights(self, logw):
+        lw = np.ascontiguousarray(logw, np.float32).reshape(self.n_rows)
+        with self._lock:
+            _lib.check(self._lib.auvpf_set_logw(self._h, _ptr(lw)))
+            _lib.check(self._lib.auvpf_sync(self._h))
+
+    # -- predict: auv_pf.predict (auv_pf.py:213-216) -----------------------------------------
+    def predict(self, odom_t, dt=None, noise=None):
+        """``dt`` defaults to ``self.time - self.old_time`` like the reference
+        (:214) when the caller maintains those, else must be given (or carried by
+        the odom object).  ``odom_t`` may be a list of F odoms (one per filter)."""
+        if dt is None and self.time is not None and self.old_time is not None:
+            dt = self.time - self.old_time
+        many = isinstance(odom_t, (list, tuple)) and len(odom_t) == self.n_filters and self.n_filters > 1 \
+            and not np.isscalar(odom_t[1])
+        rows = [_odom_row(o, dt) for o in odom_t] if many else [_odom_row(odom_t, dt)]
+        if any(r[9] is None for r in rows):
+            raise ValueError("predict needs dt")
+        od = np.ascontiguousarray(rows, np.float64)
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(self.n_rows, 6)
+        with self._lock:
+            _lib.check(self._lib.auvpf_predict(self._h, _ptr(od), od.shape[0], _ptr(nz)))
+
+    # -- update: auv_pf.update (auv_pf.py:135-167) -------------------------------------------
+    def update(self, meas, return_weights=True):
+        """GPS form (what the reference does): ``meas`` is a ROS Odometry-shaped GPS
+        fix (``pose.pose.position.{x,y}``, already in the map frame -- the
+        utm->map ``transformPoint`` of :151 stays in the node) or an ``(x, y)``
+        pair.  MBES form: ``meas`` is an array of B ranges (or (F, B)), or a
+        LaserScan-shaped object with ``.ranges``.  Returns the reference's
+        ``weights`` array (linear float64, ``+ 1e-200``, :165) unless
+        ``return_weights=False`` (weights stay on the GPU for ``resample()``)."""
+        if hasattr(meas, "ranges"):
+            return self.update_mbes(np.asarray(meas.ranges, np.float32), return_weights)
+        if hasattr(meas, "pose"):
+            p = meas.pose.pose.position
+            return self.update_gps((p.x, p.y), return_weights)
+        a = np.asarray(meas)
+        if a.size == 2 * self.n_filters and self.n_beams != 2 * self.n_filters:
+            return self.update_gps(a, return_weights)
+        return self.update_mbes(a, return_weights)
+
+    def _weights_out(self, logw):
+        return np.exp(logw.astype(np.float64)) + 1.0e-200          # auv_pf.py:165
+
+    def update_gps(self, gps_xy, return_weights=True):
+        g = np.ascontiguousarray(np.broadcast_to(np.asarray(gps_xy, np.float64).reshape(-1, 2),
+                                                 (self.n_filters, 2)))
+        out = np.empty(self.n_rows, np.float32) if return_weights else None
+        with self._lock:
+            _lib.check(self._lib.auvpf_update_gps(self._h, _ptr(g), _ptr(out)))
+        return self._weights_out(out) if return_weights else None
+
+    def update_mbes(self, ranges, return_weights=True):
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(ranges, np.float32).reshape(-1, self.n_beams),
+                                                 (self.n_filters, self.n_beams)))
+        out = np.empty(self.n_rows, np.float32) if return_weights else None
+        with self._lock:
+            _lib.check(self._lib.auvpf_update_mbes(self._h, _ptr(r), _ptr(out)))
+        return self._weights_out(out) if return_weights else None
+
+    def raycast(self, poses):
+        """Expected ranges (n, B) float32 for explicit poses (parity probe)."""
+        p = np.ascontiguousarray(poses, np.float64).reshape(-1, 6)
+        out = np.empty((p.shape[0], self.n_beams), np.float32)
+        with self._lock:
+            _lib.check(self._lib.auvpf_raycast(self._h, _ptr(p), p.shape[0], _ptr(out)))
+        return out
+
+    # -- resample: auv_pf.resample (auv_pf.py:169-192) ---------------------------------------
+    def resample(self, weights=None, u=None, noise=None, return_ancestors=False, roughen=True):
+        """Normalise (:172), draw ancestors, reassign poses (:183-189,195-198) and add
+        ``resampling_noise_covariance`` noise to every particle (:191-192).
+        ``weights=None`` uses the device-resident log-weights of the last update;
+        a float64 array reproduces the reference call ``resample(weights)``.
+        ``u``: the ``random()`` of resampling.py:157 (one per filter), default Philox."""
+        anc = np.empty(self.n_rows, np.int32) if return_ancestors else None
+        uu = None if u is None else np.ascontiguousarray(np.broadcast_to(np.asarray(u, np.float64).reshape(-1),
+                                                                         (self.n_filters,)))
+        rv = (C.c_double * 6)(*self.res_noise_cov) if roughen else None
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(self.n_rows, 6)
+        flags = _lib.RS_INPLACE_REF if self.inplace_reference else _lib.RS_SORTED
+        with self._lock:
+            if weights is None:
+                rc = self._lib.auvpf_resample(self._h, self.resampler, flags, _ptr(uu), _ptr(anc), rv, _ptr(nz))
+            else:
+                w = np.ascontiguousarray(weights, np.float64).reshape(self.n_rows)
+                rc = self._lib.auvpf_resample_weights(self._h, _ptr(w), self.resampler, flags, _ptr(uu),
+                                                      _ptr(anc), rv, _ptr(nz))
+            _lib.check(rc)
+        return anc
+
+    def weights_q(self):
+        """Fixed-point normalised weights of the last resample: uint64 q, w = q * 2^-52."""
+        out = np.empty(self.n_rows, np.uint64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_get_weights_q(self._h, _ptr(out)))
+        return out
+
+    def apply_indices(self, indices):
+        """The reference's keep/lost/dupes reassignment for given indices (auv_pf.py:183-198)."""
+        idx = np.ascontiguousarray(indices, np.int32).reshape(self.n_rows)
+        with self._lock:
+            _lib.check(self._lib.auvpf_apply_indices(self._h, _ptr(idx), 0))
+
+    def reassign_poses(self, lost, dupes):
+        """auv_pf.reassign_poses (auv_pf.py:195-198) for explicit lists."""
+        idx = np.arange(self.n_rows, dtype=np.int32)
+        n = min(len(lost), len(dupes))
+        idx[np.asarray(lost[:n], np.int64)] = np.asarray(dupes[:n], np.int32)
+        # an index array in which every slot names its source is its own ancestor map
+        p = self.poses()
+        self.set_poses(p[idx])
+
+    def roughen(self, var=None, noise=None):
+        v = (C.c_double * 6)(*parse_covariance(self.res_noise_cov if var is None else var))
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(self.n_rows, 6)
+        with self._lock:
+            _lib.check(self._lib.auvpf_roughen(self._h, v, _ptr(nz)))
+
+    # -- estimate: auv_pf.update_loc_pose (auv_pf.py:218-252) --------------------------------
+    def mean_cov(self):
+        """``(mean (F,6), cov (F,3,3))``: unweighted mean pose with the arithmetic mean of
+        the wrapped yaws, and the reference's partially filled 3x3 covariance."""
+        mean = np.empty((self.n_filters, 6), np.float64)
+        cov = np.empty((self.n_filters, 9), np.float64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_mean_cov(self._h, _ptr(mean), _ptr(cov)))
+        return mean, cov.reshape(self.n_filters, 3, 3)
+
+    def neff(self):
+        out = np.empty(self.n_filters, np.float64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_neff(self._h, _ptr(out)))
+        return out
+
+    # -- measurement support -----------------------------------------------------------------
+    def profile(self, on=True):
+        _lib.check(self._lib.auvpf_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        n = len(_lib.K_NAMES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        with self._lock:
+            _lib.check(self._lib.auvpf_profile_read(self._h, ms, cnt, 1 if reset else 0))
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(_lib.K_NAMES)}

@@ -1,0 +1,94 @@
+"""ctypes binding of the TEST-ONLY host simulator (tests/hostsim/hostsim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libauvpf_hostsim.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(_HERE, "hostsim.cpp")
+        hdr = os.path.join(_HERE, "..", "..", "smarc_navigation_b200", "csrc", "auvpf_math.cuh")
+        if (not os.path.isfile(_SO)) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            subprocess.check_call(["make", "-C", _HERE], stdout=subprocess.DEVNULL)
+        _lib = C.CDLL(_SO)
+        _lib.hs_resample.restype = C.c_int
+        _lib.hs_count_below.restype = C.c_long
+        _lib.hs_wrap_pi.restype = C.c_float
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def raycast_poses(dem, shift, range_max, m2o, poses, beams, want_mip=False):
+    L = lib()
+    z = np.ascontiguousarray(dem["z"], np.float32)
+    H, W = z.shape
+    poses = np.ascontiguousarray(poses, np.float64)
+    beams = np.ascontiguousarray(beams, np.float32)
+    m2o = np.ascontiguousarray(m2o, np.float64).reshape(16)
+    n, B = poses.shape[0], beams.shape[0]
+    out = np.empty((n, B), np.float32)
+    oH, oW = C.c_int(), C.c_int()
+    L.hs_mip_dims(C.c_int(H), C.c_int(W), C.c_int(shift), C.byref(oH), C.byref(oW))
+    mip = np.empty((oH.value, oW.value), np.float32)
+    L.hs_raycast_poses(_p(z), C.c_int(H), C.c_int(W), C.c_double(dem["x0"]), C.c_double(dem["y0"]),
+                       C.c_double(dem["res"]), C.c_int(shift), C.c_double(range_max), _p(m2o), _p(poses),
+                       C.c_long(n), _p(beams), C.c_int(B), _p(out), _p(mip))
+    return (out, mip) if want_mip else out
+
+
+def propagate(poses, params, noise):
+    """poses (n,6) f64 -> (n,6) f64 through the fp32/fp64 SoA device math."""
+    L = lib()
+    P = np.asarray(poses, np.float64)
+    x, y = P[:, 0].copy(), P[:, 1].copy()
+    z, r, p, w = (P[:, k].astype(np.float32) for k in (2, 3, 4, 5))
+    nz = np.ascontiguousarray(noise, np.float32)
+    f = [C.c_float(float(v)) for v in params]
+    L.hs_propagate(_p(x), _p(y), _p(z), _p(r), _p(p), _p(w), C.c_long(len(x)), *f, _p(nz))
+    return np.stack([x, y, z.astype(np.float64), r.astype(np.float64), p.astype(np.float64), w.astype(np.float64)], -1)
+
+
+def philox(ctr, key):
+    L = lib()
+    ctr = np.ascontiguousarray(ctr, np.uint32)
+    key = np.ascontiguousarray(key, np.uint32)
+    out = np.empty_like(ctr)
+    L.hs_philox(_p(ctr), _p(key), C.c_long(ctr.shape[0]), _p(out))
+    return out
+
+
+def normals6(seed, ids, step, stream):
+    L = lib()
+    ids = np.ascontiguousarray(ids, np.int64)
+    out = np.empty((len(ids), 6), np.float32)
+    L.hs_normals6(C.c_uint64(seed), _p(ids), C.c_long(len(ids)), C.c_uint32(step), C.c_uint32(stream), _p(out))
+    return out
+
+
+def resample(logw, u):
+    L = lib()
+    lw = np.ascontiguousarray(logw, np.float32)
+    qq = np.empty(len(lw), np.uint64)
+    anc = np.empty(len(lw), np.int32)
+    rc = L.hs_resample(_p(lw), C.c_long(len(lw)), C.c_double(u), _p(qq), _p(anc))
+    if rc:
+        raise FloatingPointError("degenerate")
+    return qq, anc
+
+
+def count_below(u, N, c):
+    return int(lib().hs_count_below(C.c_double(u), C.c_long(N), C.c_uint64(c)))
+
+
+def wrap_pi(a):
+    return float(lib().hs_wrap_pi(C.c_float(a)))

@@ -1,0 +1,195 @@
+// hostsim.cpp -- TEST-ONLY host compile of the device math (auvpf_math.cuh).
+//
+// The build container has no GPU.  This file compiles the very same
+// __host__ __device__ functions the CUDA kernels call and drives them with
+// plain loops, so the CPU test-suite can check the kernel ARITHMETIC (raycast
+// traversal, propagate, fixed-point normalisation, ancestor search, Philox)
+// against the oracle before any GPU time is spent.  It is NOT part of the
+// product: nothing under smarc_navigation_b200/ loads it, and it is never used
+// as a fallback.  The GPU parity tests (-m gpu) go through libauvpf.so.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../smarc_navigation_b200/csrc/auvpf_math.cuh"
+
+using namespace auvpf;
+
+namespace {
+struct HostDem {
+    std::vector<float> mip;
+    DemView v;
+};
+
+void build_mip(const float *z, int H, int W, int shift, std::vector<float> &out, int &oH, int &oW)
+{
+    std::vector<float> prev;
+    int pH = 0, pW = 0;
+    for (int L = 1; L <= shift; ++L) {
+        int S = 1 << L;
+        int h = std::max(1, (H - 1 + S - 1) / S), w = std::max(1, (W - 1 + S - 1) / S);
+        std::vector<float> lvl((size_t)h * w);
+        for (int bi = 0; bi < h; ++bi)
+            for (int bj = 0; bj < w; ++bj) {
+                float m = -INFINITY;
+                if (L == 1) {
+                    for (int di = 0; di <= 2; ++di)
+                        for (int dj = 0; dj <= 2; ++dj)
+                            m = std::max(m, z[(size_t)std::min(2 * bi + di, H - 1) * W + std::min(2 * bj + dj, W - 1)]);
+                } else {
+                    for (int di = 0; di < 2; ++di)
+                        for (int dj = 0; dj < 2; ++dj) {
+                            int i = 2 * bi + di, j = 2 * bj + dj;
+                            if (i < pH && j < pW) m = std::max(m, prev[(size_t)i * pW + j]);
+                        }
+                }
+                lvl[(size_t)bi * w + bj] = m;
+            }
+        prev.swap(lvl);
+        pH = h;
+        pW = w;
+    }
+    out.swap(prev);
+    oH = pH;
+    oW = pW;
+}
+}   // namespace
+
+extern "C" {
+
+// expected ranges (n, B) for explicit poses: mirrors k_raycast_poses
+void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double res, int shift, double range_max,
+                      const double *m2o, const double *poses, long n, const float *beams, int B, float *out,
+                      float *mip_out /* optional, for checking the pyramid */)
+{
+    HostDem d;
+    int mH, mW;
+    build_mip(z, H, W, shift, d.mip, mH, mW);
+    if (mip_out) memcpy(mip_out, d.mip.data(), sizeof(float) * d.mip.size());
+    DemView &v = d.v;
+    v.z = z;
+    v.mip = d.mip.data();
+    v.W = W;
+    v.H = H;
+    v.mipW = mW;
+    v.mipH = mH;
+    v.shift = shift;
+    v.inv_res = (float)(1.0 / res);
+    v.range_max = (float)range_max;
+    v.zmax = *std::max_element(z, z + (size_t)H * W);
+    v.x0 = x0;
+    v.y0 = y0;
+    v.inv_res_d = 1.0 / res;
+    FrameParams fp;
+    bool ident = true;
+    for (int a = 0; a < 3; ++a) {
+        fp.m2o_t[a] = m2o[4 * a + 3];
+        for (int b = 0; b < 3; ++b) {
+            fp.m2o_r[3 * a + b] = m2o[4 * a + b];
+            if (m2o[4 * a + b] != (a == b ? 1.0 : 0.0)) ident = false;
+        }
+    }
+    fp.m2o_identity_r = ident;
+    for (long i = 0; i < n; ++i) {
+        const double *ps = poses + 6 * i;
+        double p[3];
+        double R[9];
+        particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
+        int ix0, iy0;
+        float lx0, ly0;
+        origin_cell(v, p, ix0, iy0, lx0, ly0);
+        for (int b = 0; b < B; ++b) {
+            Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
+            out[(size_t)i * B + b] = raycast_one(v, ray);
+        }
+    }
+}
+
+int hs_mip_dims(int H, int W, int shift, int *oH, int *oW)
+{
+    int S = 1 << shift;
+    *oH = std::max(1, (H - 1 + S - 1) / S);
+    *oW = std::max(1, (W - 1 + S - 1) / S);
+    return 0;
+}
+
+// propagate: mirrors k_propagate with injected noise (n,6); params computed by the caller
+void hs_propagate(double *x, double *y, float *z, float *roll, float *pitch, float *yaw, long n, float a, float b,
+                  float wzdt, float proll, float ppitch, float pz, float sx, float sy, float syaw, const float *noise)
+{
+    PredictParams p{a, b, wzdt, proll, ppitch, pz, sx, sy, syaw, 0.f};
+    for (long i = 0; i < n; ++i)
+        propagate_one(p, x[i], y[i], z[i], roll[i], pitch[i], yaw[i], noise[6 * i], noise[6 * i + 1], noise[6 * i + 5]);
+}
+
+void hs_philox(const uint32_t *ctr, const uint32_t *key, long n, uint32_t *out)
+{
+    for (long i = 0; i < n; ++i) {
+        U4 c{ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3]};
+        U4 r = philox4x32_10(c, key[2 * i], key[2 * i + 1]);
+        out[4 * i] = r.x;
+        out[4 * i + 1] = r.y;
+        out[4 * i + 2] = r.z;
+        out[4 * i + 3] = r.w;
+    }
+}
+
+// the 6 normals of six_normals() for particle ids
+void hs_normals6(uint64_t seed, const int64_t *ids, long n, uint32_t step, uint32_t stream, float *out)
+{
+    for (long i = 0; i < n; ++i) {
+        U4 r0 = philox_for(seed, ids[i], step, stream, 0), r1 = philox_for(seed, ids[i], step, stream, 1);
+        float *o = out + 6 * i;
+        box_muller(r0.x, r0.y, o[0], o[1]);
+        box_muller(r0.z, r0.w, o[2], o[3]);
+        box_muller(r1.x, r1.y, o[4], o[5]);
+    }
+}
+
+// fixed-point normalisation + systematic select, sequentially, with the device functions
+int hs_resample(const float *logw, long M, double u, uint64_t *qq_out, int32_t *anc_out)
+{
+    float m = -INFINITY;
+    for (long i = 0; i < M; ++i)
+        if (logw[i] == logw[i] && logw[i] > m) m = logw[i];
+    if (!std::isfinite(m)) return -1;
+    uint64_t lo = 0, hi = 0;
+    for (long i = 0; i < M; ++i) {
+        uint64_t a = a_from_logw(logw[i], m);
+        lo += a & 0xFFFFFFFFull;
+        hi += a >> 32;
+    }
+    unsigned __int128 A = (unsigned __int128)lo + ((unsigned __int128)hi << 32);
+    uint64_t A_lo = (uint64_t)A, A_hi = (uint64_t)(A >> 64);
+    std::vector<uint64_t> cdf(M);
+    uint64_t acc = 0;
+    for (long i = 0; i < M; ++i) {
+        acc += q_from_a(a_from_logw(logw[i], m), A_lo, A_hi);
+        cdf[i] = acc;
+    }
+    uint64_t D = (1ull << kQBits) - acc;
+    for (long i = 0; i < M; ++i) {
+        uint64_t q = q_from_a(a_from_logw(logw[i], m), A_lo, A_hi);
+        if (qq_out) qq_out[i] = q + ((uint64_t)i < D ? 1 : 0);
+    }
+    double n = (double)M;
+    for (long i = 0; i < M; ++i) {
+        double pos = sys_position(u, i, n);
+        long l = 0, h = M;
+        while (l < h) {
+            long mid = (l + h) >> 1;
+            uint64_t jg1 = (uint64_t)(mid + 1);
+            double c = cdf_value(cdf[mid] + (jg1 < D ? jg1 : D));
+            if (pos < c) h = mid;
+            else l = mid + 1;
+        }
+        anc_out[i] = (int32_t)std::min(l, M - 1);
+    }
+    return 0;
+}
+
+long hs_count_below(double u, long N, uint64_t c) { return (long)sys_count_below(u, N, c); }
+
+float hs_wrap_pi(float a) { return wrap_pi(a); }
+}

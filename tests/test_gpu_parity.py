@@ -1,0 +1,522 @@
+"""GPU parity tests proper: every call goes through the C ABI (libauvpf.so) via the
+Python facade and is compared with the oracle / the golden vectors of the
+unmodified reference.  Tolerances are the ones BASELINE.json's north_star
+states: ancestors bit-exact, beam ranges 1e-4 m, log-weights 1e-5 relative."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import pf_oracle as o
+from oracle import tf_stub
+from smarc_navigation_b200 import world
+
+pytestmark = pytest.mark.gpu
+
+RANGE_TOL = 1e-4
+LOGW_RTOL = 1e-5
+FRAGILE = 2e-3
+
+
+_DEMS = {}
+
+
+def _dem(n, res, seed=1):
+    key = (n, res, seed)
+    if key not in _DEMS:
+        _DEMS[key] = world.make_dem(n, res, seed=seed)
+    return _DEMS[key]
+
+
+def _pf(**kw):
+    from smarc_navigation_b200 import ParticleFilter
+    return ParticleFilter(**kw)
+
+
+def _dyaw(a, b):
+    return (a - b + np.pi) % (2 * np.pi) - np.pi
+
+
+def _cloud(rng, n, centre, spread, roll_pitch=0.03, z=-5.0):
+    poses = np.zeros((n, 6))
+    poses[:, 0] = centre[0] + rng.normal(0, spread, n)
+    poses[:, 1] = centre[1] + rng.normal(0, spread, n)
+    poses[:, 2] = z
+    poses[:, 3] = rng.normal(0, roll_pitch, n)
+    poses[:, 4] = rng.normal(0, roll_pitch, n)
+    poses[:, 5] = rng.uniform(-np.pi, np.pi, n)
+    poses[:, 2:6] = poses[:, 2:6].astype(np.float32)
+    return poses
+
+
+# --------------------------------------------------------------------------- a2 / a9 / a3(GPS)
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_particle_golden_init_predict_gps_roughen(golden, case):
+    g = golden("particle")
+    k = lambda s: g[case + "_" + s]
+    N = k("init_noise").shape[0]
+    pf = _pf(particle_count=N, init_covariance=k("init_cov"), motion_covariance=k("process_cov"),
+             resampling_noise_covariance=k("res_cov"), measurement_std=float(k("meas_std")), m2o_matrix=k("m2o"),
+             init_noise=k("init_noise"))
+    np.testing.assert_allclose(pf.poses(), k("poses0"), atol=2e-6)          # fp32 noise * sigma
+    pf.set_poses(k("poses_start"))
+    for odom, noise, want in zip(k("odoms"), k("pred_noise"), k("pred_poses")):
+        pf.predict((odom[0:3], odom[3], odom[4:8], odom[8]), dt=odom[9], noise=noise)
+        got = pf.poses()
+        np.testing.assert_allclose(got[:, 0:2], want[:, 0:2], atol=1e-4)     # G1
+        np.testing.assert_allclose(got[:, 2:5], want[:, 2:5], atol=1e-6)
+        assert np.abs(_dyaw(got[:, 5], want[:, 5])).max() < 1e-5
+    # GPS weight on the GPU state vs scipy's multivariate_normal.pdf on the reference state:
+    # feed the reference's final poses so only the weight arithmetic is compared
+    pf.set_poses(k("pred_poses")[-1])
+    w = pf.update(tuple(k("gps")))
+    want_logw = np.log(k("w"))
+    got_logw = pf.log_weights().astype(np.float64)
+    tol = LOGW_RTOL * np.abs(want_logw) + 5e-5 * (1.0 / float(k("meas_std")) ** 2)   # fp32 yaw/z state quantisation
+    assert np.all(np.abs(got_logw - want_logw) <= tol)
+    np.testing.assert_allclose(w, np.exp(got_logw) + 1e-200, rtol=1e-12)
+    pf.roughen(k("res_cov"), noise=k("res_noise"))
+    got = pf.poses()
+    np.testing.assert_allclose(got[:, 0:2], k("poses_rough")[:, 0:2], atol=1e-5)
+    np.testing.assert_allclose(got[:, 2:5], k("poses_rough")[:, 2:5], atol=2e-6)
+    assert np.abs(_dyaw(got[:, 5], k("poses_rough")[:, 5])).max() < 1e-5
+    pf.close()
+
+
+def test_philox_streams_match_spec():
+    """Device-generated normals follow the documented Philox contract."""
+    N, seed = 4096, 0x1234567890ABCDEF
+    var = [4.0, 1.0, 0.25, 0.01, 0.04, 0.09]
+    pf = _pf(particle_count=N, init_covariance=var, seed=seed, global_offset=1000, global_count=100000)
+    ids = 1000 + np.arange(N, dtype=np.int64)
+    n = o.philox_normals(seed, 1, 0, ids, 2)[:, :6]                           # stream 1 = init, step 0
+    np.testing.assert_allclose(pf.poses(), np.sqrt(var)[None, :] * n, rtol=3e-5, atol=3e-6)
+    p0 = pf.poses()
+    pf.roughen([1.0] * 6)                                                      # stream 3, step 0
+    n = o.philox_normals(seed, 3, 0, ids, 2)[:, :6]
+    np.testing.assert_allclose(pf.poses() - p0, n, rtol=1e-4, atol=1e-5)
+    pf.close()
+    # predict: stream 2, normals 0,1 -> x,y ; 2 -> yaw
+    pf = _pf(particle_count=N, motion_covariance=[1.0, 1.0, 0, 0, 0, 1e-2], seed=seed)
+    pf.predict(((0.0, 0.0, 0.0), 0.0, (0, 0, 0, 1.0), -3.0), dt=0.1)
+    n = o.philox_normals(seed, 2, 0, np.arange(N, dtype=np.int64), 1)
+    got = pf.poses()
+    np.testing.assert_allclose(got[:, 0], n[:, 0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got[:, 1], n[:, 1], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got[:, 5], 0.1 * n[:, 2], rtol=1e-4, atol=1e-5)
+    assert np.all(got[:, 2] == -3.0)
+    pf.close()
+
+
+# --------------------------------------------------------------------------- a4 raycast, a3 MBES
+def _check_ranges(pf, dem, poses, beams, m2o, range_max, max_fragile=2e-3):
+    out = c_oracle.update_mbes(dem, poses, m2o, beams, None, 1.0, 0.5, range_max, want_ranges=True, want_diag=True)
+    r = pf.raycast(poses)
+    ro, dg = out["ranges"], out["diag"]
+    fragile = (dg[..., 0] < FRAGILE) | (dg[..., 1] < FRAGILE) | (dg[..., 2] < FRAGILE)
+    err = np.abs(r - ro)
+    assert fragile.mean() <= max_fragile
+    assert err[~fragile].max() <= RANGE_TOL, err[~fragile].max()
+    return ro, r
+
+
+@pytest.mark.parametrize("cfg,coarse", [("C2", -1), ("C2", 1), ("C2", 4), ("C3", -1), ("C3", 5)])
+def test_raycast_ranges_vs_oracle(cfg, coarse):
+    """G4: >= 1e5 rays per config within 1e-4 m of the float64 triangulated-DEM oracle."""
+    c = world.CONFIGS[cfg]
+    dem = _dem(c["dem_n"], c["res"])
+    beams = world.make_beams(c["beams"])
+    rng = np.random.default_rng(21)
+    ext = c["dem_n"] * c["res"]
+    n = 400 if cfg == "C2" else 200
+    poses = np.concatenate([_cloud(rng, n // 2, (0.3 * ext, 0.3 * ext), 3.0),
+                            _cloud(rng, n // 2, (0.93 * ext, 0.91 * ext), 2.0)])
+    pf = _pf(particle_count=16, range_max=world.RANGE_MAX, coarse_level=coarse)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    ro, r = _check_ranges(pf, dem, poses, beams, np.eye(4), world.RANGE_MAX)
+    assert ro.size >= 100000 and (ro < world.RANGE_MAX).all()
+    pf.close()
+
+
+def test_raycast_edge_cases():
+    dem = world.make_dem(300, 2.0, seed=11)
+    beams = world.make_beams(128, half_angle_deg=75.0)
+    rng = np.random.default_rng(7)
+    q = tf_stub.quaternion_from_euler(0.01, -0.02, 0.7)
+    m2o = tf_stub.translation_matrix([300.0, 250.0, 1.0]).dot(tf_stub.quaternion_matrix(q))
+    for m, rmax in ((np.eye(4), world.RANGE_MAX), (m2o, world.RANGE_MAX), (np.eye(4), 30.0)):
+        pf = _pf(particle_count=16, range_max=rmax, m2o_matrix=m)
+        pf.set_dem(dem)
+        pf.set_beams(beams)
+        c = (0.0, 0.0) if m is m2o else (300.0, 300.0)
+        _check_ranges(pf, dem, _cloud(rng, 64, c, 3.0), beams, m, rmax, 2e-2)
+        if m is not m2o:
+            ro, r = _check_ranges(pf, dem, _cloud(rng, 64, (8.0, 590.0), 6.0), beams, m, rmax, 2e-2)       # border
+            assert (ro >= rmax).any()
+            _check_ranges(pf, dem, _cloud(rng, 32, (-40.0, 300.0), 3.0), beams, m, rmax, 2e-2)           # outside
+            _check_ranges(pf, dem, _cloud(rng, 64, (300.0, 300.0), 3.0, roll_pitch=0.5), beams, m, rmax, 2e-2)
+            up = _cloud(rng, 16, (300.0, 300.0), 3.0)
+            up[:, 3] = np.float32(np.pi)
+            ro, r = _check_ranges(pf, dem, up, beams, m, rmax)
+            assert (r == np.float32(rmax)).all()                                                         # all miss
+            below = _cloud(rng, 16, (300.0, 300.0), 3.0, z=-60.0)
+            ro, r = _check_ranges(pf, dem, below, beams, m, rmax)
+            assert (r == 0.0).all()
+        pf.close()
+
+
+@pytest.mark.parametrize("cfg", ["C2", "C3"])
+def test_update_mbes_logw_vs_oracle(cfg):
+    """G2 (MBES form): fused raycast + likelihood log-weights within 1e-5 relative."""
+    c = world.CONFIGS[cfg]
+    dem = _dem(c["dem_n"], c["res"])
+    B = c["beams"]
+    beams = world.make_beams(B)
+    rng = np.random.default_rng(31)
+    ext = c["dem_n"] * c["res"]
+    N = 512
+    poses = _cloud(rng, N, (0.3 * ext, 0.3 * ext), 2.0)
+    truth = poses[:1].copy()
+    truth[0, 0:2] = 0.3 * ext
+    r_true = c_oracle.update_mbes(dem, truth, np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX, want_ranges=True)["ranges"][0]
+    meas = (r_true + rng.normal(0, 0.05, B)).astype(np.float32)
+    meas[5] = np.nan                # invalid beams are skipped
+    meas[17] = 0.1                  # below range_min
+    meas[40] = 500.0                # above range_max
+    for std in (1.0, 0.2):
+        pf = _pf(particle_count=N, measurement_std=std, range_min=world.RANGE_MIN, range_max=world.RANGE_MAX)
+        pf.set_dem(dem)
+        pf.set_beams(beams)
+        pf.set_poses(poses)
+        w = pf.update(meas)
+        got = pf.log_weights().astype(np.float64)
+        want = c_oracle.update_mbes(dem, poses, np.eye(4), beams, meas.astype(np.float64), std, world.RANGE_MIN,
+                                    world.RANGE_MAX)["logw"]
+        lognorm = -(B - 3) * np.log(std * np.sqrt(2 * np.pi))
+        tol = LOGW_RTOL * (np.abs(want - lognorm) + abs(lognorm))      # relative to the terms, not their difference
+        assert np.all(np.abs(got - want) <= tol), np.max(np.abs(got - want) / tol)
+        assert w.shape == (N,) and np.all(w >= 1e-200)
+        pf.close()
+
+
+# --------------------------------------------------------------------------- a5 / a7 / a8(sorted) / a9
+@pytest.mark.parametrize("N,scale", [(1, 1.0), (100, 3.0), (4097, 10.0), (65536, 25.0), (1048576, 6.0),
+                                     (16777216, 4.0)])
+def test_systematic_resample_bit_exact(N, scale):
+    """G3: ancestors == reference systematic_resample on the GPU's own quantised weights,
+    and the quantised weights == the oracle's fixed-point pipeline, bit for bit."""
+    rng = np.random.default_rng(N)
+    logw = (rng.normal(0, scale, N) - 470.0).astype(np.float32)
+    if N > 10:
+        logw[3] = -np.inf
+        logw[5] = np.nan
+    u = float(rng.uniform())
+    pf = _pf(particle_count=N, resampling_noise_covariance=[0.0] * 6)
+    poses = np.zeros((N, 6))
+    poses[:, 0] = np.arange(N)
+    poses[:, 1] = -2.0 * np.arange(N)
+    poses[:, 5] = (np.arange(N) % 7).astype(np.float32)
+    pf.set_poses(poses)
+    pf.set_log_weights(logw)
+    anc = pf.resample(u=u, return_ancestors=True, roughen=False)
+    qq = pf.weights_q()
+    q_ref, m, A = c_oracle.quantise_logw(logw)
+    np.testing.assert_array_equal(qq, q_ref)
+    w = o.weights_from_q(qq)
+    np.testing.assert_array_equal(anc, c_oracle.systematic(w, u))
+    if N <= 65536:
+        np.testing.assert_array_equal(anc, o.systematic_resample(w, u))
+        if N >= 100:
+            ref = o.normalise_logw(logw)
+            np.testing.assert_allclose(w, ref, atol=2.0 ** -50)
+    assert np.all(np.diff(anc) >= 0)
+    got = pf.poses()
+    np.testing.assert_array_equal(got[:, 0], poses[anc, 0])
+    np.testing.assert_array_equal(got[:, 1], poses[anc, 1])
+    np.testing.assert_array_equal(got[:, 5], poses[anc, 5])
+    neff = pf.neff()[0]
+    np.testing.assert_allclose(neff, 1.0 / np.sum(w * w), rtol=1e-9)
+    pf.close()
+
+
+def test_resample_reference_golden_weights(golden):
+    """The reference's resample(weights) call: linear float64 weights in, systematic out."""
+    g = golden("resampling")
+    names = sorted({k[:-2] for k in g.files if k.endswith("_w")})
+    for n in names:
+        w, u = g[n + "_w"], float(g[n + "_u"])
+        N = len(w)
+        pf = _pf(particle_count=N)
+        anc = pf.resample(weights=w, u=u, return_ancestors=True, roughen=False)
+        qq = pf.weights_q()
+        np.testing.assert_array_equal(qq, o.quantise_linear(w)[0])
+        wq = o.weights_from_q(qq)
+        np.testing.assert_allclose(wq, w / w.sum(), atol=2.0 ** -50)
+        np.testing.assert_array_equal(anc, o.systematic_resample(wq, u))
+        want = g[n + "_systematic"]
+        if want[0] >= 0:
+            # vs the reference run on the UNquantised weights: identical except where a position
+            # falls within 2^-52-grid distance of a CDF step
+            assert (anc != want).mean() <= 0.01
+        pf.close()
+
+
+def test_uniform_weights_identity_and_roughening():
+    N = 1 << 20
+    pf = _pf(particle_count=N, resampling_noise_covariance=[0.25, 0.25, 0, 0, 0, 1e-4], seed=5)
+    pf.set_log_weights(np.full(N, -123.0, np.float32))
+    p0 = np.zeros((N, 6))
+    p0[:, 0] = np.arange(N)
+    pf.set_poses(p0)
+    anc = pf.resample(u=0.37, return_ancestors=True)                 # fused Philox roughening
+    np.testing.assert_array_equal(anc, np.arange(N, dtype=np.int32))
+    got = pf.poses()
+    n = o.philox_normals(5, 3, 0, np.arange(N, dtype=np.int64), 2)[:, :6]
+    np.testing.assert_allclose(got[:, 0] - p0[:, 0], 0.5 * n[:, 0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got[:, 1], 0.5 * n[:, 1], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got[:, 5], 0.01 * n[:, 5], rtol=1e-4, atol=1e-6)
+    assert np.all(got[:, 2:5] == 0.0)
+    pf.close()
+
+
+def test_degenerate_weights_raise_and_leave_state():
+    from smarc_navigation_b200 import DegenerateWeights
+    N = 1000
+    pf = _pf(particle_count=N, init_covariance=[1.0] * 6)
+    p0 = pf.poses()
+    pf.set_log_weights(np.full(N, -np.inf, np.float32))
+    with pytest.raises(DegenerateWeights):
+        pf.resample(u=0.5)
+    pf.set_log_weights(np.full(N, np.nan, np.float32))
+    with pytest.raises(DegenerateWeights):
+        pf.resample(u=0.5)
+    with pytest.raises(DegenerateWeights):
+        pf.resample(weights=np.zeros(N), u=0.5)
+    np.testing.assert_array_equal(pf.poses(), p0)
+    pf.close()
+
+
+# --------------------------------------------------------------------------- a8 reference slot map
+def test_inplace_reference_map(golden):
+    """auv_pf.resample's keep/lost/dupes reassignment (auv_pf.py:183-198) on the golden
+    residual_resample indices, then roughening with the reference's own draws."""
+    g = golden("auv_pf_cycle")
+    N = g["init_noise"].shape[0]
+    for c in range(g["gps"].shape[0]):
+        pf = _pf(particle_count=N, resampling_noise_covariance=g["res_cov"])
+        pf.set_poses(g["poses_pred"][c])
+        pf.apply_indices(g["indices"][c])
+        got = pf.poses()
+        A = o.ancestor_map(g["indices"][c], N)
+        np.testing.assert_array_equal(got[:, 0:2], g["poses_pred"][c][A, 0:2])
+        pf.roughen(noise=g["res_noise"][c])
+        got = pf.poses()
+        np.testing.assert_allclose(got[:, 0:2], g["poses_res"][c][:, 0:2], atol=1e-5)
+        assert np.abs(_dyaw(got[:, 5], g["poses_res"][c][:, 5])).max() < 1e-5
+        pf.close()
+    rng = np.random.default_rng(3)
+    for N in (1, 2, 1000, 300000):
+        idx = rng.integers(0, N, N).astype(np.int32)
+        pf = _pf(particle_count=N)
+        p = np.zeros((N, 6))
+        p[:, 0] = np.arange(N)
+        pf.set_poses(p)
+        pf.apply_indices(idx)
+        np.testing.assert_array_equal(pf.poses()[:, 0], o.ancestor_map(idx, N).astype(np.float64))
+        pf.close()
+
+
+def test_inplace_mode_of_resample():
+    N = 5000
+    rng = np.random.default_rng(8)
+    logw = rng.normal(0, 2, N).astype(np.float32)
+    p = np.zeros((N, 6))
+    p[:, 0] = np.arange(N)
+    pf = _pf(particle_count=N, inplace_reference=True)
+    pf.set_poses(p)
+    pf.set_log_weights(logw)
+    anc = pf.resample(u=0.123, return_ancestors=True, roughen=False)
+    np.testing.assert_array_equal(pf.poses()[:, 0], o.ancestor_map(anc, N).astype(np.float64))
+    pf.close()
+
+
+# --------------------------------------------------------------------------- a10 estimate
+def test_estimate_vs_reference_golden(golden):
+    g = golden("auv_pf_cycle")
+    N = g["init_noise"].shape[0]
+    pf = _pf(particle_count=N)
+    for c in range(g["gps"].shape[0]):
+        pf.set_poses(g["poses_res"][c])
+        mean, cov = pf.mean_cov()
+        ave, cov_ref, quat = o.estimate(pf.poses())
+        np.testing.assert_allclose(mean[0], ave, atol=1e-9)
+        np.testing.assert_allclose(cov[0], cov_ref, atol=1e-9)
+        e = g["estimate"][c]
+        np.testing.assert_allclose(mean[0, 0:3], e[0:3], atol=5e-6)
+        np.testing.assert_allclose(o.covariance36(cov[0]), e[7:43], atol=1e-5)
+        assert cov[0][2, 0] == 0.0 and cov[0][2, 1] == 0.0 and cov[0][1, 0] == cov[0][0, 1]
+    pf.close()
+
+
+# --------------------------------------------------------------------------- batched filters
+def test_batched_filters_match_single_filters():
+    F, M, B = 4, 3000, 64
+    dem = world.make_dem(200, 2.0, seed=9)
+    beams = world.make_beams(B)
+    rng = np.random.default_rng(17)
+    poses = np.concatenate([_cloud(rng, M, (100.0 + 30 * f, 150.0 + 20 * f), 2.0) for f in range(F)])
+    meas = np.stack([rng.uniform(15, 40, B) for _ in range(F)]).astype(np.float32)
+    us = rng.uniform(size=F)
+    pf = _pf(particle_count=M, n_filters=F, range_max=world.RANGE_MAX)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    pf.set_poses(poses)
+    pf.update(meas, return_weights=False)
+    logw = pf.log_weights()
+    anc = pf.resample(u=us, return_ancestors=True, roughen=False)
+    after = pf.poses()
+    mean, cov = pf.mean_cov()
+    for f in range(F):
+        sl = slice(f * M, (f + 1) * M)
+        want = c_oracle.update_mbes(dem, poses[sl], np.eye(4), beams, meas[f].astype(np.float64), 0.01, 0.0,
+                                    world.RANGE_MAX)["logw"]
+        np.testing.assert_allclose(logw[sl], want, rtol=LOGW_RTOL)
+        qq, m, A = c_oracle.quantise_logw(logw[sl])
+        a = c_oracle.systematic(o.weights_from_q(qq), float(us[f]))
+        np.testing.assert_array_equal(anc[sl], a)
+        np.testing.assert_array_equal(after[sl, 0:2], poses[sl][a, 0:2])
+        ave, cref, _ = o.estimate(after[sl])
+        np.testing.assert_allclose(mean[f], ave, atol=1e-9)
+    # per-filter odometry
+    od = [world.Odom(np.array([1.0 + f, 0, 0]), 0.1 * f, world.quat_from_rpy(0.01 * f, 0.0, 0.0), -5.0 - f, 0.1)
+          for f in range(F)]
+    before = pf.poses()
+    pf.predict(od)
+    got = pf.poses()
+    for f in range(F):
+        sl = slice(f * M, (f + 1) * M)
+        want = o.motion_pred(before[sl], od[f].v, od[f].wz, od[f].quat, od[f].z, od[f].dt, [0.0] * 6, np.zeros((M, 6)))
+        np.testing.assert_allclose(got[sl, 0:2], want[:, 0:2], atol=1e-5)
+        assert np.all(got[sl, 2] == np.float32(-5.0 - f))
+    pf.close()
+
+
+# --------------------------------------------------------------------------- G5 cycle
+def test_c1_cycle_lockstep_and_convergence():
+    """C1 (100 particles x 256 beams, 200 cycles).  Lock-step: every cycle the oracle starts
+    from the GPU's state and must reproduce propagate, log-weights, ancestors (bit-exact given
+    the GPU log-weights) and the roughened state.  Free-running: the filter tracks the truth."""
+    c = world.CONFIGS["C1"]
+    dem = _dem(c["dem_n"], c["res"])
+    B, N = c["beams"], c["particles"]
+    beams = world.make_beams(B)
+    P = world.MBES_PARAMS
+    ext = c["dem_n"] * c["res"]
+    traj = world.Trajectory(ext)
+    rng = np.random.default_rng(4)
+    init_noise = rng.normal(size=(N, 6)).astype(np.float32)
+    pf = _pf(particle_count=N, init_covariance=P["init_covariance"], motion_covariance=P["motion_covariance"],
+             resampling_noise_covariance=P["resampling_noise_covariance"], measurement_std=P["measurement_std"],
+             range_min=world.RANGE_MIN, range_max=world.RANGE_MAX, init_mean=traj.truth, init_noise=init_noise)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    rng5, rng6 = np.random.default_rng(5), np.random.default_rng(6)
+    errs = []
+    for cyc in range(200):
+        odoms, truth = traj.cycle()
+        state = pf.poses()
+        for od in odoms:
+            nz = rng5.normal(size=(N, 6)).astype(np.float32)
+            pf.predict(od, noise=nz)
+            state = o.motion_pred(state, od.v, od.wz, od.quat, od.z, od.dt, P["motion_covariance"], nz.astype(np.float64))
+        got = pf.poses()
+        assert np.abs(got[:, 0:2] - state[:, 0:2]).max() < 1e-4
+        assert np.abs(_dyaw(got[:, 5], state[:, 5])).max() < 1e-5
+        r_true = c_oracle.update_mbes(dem, truth[None, :], np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX,
+                                      want_ranges=True)["ranges"][0]
+        meas = (r_true + world.ping_noise(B, cyc)).astype(np.float32)
+        pf.update(meas, return_weights=False)
+        logw = pf.log_weights()
+        want = c_oracle.update_mbes(dem, got, np.eye(4), beams, meas.astype(np.float64), P["measurement_std"],
+                                    world.RANGE_MIN, world.RANGE_MAX)["logw"]
+        np.testing.assert_allclose(logw, want, rtol=LOGW_RTOL)
+        u = float(rng6.uniform())
+        rn = rng5.normal(size=(N, 6)).astype(np.float32)
+        anc = pf.resample(u=u, noise=rn, return_ancestors=True)
+        qq = o.quantise_logw(logw)[0]
+        np.testing.assert_array_equal(pf.weights_q(), qq)
+        a_ref = o.systematic_resample(o.weights_from_q(qq), u)
+        np.testing.assert_array_equal(anc, a_ref)
+        want_state = o.add_noise(got[a_ref], P["resampling_noise_covariance"], rn.astype(np.float64))
+        after = pf.poses()
+        np.testing.assert_allclose(after[:, 0:2], want_state[:, 0:2], atol=1e-5)
+        assert np.abs(_dyaw(after[:, 5], want_state[:, 5])).max() < 1e-5
+        mean, cov = pf.mean_cov()
+        errs.append(np.hypot(mean[0, 0] - truth[0], mean[0, 1] - truth[1]))
+    assert np.mean(errs[100:]) < 1.0, np.mean(errs[100:])
+    pf.close()
+
+
+# --------------------------------------------------------------------------- full-size properties
+def test_c3_full_size_properties():
+    """At BASELINE C3 size (1M x 512 on the 4000^2 DEM) the oracle is too slow for a full
+    comparison; check size-independent properties and an oracle-checked subsample."""
+    c = world.CONFIGS["C3"]
+    dem = _dem(c["dem_n"], c["res"])
+    B, N = c["beams"], c["particles"]
+    beams = world.make_beams(B)
+    P = world.MBES_PARAMS
+    truth = np.array([600.0, 600.0, -5.0, 0.01, -0.02, 0.3])
+    pf = _pf(particle_count=N, init_covariance=P["init_covariance"], measurement_std=P["measurement_std"],
+             resampling_noise_covariance=[0.0] * 6, range_min=world.RANGE_MIN, range_max=world.RANGE_MAX,
+             init_mean=truth, seed=11)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    r_true = c_oracle.update_mbes(dem, truth[None, :], np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX,
+                                  want_ranges=True)["ranges"][0]
+    meas = r_true.astype(np.float32)
+    poses = pf.poses()
+    pf.update(meas, return_weights=False)
+    logw = pf.log_weights()
+    sub = np.random.default_rng(0).choice(N, 2000, replace=False)
+    want = c_oracle.update_mbes(dem, poses[sub], np.eye(4), beams, meas.astype(np.float64), P["measurement_std"],
+                                world.RANGE_MIN, world.RANGE_MAX)["logw"]
+    np.testing.assert_allclose(logw[sub], want, rtol=LOGW_RTOL)
+    # the best particles are the ones nearest the truth
+    best = np.argsort(logw)[-100:]
+    assert np.hypot(poses[best, 0] - truth[0], poses[best, 1] - truth[1]).mean() < 1.5
+    anc = pf.resample(u=0.5, return_ancestors=True, roughen=False)
+    qq = pf.weights_q()
+    assert int(qq.sum(dtype=np.uint64)) == 1 << 52
+    assert np.all(np.diff(anc) >= 0) and anc.min() >= 0 and anc.max() < N
+    counts = np.bincount(anc, minlength=N)
+    expect = o.weights_from_q(qq) * N
+    assert np.abs(counts - expect).max() <= 1.0 + 1e-9           # systematic: |offspring - N w| < 1
+    after = pf.poses()
+    np.testing.assert_array_equal(after[:, 0], poses[anc, 0])
+    # idempotence: resampling uniform weights with the same u leaves the set unchanged
+    pf.set_log_weights(np.zeros(N, np.float32))
+    anc2 = pf.resample(u=0.5, return_ancestors=True, roughen=False)
+    np.testing.assert_array_equal(anc2, np.arange(N, dtype=np.int32))
+    np.testing.assert_array_equal(pf.poses(), after)
+    pf.close()
+
+
+def test_device_pointer_inputs():
+    """Torch tensors pass zero-copy through data_ptr()."""
+    import ctypes as C
+    import torch
+    from smarc_navigation_b200 import _lib
+    N = 10000
+    pf = _pf(particle_count=N)
+    lw = torch.randn(N, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    L = _lib.load()
+    _lib.check(L.auvpf_set_logw(pf._h, C.c_void_p(lw.data_ptr())))
+    anc_t = torch.empty(N, device="cuda", dtype=torch.int32)
+    u = np.array([0.25])
+    _lib.check(L.auvpf_resample(pf._h, 0, 0, C.c_void_p(u.ctypes.data), C.c_void_p(anc_t.data_ptr()), None, None))
+    pf.sync()
+    qq = o.quantise_logw(lw.cpu().numpy())[0]
+    np.testing.assert_array_equal(anc_t.cpu().numpy(), o.systematic_resample(o.weights_from_q(qq), 0.25))
+    pf.close()

@@ -1,0 +1,216 @@
+"""Kernel ARITHMETIC vs the oracle, on the CPU: the __host__ __device__ functions of
+smarc_navigation_b200/csrc/auvpf_math.cuh compiled for the host (tests/hostsim).
+This is how kernel logic is checked in a container without a GPU; the GPU parity
+tests (test_gpu_*.py) repeat the same comparisons through libauvpf.so."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from oracle import pf_oracle as o
+from oracle import tf_stub
+from smarc_navigation_b200 import world
+from tests.hostsim import binding as hs
+
+RANGE_TOL = 1e-4      # north_star: beam ranges within 1e-4 m
+FRAGILE = 2e-3        # rays whose first-hit decision hinges on < 2 mm are excluded (and counted)
+
+
+def _cloud(rng, n, centre, spread, roll_pitch=0.03, z=-5.0):
+    poses = np.zeros((n, 6))
+    poses[:, 0] = centre[0] + rng.normal(0, spread, n)
+    poses[:, 1] = centre[1] + rng.normal(0, spread, n)
+    poses[:, 2] = z
+    poses[:, 3] = rng.normal(0, roll_pitch, n)
+    poses[:, 4] = rng.normal(0, roll_pitch, n)
+    poses[:, 5] = rng.uniform(-np.pi, np.pi, n)
+    poses[:, 2:6] = poses[:, 2:6].astype(np.float32)     # the device keeps z, roll, pitch, yaw in fp32
+    return poses
+
+
+def _compare(dem, shift, poses, beams, m2o, range_max, max_fragile_frac=2e-3):
+    out = c_oracle.update_mbes(dem, poses, m2o, beams, None, 1.0, 0.5, range_max, want_ranges=True, want_diag=True)
+    r = hs.raycast_poses(dem, shift, range_max, m2o, poses, beams.astype(np.float32))
+    ro, dg = out["ranges"], out["diag"]
+    fragile = (dg[..., 0] < FRAGILE) | (dg[..., 1] < FRAGILE) | (dg[..., 2] < FRAGILE)
+    err = np.abs(r - ro)
+    assert fragile.mean() <= max_fragile_frac, fragile.mean()
+    assert err[~fragile].max() <= RANGE_TOL, err[~fragile].max()
+    # fragile rays must still be sane: either equal or both valid ranges
+    assert np.all((r >= 0) & (r <= np.float32(range_max)))
+    return ro, err, fragile
+
+
+@pytest.mark.parametrize("n,res,shift,B", [(500, 2.0, 1, 256), (500, 2.0, 2, 256), (500, 2.0, 4, 64),
+                                           (1200, 0.5, 3, 512), (1200, 0.5, 5, 128)])
+def test_raycast_fan_over_synthetic_bathymetry(n, res, shift, B):
+    dem = world.make_dem(n, res)
+    rng = np.random.default_rng(4)
+    poses = _cloud(rng, 96, (0.45 * n * res,) * 2, 3.0)
+    ro, err, fragile = _compare(dem, shift, poses, world.make_beams(B), np.eye(4), world.RANGE_MAX)
+    assert (ro < world.RANGE_MAX).all()          # every beam hits the seafloor here
+
+
+def test_raycast_far_from_origin_keeps_tolerance():
+    """World coordinates ~1.9 km: fp32 world coordinates would already be off by 1.2e-4 m."""
+    n, res = 4000, 0.5
+    dem = world.make_dem(n, res)
+    rng = np.random.default_rng(5)
+    poses = _cloud(rng, 48, (1900.0, 1850.0), 2.0)
+    _compare(dem, 3, poses, world.make_beams(512), np.eye(4), world.RANGE_MAX)
+
+
+def test_raycast_with_map_to_odom_transform():
+    dem = world.make_dem(500, 2.0)
+    rng = np.random.default_rng(6)
+    q = tf_stub.quaternion_from_euler(0.01, -0.02, 0.7)
+    m2o = tf_stub.translation_matrix([400.0, 300.0, 1.5]).dot(tf_stub.quaternion_matrix(q))
+    poses = _cloud(rng, 64, (50.0, 80.0), 5.0)
+    _compare(dem, 1, poses, world.make_beams(256), m2o, world.RANGE_MAX)
+
+
+def test_raycast_edges_misses_and_steep_rays():
+    """Particles at / outside the map border, short range_max (misses), large roll
+    (beams up to ~horizontal), upward-looking beams."""
+    dem = world.make_dem(300, 2.0, seed=11)
+    rng = np.random.default_rng(7)
+    beams = world.make_beams(128, half_angle_deg=75.0)
+    edge = _cloud(rng, 64, (8.0, 590.0), 6.0)                       # straddles two borders
+    ro, err, fr = _compare(dem, 2, edge, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2)
+    assert (ro >= world.RANGE_MAX).any() and (ro < world.RANGE_MAX).any()
+    outside = _cloud(rng, 32, (-40.0, 300.0), 3.0)
+    _compare(dem, 2, outside, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2)
+    tilted = _cloud(rng, 64, (300.0, 300.0), 3.0, roll_pitch=0.5)
+    _compare(dem, 2, tilted, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2)
+    short = _cloud(rng, 32, (300.0, 300.0), 3.0)
+    ro, err, fr = _compare(dem, 2, short, beams, np.eye(4), 30.0, max_fragile_frac=2e-2)
+    assert (ro == 30.0).any()
+    up = _cloud(rng, 16, (300.0, 300.0), 3.0)
+    up[:, 3] = np.pi                                                # sonar looking up: all miss
+    ro, err, fr = _compare(dem, 2, up, beams, np.eye(4), world.RANGE_MAX)
+    assert (ro == world.RANGE_MAX).all()
+    below = _cloud(rng, 16, (300.0, 300.0), 3.0, z=-60.0)           # vehicle under the seafloor: range 0
+    ro, err, fr = _compare(dem, 2, below, beams, np.eye(4), world.RANGE_MAX)
+    assert (ro == 0.0).all()
+
+
+def test_raycast_rough_terrain_random_directions():
+    dem = world.make_dem(200, 1.0, seed=3)
+    dem["z"] = (dem["z"] + np.random.default_rng(1).normal(0, 0.6, dem["z"].shape)).astype(np.float32)
+    rng = np.random.default_rng(8)
+    d = rng.normal(size=(96, 3))
+    d[:, 2] = -np.abs(d[:, 2])
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    poses = _cloud(rng, 48, (100.0, 100.0), 20.0, roll_pitch=0.2, z=-12.0)
+    _compare(dem, 2, poses, d, np.eye(4), 80.0, max_fragile_frac=3e-2)
+
+
+def test_mip_is_conservative():
+    dem = world.make_dem(130, 2.0, seed=2)
+    z = dem["z"]
+    for shift in (1, 2, 3, 5):
+        _, mip = hs.raycast_poses(dem, shift, 50.0, np.eye(4), np.zeros((1, 6)), world.make_beams(4).astype(np.float32),
+                                  want_mip=True)
+        S = 1 << shift
+        for bi in range(mip.shape[0]):
+            for bj in range(mip.shape[1]):
+                blk = z[bi * S:min((bi + 1) * S, z.shape[0] - 1) + 1, bj * S:min((bj + 1) * S, z.shape[1] - 1) + 1]
+                assert mip[bi, bj] == blk.max()
+
+
+def test_propagate_matches_reference_golden(golden):
+    """G1: fp32/fp64 SoA propagate vs Particle.motion_pred golden, injected normals."""
+    g = golden("particle")
+    for case in ("a", "b"):
+        poses = g[case + "_poses_start"].copy()
+        cov = g[case + "_process_cov"]
+        for odom, noise, want in zip(g[case + "_odoms"], g[case + "_pred_noise"], g[case + "_pred_poses"]):
+            roll, pitch = o.odom_roll_pitch(odom[4:8])
+            dt = odom[9]
+            vx, vy, vz = odom[0:3] * dt
+            cr, sr, cp, sp = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch)
+            params = (cp * vx + sp * sr * vy + sp * cr * vz, cr * vy - sr * vz, odom[3] * dt, roll, pitch, odom[8],
+                      np.sqrt(cov[0]), np.sqrt(cov[1]), np.sqrt(cov[5]))
+            poses = hs.propagate(poses, params, noise)
+            np.testing.assert_allclose(poses[:, 0:2], want[:, 0:2], atol=1e-4)
+            np.testing.assert_allclose(poses[:, 2:5], want[:, 2:5], atol=1e-6)
+            dyaw = (poses[:, 5] - want[:, 5] + np.pi) % (2 * np.pi) - np.pi
+            assert np.abs(dyaw).max() < 1e-5
+
+
+def test_propagate_200_steps_drift():
+    """200 predicts at map coordinates ~1 km stay within 1e-4 m / 1e-5 rad of float64."""
+    rng = np.random.default_rng(12)
+    N = 256
+    poses = np.zeros((N, 6))
+    poses[:, 0] = 1000 + rng.normal(0, 2, N)
+    poses[:, 1] = 900 + rng.normal(0, 2, N)
+    poses[:, 5] = rng.uniform(-3, 3, N)
+    ref = poses.copy()
+    sim = poses.copy()
+    sim[:, 5] = sim[:, 5].astype(np.float32)
+    ref[:, 5] = sim[:, 5]
+    cov = np.array([1e-4, 1e-4, 0, 0, 0, 1e-6])
+    traj = world.Trajectory(2000.0)
+    for s in range(200):
+        od = traj.step()
+        noise = rng.normal(size=(N, 6)).astype(np.float32)
+        ref = o.motion_pred(ref, od.v, od.wz, od.quat, od.z, od.dt, cov, noise.astype(np.float64))
+        roll, pitch = o.odom_roll_pitch(od.quat)
+        vx, vy, vz = od.v * od.dt
+        cr, sr, cp, sp = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch)
+        params = (cp * vx + sp * sr * vy + sp * cr * vz, cr * vy - sr * vz, od.wz * od.dt, roll, pitch, od.z,
+                  np.sqrt(cov[0]), np.sqrt(cov[1]), np.sqrt(cov[5]))
+        sim = hs.propagate(sim, params, noise)
+    assert np.abs(sim[:, 0:2] - ref[:, 0:2]).max() < 1e-4
+    dyaw = (sim[:, 5] - ref[:, 5] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(dyaw).max() < 1e-5
+
+
+def test_wrap_pi():
+    for a in (0.0, 3.0, -3.0, 3.2, -3.2, 6.0, -6.0, 9.5, -9.5, 40.0, -40.0, np.pi, -np.pi):
+        w = hs.wrap_pi(a)
+        ref = (np.float64(np.float32(a)) + np.pi) % (2 * np.pi) - np.pi
+        d = (w - ref + np.pi) % (2 * np.pi) - np.pi
+        assert abs(d) < 4e-6 and -np.pi - 1e-6 <= w <= np.pi + 1e-6
+
+
+def test_philox_and_normals():
+    rng = np.random.default_rng(3)
+    ctr = rng.integers(0, 2 ** 32, (64, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2 ** 32, (64, 2), dtype=np.uint64).astype(np.uint32)
+    np.testing.assert_array_equal(hs.philox(ctr, key), o.philox4x32_10(ctr, key))
+    ids = np.array([0, 1, 2, 12345, 2 ** 33 + 7], np.int64)
+    got = hs.normals6(0xDEADBEEF12345678, ids, 9, 3)
+    want = o.philox_normals(0xDEADBEEF12345678, 3, 9, ids, 2)[:, :6]
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
+    big = hs.normals6(42, np.arange(200000, dtype=np.int64), 0, 1)
+    assert abs(big.mean()) < 5e-3 and abs(big.std() - 1) < 5e-3
+    assert abs((big ** 3).mean()) < 2e-2 and abs((big ** 4).mean() - 3) < 5e-2
+
+
+@pytest.mark.parametrize("N,scale", [(1, 1.0), (2, 1.0), (100, 3.0), (4097, 10.0), (65536, 25.0)])
+def test_fixed_point_resample_is_bit_exact(N, scale):
+    """G3: device normalise + select arithmetic == oracle quantiser == reference systematic."""
+    rng = np.random.default_rng(N)
+    logw = (rng.normal(0, scale, N) - 470.0).astype(np.float32)
+    if N > 10:
+        logw[3] = -np.inf
+        logw[5] = np.nan
+    u = float(rng.uniform())
+    qq, anc = hs.resample(logw, u)
+    q_ref, m, A = c_oracle.quantise_logw(logw)
+    np.testing.assert_array_equal(qq, q_ref)
+    if N <= 5000:
+        np.testing.assert_array_equal(qq, o.quantise_logw(logw)[0])
+    w = o.weights_from_q(qq)
+    np.testing.assert_array_equal(anc, o.systematic_resample(w, u))
+    np.testing.assert_array_equal(anc, c_oracle.systematic(w, u))
+
+
+def test_count_below_matches_positions():
+    rng = np.random.default_rng(1)
+    for N in (1, 7, 1000, 1 << 20):
+        u = float(rng.uniform())
+        pos = (u + np.arange(N)) / float(N)
+        for c in [0, 1, 1 << 51, (1 << 52) - 1, 1 << 52] + [int(x) for x in rng.integers(0, 1 << 52, 20)]:
+            assert hs.count_below(u, N, c) == int((pos < np.ldexp(float(c), -52)).sum())
