@@ -215,7 +215,7 @@ def run_ours(args):
     common = dict(init_covariance=P["init_covariance"], motion_covariance=P["motion_covariance"],
                   resampling_noise_covariance=P["resampling_noise_covariance"],
                   measurement_std=P["measurement_std"], range_min=world.RANGE_MIN, range_max=world.RANGE_MAX,
-                  init_mean=traj.truth, seed=4)
+                  init_mean=traj.truth, seed=4, coarse_level=int(os.environ.get("AUVPF_COARSE_LEVEL", "-1"), 0))
     if G == 1:
         pf = ParticleFilter(particle_count=M, device=local_rank, **common)
         filt = pf

@@ -92,7 +92,10 @@ struct auvpf_handle {
     bool have_norm = false;
 
     // map / sensor
-    float *dem_z = nullptr, *mip = nullptr, *beams = nullptr, *meas = nullptr;
+    float *dem_z = nullptr, *mip = nullptr, *mip_hi = nullptr, *beams = nullptr, *meas = nullptr;
+    float *beam_aux = nullptr;   // [2B]: |sin th|, 1/|sin th|
+    int *beam_order = nullptr;   // [32 * chunk]
+    FanParams fan{};
     DemView dem{};
     bool have_dem = false;
     int B = 0;
@@ -617,7 +620,7 @@ int auvpf_destroy(auvpf_handle *h)
     void *bufs[] = {h->logw,    h->cdf,   h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
                     h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->status,  h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
-                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas};
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -656,24 +659,44 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->dem_z);
     cudaFree(h->mip);
-    h->dem_z = h->mip = nullptr;
+    cudaFree(h->mip_hi);
+    h->dem_z = h->mip = h->mip_hi = nullptr;
     h->have_dem = false;
     const size_t n = (size_t)H * W;
-    CU(cudaMalloc(&h->dem_z, n * sizeof(float)));
-    CU(cudaMemcpyAsync(h->dem_z, z, n * sizeof(float), is_device_ptr(z) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                       h->stream));
-    // coarse level: blocks of about 4 m unless the caller chose
-    int shift = h->cfg.coarse_level;
-    if (shift < 0) {
-        shift = (int)std::lround(std::log2(4.0 / res));
+    const int pitch = W + 2;
+    const size_t n_pad = (size_t)(H + 2) * pitch;
+    const float *src = nullptr;
+    {
+        int rc0 = stage_in(h, S_IN0, z, n, &src);
+        if (rc0) return rc0;
     }
-    if (shift < 1) shift = 1;
-    if (shift > 8) shift = 8;
-    // build levels 1..shift
-    float *prev = nullptr;
-    int pH = 0, pW = 0;
+    CU(cudaMalloc(&h->dem_z, n_pad * sizeof(float)));
+    {
+        dim3 tb(32, 8), gr((W + 2 + tb.x - 1) / tb.x, (H + 2 + tb.y - 1) / tb.y);
+        k_pad_dem<<<gr, tb, 0, h->stream>>>(src, H, W, h->dem_z);
+        CU(cudaGetLastError());
+    }
+    const float *z00 = h->dem_z + pitch + 1;   // vertex (0, 0) inside the padding
+    // max-mip levels used for skipping: a finer one (blocks of about 2 m) and a coarser one
+    // (about 16 m) unless the caller chose: coarse_level = lo | (hi << 8), hi == 0 -> one level
+    int lo, hi;
+    if (h->cfg.coarse_level < 0) {
+        lo = (int)std::lround(std::log2(2.0 / res));
+        if (lo < 1) lo = 1;
+        hi = lo + 3;
+    } else {
+        lo = h->cfg.coarse_level & 0xff;
+        hi = (h->cfg.coarse_level >> 8) & 0xff;
+    }
+    if (lo < 1) lo = 1;
+    if (lo > 10) lo = 10;
+    if (hi > 12) hi = 12;
+    if (hi <= lo) hi = 0;
+    const int top = hi ? hi : lo;
+    float *prev = nullptr, *lvl_lo = nullptr, *lvl_hi = nullptr;
+    int pH = 0, pW = 0, loH = 0, loW = 0, hiH = 0, hiW = 0;
     dim3 tb(32, 8);
-    for (int L = 1; L <= shift; ++L) {
+    for (int L = 1; L <= top; ++L) {
         int S = 1 << L;
         int oH = (H - 1 + S - 1) / S, oW = (W - 1 + S - 1) / S;
         if (oH < 1) oH = 1;
@@ -681,18 +704,21 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
         float *lvl;
         CU(cudaMalloc(&lvl, (size_t)oH * oW * sizeof(float)));
         dim3 gr((oW + tb.x - 1) / tb.x, (oH + tb.y - 1) / tb.y);
-        if (L == 1) k_mip_level1<<<gr, tb, 0, h->stream>>>(h->dem_z, H, W, lvl, oH, oW);
+        if (L == 1) k_mip_level1<<<gr, tb, 0, h->stream>>>(z00, pitch, H, W, lvl, oH, oW);
         else k_mip_down<<<gr, tb, 0, h->stream>>>(prev, pH, pW, lvl, oH, oW);
         CU(cudaGetLastError());
-        if (prev) {
+        if (prev && prev != lvl_lo) {
             CU(cudaStreamSynchronize(h->stream));
             cudaFree(prev);
         }
         prev = lvl;
         pH = oH;
         pW = oW;
+        if (L == lo) { lvl_lo = lvl; loH = oH; loW = oW; }
+        if (L == hi) { lvl_hi = lvl; hiH = oH; hiW = oW; }
     }
-    h->mip = prev;
+    h->mip = lvl_lo;
+    h->mip_hi = lvl_hi;
     // global maximum height
     int *d_max;
     void *tmp;
@@ -701,25 +727,40 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
     d_max = static_cast<int *>(tmp);
     int init = 0x80000000;   // ordered encoding below every float
     CU(cudaMemcpyAsync(d_max, &init, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    k_max_f32<<<296, 256, 0, h->stream>>>(h->dem_z, (int64_t)n, d_max);
+    k_max_f32<<<296, 256, 0, h->stream>>>(h->dem_z, (int64_t)n_pad, d_max);
     int mx;
     CU(cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     mx = mx >= 0 ? mx : mx ^ 0x7FFFFFFF;
     float zmax;
     memcpy(&zmax, &mx, sizeof zmax);
+    // Lipschitz constant of the surface (validity of the fan sweep)
+    init = 0;
+    CU(cudaMemcpyAsync(d_max, &init, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    k_max_slope<<<296, 256, 0, h->stream>>>(z00, pitch, H, W, (float)(1.0 / res), d_max);
+    CU(cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    float max_slope;
+    memcpy(&max_slope, &mx, sizeof max_slope);
 
     DemView &d = h->dem;
-    d.z = h->dem_z;
-    d.mip = h->mip;
+    d.z = z00;
     d.W = W;
     d.H = H;
-    d.mipW = pW;
-    d.mipH = pH;
-    d.shift = shift;
-    d.inv_res = (float)(1.0 / res);
+    d.pitch = pitch;
+    d.mip[0] = lvl_lo;
+    d.mipW[0] = loW;
+    d.mipH[0] = loH;
+    d.shift[0] = lo;
+    d.mip[1] = lvl_hi ? lvl_hi : lvl_lo;
+    d.mipW[1] = lvl_hi ? hiW : loW;
+    d.mipH[1] = lvl_hi ? hiH : loH;
+    d.shift[1] = lvl_hi ? hi : lo;
+    d.n_levels = lvl_hi ? 2 : 1;
     d.range_max = (float)h->cfg.range_max;
     d.zmax = zmax;
+    d.max_slope = max_slope * 1.0001f + 1e-6f;
+    d.res = (float)res;
     d.x0 = x0;
     d.y0 = y0;
     d.inv_res_d = 1.0 / res;
@@ -730,7 +771,7 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
     cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, h->device);
     cudaDeviceGetAttribute(&win_max, cudaDevAttrMaxAccessPolicyWindowSize, h->device);
     if (persist_max > 0 && win_max > 0) {
-        size_t bytes = std::min(n * sizeof(float), (size_t)win_max);
+        size_t bytes = std::min(n_pad * sizeof(float), (size_t)win_max);
         size_t carve = std::min(bytes, (size_t)persist_max);
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
         cudaStreamAttrValue at{};
@@ -747,17 +788,36 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
 
 int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
 {
-    if (!h || !dirs_xyz || B <= 0 || B > 8192) return fail(AUVPF_ERR_BADARG, "bad beam table");
+    if (!h || !dirs_xyz || B <= 0 || B > 4096) return fail(AUVPF_ERR_BADARG, "bad beam table (1..4096 beams)");
     Guard g(h);
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(h->beams);
     cudaFree(h->meas);
-    h->beams = h->meas = nullptr;
+    cudaFree(h->beam_aux);
+    cudaFree(h->beam_order);
+    h->beams = h->meas = h->beam_aux = nullptr;
+    h->beam_order = nullptr;
+    h->B = 0;
+    std::vector<float> host(3 * (size_t)B);
+    CU(cudaMemcpy(host.data(), dirs_xyz, sizeof(float) * 3 * B,
+                  is_device_ptr(dirs_xyz) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+    // host-side analysis: planar sorted fan? per-lane sweep order (auvpf_fan.h)
+    FanPlan plan = plan_fan(host.data(), B);
+    std::vector<float> aux(2 * (size_t)B);
+    for (int b = 0; b < B; ++b) {
+        aux[b] = plan.s[b];
+        aux[B + b] = plan.inv_s[b];
+    }
     CU(cudaMalloc(&h->beams, sizeof(float) * 3 * B));
     CU(cudaMalloc(&h->meas, sizeof(float) * (size_t)B * h->F));
-    CU(cudaMemcpyAsync(h->beams, dirs_xyz, sizeof(float) * 3 * B,
-                       is_device_ptr(dirs_xyz) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMalloc(&h->beam_aux, sizeof(float) * 2 * B));
+    CU(cudaMalloc(&h->beam_order, sizeof(int) * plan.order.size()));
+    CU(cudaMemcpy(h->beams, host.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->beam_aux, aux.data(), sizeof(float) * 2 * B, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->beam_order, plan.order.data(), sizeof(int) * plan.order.size(), cudaMemcpyHostToDevice));
+    h->fan.planar = plan.planar ? 1 : 0;
+    h->fan.chunk = plan.chunk;
+    for (int a = 0; a < 3; ++a) h->fan.c0[a] = plan.c0[a];
     h->B = B;
     return AUVPF_OK;
 }
@@ -893,9 +953,10 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
     const double var = h->cfg.meas_std * h->cfg.meas_std;
     {
         Prof pr(h, AUVPF_K_UPDATE_MBES);
-        const size_t smem = sizeof(float) * 4 * h->B;
+        const size_t smem = sizeof(float) * 6 * h->B + sizeof(int) * 32 * h->fan.chunk;
         k_update_mbes<<<grid1(h->M, kMbesWarps, h->F), kMbesWarps * 32, smem, h->stream>>>(
-            h->st[h->cur], h->M, h->frame, h->dem, h->beams, h->meas, h->B, (float)h->cfg.range_min,
+            h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beams, h->beam_aux, h->beam_order, h->meas, h->B,
+            (float)h->cfg.range_min,
             (float)(-0.5 / var), (float)std::log(h->cfg.meas_std * std::sqrt(2.0 * kPi)), h->logw);
         LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
         CU(cudaGetLastError());
@@ -916,8 +977,8 @@ int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges
     if ((rc = stage_out(h, S_OUT0, ranges_out, (size_t)n * h->B, &od))) return rc;
     {
         Prof pr(h, AUVPF_K_OTHER);
-        k_raycast_poses<<<grid1(n, kMbesWarps, 1), kMbesWarps * 32, 0, h->stream>>>(pd, n, h->frame, h->dem, h->beams,
-                                                                                   h->B, od);
+        k_raycast_poses<<<grid1(n, kMbesWarps, 1), kMbesWarps * 32, 0, h->stream>>>(
+            pd, n, h->frame, h->dem, h->fan, h->beams, h->beam_aux, h->beam_order, h->B, od);
         LAUNCHED(h, AUVPF_K_OTHER, 1);
         CU(cudaGetLastError());
     }

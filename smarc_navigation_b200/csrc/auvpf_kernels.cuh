@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "auvpf_fan.h"
 #include "auvpf_math.cuh"
 
 namespace auvpf {
@@ -214,18 +215,78 @@ k_update_gps(StateView s, int64_t M, FrameParams fp, const double *gps_xy, float
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused raycast + beam-range log-likelihood (a3 + a4).  One warp per particle, lanes over
-// beams, warp-shuffle reduction; beams (dir + measured range) staged in shared memory.
+// Fused raycast + beam-range log-likelihood (a3 + a4).  One warp per particle; each lane owns a
+// chunk of ADJACENT beams and sweeps it outward from the fan centre (auvpf_math.cuh "Fan
+// sweep"): the first beam of a chunk is a full hierarchical traversal, every later beam starts
+// at the lateral distance its inner neighbour was found clear to and is resolved by a walk
+// of one or two cells.  Log-likelihood by warp-shuffle reduction over the lanes' partial sums.
 // The DEM is read through the read-only path; at the benchmark configs the footprint of a
 // particle cloud is L1/L2 resident.
 constexpr int kMbesWarps = 8;
+constexpr int kExactThreshold = 12;   // run the postponed exact-cell tests once this many lanes wait
+
+struct FanParams {
+    float c0[3];     // fan centre direction, sensor frame
+    int planar;      // beams form a sorted planar fan
+    int chunk;       // beams per lane
+};
+
+// Warp-cooperative traversal driver: MUST be called by all 32 lanes of a converged warp.
+// Every iteration all unresolved lanes do one uniform node step; lanes whose ray reached a cell
+// that cannot be skipped park (pending) until enough lanes are parked -- or nobody else can
+// make progress -- and then run the exact two-triangle test together.
+__device__ __forceinline__ float raycast_warp(const DemView &m, const Ray &r, bool valid, float t_lo)
+{
+    Trav s;
+    float range = m.range_max;
+    bool active = valid && trav_init(s, m, r, range, t_lo);
+    bool pending = false;
+    while (__any_sync(0xffffffffu, active)) {
+        if (active && !pending) {
+            const int res = trav_step(s, m, r);
+            if (res == kMiss) {
+                range = m.range_max;
+                active = false;
+            } else if (res == kPending)
+                pending = true;
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, pending);
+        if (pm) {
+            const unsigned wm = __ballot_sync(0xffffffffu, active && !pending);
+            if (wm == 0u || __popc(pm) >= kExactThreshold) {
+                if (pending) {
+                    if (trav_exact(s, m, r, range)) active = false;
+                    pending = false;
+                }
+            }
+        }
+    }
+    return range;
+}
+
+// One lane's k-th beam of its chunk.  `valid` lanes need a range; p_clear carries the sweep.
+__device__ __forceinline__ float fan_ray(const DemView &dem, const Ray &ray, bool valid, bool full, float inv_s,
+                                         float s_b, float &p_clear)
+{
+    float t_lo = 0.f;
+    if (valid && !full) t_lo = sweep_bound(p_clear, inv_s, dem.res);
+    const bool want_full = valid && !(t_lo > 0.f);
+    float range;
+    if (__any_sync(0xffffffffu, want_full))       // someone starts from the sensor: traverse together
+        range = raycast_warp(dem, ray, valid, t_lo);
+    else
+        range = valid ? raycast_from(dem, ray, t_lo) : dem.range_max;
+    if (valid) p_clear = range * s_b;             // a miss (range_max) leaves the whole ray clear
+    return range;
+}
 
 __global__ void __launch_bounds__(kMbesWarps * 32)
-k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, const float *__restrict__ beam_dirs,
-              const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,
-              float log_norm_per_beam, float *__restrict__ logw)
+k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan, const float *__restrict__ beam_dirs,
+              const float *__restrict__ beam_aux, const int *__restrict__ order, const float *__restrict__ meas, int B,
+              float range_min, float neg_half_inv_var, float log_norm_per_beam, float *__restrict__ logw)
 {
-    extern __shared__ float sm[];   // [4*B]: dx, dy, dz, measured range (NaN = skip)
+    extern __shared__ float sm[];   // [6*B] dx, dy, dz, measured range (NaN = skip), |sin th|, 1/|sin th|; then order
+    int *s_ord = reinterpret_cast<int *>(sm + 6 * B);
     __shared__ int s_valid;
     const int f = blockIdx.y;
     if (threadIdx.x == 0) s_valid = 0;
@@ -238,8 +299,11 @@ k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, const float *
         float r = meas[(size_t)f * B + b];
         bool ok = isfinite(r) && r >= range_min && r <= dem.range_max;
         sm[3 * B + b] = ok ? r : __int_as_float(0x7fc00000);
+        sm[4 * B + b] = beam_aux[b];
+        sm[5 * B + b] = beam_aux[B + b];
         nv += ok ? 1 : 0;
     }
+    for (int k = threadIdx.x; k < 32 * fan.chunk; k += blockDim.x) s_ord[k] = order[k];
     if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
     const float lognorm = -(float)s_valid * log_norm_per_beam;
@@ -253,22 +317,27 @@ k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, const float *
     int ix0, iy0;
     float lx0, ly0;
     origin_cell(dem, p, ix0, iy0, lx0, ly0);
-    float acc = 0.f;
-    for (int b = lane; b < B; b += 32) {
-        float rm = sm[3 * B + b];
-        if (rm != rm) continue;     // invalid measured beam: skipped, no raycast needed
+    const bool sweep_ok = fan.planar && fan_sweep_valid(dem, p, R, fan.c0);
+    float acc = 0.f, p_clear = 0.f;
+    for (int k = 0; k < fan.chunk; ++k) {           // warp-uniform trip count
+        const int o = s_ord[lane * fan.chunk + k];
+        const int b = o >= 0 ? (o & (kOrdFull - 1)) : 0;
+        const float rm = sm[3 * B + b];
+        const bool valid = o >= 0 && rm == rm;      // invalid measured beam: no raycast needed
+        const bool full = (o & kOrdFull) != 0 || !sweep_ok;
         Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, sm[b], sm[B + b], sm[2 * B + b]);
-        float e = rm - raycast_one(dem, ray);
-        acc = fmaf(e, e, acc);
+        const float e = rm - fan_ray(dem, ray, valid, full, sm[5 * B + b], sm[4 * B + b], p_clear);
+        if (valid) acc = fmaf(e, e, acc);
     }
     acc = warp_sum(acc);
     if (lane == 0) logw[row] = fmaf(neg_half_inv_var, acc, lognorm);
 }
 
-// Parity probe: expected ranges for explicit poses, (n, B) float32.
+// Parity probe: expected ranges for explicit poses, (n, B) float32; same traversal as above.
 __global__ void __launch_bounds__(kMbesWarps * 32)
-k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, DemView dem,
-                const float *__restrict__ beam_dirs, int B, float *__restrict__ out)
+k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, DemView dem, FanParams fan,
+                const float *__restrict__ beam_dirs, const float *__restrict__ beam_aux,
+                const int *__restrict__ order, int B, float *__restrict__ out)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * kMbesWarps + warp;
@@ -280,16 +349,32 @@ k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, Dem
     int ix0, iy0;
     float lx0, ly0;
     origin_cell(dem, p, ix0, iy0, lx0, ly0);
-    for (int b = lane; b < B; b += 32) {
+    const bool sweep_ok = fan.planar && fan_sweep_valid(dem, p, R, fan.c0);
+    float p_clear = 0.f;
+    for (int k = 0; k < fan.chunk; ++k) {
+        const int o = order[lane * fan.chunk + k];
+        const int b = o >= 0 ? (o & (kOrdFull - 1)) : 0;
+        const bool valid = o >= 0;
+        const bool full = (o & kOrdFull) != 0 || !sweep_ok;
         Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, beam_dirs[3 * b], beam_dirs[3 * b + 1], beam_dirs[3 * b + 2]);
-        out[(size_t)i * B + b] = raycast_one(dem, ray);
+        const float rr = fan_ray(dem, ray, valid, full, beam_aux[B + b], beam_aux[b], p_clear);
+        if (valid) out[(size_t)i * B + b] = rr;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Max-mip pyramid.  Level 1 block (bi,bj) = max over vertices [2bi, 2bi+2] x [2bj, 2bj+2] (closed
 // footprint of a 2x2-cell block); level L+1 = max of 2x2 children.
-__global__ void k_mip_level1(const float *z, int H, int W, float *out, int oH, int oW)
+// Copy an H x W DEM into the padded layout: (H+2) x (W+2) with a replicated one-vertex border.
+__global__ void k_pad_dem(const float *src, int H, int W, float *dst)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x - 1, i = blockIdx.y * blockDim.y + threadIdx.y - 1;
+    if (j > W || i > H) return;
+    int si = min(max(i, 0), H - 1), sj = min(max(j, 0), W - 1);
+    dst[(size_t)(i + 1) * (W + 2) + (j + 1)] = src[(size_t)si * W + sj];
+}
+
+__global__ void k_mip_level1(const float *z, int pitch, int H, int W, float *out, int oH, int oW)
 {
     int bj = blockIdx.x * blockDim.x + threadIdx.x, bi = blockIdx.y * blockDim.y + threadIdx.y;
     if (bj >= oW || bi >= oH) return;
@@ -297,7 +382,7 @@ __global__ void k_mip_level1(const float *z, int H, int W, float *out, int oH, i
     for (int di = 0; di <= 2; ++di)
         for (int dj = 0; dj <= 2; ++dj) {
             int i = min(2 * bi + di, H - 1), j = min(2 * bj + dj, W - 1);
-            m = fmaxf(m, z[(size_t)i * W + j]);
+            m = fmaxf(m, z[(size_t)i * pitch + j]);
         }
     out[(size_t)bi * oW + bj] = m;
 }
@@ -313,6 +398,22 @@ __global__ void k_mip_down(const float *in, int iH, int iW, float *out, int oH, 
             if (i < iH && j < iW) m = fmaxf(m, in[(size_t)i * iW + j]);
         }
     out[(size_t)bi * oW + bj] = m;
+}
+
+// largest triangle gradient norm of the DEM (two triangles per cell, diagonal (i,j)->(i+1,j+1))
+__global__ void k_max_slope(const float *z, int pitch, int H, int W, float inv_res, int *out_ordered)
+{
+    float m = 0.f;
+    const int64_t n = (int64_t)(H - 1) * (W - 1);
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        int i = (int)(c / (W - 1)), j = (int)(c % (W - 1));
+        const float *p = z + (size_t)i * pitch + j;
+        float z00 = p[0], z01 = p[1], z10 = p[pitch], z11 = p[pitch + 1];
+        float g1 = hypotf(z01 - z00, z11 - z01), g2 = hypotf(z11 - z10, z10 - z00);
+        m = fmaxf(m, fmaxf(g1, g2) * inv_res);
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(out_ordered, float_to_ordered(m));
 }
 
 __global__ void k_max_f32(const float *in, int64_t n, int *out_ordered)

@@ -7,6 +7,7 @@
 // only ever runs the __device__ instantiations.
 #pragma once
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 
 #if defined(__CUDACC__)
@@ -227,15 +228,31 @@ AUVPF_HD void particle_frame(const FrameParams &f, double x, double y, float z, 
 
 // ---------------------------------------------------------------------------------------------
 // Heightfield raycast (spec: oracle/c/auvpf_oracle.c RAYCAST SPEC).
+//
+// The DEM is stored with a one-vertex replicated border (pitch W + 2) so that a cell index
+// one outside the map can be read without going out of bounds; `z` points at vertex (0, 0)
+// inside the padding.
+//
+// Traversal = ONE uniform loop of "node steps".  A node is either a max-mip block (levels
+// lv[0] < lv[1] of the pyramid, block = 2^shift cells, value = max over the block's closed
+// vertex footprint) or, below lv[0], a single cell (max of its 4 corners, computed on the
+// fly).  A step computes the node's exit time; if the ray stays above the node's maximum
+// over [t, t_exit] the node is skipped (and the level raised again when a coarser boundary is
+// crossed), otherwise the level is lowered; a cell that cannot be skipped becomes PENDING for
+// the exact two-triangle test.  Because the level is data, not control flow, all lanes of a
+// warp execute the same instructions whatever level each ray is at.
+constexpr int kMaxLevels = 2;
+
 struct DemView {
-    const float *z;      // H x W vertex heights
-    const float *mip;    // coarse max-mip level: mipH x mipW block maxima (closed vertex footprint)
-    int W, H;
-    int mipW, mipH;
-    int shift;           // block = 2^shift cells
-    float inv_res;
+    const float *z;      // vertex (0,0); row pitch `pitch` floats; rows/cols -1 .. H / W are readable
+    int W, H, pitch;
+    const float *mip[kMaxLevels];   // mip[0] = finer block level, mip[1] = coarser (or unused)
+    int mipW[kMaxLevels], mipH[kMaxLevels], shift[kMaxLevels];
+    int n_levels;        // 1 or 2
     float range_max;
     float zmax;          // global maximum height
+    float max_slope;     // largest triangle gradient norm |grad h| (Lipschitz constant of the surface)
+    float res;           // cell size [m]
     double x0, y0, inv_res_d;
 };
 
@@ -246,236 +263,341 @@ struct Ray {
     float dgx, dgy, dz;  // direction in grid units / metres
 };
 
-AUVPF_HD float dem_at(const DemView &m, int row, int col)
+AUVPF_HD float ldg_f(const float *p)
 {
 #if defined(__CUDA_ARCH__)
-    return __ldg(m.z + (size_t)row * m.W + col);
+    return __ldg(p);
 #else
-    return m.z[(size_t)row * m.W + col];
+    return *p;
+#endif
+}
+
+AUVPF_HD float rcp_rn(float x)
+{
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);      // correctly rounded, same value as the host's 1.0f / x
+#else
+    return 1.0f / x;
+#endif
+}
+
+AUVPF_HD float fast_div(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
 #endif
 }
 
 AUVPF_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// General surface evaluation at local grid point (px, py).
-AUVPF_HD float surf_local(const DemView &m, const Ray &r, float px, float py)
-{
-    int cx = clampi(r.ix0 + (int)floorf(px), 0, m.W - 2);
-    int cy = clampi(r.iy0 + (int)floorf(py), 0, m.H - 2);
-    float u = px - (float)(cx - r.ix0), v = py - (float)(cy - r.iy0);
-    float z00 = dem_at(m, cy, cx), z01 = dem_at(m, cy, cx + 1);
-    float z10 = dem_at(m, cy + 1, cx), z11 = dem_at(m, cy + 1, cx + 1);
-    return (u >= v) ? z00 + u * (z01 - z00) + v * (z11 - z01) : z00 + u * (z11 - z10) + v * (z10 - z00);
-}
+constexpr float kBigT = 3.0e38f;
+constexpr float kSkipMargin = 2.0e-3f;   // [m] slack that keeps max skipping conservative in fp32
 
-// Crossing walker over the three line families x = k, y = k, x - y = k.
-struct Walker {
-    float tx, ty, td;    // next crossing time of each family
-    float kx, ky, kd;    // its line index (local grid units), kept as float
-    float sx, sy, sd;    // +-1 step (0 = family never crossed)
-    float ix, iy, id;    // 1 / derivative of the family coordinate
-    float c0d;           // lx0 - ly0
+struct Trav {
+    // per-ray constants
+    float ix, iy;        // 1 / dgx, 1 / dgy (0 when the ray never crosses that family)
+    float te;            // end of the clipped ray
+    int bx, by;          // 1 when moving in +x / +y
+    // state
+    float t;             // entry time into the current node
+    int cx, cy;          // absolute level-0 cell entered at t
+    int li;              // level index: n_levels-1 .. 0 = mip levels, -1 = cells
+    // pending exact test (valid when the step returned kPending)
+    float t_out;
+    float z00, z01, z10, z11;
 };
 
-constexpr float kBigT = 3.0e38f;
+enum StepResult : int { kContinue = 0, kPending = 1, kMiss = 2 };
 
-AUVPF_HD void walker_setup(Walker &w, const Ray &r)
+// Clip the ray and place the traversal at its start.  Returns false (with `range` set) when
+// the ray is resolved without traversal.  `t_lo` is a CERTIFIED clear prefix: the caller
+// guarantees f > 0 on [0, t_lo) (fan sweep, see sweep_bound); 0 = none.
+AUVPF_HD bool trav_init(Trav &s, const DemView &m, const Ray &r, float &range, float t_lo = 0.f)
 {
-    float dd = r.dgx - r.dgy;
-    w.sx = r.dgx > 0.f ? 1.f : (r.dgx < 0.f ? -1.f : 0.f);
-    w.sy = r.dgy > 0.f ? 1.f : (r.dgy < 0.f ? -1.f : 0.f);
-    w.sd = dd > 0.f ? 1.f : (dd < 0.f ? -1.f : 0.f);
-    w.ix = w.sx != 0.f ? 1.0f / r.dgx : 0.f;
-    w.iy = w.sy != 0.f ? 1.0f / r.dgy : 0.f;
-    w.id = w.sd != 0.f ? 1.0f / dd : 0.f;
-    w.c0d = r.lx0 - r.ly0;
-}
-
-AUVPF_HD void family_init(float coord, float c0, float s, float inv, float t_from, float &k, float &t)
-{
-    if (s == 0.f) {
-        k = 0.f;
-        t = kBigT;
-        return;
-    }
-    k = s > 0.f ? floorf(coord) + 1.f : ceilf(coord) - 1.f;
-    t = (k - c0) * inv;
-    // a crossing that rounds to <= t_from is the one we are standing on: move on
-    for (int g = 0; g < 3 && t <= t_from; ++g) {
-        k += s;
-        t = (k - c0) * inv;
-    }
-}
-
-// (Re)aim the walker at the first crossings strictly after t_from.
-AUVPF_HD void walker_seek(Walker &w, const Ray &r, float t_from)
-{
-    float px = r.lx0 + t_from * r.dgx, py = r.ly0 + t_from * r.dgy;
-    family_init(px, r.lx0, w.sx, w.ix, t_from, w.kx, w.tx);
-    family_init(py, r.ly0, w.sy, w.iy, t_from, w.ky, w.ty);
-    family_init(px - py, w.c0d, w.sd, w.id, t_from, w.kd, w.td);
-}
-
-// f = ray height - surface height at the next crossing (<= t_stop); advances the walker.
-// Returns false when the next crossing lies beyond t_stop.
-AUVPF_HD bool walker_next(Walker &w, const DemView &m, const Ray &r, float t_stop, float &t_out, float &f_out)
-{
-    float t = fminf(w.tx, fminf(w.ty, w.td));
-    if (!(t <= t_stop)) return false;
-    float px = r.lx0 + t * r.dgx, py = r.ly0 + t * r.dgy;
-    int row, col, stride;
-    float frac;
-    if (t == w.tx) {                    // vertical grid line x = kx: edge (iy,kx)-(iy+1,kx)
-        int k = (int)w.kx;
-        float fy = floorf(py);
-        col = clampi(r.ix0 + k, 0, m.W - 1);
-        row = clampi(r.iy0 + (int)fy, 0, m.H - 2);
-        frac = py - (float)(row - r.iy0);
-        stride = m.W;
-        w.kx += w.sx;
-        w.tx = (w.kx - r.lx0) * w.ix;
-    } else if (t == w.ty) {             // horizontal grid line y = ky: edge (ky,ix)-(ky,ix+1)
-        int k = (int)w.ky;
-        float fx = floorf(px);
-        row = clampi(r.iy0 + k, 0, m.H - 1);
-        col = clampi(r.ix0 + (int)fx, 0, m.W - 2);
-        frac = px - (float)(col - r.ix0);
-        stride = 1;
-        w.ky += w.sy;
-        w.ty = (w.ky - r.ly0) * w.iy;
-    } else {                            // diagonal x - y = kd: edge (iy,ix)-(iy+1,ix+1)
-        int k = (int)w.kd;
-        float fx = floorf(px);
-        col = clampi(r.ix0 + (int)fx, 0, m.W - 2);
-        row = clampi(r.iy0 + ((int)fx - k), 0, m.H - 2);
-        frac = px - (float)(col - r.ix0);
-        stride = m.W + 1;
-        w.kd += w.sd;
-        w.td = (w.kd - w.c0d) * w.id;
-    }
-    const float *p = m.z + (size_t)row * m.W + col;
-#if defined(__CUDA_ARCH__)
-    float za = __ldg(p), zb = __ldg(p + stride);
-#else
-    float za = p[0], zb = p[stride];
-#endif
-    float h = za + frac * (zb - za);
-    t_out = t;
-    f_out = (r.oz + t * r.dz) - h;
-    return true;
-}
-
-AUVPF_HD float mip_at(const DemView &m, int by, int bx)
-{
-#if defined(__CUDA_ARCH__)
-    return __ldg(m.mip + (size_t)by * m.mipW + bx);
-#else
-    return m.mip[(size_t)by * m.mipW + bx];
-#endif
-}
-
-constexpr float kSkipMargin = 2.0e-3f;   // [m] slack that keeps max-mip skipping conservative in fp32
-
-// First-hit range of one ray; misses return range_max.
-AUVPF_HD float raycast_one(const DemView &m, const Ray &r)
-{
+    s.ix = r.dgx != 0.f ? rcp_rn(r.dgx) : 0.f;
+    s.iy = r.dgy != 0.f ? rcp_rn(r.dgy) : 0.f;
+    s.bx = r.dgx > 0.f ? 1 : 0;
+    s.by = r.dgy > 0.f ? 1 : 0;
     float ts = 0.f, te = m.range_max;
-    // clip to the map footprint (local coordinates)
+    range = m.range_max;
     {
         float lo = -(float)r.ix0, hi = (float)(m.W - 1 - r.ix0);
         if (r.dgx != 0.f) {
-            float inv = 1.0f / r.dgx;
-            float t1 = (lo - r.lx0) * inv, t2 = (hi - r.lx0) * inv;
+            float t1 = (lo - r.lx0) * s.ix, t2 = (hi - r.lx0) * s.ix;
             ts = fmaxf(ts, fminf(t1, t2));
             te = fminf(te, fmaxf(t1, t2));
         } else if (r.lx0 < lo || r.lx0 > hi)
-            return m.range_max;
+            return false;
         lo = -(float)r.iy0;
         hi = (float)(m.H - 1 - r.iy0);
         if (r.dgy != 0.f) {
-            float inv = 1.0f / r.dgy;
-            float t1 = (lo - r.ly0) * inv, t2 = (hi - r.ly0) * inv;
+            float t1 = (lo - r.ly0) * s.iy, t2 = (hi - r.ly0) * s.iy;
             ts = fmaxf(ts, fminf(t1, t2));
             te = fminf(te, fmaxf(t1, t2));
         } else if (r.ly0 < lo || r.ly0 > hi)
-            return m.range_max;
+            return false;
     }
-    if (!(ts <= te)) return m.range_max;
-
-    // Sample at the clip start: spec says f(ts) <= 0 -> range = ts.
-    float t_prev = ts;
-    float f_prev = (r.oz + ts * r.dz) - surf_local(m, r, r.lx0 + ts * r.dgx, r.ly0 + ts * r.dgy);
-    if (f_prev <= 0.f) return ts;
-
-    // Nothing can be hit above the global maximum height.
-    float t_cur = ts;
-    if (r.oz + ts * r.dz > m.zmax + kSkipMargin) {
-        if (r.dz >= 0.f) return m.range_max;
-        float tz = (m.zmax + kSkipMargin - r.oz) / r.dz;
-        if (tz >= te) return m.range_max;
-        if (tz > t_cur) t_cur = tz;
+    ts = fmaxf(ts, t_lo);
+    if (!(ts <= te)) return false;
+    // nothing can be hit above the global maximum height
+    if (fmaf(ts, r.dz, r.oz) > m.zmax + kSkipMargin) {
+        if (r.dz >= 0.f) return false;
+        float tz = (m.zmax + kSkipMargin - r.oz) * rcp_rn(r.dz);
+        if (tz >= te) return false;
+        ts = fmaxf(ts, tz);
     }
-    bool synced = (t_cur == ts);      // (t_prev, f_prev) is a sample at t_cur?
+    s.te = te;
+    s.t = ts;
+    s.cx = clampi(r.ix0 + (int)floorf(fmaf(ts, r.dgx, r.lx0)), 0, m.W - 2);
+    s.cy = clampi(r.iy0 + (int)floorf(fmaf(ts, r.dgy, r.ly0)), 0, m.H - 2);
+    s.li = t_lo > 0.f ? -1 : m.n_levels - 1;   // a swept ray starts next to its hit: look at cells first
+    return true;
+}
 
-    Walker w;
-    walker_setup(w, r);
-
-    // coarse DDA over max-mip blocks (absolute block indices)
-    const int S = 1 << m.shift;
-    float px = r.lx0 + t_cur * r.dgx, py = r.ly0 + t_cur * r.dgy;
-    int bx = clampi((r.ix0 + (int)floorf(px)) >> m.shift, 0, m.mipW - 1);
-    int by = clampi((r.iy0 + (int)floorf(py)) >> m.shift, 0, m.mipH - 1);
-    const int sbx = r.dgx > 0.f ? 1 : -1, sby = r.dgy > 0.f ? 1 : -1;
-    // local coordinate of the next coarse line ahead of the block, per axis
-    float lxn = (float)(((bx + (sbx > 0 ? 1 : 0)) << m.shift) - r.ix0);
-    float lyn = (float)(((by + (sby > 0 ? 1 : 0)) << m.shift) - r.iy0);
-    const float fS = (float)S;
-    float tcx = w.sx != 0.f ? (lxn - r.lx0) * w.ix : kBigT;
-    float tcy = w.sy != 0.f ? (lyn - r.ly0) * w.iy : kBigT;
-    // standing on (or a hair past) a coarse line: we are already in the next block
-    for (int g = 0; g < 2 && tcx <= t_cur; ++g) { bx += sbx; lxn += sbx * fS; tcx = (lxn - r.lx0) * w.ix; }
-    for (int g = 0; g < 2 && tcy <= t_cur; ++g) { by += sby; lyn += sby * fS; tcy = (lyn - r.ly0) * w.iy; }
-    bool walking = false;             // walker aimed at t_prev?
-
-    while (t_cur < te) {
-        float t_next = fminf(fminf(tcx, tcy), te);
-        int cbx = clampi(bx, 0, m.mipW - 1), cby = clampi(by, 0, m.mipH - 1);
-        float zlow = r.oz + (r.dz < 0.f ? t_next : t_cur) * r.dz;
-        if (zlow > mip_at(m, cby, cbx) + kSkipMargin) {
-            synced = false;           // skipped: no sample carried across
-            walking = false;
+// One node step (see the header comment).  kPending leaves the cell corners and its exit
+// time in `s` for trav_exact; kMiss means the ray ended without a hit.
+AUVPF_HD int trav_step(Trav &s, const DemView &m, const Ray &r)
+{
+    const int li = s.li;
+    const int sh = li < 0 ? 0 : (li == 0 ? m.shift[0] : m.shift[1]);
+    const int nx = s.cx >> sh, ny = s.cy >> sh;
+    const int X = (nx + s.bx) << sh, Y = (ny + s.by) << sh;      // node's far grid lines (absolute)
+    const float tX = s.ix != 0.f ? ((float)(X - r.ix0) - r.lx0) * s.ix : kBigT;
+    const float tY = s.iy != 0.f ? ((float)(Y - r.iy0) - r.ly0) * s.iy : kBigT;
+    const float t_out = fminf(fminf(tX, tY), s.te);
+    float nodemax;
+    if (li >= 0) {
+        const float *mp = li == 0 ? m.mip[0] : m.mip[1];
+        const int mw = li == 0 ? m.mipW[0] : m.mipW[1], mh = li == 0 ? m.mipH[0] : m.mipH[1];
+        nodemax = ldg_f(mp + (size_t)clampi(ny, 0, mh - 1) * mw + clampi(nx, 0, mw - 1));
+    } else {
+        const float *p = m.z + (ptrdiff_t)s.cy * m.pitch + s.cx;
+        s.z00 = ldg_f(p);
+        s.z01 = ldg_f(p + 1);
+        s.z10 = ldg_f(p + m.pitch);
+        s.z11 = ldg_f(p + m.pitch + 1);
+        nodemax = fmaxf(fmaxf(s.z00, s.z01), fmaxf(s.z10, s.z11));
+    }
+    const float zlow = fmaf(r.dz < 0.f ? t_out : s.t, r.dz, r.oz);
+    if (zlow > nodemax + kSkipMargin) {
+        // skip the node
+        if (t_out >= s.te) return kMiss;
+        int ncx, ncy;
+        if (tX <= tY) {
+            ncx = s.bx ? X : X - 1;
+            ncy = s.cy;
+            if (sh > 0) {
+                int c = r.iy0 + (int)floorf(fmaf(t_out, r.dgy, r.ly0));
+                ncy = clampi(c, ny << sh, ((ny + 1) << sh) - 1);    // exit through x: still inside the node's rows
+            }
         } else {
-            if (!synced) {
-                t_prev = t_cur;
-                f_prev = (r.oz + t_cur * r.dz) - surf_local(m, r, r.lx0 + t_cur * r.dgx, r.ly0 + t_cur * r.dgy);
-                if (f_prev <= 0.f) return t_cur;
-                synced = true;
-                walking = false;
-            }
-            if (!walking) {
-                walker_seek(w, r, t_prev);
-                walking = true;
-            }
-            float t, f;
-            while (walker_next(w, m, r, t_next, t, f)) {
-                if (f <= 0.f) return t_prev + (t - t_prev) * (f_prev / (f_prev - f));
-                t_prev = t;
-                f_prev = f;
+            ncy = s.by ? Y : Y - 1;
+            ncx = s.cx;
+            if (sh > 0) {
+                int c = r.ix0 + (int)floorf(fmaf(t_out, r.dgx, r.lx0));
+                ncx = clampi(c, nx << sh, ((nx + 1) << sh) - 1);
             }
         }
-        if (t_next >= te) {
-            if (synced) {             // close the last partial segment at te
-                float f = (r.oz + te * r.dz) - surf_local(m, r, r.lx0 + te * r.dgx, r.ly0 + te * r.dgy);
-                if (f <= 0.f && te > t_prev) return t_prev + (te - t_prev) * (f_prev / (f_prev - f));
+        // raise the level again when a coarser block boundary was crossed
+        int nli = li;
+        if (li + 1 < m.n_levels) {
+            const int ps = li + 1 == 0 ? m.shift[0] : m.shift[1];
+            if (((ncx >> ps) != (s.cx >> ps)) || ((ncy >> ps) != (s.cy >> ps))) {
+                nli = li + 1;
+                if (nli + 1 < m.n_levels) {
+                    const int ps2 = m.shift[1];
+                    if (((ncx >> ps2) != (s.cx >> ps2)) || ((ncy >> ps2) != (s.cy >> ps2))) nli = nli + 1;
+                }
             }
-            break;
         }
-        // step the coarse DDA
-        t_cur = t_next;
-        if (tcx <= tcy) { bx += sbx; lxn += sbx * fS; tcx = (lxn - r.lx0) * w.ix; }
-        else { by += sby; lyn += sby * fS; tcy = (lyn - r.ly0) * w.iy; }
+        s.li = nli;
+        s.cx = clampi(ncx, -1, m.W - 1);
+        s.cy = clampi(ncy, -1, m.H - 1);
+        s.t = t_out;
+        return kContinue;
     }
-    return m.range_max;
+    if (li >= 0) {
+        s.li = li - 1;     // look closer
+        return kContinue;
+    }
+    s.t_out = t_out;
+    return kPending;
+}
+
+AUVPF_HD float tri_height4(float z00, float z01, float z10, float z11, float u, float v)
+{
+    return (u >= v) ? z00 + u * (z01 - z00) + v * (z11 - z01) : z00 + u * (z11 - z10) + v * (z10 - z00);
+}
+
+// Exact two-triangle test of one cell over the ray segment [ta, tb]; (ua,va), (ub,vb) are the
+// segment end points in cell coordinates.  Returns true and the range when f has its first
+// root in the segment (or f(ta) <= 0, spec: range = ta).
+AUVPF_HD bool exact_segment(float z00, float z01, float z10, float z11, float ua, float va, float ub, float vb,
+                            float ta, float tb, const Ray &r, float &range)
+{
+    const float fa = fmaf(ta, r.dz, r.oz) - tri_height4(z00, z01, z10, z11, ua, va);
+    if (fa <= 0.f) {
+        range = ta;
+        return true;
+    }
+    const float fb = fmaf(tb, r.dz, r.oz) - tri_height4(z00, z01, z10, z11, ub, vb);
+    const float ga = ua - va, gb = ub - vb;
+    float t0 = ta, f0 = fa, t1 = tb, f1 = fb;
+    bool hit;
+    if (ga * gb < 0.f) {             // the segment crosses the cell diagonal
+        const float sd = fast_div(ga, ga - gb);
+        const float td = fmaf(sd, tb - ta, ta);
+        const float ud = fmaf(sd, ub - ua, ua);
+        const float fd = fmaf(td, r.dz, r.oz) - fmaf(ud, z11 - z00, z00);
+        if (fd <= 0.f) {
+            t1 = td;
+            f1 = fd;
+            hit = true;
+        } else {
+            t0 = td;
+            f0 = fd;
+            hit = fb <= 0.f;
+        }
+    } else
+        hit = fb <= 0.f;
+    if (hit) range = t1 > t0 ? fmaf(t1 - t0, fast_div(f0, f0 - f1), t0) : t0;
+    return hit;
+}
+
+// Exact test of the pending cell over [s.t, s.t_out].  Returns true with the range when the
+// ray is resolved (hit, or miss at the end of the ray); otherwise advances into the next cell.
+AUVPF_HD bool trav_exact(Trav &s, const DemView &m, const Ray &r, float &range)
+{
+    const float ta = s.t, tb = s.t_out;
+    const float cxl = (float)(s.cx - r.ix0), cyl = (float)(s.cy - r.iy0);
+    const float ua = fmaf(ta, r.dgx, r.lx0) - cxl, va = fmaf(ta, r.dgy, r.ly0) - cyl;
+    const float ub = fmaf(tb, r.dgx, r.lx0) - cxl, vb = fmaf(tb, r.dgy, r.ly0) - cyl;
+    if (exact_segment(s.z00, s.z01, s.z10, s.z11, ua, va, ub, vb, ta, tb, r, range)) return true;
+    if (tb >= s.te) {                // end of the ray: miss
+        range = m.range_max;
+        return true;
+    }
+    // advance into the neighbouring cell (integer step, exact topology)
+    const int X = s.cx + s.bx, Y = s.cy + s.by;
+    const float tX = s.ix != 0.f ? ((float)(X - r.ix0) - r.lx0) * s.ix : kBigT;
+    const float tY = s.iy != 0.f ? ((float)(Y - r.iy0) - r.ly0) * s.iy : kBigT;
+    int ncx = s.cx, ncy = s.cy;
+    if (tX <= tY) ncx = s.bx ? X : X - 1;
+    else ncy = s.by ? Y : Y - 1;
+    int nli = -1;
+    const int ps = m.shift[0];
+    if (((ncx >> ps) != (s.cx >> ps)) || ((ncy >> ps) != (s.cy >> ps))) {
+        nli = 0;
+        if (m.n_levels > 1) {
+            const int ps2 = m.shift[1];
+            if (((ncx >> ps2) != (s.cx >> ps2)) || ((ncy >> ps2) != (s.cy >> ps2))) nli = 1;
+        }
+    }
+    s.li = nli;
+    s.cx = clampi(ncx, -1, m.W - 1);
+    s.cy = clampi(ncy, -1, m.H - 1);
+    s.t = tb;
+    return false;
+}
+
+// Tight cell-by-cell walk for a ray that starts next to its hit (fan sweep): incremental
+// DDA over cells, 4-corner max pre-check, exact test.  Gives up after kNearCells cells and
+// hands the state back to the hierarchical traversal.
+constexpr int kNearCells = 12;
+
+AUVPF_HD bool near_walk(Trav &s, const DemView &m, const Ray &r, float &range)
+{
+    float t = s.t;
+    int cx = s.cx, cy = s.cy;
+    float cxl = (float)(cx - r.ix0), cyl = (float)(cy - r.iy0);
+    const float sxf = s.bx ? 1.f : -1.f, syf = s.by ? 1.f : -1.f;
+    const float bxf = s.bx ? 1.f : 0.f, byf = s.by ? 1.f : 0.f;
+    const int sxi = s.bx ? 1 : -1, syi = s.by ? 1 : -1;
+    float tx = s.ix != 0.f ? ((cxl + bxf) - r.lx0) * s.ix : kBigT;
+    float ty = s.iy != 0.f ? ((cyl + byf) - r.ly0) * s.iy : kBigT;
+    const float *p = m.z + (ptrdiff_t)cy * m.pitch + cx;
+    for (int n = 0; n < kNearCells; ++n) {
+        const float t_out = fminf(fminf(tx, ty), s.te);
+        const float z00 = ldg_f(p), z01 = ldg_f(p + 1), z10 = ldg_f(p + m.pitch), z11 = ldg_f(p + m.pitch + 1);
+        const float zmax4 = fmaxf(fmaxf(z00, z01), fmaxf(z10, z11));
+        const float zlow = fmaf(r.dz < 0.f ? t_out : t, r.dz, r.oz);
+        if (!(zlow > zmax4 + kSkipMargin)) {
+            const float ua = fmaf(t, r.dgx, r.lx0) - cxl, va = fmaf(t, r.dgy, r.ly0) - cyl;
+            const float ub = fmaf(t_out, r.dgx, r.lx0) - cxl, vb = fmaf(t_out, r.dgy, r.ly0) - cyl;
+            if (exact_segment(z00, z01, z10, z11, ua, va, ub, vb, t, t_out, r, range)) return true;
+        }
+        if (t_out >= s.te) {
+            range = m.range_max;
+            return true;
+        }
+        if (tx <= ty) {
+            cxl += sxf;
+            cx += sxi;
+            p += sxi;
+            tx = ((cxl + bxf) - r.lx0) * s.ix;
+        } else {
+            cyl += syf;
+            cy += syi;
+            p += syi * m.pitch;
+            ty = ((cyl + byf) - r.ly0) * s.iy;
+        }
+        t = t_out;
+        if (cx < 0 || cy < 0 || cx > m.W - 2 || cy > m.H - 2) break;   // left the map by rounding: let the generic path finish
+    }
+    s.t = t;
+    s.cx = clampi(cx, -1, m.W - 1);
+    s.cy = clampi(cy, -1, m.H - 1);
+    s.li = -1;
+    return false;
+}
+
+// Scalar drivers (host simulator; swept rays in the kernels).  The kernels run FULL traversals
+// through the warp-cooperative driver in auvpf_kernels.cuh around the same functions.
+AUVPF_HD float raycast_from(const DemView &m, const Ray &r, float t_lo)
+{
+    Trav s;
+    float range;
+    if (!trav_init(s, m, r, range, t_lo)) return range;
+    if (t_lo > 0.f && near_walk(s, m, r, range)) return range;
+    for (;;) {
+        int res = trav_step(s, m, r);
+        if (res == kMiss) return m.range_max;
+        if (res == kPending && trav_exact(s, m, r, range)) return range;
+    }
+}
+
+AUVPF_HD float raycast_one(const DemView &m, const Ray &r) { return raycast_from(m, r, 0.f); }
+
+// ---------------------------------------------------------------------------------------------
+// Fan sweep.  When the beams form a planar fan d_b = cos(th_b) c0 +
+// sin(th_b) a0 and the height above the terrain is strictly decreasing along the fan's
+// centre direction c = R c0 (true when c_z + max_slope |c_xy| < 0), the terrain profile in the
+// fan plane is a single-valued function of the lateral coordinate p = t sin(th).  Then a ray
+// that is clear of the terrain up to lateral distance p_clear certifies every ray further out
+// on the same side (|th'| > |th|) to be clear up to the same lateral distance: at equal p the
+// outer ray is higher.  So beams are swept outward and each starts at
+// t_lo = (p_clear - margin) / |sin th'| instead of at the sensor.
+// The terrain must also be DEFINED wherever the fan can reach (outside the map there is no
+// surface, and "clear because outside" certifies nothing for a ray that is inside), so the
+// sweep is only used when the whole reach of the sensor lies inside the map footprint.
+AUVPF_HD bool fan_sweep_valid(const DemView &m, const double p[3], const double R[9], const float c0[3])
+{
+    const double reach = (double)m.range_max;
+    const double xmax = m.x0 + (double)(m.W - 1) * (double)m.res, ymax = m.y0 + (double)(m.H - 1) * (double)m.res;
+    if (!(p[0] - reach > m.x0 && p[0] + reach < xmax && p[1] - reach > m.y0 && p[1] + reach < ymax)) return false;
+    const float max_slope = m.max_slope;
+    const double cx = R[0] * c0[0] + R[1] * c0[1] + R[2] * c0[2];
+    const double cy = R[3] * c0[0] + R[4] * c0[1] + R[5] * c0[2];
+    const double cz = R[6] * c0[0] + R[7] * c0[1] + R[8] * c0[2];
+    return cz + (double)max_slope * sqrt(cx * cx + cy * cy) < -0.05;
+}
+
+AUVPF_HD float sweep_bound(float p_clear, float inv_s, float res)
+{
+    const float p = p_clear * 0.9999f - 0.5f * res;      // back off half a cell: fp slack, near-planarity
+    return p > 0.f ? p * inv_s : 0.f;
 }
 
 // Build the ray of beam direction d (sensor frame) for a particle frame (p, R).

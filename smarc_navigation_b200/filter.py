@@ -89,6 +89,8 @@ class ParticleFilter(object):
         cfg.device = int(device)
         cfg.particle_count = self.pc
         cfg.n_filters = self.n_filters
+        if isinstance(coarse_level, (tuple, list)):          # (finer, coarser) max-mip levels
+            coarse_level = int(coarse_level[0]) | (int(coarse_level[1]) << 8)
         cfg.coarse_level = int(coarse_level)
         cfg.global_offset = int(global_offset)
         cfg.global_count = int(global_count)

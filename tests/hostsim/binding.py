@@ -28,7 +28,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def raycast_poses(dem, shift, range_max, m2o, poses, beams, want_mip=False):
+def raycast_poses(dem, shift, range_max, m2o, poses, beams, want_mip=False, shift_hi=0, fan=True, want_swept=False):
     L = lib()
     z = np.ascontiguousarray(dem["z"], np.float32)
     H, W = z.shape
@@ -40,9 +40,12 @@ def raycast_poses(dem, shift, range_max, m2o, poses, beams, want_mip=False):
     oH, oW = C.c_int(), C.c_int()
     L.hs_mip_dims(C.c_int(H), C.c_int(W), C.c_int(shift), C.byref(oH), C.byref(oW))
     mip = np.empty((oH.value, oW.value), np.float32)
+    swept = C.c_long()
     L.hs_raycast_poses(_p(z), C.c_int(H), C.c_int(W), C.c_double(dem["x0"]), C.c_double(dem["y0"]),
-                       C.c_double(dem["res"]), C.c_int(shift), C.c_double(range_max), _p(m2o), _p(poses),
-                       C.c_long(n), _p(beams), C.c_int(B), _p(out), _p(mip))
+                       C.c_double(dem["res"]), C.c_int(shift), C.c_int(shift_hi), C.c_double(range_max), _p(m2o), _p(poses),
+                       C.c_long(n), _p(beams), C.c_int(B), _p(out), _p(mip), C.c_int(1 if fan else 0), C.byref(swept))
+    if want_swept:
+        return out, int(swept.value)
     return (out, mip) if want_mip else out
 
 

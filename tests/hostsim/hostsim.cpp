@@ -12,6 +12,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../smarc_navigation_b200/csrc/auvpf_fan.h"
 #include "../../smarc_navigation_b200/csrc/auvpf_math.cuh"
 
 using namespace auvpf;
@@ -59,25 +60,52 @@ void build_mip(const float *z, int H, int W, int shift, std::vector<float> &out,
 extern "C" {
 
 // expected ranges (n, B) for explicit poses: mirrors k_raycast_poses
-void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double res, int shift, double range_max,
+void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double res, int shift, int shift_hi,
+                      double range_max,
                       const double *m2o, const double *poses, long n, const float *beams, int B, float *out,
-                      float *mip_out /* optional, for checking the pyramid */)
+                      float *mip_out /* optional, for checking the pyramid */, int use_fan, long *n_swept)
 {
+    FanPlan plan = plan_fan(beams, B);
+    *n_swept = 0;
     HostDem d;
-    int mH, mW;
+    int mH, mW, mH2 = 0, mW2 = 0;
+    std::vector<float> mip_hi;
     build_mip(z, H, W, shift, d.mip, mH, mW);
+    if (shift_hi > shift) build_mip(z, H, W, shift_hi, mip_hi, mH2, mW2);
+    // padded copy: replicated one-vertex border, pitch W + 2 (as auvpf_set_dem stores it)
+    const int pitch = W + 2;
+    std::vector<float> zp((size_t)(H + 2) * pitch);
+    for (int i = -1; i <= H; ++i)
+        for (int j = -1; j <= W; ++j)
+            zp[(size_t)(i + 1) * pitch + (j + 1)] = z[(size_t)std::min(std::max(i, 0), H - 1) * W + std::min(std::max(j, 0), W - 1)];
     if (mip_out) memcpy(mip_out, d.mip.data(), sizeof(float) * d.mip.size());
     DemView &v = d.v;
-    v.z = z;
-    v.mip = d.mip.data();
+    v.z = zp.data() + pitch + 1;
     v.W = W;
     v.H = H;
-    v.mipW = mW;
-    v.mipH = mH;
-    v.shift = shift;
-    v.inv_res = (float)(1.0 / res);
+    v.pitch = pitch;
+    v.mip[0] = d.mip.data();
+    v.mipW[0] = mW;
+    v.mipH[0] = mH;
+    v.shift[0] = shift;
+    v.mip[1] = mip_hi.empty() ? d.mip.data() : mip_hi.data();
+    v.mipW[1] = mip_hi.empty() ? mW : mW2;
+    v.mipH[1] = mip_hi.empty() ? mH : mH2;
+    v.shift[1] = mip_hi.empty() ? shift : shift_hi;
+    v.n_levels = mip_hi.empty() ? 1 : 2;
     v.range_max = (float)range_max;
     v.zmax = *std::max_element(z, z + (size_t)H * W);
+    v.res = (float)res;
+    {
+        float ms = 0.f;
+        for (int i = 0; i + 1 < H; ++i)
+            for (int j = 0; j + 1 < W; ++j) {
+                float z00 = z[(size_t)i * W + j], z01 = z[(size_t)i * W + j + 1], z10 = z[(size_t)(i + 1) * W + j],
+                      z11 = z[(size_t)(i + 1) * W + j + 1];
+                ms = std::max(ms, std::max(std::hypot(z01 - z00, z11 - z01), std::hypot(z11 - z10, z10 - z00)) * (float)(1.0 / res));
+            }
+        v.max_slope = ms * 1.0001f + 1e-6f;
+    }
     v.x0 = x0;
     v.y0 = y0;
     v.inv_res_d = 1.0 / res;
@@ -99,9 +127,29 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
         int ix0, iy0;
         float lx0, ly0;
         origin_cell(v, p, ix0, iy0, lx0, ly0);
-        for (int b = 0; b < B; ++b) {
-            Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
-            out[(size_t)i * B + b] = raycast_one(v, ray);
+        if (!use_fan) {
+            for (int b = 0; b < B; ++b) {
+                Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
+                out[(size_t)i * B + b] = raycast_one(v, ray);
+            }
+            continue;
+        }
+        // the kernels' lane / chunk sweep, lane by lane (k_update_mbes, k_raycast_poses)
+        const bool sweep_ok = plan.planar && fan_sweep_valid(v, p, R, plan.c0);
+        for (int lane = 0; lane < kFanLanes; ++lane) {
+            float p_clear = 0.f;
+            for (int k = 0; k < plan.chunk; ++k) {
+                int o = plan.order[(size_t)lane * plan.chunk + k];
+                if (o < 0) continue;
+                int b = o & (kOrdFull - 1);
+                bool full = (o & kOrdFull) != 0 || !sweep_ok;
+                Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
+                float t_lo = full ? 0.f : sweep_bound(p_clear, plan.inv_s[b], v.res);
+                float range = raycast_from(v, ray, t_lo);
+                if (t_lo > 0.f) ++*n_swept;
+                p_clear = range * plan.s[b];
+                out[(size_t)i * B + b] = range;
+            }
         }
     }
 }

@@ -27,9 +27,9 @@ def _cloud(rng, n, centre, spread, roll_pitch=0.03, z=-5.0):
     return poses
 
 
-def _compare(dem, shift, poses, beams, m2o, range_max, max_fragile_frac=2e-3):
+def _compare(dem, shift, poses, beams, m2o, range_max, max_fragile_frac=2e-3, shift_hi=0):
     out = c_oracle.update_mbes(dem, poses, m2o, beams, None, 1.0, 0.5, range_max, want_ranges=True, want_diag=True)
-    r = hs.raycast_poses(dem, shift, range_max, m2o, poses, beams.astype(np.float32))
+    r = hs.raycast_poses(dem, shift, range_max, m2o, poses, beams.astype(np.float32), shift_hi=shift_hi)
     ro, dg = out["ranges"], out["diag"]
     fragile = (dg[..., 0] < FRAGILE) | (dg[..., 1] < FRAGILE) | (dg[..., 2] < FRAGILE)
     err = np.abs(r - ro)
@@ -40,13 +40,14 @@ def _compare(dem, shift, poses, beams, m2o, range_max, max_fragile_frac=2e-3):
     return ro, err, fragile
 
 
-@pytest.mark.parametrize("n,res,shift,B", [(500, 2.0, 1, 256), (500, 2.0, 2, 256), (500, 2.0, 4, 64),
-                                           (1200, 0.5, 3, 512), (1200, 0.5, 5, 128)])
-def test_raycast_fan_over_synthetic_bathymetry(n, res, shift, B):
+@pytest.mark.parametrize("n,res,shift,hi,B", [(500, 2.0, 1, 0, 256), (500, 2.0, 2, 0, 256), (500, 2.0, 4, 0, 64),
+                                              (1200, 0.5, 3, 0, 512), (1200, 0.5, 5, 0, 128),
+                                              (500, 2.0, 1, 3, 256), (1200, 0.5, 2, 5, 512), (1200, 0.5, 1, 2, 128)])
+def test_raycast_fan_over_synthetic_bathymetry(n, res, shift, hi, B):
     dem = world.make_dem(n, res)
     rng = np.random.default_rng(4)
     poses = _cloud(rng, 96, (0.45 * n * res,) * 2, 3.0)
-    ro, err, fragile = _compare(dem, shift, poses, world.make_beams(B), np.eye(4), world.RANGE_MAX)
+    ro, err, fragile = _compare(dem, shift, poses, world.make_beams(B), np.eye(4), world.RANGE_MAX, shift_hi=hi)
     assert (ro < world.RANGE_MAX).all()          # every beam hits the seafloor here
 
 
@@ -68,28 +69,30 @@ def test_raycast_with_map_to_odom_transform():
     _compare(dem, 1, poses, world.make_beams(256), m2o, world.RANGE_MAX)
 
 
-def test_raycast_edges_misses_and_steep_rays():
+@pytest.mark.parametrize("lo,hi", [(2, 0), (1, 4), (2, 3)])
+def test_raycast_edges_misses_and_steep_rays(lo, hi):
     """Particles at / outside the map border, short range_max (misses), large roll
     (beams up to ~horizontal), upward-looking beams."""
     dem = world.make_dem(300, 2.0, seed=11)
     rng = np.random.default_rng(7)
     beams = world.make_beams(128, half_angle_deg=75.0)
+    kw = dict(shift_hi=hi)
     edge = _cloud(rng, 64, (8.0, 590.0), 6.0)                       # straddles two borders
-    ro, err, fr = _compare(dem, 2, edge, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2)
+    ro, err, fr = _compare(dem, lo, edge, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2, **kw)
     assert (ro >= world.RANGE_MAX).any() and (ro < world.RANGE_MAX).any()
     outside = _cloud(rng, 32, (-40.0, 300.0), 3.0)
-    _compare(dem, 2, outside, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2)
+    _compare(dem, lo, outside, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2, **kw)
     tilted = _cloud(rng, 64, (300.0, 300.0), 3.0, roll_pitch=0.5)
-    _compare(dem, 2, tilted, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2)
+    _compare(dem, lo, tilted, beams, np.eye(4), world.RANGE_MAX, max_fragile_frac=2e-2, **kw)
     short = _cloud(rng, 32, (300.0, 300.0), 3.0)
-    ro, err, fr = _compare(dem, 2, short, beams, np.eye(4), 30.0, max_fragile_frac=2e-2)
+    ro, err, fr = _compare(dem, lo, short, beams, np.eye(4), 30.0, max_fragile_frac=2e-2, **kw)
     assert (ro == 30.0).any()
     up = _cloud(rng, 16, (300.0, 300.0), 3.0)
-    up[:, 3] = np.pi                                                # sonar looking up: all miss
-    ro, err, fr = _compare(dem, 2, up, beams, np.eye(4), world.RANGE_MAX)
+    up[:, 3] = np.float32(np.pi)                                    # sonar looking up: all miss
+    ro, err, fr = _compare(dem, lo, up, beams, np.eye(4), world.RANGE_MAX, **kw)
     assert (ro == world.RANGE_MAX).all()
     below = _cloud(rng, 16, (300.0, 300.0), 3.0, z=-60.0)           # vehicle under the seafloor: range 0
-    ro, err, fr = _compare(dem, 2, below, beams, np.eye(4), world.RANGE_MAX)
+    ro, err, fr = _compare(dem, lo, below, beams, np.eye(4), world.RANGE_MAX, **kw)
     assert (ro == 0.0).all()
 
 
@@ -102,6 +105,7 @@ def test_raycast_rough_terrain_random_directions():
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     poses = _cloud(rng, 48, (100.0, 100.0), 20.0, roll_pitch=0.2, z=-12.0)
     _compare(dem, 2, poses, d, np.eye(4), 80.0, max_fragile_frac=3e-2)
+    _compare(dem, 1, poses, d, np.eye(4), 80.0, max_fragile_frac=3e-2, shift_hi=3)
 
 
 def test_mip_is_conservative():
@@ -214,3 +218,54 @@ def test_count_below_matches_positions():
         pos = (u + np.arange(N)) / float(N)
         for c in [0, 1, 1 << 51, (1 << 52) - 1, 1 << 52] + [int(x) for x in rng.integers(0, 1 << 52, 20)]:
             assert hs.count_below(u, N, c) == int((pos < np.ldexp(float(c), -52)).sum())
+
+
+def _ridged_dem(n=400, res=0.5, seed=5):
+    """Steep short-wavelength ridges: outer beams are occluded (first-hit jumps)."""
+    rng = np.random.default_rng(seed)
+    x = np.arange(n) * res
+    X, Y = np.meshgrid(x, x)
+    z = -30.0 + 2.5 * np.sin(2 * np.pi * X / 9.0) * np.cos(2 * np.pi * Y / 13.0) + 1.0 * np.sin(2 * np.pi * (X + Y) / 4.0)
+    z += rng.normal(0, 0.05, z.shape)
+    return {"z": z.astype(np.float32), "x0": 0.0, "y0": 0.0, "res": res}
+
+
+@pytest.mark.parametrize("lo,hi", [(2, 0), (2, 5)])
+def test_fan_sweep_exact_under_occlusion(lo, hi):
+    """The fan sweep (certified start from the inner neighbour's clear extent) must return
+    the same first hits as independent rays, also where ridges occlude the outer beams."""
+    dem = _ridged_dem()
+    rng = np.random.default_rng(9)
+    beams = world.make_beams(512, half_angle_deg=70.0)
+    poses = _cloud(rng, 48, (100.0, 100.0), 8.0, roll_pitch=0.04, z=-21.0)   # steep scene: sweep valid for tilt < ~14 deg
+    rmax = 60.0
+    r_fan, nsw = hs.raycast_poses(dem, lo, rmax, np.eye(4), poses, beams.astype(np.float32), shift_hi=hi, want_swept=True)
+    r_ind = hs.raycast_poses(dem, lo, rmax, np.eye(4), poses, beams.astype(np.float32), shift_hi=hi, fan=False)
+    assert nsw > 0.8 * r_fan.size                                     # the sweep is really in use
+    # occlusion jumps are present in this scene
+    assert (np.abs(np.diff(r_ind, axis=1)) > 2.0).sum() > 50
+    np.testing.assert_allclose(r_fan, r_ind, rtol=0, atol=3e-5)         # same first hits (fp32 rounding only)
+    ro, err, fragile = _compare(dem, lo, poses, beams, np.eye(4), rmax, max_fragile_frac=5e-2, shift_hi=hi)
+
+
+def test_fan_plan():
+    """Host-side fan analysis: planarity / ordering detection and per-lane sweep order."""
+    import ctypes as C
+    for B in (512, 256, 100, 33):
+        beams = world.make_beams(B).astype(np.float32)
+        r, nsw = hs.raycast_poses(world.make_dem(100, 2.0), 1, 60.0, np.eye(4), np.array([[100.0, 100.0, -5, 0, 0, 0.3]]),
+                                  beams, want_swept=True)
+        chunk = (B + 31) // 32
+        assert nsw >= B - 2 * 32 - 4 if chunk > 1 else nsw == 0
+    # non-planar or unsorted beam sets are never swept
+    rng = np.random.default_rng(2)
+    d = rng.normal(size=(128, 3))
+    d[:, 2] = -np.abs(d[:, 2]) - 0.5
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r, nsw = hs.raycast_poses(world.make_dem(100, 2.0), 1, 60.0, np.eye(4), np.array([[100.0, 100.0, -5, 0, 0, 0.3]]),
+                              d.astype(np.float32), want_swept=True)
+    assert nsw == 0
+    shuffled = world.make_beams(128)[rng.permutation(128)].astype(np.float32)
+    r, nsw = hs.raycast_poses(world.make_dem(100, 2.0), 1, 60.0, np.eye(4), np.array([[100.0, 100.0, -5, 0, 0, 0.3]]),
+                              shuffled, want_swept=True)
+    assert nsw == 0
