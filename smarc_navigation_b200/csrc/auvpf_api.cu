@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -93,11 +94,15 @@ struct auvpf_handle {
 
     // map / sensor
     float *dem_z = nullptr, *mip = nullptr, *mip_hi = nullptr, *beams = nullptr, *meas = nullptr;
-    float *beam_aux = nullptr;   // [2B]: |sin th|, 1/|sin th|
+    float *beam_aux = nullptr;   // [3B]: |sin th|, 1/|sin th|, 1/cos th
+    double *beam_tan = nullptr;  // [B]: tan |th| (profile merge)
+    unsigned char *flags = nullptr;   // [N]: particle needs the per-ray kernel
+    DevBuf probe_flags;
     int *beam_order = nullptr;   // [32 * chunk]
     FanParams fan{};
     DemView dem{};
     bool have_dem = false;
+    bool use_profile = true;   // AUVPF_NO_PROFILE=1 in the environment forces the per-ray kernel
     int B = 0;
     FrameParams frame{};
 
@@ -606,6 +611,10 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         }
     }
     h->frame.m2o_identity_r = ident ? 1 : 0;
+    {
+        const char *np = getenv("AUVPF_NO_PROFILE");
+        h->use_profile = !(np && np[0] == '1');
+    }
     *out = h;
     return AUVPF_OK;
 }
@@ -620,7 +629,7 @@ int auvpf_destroy(auvpf_handle *h)
     void *bufs[] = {h->logw,    h->cdf,   h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
                     h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->status,  h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
-                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order};
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flags, h->probe_flags.p};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -795,28 +804,38 @@ int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
     cudaFree(h->meas);
     cudaFree(h->beam_aux);
     cudaFree(h->beam_order);
+    cudaFree(h->beam_tan);
     h->beams = h->meas = h->beam_aux = nullptr;
     h->beam_order = nullptr;
+    h->beam_tan = nullptr;
     h->B = 0;
     std::vector<float> host(3 * (size_t)B);
     CU(cudaMemcpy(host.data(), dirs_xyz, sizeof(float) * 3 * B,
                   is_device_ptr(dirs_xyz) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
     // host-side analysis: planar sorted fan? per-lane sweep order (auvpf_fan.h)
     FanPlan plan = plan_fan(host.data(), B);
-    std::vector<float> aux(2 * (size_t)B);
+    std::vector<float> aux(3 * (size_t)B);
     for (int b = 0; b < B; ++b) {
         aux[b] = plan.s[b];
         aux[B + b] = plan.inv_s[b];
+        aux[2 * B + b] = plan.sec_t[b];
     }
     CU(cudaMalloc(&h->beams, sizeof(float) * 3 * B));
     CU(cudaMalloc(&h->meas, sizeof(float) * (size_t)B * h->F));
-    CU(cudaMalloc(&h->beam_aux, sizeof(float) * 2 * B));
+    CU(cudaMalloc(&h->beam_aux, sizeof(float) * 3 * B));
+    CU(cudaMalloc(&h->beam_tan, sizeof(double) * B));
+    CU(cudaMemcpy(h->beam_tan, plan.tan_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
+    if (!h->flags) CU(cudaMalloc(&h->flags, (size_t)h->N));
     CU(cudaMalloc(&h->beam_order, sizeof(int) * plan.order.size()));
     CU(cudaMemcpy(h->beams, host.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->beam_aux, aux.data(), sizeof(float) * 2 * B, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->beam_aux, aux.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->beam_order, plan.order.data(), sizeof(int) * plan.order.size(), cudaMemcpyHostToDevice));
     h->fan.planar = plan.planar ? 1 : 0;
     h->fan.chunk = plan.chunk;
+    h->fan.lanes_first = plan.lanes_first;
+    h->fan.n1 = plan.n1;
+    h->fan.sgn1 = plan.sgn1;
+    for (int a = 0; a < 3; ++a) h->fan.a0[a] = plan.a0[a];
     for (int a = 0; a < 3; ++a) h->fan.c0[a] = plan.c0[a];
     h->B = B;
     return AUVPF_OK;
@@ -953,11 +972,22 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
     const double var = h->cfg.meas_std * h->cfg.meas_std;
     {
         Prof pr(h, AUVPF_K_UPDATE_MBES);
+        const float nhiv = (float)(-0.5 / var), lnb = (float)std::log(h->cfg.meas_std * std::sqrt(2.0 * kPi));
+        const unsigned char *only = nullptr;
+        if (h->fan.planar && h->use_profile) {
+            // profile merge: one thread per particle; what it cannot certify is flagged ...
+            const size_t smp = (sizeof(double) + 3 * sizeof(float)) * h->B;
+            k_update_mbes_profile<<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
+                h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
+                (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flags);
+            LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
+            only = h->flags;
+        }
+        // ... and recast ray by ray (everything, when the beam set is not a planar fan)
         const size_t smem = sizeof(float) * 6 * h->B + sizeof(int) * 32 * h->fan.chunk;
         k_update_mbes<<<grid1(h->M, kMbesWarps, h->F), kMbesWarps * 32, smem, h->stream>>>(
             h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beams, h->beam_aux, h->beam_order, h->meas, h->B,
-            (float)h->cfg.range_min,
-            (float)(-0.5 / var), (float)std::log(h->cfg.meas_std * std::sqrt(2.0 * kPi)), h->logw);
+            (float)h->cfg.range_min, nhiv, lnb, h->logw, only);
         LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
         CU(cudaGetLastError());
     }
@@ -977,8 +1007,18 @@ int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges
     if ((rc = stage_out(h, S_OUT0, ranges_out, (size_t)n * h->B, &od))) return rc;
     {
         Prof pr(h, AUVPF_K_OTHER);
-        k_raycast_poses<<<grid1(n, kMbesWarps, 1), kMbesWarps * 32, 0, h->stream>>>(
-            pd, n, h->frame, h->dem, h->fan, h->beams, h->beam_aux, h->beam_order, h->B, od);
+        const unsigned char *only = nullptr;
+        if (h->fan.planar && h->use_profile) {
+            void *fl;
+            if ((rc = slot_reserve(h, S_OUT1, (size_t)n, &fl))) return rc;
+            const size_t smp = (sizeof(double) + 2 * sizeof(float)) * h->B;
+            k_raycast_poses_profile<<<grid1(n, kProfThreads, 1), kProfThreads, smp, h->stream>>>(
+                pd, n, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->B, od, static_cast<unsigned char *>(fl));
+            only = static_cast<unsigned char *>(fl);
+        }
+        const size_t smem = sizeof(float) * 6 * h->B + sizeof(int) * 32 * h->fan.chunk;
+        k_raycast_poses<<<grid1(n, kMbesWarps, 1), kMbesWarps * 32, smem, h->stream>>>(
+            pd, n, h->frame, h->dem, h->fan, h->beams, h->beam_aux, h->beam_order, h->B, od, only);
         LAUNCHED(h, AUVPF_K_OTHER, 1);
         CU(cudaGetLastError());
     }

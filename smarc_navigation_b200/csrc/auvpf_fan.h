@@ -15,17 +15,29 @@ constexpr int kOrdFull = 1 << 30;    // flag in the order table: start of a swee
 struct FanPlan {
     bool planar = false;             // beams form a sorted planar fan (sweep allowed)
     float c0[3] = {0, 0, -1};        // fan centre direction (sensor frame)
-    int chunk = 1;                   // beams per lane
+    int chunk = 1;                   // beams per lane (loop trip count)
+    int lanes_first = 0;             // lanes holding the first side (lower beam indices) of the fan
     std::vector<float> s, inv_s;     // |sin th_b| and its reciprocal (0 = unusable)
+    std::vector<double> tan_t;       // tan |th_b| (profile merge; float64, it enters a cancelling denominator)
+    std::vector<float> sec_t;        // 1 / cos th_b
+    float a0[3] = {0, 1, 0};         // lateral unit vector (sensor frame): th > 0 leans towards +a0
+    int n1 = 0;                      // beams [0, n1) are one side of the centre, [n1, B) the other
+    int sgn1 = -1;                   // sign of th on the first side
     std::vector<int32_t> order;      // [32 * chunk]: beam index | kOrdFull, or -1 (padding)
 };
 
+// Lane layout of a planar fan: the beams of each side of the centre are split into contiguous
+// chunks, one per lane, and every lane processes its chunk OUTWARD (entry 0 = the beam nearest
+// the centre).  No chunk straddles the centre.  Lanes [0, lanes_first) hold the first side
+// (their inner neighbour is lane + 1), lanes [lanes_first, 32) the second side (inner
+// neighbour lane - 1); the kernels chain the chunk starts outward through those neighbours.
 inline FanPlan plan_fan(const float *dirs, int B)
 {
     FanPlan f;
-    f.chunk = (B + kFanLanes - 1) / kFanLanes;
     f.s.assign(B, 0.f);
     f.inv_s.assign(B, 0.f);
+    f.tan_t.assign(B, 0.0);
+    f.sec_t.assign(B, 1.f);
     std::vector<double> th(B, 0.0);
     auto D = [&](int b, int a) { return (double)dirs[3 * b + a]; };
     // plane normal from the most separated pair (first / last), centre = normalised mean
@@ -60,29 +72,52 @@ inline FanPlan plan_fan(const float *dirs, int B)
                 if (!((th[b] > th[b - 1]) == (th[1] > th[0])) || th[b] == th[b - 1]) ok = false;       // strictly monotone
             if (ok) {
                 f.planar = true;
-                for (int a = 0; a < 3; ++a) f.c0[a] = (float)c[a];
+                for (int a = 0; a < 3; ++a) {
+                    f.c0[a] = (float)c[a];
+                    f.a0[a] = (float)a0[a];
+                }
                 for (int b = 0; b < B; ++b) {
                     double sn = std::fabs(std::sin(th[b]));
                     f.s[b] = (float)sn;
-                    f.inv_s[b] = sn > 1e-3 ? (float)(1.0 / sn) : 0.f;
+                    f.inv_s[b] = sn > 1e-6 ? (float)(1.0 / sn) : 0.f;
+                    f.tan_t[b] = std::fabs(std::tan(th[b]));
+                    f.sec_t[b] = (float)(1.0 / std::cos(th[b]));
                 }
             }
         }
     }
-    // per-lane processing order: each side of the centre outward; without a fan every beam is a start
+    if (!f.planar) {
+        // no fan: every beam is traversed from the sensor; lane l takes beams l, l+32, ... (adjacent
+        // lanes = adjacent beams keeps the warp's rays coherent)
+        f.chunk = (B + kFanLanes - 1) / kFanLanes;
+        f.lanes_first = 0;
+        f.order.assign((size_t)kFanLanes * f.chunk, -1);
+        for (int b = 0; b < B; ++b) f.order[(size_t)(b % kFanLanes) * f.chunk + b / kFanLanes] = b | kOrdFull;
+        return f;
+    }
+    // sides of the centre in index order: [0, n1) has one sign of th, [n1, B) the other
+    int n1 = 0;
+    while (n1 < B && (th[n1] < 0.0) == (th[0] < 0.0)) ++n1;
+    const int n2 = B - n1;
+    f.n1 = n1;
+    f.sgn1 = th[0] < 0.0 ? -1 : 1;
+    int l1 = n2 == 0 ? kFanLanes : (int)std::lround((double)kFanLanes * n1 / B);
+    if (n1 > 0 && l1 < 1) l1 = 1;
+    if (n2 > 0 && l1 > kFanLanes - 1) l1 = kFanLanes - 1;
+    l1 = std::min(l1, n1);
+    const int l2 = std::min(kFanLanes - l1, n2);
+    const int c1 = l1 ? (n1 + l1 - 1) / l1 : 0, c2 = l2 ? (n2 + l2 - 1) / l2 : 0;
+    f.chunk = std::max(1, std::max(c1, c2));
+    f.lanes_first = l1;
     f.order.assign((size_t)kFanLanes * f.chunk, -1);
-    for (int l = 0; l < kFanLanes; ++l) {
-        int lo = l * f.chunk, hi = std::min(B, lo + f.chunk), k = 0;
-        if (lo >= hi) continue;
-        std::vector<int> neg, pos;
-        for (int b = lo; b < hi; ++b) (f.planar && th[b] < 0.0 ? neg : pos).push_back(b);
-        auto outward = [&](int x, int y) { return std::fabs(th[x]) < std::fabs(th[y]); };
-        if (f.planar) {
-            std::sort(neg.begin(), neg.end(), outward);
-            std::sort(pos.begin(), pos.end(), outward);
-        }
-        for (size_t i = 0; i < neg.size(); ++i) f.order[(size_t)l * f.chunk + k++] = neg[i] | ((i == 0 || !f.planar) ? kOrdFull : 0);
-        for (size_t i = 0; i < pos.size(); ++i) f.order[(size_t)l * f.chunk + k++] = pos[i] | ((i == 0 || !f.planar) ? kOrdFull : 0);
+    // first side: inner end is index n1-1; lane l1-1 is innermost.  Chunks are cut from the inside.
+    for (int j = 0; j < n1; ++j) {                 // j = distance from the centre
+        int lane = l1 - 1 - j / c1, k = j % c1, b = n1 - 1 - j;
+        f.order[(size_t)lane * f.chunk + k] = b | (k == 0 ? kOrdFull : 0);
+    }
+    for (int j = 0; j < n2; ++j) {
+        int lane = l1 + j / c2, k = j % c2, b = n1 + j;
+        f.order[(size_t)lane * f.chunk + k] = b | (k == 0 ? kOrdFull : 0);
     }
     return f;
 }

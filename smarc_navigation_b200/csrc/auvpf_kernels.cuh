@@ -226,20 +226,23 @@ constexpr int kMbesWarps = 8;
 constexpr int kExactThreshold = 12;   // run the postponed exact-cell tests once this many lanes wait
 
 struct FanParams {
-    float c0[3];     // fan centre direction, sensor frame
-    int planar;      // beams form a sorted planar fan
-    int chunk;       // beams per lane
+    float c0[3];      // fan centre direction, sensor frame
+    int planar;       // beams form a sorted planar fan
+    int chunk;        // beams per lane
+    int lanes_first;  // lanes holding the first side of the fan (auvpf_fan.h)
+    float a0[3];      // lateral unit vector, sensor frame (th > 0 leans towards +a0)
+    int n1, sgn1;     // beams [0, n1) on the side of sign sgn1, [n1, B) on the other
 };
 
 // Warp-cooperative traversal driver: MUST be called by all 32 lanes of a converged warp.
 // Every iteration all unresolved lanes do one uniform node step; lanes whose ray reached a cell
 // that cannot be skipped park (pending) until enough lanes are parked -- or nobody else can
 // make progress -- and then run the exact two-triangle test together.
-__device__ __forceinline__ float raycast_warp(const DemView &m, const Ray &r, bool valid, float t_lo)
+__device__ __forceinline__ float raycast_warp(const DemView &m, const Ray &r, bool valid, bool interior)
 {
     Trav s;
     float range = m.range_max;
-    bool active = valid && trav_init(s, m, r, range, t_lo);
+    bool active = valid && trav_init(s, m, r, range, 0.f, interior);
     bool pending = false;
     while (__any_sync(0xffffffffu, active)) {
         if (active && !pending) {
@@ -264,46 +267,92 @@ __device__ __forceinline__ float raycast_warp(const DemView &m, const Ray &r, bo
     return range;
 }
 
-// One lane's k-th beam of its chunk.  `valid` lanes need a range; p_clear carries the sweep.
-__device__ __forceinline__ float fan_ray(const DemView &dem, const Ray &ray, bool valid, bool full, float inv_s,
-                                         float s_b, float &p_clear)
+// Beam tables staged in shared memory by both kernels:
+//   sm[0..B) dx, [B..2B) dy, [2B..3B) dz (sensor frame), [3B..4B) measured range (NaN = not
+//   needed), [4B..5B) |sin th|, [5B..6B) 1/|sin th|; then the per-lane order table (ints).
+// Casts every beam of one particle (warp-cooperative, call with all 32 lanes) and hands
+// (beam, range) of the needed beams to `sink`.
+template <class Sink>
+__device__ __forceinline__ void fan_cast(const DemView &dem, const FanParams &fan, const float *sm, int B,
+                                         const int *s_ord, const double p[3], const double R[9], int lane, Sink sink)
 {
-    float t_lo = 0.f;
-    if (valid && !full) t_lo = sweep_bound(p_clear, inv_s, dem.res);
-    const bool want_full = valid && !(t_lo > 0.f);
-    float range;
-    if (__any_sync(0xffffffffu, want_full))       // someone starts from the sensor: traverse together
-        range = raycast_warp(dem, ray, valid, t_lo);
-    else
-        range = valid ? raycast_from(dem, ray, t_lo) : dem.range_max;
-    if (valid) p_clear = range * s_b;             // a miss (range_max) leaves the whole ray clear
-    return range;
+    int ix0, iy0;
+    float lx0, ly0;
+    origin_cell(dem, p, ix0, iy0, lx0, ly0);
+    const int C = fan.chunk;
+    const bool sweep_ok = fan.planar && fan_sweep_valid(dem, p, R, fan.c0);     // warp-uniform
+    if (!sweep_ok) {
+        // no certified sweep for this particle: every beam is traversed from the sensor
+        for (int k = 0; k < C; ++k) {
+            const int o = s_ord[lane * C + k];
+            const int b = o >= 0 ? (o & (kOrdFull - 1)) : 0;
+            const bool need = o >= 0 && sm[3 * B + b] == sm[3 * B + b];
+            Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, sm[b], sm[B + b], sm[2 * B + b]);
+            const float range = raycast_warp(dem, ray, need, false);
+            if (need) sink(b, range);
+        }
+        return;
+    }
+    // ---- chunk starts: every lane traverses the innermost beam of its chunk from the sensor,
+    // all 32 together through the cooperative driver.  (Chaining the starts outward through the
+    // neighbouring lane was measured: 2 active lanes x a long sequential walk costs more warp
+    // instructions than this one cooperative traversal.)
+    float p_clear = 0.f;
+    {
+        const int o = s_ord[lane * C];
+        const bool has = o >= 0;
+        const int b = has ? (o & (kOrdFull - 1)) : 0;
+        Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, sm[b], sm[B + b], sm[2 * B + b]);
+        const float range = raycast_warp(dem, ray, has, true);
+        if (has) p_clear = range * sm[4 * B + b];
+        if (has && sm[3 * B + b] == sm[3 * B + b]) sink(b, range);
+    }
+    // ---- sweep every lane's chunk outward
+    for (int k = 1; k < C; ++k) {
+        const int o = s_ord[lane * C + k];
+        const int b = o >= 0 ? (o & (kOrdFull - 1)) : 0;
+        if (o >= 0 && sm[3 * B + b] == sm[3 * B + b]) {
+            Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, sm[b], sm[B + b], sm[2 * B + b]);
+            const float range = raycast_from(dem, ray, sweep_bound(p_clear, sm[5 * B + b]), true);
+            p_clear = range * sm[4 * B + b];        // a miss (range_max) leaves the whole ray clear
+            sink(b, range);
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_fan_tables(float *sm, int *s_ord, int B, const FanParams &fan,
+                                                 const float *beam_dirs, const float *beam_aux, const int *order)
+{
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        sm[b] = beam_dirs[3 * b];
+        sm[B + b] = beam_dirs[3 * b + 1];
+        sm[2 * B + b] = beam_dirs[3 * b + 2];
+        sm[4 * B + b] = beam_aux[b];
+        sm[5 * B + b] = beam_aux[B + b];
+    }
+    for (int k = threadIdx.x; k < 32 * fan.chunk; k += blockDim.x) s_ord[k] = order[k];
 }
 
 __global__ void __launch_bounds__(kMbesWarps * 32)
 k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan, const float *__restrict__ beam_dirs,
               const float *__restrict__ beam_aux, const int *__restrict__ order, const float *__restrict__ meas, int B,
-              float range_min, float neg_half_inv_var, float log_norm_per_beam, float *__restrict__ logw)
+              float range_min, float neg_half_inv_var, float log_norm_per_beam, float *__restrict__ logw,
+              const unsigned char *__restrict__ only_flagged)
 {
-    extern __shared__ float sm[];   // [6*B] dx, dy, dz, measured range (NaN = skip), |sin th|, 1/|sin th|; then order
+    extern __shared__ float sm[];
     int *s_ord = reinterpret_cast<int *>(sm + 6 * B);
     __shared__ int s_valid;
     const int f = blockIdx.y;
     if (threadIdx.x == 0) s_valid = 0;
+    stage_fan_tables(sm, s_ord, B, fan, beam_dirs, beam_aux, order);
     __syncthreads();
     int nv = 0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        sm[b] = beam_dirs[3 * b];
-        sm[B + b] = beam_dirs[3 * b + 1];
-        sm[2 * B + b] = beam_dirs[3 * b + 2];
         float r = meas[(size_t)f * B + b];
         bool ok = isfinite(r) && r >= range_min && r <= dem.range_max;
-        sm[3 * B + b] = ok ? r : __int_as_float(0x7fc00000);
-        sm[4 * B + b] = beam_aux[b];
-        sm[5 * B + b] = beam_aux[B + b];
+        sm[3 * B + b] = ok ? r : __int_as_float(0x7fc00000);     // invalid measured beam: no raycast needed
         nv += ok ? 1 : 0;
     }
-    for (int k = threadIdx.x; k < 32 * fan.chunk; k += blockDim.x) s_ord[k] = order[k];
     if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
     const float lognorm = -(float)s_valid * log_norm_per_beam;
@@ -311,24 +360,15 @@ k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan
     const int64_t i = (int64_t)blockIdx.x * kMbesWarps + warp;
     if (i >= M) return;
     const int64_t row = (int64_t)f * M + i;
+    if (only_flagged && !only_flagged[row]) return;       // warp-uniform: resolved by the profile kernel
     double p[3];
     double R[9];
     particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
-    int ix0, iy0;
-    float lx0, ly0;
-    origin_cell(dem, p, ix0, iy0, lx0, ly0);
-    const bool sweep_ok = fan.planar && fan_sweep_valid(dem, p, R, fan.c0);
-    float acc = 0.f, p_clear = 0.f;
-    for (int k = 0; k < fan.chunk; ++k) {           // warp-uniform trip count
-        const int o = s_ord[lane * fan.chunk + k];
-        const int b = o >= 0 ? (o & (kOrdFull - 1)) : 0;
-        const float rm = sm[3 * B + b];
-        const bool valid = o >= 0 && rm == rm;      // invalid measured beam: no raycast needed
-        const bool full = (o & kOrdFull) != 0 || !sweep_ok;
-        Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, sm[b], sm[B + b], sm[2 * B + b]);
-        const float e = rm - fan_ray(dem, ray, valid, full, sm[5 * B + b], sm[4 * B + b], p_clear);
-        if (valid) acc = fmaf(e, e, acc);
-    }
+    float acc = 0.f;
+    fan_cast(dem, fan, sm, B, s_ord, p, R, lane, [&](int b, float range) {
+        const float e = sm[3 * B + b] - range;
+        acc = fmaf(e, e, acc);
+    });
     acc = warp_sum(acc);
     if (lane == 0) logw[row] = fmaf(neg_half_inv_var, acc, lognorm);
 }
@@ -337,29 +377,124 @@ k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan
 __global__ void __launch_bounds__(kMbesWarps * 32)
 k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, DemView dem, FanParams fan,
                 const float *__restrict__ beam_dirs, const float *__restrict__ beam_aux,
-                const int *__restrict__ order, int B, float *__restrict__ out)
+                const int *__restrict__ order, int B, float *__restrict__ out,
+                const unsigned char *__restrict__ only_flagged)
 {
+    extern __shared__ float sm[];
+    int *s_ord = reinterpret_cast<int *>(sm + 6 * B);
+    stage_fan_tables(sm, s_ord, B, fan, beam_dirs, beam_aux, order);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) sm[3 * B + b] = 0.f;      // every beam is needed
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * kMbesWarps + warp;
+    if (i >= n) return;
+    if (only_flagged && !only_flagged[i]) return;
+    const double *ps = poses + 6 * i;
+    double p[3];
+    double R[9];
+    particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
+    fan_cast(dem, fan, sm, B, s_ord, p, R, lane, [&](int b, float range) { out[(size_t)i * B + b] = range; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Profile-merge kernels (auvpf_math.cuh "Profile merge"): ONE THREAD per particle marches the
+// terrain profile of each side of the fan once and resolves all its beams on the way --
+// O(cells + beams) per particle instead of O(beams x cells per ray).  Lanes of a warp are
+// neighbouring particles doing the same march, so the warp stays converged and the DEM
+// footprint is shared in L1.  Particles that cannot be certified (near the map border, centre
+// beam missed, a triangle steeper than the fan tilt allows) are flagged and recast by the
+// per-ray kernel above.
+constexpr int kProfThreads = 128;
+
+// shared memory: tan (double B) | sec (float B) | cosec (float B) | measured range (float B)
+__device__ __forceinline__ void stage_profile_tables(double *s_tan, float *s_sec, float *s_cosec, int B,
+                                                     const double *beam_tan, const float *beam_aux)
+{
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        s_tan[b] = beam_tan[b];
+        s_cosec[b] = beam_aux[B + b];
+        s_sec[b] = beam_aux[2 * B + b];
+    }
+}
+
+__device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, const double *s_tan, const float *s_sec,
+                                                 const float *s_cosec)
+{
+    FanTables T;
+    T.dx = T.dy = T.dz = nullptr;
+    T.tan_t = s_tan;
+    T.sec_t = s_sec;
+    T.cosec_t = s_cosec;
+    T.B = B;
+    T.n1 = fan.n1;
+    T.sgn1 = fan.sgn1;
+    for (int a = 0; a < 3; ++a) {
+        T.c0[a] = fan.c0[a];
+        T.a0[a] = fan.a0[a];
+    }
+    return T;
+}
+
+__global__ void __launch_bounds__(kProfThreads)
+k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan,
+                      const double *__restrict__ beam_tan, const float *__restrict__ beam_aux,
+                      const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,
+                      float log_norm_per_beam, float *__restrict__ logw, unsigned char *__restrict__ flags)
+{
+    extern __shared__ double smd[];
+    double *s_tan = smd;
+    float *s_sec = reinterpret_cast<float *>(smd + B), *s_cosec = s_sec + B, *s_meas = s_cosec + B;
+    __shared__ int s_valid;
+    const int f = blockIdx.y;
+    if (threadIdx.x == 0) s_valid = 0;
+    stage_profile_tables(s_tan, s_sec, s_cosec, B, beam_tan, beam_aux);
+    __syncthreads();
+    int nv = 0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        float r = meas[(size_t)f * B + b];
+        bool ok = isfinite(r) && r >= range_min && r <= dem.range_max;
+        s_meas[b] = ok ? r : __int_as_float(0x7fc00000);
+        nv += ok ? 1 : 0;
+    }
+    if (nv) atomicAdd(&s_valid, nv);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
+    if (i >= M) return;
+    const int64_t row = (int64_t)f * M + i;
+    double p[3];
+    double R[9];
+    particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
+    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_cosec);
+    float acc = 0.f;
+    const bool ok = profile_particle(dem, T, p, R, [&](int b, float range) {
+        const float rm = s_meas[b];
+        const float e = rm - range;
+        if (rm == rm) acc = fmaf(e, e, acc);
+    });
+    flags[row] = ok ? 0 : 1;
+    if (ok) logw[row] = fmaf(neg_half_inv_var, acc, -(float)s_valid * log_norm_per_beam);
+}
+
+__global__ void __launch_bounds__(kProfThreads)
+k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams fp, DemView dem, FanParams fan,
+                        const double *__restrict__ beam_tan, const float *__restrict__ beam_aux, int B,
+                        float *__restrict__ out, unsigned char *__restrict__ flags)
+{
+    extern __shared__ double smd[];
+    double *s_tan = smd;
+    float *s_sec = reinterpret_cast<float *>(smd + B), *s_cosec = s_sec + B;
+    stage_profile_tables(s_tan, s_sec, s_cosec, B, beam_tan, beam_aux);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
     if (i >= n) return;
     const double *ps = poses + 6 * i;
     double p[3];
     double R[9];
     particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
-    int ix0, iy0;
-    float lx0, ly0;
-    origin_cell(dem, p, ix0, iy0, lx0, ly0);
-    const bool sweep_ok = fan.planar && fan_sweep_valid(dem, p, R, fan.c0);
-    float p_clear = 0.f;
-    for (int k = 0; k < fan.chunk; ++k) {
-        const int o = order[lane * fan.chunk + k];
-        const int b = o >= 0 ? (o & (kOrdFull - 1)) : 0;
-        const bool valid = o >= 0;
-        const bool full = (o & kOrdFull) != 0 || !sweep_ok;
-        Ray ray = make_ray(dem, p, ix0, iy0, lx0, ly0, R, beam_dirs[3 * b], beam_dirs[3 * b + 1], beam_dirs[3 * b + 2]);
-        const float rr = fan_ray(dem, ray, valid, full, beam_aux[B + b], beam_aux[b], p_clear);
-        if (valid) out[(size_t)i * B + b] = rr;
-    }
+    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_cosec);
+    float *row = out + (size_t)i * B;
+    const bool ok = profile_particle(dem, T, p, R, [&](int b, float range) { row[b] = range; });
+    flags[i] = ok ? 0 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -314,7 +314,9 @@ enum StepResult : int { kContinue = 0, kPending = 1, kMiss = 2 };
 // Clip the ray and place the traversal at its start.  Returns false (with `range` set) when
 // the ray is resolved without traversal.  `t_lo` is a CERTIFIED clear prefix: the caller
 // guarantees f > 0 on [0, t_lo) (fan sweep, see sweep_bound); 0 = none.
-AUVPF_HD bool trav_init(Trav &s, const DemView &m, const Ray &r, float &range, float t_lo = 0.f)
+// `interior` = the map covers the sensor's whole reach (fan_sweep_valid): no clipping needed.
+AUVPF_HD bool trav_init(Trav &s, const DemView &m, const Ray &r, float &range, float t_lo = 0.f,
+                        bool interior = false)
 {
     s.ix = r.dgx != 0.f ? rcp_rn(r.dgx) : 0.f;
     s.iy = r.dgy != 0.f ? rcp_rn(r.dgy) : 0.f;
@@ -322,7 +324,7 @@ AUVPF_HD bool trav_init(Trav &s, const DemView &m, const Ray &r, float &range, f
     s.by = r.dgy > 0.f ? 1 : 0;
     float ts = 0.f, te = m.range_max;
     range = m.range_max;
-    {
+    if (!interior) {
         float lo = -(float)r.ix0, hi = (float)(m.W - 1 - r.ix0);
         if (r.dgx != 0.f) {
             float t1 = (lo - r.lx0) * s.ix, t2 = (hi - r.lx0) * s.ix;
@@ -555,11 +557,11 @@ AUVPF_HD bool near_walk(Trav &s, const DemView &m, const Ray &r, float &range)
 
 // Scalar drivers (host simulator; swept rays in the kernels).  The kernels run FULL traversals
 // through the warp-cooperative driver in auvpf_kernels.cuh around the same functions.
-AUVPF_HD float raycast_from(const DemView &m, const Ray &r, float t_lo)
+AUVPF_HD float raycast_from(const DemView &m, const Ray &r, float t_lo, bool interior = false)
 {
     Trav s;
     float range;
-    if (!trav_init(s, m, r, range, t_lo)) return range;
+    if (!trav_init(s, m, r, range, t_lo, interior)) return range;
     if (t_lo > 0.f && near_walk(s, m, r, range)) return range;
     for (;;) {
         int res = trav_step(s, m, r);
@@ -594,9 +596,11 @@ AUVPF_HD bool fan_sweep_valid(const DemView &m, const double p[3], const double 
     return cz + (double)max_slope * sqrt(cx * cx + cy * cy) < -0.05;
 }
 
-AUVPF_HD float sweep_bound(float p_clear, float inv_s, float res)
+AUVPF_HD float sweep_bound(float p_clear, float inv_s)
 {
-    const float p = p_clear * 0.9999f - 0.5f * res;      // back off half a cell: fp slack, near-planarity
+    // small back-off for fp32 rounding of p_clear and near-planarity of the beam table; should
+    // rounding still leave f(t_lo) <= 0, the hit lies within ~1e-5 m of t_lo (f(t_lo) >= 0 exactly)
+    const float p = p_clear * (1.0f - 2.0e-5f) - 2.0e-4f;
     return p > 0.f ? p * inv_s : 0.f;
 }
 
@@ -630,6 +634,194 @@ AUVPF_HD void origin_cell(const DemView &m, const double p[3], int &ix0, int &iy
     iy0 = (int)fy;
     lx0 = (float)(gx - fx);
     ly0 = (float)(gy - fy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Profile merge: all beams of one side of a planar fan in
+// O(cells + beams).  In fan-plane coordinates (p lateral, q along the fan centre c) the
+// terrain is a single-valued profile q = T(p) that is LINEAR inside every DEM triangle:
+//     T(p) = (alpha + beta p) / gamma,   gamma = c_z - c_g . grad h  (< 0 when the height above
+//     the terrain decreases along c).
+// Beam th is the line q = p cot th; it hits where it first meets the profile, and because a
+// more outward beam is higher at equal p, the hits of th_0 < th_1 < ... occur at increasing p.
+// So the profile is marched ONCE outward, triangle by triangle, and the beams are resolved in
+// order on the way (a merge of two monotone sequences) -- the same first hits as casting each
+// ray separately, occlusions included.  Needs: planar sorted fan, the map covering the sensor's
+// reach, gamma < 0 on every triangle met (checked on the fly; otherwise the caller falls back
+// to per-ray traversal).
+struct ProfFrame {
+    int ix0, iy0;          // origin cell
+    float g0x, g0y;        // origin in local grid units
+    float oz;              // origin height
+    float agx, agy, az;    // lateral unit vector of this side: xy in grid units per metre, z
+    float cgx, cgy, cz;    // fan centre direction, same units
+    double agx_d, agy_d, az_d, cgx_d, cgy_d, cz_d;   // the same in float64 (hit denominators)
+};
+
+constexpr float kGammaMin = 0.05f;      // -gamma must exceed this (|cos| of the worst slope/tilt combination)
+constexpr float kProbeCells = 1.0e-3f;  // how far beyond a boundary the next triangle is looked up
+
+// Marches one side.  tan_t / sec_t / cosec_t are indexed by beam; the j-th beam outward is
+// beam0 + j * bstep.  Calls sink(beam, range) for every beam of the side in outward order.
+// Returns false if the side cannot be certified (caller must recast its beams ray by ray;
+// nothing has been emitted for beams >= the returned *n_done).
+template <class Sink>
+AUVPF_HD bool profile_side(const DemView &m, const ProfFrame &F, float q0, int n_side, int beam0, int bstep,
+                           const double *tan_t, const float *sec_t, const float *cosec_t, Sink sink, int *n_done)
+{
+    int j = 0;
+    *n_done = 0;
+    float p_cur = 0.f;
+    // curve point at p_cur (local grid units), starts under the sensor along c
+    float gx = fmaf(q0, F.cgx, F.g0x), gy = fmaf(q0, F.cgy, F.g0y);
+    const float p_limit = m.range_max;
+    const int max_steps = 8 * (int)(m.range_max / m.res) + 256;
+    bool at_limit = false;
+    float dirx = 0.f, diry = 0.f;         // the start point lies inside its triangle: no probe step
+    for (int step = 0; step < max_steps && j < n_side; ++step) {
+        // triangle just ahead of the current curve point: continue a hair along the direction
+        // the curve had when it reached the boundary
+        const float qx = fmaf(kProbeCells, dirx, gx), qy = fmaf(kProbeCells, diry, gy);
+        const float fx = floorf(qx), fy = floorf(qy);
+        const int cx = clampi(F.ix0 + (int)fx, 0, m.W - 2), cy = clampi(F.iy0 + (int)fy, 0, m.H - 2);
+        const float cxl = (float)(cx - F.ix0), cyl = (float)(cy - F.iy0);
+        const bool lower = (qx - cxl) >= (qy - cyl);
+        const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
+        const float z00 = ldg_f(zp), z01 = ldg_f(zp + 1), z10 = ldg_f(zp + m.pitch), z11 = ldg_f(zp + m.pitch + 1);
+        const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
+        const float Dv = lower ? z11 - z01 : z10 - z00;
+        const float gamma = F.cz - F.cgx * Du - F.cgy * Dv;
+        if (!(gamma < -kGammaMin)) {
+            *n_done = j;
+            return false;
+        }
+        const float ig = rcp_rn(gamma);
+        // The hit q = alpha / (gamma - beta tan th) cancels heavily for far / grazing beams
+        // (alpha: 15 m - 15 m; denominator: down to ~0.05), so these three are kept in float64.
+        const double Du_d = (double)Du, Dv_d = (double)Dv;
+        const double alpha_d = ((double)z00 - (double)F.oz) + ((double)F.g0x - (double)cxl) * Du_d +
+                               ((double)F.g0y - (double)cyl) * Dv_d;
+        const double beta_d = F.agx_d * Du_d + F.agy_d * Dv_d - F.az_d;
+        const double gamma_d = F.cz_d - F.cgx_d * Du_d - F.cgy_d * Dv_d;
+        const float alpha = (float)alpha_d, beta = (float)beta_d;
+        const float ta = alpha * ig, tb = beta * ig;          // T(p) = ta + tb p
+        // curve in grid units: G(p) = (X0 + p X1, Y0 + p Y1)
+        const float X0 = fmaf(F.cgx, ta, F.g0x), X1 = fmaf(F.cgx, tb, F.agx);
+        const float Y0 = fmaf(F.cgy, ta, F.g0y), Y1 = fmaf(F.cgy, tb, F.agy);
+        // leave the triangle through u = const, v = const or the diagonal u = v
+        const float bu = lower ? cxl + 1.f : cxl, bv = lower ? cyl : cyl + 1.f;
+        const float pu = X1 != 0.f ? (bu - X0) * rcp_rn(X1) : kBigT;
+        const float pv = Y1 != 0.f ? (bv - Y0) * rcp_rn(Y1) : kBigT;
+        const float dd = X1 - Y1;
+        const float pd = dd != 0.f ? ((cxl - cyl) - (X0 - Y0)) * rcp_rn(dd) : kBigT;
+        const float pmin = p_cur + 1.0e-5f;
+        float p_out = kBigT;
+        if (pu > pmin) p_out = pu;
+        if (pv > pmin && pv < p_out) p_out = pv;
+        if (pd > pmin && pd < p_out) p_out = pd;
+        if (!(p_out < kBigT)) p_out = p_cur + 0.25f * m.res;  // degenerate: creep
+        p_out = fminf(p_out, p_limit);
+        const float T_out = fmaf(tb, p_out, ta);
+        // beams whose line has met the profile by the end of this segment
+        while (j < n_side) {
+            const int b = beam0 + j * bstep;
+            const double tn_d = tan_t[b];
+            const float tn = (float)tn_d;
+            float range;
+            if (T_out * tn <= p_out) {
+                const float q = alpha * rcp_rn((float)(gamma_d - beta_d * tn_d));   // q of the intersection
+                const float t = q * sec_t[b];
+                range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
+            } else if (p_out * cosec_t[b] > m.range_max) {
+                range = m.range_max;                                  // cannot meet the profile within range
+            } else
+                break;
+            sink(b, range);
+            ++j;
+        }
+        if (p_out >= p_limit) {
+            at_limit = true;
+            break;
+        }
+        p_cur = p_out;
+        gx = fmaf(p_out, X1, X0);
+        gy = fmaf(p_out, Y1, Y0);
+        const float inv_len = 1.0f / sqrtf(fmaf(X1, X1, Y1 * Y1) + 1.0e-30f);
+        dirx = X1 * inv_len;
+        diry = Y1 * inv_len;
+    }
+    if (j < n_side && !at_limit) {       // ran out of steps before the profile was exhausted: not certified
+        *n_done = j;
+        return false;
+    }
+    for (; j < n_side; ++j) sink(beam0 + j * bstep, m.range_max);
+    *n_done = n_side;
+    return true;
+}
+
+// Beam tables of a planar fan as the profile merge needs them (device: shared memory).
+struct FanTables {
+    const float *dx, *dy, *dz;               // beam directions, sensor frame
+    const double *tan_t;                     // tan|th| (float64, see profile_side)
+    const float *sec_t, *cosec_t;            // 1/cos th, 1/|sin th| (0 = centre beam)
+    int B, n1, sgn1;                         // beams [0,n1) on the side sign sgn1, [n1,B) on the other
+    float c0[3], a0[3];                      // fan centre / lateral unit vectors, sensor frame
+};
+
+// All beams of one particle by profile merge.  Returns false when the particle cannot be
+// certified (not inside the map's interior, centre beam missed, a triangle with gamma >= 0):
+// the caller must then cast its beams ray by ray.  sink(beam, range) may have been called for
+// some beams before a failure; callers discard those.
+template <class Sink>
+AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const double p[3], const double R[9], Sink sink)
+{
+    const double reach = (double)m.range_max;
+    const double xmax = m.x0 + (double)(m.W - 1) * (double)m.res, ymax = m.y0 + (double)(m.H - 1) * (double)m.res;
+    if (!(p[0] - reach > m.x0 && p[0] + reach < xmax && p[1] - reach > m.y0 && p[1] + reach < ymax)) return false;
+    int ix0, iy0;
+    float lx0, ly0;
+    origin_cell(m, p, ix0, iy0, lx0, ly0);
+    // centre beam from the sensor: q0 = T(0)
+    Ray rc = make_ray(m, p, ix0, iy0, lx0, ly0, R, T.c0[0], T.c0[1], T.c0[2]);
+    const float q0 = raycast_from(m, rc, 0.f, true);
+    if (!(q0 < m.range_max)) return false;
+    if (q0 <= 0.f) {                          // sensor at / under the surface: every range is 0 (spec)
+        for (int b = 0; b < T.B; ++b) sink(b, 0.f);
+        return true;
+    }
+    double aw[3];
+    for (int a = 0; a < 3; ++a) aw[a] = R[3 * a] * T.a0[0] + R[3 * a + 1] * T.a0[1] + R[3 * a + 2] * T.a0[2];
+    ProfFrame F;
+    F.ix0 = ix0;
+    F.iy0 = iy0;
+    F.g0x = lx0;
+    F.g0y = ly0;
+    F.oz = rc.oz;
+    F.cgx = rc.dgx;
+    F.cgy = rc.dgy;
+    F.cz = rc.dz;
+    double cw[3];
+    for (int a = 0; a < 3; ++a) cw[a] = R[3 * a] * T.c0[0] + R[3 * a + 1] * T.c0[1] + R[3 * a + 2] * T.c0[2];
+    F.cgx_d = cw[0] * m.inv_res_d;
+    F.cgy_d = cw[1] * m.inv_res_d;
+    F.cz_d = cw[2];
+    const float an = (float)sqrt(aw[0] * aw[0] + aw[1] * aw[1]);
+    if (!(an > 1.0e-3f)) return false;        // fan plane (nearly) horizontal
+    for (int side = 0; side < 2; ++side) {
+        const int n_side = side == 0 ? T.n1 : T.B - T.n1;
+        if (n_side <= 0) continue;
+        const float sg = (float)(side == 0 ? T.sgn1 : -T.sgn1);
+        F.agx = sg * (float)(aw[0] * m.inv_res_d);
+        F.agy = sg * (float)(aw[1] * m.inv_res_d);
+        F.az = sg * (float)aw[2];
+        F.agx_d = (double)sg * aw[0] * m.inv_res_d;
+        F.agy_d = (double)sg * aw[1] * m.inv_res_d;
+        F.az_d = (double)sg * aw[2];
+        int n_done;
+        const int beam0 = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;
+        if (!profile_side(m, F, q0, n_side, beam0, bstep, T.tan_t, T.sec_t, T.cosec_t, sink, &n_done)) return false;
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -43,7 +43,7 @@ def raycast_poses(dem, shift, range_max, m2o, poses, beams, want_mip=False, shif
     swept = C.c_long()
     L.hs_raycast_poses(_p(z), C.c_int(H), C.c_int(W), C.c_double(dem["x0"]), C.c_double(dem["y0"]),
                        C.c_double(dem["res"]), C.c_int(shift), C.c_int(shift_hi), C.c_double(range_max), _p(m2o), _p(poses),
-                       C.c_long(n), _p(beams), C.c_int(B), _p(out), _p(mip), C.c_int(1 if fan else 0), C.byref(swept))
+                       C.c_long(n), _p(beams), C.c_int(B), _p(out), _p(mip), C.c_int(int(fan)), C.byref(swept))
     if want_swept:
         return out, int(swept.value)
     return (out, mip) if want_mip else out

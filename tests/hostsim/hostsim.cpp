@@ -127,6 +127,38 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
         int ix0, iy0;
         float lx0, ly0;
         origin_cell(v, p, ix0, iy0, lx0, ly0);
+        if (use_fan == 2) {
+            // profile merge (k_update_mbes_profile): one march per side, generic fallback
+            FanTables T;
+            std::vector<float> dx(B), dy(B), dz(B);
+            for (int b = 0; b < B; ++b) {
+                dx[b] = beams[3 * b];
+                dy[b] = beams[3 * b + 1];
+                dz[b] = beams[3 * b + 2];
+            }
+            T.dx = dx.data();
+            T.dy = dy.data();
+            T.dz = dz.data();
+            T.tan_t = plan.tan_t.data();
+            T.sec_t = plan.sec_t.data();
+            T.cosec_t = plan.inv_s.data();
+            T.B = B;
+            T.n1 = plan.n1;
+            T.sgn1 = plan.sgn1;
+            for (int a = 0; a < 3; ++a) {
+                T.c0[a] = plan.c0[a];
+                T.a0[a] = plan.a0[a];
+            }
+            float *row = out + (size_t)i * B;
+            bool ok = plan.planar && profile_particle(v, T, p, R, [&](int b, float range) { row[b] = range; });
+            if (ok) *n_swept += B;
+            else
+                for (int b = 0; b < B; ++b) {
+                    Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
+                    row[b] = raycast_one(v, ray);
+                }
+            continue;
+        }
         if (!use_fan) {
             for (int b = 0; b < B; ++b) {
                 Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
@@ -134,23 +166,48 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
             }
             continue;
         }
-        // the kernels' lane / chunk sweep, lane by lane (k_update_mbes, k_raycast_poses)
+        // the kernels' fan_cast, lane by lane (auvpf_kernels.cuh)
         const bool sweep_ok = plan.planar && fan_sweep_valid(v, p, R, plan.c0);
-        for (int lane = 0; lane < kFanLanes; ++lane) {
-            float p_clear = 0.f;
-            for (int k = 0; k < plan.chunk; ++k) {
-                int o = plan.order[(size_t)lane * plan.chunk + k];
+        const int C = plan.chunk;
+        if (!sweep_ok) {
+            for (int b = 0; b < B; ++b) {
+                Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
+                out[(size_t)i * B + b] = raycast_one(v, ray);
+            }
+            continue;
+        }
+        float p_clear[kFanLanes];
+        const int L1 = plan.lanes_first;
+        const int max_chain = std::max(L1, kFanLanes - L1) - 1;
+        for (int c = 0; c <= max_chain; ++c)
+            for (int lane = 0; lane < kFanLanes; ++lane) {
+                const bool first_side = lane < L1;
+                const int chain = first_side ? (L1 - 1 - lane) : (lane - L1);
+                if (chain != c) continue;
+                int o = plan.order[(size_t)lane * C];
+                p_clear[lane] = 0.f;
                 if (o < 0) continue;
                 int b = o & (kOrdFull - 1);
-                bool full = (o & kOrdFull) != 0 || !sweep_ok;
                 Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
-                float t_lo = full ? 0.f : sweep_bound(p_clear, plan.inv_s[b], v.res);
-                float range = raycast_from(v, ray, t_lo);
+                float t_lo = 0.f;
+                (void)first_side;   // chunk starts are traversed from the sensor (see fan_cast)
+                float range = raycast_from(v, ray, t_lo, true);
                 if (t_lo > 0.f) ++*n_swept;
-                p_clear = range * plan.s[b];
+                p_clear[lane] = range * plan.s[b];
                 out[(size_t)i * B + b] = range;
             }
-        }
+        for (int lane = 0; lane < kFanLanes; ++lane)
+            for (int k = 1; k < C; ++k) {
+                int o = plan.order[(size_t)lane * C + k];
+                if (o < 0) continue;
+                int b = o & (kOrdFull - 1);
+                Ray ray = make_ray(v, p, ix0, iy0, lx0, ly0, R, beams[3 * b], beams[3 * b + 1], beams[3 * b + 2]);
+                float t_lo = sweep_bound(p_clear[lane], plan.inv_s[b]);
+                float range = raycast_from(v, ray, t_lo, true);
+                if (t_lo > 0.f) ++*n_swept;
+                p_clear[lane] = range * plan.s[b];
+                out[(size_t)i * B + b] = range;
+            }
     }
 }
 

@@ -27,9 +27,10 @@ def _cloud(rng, n, centre, spread, roll_pitch=0.03, z=-5.0):
     return poses
 
 
-def _compare(dem, shift, poses, beams, m2o, range_max, max_fragile_frac=2e-3, shift_hi=0):
+def _compare(dem, shift, poses, beams, m2o, range_max, max_fragile_frac=2e-3, shift_hi=0, fan=1):
+    beams = np.asarray(beams, np.float32).astype(np.float64)      # identical (fp32) directions for both arms
     out = c_oracle.update_mbes(dem, poses, m2o, beams, None, 1.0, 0.5, range_max, want_ranges=True, want_diag=True)
-    r = hs.raycast_poses(dem, shift, range_max, m2o, poses, beams.astype(np.float32), shift_hi=shift_hi)
+    r = hs.raycast_poses(dem, shift, range_max, m2o, poses, beams.astype(np.float32), shift_hi=shift_hi, fan=fan)
     ro, dg = out["ranges"], out["diag"]
     fragile = (dg[..., 0] < FRAGILE) | (dg[..., 1] < FRAGILE) | (dg[..., 2] < FRAGILE)
     err = np.abs(r - ro)
@@ -269,3 +270,36 @@ def test_fan_plan():
     r, nsw = hs.raycast_poses(world.make_dem(100, 2.0), 1, 60.0, np.eye(4), np.array([[100.0, 100.0, -5, 0, 0, 0.3]]),
                               shuffled, want_swept=True)
     assert nsw == 0
+
+
+@pytest.mark.parametrize("name", ["C2", "C3", "tilted", "ridged", "ridged_tilted", "border", "short_range"])
+def test_profile_merge_vs_oracle(name):
+    """Profile merge (one march per fan side, O(cells + beams)) returns the oracle's first hits."""
+    rng = np.random.default_rng(4)
+    rmax, lo, hi, frag = 120.0, 2, 5, 5e-3
+    if name == "C2":
+        dem, poses, beams, lo, hi = world.make_dem(500, 2.0), _cloud(rng, 96, (450.0, 450.0), 3.0), world.make_beams(256), 1, 0
+    elif name == "C3":
+        dem, poses, beams = world.make_dem(1200, 0.5), _cloud(rng, 96, (300.0, 300.0), 3.0), world.make_beams(512)
+    elif name == "tilted":
+        dem, poses, beams = world.make_dem(1200, 0.5), _cloud(rng, 96, (300.0, 300.0), 3.0, roll_pitch=0.3), world.make_beams(512, 70.0)
+    elif name == "ridged":
+        dem, poses, beams, rmax, frag = _ridged_dem(), _cloud(rng, 48, (100.0, 100.0), 8.0, roll_pitch=0.04, z=-21.0), \
+            world.make_beams(512, 70.0), 60.0, 5e-2
+    elif name == "ridged_tilted":
+        dem, poses, beams, rmax, frag = _ridged_dem(), _cloud(rng, 48, (100.0, 100.0), 8.0, roll_pitch=0.2, z=-21.0), \
+            world.make_beams(512, 70.0), 60.0, 5e-2
+    elif name == "border":          # reach leaves the map: every particle falls back to per-ray traversal
+        dem, poses, beams, frag = world.make_dem(300, 2.0, seed=11), _cloud(rng, 32, (8.0, 590.0), 6.0), world.make_beams(128, 75.0), 2e-2
+    else:                           # short range_max: outer beams miss
+        dem, poses, beams, rmax = world.make_dem(500, 2.0), _cloud(rng, 48, (450.0, 450.0), 3.0), world.make_beams(256), 30.0
+    r, n_prof = hs.raycast_poses(dem, lo, rmax, np.eye(4), poses, beams.astype(np.float32), shift_hi=hi, fan=2, want_swept=True)
+    ro, err, fragile = _compare(dem, lo, poses, beams, np.eye(4), rmax, max_fragile_frac=frag, shift_hi=hi, fan=2)
+    if name == "border":
+        assert n_prof == 0
+    elif name in ("tilted", "ridged_tilted"):
+        assert n_prof >= 0.8 * r.size           # steep triangle x large tilt: a few particles fall back
+    else:
+        assert n_prof == r.size                 # every particle certified by the profile march
+    if name == "short_range":
+        assert (ro == rmax).any() and (ro < rmax).any()
