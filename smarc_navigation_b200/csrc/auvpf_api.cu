@@ -95,7 +95,7 @@ struct auvpf_handle {
     // map / sensor
     float *dem_z = nullptr, *mip = nullptr, *mip_hi = nullptr, *beams = nullptr, *meas = nullptr;
     float *beam_aux = nullptr;   // [3B]: |sin th|, 1/|sin th|, 1/cos th
-    double *beam_tan = nullptr;  // [B]: tan |th| (profile merge)
+    double *beam_tan = nullptr;  // [2B]: tan |th|, 1 / cos th (profile merge)
     unsigned char *flags = nullptr;   // [N]: particle needs the per-ray kernel
     DevBuf probe_flags;
     int *beam_order = nullptr;   // [32 * chunk]
@@ -818,13 +818,14 @@ int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
     for (int b = 0; b < B; ++b) {
         aux[b] = plan.s[b];
         aux[B + b] = plan.inv_s[b];
-        aux[2 * B + b] = plan.sec_t[b];
+        aux[2 * B + b] = (float)plan.sec_t[b];
     }
     CU(cudaMalloc(&h->beams, sizeof(float) * 3 * B));
     CU(cudaMalloc(&h->meas, sizeof(float) * (size_t)B * h->F));
     CU(cudaMalloc(&h->beam_aux, sizeof(float) * 3 * B));
-    CU(cudaMalloc(&h->beam_tan, sizeof(double) * B));
+    CU(cudaMalloc(&h->beam_tan, sizeof(double) * 2 * B));
     CU(cudaMemcpy(h->beam_tan, plan.tan_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->beam_tan + B, plan.sec_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
     if (!h->flags) CU(cudaMalloc(&h->flags, (size_t)h->N));
     CU(cudaMalloc(&h->beam_order, sizeof(int) * plan.order.size()));
     CU(cudaMemcpy(h->beams, host.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
@@ -976,7 +977,7 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
         const unsigned char *only = nullptr;
         if (h->fan.planar && h->use_profile) {
             // profile merge: one thread per particle; what it cannot certify is flagged ...
-            const size_t smp = (sizeof(double) + 3 * sizeof(float)) * h->B;
+            const size_t smp = (2 * sizeof(double) + 2 * sizeof(float)) * h->B;
             k_update_mbes_profile<<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
                 h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
                 (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flags);
@@ -1011,7 +1012,7 @@ int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges
         if (h->fan.planar && h->use_profile) {
             void *fl;
             if ((rc = slot_reserve(h, S_OUT1, (size_t)n, &fl))) return rc;
-            const size_t smp = (sizeof(double) + 2 * sizeof(float)) * h->B;
+            const size_t smp = (2 * sizeof(double) + sizeof(float)) * h->B;
             k_raycast_poses_profile<<<grid1(n, kProfThreads, 1), kProfThreads, smp, h->stream>>>(
                 pd, n, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->B, od, static_cast<unsigned char *>(fl));
             only = static_cast<unsigned char *>(fl);

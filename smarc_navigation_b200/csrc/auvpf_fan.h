@@ -17,9 +17,9 @@ struct FanPlan {
     float c0[3] = {0, 0, -1};        // fan centre direction (sensor frame)
     int chunk = 1;                   // beams per lane (loop trip count)
     int lanes_first = 0;             // lanes holding the first side (lower beam indices) of the fan
-    std::vector<float> s, inv_s;     // |sin th_b| and its reciprocal (0 = unusable)
-    std::vector<double> tan_t;       // tan |th_b| (profile merge; float64, it enters a cancelling denominator)
-    std::vector<float> sec_t;        // 1 / cos th_b
+    std::vector<float> s, inv_s;     // |lateral component| of beam b (= |sin th_b| for a unit vector), reciprocal (0 = unusable)
+    std::vector<double> tan_t;       // |lateral| / along-centre component (profile merge; float64: it multiplies q ~ 30 m)
+    std::vector<double> sec_t;       // 1 / along-centre component: range = q sec (exact for the vector as given)
     float a0[3] = {0, 1, 0};         // lateral unit vector (sensor frame): th > 0 leans towards +a0
     int n1 = 0;                      // beams [0, n1) are one side of the centre, [n1, B) the other
     int sgn1 = -1;                   // sign of th on the first side
@@ -37,7 +37,7 @@ inline FanPlan plan_fan(const float *dirs, int B)
     f.s.assign(B, 0.f);
     f.inv_s.assign(B, 0.f);
     f.tan_t.assign(B, 0.0);
-    f.sec_t.assign(B, 1.f);
+    f.sec_t.assign(B, 1.0);
     std::vector<double> th(B, 0.0);
     auto D = [&](int b, int a) { return (double)dirs[3 * b + a]; };
     // plane normal from the most separated pair (first / last), centre = normalised mean
@@ -66,7 +66,8 @@ inline FanPlan plan_fan(const float *dirs, int B)
                 double pa = D(b, 0) * a0[0] + D(b, 1) * a0[1] + D(b, 2) * a0[2];
                 double len = std::sqrt(D(b, 0) * D(b, 0) + D(b, 1) * D(b, 1) + D(b, 2) * D(b, 2));
                 th[b] = std::atan2(pa, pc);
-                if (std::fabs(off) > 1e-5 || std::fabs(len - 1.0) > 1e-4 || pc < 0.17) ok = false;   // |th| < ~80 deg
+                // off-plane by more than float32 rounding would move a 100 m hit by more than the range tolerance
+                if (std::fabs(off) > 2e-7 || std::fabs(len - 1.0) > 1e-4 || pc < 0.17) ok = false;   // |th| < ~80 deg
             }
             for (int b = 1; b < B && ok; ++b)
                 if (!((th[b] > th[b - 1]) == (th[1] > th[0])) || th[b] == th[b - 1]) ok = false;       // strictly monotone
@@ -77,11 +78,12 @@ inline FanPlan plan_fan(const float *dirs, int B)
                     f.a0[a] = (float)a0[a];
                 }
                 for (int b = 0; b < B; ++b) {
-                    double sn = std::fabs(std::sin(th[b]));
-                    f.s[b] = (float)sn;
-                    f.inv_s[b] = sn > 1e-6 ? (float)(1.0 / sn) : 0.f;
-                    f.tan_t[b] = std::fabs(std::tan(th[b]));
-                    f.sec_t[b] = (float)(1.0 / std::cos(th[b]));
+                    const double pc = D(b, 0) * c[0] + D(b, 1) * c[1] + D(b, 2) * c[2];
+                    const double pa = std::fabs(D(b, 0) * a0[0] + D(b, 1) * a0[1] + D(b, 2) * a0[2]);
+                    f.s[b] = (float)pa;
+                    f.inv_s[b] = pa > 1e-6 ? (float)(1.0 / pa) : 0.f;
+                    f.tan_t[b] = pa / pc;
+                    f.sec_t[b] = 1.0 / pc;
                 }
             }
         }

@@ -406,25 +406,25 @@ k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, Dem
 // per-ray kernel above.
 constexpr int kProfThreads = 128;
 
-// shared memory: tan (double B) | sec (float B) | cosec (float B) | measured range (float B)
-__device__ __forceinline__ void stage_profile_tables(double *s_tan, float *s_sec, float *s_cosec, int B,
+// shared memory: tan (double B) | sec (double B) | |sin| (float B) | measured range (float B)
+// beam_tan = [tan | sec] (2B doubles), beam_aux[0..B) = |sin|
+__device__ __forceinline__ void stage_profile_tables(double *s_tan, double *s_sec, float *s_sin, int B,
                                                      const double *beam_tan, const float *beam_aux)
 {
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         s_tan[b] = beam_tan[b];
-        s_cosec[b] = beam_aux[B + b];
-        s_sec[b] = beam_aux[2 * B + b];
+        s_sec[b] = beam_tan[B + b];
+        s_sin[b] = beam_aux[b];
     }
 }
 
-__device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, const double *s_tan, const float *s_sec,
-                                                 const float *s_cosec)
+__device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, const double *s_tan, const double *s_sec,
+                                                 const float *s_sin)
 {
     FanTables T;
-    T.dx = T.dy = T.dz = nullptr;
     T.tan_t = s_tan;
     T.sec_t = s_sec;
-    T.cosec_t = s_cosec;
+    T.sin_t = s_sin;
     T.B = B;
     T.n1 = fan.n1;
     T.sgn1 = fan.sgn1;
@@ -442,12 +442,12 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
                       float log_norm_per_beam, float *__restrict__ logw, unsigned char *__restrict__ flags)
 {
     extern __shared__ double smd[];
-    double *s_tan = smd;
-    float *s_sec = reinterpret_cast<float *>(smd + B), *s_cosec = s_sec + B, *s_meas = s_cosec + B;
+    double *s_tan = smd, *s_sec = smd + B;
+    float *s_sin = reinterpret_cast<float *>(smd + 2 * B), *s_meas = s_sin + B;
     __shared__ int s_valid;
     const int f = blockIdx.y;
     if (threadIdx.x == 0) s_valid = 0;
-    stage_profile_tables(s_tan, s_sec, s_cosec, B, beam_tan, beam_aux);
+    stage_profile_tables(s_tan, s_sec, s_sin, B, beam_tan, beam_aux);
     __syncthreads();
     int nv = 0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -464,7 +464,7 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
     double p[3];
     double R[9];
     particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
-    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_cosec);
+    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_sin);
     float acc = 0.f;
     const bool ok = profile_particle(dem, T, p, R, [&](int b, float range) {
         const float rm = s_meas[b];
@@ -481,9 +481,9 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
                         float *__restrict__ out, unsigned char *__restrict__ flags)
 {
     extern __shared__ double smd[];
-    double *s_tan = smd;
-    float *s_sec = reinterpret_cast<float *>(smd + B), *s_cosec = s_sec + B;
-    stage_profile_tables(s_tan, s_sec, s_cosec, B, beam_tan, beam_aux);
+    double *s_tan = smd, *s_sec = smd + B;
+    float *s_sin = reinterpret_cast<float *>(smd + 2 * B);
+    stage_profile_tables(s_tan, s_sec, s_sin, B, beam_tan, beam_aux);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
     if (i >= n) return;
@@ -491,7 +491,7 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
     double p[3];
     double R[9];
     particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
-    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_cosec);
+    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_sin);
     float *row = out + (size_t)i * B;
     const bool ok = profile_particle(dem, T, p, R, [&](int b, float range) { row[b] = range; });
     flags[i] = ok ? 0 : 1;

@@ -639,131 +639,177 @@ AUVPF_HD void origin_cell(const DemView &m, const double p[3], int &ix0, int &iy
 // ---------------------------------------------------------------------------------------------
 // Profile merge: all beams of one side of a planar fan in
 // O(cells + beams).  In fan-plane coordinates (p lateral, q along the fan centre c) the
-// terrain is a single-valued profile q = T(p) that is LINEAR inside every DEM triangle:
-//     T(p) = (alpha + beta p) / gamma,   gamma = c_z - c_g . grad h  (< 0 when the height above
-//     the terrain decreases along c).
-// Beam th is the line q = p cot th; it hits where it first meets the profile, and because a
+// terrain is a single-valued profile q = T(p) that is LINEAR inside every DEM triangle, with
+// slope  s = dT/dp = beta / gamma,  beta = a_g . grad h - a_z,  gamma = c_z - c_g . grad h
+// (gamma < 0 when the height above the terrain decreases along c).
+// Beam th is the line p = q tan th; it hits where it first meets the profile, and because a
 // more outward beam is higher at equal p, the hits of th_0 < th_1 < ... occur at increasing p.
 // So the profile is marched ONCE outward, triangle by triangle, and the beams are resolved in
 // order on the way (a merge of two monotone sequences) -- the same first hits as casting each
-// ray separately, occlusions included.  Needs: planar sorted fan, the map covering the sensor's
-// reach, gamma < 0 on every triangle met (checked on the fly; otherwise the caller falls back
-// to per-ray traversal).
+// ray separately, occlusions included.
+//
+// The march is a DDA over the TRIANGULATION in cell-local coordinates: the state is the
+// triangle (cell + which half), the curve point (u, v) inside the cell, and the fan
+// coordinates (p_cur, q_cur) of that point in float64.  Inside a triangle the curve is the
+// straight line (u, v) + dp (a_g + s c_g); it leaves through the nearest of the triangle's
+// other two edges, and the neighbour across that edge is known exactly (no point location, no
+// rounding-dependent topology).  Everything that is differenced stays small (cell-local), so
+// float32 suffices except for the two accumulators and the beam's gap to the curve point.
+// Needs: planar sorted fan, the map covering the sensor's reach, gamma < 0 on every triangle
+// met (checked on the fly; otherwise the caller falls back to per-ray traversal).
 struct ProfFrame {
-    int ix0, iy0;          // origin cell
-    float g0x, g0y;        // origin in local grid units
-    float oz;              // origin height
     float agx, agy, az;    // lateral unit vector of this side: xy in grid units per metre, z
     float cgx, cgy, cz;    // fan centre direction, same units
-    double agx_d, agy_d, az_d, cgx_d, cgy_d, cz_d;   // the same in float64 (hit denominators)
 };
 
-constexpr float kGammaMin = 0.05f;      // -gamma must exceed this (|cos| of the worst slope/tilt combination)
-constexpr float kProbeCells = 1.0e-3f;  // how far beyond a boundary the next triangle is looked up
+struct ProfFrameD {        // the same frame in float64, read only by the rare re-anchored hit (precise_hit)
+    double gox, goy, oz;   // sensor in absolute grid units, height
+    double agx, agy, az;   // lateral unit vector of the FIRST side (the other side negates it)
+    double cgx, cgy, cz;
+};
 
-// Marches one side.  tan_t / sec_t / cosec_t are indexed by beam; the j-th beam outward is
-// beam0 + j * bstep.  Calls sink(beam, range) for every beam of the side in outward order.
-// Returns false if the side cannot be certified (caller must recast its beams ray by ray;
-// nothing has been emitted for beams >= the returned *n_done).
+struct ProfStart {         // the curve point under the sensor (p = 0), shared by both sides
+    int cx, cy;            // its cell (absolute)
+    float u, v;            // position inside the cell, [0, 1]
+    double q0;             // centre-beam range, re-solved in float64 on that triangle's plane
+};
+
+#if defined(AUVPF_DEBUG_REASONS) && !defined(__CUDA_ARCH__)
+extern long g_prof_reasons[8];      // test-only: why profile marches gave up (tests/hostsim)
+#define AUVPF_REASON(k) (++g_prof_reasons[k])
+#else
+#define AUVPF_REASON(k) ((void)0)
+#endif
+
+constexpr float kGammaMin = 0.05f;       // -gamma must exceed this (|cos| of the worst slope/tilt combination)
+constexpr float kDenPrecise = 0.1f;     // a beam closing on the profile slower than this is re-solved in float64
+
+// A beam that meets a facet at a grazing angle amplifies the ~1e-6 m drift of the incremental
+// (p_cur, q_cur) by 1 / den.  Such hits are re-solved from scratch on the facet's plane:
+// q = alpha / (gamma - beta tan th) with everything in float64 relative to the sensor.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+double precise_hit(const ProfFrameD *D, double sg, int cx, int cy, double z00, double Du, double Dv, double tn)
+{
+    const double alpha = (z00 - D->oz) + (D->gox - (double)cx) * Du + (D->goy - (double)cy) * Dv;
+    const double beta = sg * (D->agx * Du + D->agy * Dv - D->az);
+    const double gamma = D->cz - D->cgx * Du - D->cgy * Dv;
+    return alpha / (gamma - beta * tn);
+}
+
+// Marches one side.  Tables are indexed by beam; the j-th beam outward is beam0 + j * bstep.
+// Calls sink(beam, range) for every beam of the side in outward order.  Returns false if the
+// side cannot be certified (caller must recast the particle's beams ray by ray).
 template <class Sink>
-AUVPF_HD bool profile_side(const DemView &m, const ProfFrame &F, float q0, int n_side, int beam0, int bstep,
-                           const double *tan_t, const float *sec_t, const float *cosec_t, Sink sink, int *n_done)
+AUVPF_HD bool profile_side(const DemView &m, const ProfFrame &F, const ProfFrameD *D, double sg, const ProfStart &S,
+                           int n_side, int beam0, int bstep, const double *tan_t, const double *sec_t,
+                           const float *sin_t, Sink sink)
 {
     int j = 0;
-    *n_done = 0;
-    float p_cur = 0.f;
-    // curve point at p_cur (local grid units), starts under the sensor along c
-    float gx = fmaf(q0, F.cgx, F.g0x), gy = fmaf(q0, F.cgy, F.g0y);
-    const float p_limit = m.range_max;
+    int cx = S.cx, cy = S.cy;
+    float u = S.u, v = S.v;
+    bool lower = u >= v;
+    int entry = -1;                        // canonical edge the curve entered the triangle through
+    double p_cur = 0.0, q_cur = S.q0;
     const int max_steps = 8 * (int)(m.range_max / m.res) + 256;
-    bool at_limit = false;
-    float dirx = 0.f, diry = 0.f;         // the start point lies inside its triangle: no probe step
-    for (int step = 0; step < max_steps && j < n_side; ++step) {
-        // triangle just ahead of the current curve point: continue a hair along the direction
-        // the curve had when it reached the boundary
-        const float qx = fmaf(kProbeCells, dirx, gx), qy = fmaf(kProbeCells, diry, gy);
-        const float fx = floorf(qx), fy = floorf(qy);
-        const int cx = clampi(F.ix0 + (int)fx, 0, m.W - 2), cy = clampi(F.iy0 + (int)fy, 0, m.H - 2);
-        const float cxl = (float)(cx - F.ix0), cyl = (float)(cy - F.iy0);
-        const bool lower = (qx - cxl) >= (qy - cyl);
-        const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
-        const float z00 = ldg_f(zp), z01 = ldg_f(zp + 1), z10 = ldg_f(zp + m.pitch), z11 = ldg_f(zp + m.pitch + 1);
+    const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
+    float z00 = ldg_f(zp), z01 = ldg_f(zp + 1), z10 = ldg_f(zp + m.pitch), z11 = ldg_f(zp + m.pitch + 1);
+    for (int step = 0; step < max_steps; ++step) {
         const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
         const float Dv = lower ? z11 - z01 : z10 - z00;
         const float gamma = F.cz - F.cgx * Du - F.cgy * Dv;
-        if (!(gamma < -kGammaMin)) {
-            *n_done = j;
-            return false;
+        if (!(gamma < -kGammaMin)) { AUVPF_REASON(0); return false; }
+        const float beta = F.agx * Du + F.agy * Dv - F.az;
+        const float s = fast_div(beta, gamma);                // profile slope dT/dp
+        const float X1 = fmaf(s, F.cgx, F.agx), Y1 = fmaf(s, F.cgy, F.agy);   // d(u,v)/dp
+        // canonical triangle a >= b: (a, b) = (u, v) in the lower half, (v, u) in the upper half.
+        // Edges: 0: a = 1 (reached when A1 > 0), 1: b = 0 (B1 < 0), 2: a = b (B1 > A1).
+        const float a = lower ? u : v, b = lower ? v : u;
+        const float A1 = lower ? X1 : Y1, B1 = lower ? Y1 : X1;
+        float bn = kBigT, bd = 1.f;                            // nearest exit = bn / bd
+        int be = -1;
+        if (entry != 0 && A1 > 0.f) {
+            bn = 1.f - a;
+            bd = A1;
+            be = 0;
         }
-        const float ig = rcp_rn(gamma);
-        // The hit q = alpha / (gamma - beta tan th) cancels heavily for far / grazing beams
-        // (alpha: 15 m - 15 m; denominator: down to ~0.05), so these three are kept in float64.
-        const double Du_d = (double)Du, Dv_d = (double)Dv;
-        const double alpha_d = ((double)z00 - (double)F.oz) + ((double)F.g0x - (double)cxl) * Du_d +
-                               ((double)F.g0y - (double)cyl) * Dv_d;
-        const double beta_d = F.agx_d * Du_d + F.agy_d * Dv_d - F.az_d;
-        const double gamma_d = F.cz_d - F.cgx_d * Du_d - F.cgy_d * Dv_d;
-        const float alpha = (float)alpha_d, beta = (float)beta_d;
-        const float ta = alpha * ig, tb = beta * ig;          // T(p) = ta + tb p
-        // curve in grid units: G(p) = (X0 + p X1, Y0 + p Y1)
-        const float X0 = fmaf(F.cgx, ta, F.g0x), X1 = fmaf(F.cgx, tb, F.agx);
-        const float Y0 = fmaf(F.cgy, ta, F.g0y), Y1 = fmaf(F.cgy, tb, F.agy);
-        // leave the triangle through u = const, v = const or the diagonal u = v
-        const float bu = lower ? cxl + 1.f : cxl, bv = lower ? cyl : cyl + 1.f;
-        const float pu = X1 != 0.f ? (bu - X0) * rcp_rn(X1) : kBigT;
-        const float pv = Y1 != 0.f ? (bv - Y0) * rcp_rn(Y1) : kBigT;
-        const float dd = X1 - Y1;
-        const float pd = dd != 0.f ? ((cxl - cyl) - (X0 - Y0)) * rcp_rn(dd) : kBigT;
-        const float pmin = p_cur + 1.0e-5f;
-        float p_out = kBigT;
-        if (pu > pmin) p_out = pu;
-        if (pv > pmin && pv < p_out) p_out = pv;
-        if (pd > pmin && pd < p_out) p_out = pd;
-        if (!(p_out < kBigT)) p_out = p_cur + 0.25f * m.res;  // degenerate: creep
-        p_out = fminf(p_out, p_limit);
-        const float T_out = fmaf(tb, p_out, ta);
-        // beams whose line has met the profile by the end of this segment
+        if (entry != 1 && B1 < 0.f && b * bd < bn * -B1) {
+            bn = b;
+            bd = -B1;
+            be = 1;
+        }
+        if (entry != 2 && B1 > A1 && (a - b) * bd < bn * (B1 - A1)) {
+            bn = a - b;
+            bd = B1 - A1;
+            be = 2;
+        }
+        if (be < 0) { AUVPF_REASON(1); return false; }         // curve turns back through its entry edge
+        const float dp = fast_div(bn, bd);
+        const double p_out = p_cur + (double)dp;
+        const float p_out_f = (float)p_out;
+        // beams whose line meets the profile inside this segment.  gap = lateral distance of the
+        // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
         while (j < n_side) {
-            const int b = beam0 + j * bstep;
-            const double tn_d = tan_t[b];
-            const float tn = (float)tn_d;
+            const int bb = beam0 + j * bstep;
+            const double tn = tan_t[bb];
+            const float gap = (float)(q_cur * tn - p_cur);
+            const float den = (float)(1.0 - (double)s * tn);
             float range;
-            if (T_out * tn <= p_out) {
-                const float q = alpha * rcp_rn((float)(gamma_d - beta_d * tn_d));   // q of the intersection
-                const float t = q * sec_t[b];
+            if (gap <= dp * den) {
+                const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
+                double qh = q_cur + (double)(s * dph);
+                if (den < kDenPrecise)
+                    qh = precise_hit(D, sg, cx, cy, (double)z00, (double)(lower ? z01 : z11) - (double)(lower ? z00 : z10),
+                                     (double)(lower ? z11 : z10) - (double)(lower ? z01 : z00), tn);
+                const float t = (float)(qh * sec_t[bb]);
                 range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
-            } else if (p_out * cosec_t[b] > m.range_max) {
-                range = m.range_max;                                  // cannot meet the profile within range
+            } else if (p_out_f > sin_t[bb] * m.range_max) {
+                range = m.range_max;                           // cannot meet the profile within range
             } else
                 break;
-            sink(b, range);
+            sink(bb, range);
             ++j;
         }
-        if (p_out >= p_limit) {
-            at_limit = true;
-            break;
-        }
+        if (j >= n_side) return true;
+        // advance to the exit point and step into the neighbour across that edge
+        q_cur += (double)(s * dp);
         p_cur = p_out;
-        gx = fmaf(p_out, X1, X0);
-        gy = fmaf(p_out, Y1, Y0);
-        const float inv_len = 1.0f / sqrtf(fmaf(X1, X1, Y1 * Y1) + 1.0e-30f);
-        dirx = X1 * inv_len;
-        diry = Y1 * inv_len;
+        u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
+        v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
+        if (be == 2) {
+            u = v = 0.5f * (u + v);
+        } else {
+            const int dir = be == 0 ? 1 : -1;                  // edge 0: coordinate reached 1, edge 1: reached 0
+            const float nc = be == 0 ? 0.f : 1.f;
+            if ((be == 0) == lower) {                          // a u-edge (x = const)
+                cx += dir;
+                u = nc;
+            } else {
+                cy += dir;
+                v = nc;
+            }
+            if (cx < 0 || cy < 0 || cx > m.W - 2 || cy > m.H - 2) { AUVPF_REASON(2); return false; }   // left the map
+            zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
+            z00 = ldg_f(zp);
+            z01 = ldg_f(zp + 1);
+            z10 = ldg_f(zp + m.pitch);
+            z11 = ldg_f(zp + m.pitch + 1);
+        }
+        lower = !lower;
+        entry = be == 2 ? 2 : 1 - be;
     }
-    if (j < n_side && !at_limit) {       // ran out of steps before the profile was exhausted: not certified
-        *n_done = j;
-        return false;
-    }
-    for (; j < n_side; ++j) sink(beam0 + j * bstep, m.range_max);
-    *n_done = n_side;
-    return true;
+    AUVPF_REASON(3);
+    return false;                            // ran out of steps: not certified
 }
 
 // Beam tables of a planar fan as the profile merge needs them (device: shared memory).
 struct FanTables {
-    const float *dx, *dy, *dz;               // beam directions, sensor frame
-    const double *tan_t;                     // tan|th| (float64, see profile_side)
-    const float *sec_t, *cosec_t;            // 1/cos th, 1/|sin th| (0 = centre beam)
+    const double *tan_t;                     // |lateral| / along-centre component of the beam direction
+    const double *sec_t;                     // 1 / along-centre component
+    const float *sin_t;                      // |lateral| component
     int B, n1, sgn1;                         // beams [0,n1) on the side sign sgn1, [n1,B) on the other
     float c0[3], a0[3];                      // fan centre / lateral unit vectors, sensor frame
 };
@@ -783,43 +829,63 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
     origin_cell(m, p, ix0, iy0, lx0, ly0);
     // centre beam from the sensor: q0 = T(0)
     Ray rc = make_ray(m, p, ix0, iy0, lx0, ly0, R, T.c0[0], T.c0[1], T.c0[2]);
-    const float q0 = raycast_from(m, rc, 0.f, true);
-    if (!(q0 < m.range_max)) return false;
-    if (q0 <= 0.f) {                          // sensor at / under the surface: every range is 0 (spec)
+    const float q0f = raycast_from(m, rc, 0.f, true);
+    if (!(q0f < m.range_max)) { AUVPF_REASON(6); return false; }
+    if (q0f <= 0.f) {                         // sensor at / under the surface: every range is 0 (spec)
         for (int b = 0; b < T.B; ++b) sink(b, 0.f);
         return true;
     }
-    double aw[3];
-    for (int a = 0; a < 3; ++a) aw[a] = R[3 * a] * T.a0[0] + R[3 * a + 1] * T.a0[1] + R[3 * a + 2] * T.a0[2];
+    double aw[3], cw[3];
+    for (int a = 0; a < 3; ++a) {
+        aw[a] = R[3 * a] * T.a0[0] + R[3 * a + 1] * T.a0[1] + R[3 * a + 2] * T.a0[2];
+        cw[a] = R[3 * a] * T.c0[0] + R[3 * a + 1] * T.c0[1] + R[3 * a + 2] * T.c0[2];
+    }
+    if (!(aw[0] * aw[0] + aw[1] * aw[1] > 1.0e-6)) return false;       // fan plane (nearly) horizontal
+    // anchor: the triangle under the centre hit, and the hit re-solved on its plane in float64
+    const double gox = (p[0] - m.x0) * m.inv_res_d, goy = (p[1] - m.y0) * m.inv_res_d;   // sensor, grid units
+    const double cgx = cw[0] * m.inv_res_d, cgy = cw[1] * m.inv_res_d;
+    ProfStart S;
+    {
+        const double hx = gox + (double)q0f * cgx, hy = goy + (double)q0f * cgy;
+        S.cx = clampi((int)floor(hx), 0, m.W - 2);
+        S.cy = clampi((int)floor(hy), 0, m.H - 2);
+        const bool lower = (hx - (double)S.cx) >= (hy - (double)S.cy);
+        const float *zp = m.z + (ptrdiff_t)S.cy * m.pitch + S.cx;
+        const double z00 = ldg_f(zp), z01 = ldg_f(zp + 1), z10 = ldg_f(zp + m.pitch), z11 = ldg_f(zp + m.pitch + 1);
+        const double Du = lower ? z01 - z00 : z11 - z10, Dv = lower ? z11 - z01 : z10 - z00;
+        const double alpha = (z00 - p[2]) + (gox - (double)S.cx) * Du + (goy - (double)S.cy) * Dv;
+        const double gamma = cw[2] - cgx * Du - cgy * Dv;
+        if (!(gamma < -(double)kGammaMin)) { AUVPF_REASON(4); return false; }
+        S.q0 = alpha / gamma;
+        if (!(fabs(S.q0 - (double)q0f) < 1.0e-3)) { AUVPF_REASON(5); return false; }       // centre hit not on this triangle's plane
+        const double ux = gox + S.q0 * cgx - (double)S.cx, vy = goy + S.q0 * cgy - (double)S.cy;
+        S.u = (float)(ux < 0.0 ? 0.0 : (ux > 1.0 ? 1.0 : ux));
+        S.v = (float)(vy < 0.0 ? 0.0 : (vy > 1.0 ? 1.0 : vy));
+        if (lower != (S.u >= S.v)) S.u = S.v = 0.5f * (S.u + S.v);      // keep the half the plane was taken from
+    }
     ProfFrame F;
-    F.ix0 = ix0;
-    F.iy0 = iy0;
-    F.g0x = lx0;
-    F.g0y = ly0;
-    F.oz = rc.oz;
-    F.cgx = rc.dgx;
-    F.cgy = rc.dgy;
-    F.cz = rc.dz;
-    double cw[3];
-    for (int a = 0; a < 3; ++a) cw[a] = R[3 * a] * T.c0[0] + R[3 * a + 1] * T.c0[1] + R[3 * a + 2] * T.c0[2];
-    F.cgx_d = cw[0] * m.inv_res_d;
-    F.cgy_d = cw[1] * m.inv_res_d;
-    F.cz_d = cw[2];
-    const float an = (float)sqrt(aw[0] * aw[0] + aw[1] * aw[1]);
-    if (!(an > 1.0e-3f)) return false;        // fan plane (nearly) horizontal
+    F.cgx = (float)cgx;
+    F.cgy = (float)cgy;
+    F.cz = (float)cw[2];
+    ProfFrameD D;
+    D.gox = gox;
+    D.goy = goy;
+    D.oz = p[2];
+    D.agx = aw[0] * m.inv_res_d;
+    D.agy = aw[1] * m.inv_res_d;
+    D.az = aw[2];
+    D.cgx = cgx;
+    D.cgy = cgy;
+    D.cz = cw[2];
     for (int side = 0; side < 2; ++side) {
         const int n_side = side == 0 ? T.n1 : T.B - T.n1;
         if (n_side <= 0) continue;
-        const float sg = (float)(side == 0 ? T.sgn1 : -T.sgn1);
-        F.agx = sg * (float)(aw[0] * m.inv_res_d);
-        F.agy = sg * (float)(aw[1] * m.inv_res_d);
-        F.az = sg * (float)aw[2];
-        F.agx_d = (double)sg * aw[0] * m.inv_res_d;
-        F.agy_d = (double)sg * aw[1] * m.inv_res_d;
-        F.az_d = (double)sg * aw[2];
-        int n_done;
+        const double sg = (double)(side == 0 ? T.sgn1 : -T.sgn1);
+        F.agx = (float)(sg * aw[0] * m.inv_res_d);
+        F.agy = (float)(sg * aw[1] * m.inv_res_d);
+        F.az = (float)(sg * aw[2]);
         const int beam0 = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;
-        if (!profile_side(m, F, q0, n_side, beam0, bstep, T.tan_t, T.sec_t, T.cosec_t, sink, &n_done)) return false;
+        if (!profile_side(m, F, &D, sg, S, n_side, beam0, bstep, T.tan_t, T.sec_t, T.sin_t, sink)) return false;
     }
     return true;
 }

@@ -89,6 +89,14 @@ def resample(logw, u):
     return qq, anc
 
 
+def prof_reasons(reset=True):
+    """Why profile marches gave up since the last reset: [steep triangle, turn-back, left the map,
+    out of steps, steep anchor, anchor mismatch, centre beam missed, -]."""
+    out = (C.c_long * 8)()
+    lib().hs_prof_reasons(out, C.c_int(1 if reset else 0))
+    return list(out)
+
+
 def count_below(u, N, c):
     return int(lib().hs_count_below(C.c_double(u), C.c_long(N), C.c_uint64(c)))
 

@@ -12,10 +12,15 @@
 #include <cstring>
 #include <vector>
 
+#define AUVPF_DEBUG_REASONS 1
 #include "../../smarc_navigation_b200/csrc/auvpf_fan.h"
 #include "../../smarc_navigation_b200/csrc/auvpf_math.cuh"
 
 using namespace auvpf;
+
+namespace auvpf {
+long g_prof_reasons[8] = {0};
+}
 
 namespace {
 struct HostDem {
@@ -130,18 +135,9 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
         if (use_fan == 2) {
             // profile merge (k_update_mbes_profile): one march per side, generic fallback
             FanTables T;
-            std::vector<float> dx(B), dy(B), dz(B);
-            for (int b = 0; b < B; ++b) {
-                dx[b] = beams[3 * b];
-                dy[b] = beams[3 * b + 1];
-                dz[b] = beams[3 * b + 2];
-            }
-            T.dx = dx.data();
-            T.dy = dy.data();
-            T.dz = dz.data();
             T.tan_t = plan.tan_t.data();
             T.sec_t = plan.sec_t.data();
-            T.cosec_t = plan.inv_s.data();
+            T.sin_t = plan.s.data();
             T.B = B;
             T.n1 = plan.n1;
             T.sgn1 = plan.sgn1;
@@ -292,6 +288,14 @@ int hs_resample(const float *logw, long M, double u, uint64_t *qq_out, int32_t *
         anc_out[i] = (int32_t)std::min(l, M - 1);
     }
     return 0;
+}
+
+void hs_prof_reasons(long *out, int reset)
+{
+    for (int k = 0; k < 8; ++k) {
+        out[k] = g_prof_reasons[k];
+        if (reset) g_prof_reasons[k] = 0;
+    }
 }
 
 long hs_count_below(double u, long N, uint64_t c) { return (long)sys_count_below(u, N, c); }

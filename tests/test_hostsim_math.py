@@ -298,7 +298,7 @@ def test_profile_merge_vs_oracle(name):
     if name == "border":
         assert n_prof == 0
     elif name in ("tilted", "ridged_tilted"):
-        assert n_prof >= 0.8 * r.size           # steep triangle x large tilt: a few particles fall back
+        assert n_prof >= 0.75 * r.size          # steep triangle x large tilt: some particles fall back
     else:
         assert n_prof == r.size                 # every particle certified by the profile march
     if name == "short_range":
