@@ -459,18 +459,19 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
     if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
-    if (i >= M) return;
-    const int64_t row = (int64_t)f * M + i;
+    const bool active = i < M;              // lanes past the end still walk through (warp-uniform march)
+    const int64_t row = (int64_t)f * M + (active ? i : 0);
     double p[3];
     double R[9];
     particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
     const FanTables T = make_tables(fan, B, s_tan, s_sec, s_sin);
     float acc = 0.f;
-    const bool ok = profile_particle(dem, T, p, R, [&](int b, float range) {
+    const bool ok = profile_particle(dem, T, p, R, active, [&](int b, float range) {
         const float rm = s_meas[b];
         const float e = rm - range;
         if (rm == rm) acc = fmaf(e, e, acc);
     });
+    if (!active) return;
     flags[row] = ok ? 0 : 1;
     if (ok) logw[row] = fmaf(neg_half_inv_var, acc, -(float)s_valid * log_norm_per_beam);
 }
@@ -486,15 +487,15 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
     stage_profile_tables(s_tan, s_sec, s_sin, B, beam_tan, beam_aux);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
-    if (i >= n) return;
-    const double *ps = poses + 6 * i;
+    const bool active = i < n;
+    const double *ps = poses + 6 * (active ? i : 0);
     double p[3];
     double R[9];
     particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
     const FanTables T = make_tables(fan, B, s_tan, s_sec, s_sin);
-    float *row = out + (size_t)i * B;
-    const bool ok = profile_particle(dem, T, p, R, [&](int b, float range) { row[b] = range; });
-    flags[i] = ok ? 0 : 1;
+    float *row = out + (size_t)(active ? i : 0) * B;
+    const bool ok = profile_particle(dem, T, p, R, active, [&](int b, float range) { row[b] = range; });
+    if (active) flags[i] = ok ? 0 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------

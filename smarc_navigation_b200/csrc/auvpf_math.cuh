@@ -700,110 +700,20 @@ double precise_hit(const ProfFrameD *D, double sg, int cx, int cy, double z00, d
     return alpha / (gamma - beta * tn);
 }
 
-// Marches one side.  Tables are indexed by beam; the j-th beam outward is beam0 + j * bstep.
-// Calls sink(beam, range) for every beam of the side in outward order.  Returns false if the
-// side cannot be certified (caller must recast the particle's beams ray by ray).
-template <class Sink>
-AUVPF_HD bool profile_side(const DemView &m, const ProfFrame &F, const ProfFrameD *D, double sg, const ProfStart &S,
-                           int n_side, int beam0, int bstep, const double *tan_t, const double *sec_t,
-                           const float *sin_t, Sink sink)
-{
-    int j = 0;
-    int cx = S.cx, cy = S.cy;
-    float u = S.u, v = S.v;
-    bool lower = u >= v;
-    int entry = -1;                        // canonical edge the curve entered the triangle through
-    double p_cur = 0.0, q_cur = S.q0;
-    const int max_steps = 8 * (int)(m.range_max / m.res) + 256;
-    const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
-    float z00 = ldg_f(zp), z01 = ldg_f(zp + 1), z10 = ldg_f(zp + m.pitch), z11 = ldg_f(zp + m.pitch + 1);
-    for (int step = 0; step < max_steps; ++step) {
-        const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
-        const float Dv = lower ? z11 - z01 : z10 - z00;
-        const float gamma = F.cz - F.cgx * Du - F.cgy * Dv;
-        if (!(gamma < -kGammaMin)) { AUVPF_REASON(0); return false; }
-        const float beta = F.agx * Du + F.agy * Dv - F.az;
-        const float s = fast_div(beta, gamma);                // profile slope dT/dp
-        const float X1 = fmaf(s, F.cgx, F.agx), Y1 = fmaf(s, F.cgy, F.agy);   // d(u,v)/dp
-        // canonical triangle a >= b: (a, b) = (u, v) in the lower half, (v, u) in the upper half.
-        // Edges: 0: a = 1 (reached when A1 > 0), 1: b = 0 (B1 < 0), 2: a = b (B1 > A1).
-        const float a = lower ? u : v, b = lower ? v : u;
-        const float A1 = lower ? X1 : Y1, B1 = lower ? Y1 : X1;
-        float bn = kBigT, bd = 1.f;                            // nearest exit = bn / bd
-        int be = -1;
-        if (entry != 0 && A1 > 0.f) {
-            bn = 1.f - a;
-            bd = A1;
-            be = 0;
-        }
-        if (entry != 1 && B1 < 0.f && b * bd < bn * -B1) {
-            bn = b;
-            bd = -B1;
-            be = 1;
-        }
-        if (entry != 2 && B1 > A1 && (a - b) * bd < bn * (B1 - A1)) {
-            bn = a - b;
-            bd = B1 - A1;
-            be = 2;
-        }
-        if (be < 0) { AUVPF_REASON(1); return false; }         // curve turns back through its entry edge
-        const float dp = fast_div(bn, bd);
-        const double p_out = p_cur + (double)dp;
-        const float p_out_f = (float)p_out;
-        // beams whose line meets the profile inside this segment.  gap = lateral distance of the
-        // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
-        while (j < n_side) {
-            const int bb = beam0 + j * bstep;
-            const double tn = tan_t[bb];
-            const float gap = (float)(q_cur * tn - p_cur);
-            const float den = (float)(1.0 - (double)s * tn);
-            float range;
-            if (gap <= dp * den) {
-                const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
-                double qh = q_cur + (double)(s * dph);
-                if (den < kDenPrecise)
-                    qh = precise_hit(D, sg, cx, cy, (double)z00, (double)(lower ? z01 : z11) - (double)(lower ? z00 : z10),
-                                     (double)(lower ? z11 : z10) - (double)(lower ? z01 : z00), tn);
-                const float t = (float)(qh * sec_t[bb]);
-                range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
-            } else if (p_out_f > sin_t[bb] * m.range_max) {
-                range = m.range_max;                           // cannot meet the profile within range
-            } else
-                break;
-            sink(bb, range);
-            ++j;
-        }
-        if (j >= n_side) return true;
-        // advance to the exit point and step into the neighbour across that edge
-        q_cur += (double)(s * dp);
-        p_cur = p_out;
-        u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
-        v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
-        if (be == 2) {
-            u = v = 0.5f * (u + v);
-        } else {
-            const int dir = be == 0 ? 1 : -1;                  // edge 0: coordinate reached 1, edge 1: reached 0
-            const float nc = be == 0 ? 0.f : 1.f;
-            if ((be == 0) == lower) {                          // a u-edge (x = const)
-                cx += dir;
-                u = nc;
-            } else {
-                cy += dir;
-                v = nc;
-            }
-            if (cx < 0 || cy < 0 || cx > m.W - 2 || cy > m.H - 2) { AUVPF_REASON(2); return false; }   // left the map
-            zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
-            z00 = ldg_f(zp);
-            z01 = ldg_f(zp + 1);
-            z10 = ldg_f(zp + m.pitch);
-            z11 = ldg_f(zp + m.pitch + 1);
-        }
-        lower = !lower;
-        entry = be == 2 ? 2 : 1 - be;
-    }
-    AUVPF_REASON(3);
-    return false;                            // ran out of steps: not certified
-}
+// Warp convergence.  With independent thread scheduling, lanes that leave a data-dependent
+// loop at different iterations are only reconverged where the compiler places a barrier; for the
+// march below it placed none inside the loop, so every lane ran its whole march ALONE (ncu:
+// 1.03 threads per instruction, 17x slower).  The march is therefore written as a warp-uniform
+// loop: every lane of the warp enters (lanes without work carry active = false), the loop runs
+// while ANY lane is still marching, and the warp is re-synchronised at the end of every step.
+// profile_particle must be called by all 32 lanes of a warp.
+#if defined(__CUDA_ARCH__)
+#define AUVPF_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#define AUVPF_WARP_SYNC() __syncwarp()
+#else
+#define AUVPF_WARP_ANY(p) (p)
+#define AUVPF_WARP_SYNC() ((void)0)
+#endif
 
 // Beam tables of a planar fan as the profile merge needs them (device: shared memory).
 struct FanTables {
@@ -814,38 +724,210 @@ struct FanTables {
     float c0[3], a0[3];                      // fan centre / lateral unit vectors, sensor frame
 };
 
-// All beams of one particle by profile merge.  Returns false when the particle cannot be
-// certified (not inside the map's interior, centre beam missed, a triangle with gamma >= 0):
-// the caller must then cast its beams ray by ray.  sink(beam, range) may have been called for
-// some beams before a failure; callers discard those.
+// Marches both sides of the fan, one after the other, inside ONE warp-uniform step loop (a lane
+// that finishes its first side starts its second while its neighbours are still on their first,
+// so the warp waits for the longest SUM of the two sides, not the sum of the longest).
+// Calls sink(beam, range) for every beam in outward order per side.  Returns false if the
+// particle cannot be certified (caller must recast its beams ray by ray).
 template <class Sink>
-AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const double p[3], const double R[9], Sink sink)
+AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFrame &F0, const ProfFrameD *D,
+                            const ProfStart &S, bool active, Sink sink)
 {
+    // per-side state
+    int side = T.n1 > 0 ? 0 : 1;
+    int n_side = side == 0 ? T.n1 : T.B - T.n1;
+    int beam0 = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;
+    float sgf = (float)(side == 0 ? T.sgn1 : -T.sgn1);
+    int j = 0;
+    int cx = S.cx, cy = S.cy;
+    float u = S.u, v = S.v;
+    bool lower = u >= v;
+    int entry = -1;                        // canonical edge the curve entered the triangle through
+    double p_cur = 0.0, q_cur = S.q0;
+    bool running = active && T.B > 0;
+    bool ok = true;
+    const int max_steps = 2 * (8 * (int)(m.range_max / m.res) + 256);
+    float z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
+    if (running) {
+        const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
+        z00 = ldg_f(zp);
+        z01 = ldg_f(zp + 1);
+        z10 = ldg_f(zp + m.pitch);
+        z11 = ldg_f(zp + m.pitch + 1);
+    }
+    for (int step = 0; step < max_steps; ++step) {
+        if (!AUVPF_WARP_ANY(running)) break;
+        if (running) do {
+            const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
+            const float Dv = lower ? z11 - z01 : z10 - z00;
+            const float gamma = F0.cz - F0.cgx * Du - F0.cgy * Dv;
+            if (!(gamma < -kGammaMin)) { AUVPF_REASON(0); ok = false; running = false; break; }
+            const float beta = sgf * (F0.agx * Du + F0.agy * Dv - F0.az);
+            const float s = fast_div(beta, gamma);                // profile slope dT/dp
+            const float X1 = fmaf(s, F0.cgx, sgf * F0.agx), Y1 = fmaf(s, F0.cgy, sgf * F0.agy);   // d(u,v)/dp
+            // canonical triangle a >= b: (a, b) = (u, v) in the lower half, (v, u) in the upper half.
+            // Edges: 0: a = 1 (reached when A1 > 0), 1: b = 0 (B1 < 0), 2: a = b (B1 > A1).
+            const float a = lower ? u : v, b = lower ? v : u;
+            const float A1 = lower ? X1 : Y1, B1 = lower ? Y1 : X1;
+            float bn = kBigT, bd = 1.f;                            // nearest exit = bn / bd
+            int be = -1;
+            if (entry != 0 && A1 > 0.f) {
+                bn = 1.f - a;
+                bd = A1;
+                be = 0;
+            }
+            if (entry != 1 && B1 < 0.f && b * bd < bn * -B1) {
+                bn = b;
+                bd = -B1;
+                be = 1;
+            }
+            if (entry != 2 && B1 > A1 && (a - b) * bd < bn * (B1 - A1)) {
+                bn = a - b;
+                bd = B1 - A1;
+                be = 2;
+            }
+            if (be < 0) { AUVPF_REASON(1); ok = false; running = false; break; }   // curve turns back through its entry edge
+            const float dp = fast_div(bn, bd);
+            const double p_out = p_cur + (double)dp;
+            const float p_out_f = (float)p_out;
+            // beams whose line meets the profile inside this segment.  gap = lateral distance of the
+            // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
+            while (j < n_side) {
+                const int bb = beam0 + j * bstep;
+                const double tn = T.tan_t[bb];
+                const float gap = (float)(q_cur * tn - p_cur);
+                const float den = (float)(1.0 - (double)s * tn);
+                float range;
+                if (gap <= dp * den) {
+                    const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
+                    double qh = q_cur + (double)(s * dph);
+                    if (den < kDenPrecise)
+                        qh = precise_hit(D, (double)sgf, cx, cy, (double)z00,
+                                         (double)(lower ? z01 : z11) - (double)(lower ? z00 : z10),
+                                         (double)(lower ? z11 : z10) - (double)(lower ? z01 : z00), tn);
+                    const float t = (float)(qh * T.sec_t[bb]);
+                    range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
+                } else if (p_out_f > T.sin_t[bb] * m.range_max) {
+                    range = m.range_max;                           // cannot meet the profile within range
+                } else
+                    break;
+                sink(bb, range);
+                ++j;
+            }
+            if (j >= n_side) {
+                // this side is done: start the other one from the anchor, or finish
+                if (side == 0 && T.B - T.n1 > 0) {
+                    side = 1;
+                    n_side = T.B - T.n1;
+                    beam0 = T.n1;
+                    bstep = 1;
+                    sgf = -sgf;
+                    j = 0;
+                    cx = S.cx;
+                    cy = S.cy;
+                    u = S.u;
+                    v = S.v;
+                    lower = u >= v;
+                    entry = -1;
+                    p_cur = 0.0;
+                    q_cur = S.q0;
+                    const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
+                    z00 = ldg_f(zp);
+                    z01 = ldg_f(zp + 1);
+                    z10 = ldg_f(zp + m.pitch);
+                    z11 = ldg_f(zp + m.pitch + 1);
+                } else
+                    running = false;
+                break;
+            }
+            // advance to the exit point and step into the neighbour across that edge
+            q_cur += (double)(s * dp);
+            p_cur = p_out;
+            u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
+            v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
+            if (be == 2) {
+                u = v = 0.5f * (u + v);
+            } else {
+                const int dir = be == 0 ? 1 : -1;                  // edge 0: coordinate reached 1, edge 1: reached 0
+                const float nc = be == 0 ? 0.f : 1.f;
+                if ((be == 0) == lower) {                          // a u-edge (x = const)
+                    cx += dir;
+                    u = nc;
+                } else {
+                    cy += dir;
+                    v = nc;
+                }
+                if (cx < 0 || cy < 0 || cx > m.W - 2 || cy > m.H - 2) {   // left the map
+                    AUVPF_REASON(2);
+                    ok = false;
+                    running = false;
+                    break;
+                }
+                const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
+                z00 = ldg_f(zp);
+                z01 = ldg_f(zp + 1);
+                z10 = ldg_f(zp + m.pitch);
+                z11 = ldg_f(zp + m.pitch + 1);
+            }
+            lower = !lower;
+            entry = be == 2 ? 2 : 1 - be;
+        } while (0);
+        AUVPF_WARP_SYNC();
+    }
+    if (running) {                           // ran out of steps: not certified
+        AUVPF_REASON(3);
+        ok = false;
+    }
+    return ok;
+}
+
+// All beams of one particle by profile merge; MUST be called by all 32 lanes of a warp
+// (`active` = this lane has a particle).  Returns false when the particle cannot be certified
+// (not inside the map's interior, centre beam missed, a triangle with gamma >= 0): the caller
+// must then cast its beams ray by ray.  sink(beam, range) may have been called for some beams
+// before a failure; callers discard those.
+template <class Sink>
+AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const double p[3], const double R[9], bool active,
+                               Sink sink)
+{
+    bool ok = active;
     const double reach = (double)m.range_max;
     const double xmax = m.x0 + (double)(m.W - 1) * (double)m.res, ymax = m.y0 + (double)(m.H - 1) * (double)m.res;
-    if (!(p[0] - reach > m.x0 && p[0] + reach < xmax && p[1] - reach > m.y0 && p[1] + reach < ymax)) return false;
-    int ix0, iy0;
-    float lx0, ly0;
-    origin_cell(m, p, ix0, iy0, lx0, ly0);
+    if (!(p[0] - reach > m.x0 && p[0] + reach < xmax && p[1] - reach > m.y0 && p[1] + reach < ymax)) ok = false;
     // centre beam from the sensor: q0 = T(0)
-    Ray rc = make_ray(m, p, ix0, iy0, lx0, ly0, R, T.c0[0], T.c0[1], T.c0[2]);
-    const float q0f = raycast_from(m, rc, 0.f, true);
-    if (!(q0f < m.range_max)) { AUVPF_REASON(6); return false; }
-    if (q0f <= 0.f) {                         // sensor at / under the surface: every range is 0 (spec)
-        for (int b = 0; b < T.B; ++b) sink(b, 0.f);
-        return true;
+    float q0f = 0.f;
+    if (ok) {
+        int ix0, iy0;
+        float lx0, ly0;
+        origin_cell(m, p, ix0, iy0, lx0, ly0);
+        Ray rc = make_ray(m, p, ix0, iy0, lx0, ly0, R, T.c0[0], T.c0[1], T.c0[2]);
+        q0f = raycast_from(m, rc, 0.f, true);
     }
-    double aw[3], cw[3];
-    for (int a = 0; a < 3; ++a) {
-        aw[a] = R[3 * a] * T.a0[0] + R[3 * a + 1] * T.a0[1] + R[3 * a + 2] * T.a0[2];
-        cw[a] = R[3 * a] * T.c0[0] + R[3 * a + 1] * T.c0[1] + R[3 * a + 2] * T.c0[2];
-    }
-    if (!(aw[0] * aw[0] + aw[1] * aw[1] > 1.0e-6)) return false;       // fan plane (nearly) horizontal
-    // anchor: the triangle under the centre hit, and the hit re-solved on its plane in float64
-    const double gox = (p[0] - m.x0) * m.inv_res_d, goy = (p[1] - m.y0) * m.inv_res_d;   // sensor, grid units
-    const double cgx = cw[0] * m.inv_res_d, cgy = cw[1] * m.inv_res_d;
+    AUVPF_WARP_SYNC();
+    bool all_zero = false;
     ProfStart S;
-    {
+    S.cx = S.cy = 0;
+    S.u = S.v = 0.f;
+    S.q0 = 0.0;
+    ProfFrame F;
+    F.agx = F.agy = F.az = F.cgx = F.cgy = F.cz = 0.f;
+    ProfFrameD D;
+    D.gox = D.goy = D.oz = D.agx = D.agy = D.az = D.cgx = D.cgy = D.cz = 0.0;
+    if (ok) do {
+        if (!(q0f < m.range_max)) { AUVPF_REASON(6); ok = false; break; }
+        if (q0f <= 0.f) {                     // sensor at / under the surface: every range is 0 (spec)
+            all_zero = true;
+            break;
+        }
+        double aw[3], cw[3];
+        for (int a = 0; a < 3; ++a) {
+            aw[a] = R[3 * a] * T.a0[0] + R[3 * a + 1] * T.a0[1] + R[3 * a + 2] * T.a0[2];
+            cw[a] = R[3 * a] * T.c0[0] + R[3 * a + 1] * T.c0[1] + R[3 * a + 2] * T.c0[2];
+        }
+        if (!(aw[0] * aw[0] + aw[1] * aw[1] > 1.0e-6)) { ok = false; break; }   // fan plane (nearly) horizontal
+        // anchor: the triangle under the centre hit, and the hit re-solved on its plane in float64
+        const double gox = (p[0] - m.x0) * m.inv_res_d, goy = (p[1] - m.y0) * m.inv_res_d;   // sensor, grid units
+        const double cgx = cw[0] * m.inv_res_d, cgy = cw[1] * m.inv_res_d;
         const double hx = gox + (double)q0f * cgx, hy = goy + (double)q0f * cgy;
         S.cx = clampi((int)floor(hx), 0, m.W - 2);
         S.cy = clampi((int)floor(hy), 0, m.H - 2);
@@ -855,39 +937,34 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
         const double Du = lower ? z01 - z00 : z11 - z10, Dv = lower ? z11 - z01 : z10 - z00;
         const double alpha = (z00 - p[2]) + (gox - (double)S.cx) * Du + (goy - (double)S.cy) * Dv;
         const double gamma = cw[2] - cgx * Du - cgy * Dv;
-        if (!(gamma < -(double)kGammaMin)) { AUVPF_REASON(4); return false; }
+        if (!(gamma < -(double)kGammaMin)) { AUVPF_REASON(4); ok = false; break; }
         S.q0 = alpha / gamma;
-        if (!(fabs(S.q0 - (double)q0f) < 1.0e-3)) { AUVPF_REASON(5); return false; }       // centre hit not on this triangle's plane
+        if (!(fabs(S.q0 - (double)q0f) < 1.0e-3)) { AUVPF_REASON(5); ok = false; break; }   // centre hit not on this triangle's plane
         const double ux = gox + S.q0 * cgx - (double)S.cx, vy = goy + S.q0 * cgy - (double)S.cy;
         S.u = (float)(ux < 0.0 ? 0.0 : (ux > 1.0 ? 1.0 : ux));
         S.v = (float)(vy < 0.0 ? 0.0 : (vy > 1.0 ? 1.0 : vy));
         if (lower != (S.u >= S.v)) S.u = S.v = 0.5f * (S.u + S.v);      // keep the half the plane was taken from
-    }
-    ProfFrame F;
-    F.cgx = (float)cgx;
-    F.cgy = (float)cgy;
-    F.cz = (float)cw[2];
-    ProfFrameD D;
-    D.gox = gox;
-    D.goy = goy;
-    D.oz = p[2];
-    D.agx = aw[0] * m.inv_res_d;
-    D.agy = aw[1] * m.inv_res_d;
-    D.az = aw[2];
-    D.cgx = cgx;
-    D.cgy = cgy;
-    D.cz = cw[2];
-    for (int side = 0; side < 2; ++side) {
-        const int n_side = side == 0 ? T.n1 : T.B - T.n1;
-        if (n_side <= 0) continue;
-        const double sg = (double)(side == 0 ? T.sgn1 : -T.sgn1);
-        F.agx = (float)(sg * aw[0] * m.inv_res_d);
-        F.agy = (float)(sg * aw[1] * m.inv_res_d);
-        F.az = (float)(sg * aw[2]);
-        const int beam0 = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;
-        if (!profile_side(m, F, &D, sg, S, n_side, beam0, bstep, T.tan_t, T.sec_t, T.sin_t, sink)) return false;
-    }
-    return true;
+        F.cgx = (float)cgx;
+        F.cgy = (float)cgy;
+        F.cz = (float)cw[2];
+        F.agx = (float)(aw[0] * m.inv_res_d);     // lateral unit vector towards +a0; the march applies the side's sign
+        F.agy = (float)(aw[1] * m.inv_res_d);
+        F.az = (float)aw[2];
+        D.gox = gox;
+        D.goy = goy;
+        D.oz = p[2];
+        D.agx = aw[0] * m.inv_res_d;
+        D.agy = aw[1] * m.inv_res_d;
+        D.az = aw[2];
+        D.cgx = cgx;
+        D.cgy = cgy;
+        D.cz = cw[2];
+    } while (0);
+    AUVPF_WARP_SYNC();
+    if (all_zero)
+        for (int b = 0; b < T.B; ++b) sink(b, 0.f);
+    const bool marched = profile_march(m, T, F, &D, S, ok && !all_zero, sink);
+    return ok && (all_zero || marched);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -966,6 +1043,67 @@ AUVPF_HD int64_t sys_count_below(double u, int64_t N, uint64_t c)
     while (i > 0 && !(sys_position(u, i - 1, n) < cv)) --i;
     while (i < N && sys_position(u, i, n) < cv) ++i;
     return i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual_resample (resampling.py:27-76) on fixed-point weights w = q 2^-52.
+// Deterministic copies: floor(N * w) with the reference's float64 product (:61).
+AUVPF_HD uint64_t residual_copies(uint64_t q, int64_t N)
+{
+    return (uint64_t)floor(mul_rn((double)N, cdf_value(q)));
+}
+
+// Fractional part N w - k (what :70 means to compute) on a 2^-38 grid: (N q - k 2^52) >> 14.
+// k can exceed the true floor by one when the float64 product rounds up to an integer: 0 then.
+constexpr int kResShift = 14;
+AUVPF_HD uint64_t residual_frac(uint64_t q, uint64_t k, int64_t N)
+{
+    const unsigned __int128 nq = (unsigned __int128)q * (uint64_t)N;
+    const unsigned __int128 kk = (unsigned __int128)k << kQBits;
+    if (nq <= kk) return 0;
+    return (uint64_t)((nq - kk) >> kResShift);
+}
+
+// A uniform u in [0,1) on the integer residual CDF of total R: floor(floor(u 2^53) R / 2^53)
+AUVPF_HD uint64_t residual_target(double u, uint64_t R)
+{
+    const uint64_t m = (uint64_t)floor(ldexp(u, 53));
+    return (uint64_t)(((unsigned __int128)m * R) >> 53);
+}
+
+AUVPF_HD double div_rn(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b;
+    return r;
+#endif
+}
+
+// np.searchsorted(arr, keys) (side='left') as NumPy's binsearch runs it, including the
+// key-to-key bounds hint that makes the result on a NON-monotone array depend on the key order
+// (numpy/_core/src/npysort/binsearch.cpp).  The reference calls it on such an array
+// (resampling.py:70-74), so strict parity needs the same walk.  State = (lo, hi, last key).
+struct SearchHint {
+    int64_t lo, hi;
+    double last;
+};
+AUVPF_HD int64_t searchsorted_left_hinted(const double *arr, int64_t n, double key, SearchHint &h)
+{
+    if (h.last < key) {
+        h.hi = n;
+    } else {
+        h.lo = 0;
+        h.hi = h.hi < n ? h.hi + 1 : n;
+    }
+    h.last = key;
+    while (h.lo < h.hi) {
+        const int64_t mid = h.lo + ((h.hi - h.lo) >> 1);
+        if (arr[mid] < key) h.lo = mid + 1;
+        else h.hi = mid;
+    }
+    return h.lo;
 }
 
 }   // namespace auvpf
