@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libauvpf.so")
+LIB_PATH = os.environ.get("AUVPF_LIB") or os.path.join(_HERE, "libauvpf.so")   # AUVPF_LIB: kernel-tuning builds
 
 OK, ERR_BADARG, ERR_CUDA, ERR_STATE, ERR_DEGENERATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 SYSTEMATIC, RESIDUAL = 0, 1

@@ -405,6 +405,9 @@ k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, Dem
 // beam missed, a triangle steeper than the fan tilt allows) are flagged and recast by the
 // per-ray kernel above.
 constexpr int kProfThreads = 128;
+#ifndef AUVPF_PROF_MIN_BLOCKS
+#define AUVPF_PROF_MIN_BLOCKS 1
+#endif
 
 // shared memory: tan (double B) | sec (double B) | |sin| (float B) | measured range (float B)
 // beam_tan = [tan | sec] (2B doubles), beam_aux[0..B) = |sin|
@@ -435,7 +438,7 @@ __device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, co
     return T;
 }
 
-__global__ void __launch_bounds__(kProfThreads)
+__global__ void __launch_bounds__(kProfThreads, AUVPF_PROF_MIN_BLOCKS)
 k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan,
                       const double *__restrict__ beam_tan, const float *__restrict__ beam_aux,
                       const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,

@@ -792,13 +792,17 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             const float p_out_f = (float)p_out;
             // beams whose line meets the profile inside this segment.  gap = lateral distance of the
             // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
+            // A beam is resolved here when it hits inside the segment, or when the segment's end is
+            // beyond what the beam can reach within range_max (miss).
             while (j < n_side) {
                 const int bb = beam0 + j * bstep;
                 const double tn = T.tan_t[bb];
                 const float gap = (float)(q_cur * tn - p_cur);
-                const float den = (float)(1.0 - (double)s * tn);
-                float range;
-                if (gap <= dp * den) {
+                const float den = fmaf(-s, (float)tn, 1.0f);
+                const bool hit = gap <= dp * den;
+                if (!(hit || p_out_f > T.sin_t[bb] * m.range_max)) break;
+                float range = m.range_max;
+                if (hit) {
                     const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
                     double qh = q_cur + (double)(s * dph);
                     if (den < kDenPrecise)
@@ -807,10 +811,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                                          (double)(lower ? z11 : z10) - (double)(lower ? z01 : z00), tn);
                     const float t = (float)(qh * T.sec_t[bb]);
                     range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
-                } else if (p_out_f > T.sin_t[bb] * m.range_max) {
-                    range = m.range_max;                           // cannot meet the profile within range
-                } else
-                    break;
+                }
                 sink(bb, range);
                 ++j;
             }
@@ -840,34 +841,36 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     running = false;
                 break;
             }
-            // advance to the exit point and step into the neighbour across that edge
+            // advance to the exit point and step into the neighbour across that edge (selects, not
+            // branches: lanes leaving through different edges stay converged)
             q_cur += (double)(s * dp);
             p_cur = p_out;
             u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
             v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
-            if (be == 2) {
-                u = v = 0.5f * (u + v);
-            } else {
+            {
+                const bool diag = be == 2;                         // diagonal: same cell, other half
+                const bool uedge = !diag && ((be == 0) == lower);  // an x = const edge
+                const bool vedge = !diag && !uedge;
                 const int dir = be == 0 ? 1 : -1;                  // edge 0: coordinate reached 1, edge 1: reached 0
                 const float nc = be == 0 ? 0.f : 1.f;
-                if ((be == 0) == lower) {                          // a u-edge (x = const)
-                    cx += dir;
-                    u = nc;
-                } else {
-                    cy += dir;
-                    v = nc;
-                }
+                const float mid = 0.5f * (u + v);
+                cx += uedge ? dir : 0;
+                cy += vedge ? dir : 0;
+                u = diag ? mid : (uedge ? nc : u);
+                v = diag ? mid : (vedge ? nc : v);
                 if (cx < 0 || cy < 0 || cx > m.W - 2 || cy > m.H - 2) {   // left the map
                     AUVPF_REASON(2);
                     ok = false;
                     running = false;
                     break;
                 }
-                const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
-                z00 = ldg_f(zp);
-                z01 = ldg_f(zp + 1);
-                z10 = ldg_f(zp + m.pitch);
-                z11 = ldg_f(zp + m.pitch + 1);
+                if (!diag) {
+                    const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
+                    z00 = ldg_f(zp);
+                    z01 = ldg_f(zp + 1);
+                    z10 = ldg_f(zp + m.pitch);
+                    z11 = ldg_f(zp + m.pitch + 1);
+                }
             }
             lower = !lower;
             entry = be == 2 ? 2 : 1 - be;
@@ -1013,13 +1016,48 @@ AUVPF_HD uint64_t a_from_linear(double w, double wmax)
     return (uint64_t)floor(ldexp(w / wmax, kABits));
 }
 
-// q = floor(a * 2^52 / A), A given as two 64-bit halves
-AUVPF_HD uint64_t q_from_a(uint64_t a, uint64_t A_lo, uint64_t A_hi)
+// q = floor(a * 2^52 / A), A given as two 64-bit halves.  A generic 128-bit division costs
+// several hundred instructions per particle on the GPU (it was most of the scan kernel), so the
+// quotient is ESTIMATED in float64 (a * (2^52 / A), good to a couple of units) and then made
+// EXACT with a 128-bit multiply-back and a correction walk.  The result is the same integer
+// floor for every input; tests/hostsim checks it against Python big integers.
+struct QDiv {
+    uint64_t A_lo, A_hi;
+    double scale;        // 2^52 / A, rounded
+};
+
+AUVPF_HD QDiv make_qdiv(uint64_t A_lo, uint64_t A_hi)
 {
-    unsigned __int128 A = ((unsigned __int128)A_hi << 64) | A_lo;
-    unsigned __int128 t = (unsigned __int128)a << kQBits;
-    return (uint64_t)(t / A);
+    QDiv d;
+    d.A_lo = A_lo;
+    d.A_hi = A_hi;
+    const double Ad = (double)A_hi * 18446744073709551616.0 + (double)A_lo;
+    d.scale = Ad > 0.0 ? 4503599627370496.0 / Ad : 0.0;
+    return d;
 }
+
+AUVPF_HD uint64_t q_from_a(uint64_t a, const QDiv &d)
+{
+    if (a == 0) return 0;
+    const unsigned __int128 A = ((unsigned __int128)d.A_hi << 64) | d.A_lo;
+    const unsigned __int128 t = (unsigned __int128)a << kQBits;
+    double qe = (double)a * d.scale;
+    if (!(qe < 4503599627370496.0)) qe = 4503599627370496.0;      // a <= A, so q <= 2^52
+    uint64_t q = (uint64_t)qe;
+    // q * A <= t + 3 A < 2^128: the high product q * A_hi stays below 2^64
+    unsigned __int128 prod = (unsigned __int128)q * d.A_lo + (((unsigned __int128)(q * d.A_hi)) << 64);
+    while (prod > t) {
+        --q;
+        prod -= A;
+    }
+    while (t - prod >= A) {
+        ++q;
+        prod += A;
+    }
+    return q;
+}
+
+AUVPF_HD uint64_t q_from_a(uint64_t a, uint64_t A_lo, uint64_t A_hi) { return q_from_a(a, make_qdiv(A_lo, A_hi)); }
 
 // positions[i] = (u + i) / N of resampling.py:157, as the reference rounds it
 AUVPF_HD double sys_position(double u, int64_t i, double n)
