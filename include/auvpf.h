@@ -48,13 +48,19 @@ extern "C" {
 
 /* resampler selection for auvpf_resample* */
 #define AUVPF_SYSTEMATIC 0 /* resampling.py:135-168 systematic_resample            */
-#define AUVPF_RESIDUAL 1   /* resampling.py:27-76 residual_resample (deterministic
-                              floor(N w) copies bit-exact; residual draw: see DESIGN.md) */
+#define AUVPF_RESIDUAL 1   /* resampling.py:27-76 residual_resample, the one auv_pf.resample
+                              calls (:182): floor(N w) copies bit-exact; the remaining draw
+                              is a multinomial on the fractional parts, or -- with
+                              AUVPF_RS_STRICT_REF -- the reference's literal :70-74     */
 
 /* flags for auvpf_resample* */
 #define AUVPF_RS_SORTED 0      /* new[i] = old[ancestor[i]] (ancestors ascending)    */
 #define AUVPF_RS_INPLACE_REF 1 /* reference slot map, auv_pf.py:183-198: survivors keep
                                   their slot, pose[lost[r]] <- pose[dupes[r]]        */
+#define AUVPF_RS_STRICT_REF 2  /* AUVPF_RESIDUAL only: reproduce resampling.py:70-74 literally
+                                  (residual = w - copies, sequential sum / cumsum, NumPy's
+                                  hinted searchsorted on the non-monotone result) for lock-step
+                                  parity at the reference's particle counts (<= 65536)   */
 
 /* kernel classes for auvpf_profile_read */
 enum {

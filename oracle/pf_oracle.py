@@ -344,6 +344,37 @@ def residual_resample(weights, uniforms):
     return indexes
 
 
+RES_SHIFT = 14      # fractional parts live on a 2^-38 grid (csrc/auvpf_math.cuh kResShift)
+
+
+def residual_resample_fixed(qq, uniforms):
+    """The library's DEFAULT residual resampler on fixed-point weights ``w = qq 2^-52``
+    (DESIGN.md 5.3): the deterministic part is the reference's, bit for bit --
+    ``floor(N w_i)`` copies with the float64 product of resampling.py:61, written in index
+    order (:62-66) -- and the remaining ``N - k`` slots are a multinomial draw on the
+    fractional parts ``N w_i - k_i`` (what :70 means to compute; the reference's literal
+    ``w - num_copies`` is reproduced by ``residual_resample`` above / AUVPF_RS_STRICT_REF).
+    All-integer: ``r_i = (N q_i - k_i 2^52) >> 14``, inclusive scan ``S``, total ``R``; draw t
+    picks the first i with ``floor(floor(u_t 2^53) R / 2^53) < S_i``."""
+    qq = np.asarray(qq, np.uint64)
+    N = len(qq)
+    w = weights_from_q(qq)
+    num_copies = np.floor(N * w).astype(np.int64)                                    # :61
+    head = np.repeat(np.arange(N, dtype=np.int32), num_copies)                        # :62-66
+    k = len(head)
+    indexes = np.zeros(N, np.int32)
+    indexes[:k] = head[:N]
+    r = [max(0, int(q) * N - (int(c) << Q_BITS)) >> RES_SHIFT for q, c in zip(qq.tolist(), num_copies.tolist())]
+    S = np.cumsum(np.array(r, dtype=object))
+    R = int(S[-1]) if N else 0
+    S64 = np.array([int(v) for v in S], dtype=np.uint64)
+    u = np.asarray(uniforms, np.float64)[:N - k]
+    T = np.array([(int(np.floor(np.ldexp(x, 53))) * R) >> 53 for x in u.tolist()], dtype=np.uint64)
+    tail = np.searchsorted(S64, T, side='right')
+    indexes[k:N] = np.minimum(tail, N - 1)
+    return indexes
+
+
 # --------------------------------------------------------------------------- resample bookkeeping
 def resample_bookkeeping(indices, pc):
     """``auv_pf.resample`` lines auv_pf.py:183-187: ``keep`` = set of drawn ids,
@@ -459,3 +490,12 @@ def philox_normals(seed, stream, step, index, n_calls):
             out.append(r * np.cos(th))
             out.append(r * np.sin(th))
     return np.stack(out, -1)
+
+
+def philox_pose_normals(seed, stream, step, index):
+    """The six normals of one ``add_noise`` in POSE order ``[x, y, z, roll, pitch, yaw]``
+    (device contract ``pose_normals``, csrc/auvpf_math.cuh): call 0 gives x, y (words 0,1) and
+    yaw, z (words 2,3); call 1 gives roll, pitch (words 0,1)."""
+    n = philox_normals(seed, stream, step, index, 2)
+    return n[:, [0, 1, 3, 4, 5, 2]]
+

@@ -47,7 +47,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum Slot { S_IN0 = 0, S_IN1, S_IN2, S_OUT0, S_OUT1, S_COUNT };
+enum Slot { S_IN0 = 0, S_IN1, S_IN2, S_IN3, S_OUT0, S_OUT1, S_COUNT };
 
 struct ProfEvent {
     cudaEvent_t a, b;
@@ -72,6 +72,9 @@ struct auvpf_handle {
 
     // per-filter scalars
     long long *wmax_ordered = nullptr;
+    int *wmax_f32 = nullptr;      // [F] max log-weight published by the update kernels (ordered int)
+    bool wmax_valid = false;      // wmax_f32 describes the current logw
+    unsigned int *done = nullptr; // [F] ticket counters of k_normalise
     double *wmax = nullptr;
     unsigned long long *limbs = nullptr, *A = nullptr, *Q = nullptr, *deficit = nullptr;
     double *u = nullptr, *sumsq = nullptr, *sums = nullptr, *mom = nullptr, *gps = nullptr;
@@ -87,6 +90,7 @@ struct auvpf_handle {
     int32_t *anc = nullptr;
     int *first = nullptr;
     unsigned long long *scan2 = nullptr, *totals2 = nullptr;
+    unsigned long long *scan3 = nullptr;   // residual resampling: scan of the fractional parts
     int32_t *lost = nullptr, *dupes = nullptr;
     const double *lin_weights = nullptr;   // device pointer of the last linear weight source
     int last_src_kind = 0;
@@ -313,6 +317,8 @@ NoiseParams make_noise(auvpf_handle *h, const double var[6], const double *mean,
         n.mean[c] = mean ? mean[c] : 0.0;
     }
     n.mode = mode;
+    n.need = 0;
+    for (int c = 0; c < 6; ++c) n.need |= n.sigma[c] != 0.f ? (1u << c) : 0u;
     n.seed = h->cfg.seed;
     n.step = step;
     n.stream = stream;
@@ -395,15 +401,63 @@ int run_sum(auvpf_handle *h, const WeightSrc &src)
     return AUVPF_OK;
 }
 
-int run_scan(auvpf_handle *h, const WeightSrc &src)
+// fused = the status words and the tile counter were cleared by k_normalise, the scan writes the
+// deficit itself and skips degenerate filters (single-GPU path); otherwise (sharded path) the
+// caller supplies max / A and reads Q back.
+int run_scan(auvpf_handle *h, const WeightSrc &src, bool fused = false)
 {
     Prof pr(h, AUVPF_K_SCAN);
-    CU(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * h->F, h->stream));
-    CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
-    k_scan_q<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->A, h->cdf, h->status,
-                                                                     h->tile_counter, h->tiles_per_filter, h->Q,
-                                                                     h->sumsq);
+    if (!fused) {
+        CU(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * h->F, h->stream));
+        CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+    }
+    if (fused)      // a_i were left in h->cdf by k_normalise
+        k_scan_q_from_a<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
+            h->M, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq, h->deficit,
+            h->degenerate);
+    else
+        k_scan_q<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
+            src, h->M, h->wmax, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq,
+            nullptr, nullptr);
     LAUNCHED(h, AUVPF_K_SCAN, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+// Single-GPU normalisation: max (from the update kernel when it is current) + exact sum + A.
+int run_normalise(auvpf_handle *h, const WeightSrc &src)
+{
+    int rc;
+    NormState ns{};
+    if (src.kind == 0) {
+        if (!h->wmax_valid) {
+            Prof pr(h, AUVPF_K_NORMALISE);
+            CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * h->F, h->stream));
+            int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
+            k_weight_max_f32<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->logw, h->M, h->wmax_f32);
+            LAUNCHED(h, AUVPF_K_NORMALISE, 1);
+            h->wmax_valid = true;
+        }
+        ns.wmax_f32 = h->wmax_f32;
+    } else {
+        if ((rc = run_max(h, src))) return rc;      // float64 linear weights: separate max pass
+        ns.wmax_f32 = nullptr;
+    }
+    ns.wmax = h->wmax;
+    ns.limbs = h->limbs;
+    ns.done = h->done;
+    ns.A = h->A;
+    ns.degenerate = h->degenerate;
+    ns.sumsq = h->sumsq;
+    ns.status = h->status;
+    ns.tile_counter = h->tile_counter;
+    ns.tiles_total = (long long)h->tiles_per_filter * h->F;
+    ns.a_out = h->cdf;
+    Prof pr(h, AUVPF_K_NORMALISE);
+    int blocks = (int)std::min<int64_t>((h->M + kThreads * 4 - 1) / (kThreads * 4), 1184);
+    if (blocks < 1) blocks = 1;
+    k_normalise<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, ns);
+    LAUNCHED(h, AUVPF_K_NORMALISE, 1);
     CU(cudaGetLastError());
     return AUVPF_OK;
 }
@@ -457,19 +511,99 @@ int apply_indices_dev(auvpf_handle *h, const int32_t *idx)
     return AUVPF_OK;
 }
 
+int reset_scan_state(auvpf_handle *h)
+{
+    CU(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * h->F, h->stream));
+    CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+    return AUVPF_OK;
+}
+
+// residual_resample (resampling.py:27-76) + the reference's application of its indices.
+// u: (F, M) float64 uniforms -- the random(N - k) of :74, first M - k of each row consumed -- or
+// nullptr for Philox.
+int do_resample_residual(auvpf_handle *h, const WeightSrc &src, int32_t flags, const double *u,
+                         int32_t *ancestors_out, const double *rough_var, const float *rough_noise)
+{
+    if (h->global_count != h->M)
+        return fail(AUVPF_ERR_BADARG, "residual resampling is not available for a particle-sharded filter");
+    const bool strict = (flags & AUVPF_RS_STRICT_REF) != 0;
+    const bool inplace = (flags & AUVPF_RS_INPLACE_REF) != 0;
+    if (strict && h->M > 65536)
+        return fail(AUVPF_ERR_BADARG, "AUVPF_RS_STRICT_REF emulates the reference's sequential draw: particle_count <= 65536");
+    int rc;
+    if ((rc = run_normalise(h, src))) return rc;
+    if ((rc = run_scan(h, src, /*fused=*/true))) return rc;
+    h->have_norm = true;
+    h->last_src_kind = src.kind;
+    h->lin_weights = src.lin;
+    if ((rc = check_degenerate(h))) return rc;
+    if ((rc = ensure_inplace_buffers(h))) return rc;
+    if (!h->scan3) CU(cudaMalloc(&h->scan3, sizeof(unsigned long long) * h->N));
+    if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
+    const double *ud = nullptr;
+    if (u && (rc = stage_in(h, S_IN3, u, (size_t)h->N, &ud))) return rc;
+    const float *rn = nullptr;
+    if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
+    const uint32_t step = h->step_resample++;
+    unsigned long long *K = h->totals2, *R = h->totals2 + h->F;
+    const dim3 g = grid1(h->M, kThreads, h->F);
+    {
+        Prof pr(h, AUVPF_K_SCAN);
+        if ((rc = reset_scan_state(h))) return rc;
+        k_scan_copies<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
+            h->cdf, h->M, h->deficit, h->global_offset, h->scan2, h->status, h->tile_counter, h->tiles_per_filter, K);
+        LAUNCHED(h, AUVPF_K_SCAN, 1);
+        if (!strict) {
+            if ((rc = reset_scan_state(h))) return rc;
+            k_scan_fracs<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
+                h->cdf, h->M, h->deficit, h->global_offset, h->scan3, h->status, h->tile_counter, h->tiles_per_filter,
+                R);
+            LAUNCHED(h, AUVPF_K_SCAN, 1);
+        }
+        CU(cudaGetLastError());
+    }
+    {
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        k_residual_fill<<<g, kThreads, 0, h->stream>>>(h->scan2, h->scan3, h->M, K, R, ud, h->cfg.seed, step,
+                                                      strict ? 0 : 1, h->anc);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+        if (strict) {
+            k_residual_strict<<<h->F, kThreads, 0, h->stream>>>(h->cdf, h->M, h->deficit, h->global_offset, K,
+                                                                reinterpret_cast<double *>(h->scan3), ud, h->cfg.seed,
+                                                                step, h->anc);
+            LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+        }
+        CU(cudaGetLastError());
+    }
+    if (ancestors_out) {
+        if (is_device_ptr(ancestors_out))
+            CU(cudaMemcpyAsync(ancestors_out, h->anc, sizeof(int32_t) * h->N, cudaMemcpyDeviceToDevice, h->stream));
+        else if ((rc = finish_out(h, ancestors_out, (const int32_t *)h->anc, (size_t)h->N)))
+            return rc;
+    }
+    if (inplace) {                       // the reference: keep / lost / dupes, then add_noise on every particle
+        if ((rc = apply_indices_dev(h, h->anc))) return rc;
+        if (rough_var && (rc = auvpf_roughen(h, rough_var, rough_noise))) return rc;
+    } else {
+        NoiseParams rough = make_noise(h, rough_var, nullptr, rough_var ? 1 : 0, h->step_rough, kStreamRoughen);
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        k_gather_indices<<<g, kThreads, 0, h->stream>>>(h->anc, h->M, h->st[h->cur], h->st[1 - h->cur], rough, rn);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+        CU(cudaGetLastError());
+        h->cur = 1 - h->cur;
+        if (rough_var) h->step_rough++;
+    }
+    return AUVPF_OK;
+}
+
 int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t flags, const double *u,
                 int32_t *ancestors_out, const double *rough_var, const float *rough_noise)
 {
-    if (mode != AUVPF_SYSTEMATIC)
-        return fail(AUVPF_ERR_BADARG, "resample mode %d not available in this build (systematic only)", mode);
+    if (mode == AUVPF_RESIDUAL) return do_resample_residual(h, src, flags, u, ancestors_out, rough_var, rough_noise);
+    if (mode != AUVPF_SYSTEMATIC) return fail(AUVPF_ERR_BADARG, "unknown resample mode %d", mode);
     int rc;
-    if ((rc = run_max(h, src))) return rc;
-    if ((rc = check_degenerate(h))) return rc;
-    if ((rc = run_sum(h, src))) return rc;
-    k_combine_limbs<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->limbs, h->A, h->F);
-    if ((rc = run_scan(h, src))) return rc;
-    k_deficit<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->Q, h->deficit, h->F);
-    LAUNCHED(h, AUVPF_K_NORMALISE, 3);
+    if ((rc = run_normalise(h, src))) return rc;
+    if ((rc = run_scan(h, src, /*fused=*/true))) return rc;
     h->have_norm = true;
     h->last_src_kind = src.kind;
     h->lin_weights = src.lin;
@@ -503,15 +637,20 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     sp.out_lo = 0;
     sp.n_out = h->M;
     sp.q_offset = 0;
+    sp.tiles_per_filter = h->tiles_per_filter;
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
         StateView dst = h->st[1 - h->cur];
         if (inplace) dst.x = nullptr;   // ancestors only
         k_select_gather<false><<<grid1(h->M, kSelTile, h->F), kThreads, 0, h->stream>>>(
-            h->cdf, sp, h->u, h->deficit, h->st[h->cur], dst, nullptr, anc_dev, nullptr, rough, rn);
+            h->cdf, sp, h->u, h->deficit, h->st[h->cur], dst, nullptr, anc_dev, nullptr, rough, rn, h->status,
+            h->degenerate);
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
+    // one small read-back at the END of the enqueued cycle: a filter without any finite weight made
+    // the kernels above skip it, the state is untouched and the call fails
+    if ((rc = check_degenerate(h))) return rc;
     if (!inplace) {
         h->cur = 1 - h->cur;
         if (rough_var) h->step_rough++;
@@ -570,7 +709,11 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         CU(cudaMalloc(&h->cdf, sizeof(unsigned long long) * h->N));
         CU(cudaMalloc(&h->wmax_ordered, sizeof(long long) * F));
         CU(cudaMalloc(&h->wmax, sizeof(double) * F));
+        CU(cudaMalloc(&h->wmax_f32, sizeof(int) * F));
+        CU(cudaMalloc(&h->done, sizeof(unsigned int) * F));
+        CU(cudaMemsetAsync(h->done, 0, sizeof(unsigned int) * F, h->stream));
         CU(cudaMalloc(&h->limbs, sizeof(unsigned long long) * 2 * F));
+        CU(cudaMemsetAsync(h->limbs, 0, sizeof(unsigned long long) * 2 * F, h->stream));
         CU(cudaMalloc(&h->A, sizeof(unsigned long long) * 2 * F));
         CU(cudaMalloc(&h->Q, sizeof(unsigned long long) * F));
         CU(cudaMalloc(&h->deficit, sizeof(unsigned long long) * F));
@@ -629,6 +772,7 @@ int auvpf_destroy(auvpf_handle *h)
     void *bufs[] = {h->logw,    h->cdf,   h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
                     h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->status,  h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
+                    h->wmax_f32, h->done, h->scan3,
                     h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flags, h->probe_flags.p};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
@@ -915,6 +1059,7 @@ int auvpf_set_logw(auvpf_handle *h, const float *logw)
     Guard g(h);
     CU(cudaMemcpyAsync(h->logw, logw, sizeof(float) * h->N,
                        is_device_ptr(logw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    h->wmax_valid = false;
     return AUVPF_OK;
 }
 
@@ -952,10 +1097,13 @@ int auvpf_update_gps(auvpf_handle *h, const double *gps_xy, float *logw_out)
     if (is_device_ptr(gps_xy)) CU(cudaMemcpyAsync(h->gps, gps_xy, sizeof(double) * 2 * h->F, cudaMemcpyDeviceToDevice, h->stream));
     else if ((rc = tiny_upload(h, h->gps, gps_xy, sizeof(double) * 2 * h->F))) return rc;
     const double var = h->cfg.meas_std * h->cfg.meas_std;
+    CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * h->F, h->stream));
+    h->wmax_valid = true;
     {
         Prof pr(h, AUVPF_K_UPDATE_GPS);
         k_update_gps<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(
-            h->st[h->cur], h->M, h->frame, h->gps, (float)(0.5 / var), (float)(-std::log(2.0 * kPi * var)), h->logw);
+            h->st[h->cur], h->M, h->frame, h->gps, (float)(0.5 / var), (float)(-std::log(2.0 * kPi * var)), h->logw,
+            h->wmax_f32);
         LAUNCHED(h, AUVPF_K_UPDATE_GPS, 1);
         CU(cudaGetLastError());
     }
@@ -971,6 +1119,8 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
     CU(cudaMemcpyAsync(h->meas, ranges, sizeof(float) * (size_t)h->B * h->F,
                        is_device_ptr(ranges) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     const double var = h->cfg.meas_std * h->cfg.meas_std;
+    CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * h->F, h->stream));
+    h->wmax_valid = true;
     {
         Prof pr(h, AUVPF_K_UPDATE_MBES);
         const float nhiv = (float)(-0.5 / var), lnb = (float)std::log(h->cfg.meas_std * std::sqrt(2.0 * kPi));
@@ -980,7 +1130,7 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
             const size_t smp = (2 * sizeof(double) + 2 * sizeof(float)) * h->B;
             k_update_mbes_profile<<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
                 h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
-                (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flags);
+                (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flags, h->wmax_f32);
             LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
             only = h->flags;
         }
@@ -988,7 +1138,7 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
         const size_t smem = sizeof(float) * 6 * h->B + sizeof(int) * 32 * h->fan.chunk;
         k_update_mbes<<<grid1(h->M, kMbesWarps, h->F), kMbesWarps * 32, smem, h->stream>>>(
             h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beams, h->beam_aux, h->beam_order, h->meas, h->B,
-            (float)h->cfg.range_min, nhiv, lnb, h->logw, only);
+            (float)h->cfg.range_min, nhiv, lnb, h->logw, only, h->wmax_f32);
         LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
         CU(cudaGetLastError());
     }
@@ -1152,6 +1302,7 @@ int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *limbs_out)
     WeightSrc src{h->logw, nullptr, 0};
     if ((rc = run_sum(h, src))) return rc;
     CU(cudaMemcpyAsync(limbs_out, h->limbs, sizeof(unsigned long long) * 2 * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemsetAsync(h->limbs, 0, sizeof(unsigned long long) * 2 * h->F, h->stream));   // k_normalise expects zeros
     CU(cudaStreamSynchronize(h->stream));
     return AUVPF_OK;
 }
@@ -1196,12 +1347,13 @@ int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t defi
     sp.out_lo = out_lo;
     sp.n_out = n_out;
     sp.q_offset = q_offset;
+    sp.tiles_per_filter = h->tiles_per_filter;
     NoiseParams none = make_noise(h, nullptr, nullptr, 0, 0, kStreamRoughen);
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
         StateView nodst{};
         k_select_gather<true><<<grid1(n_out, kSelTile, 1), kThreads, 0, h->stream>>>(
-            h->cdf, sp, h->u, h->deficit, h->st[h->cur], nodst, rd, nullptr, ad, none, nullptr);
+            h->cdf, sp, h->u, h->deficit, h->st[h->cur], nodst, rd, nullptr, ad, none, nullptr, h->status, nullptr);
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }

@@ -67,6 +67,19 @@ __device__ __forceinline__ double warp_sum_f64(double v)
     return v;
 }
 
+// Per-filter maximum of the log-weights, published by the kernel that produces them so that
+// normalisation needs no separate max pass.  float32 in the order-preserving int encoding;
+// reset value kWmaxReset (a 0x80 byte fill) decodes to -3.39e38: "no finite weight seen".
+constexpr int kWmaxReset = (int)0x80808080;
+constexpr float kWmaxNone = -3.0e38f;
+
+__device__ __forceinline__ void warp_publish_max(float v, bool valid, int *wmax_f32)
+{
+    int k = (valid && v == v) ? float_to_ordered(v) : kWmaxReset;
+    k = __reduce_max_sync(0xffffffffu, k);
+    if ((threadIdx.x & 31) == 0 && k > kWmaxReset) atomicMax(wmax_f32, k);
+}
+
 // ---------------------------------------------------------------------------------------------
 // add_noise (auv_particle.py:32-36): pose = base + sigma * n.  `set_mean` != nullptr makes it the
 // particle initialiser (pose = mean + sigma n); otherwise roughening of the current state.
@@ -74,6 +87,7 @@ struct NoiseParams {
     float sigma[6];
     double mean[6];
     int mode;                // 0 = none, 1 = pose += sigma n, 2 = pose = mean + sigma n
+    unsigned need;           // bit c: sigma[c] != 0 (normals multiplied by zero are not generated)
     uint64_t seed;
     uint32_t step;
     uint32_t stream;
@@ -88,11 +102,7 @@ __device__ __forceinline__ void six_normals(const NoiseParams &p, int64_t gid, c
 #pragma unroll
         for (int c = 0; c < 6; ++c) n[c] = __ldg(noise + row * 6 + c);
     } else {
-        U4 r0 = philox_for(p.seed, gid, p.step, p.stream, 0);
-        U4 r1 = philox_for(p.seed, gid, p.step, p.stream, 1);
-        box_muller(r0.x, r0.y, n[0], n[1]);
-        box_muller(r0.z, r0.w, n[2], n[3]);
-        box_muller(r1.x, r1.y, n[4], n[5]);
+        pose_normals(p.seed, gid, p.step, p.stream, p.need, n);
     }
 }
 
@@ -195,12 +205,12 @@ k_propagate(StateView s, int64_t M, PredictParams p0, const PredictParams *param
 // GPS update (a3, reference form): logw = -d^2 / (2 std^2) - log(2 pi std^2)
 __global__ void __launch_bounds__(kThreads)
 k_update_gps(StateView s, int64_t M, FrameParams fp, const double *gps_xy, float inv_2var, float lognorm,
-             float *logw)
+             float *logw, int *wmax_f32)
 {
     int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= M) return;
     int f = blockIdx.y;
-    int64_t row = (int64_t)f * M + i;
+    const bool active = i < M;
+    int64_t row = (int64_t)f * M + (active ? i : 0);
     double x = s.x[row], y = s.y[row], z = (double)s.z[row];
     double px, py;
     if (fp.m2o_identity_r) {
@@ -211,7 +221,9 @@ k_update_gps(StateView s, int64_t M, FrameParams fp, const double *gps_xy, float
         py = fp.m2o_r[3] * x + fp.m2o_r[4] * y + fp.m2o_r[5] * z + fp.m2o_t[1];
     }
     double dx = gps_xy[2 * f] - px, dy = gps_xy[2 * f + 1] - py;
-    logw[row] = (float)(-(dx * dx + dy * dy) * (double)inv_2var + (double)lognorm);
+    const float lw = (float)(-(dx * dx + dy * dy) * (double)inv_2var + (double)lognorm);
+    if (active) logw[row] = lw;
+    warp_publish_max(lw, active, wmax_f32 + f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -337,7 +349,7 @@ __global__ void __launch_bounds__(kMbesWarps * 32)
 k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan, const float *__restrict__ beam_dirs,
               const float *__restrict__ beam_aux, const int *__restrict__ order, const float *__restrict__ meas, int B,
               float range_min, float neg_half_inv_var, float log_norm_per_beam, float *__restrict__ logw,
-              const unsigned char *__restrict__ only_flagged)
+              const unsigned char *__restrict__ only_flagged, int *__restrict__ wmax_f32)
 {
     extern __shared__ float sm[];
     int *s_ord = reinterpret_cast<int *>(sm + 6 * B);
@@ -370,7 +382,14 @@ k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan
         acc = fmaf(e, e, acc);
     });
     acc = warp_sum(acc);
-    if (lane == 0) logw[row] = fmaf(neg_half_inv_var, acc, lognorm);
+    if (lane == 0) {
+        const float lw = fmaf(neg_half_inv_var, acc, lognorm);
+        logw[row] = lw;
+        if (lw == lw) {
+            const int k = float_to_ordered(lw);
+            if (k > kWmaxReset) atomicMax(wmax_f32 + f, k);
+        }
+    }
 }
 
 // Parity probe: expected ranges for explicit poses, (n, B) float32; same traversal as above.
@@ -406,7 +425,7 @@ k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, Dem
 // per-ray kernel above.
 constexpr int kProfThreads = 128;
 #ifndef AUVPF_PROF_MIN_BLOCKS
-#define AUVPF_PROF_MIN_BLOCKS 1
+#define AUVPF_PROF_MIN_BLOCKS 5   // 96 registers: 5 blocks per SM (97 would drop to 4: measured 14 % slower)
 #endif
 
 // shared memory: tan (double B) | sec (double B) | |sin| (float B) | measured range (float B)
@@ -442,7 +461,8 @@ __global__ void __launch_bounds__(kProfThreads, AUVPF_PROF_MIN_BLOCKS)
 k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan,
                       const double *__restrict__ beam_tan, const float *__restrict__ beam_aux,
                       const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,
-                      float log_norm_per_beam, float *__restrict__ logw, unsigned char *__restrict__ flags)
+                      float log_norm_per_beam, float *__restrict__ logw, unsigned char *__restrict__ flags,
+                      int *__restrict__ wmax_f32)
 {
     extern __shared__ double smd[];
     double *s_tan = smd, *s_sec = smd + B;
@@ -474,9 +494,12 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
         const float e = rm - range;
         if (rm == rm) acc = fmaf(e, e, acc);
     });
-    if (!active) return;
-    flags[row] = ok ? 0 : 1;
-    if (ok) logw[row] = fmaf(neg_half_inv_var, acc, -(float)s_valid * log_norm_per_beam);
+    const float lw = fmaf(neg_half_inv_var, acc, -(float)s_valid * log_norm_per_beam);
+    if (active) {
+        flags[row] = ok ? 0 : 1;
+        if (ok) logw[row] = lw;
+    }
+    warp_publish_max(lw, active && ok, wmax_f32 + f);
 }
 
 __global__ void __launch_bounds__(kProfThreads)
@@ -638,6 +661,111 @@ __global__ void k_combine_limbs(const unsigned long long *limbs, unsigned long l
     A[2 * f + 1] = (unsigned long long)(a >> 64);
 }
 
+// Single-GPU normalisation in ONE launch: the maximum arrives from the update kernel
+// (wmax_f32, ordered int) or from k_weight_max (wmax already float64 when wmax_f32 == nullptr);
+// every block adds its exact integer partial of A = sum_i a_i; the LAST block of a filter
+// (ticket counter) folds the limbs into A, publishes max / A / the degenerate flag and cleans
+// the accumulators for the next cycle.  The blocks also clear the scan's tile status words, so
+// the scan kernel needs no memset in front of it.
+struct NormState {
+    int *wmax_f32;                  // [F] ordered-int float32 max (update kernels), or nullptr
+    double *wmax;                   // [F] in (wmax_f32 == nullptr) / out
+    unsigned long long *limbs;      // [2F] zero on entry, zero on exit
+    unsigned int *done;             // [F]  zero on entry, zero on exit
+    unsigned long long *A;          // [2F] out
+    int *degenerate;                // [F]  out
+    double *sumsq;                  // [F]  zeroed
+    unsigned long long *status;     // [tiles_total] zeroed
+    unsigned int *tile_counter;     // zeroed
+    long long tiles_total;
+    unsigned long long *a_out;      // [F*M] a_i, kept for the scan (which overwrites it in place with the CDF)
+};
+
+__global__ void __launch_bounds__(kThreads) k_normalise(WeightSrc w, int64_t M, NormState ns)
+{
+    const int f = blockIdx.y;
+    // clear the scan machinery (any block, grid-stride)
+    {
+        const long long nth = (long long)gridDim.x * gridDim.y * kThreads;
+        const long long tid = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * kThreads + threadIdx.x;
+        for (long long t = tid; t < ns.tiles_total; t += nth) ns.status[t] = 0ull;
+        if (tid == 0) *ns.tile_counter = 0u;
+    }
+    double m;
+    if (ns.wmax_f32) {
+        const int k = ns.wmax_f32[f];
+        m = k > kWmaxReset ? (double)ordered_to_float(k) : -INFINITY;
+    } else
+        m = ns.wmax[f];
+    const bool bad = !isfinite(m) || (w.kind == 1 && !(m > 0.0));
+    unsigned long long lo = 0, hi = 0;
+    if (!bad) {
+        // four independent loads in flight per thread before the long float64 exp chains start
+        const int64_t stride = (int64_t)gridDim.x * kThreads;
+        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += 4 * stride) {
+            double xv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t ii = i + k * stride;
+                xv[k] = ii < M ? src_value(w, (int64_t)f * M + ii) : (w.kind == 0 ? -INFINITY : 0.0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t a = w.kind == 0 ? a_from_x(xv[k] - (double)(float)m) : a_from_linear(xv[k], m);
+                if (i + k * stride < M) ns.a_out[(int64_t)f * M + i + k * stride] = a;
+                lo += a & 0xFFFFFFFFull;
+                hi += a >> 32;
+            }
+        }
+    }
+    lo = warp_sum_u64(lo);
+    hi = warp_sum_u64(hi);
+    __shared__ unsigned long long slo[kThreads / 32], shi[kThreads / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        slo[warp] = lo;
+        shi[warp] = hi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < kThreads / 32; ++k) {
+            lo += slo[k];
+            hi += shi[k];
+        }
+        if (lo) atomicAdd(ns.limbs + 2 * f, lo);
+        if (hi) atomicAdd(ns.limbs + 2 * f + 1, hi);
+        __threadfence();
+        const unsigned int ticket = atomicAdd(ns.done + f, 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const unsigned long long l0 = atomicExch(ns.limbs + 2 * f, 0ull), l1 = atomicExch(ns.limbs + 2 * f + 1, 0ull);
+            const unsigned __int128 a = (unsigned __int128)l0 + ((unsigned __int128)l1 << 32);
+            ns.A[2 * f] = (unsigned long long)a;
+            ns.A[2 * f + 1] = (unsigned long long)(a >> 64);
+            ns.wmax[f] = m;
+            ns.degenerate[f] = (bad || a == 0) ? 1 : 0;
+            ns.sumsq[f] = 0.0;
+            ns.done[f] = 0u;
+        }
+    }
+}
+
+// float32 log-weights that did not come from an update kernel (auvpf_set_logw): max pass
+__global__ void __launch_bounds__(kThreads) k_weight_max_f32(const float *logw, int64_t M, int *wmax_f32)
+{
+    const int f = blockIdx.y;
+    float m = -INFINITY;
+    bool any = false;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        const float v = logw[(int64_t)f * M + i];
+        if (v == v) {
+            m = fmaxf(m, v);
+            any = true;
+        }
+    }
+    warp_publish_max(m, any, wmax_f32 + f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Single-pass decoupled-lookback inclusive scan (Merrill & Garland) of uint64 values.
 // One 64-bit status word per tile: [63:62] flag (1 = tile aggregate, 2 = inclusive prefix),
@@ -650,7 +778,8 @@ template <class ValueFn>
 __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigned long long *__restrict__ out,
                                                volatile unsigned long long *status, unsigned int *tile_counter,
                                                int tiles_per_filter, unsigned long long *totals,
-                                               double *sumsq /* optional: sum of (v 2^-52)^2 */)
+                                               double *sumsq /* optional: sum of (v 2^-52)^2 */,
+                                               unsigned long long *deficit = nullptr /* optional: 2^52 - total */)
 {
     __shared__ unsigned int s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
@@ -693,46 +822,52 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
     }
     unsigned long long excl = warp_off + incl - tsum;
 
-    // publish aggregate / look back (warp 0)
-    if (warp == 0) {
+    // publish the aggregate, then look back with the WHOLE block: thread k polls tile idx - k, so
+    // one hop covers kThreads predecessors.  (With warp-0-only look-back and all tiles running
+    // in lock-step the chain was tiles/32 dependent hops long; ncu showed the block waiting at the
+    // barrier for most of the kernel.)
+    {
         volatile unsigned long long *st = status + (size_t)f * tiles_per_filter;
-        if (tile == 0) {
-            if (lane == 0) {
-                st[0] = kFlagPrefix | block_total;
-                s_prefix = 0;
+        __shared__ int s_first[kThreads / 32];
+        __shared__ unsigned long long s_part[kThreads / 32];
+        if (threadIdx.x == 0) st[tile] = (tile == 0 ? kFlagPrefix : kFlagAgg) | block_total;
+        unsigned long long run = 0;
+        int idx = tile - 1;
+        while (idx >= 0) {                                   // block-uniform
+            const int j = idx - (int)threadIdx.x;
+            unsigned long long wd = kFlagPrefix;             // before the filter's first tile: prefix 0
+            if (j >= 0) {
+                do {
+                    wd = st[j];
+                } while ((wd >> 62) == 0);
             }
-        } else {
-            if (lane == 0) st[tile] = kFlagAgg | block_total;
-            unsigned long long run = 0;
-            int idx = tile - 1;
-            while (true) {
-                int j = idx - lane;
-                unsigned long long wd = kFlagPrefix;      // before the filter's first tile: prefix 0
-                if (j >= 0) {
-                    do {
-                        wd = st[j];
-                    } while ((wd >> 62) == 0);
-                }
-                unsigned pm = __ballot_sync(0xffffffffu, (wd >> 62) == 2);
-                unsigned long long val = wd & kValMask;
-                if (pm) {
-                    int L = __ffs(pm) - 1;                 // nearest tile that already has a prefix
-                    unsigned long long c = lane <= L ? val : 0ull;
-                    run += warp_sum_u64(c);
-                    break;
-                }
-                run += warp_sum_u64(val);
-                idx -= 32;
-            }
-            if (lane == 0) {
-                st[tile] = kFlagPrefix | (run + block_total);
-                s_prefix = run;
-            }
+            // nearest predecessor that already carries an inclusive prefix
+            const unsigned pm = __ballot_sync(0xffffffffu, (wd >> 62) == 2);
+            if (lane == 0) s_first[warp] = pm ? warp * 32 + (__ffs(pm) - 1) : kThreads;
+            __syncthreads();
+            int L = kThreads;
+#pragma unroll
+            for (int k = 0; k < kThreads / 32; ++k) L = min(L, s_first[k]);
+            unsigned long long c = ((int)threadIdx.x <= L) ? (wd & kValMask) : 0ull;
+            c = warp_sum_u64(c);
+            if (lane == 0) s_part[warp] = c;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kThreads / 32; ++k) run += s_part[k];
+            if (L < kThreads) break;
+            idx -= kThreads;
+        }
+        if (threadIdx.x == 0) {
+            if (tile != 0) st[tile] = kFlagPrefix | (run + block_total);
+            s_prefix = run;
         }
     }
     __syncthreads();
     unsigned long long acc = s_prefix + excl;
-    if (totals && threadIdx.x == 0 && tile == tiles_per_filter - 1) totals[f] = s_prefix + block_total;
+    if (totals && threadIdx.x == 0 && tile == tiles_per_filter - 1) {
+        totals[f] = s_prefix + block_total;
+        if (deficit) deficit[f] = (1ull << kQBits) - (s_prefix + block_total);
+    }
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         acc += v[k];
@@ -744,16 +879,49 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
     }
 }
 
-// stage 3: q_i = floor(a_i 2^52 / A); inclusive integer CDF (raw: before the deficit units)
+// stage 3: q_i = floor(a_i 2^52 / A); inclusive integer CDF (raw: before the deficit units).
+// After the kernel every tile's status word holds its inclusive prefix: the tile table that the
+// select kernel searches first.  `deficit` (optional) = 2^52 - Q, written with the total.
 __global__ void __launch_bounds__(kThreads)
 k_scan_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A, unsigned long long *cdf,
          unsigned long long *status, unsigned int *tile_counter, int tiles_per_filter, unsigned long long *Q,
-         double *sumsq)
+         double *sumsq, unsigned long long *deficit, const int *degenerate)
 {
+    int cached_f = -1;          // a tile belongs to one filter: the divisor is set up once per thread
+    QDiv d{};
+    double m = 0.0;
+    bool dead = false;
     auto value = [&](int64_t row, int f) -> unsigned long long {
-        return q_from_a(src_a(w, row, wmax[f]), A[2 * f], A[2 * f + 1]);
+        if (f != cached_f) {
+            cached_f = f;
+            d = make_qdiv(A[2 * f], A[2 * f + 1]);
+            m = wmax[f];
+            dead = degenerate && degenerate[f];
+        }
+        return dead ? 0ull : q_from_a(src_a(w, row, m), d);
     };
-    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq);
+    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit);
+}
+
+// Same scan on the a_i left in `cdf` by k_normalise (in place: a tile reads its own entries before
+// it writes them), so the float64 exp is not evaluated a second time.
+__global__ void __launch_bounds__(kThreads, 4)
+k_scan_q_from_a(int64_t M, const unsigned long long *A, unsigned long long *cdf, unsigned long long *status,
+                unsigned int *tile_counter, int tiles_per_filter, unsigned long long *Q, double *sumsq,
+                unsigned long long *deficit, const int *degenerate)
+{
+    int cached_f = -1;
+    QDiv d{};
+    bool dead = false;
+    auto value = [&](int64_t row, int f) -> unsigned long long {
+        if (f != cached_f) {
+            cached_f = f;
+            d = make_qdiv(A[2 * f], A[2 * f + 1]);
+            dead = degenerate[f] != 0;
+        }
+        return dead ? 0ull : q_from_a(cdf[row], d);
+    };
+    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit);
 }
 
 // q_i itself (parity read-back): q_i + (i_global < D)
@@ -782,7 +950,7 @@ __global__ void k_deficit(const unsigned long long *Q, unsigned long long *defic
 // contiguous CDF interval that is staged in shared memory and searched there.
 constexpr int kSelItems = 4;
 constexpr int kSelTile = kThreads * kSelItems;
-constexpr int kSelSpan = 3072;   // CDF entries staged per block (24 KB)
+constexpr int kSelSpan = 2 * kScanTile;   // CDF entries staged per block: two scan tiles (32 KB)
 
 struct SelectParams {
     int64_t M;             // local particles per filter (CDF length)
@@ -791,22 +959,31 @@ struct SelectParams {
     int64_t out_lo;        // first global output slot emitted by this launch
     int64_t n_out;         // outputs per filter emitted by this launch
     unsigned long long q_offset;   // integer CDF mass of lower shards
+    int tiles_per_filter;  // scan tiles per filter (tile table = the scan's status words)
 };
 
-__device__ __forceinline__ double full_cdf(const unsigned long long *cdf, int64_t j, const SelectParams &p,
-                                           unsigned long long D)
+// Integer form of the reference's comparison positions[i] < cumsum[j] (resampling.py:163):
+// cumsum[j] = c 2^-52 exactly and pos 2^52 is an exact float64, so  pos < c 2^-52  <=>
+// floor(pos 2^52) < c.  The search therefore runs on 64-bit integers.
+__device__ __forceinline__ unsigned long long pos_key(double pos)
 {
-    unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
-    return cdf_value(p.q_offset + cdf[j] + (jg1 < D ? jg1 : D));
+    return (unsigned long long)floor(pos * 4503599627370496.0);
 }
 
-// first j in [lo, hi) with pos < cdf(j); hi if none
-__device__ __forceinline__ int64_t search_cdf(const unsigned long long *cdf, int64_t lo, int64_t hi, double pos,
-                                              const SelectParams &p, unsigned long long D)
+__device__ __forceinline__ unsigned long long full_cdf(const unsigned long long *cdf, int64_t j, const SelectParams &p,
+                                                       unsigned long long D)
+{
+    unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
+    return p.q_offset + cdf[j] + (jg1 < D ? jg1 : D);
+}
+
+// first j in [lo, hi) with key < cdf(j); hi if none
+__device__ __forceinline__ int64_t search_cdf(const unsigned long long *cdf, int64_t lo, int64_t hi,
+                                              unsigned long long key, const SelectParams &p, unsigned long long D)
 {
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
-        if (pos < full_cdf(cdf, mid, p, D)) hi = mid;
+        if (key < full_cdf(cdf, mid, p, D)) hi = mid;
         else lo = mid + 1;
     }
     return lo;
@@ -816,73 +993,318 @@ template <bool kRecords>
 __global__ void __launch_bounds__(kThreads)
 k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, const double *__restrict__ u_all,
                 const unsigned long long *__restrict__ deficit, StateView src, StateView dst, Record *records,
-                int32_t *anc32, int64_t *anc64, NoiseParams rough, const float *rough_noise)
+                int32_t *anc32, int64_t *anc64, NoiseParams rough, const float *rough_noise,
+                const unsigned long long *__restrict__ tile_table, const int *__restrict__ degenerate)
 {
-    __shared__ double s_cdf[kSelSpan];
+    __shared__ unsigned long long s_cdf[kSelSpan];
     __shared__ int64_t s_j[2];
     const int f = blockIdx.y;
+    if (degenerate && degenerate[f]) return;            // no finite weight: nothing is emitted, the caller keeps the state
     const unsigned long long *cdf = cdf_all + (size_t)f * p.M;
     const unsigned long long D = deficit[f];
     const double u = u_all[f], n = (double)p.n_global;
     const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
     if (k0 >= p.n_out) return;
     const int64_t k1 = min(k0 + (int64_t)kSelTile, p.n_out) - 1;
-    if (threadIdx.x == 0) s_j[0] = search_cdf(cdf, 0, p.M, sys_position(u, p.out_lo + k0, n), p, D);
-    if (threadIdx.x == 32) s_j[1] = search_cdf(cdf, 0, p.M, sys_position(u, p.out_lo + k1, n), p, D);
-    __syncthreads();
-    const int64_t j_lo = min(s_j[0], p.M - 1), j_hi = min(s_j[1], p.M - 1);
+    // Level 1: the scan tiles holding the ancestors of the block's first and last output.  The
+    // tile table (inclusive prefix per tile, left in the status words by the scan) is read with
+    // coalesced loads and COUNTED (tiles whose end lies at or below the position), so there is no
+    // dependent chain of global loads.
+    const unsigned long long key_lo = pos_key(sys_position(u, p.out_lo + k0, n)),
+                             key_hi = pos_key(sys_position(u, p.out_lo + k1, n));
+    int t_lo = 0, t_hi = 0;
+    {
+        const unsigned long long *tab = tile_table + (size_t)f * p.tiles_per_filter;
+        for (int t0 = 0; t0 < p.tiles_per_filter; t0 += kThreads) {
+            const int t = t0 + threadIdx.x;
+            bool below_lo = false, below_hi = false;
+            if (t < p.tiles_per_filter) {
+                const int64_t je = min((int64_t)(t + 1) * kScanTile, p.M) - 1;
+                const unsigned long long jg1 = (unsigned long long)(p.j_global0 + je + 1);
+                const unsigned long long c = p.q_offset + (tab[t] & kValMask) + (jg1 < D ? jg1 : D);
+                below_lo = !(key_lo < c);
+                below_hi = !(key_hi < c);
+            }
+            const int c_lo = __syncthreads_count(below_lo), c_hi = __syncthreads_count(below_hi);
+            t_lo += c_lo;
+            t_hi += c_hi;
+            if (c_hi < kThreads) break;                 // monotone table: nothing further can be below
+        }
+        t_lo = min(t_lo, p.tiles_per_filter - 1);
+        t_hi = min(t_hi, p.tiles_per_filter - 1);
+    }
+    // Level 2: stage the CDF of those tiles (usually one or two) and search it in shared memory.
+    int64_t j_lo = (int64_t)t_lo * kScanTile, j_hi = min((int64_t)(t_hi + 1) * kScanTile, p.M) - 1;
+    if (j_hi - j_lo + 1 > kSelSpan) {
+        // many low-weight particles between the two ends: locate them exactly (global search)
+        if (threadIdx.x == 0) s_j[0] = search_cdf(cdf, j_lo, j_hi + 1, key_lo, p, D);
+        if (threadIdx.x == 32) s_j[1] = search_cdf(cdf, j_lo, j_hi + 1, key_hi, p, D);
+        __syncthreads();
+        j_lo = min(s_j[0], p.M - 1);
+        j_hi = min(s_j[1], p.M - 1);
+    }
     const int64_t span = j_hi - j_lo + 1;
     const bool staged = span <= kSelSpan;
     if (staged)
         for (int64_t t = threadIdx.x; t < span; t += kThreads) s_cdf[t] = full_cdf(cdf, j_lo + t, p, D);
     __syncthreads();
+
+    // Each thread resolves kSelItems ADJACENT outputs: the first by binary search, the others by
+    // walking on from it (ancestors of consecutive outputs are equal or adjacent most of the time).
+    const int64_t kb = k0 + (int64_t)threadIdx.x * kSelItems;
+    if (kb > k1) return;
+    int64_t jj[kSelItems];
+    {
+        int64_t prev = 0;       // index into the staged window / offset from j_lo
 #pragma unroll
-    for (int r = 0; r < kSelItems; ++r) {
-        const int64_t k = k0 + threadIdx.x + (int64_t)r * kThreads;
-        if (k > k1) break;
-        const int64_t i = p.out_lo + k;
-        const double pos = sys_position(u, i, n);
-        int64_t j;
-        if (staged) {
-            int lo = 0, hi = (int)span;
-            while (lo < hi) {
-                int mid = (lo + hi) >> 1;
-                if (pos < s_cdf[mid]) hi = mid;
-                else lo = mid + 1;
+        for (int r = 0; r < kSelItems; ++r) {
+            const int64_t k = kb + r;
+            if (k > k1) {
+                jj[r] = 0;
+                continue;
             }
-            j = j_lo + lo;
-        } else {
-            j = search_cdf(cdf, j_lo, j_hi + 1, pos, p, D);
-        }
-        j = min(j, p.M - 1);            // reference would run off the end (IndexError); clamp
-        const int64_t srow = (int64_t)f * p.M + j;
-        const int64_t orow = (int64_t)f * p.n_out + k;
-        double x = src.x[srow], y = src.y[srow];
-        float z = src.z[srow], ro = src.roll[srow], pi = src.pitch[srow], ya = src.yaw[srow];
-        if (anc32) anc32[orow] = (int32_t)j;
-        if (anc64) anc64[orow] = p.j_global0 + j;
-        if (kRecords) {
-            Record rec = {x, y, z, ro, pi, ya};
-            records[orow] = rec;
-        } else if (dst.x != nullptr) {
-            if (rough.mode == 1) {       // fused add_noise (auv_pf.py:191-192)
-                float nn[6];
-                six_normals(rough, (int64_t)f * rough.global_stride + i, rough_noise, orow, nn);
-                x += (double)(rough.sigma[0] * nn[0]);
-                y += (double)(rough.sigma[1] * nn[1]);
-                z += rough.sigma[2] * nn[2];
-                ro += rough.sigma[3] * nn[3];
-                pi += rough.sigma[4] * nn[4];
-                ya += rough.sigma[5] * nn[5];
+            const unsigned long long key = pos_key(sys_position(u, p.out_lo + k, n));
+            int64_t j;
+            if (staged) {
+                int lo = (int)prev, hi = (int)span;
+                if (r > 0) {                                   // short walk first
+                    int w = 0;
+                    while (w < 4 && lo < hi && !(key < s_cdf[lo])) {
+                        ++lo;
+                        ++w;
+                    }
+                    if (lo < hi && key < s_cdf[lo]) hi = lo;   // found
+                }
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (key < s_cdf[mid]) hi = mid;
+                    else lo = mid + 1;
+                }
+                prev = lo;
+                j = j_lo + lo;
+            } else {
+                j = search_cdf(cdf, j_lo + prev, j_hi + 1, key, p, D);
+                prev = j - j_lo;
             }
-            dst.x[orow] = x;
-            dst.y[orow] = y;
-            dst.z[orow] = z;
-            dst.roll[orow] = ro;
-            dst.pitch[orow] = pi;
-            dst.yaw[orow] = ya;
+            jj[r] = min(j, p.M - 1);                           // reference would run off the end (IndexError); clamp
         }
     }
+    const int64_t orow0 = (int64_t)f * p.n_out + kb;
+    const bool full4 = kb + kSelItems - 1 <= k1;
+    double x[kSelItems], y[kSelItems];
+    float z[kSelItems], ro[kSelItems], pi[kSelItems], ya[kSelItems];
+#pragma unroll
+    for (int r = 0; r < kSelItems; ++r) {
+        const int64_t srow = (int64_t)f * p.M + jj[r];
+        x[r] = src.x[srow];
+        y[r] = src.y[srow];
+        z[r] = src.z[srow];
+        ro[r] = src.roll[srow];
+        pi[r] = src.pitch[srow];
+        ya[r] = src.yaw[srow];
+    }
+    if (anc32) {
+        if (full4 && (orow0 & 3) == 0)
+            *reinterpret_cast<int4 *>(anc32 + orow0) = make_int4((int)jj[0], (int)jj[1], (int)jj[2], (int)jj[3]);
+        else
+            for (int r = 0; r < kSelItems && kb + r <= k1; ++r) anc32[orow0 + r] = (int32_t)jj[r];
+    }
+    if (anc64)
+        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) anc64[orow0 + r] = p.j_global0 + jj[r];
+    if (kRecords) {
+        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) {
+            Record rec = {x[r], y[r], z[r], ro[r], pi[r], ya[r]};
+            records[orow0 + r] = rec;
+        }
+        return;
+    }
+    if (dst.x == nullptr) return;
+    if (rough.mode == 1) {       // fused add_noise (auv_pf.py:191-192)
+#pragma unroll
+        for (int r = 0; r < kSelItems; ++r) {
+            if (kb + r > k1) break;
+            float nn[6];
+            six_normals(rough, (int64_t)f * rough.global_stride + p.out_lo + kb + r, rough_noise, orow0 + r, nn);
+            x[r] += (double)(rough.sigma[0] * nn[0]);
+            y[r] += (double)(rough.sigma[1] * nn[1]);
+            z[r] += rough.sigma[2] * nn[2];
+            ro[r] += rough.sigma[3] * nn[3];
+            pi[r] += rough.sigma[4] * nn[4];
+            ya[r] += rough.sigma[5] * nn[5];
+        }
+    }
+    if (full4 && (orow0 & 3) == 0) {
+        *reinterpret_cast<double2 *>(dst.x + orow0) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2 *>(dst.x + orow0 + 2) = make_double2(x[2], x[3]);
+        *reinterpret_cast<double2 *>(dst.y + orow0) = make_double2(y[0], y[1]);
+        *reinterpret_cast<double2 *>(dst.y + orow0 + 2) = make_double2(y[2], y[3]);
+        *reinterpret_cast<float4 *>(dst.z + orow0) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4 *>(dst.roll + orow0) = make_float4(ro[0], ro[1], ro[2], ro[3]);
+        *reinterpret_cast<float4 *>(dst.pitch + orow0) = make_float4(pi[0], pi[1], pi[2], pi[3]);
+        *reinterpret_cast<float4 *>(dst.yaw + orow0) = make_float4(ya[0], ya[1], ya[2], ya[3]);
+    } else {
+        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) {
+            dst.x[orow0 + r] = x[r];
+            dst.y[orow0 + r] = y[r];
+            dst.z[orow0 + r] = z[r];
+            dst.roll[orow0 + r] = ro[r];
+            dst.pitch[orow0 + r] = pi[r];
+            dst.yaw[orow0 + r] = ya[r];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual_resample (a6, resampling.py:27-76) on the fixed-point weights w_i = q_i 2^-52.
+// q_i is recovered from the integer CDF the scan left behind (+ the deficit unit).
+__device__ __forceinline__ unsigned long long q_from_cdf(const unsigned long long *cdf, int64_t base, int64_t i,
+                                                        unsigned long long D, int64_t global_offset)
+{
+    const unsigned long long c = cdf[base + i], prev = i > 0 ? cdf[base + i - 1] : 0ull;
+    return c - prev + ((unsigned long long)(global_offset + i) < D ? 1ull : 0ull);
+}
+
+// inclusive scan of the deterministic copy counts floor(N w_i) (:61); totals = k per filter
+__global__ void __launch_bounds__(kThreads)
+k_scan_copies(const unsigned long long *cdf, int64_t M, const unsigned long long *deficit, int64_t global_offset,
+              unsigned long long *out, unsigned long long *status, unsigned int *tile_counter, int tiles_per_filter,
+              unsigned long long *totals)
+{
+    auto value = [&](int64_t row, int f) -> unsigned long long {
+        const int64_t base = (int64_t)f * M;
+        return residual_copies(q_from_cdf(cdf, base, row - base, deficit[f], global_offset), M);
+    };
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+}
+
+// inclusive scan of the fractional parts N w_i - k_i on the 2^-38 grid; totals = R per filter
+__global__ void __launch_bounds__(kThreads)
+k_scan_fracs(const unsigned long long *cdf, int64_t M, const unsigned long long *deficit, int64_t global_offset,
+             unsigned long long *out, unsigned long long *status, unsigned int *tile_counter, int tiles_per_filter,
+             unsigned long long *totals)
+{
+    auto value = [&](int64_t row, int f) -> unsigned long long {
+        const int64_t base = (int64_t)f * M;
+        const unsigned long long q = q_from_cdf(cdf, base, row - base, deficit[f], global_offset);
+        return residual_frac(q, residual_copies(q, M), M);
+    };
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+}
+
+// first j in [0, M) with key < c[j]; M if none
+__device__ __forceinline__ int64_t first_above(const unsigned long long *c, int64_t M, unsigned long long key)
+{
+    int64_t lo = 0, hi = M;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (key < c[mid]) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+// indexes[0:k] = the copies in index order (:62-66); indexes[k:N] = multinomial draw on the
+// fractional parts (what :70-74 mean to do; the literal, numerically odd form is
+// k_residual_strict).  uniforms: (F, M) float64, the first M - k of a row are consumed (:74),
+// or nullptr for Philox (stream kStreamResample, call 1, id = f * M + t).
+__global__ void __launch_bounds__(kThreads)
+k_residual_fill(const unsigned long long *copies, const unsigned long long *fracs, int64_t M,
+                const unsigned long long *K, const unsigned long long *R, const double *uniforms, uint64_t seed,
+                uint32_t step, int fill_tail, int32_t *idx)
+{
+    const int f = blockIdx.y;
+    const int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (o >= M) return;
+    const int64_t base = (int64_t)f * M;
+    const int64_t k = (int64_t)K[f];
+    int64_t j;
+    if (o < k) {
+        j = first_above(copies + base, M, (unsigned long long)o);
+    } else {
+        if (!fill_tail) return;
+        const int64_t t = o - k;
+        const double uu = uniforms ? uniforms[base + t] : uniform53(philox_for(seed, base + t, step, kStreamResample, 1));
+        j = first_above(fracs + base, M, residual_target(uu, R[f]));
+    }
+    idx[base + o] = (int32_t)min(j, M - 1);
+}
+
+// The LITERAL residual draw of the reference (:70-74), for lock-step parity at the reference's own
+// particle counts: residual = w - num_copies (sic), residual /= sum(residual) with Python's
+// sequential sum, sequential cumsum, cumsum[-1] = 1, then NumPy's left searchsorted with its
+// key-to-key bounds hint on that non-monotone array.  One block per filter; the element-wise steps
+// are parallel, the three order-dependent ones run on thread 0.  c: (F, M) float64 scratch.
+__global__ void __launch_bounds__(kThreads)
+k_residual_strict(const unsigned long long *cdf, int64_t M, const unsigned long long *deficit, int64_t global_offset,
+                  const unsigned long long *K, double *c_all, const double *uniforms, uint64_t seed, uint32_t step,
+                  int32_t *idx)
+{
+    const int f = blockIdx.x;
+    const int64_t base = (int64_t)f * M;
+    double *c = c_all + base;
+    __shared__ double s_sum;
+    for (int64_t i = threadIdx.x; i < M; i += kThreads) {
+        const unsigned long long q = q_from_cdf(cdf, base, i, deficit[f], global_offset);
+        const double w = cdf_value(q);
+        c[i] = add_rn(w, -(double)residual_copies(q, M));                 // :70
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int64_t i = 0; i < M; ++i) s = add_rn(s, c[i]);              // builtin sum(), :71
+        s_sum = s;
+    }
+    __syncthreads();
+    const double s = s_sum;
+    for (int64_t i = threadIdx.x; i < M; i += kThreads) c[i] = div_rn(c[i], s);   // :71
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = c[0];
+        for (int64_t i = 1; i < M; ++i) {                                 // np.cumsum, :72
+            acc = add_rn(acc, c[i]);
+            c[i] = acc;
+        }
+        c[M - 1] = 1.0;                                                   // :73
+        const int64_t k = (int64_t)K[f];
+        SearchHint h;
+        h.lo = 0;
+        h.hi = M;
+        h.last = 0.0;
+        for (int64_t t = 0; t < M - k; ++t) {                             // :74
+            const double key = uniforms ? uniforms[base + t] : uniform53(philox_for(seed, base + t, step, kStreamResample, 1));
+            if (t == 0) h.last = key;
+            idx[base + k + t] = (int32_t)searchsorted_left_hinted(c, M, key, h);
+        }
+    }
+}
+
+// new[o] = old[idx[o]] (+ fused add_noise), for index arrays that are not sorted
+__global__ void __launch_bounds__(kThreads)
+k_gather_indices(const int32_t *__restrict__ idx, int64_t M, StateView src, StateView dst, NoiseParams rough,
+                 const float *rough_noise)
+{
+    const int f = blockIdx.y;
+    const int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (o >= M) return;
+    const int64_t base = (int64_t)f * M, orow = base + o, srow = base + idx[orow];
+    double x = src.x[srow], y = src.y[srow];
+    float z = src.z[srow], ro = src.roll[srow], pi = src.pitch[srow], ya = src.yaw[srow];
+    if (rough.mode == 1) {
+        float nn[6];
+        six_normals(rough, (int64_t)f * rough.global_stride + rough.global_offset + o, rough_noise, orow, nn);
+        x += (double)(rough.sigma[0] * nn[0]);
+        y += (double)(rough.sigma[1] * nn[1]);
+        z += rough.sigma[2] * nn[2];
+        ro += rough.sigma[3] * nn[3];
+        pi += rough.sigma[4] * nn[4];
+        ya += rough.sigma[5] * nn[5];
+    }
+    dst.x[orow] = x;
+    dst.y[orow] = y;
+    dst.z[orow] = z;
+    dst.roll[orow] = ro;
+    dst.pitch[orow] = pi;
+    dst.yaw[orow] = ya;
 }
 
 __global__ void __launch_bounds__(kThreads) k_load_records(const Record *__restrict__ rec, int64_t n, StateView dst)

@@ -73,21 +73,53 @@ AUVPF_HD U4 philox_for(uint64_t seed, int64_t id, uint32_t step, uint32_t stream
     return philox4x32_10(c, (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32));
 }
 
-// Box-Muller on two 32-bit words: u = (x + 0.5) 2^-32.
+// Box-Muller on two 32-bit words: u = (x + 0.5) 2^-32,
+//   n0 = sqrt(-2 ln u0) cos(2 pi u1),  n1 = sqrt(-2 ln u0) sin(2 pi u1).
+// Device: special-function-unit versions (the library logf / sincospif were 25 % of the gather
+// kernel's instructions).  -ln u0 is MUFU.LG2 except next to u0 = 1, where its ABSOLUTE error
+// would dominate the small result: there 1 - u0 is formed exactly from the complemented integer
+// and -ln(1 - t) is summed as a series.  The angle is shifted into [-pi, pi), where
+// __sinf / __cosf keep 2^-21 absolute accuracy, and the sign folded back.
 AUVPF_HD void box_muller(uint32_t a, uint32_t b, float &n0, float &n1)
 {
+#if defined(__CUDA_ARCH__)
+    const float u0 = ((float)a + 0.5f) * 2.3283064365386963e-10f;
+    const float t = ((float)(~a) + 0.5f) * 2.3283064365386963e-10f;          // 1 - u0
+    const float series = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.2f, 0.25f), 0.33333334f), 0.5f), 1.0f);
+    const float L = a >= 0xF8000000u ? series : -__logf(u0);                 // -ln u0 > 0
+    const float r = sqrtf(2.0f * L);
+    const float ang = ((float)b + 0.5f) * 1.4629180792671596e-9f - kPiF;     // 2 pi u1 - pi
+    float s, c;
+    __sincosf(ang, &s, &c);
+    n0 = -r * c;
+    n1 = -r * s;
+#else
     float u0 = ((float)a + 0.5f) * 2.3283064365386963e-10f;
     float u1 = ((float)b + 0.5f) * 2.3283064365386963e-10f;
     float r = sqrtf(-2.0f * logf(u0));
-    float s, c;
-#if defined(__CUDA_ARCH__)
-    sincospif(2.0f * u1, &s, &c);
-#else
-    s = sinf(2.0f * kPiF * u1);
-    c = cosf(2.0f * kPiF * u1);
+    n0 = r * cosf(2.0f * kPiF * u1);
+    n1 = r * sinf(2.0f * kPiF * u1);
 #endif
-    n0 = r * c;
-    n1 = r * s;
+}
+
+// The six standard normals of one add_noise (auv_particle.py:32-36) for particle `id`, in POSE
+// order [x, y, z, roll, pitch, yaw].  Contract: call 0 -> words (0,1): x, y; words (2,3): yaw, z;
+// call 1 -> words (0,1): roll, pitch.  x, y and yaw -- the only components the reference's
+// default covariances excite (auv_pf.launch:17-19) -- come from ONE Philox call; `need` (bit c =
+// component c has non-zero sigma) lets the caller skip what is multiplied by zero anyway.
+AUVPF_HD void pose_normals(uint64_t seed, int64_t id, uint32_t step, uint32_t stream, unsigned need, float n[6])
+{
+#pragma unroll
+    for (int c = 0; c < 6; ++c) n[c] = 0.f;
+    if (need & 0x27u) {                      // x, y, z or yaw
+        const U4 r0 = philox_for(seed, id, step, stream, 0);
+        if (need & 0x03u) box_muller(r0.x, r0.y, n[0], n[1]);
+        if (need & 0x24u) box_muller(r0.z, r0.w, n[5], n[2]);
+    }
+    if (need & 0x18u) {                      // roll, pitch
+        const U4 r1 = philox_for(seed, id, step, stream, 1);
+        box_muller(r1.x, r1.y, n[3], n[4]);
+    }
 }
 
 AUVPF_HD double uniform53(U4 r)

@@ -276,6 +276,31 @@ def golden_quantised_systematic(path):
     np.savez_compressed(path, **out)
 
 
+def golden_quantised_residual(path):
+    """residual_resample -- the resampler auv_pf.resample actually calls (auv_pf.py:182) -- on
+    weights that lie on the 2^-52 grid, with the ``random(N - k)`` draw of resampling.py:74
+    injected.  The GPU's AUVPF_RS_STRICT_REF mode must reproduce ``idx`` bit for bit."""
+    from oracle import pf_oracle
+    rng = np.random.default_rng(301)
+    out = {}
+    orig_random = resampling.random
+    try:
+        for name, N, scale in (("n100", 100, 2.0), ("n1000", 1000, 1.0), ("n4096", 4096, 4.0),
+                               ("n20000", 20000, 0.3)):
+            logw = (rng.normal(0, scale, N) - 470.0).astype(np.float32)
+            qq, a, A, m = pf_oracle.quantise_logw(logw)
+            w = pf_oracle.weights_from_q(qq)
+            U = rng.uniform(size=N)
+            resampling.random = lambda n_, U=U: U[:n_].copy()
+            out[name + "_logw"] = logw
+            out[name + "_qq"] = qq
+            out[name + "_U"] = U
+            out[name + "_idx"] = resampling.residual_resample(w.copy())
+    finally:
+        resampling.random = orig_random
+    np.savez_compressed(path, **out)
+
+
 def golden_auv_pf(path):
     """auv_pf.predict / update / resample / update_loc_pose, lifted class."""
     cls = lift_auv_pf()
@@ -361,6 +386,7 @@ if __name__ == "__main__":
     golden_particle(os.path.join(HERE, "particle.npz"))
     golden_resampling(os.path.join(HERE, "resampling.npz"))
     golden_quantised_systematic(os.path.join(HERE, "systematic_quantised.npz"))
+    golden_quantised_residual(os.path.join(HERE, "residual_quantised.npz"))
     golden_auv_pf(os.path.join(HERE, "auv_pf_cycle.npz"))
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):

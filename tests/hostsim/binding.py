@@ -21,6 +21,7 @@ def lib():
         _lib.hs_resample.restype = C.c_int
         _lib.hs_count_below.restype = C.c_long
         _lib.hs_wrap_pi.restype = C.c_float
+        _lib.hs_q_from_a.restype = C.c_uint64
     return _lib
 
 
@@ -95,6 +96,26 @@ def prof_reasons(reset=True):
     out = (C.c_long * 8)()
     lib().hs_prof_reasons(out, C.c_int(1 if reset else 0))
     return list(out)
+
+
+def residual(qq, U, strict=False):
+    qq = np.ascontiguousarray(qq, np.uint64)
+    U = np.ascontiguousarray(U, np.float64)
+    idx = np.zeros(len(qq), np.int32)
+    lib().hs_residual(_p(qq), C.c_long(len(qq)), _p(U), C.c_int(1 if strict else 0), _p(idx))
+    return idx
+
+
+def searchsorted(arr, keys):
+    arr = np.ascontiguousarray(arr, np.float64)
+    keys = np.ascontiguousarray(keys, np.float64)
+    out = np.zeros(len(keys), np.int64)
+    lib().hs_searchsorted(_p(arr), C.c_long(len(arr)), _p(keys), C.c_long(len(keys)), _p(out))
+    return out
+
+
+def q_from_a(a, A):
+    return int(lib().hs_q_from_a(C.c_uint64(a), C.c_uint64(A & 0xFFFFFFFFFFFFFFFF), C.c_uint64(A >> 64)))
 
 
 def count_below(u, N, c):

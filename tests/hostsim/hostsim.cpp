@@ -236,16 +236,10 @@ void hs_philox(const uint32_t *ctr, const uint32_t *key, long n, uint32_t *out)
     }
 }
 
-// the 6 normals of six_normals() for particle ids
+// the 6 normals of six_normals() for particle ids, pose order
 void hs_normals6(uint64_t seed, const int64_t *ids, long n, uint32_t step, uint32_t stream, float *out)
 {
-    for (long i = 0; i < n; ++i) {
-        U4 r0 = philox_for(seed, ids[i], step, stream, 0), r1 = philox_for(seed, ids[i], step, stream, 1);
-        float *o = out + 6 * i;
-        box_muller(r0.x, r0.y, o[0], o[1]);
-        box_muller(r0.z, r0.w, o[2], o[3]);
-        box_muller(r1.x, r1.y, o[4], o[5]);
-    }
+    for (long i = 0; i < n; ++i) pose_normals(seed, ids[i], step, stream, 0x3fu, out + 6 * i);
 }
 
 // fixed-point normalisation + systematic select, sequentially, with the device functions
@@ -289,6 +283,69 @@ int hs_resample(const float *logw, long M, double u, uint64_t *qq_out, int32_t *
     }
     return 0;
 }
+
+// residual_resample with the device functions, sequentially (mirrors k_scan_copies / k_scan_fracs /
+// k_residual_fill and, with strict != 0, k_residual_strict)
+int hs_residual(const uint64_t *qq, long M, const double *U, int strict, int32_t *idx)
+{
+    std::vector<uint64_t> copies(M), fracs(M);
+    uint64_t k = 0, R = 0;
+    for (long i = 0; i < M; ++i) {
+        const uint64_t c = residual_copies(qq[i], M);
+        k += c;
+        copies[i] = k;
+        R += residual_frac(qq[i], c, M);
+        fracs[i] = R;
+    }
+    auto first_above = [&](const std::vector<uint64_t> &c, uint64_t key) {
+        long lo = 0, hi = M;
+        while (lo < hi) {
+            long mid = (lo + hi) >> 1;
+            if (key < c[mid]) hi = mid;
+            else lo = mid + 1;
+        }
+        return lo;
+    };
+    for (long o = 0; o < (long)k && o < M; ++o) idx[o] = (int32_t)std::min<long>(first_above(copies, (uint64_t)o), M - 1);
+    if (!strict) {
+        for (long o = (long)k; o < M; ++o)
+            idx[o] = (int32_t)std::min<long>(first_above(fracs, residual_target(U[o - k], R)), M - 1);
+        return 0;
+    }
+    std::vector<double> c(M);
+    double s = 0.0;
+    for (long i = 0; i < M; ++i) {
+        c[i] = add_rn(cdf_value(qq[i]), -(double)residual_copies(qq[i], M));
+        s = add_rn(s, c[i]);
+    }
+    for (long i = 0; i < M; ++i) c[i] = div_rn(c[i], s);
+    double acc = c[0];
+    for (long i = 1; i < M; ++i) {
+        acc = add_rn(acc, c[i]);
+        c[i] = acc;
+    }
+    c[M - 1] = 1.0;
+    SearchHint h;
+    h.lo = 0;
+    h.hi = M;
+    h.last = 0.0;
+    for (long t = 0; t < M - (long)k; ++t) {
+        if (t == 0) h.last = U[t];
+        idx[k + t] = (int32_t)searchsorted_left_hinted(c.data(), M, U[t], h);
+    }
+    return 0;
+}
+
+void hs_searchsorted(const double *arr, long n, const double *keys, long nk, long *out)
+{
+    SearchHint h;
+    h.lo = 0;
+    h.hi = n;
+    h.last = nk ? keys[0] : 0.0;
+    for (long t = 0; t < nk; ++t) out[t] = (long)searchsorted_left_hinted(arr, n, keys[t], h);
+}
+
+uint64_t hs_q_from_a(uint64_t a, uint64_t A_lo, uint64_t A_hi) { return q_from_a(a, A_lo, A_hi); }
 
 void hs_prof_reasons(long *out, int reset)
 {

@@ -88,11 +88,11 @@ def test_philox_streams_match_spec():
     var = [4.0, 1.0, 0.25, 0.01, 0.04, 0.09]
     pf = _pf(particle_count=N, init_covariance=var, seed=seed, global_offset=1000, global_count=100000)
     ids = 1000 + np.arange(N, dtype=np.int64)
-    n = o.philox_normals(seed, 1, 0, ids, 2)[:, :6]                           # stream 1 = init, step 0
+    n = o.philox_pose_normals(seed, 1, 0, ids)                           # stream 1 = init, step 0
     np.testing.assert_allclose(pf.poses(), np.sqrt(var)[None, :] * n, rtol=1e-4, atol=2e-4)
     p0 = pf.poses()
     pf.roughen([1.0] * 6)                                                      # stream 3, step 0
-    n = o.philox_normals(seed, 3, 0, ids, 2)[:, :6]
+    n = o.philox_pose_normals(seed, 3, 0, ids)
     np.testing.assert_allclose(pf.poses() - p0, n, rtol=1e-4, atol=1e-4)
     pf.close()
     # predict: stream 2, normals 0,1 -> x,y ; 2 -> yaw
@@ -272,7 +272,7 @@ def test_uniform_weights_identity_and_roughening():
     anc = pf.resample(u=0.37, return_ancestors=True)                 # fused Philox roughening
     np.testing.assert_array_equal(anc, np.arange(N, dtype=np.int32))
     got = pf.poses()
-    n = o.philox_normals(5, 3, 0, np.arange(N, dtype=np.int64), 2)[:, :6]
+    n = o.philox_pose_normals(5, 3, 0, np.arange(N, dtype=np.int64))
     # fp32 Box-Muller: u0 -> 1 loses relative precision in r = sqrt(-2 ln u0); absolute error stays < 1e-4
     np.testing.assert_allclose(got[:, 0] - p0[:, 0], 0.5 * n[:, 0], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(got[:, 1], 0.5 * n[:, 1], rtol=1e-4, atol=1e-4)

@@ -186,7 +186,7 @@ def test_philox_and_normals():
     np.testing.assert_array_equal(hs.philox(ctr, key), o.philox4x32_10(ctr, key))
     ids = np.array([0, 1, 2, 12345, 2 ** 33 + 7], np.int64)
     got = hs.normals6(0xDEADBEEF12345678, ids, 9, 3)
-    want = o.philox_normals(0xDEADBEEF12345678, 3, 9, ids, 2)[:, :6]
+    want = o.philox_pose_normals(0xDEADBEEF12345678, 3, 9, ids)
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
     big = hs.normals6(42, np.arange(200000, dtype=np.int64), 0, 1)
     assert abs(big.mean()) < 5e-3 and abs(big.std() - 1) < 5e-3
@@ -210,6 +210,43 @@ def test_fixed_point_resample_is_bit_exact(N, scale):
     w = o.weights_from_q(qq)
     np.testing.assert_array_equal(anc, o.systematic_resample(w, u))
     np.testing.assert_array_equal(anc, c_oracle.systematic(w, u))
+
+
+def test_q_from_a_is_the_exact_floor():
+    """float64 estimate + 128-bit multiply-back == Python big-integer floor division."""
+    rng = np.random.default_rng(11)
+    cases = [(1, 1), (5, 5), (1, (1 << 84) + 12345), ((1 << 60), (1 << 60)), ((1 << 60), (1 << 84)),
+             ((1 << 60) - 1, (1 << 60) + 1), (3, 7), ((1 << 59) + 1, 3 * (1 << 59) + 2)]
+    for _ in range(3000):
+        abits = int(rng.integers(1, 61))
+        a = int(rng.integers(1, 1 << abits))
+        extra = int(rng.integers(0, 25))
+        A = a + int(rng.integers(0, 1 << min(abits + extra, 62))) * int(rng.integers(1, 1 << 20))
+        cases.append((a, max(A, a)))
+    for a, A in cases:
+        assert hs.q_from_a(a, A) == (a << 52) // A, (a, A)
+
+
+def test_hinted_searchsorted_is_numpys():
+    """np.searchsorted on NON-monotone arrays depends on its key-to-key hint; the device walk
+    must take the same steps (resampling.py:74 calls it on such an array)."""
+    rng = np.random.default_rng(12)
+    for n in (1, 2, 17, 1000):
+        for _ in range(20):
+            arr = np.cumsum(rng.normal(0.0, 1.0, n))          # not sorted
+            arr[-1] = 1.0
+            keys = rng.uniform(-0.5, 1.0, 200)
+            np.testing.assert_array_equal(hs.searchsorted(arr, keys), np.searchsorted(arr, keys))
+            ks = np.sort(keys)
+            np.testing.assert_array_equal(hs.searchsorted(arr, ks), np.searchsorted(arr, ks))
+
+
+def test_residual_resample_strict_and_fixed(golden):
+    g = golden("residual_quantised")
+    for n in ("n100", "n1000", "n4096", "n20000"):
+        qq, U = g[n + "_qq"], g[n + "_U"]
+        np.testing.assert_array_equal(hs.residual(qq, U, strict=True), g[n + "_idx"])     # the unmodified reference
+        np.testing.assert_array_equal(hs.residual(qq, U, strict=False), o.residual_resample_fixed(qq, U))
 
 
 def test_count_below_matches_positions():
