@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("AUVPF_LIB") or os.path.join(_HERE, "libauvpf.so")   #
 
 OK, ERR_BADARG, ERR_CUDA, ERR_STATE, ERR_DEGENERATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 SYSTEMATIC, RESIDUAL = 0, 1
-RS_SORTED, RS_INPLACE_REF = 0, 1
+RS_SORTED, RS_INPLACE_REF, RS_STRICT_REF = 0, 1, 2
 K_NAMES = ("propagate", "update_mbes", "update_gps", "normalise", "scan", "select_gather", "roughen",
            "estimate", "other")
 

@@ -454,7 +454,7 @@ int run_normalise(auvpf_handle *h, const WeightSrc &src)
     ns.tiles_total = (long long)h->tiles_per_filter * h->F;
     ns.a_out = h->cdf;
     Prof pr(h, AUVPF_K_NORMALISE);
-    int blocks = (int)std::min<int64_t>((h->M + kThreads * 4 - 1) / (kThreads * 4), 1184);
+    int blocks = (int)std::min<int64_t>((h->M + kThreads * 4 - 1) / (kThreads * 4), 740);   // one wave: 148 SMs x 5
     if (blocks < 1) blocks = 1;
     k_normalise<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, ns);
     LAUNCHED(h, AUVPF_K_NORMALISE, 1);
@@ -507,7 +507,6 @@ int apply_indices_dev(auvpf_handle *h, const int32_t *idx)
     k_reassign<<<g, kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->lost, h->dupes, h->totals2, h->totals2 + h->F);
     LAUNCHED(h, AUVPF_K_SELECT_GATHER, 6);
     CU(cudaGetLastError());
-    h->have_norm = false;   // cdf buffer was reused
     return AUVPF_OK;
 }
 
@@ -642,7 +641,7 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
         Prof pr(h, AUVPF_K_SELECT_GATHER);
         StateView dst = h->st[1 - h->cur];
         if (inplace) dst.x = nullptr;   // ancestors only
-        k_select_gather<false><<<grid1(h->M, kSelTile, h->F), kThreads, 0, h->stream>>>(
+        k_select_gather<false><<<grid1(h->M, kSelTile, h->F), kSelThreads, 0, h->stream>>>(
             h->cdf, sp, h->u, h->deficit, h->st[h->cur], dst, nullptr, anc_dev, nullptr, rough, rn, h->status,
             h->degenerate);
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
@@ -1352,7 +1351,7 @@ int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t defi
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
         StateView nodst{};
-        k_select_gather<true><<<grid1(n_out, kSelTile, 1), kThreads, 0, h->stream>>>(
+        k_select_gather<true><<<grid1(n_out, kSelTile, 1), kSelThreads, 0, h->stream>>>(
             h->cdf, sp, h->u, h->deficit, h->st[h->cur], nodst, rd, nullptr, ad, none, nullptr, h->status, nullptr);
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());

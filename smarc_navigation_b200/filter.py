@@ -62,14 +62,19 @@ class ParticleFilter(object):
     ``init_covariance``, ``motion_covariance``, ``resampling_noise_covariance``,
     ``measurement_std``, ``m2o_matrix`` (4x4 map<-odom, auv_pf.py:79-81).
     GPU-side additions: ``n_filters``, ``seed``, ``device``, ``range_min``,
-    ``range_max``, ``resampler`` ("systematic"), ``inplace_reference`` (keep the
-    reference's survivors-stay-in-slot map, auv_pf.py:183-198).
+    ``range_max``, ``resampler`` ("systematic", the north-star default, or
+    "residual", the one the reference calls, auv_pf.py:182), ``inplace_reference``
+    (keep the reference's survivors-stay-in-slot map, auv_pf.py:183-198),
+    ``strict_reference`` (residual only: reproduce resampling.py:70-74 literally,
+    particle_count <= 65536).  ``resampler="residual", inplace_reference=True,
+    strict_reference=True`` is the reference's ``resample()`` bit for bit.
     """
 
     def __init__(self, particle_count=10, init_covariance=(0.,) * 6, motion_covariance=(0.,) * 6,
                  resampling_noise_covariance=(0.,) * 6, measurement_std=0.01, m2o_matrix=None,
                  n_filters=1, seed=0, device=0, range_min=0.0, range_max=120.0, coarse_level=-1,
-                 resampler="systematic", inplace_reference=False, init_mean=None, init_noise=None,
+                 resampler="systematic", inplace_reference=False, strict_reference=False, init_mean=None,
+                 init_noise=None,
                  global_offset=0, global_count=0):
         self._lib = _lib.load()
         self.pc = int(particle_count)
@@ -81,6 +86,7 @@ class ParticleFilter(object):
         self.m2o_mat = np.identity(4) if m2o_matrix is None else np.asarray(m2o_matrix, np.float64).reshape(4, 4)
         self.resampler = {"systematic": _lib.SYSTEMATIC, "residual": _lib.RESIDUAL}[resampler]
         self.inplace_reference = bool(inplace_reference)
+        self.strict_reference = bool(strict_reference)
         self._lock = threading.Lock()      # the reference's callbacks race on self.particles
         self.time = None
         self.old_time = None
@@ -249,13 +255,23 @@ class ParticleFilter(object):
         ``resampling_noise_covariance`` noise to every particle (:191-192).
         ``weights=None`` uses the device-resident log-weights of the last update;
         a float64 array reproduces the reference call ``resample(weights)``.
-        ``u``: the ``random()`` of resampling.py:157 (one per filter), default Philox."""
+        ``u``: the ``random()`` of resampling.py:157 (one per filter) for the systematic
+        resampler, the ``random(N - k)`` array of :74 (``(F, M)``; the first ``M - k`` of a row
+        are consumed) for the residual one; default Philox."""
         anc = np.empty(self.n_rows, np.int32) if return_ancestors else None
-        uu = None if u is None else np.ascontiguousarray(np.broadcast_to(np.asarray(u, np.float64).reshape(-1),
-                                                                         (self.n_filters,)))
+        if u is None:
+            uu = None
+        elif self.resampler == _lib.RESIDUAL:
+            uu = np.zeros((self.n_filters, self.pc), np.float64)
+            ua = np.asarray(u, np.float64).reshape(self.n_filters, -1)
+            uu[:, :min(ua.shape[1], self.pc)] = ua[:, :self.pc]
+        else:
+            uu = np.ascontiguousarray(np.broadcast_to(np.asarray(u, np.float64).reshape(-1), (self.n_filters,)))
         rv = (C.c_double * 6)(*self.res_noise_cov) if roughen else None
         nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(self.n_rows, 6)
         flags = _lib.RS_INPLACE_REF if self.inplace_reference else _lib.RS_SORTED
+        if self.strict_reference and self.resampler == _lib.RESIDUAL:
+            flags |= _lib.RS_STRICT_REF
         with self._lock:
             if weights is None:
                 rc = self._lib.auvpf_resample(self._h, self.resampler, flags, _ptr(uu), _ptr(anc), rv, _ptr(nz))

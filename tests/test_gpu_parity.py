@@ -342,6 +342,59 @@ def test_inplace_mode_of_resample():
     pf.close()
 
 
+# --------------------------------------------------------------------------- a6 residual resample
+def test_residual_resample_strict_is_the_reference(golden):
+    """AUVPF_RESIDUAL + AUVPF_RS_STRICT_REF == the UNMODIFIED reference residual_resample
+    (resampling.py:27-76, the resampler auv_pf.resample calls) on the same quantised weights and
+    the same random(N - k) draw, bit for bit; with the in-place map it is auv_pf.resample()."""
+    g = golden("residual_quantised")
+    for n in ("n100", "n1000", "n4096", "n20000"):
+        logw, qq, U, idx = g[n + "_logw"], g[n + "_qq"], g[n + "_U"], g[n + "_idx"]
+        N = len(logw)
+        p = np.zeros((N, 6))
+        p[:, 0] = np.arange(N)
+        p[:, 1] = 0.5 * np.arange(N)
+        for inplace in (False, True):
+            pf = _pf(particle_count=N, resampler="residual", strict_reference=True, inplace_reference=inplace)
+            pf.set_poses(p)
+            pf.set_log_weights(logw)
+            anc = pf.resample(u=U, return_ancestors=True, roughen=False)
+            np.testing.assert_array_equal(pf.weights_q(), qq)
+            np.testing.assert_array_equal(anc, idx)
+            src = o.ancestor_map(idx, N) if inplace else idx
+            np.testing.assert_array_equal(pf.poses()[:, 0:2], p[src, 0:2])
+            pf.close()
+
+
+@pytest.mark.parametrize("N,scale", [(1, 1.0), (100, 2.0), (4097, 6.0), (65536, 1.0), (1 << 20, 3.0)])
+def test_residual_resample_default(N, scale):
+    """Default residual mode: deterministic floor(N w) copies == the reference's (:61-66), the
+    rest == the fixed-point multinomial of the oracle (residual_resample_fixed), bit for bit."""
+    rng = np.random.default_rng(1000 + N)
+    logw = (rng.normal(0, scale, N) - 30.0).astype(np.float32)
+    U = rng.uniform(size=N)
+    p = np.zeros((N, 6))
+    p[:, 0] = np.arange(N)
+    pf = _pf(particle_count=N, resampler="residual")
+    pf.set_poses(p)
+    pf.set_log_weights(logw)
+    anc = pf.resample(u=U, return_ancestors=True, roughen=False)
+    qq = pf.weights_q()
+    np.testing.assert_array_equal(qq, c_oracle.quantise_logw(logw)[0])
+    head, copies = o.residual_copies(o.weights_from_q(qq))
+    np.testing.assert_array_equal(anc[:len(head)], head)
+    np.testing.assert_array_equal(anc, o.residual_resample_fixed(qq, U))
+    np.testing.assert_array_equal(pf.poses()[:, 0], p[anc, 0])
+    # library-drawn uniforms (Philox): same head, tail only on particles with a fractional part
+    pf.set_poses(p)
+    pf.set_log_weights(logw)
+    anc2 = pf.resample(return_ancestors=True, roughen=False)
+    np.testing.assert_array_equal(anc2[:len(head)], head)
+    frac = N * o.weights_from_q(qq) - copies
+    assert np.all(frac[anc2[len(head):]] > 0)
+    pf.close()
+
+
 # --------------------------------------------------------------------------- a10 estimate
 def test_estimate_vs_reference_golden(golden):
     g = golden("auv_pf_cycle")

@@ -178,3 +178,24 @@ def test_philox_known_answers():
                      [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd],
                      [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]], np.uint32)
     np.testing.assert_array_equal(o.philox4x32_10(c, k), want)
+
+
+def test_residual_quantised_golden(golden):
+    """The literal residual_resample restatement against the unmodified reference run on
+    2^-52-grid weights with the random(N - k) draw injected; the fixed-point variant keeps the
+    reference's deterministic head and draws the tail only from particles with a fractional part."""
+    g = golden("residual_quantised")
+    for n in ("n100", "n1000", "n4096", "n20000"):
+        qq, U, idx = g[n + "_qq"], g[n + "_U"], g[n + "_idx"]
+        w = o.weights_from_q(qq)
+        np.testing.assert_array_equal(o.quantise_logw(g[n + "_logw"])[0], qq)
+        np.testing.assert_array_equal(o.residual_resample(w, U), idx)
+        head, copies = o.residual_copies(w)
+        fx = o.residual_resample_fixed(qq, U)
+        np.testing.assert_array_equal(fx[:len(head)], idx[:len(head)])
+        frac = len(w) * w - copies
+        assert np.all(frac[fx[len(head):]] > 0)
+        # the tail follows the fractional parts: chi-square-free sanity on the mean index weight
+        if len(w) - len(head) > 200:
+            pr = frac / frac.sum()
+            assert abs(pr[fx[len(head):]].mean() - (pr * pr).sum()) < 5.0 * np.sqrt((pr ** 3).sum() / (len(w) - len(head)))
