@@ -313,10 +313,15 @@ AUVPF_HD float rcp_rn(float x)
 #endif
 }
 
+// a / b where 2^-23 relative accuracy is enough (profile slopes and segment lengths; the results
+// that must be exact are re-derived in float64).  Device: ONE MUFU.RCP and a multiply --
+// __fdividef's range fix-ups were 11 % of the profile kernel's instructions.
 AUVPF_HD float fast_div(float a, float b)
 {
 #if defined(__CUDA_ARCH__)
-    return __fdividef(a, b);
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+    return a * r;
 #else
     return a / b;
 #endif
@@ -768,9 +773,12 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     // per-side state
     int side = T.n1 > 0 ? 0 : 1;
     int n_side = side == 0 ? T.n1 : T.B - T.n1;
-    int beam0 = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;
+    int bb = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;   // current beam, next one outward
     float sgf = (float)(side == 0 ? T.sgn1 : -T.sgn1);
     int j = 0;
+    double tn = 0.0;                       // the current beam's tan, 1 / cos and lateral reach
+    float sec_f = 1.f, reach = 0.f;
+    float q_f = (float)S.q0;               // float32 copy of q_cur
     int cx = S.cx, cy = S.cy;
     float u = S.u, v = S.v;
     bool lower = u >= v;
@@ -786,6 +794,9 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         z01 = ldg_f(zp + 1);
         z10 = ldg_f(zp + m.pitch);
         z11 = ldg_f(zp + m.pitch + 1);
+        tn = T.tan_t[bb];
+        sec_f = (float)T.sec_t[bb];
+        reach = T.sin_t[bb] * m.range_max;
     }
     for (int step = 0; step < max_steps; ++step) {
         if (!AUVPF_WARP_ANY(running)) break;
@@ -826,36 +837,48 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
             // A beam is resolved here when it hits inside the segment, or when the segment's end is
             // beyond what the beam can reach within range_max (miss).
+            // The current beam's constants (tan, reach = |sin| range_max, sec) live in registers and
+            // are reloaded only when the beam changes, ahead of their use.
             while (j < n_side) {
-                const int bb = beam0 + j * bstep;
-                const double tn = T.tan_t[bb];
                 const float gap = (float)(q_cur * tn - p_cur);
                 const float den = fmaf(-s, (float)tn, 1.0f);
                 const bool hit = gap <= dp * den;
-                if (!(hit || p_out_f > T.sin_t[bb] * m.range_max)) break;
+                if (!(hit || p_out_f > reach)) break;
                 float range = m.range_max;
                 if (hit) {
+                    // range = (q at the hit) / cos th.  float32 from the float32 copy of q_cur: three
+                    // roundings at <= 120 m, < 2e-5 m (tolerance 1e-4 m); grazing hits go the float64 way
                     const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
-                    double qh = q_cur + (double)(s * dph);
+                    float t = fmaf(s, dph, q_f) * sec_f;
                     if (den < kDenPrecise)
-                        qh = precise_hit(D, (double)sgf, cx, cy, (double)z00,
-                                         (double)(lower ? z01 : z11) - (double)(lower ? z00 : z10),
-                                         (double)(lower ? z11 : z10) - (double)(lower ? z01 : z00), tn);
-                    const float t = (float)(qh * T.sec_t[bb]);
+                        t = (float)(precise_hit(D, (double)sgf, cx, cy, (double)z00,
+                                                (double)(lower ? z01 : z11) - (double)(lower ? z00 : z10),
+                                                (double)(lower ? z11 : z10) - (double)(lower ? z01 : z00), tn) *
+                                    T.sec_t[bb]);
                     range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
                 }
-                sink(bb, range);
+                const int b_done = bb;
                 ++j;
+                bb += bstep;
+                if (j < n_side) {                                  // next beam's constants, in flight during the sink
+                    tn = T.tan_t[bb];
+                    sec_f = (float)T.sec_t[bb];
+                    reach = T.sin_t[bb] * m.range_max;
+                }
+                sink(b_done, range);
             }
             if (j >= n_side) {
                 // this side is done: start the other one from the anchor, or finish
                 if (side == 0 && T.B - T.n1 > 0) {
                     side = 1;
                     n_side = T.B - T.n1;
-                    beam0 = T.n1;
+                    bb = T.n1;
                     bstep = 1;
                     sgf = -sgf;
                     j = 0;
+                    tn = T.tan_t[bb];
+                    sec_f = (float)T.sec_t[bb];
+                    reach = T.sin_t[bb] * m.range_max;
                     cx = S.cx;
                     cy = S.cy;
                     u = S.u;
@@ -864,6 +887,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     entry = -1;
                     p_cur = 0.0;
                     q_cur = S.q0;
+                    q_f = (float)S.q0;
                     const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
                     z00 = ldg_f(zp);
                     z01 = ldg_f(zp + 1);
@@ -876,6 +900,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             // advance to the exit point and step into the neighbour across that edge (selects, not
             // branches: lanes leaving through different edges stay converged)
             q_cur += (double)(s * dp);
+            q_f = (float)q_cur;
             p_cur = p_out;
             u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
             v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
@@ -890,7 +915,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 cy += vedge ? dir : 0;
                 u = diag ? mid : (uedge ? nc : u);
                 v = diag ? mid : (vedge ? nc : v);
-                if (cx < 0 || cy < 0 || cx > m.W - 2 || cy > m.H - 2) {   // left the map
+                if ((unsigned)cx > (unsigned)(m.W - 2) || (unsigned)cy > (unsigned)(m.H - 2)) {   // left the map
                     AUVPF_REASON(2);
                     ok = false;
                     running = false;
