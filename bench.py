@@ -35,6 +35,7 @@ from smarc_navigation_b200 import world  # noqa: E402
 METRIC = "particle_beam_evals_per_s"
 UNIT = "evals/s"
 P_PREDICTS = 5
+RS_BYTES = 96        # algorithmic HBM bytes per particle of normalise + scan + select + gather
 
 
 def parse():
@@ -43,7 +44,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4", "C5"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work per reference step / baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -58,6 +59,8 @@ def workload(args, n_gpus):
         per_gpu = c["particles"] // 8
     else:
         per_gpu = c["particles"]
+    # C5: 256 independent filters over 8 GPUs = 32 whole filters per GPU, no cross-GPU traffic
+    c["filters_per_gpu"] = c.get("filters", 8) // 8 if name == "C5" else 1
     c["name"] = name
     c["per_gpu"] = per_gpu
     c["total"] = per_gpu * n_gpus
@@ -203,22 +206,30 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     G = world_size
     cfg = workload(args, G)
-    M, B = cfg["per_gpu"], cfg["beams"]
+    M, B, F = cfg["per_gpu"], cfg["beams"], cfg["filters_per_gpu"]
     K, W = args.steps, max(args.warmup, 3)
     P = world.MBES_PARAMS
     ext = cfg["dem_n"] * cfg["res"]
     dem = world.make_dem(cfg["dem_n"], cfg["res"])
     beams = world.make_beams(B)
-    traj = world.Trajectory(ext)
+    # one trajectory per filter (C5: offset starts, own odometry noise seed)
+    trajs = [world.Trajectory(ext, seed=2 + (rank * F + f if F > 1 else 0),
+                              offset=(12.0 * ((rank * F + f) % 16), 12.0 * ((rank * F + f) // 16)) if F > 1 else (0.0, 0.0))
+             for f in range(F)]
+    traj = trajs[0]
 
     from smarc_navigation_b200 import ParticleFilter
     common = dict(init_covariance=P["init_covariance"], motion_covariance=P["motion_covariance"],
                   resampling_noise_covariance=P["resampling_noise_covariance"],
                   measurement_std=P["measurement_std"], range_min=world.RANGE_MIN, range_max=world.RANGE_MAX,
                   init_mean=traj.truth, seed=4, coarse_level=int(os.environ.get("AUVPF_COARSE_LEVEL", "-1"), 0))
-    if G == 1:
-        pf = ParticleFilter(particle_count=M, device=local_rank, **common)
+    if G == 1 or F > 1:
+        pf = ParticleFilter(particle_count=M, n_filters=F, device=local_rank, **common)
         filt = pf
+        if F > 1:      # every filter starts around its own vehicle
+            rng0 = np.random.default_rng(4 + rank)
+            p0 = np.concatenate([t.truth[None, :] + rng0.normal(size=(M, 6)) * np.sqrt(P["init_covariance"]) for t in trajs])
+            pf.set_poses(p0)
     else:
         from smarc_navigation_b200.sharded import ShardedParticleFilter
         filt = ShardedParticleFilter(M, dist, device=local_rank, **common)
@@ -230,9 +241,12 @@ def run_ours(args):
     n_steps = 2 * (K + W) + 2
     cycles = []
     for s in range(n_steps):
-        odoms, truth = traj.cycle()
-        r_true = pf.raycast(truth[None, :])[0]
-        cycles.append((odoms, (r_true + world.ping_noise(B, s)).astype(np.float32), truth))
+        per = [t.cycle() for t in trajs]
+        truth = np.stack([c[1] for c in per])                                    # (F, 6)
+        r_true = pf.raycast(truth)                                               # (F, B)
+        noise = np.stack([world.ping_noise(B, s, seed=3 + 7 * f) for f in range(F)]) if F > 1 else world.ping_noise(B, s)[None]
+        odoms = [per[0][0][p] if F == 1 else [per[f][0][p] for f in range(F)] for p in range(P_PREDICTS)]
+        cycles.append((odoms, (r_true + noise).astype(np.float32).reshape(F * B), truth[0], truth))
     pings_dev = torch.from_numpy(np.stack([c[1] for c in cycles])).cuda()
     pings_pin = torch.from_numpy(np.stack([c[1] for c in cycles])).pin_memory()
     stream = torch.cuda.ExternalStream(pf.stream_ptr)
@@ -284,17 +298,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / K
-    value = M * G * B / (ms_per_step * 1e-3)
+    value = M * F * G * B / (ms_per_step * 1e-3)
     mean, cov = filt.mean_cov()
-    mean = np.asarray(mean).reshape(-1)
-    track_err = float(np.hypot(mean[0] - cycles[W + K - 1][2][0], mean[1] - cycles[W + K - 1][2][1]))
+    mean = np.asarray(mean).reshape(-1, 6) if F > 1 else np.asarray(mean).reshape(1, -1)
+    tr = cycles[W + K - 1][3]
+    track_err = float(np.max(np.hypot(mean[:, 0] - tr[:len(mean), 0], mean[:, 1] - tr[:len(mean), 1])))
 
     # ---- end to end through the public API, host buffers ----------------------------------------
     base = W + K
     for s in range(base, base + W):
         for od in cycles[s][0]:
             filt.predict(od)
-        filt.update_mbes(pings_pin[s].numpy()) if G > 1 else pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
+        filt.update_mbes(pings_pin[s].numpy()) if (G > 1 and F == 1) else pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
         filt.resample()
         filt.mean_cov()
     barrier()
@@ -302,7 +317,7 @@ def run_ours(args):
     for s in range(base + W, base + W + K):
         for od in cycles[s][0]:
             filt.predict(od)
-        if G > 1:
+        if G > 1 and F == 1:
             filt.update_mbes(pings_pin[s].numpy())
         else:
             pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
@@ -314,32 +329,33 @@ def run_ours(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = M * G * B * K / e2e_s
-    h2d = B * 4 + P_PREDICTS * 0 + 8            # ping ranges + the resample uniform (odometry travels as kernel arguments)
-    d2h = 16 * 8 + 4                            # pose sums/moments + the degenerate-weights flag
+    e2e_value = M * F * G * B * K / e2e_s
+    h2d = F * (B * 4 + 8) + (P_PREDICTS * F * 40 if F > 1 else 0)   # ping ranges + resample uniforms (+ per-filter odometry rows)
+    d2h = F * (16 * 8 + 4)                      # pose sums/moments + the degenerate-weights flag
 
     # ---- roofline of the dominant kernel + the HBM-bound resample path ----------------------------
     peak, peak_src = peaks()
     dem_bytes = dem["z"].size * 4
     mbes_ms, mbes_n = prof["update_mbes"]
     mbes_n = K                                               # per update (profile-merge kernel + per-ray kernel for flagged particles)
-    alg_mbes = M * (32 + 4) + dem_bytes + 16 * B            # state read + logw write, DEM once, beam table
+    alg_mbes = M * F * (32 + 4) + dem_bytes + 16 * B        # state read + logw write, DEM once, beam table
     ach = alg_mbes / (mbes_ms / max(mbes_n, 1) * 1e-3) / 1e9 if mbes_n else 0.0
     rs_ms = prof["normalise"][0] + prof["scan"][0] + prof["select_gather"][0]
     rs_n = max(prof["scan"][1], 1)
-    alg_rs = M * (4 + 4 + 12 + 12 + 4 + 32 + 32)            # max, sum, scan r/w, select r/w, gather r/w
+    alg_rs = M * F * RS_BYTES                                   # normalise 4 + scan 12 + select 12 + gather 4+32+32
     ach_rs = alg_rs / (rs_ms / rs_n * 1e-3) / 1e9 if rs_ms > 0 else 0.0
     prop_ms, prop_n = prof["propagate"]
-    ach_prop = M * 52 / (prop_ms / max(prop_n, 1) * 1e-3) / 1e9 if prop_n else 0.0
+    ach_prop = M * F * 52 / (prop_ms / max(prop_n, 1) * 1e-3) / 1e9 if prop_n else 0.0
     launches = int(sum(v[1] for v in prof.values()))
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %d particles/GPU x %d beams (%d total), %.1f m DEM %dx%d, %d predicts per cycle" % (
-            cfg["name"], M, B, M * G, cfg["res"], cfg["dem_n"], cfg["dem_n"], P_PREDICTS),
-            "parallelism": "particle-sharded x%d" % G, "l2": "flushed between steps (256 MiB memset)",
+        "config": {"workload": "%s: %s%d particles/GPU x %d beams (%d total), %.1f m DEM %dx%d, %d predicts per cycle" % (
+            cfg["name"], ("%d filters x " % F) if F > 1 else "", M, B, M * F * G, cfg["res"], cfg["dem_n"], cfg["dem_n"],
+            P_PREDICTS),
+            "parallelism": ("filter-sharded x%d (%d filters/GPU, no communication)" % (G, F)) if F > 1 else "particle-sharded x%d" % G, "l2": "flushed between steps (256 MiB memset)",
             "resampler": "systematic", "cycle_hz": 1e3 / ms_per_step},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -348,12 +364,12 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "k_update_mbes_profile (+ k_update_mbes for flagged particles): fused raycast + beam likelihood",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                      "peak_source": peak_src, "ms_per_launch": mbes_ms / max(mbes_n, 1),
-                     "evals_per_s": M * B / (mbes_ms / max(mbes_n, 1) * 1e-3) if mbes_n else None,
+                     "evals_per_s": M * F * B / (mbes_ms / max(mbes_n, 1) * 1e-3) if mbes_n else None,
                      "note": "dominant kernel is issue/latency-bound on an L1/L2-resident DEM footprint, not "
                              "HBM-bound (SURVEY 8d); the HBM-bound path is roofline_resample"},
-        "roofline_resample": {"bound": "hbm", "kernel": "normalise + k_scan_q + k_select_gather",
+        "roofline_resample": {"bound": "hbm", "kernel": "k_normalise + k_scan_q_from_a + k_select_gather",
                               "achieved": ach_rs, "peak": peak, "unit": "GB/s", "frac": ach_rs / peak,
-                              "ms_per_cycle": rs_ms / rs_n, "bytes_per_particle": 100},
+                              "ms_per_cycle": rs_ms / rs_n, "bytes_per_particle": RS_BYTES},
         "roofline_propagate": {"bound": "hbm", "achieved": ach_prop, "peak": peak, "unit": "GB/s",
                                "frac": ach_prop / peak, "ms_per_launch": prop_ms / max(prop_n, 1)},
         "kernel_ms_per_cycle": {k: v[0] / K for k, v in prof.items() if v[1]},

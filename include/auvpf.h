@@ -184,6 +184,16 @@ int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *limbs_out)
 /* stage 3: given global max and global A (F,2: lo64, hi64), quantise and scan
  * locally; returns the local total Q (F). */
 int auvpf_shard_scan(auvpf_handle *h, const float *m_global, const uint64_t *A_global, uint64_t *Q_out);
+/* Device-resident variant of stages 1-3 (no host round trip per scalar): the library
+ * exposes its per-filter device scalars -- max log-weight as ORDER-PRESERVING int32 (so an
+ * integer MAX all-reduce is the float max), the two uint64 limbs of A, the local CDF total Q --
+ * and the caller reduces / gathers them in place between the calls, ordered on the handle's
+ * stream:  max_dev; all-reduce MAX(wmax_i32);  sum_dev; all-reduce SUM(limbs);  scan_dev;
+ * all-gather(Q). */
+int auvpf_shard_buffers(auvpf_handle *h, void **wmax_i32, void **limbs_u64, void **q_u64);
+int auvpf_shard_max_dev(auvpf_handle *h);
+int auvpf_shard_sum_dev(auvpf_handle *h);
+int auvpf_shard_scan_dev(auvpf_handle *h);
 /* stage 4: emit the n_out = out_hi - out_lo offspring whose ancestors live in
  * this shard: global output slots [out_lo, out_hi) as 32-byte records
  * {double x, y; float z, roll, pitch, yaw} into `records` (device or host) and,
@@ -193,6 +203,9 @@ int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t defi
                      int64_t out_hi, void *records, int64_t *ancestors_out);
 /* stage 5: replace the local state by M records received from the exchange */
 int auvpf_shard_load(auvpf_handle *h, const void *records, int64_t n);
+/* same, with the post-resample add_noise (auv_pf.py:191-192) fused into the load */
+int auvpf_shard_load_roughen(auvpf_handle *h, const void *records, int64_t n, const double *rough_var,
+                             const float *rough_noise);
 
 /* -- measurement support ----------------------------------------------------- */
 int auvpf_profile_enable(auvpf_handle *h, int32_t on);

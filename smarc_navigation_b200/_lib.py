@@ -67,8 +67,13 @@ SYMBOLS = [
     ("auvpf_shard_max", C.c_int, [_vp, _vp]),
     ("auvpf_shard_sum", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_shard_scan", C.c_int, [_vp, _vp, _vp, _vp]),
+    ("auvpf_shard_buffers", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
+    ("auvpf_shard_max_dev", C.c_int, [_vp]),
+    ("auvpf_shard_sum_dev", C.c_int, [_vp]),
+    ("auvpf_shard_scan_dev", C.c_int, [_vp]),
     ("auvpf_shard_emit", C.c_int, [_vp, _dbl, _u64, _u64, _i64, _i64, _vp, _vp]),
     ("auvpf_shard_load", C.c_int, [_vp, _vp, _i64]),
+    ("auvpf_shard_load_roughen", C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     ("auvpf_profile_enable", C.c_int, [_vp, _i32]),
     ("auvpf_profile_read", C.c_int, [_vp, _vp, _vp, _i32]),
 ]

@@ -425,19 +425,25 @@ int run_scan(auvpf_handle *h, const WeightSrc &src, bool fused = false)
 }
 
 // Single-GPU normalisation: max (from the update kernel when it is current) + exact sum + A.
-int run_normalise(auvpf_handle *h, const WeightSrc &src)
+int ensure_wmax_f32(auvpf_handle *h)
+{
+    if (h->wmax_valid) return AUVPF_OK;
+    Prof pr(h, AUVPF_K_NORMALISE);
+    CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * h->F, h->stream));
+    int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
+    k_weight_max_f32<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->logw, h->M, h->wmax_f32);
+    LAUNCHED(h, AUVPF_K_NORMALISE, 1);
+    CU(cudaGetLastError());
+    h->wmax_valid = true;
+    return AUVPF_OK;
+}
+
+int run_normalise(auvpf_handle *h, const WeightSrc &src, bool finalise = true)
 {
     int rc;
     NormState ns{};
     if (src.kind == 0) {
-        if (!h->wmax_valid) {
-            Prof pr(h, AUVPF_K_NORMALISE);
-            CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * h->F, h->stream));
-            int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
-            k_weight_max_f32<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->logw, h->M, h->wmax_f32);
-            LAUNCHED(h, AUVPF_K_NORMALISE, 1);
-            h->wmax_valid = true;
-        }
+        if ((rc = ensure_wmax_f32(h))) return rc;
         ns.wmax_f32 = h->wmax_f32;
     } else {
         if ((rc = run_max(h, src))) return rc;      // float64 linear weights: separate max pass
@@ -453,6 +459,7 @@ int run_normalise(auvpf_handle *h, const WeightSrc &src)
     ns.tile_counter = h->tile_counter;
     ns.tiles_total = (long long)h->tiles_per_filter * h->F;
     ns.a_out = h->cdf;
+    ns.finalise = finalise ? 1 : 0;
     Prof pr(h, AUVPF_K_NORMALISE);
     int blocks = (int)std::min<int64_t>((h->M + kThreads * 4 - 1) / (kThreads * 4), 740);   // one wave: 148 SMs x 5
     if (blocks < 1) blocks = 1;
@@ -1321,6 +1328,49 @@ int auvpf_shard_scan(auvpf_handle *h, const float *m_global, const uint64_t *A_g
     return AUVPF_OK;
 }
 
+// Device-resident variant of stages 1-3: the three scalars never visit the host.  The caller
+// all-reduces / all-gathers them IN PLACE on the device between the calls, ordered on the
+// handle's stream (torch.cuda.ExternalStream + torch.distributed, sharded.py).
+int auvpf_shard_buffers(auvpf_handle *h, void **wmax_i32, void **limbs_u64, void **q_u64)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    if (wmax_i32) *wmax_i32 = h->wmax_f32;
+    if (limbs_u64) *limbs_u64 = h->limbs;
+    if (q_u64) *q_u64 = h->Q;
+    return AUVPF_OK;
+}
+
+int auvpf_shard_max_dev(auvpf_handle *h)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    return ensure_wmax_f32(h);
+}
+
+int auvpf_shard_sum_dev(auvpf_handle *h)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    WeightSrc src{h->logw, nullptr, 0};
+    h->wmax_valid = true;       // the buffer now holds the GLOBAL maximum
+    return run_normalise(h, src, /*finalise=*/false);
+}
+
+int auvpf_shard_scan_dev(auvpf_handle *h)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    k_shard_finish_sum<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->limbs, h->A, h->wmax, h->degenerate, h->sumsq,
+                                                                  h->F);
+    LAUNCHED(h, AUVPF_K_NORMALISE, 1);
+    WeightSrc src{h->logw, nullptr, 0};
+    int rc = run_scan(h, src, /*fused=*/true);
+    h->have_norm = true;
+    h->last_src_kind = 0;
+    h->wmax_valid = false;      // the maximum in the buffer is not this shard's: recompute next time unless an update refreshes it
+    return rc;
+}
+
 int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t deficit, int64_t out_lo, int64_t out_hi,
                      void *records, int64_t *ancestors_out)
 {
@@ -1361,7 +1411,8 @@ int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t defi
     return AUVPF_OK;
 }
 
-int auvpf_shard_load(auvpf_handle *h, const void *records, int64_t n)
+int auvpf_shard_load_roughen(auvpf_handle *h, const void *records, int64_t n, const double *rough_var,
+                             const float *rough_noise)
 {
     if (!h || !records) return fail(AUVPF_ERR_BADARG, "null argument");
     if (n != h->N) return fail(AUVPF_ERR_BADARG, "expected %lld records, got %lld", (long long)h->N, (long long)n);
@@ -1369,11 +1420,23 @@ int auvpf_shard_load(auvpf_handle *h, const void *records, int64_t n)
     const Record *rd = nullptr;
     int rc = stage_in(h, S_IN0, static_cast<const Record *>(records), (size_t)n, &rd);
     if (rc) return rc;
-    k_load_records<<<grid1(n, kThreads, 1), kThreads, 0, h->stream>>>(rd, n, h->st[1 - h->cur]);
-    LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
-    CU(cudaGetLastError());
+    const float *rn = nullptr;
+    if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
+    NoiseParams rough = make_noise(h, rough_var, nullptr, rough_var ? 1 : 0, h->step_rough, kStreamRoughen);
+    {
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        k_load_records<<<grid1(n, kThreads, 1), kThreads, 0, h->stream>>>(rd, n, h->st[1 - h->cur], rough, rn);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+        CU(cudaGetLastError());
+    }
     h->cur = 1 - h->cur;
+    if (rough_var) h->step_rough++;
     return AUVPF_OK;
+}
+
+int auvpf_shard_load(auvpf_handle *h, const void *records, int64_t n)
+{
+    return auvpf_shard_load_roughen(h, records, n, nullptr, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

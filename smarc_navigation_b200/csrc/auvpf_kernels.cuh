@@ -679,6 +679,7 @@ struct NormState {
     unsigned int *tile_counter;     // zeroed
     long long tiles_total;
     unsigned long long *a_out;      // [F*M] a_i, kept for the scan (which overwrites it in place with the CDF)
+    int finalise;                   // 0: particle-sharded filter -- leave the limbs for the cross-GPU sum
 };
 
 __global__ void __launch_bounds__(kThreads) k_normalise(WeightSrc w, int64_t M, NormState ns)
@@ -734,6 +735,10 @@ __global__ void __launch_bounds__(kThreads) k_normalise(WeightSrc w, int64_t M, 
         }
         if (lo) atomicAdd(ns.limbs + 2 * f, lo);
         if (hi) atomicAdd(ns.limbs + 2 * f + 1, hi);
+        if (!ns.finalise) {
+            if (blockIdx.x == 0) ns.wmax[f] = m;
+            return;
+        }
         __threadfence();
         const unsigned int ticket = atomicAdd(ns.done + f, 1u);
         if (ticket == gridDim.x - 1) {
@@ -748,6 +753,22 @@ __global__ void __launch_bounds__(kThreads) k_normalise(WeightSrc w, int64_t M, 
             ns.done[f] = 0u;
         }
     }
+}
+
+// Particle-sharded filter: after the cross-GPU all-reduce of the limbs, fold them into A and set
+// the degenerate flag (the single-GPU path does this in k_normalise's last block).
+__global__ void k_shard_finish_sum(unsigned long long *limbs, unsigned long long *A, const double *wmax,
+                                   int *degenerate, double *sumsq, int F)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const unsigned __int128 a = (unsigned __int128)limbs[2 * f] + ((unsigned __int128)limbs[2 * f + 1] << 32);
+    A[2 * f] = (unsigned long long)a;
+    A[2 * f + 1] = (unsigned long long)(a >> 64);
+    limbs[2 * f] = 0ull;
+    limbs[2 * f + 1] = 0ull;
+    degenerate[f] = (!isfinite(wmax[f]) || a == 0) ? 1 : 0;
+    sumsq[f] = 0.0;
 }
 
 // float32 log-weights that did not come from an update kernel (auvpf_set_logw): max pass
@@ -1311,11 +1332,22 @@ k_gather_indices(const int32_t *__restrict__ idx, int64_t M, StateView src, Stat
     dst.yaw[orow] = ya;
 }
 
-__global__ void __launch_bounds__(kThreads) k_load_records(const Record *__restrict__ rec, int64_t n, StateView dst)
+__global__ void __launch_bounds__(kThreads)
+k_load_records(const Record *__restrict__ rec, int64_t n, StateView dst, NoiseParams rough, const float *rough_noise)
 {
     int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     Record r = rec[i];
+    if (rough.mode == 1) {       // fused add_noise (auv_pf.py:191-192); single filter: global id = offset + i
+        float nn[6];
+        six_normals(rough, rough.global_offset + i, rough_noise, i, nn);
+        r.x += (double)(rough.sigma[0] * nn[0]);
+        r.y += (double)(rough.sigma[1] * nn[1]);
+        r.z += rough.sigma[2] * nn[2];
+        r.roll += rough.sigma[3] * nn[3];
+        r.pitch += rough.sigma[4] * nn[4];
+        r.yaw += rough.sigma[5] * nn[5];
+    }
     dst.x[i] = r.x;
     dst.y[i] = r.y;
     dst.z[i] = r.z;

@@ -112,6 +112,45 @@ def resample_sharded(ops, dist, u, group=None):
     return dict(m=m, A=A, Q_all=Q_all, D=D, bounds=bounds, send=send_counts, recv=recv_counts)
 
 
+class _DeviceArray(object):
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def resample_sharded_device(ops, dist, u, group=None, rough_var=None):
+    """The same resample with the three cross-GPU scalars kept ON THE DEVICE: the collectives run
+    in place on the library's own buffers, ordered on the library's stream, and the only host
+    read-back is the list of per-shard CDF totals that sizes the exchange."""
+    import torch
+    rank, G = dist.get_rank(group), dist.get_world_size(group)
+    M = ops.M
+    L, h = ops.L, ops.pf._h
+    with torch.cuda.stream(ops.stream):
+        ops._lib.check(L.auvpf_shard_max_dev(h))
+        dist.all_reduce(ops.t_wmax, op=dist.ReduceOp.MAX, group=group)          # order-preserving int32 == float max
+        ops._lib.check(L.auvpf_shard_sum_dev(h))
+        dist.all_reduce(ops.t_limbs, op=dist.ReduceOp.SUM, group=group)         # exact integer limbs of A
+        ops._lib.check(L.auvpf_shard_scan_dev(h))
+        dist.all_gather_into_tensor(ops.t_qall, ops.t_q, group=group)
+        Q_all = [int(q) for q in ops.t_qall.tolist()]                           # the one host synchronisation
+        if sum(Q_all) == 0:
+            raise FloatingPointError("degenerate weights on every shard")
+        D, q_offsets, bounds = plan_exchange(Q_all, M, u)
+        send_counts, recv_counts = splits_for(bounds, M, rank)
+        n_out = bounds[rank + 1] - bounds[rank]
+        send = ops.send_records(n_out)
+        ops._lib.check(L.auvpf_shard_emit(h, u, q_offsets[rank], D, bounds[rank], bounds[rank + 1],
+                                          C.c_void_p(send.data_ptr()) if n_out > 0 else None, None))
+        assert sum(recv_counts) == M and sum(send_counts) == n_out
+        dist.all_to_all_single(ops.recv_buf, send, output_split_sizes=recv_counts, input_split_sizes=send_counts,
+                               group=group)
+        rv = None if rough_var is None else (C.c_double * 6)(*rough_var)
+        ops._lib.check(L.auvpf_shard_load_roughen(h, C.c_void_p(ops.recv_buf.data_ptr()), M, rv, None))
+    return dict(Q_all=Q_all, D=D, bounds=bounds, send=send_counts, recv=recv_counts)
+
+
 class GpuShardOps(object):
     """Per-shard stages on the GPU through the C ABI (auvpf_shard_*)."""
 
@@ -124,6 +163,30 @@ class GpuShardOps(object):
         self.M = pf.pc
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.torch = torch
+        # device-resident flow: torch views of the library's scalars + persistent exchange buffers
+        self.stream = torch.cuda.ExternalStream(pf.stream_ptr, device=self.device)
+        pw, pl, pq = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(self.L.auvpf_shard_buffers(pf._h, C.byref(pw), C.byref(pl), C.byref(pq)))
+        self.t_wmax = torch.as_tensor(_DeviceArray(pw.value, (1,), "<i4"), device=self.device)
+        self.t_limbs = torch.as_tensor(_DeviceArray(pl.value, (2,), "<i8"), device=self.device)
+        self.t_q = torch.as_tensor(_DeviceArray(pq.value, (1,), "<i8"), device=self.device)
+        self.t_qall = None
+        self.send_buf = self.recv_buf = None
+
+    def prepare(self, world_size):
+        if self.t_qall is None:
+            t = self.torch
+            self.t_qall = t.zeros(world_size, dtype=t.int64, device=self.device)
+            self.send_buf = t.empty((2 * self.M, 4), dtype=t.float64, device=self.device)
+            self.recv_buf = t.empty((self.M, 4), dtype=t.float64, device=self.device)
+
+    def send_records(self, n_out):
+        """(n_out, 4) float64 = n_out 32-byte records; grows when this shard's particles own more than
+        the buffered share of the offspring (worst case world_size * M: all mass on this shard)."""
+        if n_out > self.send_buf.shape[0]:
+            self.stream.synchronize()
+            self.send_buf = self.torch.empty((n_out + n_out // 4, 4), dtype=self.torch.float64, device=self.device)
+        return self.send_buf[:max(n_out, 0)]
 
     def shard_max(self):
         out = (C.c_float * 1)()
@@ -190,10 +253,9 @@ class ShardedParticleFilter(object):
             from .rng import resample_uniform
             u = resample_uniform(self._seed, 0, self._step)
         self._step += 1
-        plan = resample_sharded(self.ops, self.dist, float(u), self.group)
-        if roughen:
-            self.pf.roughen()
-        return plan
+        self.ops.prepare(self.G)
+        return resample_sharded_device(self.ops, self.dist, float(u), self.group,
+                                       rough_var=self.pf.res_noise_cov if roughen else None)
 
     def mean_cov(self):
         import torch

@@ -17,3 +17,10 @@ l=[x for x in open('$f') if x.startswith('{')]
 if not l: print(open('$f').read()[-1500:]); sys.exit()
 d=json.loads(l[-1]); print('$f', 'ms/step %.3f'%d['ms_per_step'], 'evals/s %.3e'%d['value'], 'e2e %.3e'%d['e2e']['value'], {k:round(v,4) for k,v in d['kernel_ms_per_cycle'].items()}, 'rs_frac %.3f'%d['roofline_resample']['frac'], 'err %.4f'%d['track_error_m'])
 "; done
+if [ -n "$C5" ]; then python bench.py --workload C5 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c5_$TAG.log 2>&1; python -c "
+import json,sys
+f='gpurun_out/bench_c5_$TAG.log'
+l=[x for x in open(f) if x.startswith('{')]
+if not l: print(open(f).read()[-2500:]); sys.exit()
+d=json.loads(l[-1]); print(f, 'ms/step %.3f'%d['ms_per_step'], 'evals/s %.3e'%d['value'], 'e2e %.3e'%d['e2e']['value'], {k:round(v,4) for k,v in d['kernel_ms_per_cycle'].items()}, 'rs_frac %.3f'%d['roofline_resample']['frac'], 'err %.4f'%d['track_error_m'])
+"; fi
