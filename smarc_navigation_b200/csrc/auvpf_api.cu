@@ -100,7 +100,7 @@ struct auvpf_handle {
     float *dem_z = nullptr, *mip = nullptr, *mip_hi = nullptr, *beams = nullptr, *meas = nullptr;
     float *beam_aux = nullptr;   // [3B]: |sin th|, 1/|sin th|, 1/cos th
     double *beam_tan = nullptr;  // [2B]: tan |th|, 1 / cos th (profile merge)
-    unsigned char *flags = nullptr;   // [N]: particle needs the per-ray kernel
+    int *flagged = nullptr;           // [N]: per filter, the particles that need the per-ray kernel
     DevBuf probe_flags;
     int *beam_order = nullptr;   // [32 * chunk]
     FanParams fan{};
@@ -715,7 +715,7 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         CU(cudaMalloc(&h->cdf, sizeof(unsigned long long) * h->N));
         CU(cudaMalloc(&h->wmax_ordered, sizeof(long long) * F));
         CU(cudaMalloc(&h->wmax, sizeof(double) * F));
-        CU(cudaMalloc(&h->wmax_f32, sizeof(int) * F));
+        CU(cudaMalloc(&h->wmax_f32, sizeof(int) * 2 * F));   // [F] max log-weight | [F] flagged-particle counters
         CU(cudaMalloc(&h->done, sizeof(unsigned int) * F));
         CU(cudaMemsetAsync(h->done, 0, sizeof(unsigned int) * F, h->stream));
         CU(cudaMalloc(&h->limbs, sizeof(unsigned long long) * 2 * F));
@@ -779,7 +779,7 @@ int auvpf_destroy(auvpf_handle *h)
                     h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->status,  h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
                     h->wmax_f32, h->done, h->scan3,
-                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flags, h->probe_flags.p};
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->probe_flags.p};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -976,7 +976,7 @@ int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
     CU(cudaMalloc(&h->beam_tan, sizeof(double) * 2 * B));
     CU(cudaMemcpy(h->beam_tan, plan.tan_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->beam_tan + B, plan.sec_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
-    if (!h->flags) CU(cudaMalloc(&h->flags, (size_t)h->N));
+    if (!h->flagged) CU(cudaMalloc(&h->flagged, sizeof(int) * (size_t)h->N));
     CU(cudaMalloc(&h->beam_order, sizeof(int) * plan.order.size()));
     CU(cudaMemcpy(h->beams, host.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->beam_aux, aux.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
@@ -1125,26 +1125,31 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
     CU(cudaMemcpyAsync(h->meas, ranges, sizeof(float) * (size_t)h->B * h->F,
                        is_device_ptr(ranges) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     const double var = h->cfg.meas_std * h->cfg.meas_std;
-    CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * h->F, h->stream));
+    // one fill resets the maxima AND the flagged-particle counters (both count from kWmaxReset)
+    CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * 2 * h->F, h->stream));
     h->wmax_valid = true;
     {
         Prof pr(h, AUVPF_K_UPDATE_MBES);
         const float nhiv = (float)(-0.5 / var), lnb = (float)std::log(h->cfg.meas_std * std::sqrt(2.0 * kPi));
-        const unsigned char *only = nullptr;
+        const int *list = nullptr;
+        unsigned int *count = reinterpret_cast<unsigned int *>(h->wmax_f32 + h->F);
+        int64_t ray_blocks = (h->M + kMbesWarps - 1) / kMbesWarps;
         if (h->fan.planar && h->use_profile) {
-            // profile merge: one thread per particle; what it cannot certify is flagged ...
+            // profile merge: one thread per particle; what it cannot certify goes on a list ...
             const size_t smp = (2 * sizeof(double) + 2 * sizeof(float)) * h->B;
             k_update_mbes_profile<<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
                 h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
-                (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flags, h->wmax_f32);
+                (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count, h->wmax_f32);
             LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
-            only = h->flags;
+            list = h->flagged;
+            // ... that a SMALL grid walks (a full-size grid of early-exit blocks cost 0.35 ms at C3)
+            ray_blocks = std::min<int64_t>(ray_blocks, std::max<int64_t>(1, (148 * 8) / h->F));
         }
-        // ... and recast ray by ray (everything, when the beam set is not a planar fan)
+        // per-ray kernel: the listed particles (everything, when the beam set is not a planar fan)
         const size_t smem = sizeof(float) * 6 * h->B + sizeof(int) * 32 * h->fan.chunk;
-        k_update_mbes<<<grid1(h->M, kMbesWarps, h->F), kMbesWarps * 32, smem, h->stream>>>(
+        k_update_mbes<<<dim3((unsigned)ray_blocks, (unsigned)h->F), kMbesWarps * 32, smem, h->stream>>>(
             h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beams, h->beam_aux, h->beam_order, h->meas, h->B,
-            (float)h->cfg.range_min, nhiv, lnb, h->logw, only, h->wmax_f32);
+            (float)h->cfg.range_min, nhiv, lnb, h->logw, list, count, h->wmax_f32);
         LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
         CU(cudaGetLastError());
     }

@@ -349,12 +349,17 @@ __global__ void __launch_bounds__(kMbesWarps * 32)
 k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan, const float *__restrict__ beam_dirs,
               const float *__restrict__ beam_aux, const int *__restrict__ order, const float *__restrict__ meas, int B,
               float range_min, float neg_half_inv_var, float log_norm_per_beam, float *__restrict__ logw,
-              const unsigned char *__restrict__ only_flagged, int *__restrict__ wmax_f32)
+              const int *__restrict__ flagged_list, const unsigned int *__restrict__ flagged_count,
+              int *__restrict__ wmax_f32)
 {
     extern __shared__ float sm[];
     int *s_ord = reinterpret_cast<int *>(sm + 6 * B);
     __shared__ int s_valid;
     const int f = blockIdx.y;
+    // With a list (particles the profile kernel could not certify, usually none) the grid is small
+    // and its warps walk the list; without one every particle of the filter is cast.
+    const int64_t n_work = flagged_list ? (int64_t)(flagged_count[f] - (unsigned int)kWmaxReset) : M;
+    if ((int64_t)blockIdx.x * kMbesWarps >= n_work) return;
     if (threadIdx.x == 0) s_valid = 0;
     stage_fan_tables(sm, s_ord, B, fan, beam_dirs, beam_aux, order);
     __syncthreads();
@@ -369,26 +374,27 @@ k_update_mbes(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan
     __syncthreads();
     const float lognorm = -(float)s_valid * log_norm_per_beam;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t i = (int64_t)blockIdx.x * kMbesWarps + warp;
-    if (i >= M) return;
-    const int64_t row = (int64_t)f * M + i;
-    if (only_flagged && !only_flagged[row]) return;       // warp-uniform: resolved by the profile kernel
-    double p[3];
-    double R[9];
-    particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
-    float acc = 0.f;
-    fan_cast(dem, fan, sm, B, s_ord, p, R, lane, [&](int b, float range) {
-        const float e = sm[3 * B + b] - range;
-        acc = fmaf(e, e, acc);
-    });
-    acc = warp_sum(acc);
-    if (lane == 0) {
-        const float lw = fmaf(neg_half_inv_var, acc, lognorm);
-        logw[row] = lw;
-        if (lw == lw) {
-            const int k = float_to_ordered(lw);
-            if (k > kWmaxReset) atomicMax(wmax_f32 + f, k);
+    for (int64_t w = (int64_t)blockIdx.x * kMbesWarps + warp; w < n_work; w += (int64_t)gridDim.x * kMbesWarps) {
+        const int64_t i = flagged_list ? (int64_t)flagged_list[(int64_t)f * M + w] : w;
+        const int64_t row = (int64_t)f * M + i;
+        double p[3];
+        double R[9];
+        particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
+        float acc = 0.f;
+        fan_cast(dem, fan, sm, B, s_ord, p, R, lane, [&](int b, float range) {
+            const float e = sm[3 * B + b] - range;
+            acc = fmaf(e, e, acc);
+        });
+        acc = warp_sum(acc);
+        if (lane == 0) {
+            const float lw = fmaf(neg_half_inv_var, acc, lognorm);
+            logw[row] = lw;
+            if (lw == lw) {
+                const int k = float_to_ordered(lw);
+                if (k > kWmaxReset) atomicMax(wmax_f32 + f, k);
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -461,8 +467,8 @@ __global__ void __launch_bounds__(kProfThreads, AUVPF_PROF_MIN_BLOCKS)
 k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan,
                       const double *__restrict__ beam_tan, const float *__restrict__ beam_aux,
                       const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,
-                      float log_norm_per_beam, float *__restrict__ logw, unsigned char *__restrict__ flags,
-                      int *__restrict__ wmax_f32)
+                      float log_norm_per_beam, float *__restrict__ logw, int *__restrict__ flagged_list,
+                      unsigned int *__restrict__ flagged_count, int *__restrict__ wmax_f32)
 {
     extern __shared__ double smd[];
     double *s_tan = smd, *s_sec = smd + B;
@@ -496,8 +502,8 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
     });
     const float lw = fmaf(neg_half_inv_var, acc, -(float)s_valid * log_norm_per_beam);
     if (active) {
-        flags[row] = ok ? 0 : 1;
         if (ok) logw[row] = lw;
+        else flagged_list[(int64_t)f * M + (atomicAdd(flagged_count + f, 1u) - (unsigned int)kWmaxReset)] = (int)i;
     }
     warp_publish_max(lw, active && ok, wmax_f32 + f);
 }

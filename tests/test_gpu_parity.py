@@ -200,6 +200,47 @@ def test_update_mbes_logw_vs_oracle(cfg):
         pf.close()
 
 
+def test_update_mbes_mixed_profile_and_per_ray_particles():
+    """Particles the profile march cannot certify (sensor reach leaves the map, large tilt on steep
+    facets) are listed by the profile kernel and recast ray by ray: the log-weights of a cloud that
+    mixes both kinds -- in two filters at once -- still match the oracle, and resampling on them
+    (max published by both kernels) is exact."""
+    dem = _dem(500, 2.0)
+    B, N, F = 128, 3000, 2
+    beams = world.make_beams(B, 70.0).astype(np.float32).astype(np.float64)     # identical directions for both arms
+    rng = np.random.default_rng(77)
+    near_border = _cloud(rng, N // 3, (30.0, 500.0), 25.0)            # reach (120 m) crosses x = 0 for most
+    tilted = _cloud(rng, N // 3, (500.0, 500.0), 3.0, roll_pitch=0.35)
+    plain = _cloud(rng, N - 2 * (N // 3), (500.0, 500.0), 3.0)
+    one = np.concatenate([near_border, tilted, plain])[rng.permutation(N)]
+    poses = np.concatenate([one, one[::-1]])                            # second filter: the same cloud reversed
+    truth = np.array([[500.0, 500.0, -5.0, 0.0, 0.0, 0.3]])
+    r_true = c_oracle.update_mbes(dem, truth, np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX, want_ranges=True)["ranges"][0]
+    meas = np.stack([r_true + rng.normal(0, 0.05, B), r_true + rng.normal(0, 0.05, B)]).astype(np.float32)
+    pf = _pf(particle_count=N, n_filters=F, measurement_std=1.0, range_min=world.RANGE_MIN, range_max=world.RANGE_MAX)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    pf.set_poses(poses)
+    pf.update_mbes(meas, return_weights=False)
+    got = pf.log_weights().astype(np.float64).reshape(F, N)
+    lognorm = -B * np.log(np.sqrt(2 * np.pi))
+    for f in range(F):
+        out = c_oracle.update_mbes(dem, poses[f * N:(f + 1) * N], np.eye(4), beams, meas[f].astype(np.float64), 1.0,
+                                   world.RANGE_MIN, world.RANGE_MAX, want_diag=True)
+        want, dg = out["logw"], out["diag"]
+        sturdy = ~((dg[..., 0] < 1e-3) | (dg[..., 1] < 1e-3) | (dg[..., 2] < 1e-3)).any(axis=1)
+        tol = LOGW_RTOL * (np.abs(want - lognorm) + abs(lognorm)) + 1e-3
+        assert sturdy.mean() > 0.9
+        assert np.all(np.abs(got[f] - want)[sturdy] <= tol[sturdy]), np.max((np.abs(got[f] - want) / tol)[sturdy])
+    anc = pf.resample(u=[0.25, 0.75], return_ancestors=True, roughen=False)
+    qq = pf.weights_q().reshape(F, N)
+    lw32 = pf.log_weights().reshape(F, N)
+    for f in range(F):
+        np.testing.assert_array_equal(qq[f], o.quantise_logw(lw32[f])[0])       # the max came from BOTH kernels
+        np.testing.assert_array_equal(anc.reshape(F, N)[f], o.systematic_resample(o.weights_from_q(qq[f]), [0.25, 0.75][f]))
+    pf.close()
+
+
 # --------------------------------------------------------------------------- a5 / a7 / a8(sorted) / a9
 @pytest.mark.parametrize("N,scale", [(1, 1.0), (100, 3.0), (4097, 10.0), (65536, 25.0), (1048576, 6.0),
                                      (16777216, 4.0)])
