@@ -1136,7 +1136,7 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
         int64_t ray_blocks = (h->M + kMbesWarps - 1) / kMbesWarps;
         if (h->fan.planar && h->use_profile) {
             // profile merge: one thread per particle; what it cannot certify goes on a list ...
-            const size_t smp = (2 * sizeof(double) + 2 * sizeof(float)) * h->B;
+            const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B;
             k_update_mbes_profile<<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
                 h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
                 (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count, h->wmax_f32);
@@ -1173,7 +1173,7 @@ int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges
         if (h->fan.planar && h->use_profile) {
             void *fl;
             if ((rc = slot_reserve(h, S_OUT1, (size_t)n, &fl))) return rc;
-            const size_t smp = (2 * sizeof(double) + sizeof(float)) * h->B;
+            const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B;
             k_raycast_poses_profile<<<grid1(n, kProfThreads, 1), kProfThreads, smp, h->stream>>>(
                 pd, n, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->B, od, static_cast<unsigned char *>(fl));
             only = static_cast<unsigned char *>(fl);

@@ -434,25 +434,15 @@ constexpr int kProfThreads = 128;
 #define AUVPF_PROF_MIN_BLOCKS 5   // 96 registers: 5 blocks per SM (97 would drop to 4: measured 14 % slower)
 #endif
 
-// shared memory: tan (double B) | sec (double B) | |sin| (float B) | measured range (float B)
-// beam_tan = [tan | sec] (2B doubles), beam_aux[0..B) = |sin|
-__device__ __forceinline__ void stage_profile_tables(double *s_tan, double *s_sec, float *s_sin, int B,
-                                                     const double *beam_tan, const float *beam_aux)
-{
-    for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        s_tan[b] = beam_tan[b];
-        s_sec[b] = beam_tan[B + b];
-        s_sin[b] = beam_aux[b];
-    }
-}
-
+// shared memory: tan (double B) | sec (double B) | aux (BeamAux B: sec, reach, measured range)
+// beam_tan = [tan | sec] (2B doubles), beam_aux[0..B) = |lateral component|
 __device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, const double *s_tan, const double *s_sec,
-                                                 const float *s_sin)
+                                                 const BeamAux *s_aux)
 {
     FanTables T;
     T.tan_t = s_tan;
     T.sec_t = s_sec;
-    T.sin_t = s_sin;
+    T.aux = s_aux;
     T.B = B;
     T.n1 = fan.n1;
     T.sgn1 = fan.sgn1;
@@ -472,17 +462,23 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
 {
     extern __shared__ double smd[];
     double *s_tan = smd, *s_sec = smd + B;
-    float *s_sin = reinterpret_cast<float *>(smd + 2 * B), *s_meas = s_sin + B;
+    BeamAux *s_aux = reinterpret_cast<BeamAux *>(smd + 2 * B);
     __shared__ int s_valid;
     const int f = blockIdx.y;
     if (threadIdx.x == 0) s_valid = 0;
-    stage_profile_tables(s_tan, s_sec, s_sin, B, beam_tan, beam_aux);
     __syncthreads();
     int nv = 0;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
-        float r = meas[(size_t)f * B + b];
-        bool ok = isfinite(r) && r >= range_min && r <= dem.range_max;
-        s_meas[b] = ok ? r : __int_as_float(0x7fc00000);
+        s_tan[b] = beam_tan[b];
+        s_sec[b] = beam_tan[B + b];
+        const float r = meas[(size_t)f * B + b];
+        const bool ok = isfinite(r) && r >= range_min && r <= dem.range_max;
+        BeamAux a;
+        a.sec = (float)beam_tan[B + b];
+        a.reach = beam_aux[b] * dem.range_max;
+        a.meas = ok ? r : __int_as_float(0x7fc00000);        // invalid measured beam: skipped in the sum
+        a.pad = 0.f;
+        s_aux[b] = a;
         nv += ok ? 1 : 0;
     }
     if (nv) atomicAdd(&s_valid, nv);
@@ -493,10 +489,9 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
     double p[3];
     double R[9];
     particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
-    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_sin);
+    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_aux);
     float acc = 0.f;
-    const bool ok = profile_particle(dem, T, p, R, active, [&](int b, float range) {
-        const float rm = s_meas[b];
+    const bool ok = profile_particle(dem, T, p, R, active, [&](int, float range, float rm) {
         const float e = rm - range;
         if (rm == rm) acc = fmaf(e, e, acc);
     });
@@ -515,8 +510,17 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
 {
     extern __shared__ double smd[];
     double *s_tan = smd, *s_sec = smd + B;
-    float *s_sin = reinterpret_cast<float *>(smd + 2 * B);
-    stage_profile_tables(s_tan, s_sec, s_sin, B, beam_tan, beam_aux);
+    BeamAux *s_aux = reinterpret_cast<BeamAux *>(smd + 2 * B);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        s_tan[b] = beam_tan[b];
+        s_sec[b] = beam_tan[B + b];
+        BeamAux a;
+        a.sec = (float)beam_tan[B + b];
+        a.reach = beam_aux[b] * dem.range_max;
+        a.meas = 0.f;
+        a.pad = 0.f;
+        s_aux[b] = a;
+    }
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
     const bool active = i < n;
@@ -524,9 +528,9 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
     double p[3];
     double R[9];
     particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
-    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_sin);
+    const FanTables T = make_tables(fan, B, s_tan, s_sec, s_aux);
     float *row = out + (size_t)(active ? i : 0) * B;
-    const bool ok = profile_particle(dem, T, p, R, active, [&](int b, float range) { row[b] = range; });
+    const bool ok = profile_particle(dem, T, p, R, active, [&](int b, float range, float) { row[b] = range; });
     if (active) flags[i] = ok ? 0 : 1;
 }
 

@@ -729,9 +729,15 @@ __host__ __device__ __noinline__
 #else
 inline
 #endif
-double precise_hit(const ProfFrameD *D, double sg, int cx, int cy, double z00, double Du, double Dv, double tn)
+double precise_hit(const ProfFrameD *D, float sgf, int cx, int cy, float z00, float z01, float z10, float z11, bool lower,
+                   double tn)
 {
-    const double alpha = (z00 - D->oz) + (D->gox - (double)cx) * Du + (D->goy - (double)cy) * Dv;
+    // float32 arguments on purpose: with float64 ones the compiler hoisted six conversions and two
+    // float64 subtractions out of the beam loop into EVERY step (ncu: the slowest instructions there)
+    const double Du = lower ? (double)z01 - (double)z00 : (double)z11 - (double)z10;
+    const double Dv = lower ? (double)z11 - (double)z01 : (double)z10 - (double)z00;
+    const double sg = (double)sgf;
+    const double alpha = ((double)z00 - D->oz) + (D->gox - (double)cx) * Du + (D->goy - (double)cy) * Dv;
     const double beta = sg * (D->agx * Du + D->agy * Dv - D->az);
     const double gamma = D->cz - D->cgx * Du - D->cgy * Dv;
     return alpha / (gamma - beta * tn);
@@ -745,18 +751,27 @@ double precise_hit(const ProfFrameD *D, double sg, int cx, int cy, double z00, d
 // while ANY lane is still marching, and the warp is re-synchronised at the end of every step.
 // profile_particle must be called by all 32 lanes of a warp.
 #if defined(__CUDA_ARCH__)
-#define AUVPF_WARP_ANY(p) __any_sync(0xffffffffu, (p))
+#define AUVPF_WARP_BALLOT(p) __ballot_sync(0xffffffffu, (p))
 #define AUVPF_WARP_SYNC() __syncwarp()
+#define AUVPF_WARP_SYNC_MASK(m) __syncwarp(m)
 #else
-#define AUVPF_WARP_ANY(p) (p)
+#define AUVPF_WARP_BALLOT(p) ((p) ? 1u : 0u)
 #define AUVPF_WARP_SYNC() ((void)0)
+#define AUVPF_WARP_SYNC_MASK(m) ((void)(m))
 #endif
 
 // Beam tables of a planar fan as the profile merge needs them (device: shared memory).
+struct BeamAux {                             // one 16-byte load per beam
+    float sec;                               // 1 / along-centre component (float32 copy)
+    float reach;                             // |lateral component| * range_max: lateral distance the beam can cover
+    float meas;                              // measured range of the ping (NaN = beam not used); 0 for probes
+    float pad;
+};
+
 struct FanTables {
     const double *tan_t;                     // |lateral| / along-centre component of the beam direction
-    const double *sec_t;                     // 1 / along-centre component
-    const float *sin_t;                      // |lateral| component
+    const double *sec_t;                     // 1 / along-centre component (float64: grazing hits only)
+    const BeamAux *aux;
     int B, n1, sgn1;                         // beams [0,n1) on the side sign sgn1, [n1,B) on the other
     float c0[3], a0[3];                      // fan centre / lateral unit vectors, sensor frame
 };
@@ -776,35 +791,38 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     int bb = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;   // current beam, next one outward
     float sgf = (float)(side == 0 ? T.sgn1 : -T.sgn1);
     int j = 0;
-    double tn = 0.0;                       // the current beam's tan, 1 / cos and lateral reach
-    float sec_f = 1.f, reach = 0.f;
-    float q_f = (float)S.q0;               // float32 copy of q_cur
+    double tn = 0.0;                       // the current beam's tan ...
+    BeamAux ax;                            // ... and its float32 constants; reloaded only when the beam changes
+    ax.sec = 1.f;
+    ax.reach = ax.meas = ax.pad = 0.f;
     int cx = S.cx, cy = S.cy;
+    int zi = cy * m.pitch + cx;            // index of the cell's vertex (0, 0) in the padded DEM
     float u = S.u, v = S.v;
     bool lower = u >= v;
     int entry = -1;                        // canonical edge the curve entered the triangle through
     double p_cur = 0.0, q_cur = S.q0;
+    float p_f = 0.f, q_f = (float)S.q0;    // float32 copies of the two accumulators
     bool running = active && T.B > 0;
     bool ok = true;
     const int max_steps = 2 * (8 * (int)(m.range_max / m.res) + 256);
     float z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
     if (running) {
-        const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
-        z00 = ldg_f(zp);
-        z01 = ldg_f(zp + 1);
-        z10 = ldg_f(zp + m.pitch);
-        z11 = ldg_f(zp + m.pitch + 1);
+        z00 = ldg_f(m.z + zi);
+        z01 = ldg_f(m.z + zi + 1);
+        z10 = ldg_f(m.z + zi + m.pitch);
+        z11 = ldg_f(m.z + zi + m.pitch + 1);
         tn = T.tan_t[bb];
-        sec_f = (float)T.sec_t[bb];
-        reach = T.sin_t[bb] * m.range_max;
+        ax = T.aux[bb];
     }
     for (int step = 0; step < max_steps; ++step) {
-        if (!AUVPF_WARP_ANY(running)) break;
-        if (running) do {
+        const unsigned act = AUVPF_WARP_BALLOT(running);
+        if (!act) break;
+        if (running) {
+            bool fail = false;
             const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
             const float Dv = lower ? z11 - z01 : z10 - z00;
             const float gamma = F0.cz - F0.cgx * Du - F0.cgy * Dv;
-            if (!(gamma < -kGammaMin)) { AUVPF_REASON(0); ok = false; running = false; break; }
+            if (!(gamma < -kGammaMin)) { AUVPF_REASON(0); fail = true; }
             const float beta = sgf * (F0.agx * Du + F0.agy * Dv - F0.az);
             const float s = fast_div(beta, gamma);                // profile slope dT/dp
             const float X1 = fmaf(s, F0.cgx, sgf * F0.agx), Y1 = fmaf(s, F0.cgy, sgf * F0.agy);   // d(u,v)/dp
@@ -829,45 +847,45 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 bd = B1 - A1;
                 be = 2;
             }
-            if (be < 0) { AUVPF_REASON(1); ok = false; running = false; break; }   // curve turns back through its entry edge
+            if (be < 0 && !fail) { AUVPF_REASON(1); fail = true; }   // curve turns back through its entry edge
             const float dp = fast_div(bn, bd);
-            const double p_out = p_cur + (double)dp;
-            const float p_out_f = (float)p_out;
+            const float p_out_f = p_f + dp;
             // beams whose line meets the profile inside this segment.  gap = lateral distance of the
             // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
             // A beam is resolved here when it hits inside the segment, or when the segment's end is
             // beyond what the beam can reach within range_max (miss).
-            // The current beam's constants (tan, reach = |sin| range_max, sec) live in registers and
-            // are reloaded only when the beam changes, ahead of their use.
-            while (j < n_side) {
+            while (!fail && j < n_side) {
                 const float gap = (float)(q_cur * tn - p_cur);
                 const float den = fmaf(-s, (float)tn, 1.0f);
                 const bool hit = gap <= dp * den;
-                if (!(hit || p_out_f > reach)) break;
+                if (!(hit || p_out_f > ax.reach)) break;
                 float range = m.range_max;
                 if (hit) {
                     // range = (q at the hit) / cos th.  float32 from the float32 copy of q_cur: three
                     // roundings at <= 120 m, < 2e-5 m (tolerance 1e-4 m); grazing hits go the float64 way
                     const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
-                    float t = fmaf(s, dph, q_f) * sec_f;
+                    float t = fmaf(s, dph, q_f) * ax.sec;
                     if (den < kDenPrecise)
-                        t = (float)(precise_hit(D, (double)sgf, cx, cy, (double)z00,
-                                                (double)(lower ? z01 : z11) - (double)(lower ? z00 : z10),
-                                                (double)(lower ? z11 : z10) - (double)(lower ? z01 : z00), tn) *
-                                    T.sec_t[bb]);
+                        t = (float)(precise_hit(D, sgf, cx, cy, z00, z01, z10, z11, lower, tn) * T.sec_t[bb]);
                     range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
                 }
                 const int b_done = bb;
+                const float meas = ax.meas;
                 ++j;
                 bb += bstep;
                 if (j < n_side) {                                  // next beam's constants, in flight during the sink
                     tn = T.tan_t[bb];
-                    sec_f = (float)T.sec_t[bb];
-                    reach = T.sin_t[bb] * m.range_max;
+                    ax = T.aux[bb];
                 }
-                sink(b_done, range);
+                sink(b_done, range, meas);
             }
-            if (j >= n_side) {
+            // Lanes leave the beam loop after different trip counts; without this barrier each group
+            // ran the code below on its own (ncu: 2.3 executions per step at 13 of 32 lanes).
+            AUVPF_WARP_SYNC_MASK(act);
+            if (fail) {
+                ok = false;
+                running = false;
+            } else if (j >= n_side) {
                 // this side is done: start the other one from the anchor, or finish
                 if (side == 0 && T.B - T.n1 > 0) {
                     side = 1;
@@ -877,34 +895,33 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     sgf = -sgf;
                     j = 0;
                     tn = T.tan_t[bb];
-                    sec_f = (float)T.sec_t[bb];
-                    reach = T.sin_t[bb] * m.range_max;
+                    ax = T.aux[bb];
                     cx = S.cx;
                     cy = S.cy;
+                    zi = cy * m.pitch + cx;
                     u = S.u;
                     v = S.v;
                     lower = u >= v;
                     entry = -1;
                     p_cur = 0.0;
                     q_cur = S.q0;
+                    p_f = 0.f;
                     q_f = (float)S.q0;
-                    const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
-                    z00 = ldg_f(zp);
-                    z01 = ldg_f(zp + 1);
-                    z10 = ldg_f(zp + m.pitch);
-                    z11 = ldg_f(zp + m.pitch + 1);
+                    z00 = ldg_f(m.z + zi);
+                    z01 = ldg_f(m.z + zi + 1);
+                    z10 = ldg_f(m.z + zi + m.pitch);
+                    z11 = ldg_f(m.z + zi + m.pitch + 1);
                 } else
                     running = false;
-                break;
-            }
-            // advance to the exit point and step into the neighbour across that edge (selects, not
-            // branches: lanes leaving through different edges stay converged)
-            q_cur += (double)(s * dp);
-            q_f = (float)q_cur;
-            p_cur = p_out;
-            u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
-            v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
-            {
+            } else {
+                // advance to the exit point and step into the neighbour across that edge (selects, not
+                // branches: lanes leaving through different edges stay converged)
+                q_cur += (double)(s * dp);
+                p_cur += (double)dp;
+                q_f = (float)q_cur;
+                p_f = (float)p_cur;
+                u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
+                v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
                 const bool diag = be == 2;                         // diagonal: same cell, other half
                 const bool uedge = !diag && ((be == 0) == lower);  // an x = const edge
                 const bool vedge = !diag && !uedge;
@@ -913,25 +930,23 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 const float mid = 0.5f * (u + v);
                 cx += uedge ? dir : 0;
                 cy += vedge ? dir : 0;
+                zi += uedge ? dir : (vedge ? dir * m.pitch : 0);
                 u = diag ? mid : (uedge ? nc : u);
                 v = diag ? mid : (vedge ? nc : v);
                 if ((unsigned)cx > (unsigned)(m.W - 2) || (unsigned)cy > (unsigned)(m.H - 2)) {   // left the map
                     AUVPF_REASON(2);
                     ok = false;
                     running = false;
-                    break;
+                } else if (!diag) {
+                    z00 = ldg_f(m.z + zi);
+                    z01 = ldg_f(m.z + zi + 1);
+                    z10 = ldg_f(m.z + zi + m.pitch);
+                    z11 = ldg_f(m.z + zi + m.pitch + 1);
                 }
-                if (!diag) {
-                    const float *zp = m.z + (ptrdiff_t)cy * m.pitch + cx;
-                    z00 = ldg_f(zp);
-                    z01 = ldg_f(zp + 1);
-                    z10 = ldg_f(zp + m.pitch);
-                    z11 = ldg_f(zp + m.pitch + 1);
-                }
+                lower = !lower;
+                entry = be == 2 ? 2 : 1 - be;
             }
-            lower = !lower;
-            entry = be == 2 ? 2 : 1 - be;
-        } while (0);
+        }
         AUVPF_WARP_SYNC();
     }
     if (running) {                           // ran out of steps: not certified
@@ -1022,7 +1037,7 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
     } while (0);
     AUVPF_WARP_SYNC();
     if (all_zero)
-        for (int b = 0; b < T.B; ++b) sink(b, 0.f);
+        for (int b = 0; b < T.B; ++b) sink(b, 0.f, T.aux[b].meas);
     const bool marched = profile_march(m, T, F, &D, S, ok && !all_zero, sink);
     return ok && (all_zero || marched);
 }

@@ -135,9 +135,16 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
         if (use_fan == 2) {
             // profile merge (k_update_mbes_profile): one march per side, generic fallback
             FanTables T;
+            std::vector<BeamAux> aux(B);
+            for (int b = 0; b < B; ++b) {
+                aux[b].sec = (float)plan.sec_t[b];
+                aux[b].reach = plan.s[b] * v.range_max;
+                aux[b].meas = 0.f;
+                aux[b].pad = 0.f;
+            }
             T.tan_t = plan.tan_t.data();
             T.sec_t = plan.sec_t.data();
-            T.sin_t = plan.s.data();
+            T.aux = aux.data();
             T.B = B;
             T.n1 = plan.n1;
             T.sgn1 = plan.sgn1;
@@ -146,7 +153,7 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
                 T.a0[a] = plan.a0[a];
             }
             float *row = out + (size_t)i * B;
-            bool ok = plan.planar && profile_particle(v, T, p, R, true, [&](int b, float range) { row[b] = range; });
+            bool ok = plan.planar && profile_particle(v, T, p, R, true, [&](int b, float range, float) { row[b] = range; });
             if (ok) *n_swept += B;
             else
                 for (int b = 0; b < B; ++b) {
