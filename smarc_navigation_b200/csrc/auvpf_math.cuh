@@ -792,6 +792,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     float sgf = (float)(side == 0 ? T.sgn1 : -T.sgn1);
     int j = 0;
     double tn = 0.0;                       // the current beam's tan ...
+    float tn_f = 0.f, gap = 0.f;           // ... its float32 copy, and the beam line's lead over the curve point
+    const float rmax = m.range_max;
     BeamAux ax;                            // ... and its float32 constants; reloaded only when the beam changes
     ax.sec = 1.f;
     ax.reach = ax.meas = ax.pad = 0.f;
@@ -813,6 +815,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         z11 = ldg_f(m.z + zi + m.pitch + 1);
         tn = T.tan_t[bb];
         ax = T.aux[bb];
+        tn_f = (float)tn;
+        gap = (float)(q_cur * tn);
     }
     for (int step = 0; step < max_steps; ++step) {
         const unsigned act = AUVPF_WARP_BALLOT(running);
@@ -854,21 +858,20 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
             // A beam is resolved here when it hits inside the segment, or when the segment's end is
             // beyond what the beam can reach within range_max (miss).
+            // gap is carried in float32: set in float64 when the beam changes (the product q tan and p
+            // cancel), then moved along with the curve point segment by segment (gap -= dp den), so the
+            // test below has no float64 and no conversion in it.
             while (!fail && j < n_side) {
-                const float gap = (float)(q_cur * tn - p_cur);
-                const float den = fmaf(-s, (float)tn, 1.0f);
+                const float den = fmaf(-s, tn_f, 1.0f);
                 const bool hit = gap <= dp * den;
                 if (!(hit || p_out_f > ax.reach)) break;
-                float range = m.range_max;
-                if (hit) {
-                    // range = (q at the hit) / cos th.  float32 from the float32 copy of q_cur: three
-                    // roundings at <= 120 m, < 2e-5 m (tolerance 1e-4 m); grazing hits go the float64 way
-                    const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
-                    float t = fmaf(s, dph, q_f) * ax.sec;
-                    if (den < kDenPrecise)
-                        t = (float)(precise_hit(D, sgf, cx, cy, z00, z01, z10, z11, lower, tn) * T.sec_t[bb]);
-                    range = t <= m.range_max ? fmaxf(t, 0.f) : m.range_max;
-                }
+                // range = (q at the hit) / cos th.  float32 from the float32 copy of q_cur: three
+                // roundings at <= 120 m, < 2e-5 m (tolerance 1e-4 m); grazing hits go the float64 way
+                const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
+                float t = fmaf(s, dph, q_f) * ax.sec;
+                if (hit && den < kDenPrecise)
+                    t = (float)(precise_hit(D, sgf, cx, cy, z00, z01, z10, z11, lower, tn) * T.sec_t[bb]);
+                const float range = (hit && t <= rmax) ? fmaxf(t, 0.f) : rmax;   // not hit: out of reach, a miss
                 const int b_done = bb;
                 const float meas = ax.meas;
                 ++j;
@@ -876,6 +879,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 if (j < n_side) {                                  // next beam's constants, in flight during the sink
                     tn = T.tan_t[bb];
                     ax = T.aux[bb];
+                    tn_f = (float)tn;
+                    gap = (float)(q_cur * tn - p_cur);
                 }
                 sink(b_done, range, meas);
             }
@@ -896,6 +901,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     j = 0;
                     tn = T.tan_t[bb];
                     ax = T.aux[bb];
+                    tn_f = (float)tn;
+                    gap = (float)(S.q0 * tn);
                     cx = S.cx;
                     cy = S.cy;
                     zi = cy * m.pitch + cx;
@@ -916,6 +923,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             } else {
                 // advance to the exit point and step into the neighbour across that edge (selects, not
                 // branches: lanes leaving through different edges stay converged)
+                gap = fmaf(-dp, fmaf(-s, tn_f, 1.0f), gap);         // the current beam's lead at the new curve point
                 q_cur += (double)(s * dp);
                 p_cur += (double)dp;
                 q_f = (float)q_cur;
