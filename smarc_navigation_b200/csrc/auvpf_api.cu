@@ -1137,9 +1137,16 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
         if (h->fan.planar && h->use_profile) {
             // profile merge: one thread per particle; what it cannot certify goes on a list ...
             const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B;
-            k_update_mbes_profile<<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
-                h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
-                (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count, h->wmax_f32);
+            if (h->N <= kProfSmallLimit)
+                k_update_mbes_profile<kProfThreadsSmall, kProfMinBlocksSmall>
+                    <<<grid1(h->M, kProfThreadsSmall, h->F), kProfThreadsSmall, smp, h->stream>>>(
+                        h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
+                        (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count, h->wmax_f32);
+            else
+                k_update_mbes_profile<kProfThreads, kProfMinBlocks>
+                    <<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
+                        h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
+                        (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count, h->wmax_f32);
             LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
             list = h->flagged;
             // ... that a SMALL grid walks (a full-size grid of early-exit blocks cost 0.35 ms at C3)

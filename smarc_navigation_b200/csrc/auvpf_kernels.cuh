@@ -429,10 +429,13 @@ k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, Dem
 // footprint is shared in L1.  Particles that cannot be certified (near the map border, centre
 // beam missed, a triangle steeper than the fan tilt allows) are flagged and recast by the
 // per-ray kernel above.
-constexpr int kProfThreads = 128;
-#ifndef AUVPF_PROF_MIN_BLOCKS
-#define AUVPF_PROF_MIN_BLOCKS 5   // 96 registers: 5 blocks per SM (97 would drop to 4: measured 14 % slower)
-#endif
+// Block shapes of the profile kernel, measured at C3 / C2 (ms): (128 thr, 5 blocks/SM, 96 regs) 4.60 / 0.142;
+// (128, 6, 80 regs) 4.23 / 0.142; (192, 3, 96 regs) 4.24 / 0.132; (256, 2, 109 regs, no spill) 4.44 / 0.118.
+// A saturated GPU wants the 24-warp or the 192-thread shape; a cloud that does not fill the machine
+// (fewer than ~4 warps per scheduler) runs fastest with all the registers it wants.
+constexpr int kProfThreads = 192, kProfMinBlocks = 3;
+constexpr int kProfThreadsSmall = 256, kProfMinBlocksSmall = 2;
+constexpr int64_t kProfSmallLimit = 148 * 4 * 4 * 32;      // particles below which the small-cloud shape is used
 
 // shared memory: tan (double B) | sec (double B) | aux (BeamAux B: sec, reach, measured range)
 // beam_tan = [tan | sec] (2B doubles), beam_aux[0..B) = |lateral component|
@@ -453,7 +456,8 @@ __device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, co
     return T;
 }
 
-__global__ void __launch_bounds__(kProfThreads, AUVPF_PROF_MIN_BLOCKS)
+template <int kT, int kMinB>
+__global__ void __launch_bounds__(kT, kMinB)
 k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan,
                       const double *__restrict__ beam_tan, const float *__restrict__ beam_aux,
                       const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,
@@ -477,13 +481,13 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
         a.sec = (float)beam_tan[B + b];
         a.reach = beam_aux[b] * dem.range_max;
         a.meas = ok ? r : __int_as_float(0x7fc00000);        // invalid measured beam: skipped in the sum
-        a.pad = 0.f;
+        a.rmax = dem.range_max;
         s_aux[b] = a;
         nv += ok ? 1 : 0;
     }
     if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
+    const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
     const bool active = i < M;              // lanes past the end still walk through (warp-uniform march)
     const int64_t row = (int64_t)f * M + (active ? i : 0);
     double p[3];
@@ -518,7 +522,7 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
         a.sec = (float)beam_tan[B + b];
         a.reach = beam_aux[b] * dem.range_max;
         a.meas = 0.f;
-        a.pad = 0.f;
+        a.rmax = dem.range_max;
         s_aux[b] = a;
     }
     __syncthreads();

@@ -765,8 +765,44 @@ struct BeamAux {                             // one 16-byte load per beam
     float sec;                               // 1 / along-centre component (float32 copy)
     float reach;                             // |lateral component| * range_max: lateral distance the beam can cover
     float meas;                              // measured range of the ping (NaN = beam not used); 0 for probes
-    float pad;
+    float rmax;                              // range_max, carried here so the beam loop reads no constant-bank value
 };
+
+// Per-beam table reads.  On the device the tables are in shared memory and are read with explicit
+// 32-bit shared addresses: through the generic pointers the compiler re-derived the shared window
+// base (S2R SR_CgaCtaId + LEA) in every trip of the beam loop (ncu: 3 % of the stall samples).
+struct BeamTabs {
+#if defined(__CUDA_ARCH__)
+    uint32_t tan_s, aux_s;
+#else
+    const double *tan_t;
+    const BeamAux *aux;
+#endif
+};
+
+AUVPF_HD double beam_tan(const BeamTabs &t, int b)
+{
+#if defined(__CUDA_ARCH__)
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(t.tan_s + 8u * (uint32_t)b));
+    return v;
+#else
+    return t.tan_t[b];
+#endif
+}
+
+AUVPF_HD BeamAux beam_aux(const BeamTabs &t, int b)
+{
+#if defined(__CUDA_ARCH__)
+    BeamAux a;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(a.sec), "=f"(a.reach), "=f"(a.meas), "=f"(a.rmax)
+                 : "r"(t.aux_s + 16u * (uint32_t)b));
+    return a;
+#else
+    return t.aux[b];
+#endif
+}
 
 struct FanTables {
     const double *tan_t;                     // |lateral| / along-centre component of the beam direction
@@ -793,10 +829,18 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     int j = 0;
     double tn = 0.0;                       // the current beam's tan ...
     float tn_f = 0.f, gap = 0.f;           // ... its float32 copy, and the beam line's lead over the curve point
-    const float rmax = m.range_max;
     BeamAux ax;                            // ... and its float32 constants; reloaded only when the beam changes
     ax.sec = 1.f;
-    ax.reach = ax.meas = ax.pad = 0.f;
+    ax.reach = ax.meas = 0.f;
+    ax.rmax = m.range_max;
+    BeamTabs tabs;
+#if defined(__CUDA_ARCH__)
+    tabs.tan_s = (uint32_t)__cvta_generic_to_shared(T.tan_t);
+    tabs.aux_s = (uint32_t)__cvta_generic_to_shared(T.aux);
+#else
+    tabs.tan_t = T.tan_t;
+    tabs.aux = T.aux;
+#endif
     int cx = S.cx, cy = S.cy;
     int zi = cy * m.pitch + cx;            // index of the cell's vertex (0, 0) in the padded DEM
     float u = S.u, v = S.v;
@@ -813,8 +857,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         z01 = ldg_f(m.z + zi + 1);
         z10 = ldg_f(m.z + zi + m.pitch);
         z11 = ldg_f(m.z + zi + m.pitch + 1);
-        tn = T.tan_t[bb];
-        ax = T.aux[bb];
+        tn = beam_tan(tabs, bb);
+        ax = beam_aux(tabs, bb);
         tn_f = (float)tn;
         gap = (float)(q_cur * tn);
     }
@@ -871,14 +915,15 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 float t = fmaf(s, dph, q_f) * ax.sec;
                 if (hit && den < kDenPrecise)
                     t = (float)(precise_hit(D, sgf, cx, cy, z00, z01, z10, z11, lower, tn) * T.sec_t[bb]);
+                const float rmax = ax.rmax;
                 const float range = (hit && t <= rmax) ? fmaxf(t, 0.f) : rmax;   // not hit: out of reach, a miss
                 const int b_done = bb;
                 const float meas = ax.meas;
                 ++j;
                 bb += bstep;
                 if (j < n_side) {                                  // next beam's constants, in flight during the sink
-                    tn = T.tan_t[bb];
-                    ax = T.aux[bb];
+                    tn = beam_tan(tabs, bb);
+                    ax = beam_aux(tabs, bb);
                     tn_f = (float)tn;
                     gap = (float)(q_cur * tn - p_cur);
                 }
@@ -899,8 +944,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     bstep = 1;
                     sgf = -sgf;
                     j = 0;
-                    tn = T.tan_t[bb];
-                    ax = T.aux[bb];
+                    tn = beam_tan(tabs, bb);
+                    ax = beam_aux(tabs, bb);
                     tn_f = (float)tn;
                     gap = (float)(S.q0 * tn);
                     cx = S.cx;

@@ -140,7 +140,7 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
                 aux[b].sec = (float)plan.sec_t[b];
                 aux[b].reach = plan.s[b] * v.range_max;
                 aux[b].meas = 0.f;
-                aux[b].pad = 0.f;
+                aux[b].rmax = v.range_max;
             }
             T.tan_t = plan.tan_t.data();
             T.sec_t = plan.sec_t.data();
