@@ -249,7 +249,11 @@ def run_ours(args):
         truth = np.stack([c[1] for c in per])                                    # (F, 6)
         r_true = pf.raycast(truth)                                               # (F, B)
         noise = np.stack([world.ping_noise(B, s, seed=3 + 7 * f) for f in range(F)]) if F > 1 else world.ping_noise(B, s)[None]
-        odoms = [per[0][0][p] if F == 1 else [per[f][0][p] for f in range(F)] for p in range(P_PREDICTS)]
+        if F == 1:
+            odoms = [per[0][0][p] for p in range(P_PREDICTS)]
+        else:       # batched filters: one (F, 11) array of ABI odometry rows per predict
+            odoms = [np.array([[o.v[0], o.v[1], o.v[2], o.wz, o.quat[0], o.quat[1], o.quat[2], o.quat[3], o.z, o.dt, 0.0]
+                               for o in (per[f][0][p] for f in range(F))]) for p in range(P_PREDICTS)]
         cycles.append((odoms, (r_true + noise).astype(np.float32).reshape(F * B), truth[0], truth))
     pings_dev = torch.from_numpy(np.stack([c[1] for c in cycles])).cuda()
     pings_pin = torch.from_numpy(np.stack([c[1] for c in cycles])).pin_memory()

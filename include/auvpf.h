@@ -194,6 +194,22 @@ int auvpf_shard_buffers(auvpf_handle *h, void **wmax_i32, void **limbs_u64, void
 int auvpf_shard_max_dev(auvpf_handle *h);
 int auvpf_shard_sum_dev(auvpf_handle *h);
 int auvpf_shard_scan_dev(auvpf_handle *h);
+/* Peer-memory exchange: stages 4-5 in ONE kernel over NVLink.  Each rank exports a CUDA IPC
+ * handle of its state / CDF / tile-table slab (auvpf_ipc_export, AUVPF_IPC_BLOB_BYTES per
+ * rank), the blobs of all ranks are gathered by the caller (rank order) and imported once
+ * (auvpf_ipc_import; <= 8 ranks of one node).  After scan_dev and the all-gather of Q,
+ * auvpf_shard_gather_p2p(u, q_all) -- q_all: the gathered int64 totals, DEVICE memory -- selects
+ * this rank's ancestors in the global CDF reading the owners' tile tables and CDF directly,
+ * loads their state from the owners' memory, adds the roughening noise and writes this rank's
+ * new state: no records, no all-to-all, no host synchronisation.  Calls must be made by every
+ * rank in the same order.  When no shard has any finite weight the state is carried over
+ * unchanged and auvpf_shard_degenerate() reports 1 (that call synchronises). */
+#define AUVPF_IPC_BLOB_BYTES 256
+int auvpf_ipc_export(auvpf_handle *h, void *blob);
+int auvpf_ipc_import(auvpf_handle *h, const void *blobs, int32_t n_ranks, int32_t my_rank);
+int auvpf_shard_gather_p2p(auvpf_handle *h, double u, const int64_t *q_all_dev, const double *rough_var,
+                           const float *rough_noise, int64_t *ancestors_out_dev);
+int auvpf_shard_degenerate(auvpf_handle *h, int32_t *flag);
 /* stage 4: emit the n_out = out_hi - out_lo offspring whose ancestors live in
  * this shard: global output slots [out_lo, out_hi) as 32-byte records
  * {double x, y; float z, roll, pitch, yaw} into `records` (device or host) and,

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get("AUVPF_LIB") or os.path.join(_HERE, "libauvpf.so")   #
 OK, ERR_BADARG, ERR_CUDA, ERR_STATE, ERR_DEGENERATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 SYSTEMATIC, RESIDUAL = 0, 1
 RS_SORTED, RS_INPLACE_REF, RS_STRICT_REF = 0, 1, 2
+IPC_BLOB_BYTES = 256
 K_NAMES = ("propagate", "update_mbes", "update_gps", "normalise", "scan", "select_gather", "roughen",
            "estimate", "other")
 
@@ -71,6 +72,10 @@ SYMBOLS = [
     ("auvpf_shard_max_dev", C.c_int, [_vp]),
     ("auvpf_shard_sum_dev", C.c_int, [_vp]),
     ("auvpf_shard_scan_dev", C.c_int, [_vp]),
+    ("auvpf_ipc_export", C.c_int, [_vp, _vp]),
+    ("auvpf_ipc_import", C.c_int, [_vp, _vp, _i32, _i32]),
+    ("auvpf_shard_gather_p2p", C.c_int, [_vp, _dbl, _vp, _vp, _vp, _vp]),
+    ("auvpf_shard_degenerate", C.c_int, [_vp, C.POINTER(_i32)]),
     ("auvpf_shard_emit", C.c_int, [_vp, _dbl, _u64, _u64, _i64, _i64, _vp, _vp]),
     ("auvpf_shard_load", C.c_int, [_vp, _vp, _i64]),
     ("auvpf_shard_load_roughen", C.c_int, [_vp, _vp, _i64, _vp, _vp]),

@@ -64,7 +64,15 @@ struct auvpf_handle {
     int F = 1;
     int64_t global_offset = 0, global_count = 0;
 
-    // state (double-buffered SoA)
+    // state (double-buffered SoA), integer CDF and scan tile table live in ONE allocation (the
+    // slab) so that a single CUDA IPC handle exposes them to the other ranks of a sharded filter
+    void *slab = nullptr;
+    size_t slab_bytes = 0;
+    int64_t slab_off[14] = {0};            // st[0].{x,y,z,roll,pitch,yaw}, st[1].{...}, cdf, status
+    void *peer_slab[8] = {nullptr};        // peers' slabs opened through IPC ([rank] == own slab)
+    int n_peers = 0, my_peer = 0;
+    unsigned long long *shard_meta = nullptr;   // [n_peers + 2]: per-shard CDF offsets, deficit, degenerate flag
+    PeerTable *peer_tables = nullptr;           // [2] device: peers' pointers with buffer 0 / 1 as the gather source
     StateView st[2];
     int cur = 0;
     float *logw = nullptr;
@@ -327,25 +335,36 @@ NoiseParams make_noise(auvpf_handle *h, const double var[6], const double *mean,
     return n;
 }
 
-int alloc_state(StateView &s, int64_t n)
+StateView state_at(void *slab, const int64_t *off)
 {
-    CU(cudaMalloc(&s.x, n * sizeof(double)));
-    CU(cudaMalloc(&s.y, n * sizeof(double)));
-    CU(cudaMalloc(&s.z, n * sizeof(float)));
-    CU(cudaMalloc(&s.roll, n * sizeof(float)));
-    CU(cudaMalloc(&s.pitch, n * sizeof(float)));
-    CU(cudaMalloc(&s.yaw, n * sizeof(float)));
-    return AUVPF_OK;
+    char *b = static_cast<char *>(slab);
+    StateView s;
+    s.x = reinterpret_cast<double *>(b + off[0]);
+    s.y = reinterpret_cast<double *>(b + off[1]);
+    s.z = reinterpret_cast<float *>(b + off[2]);
+    s.roll = reinterpret_cast<float *>(b + off[3]);
+    s.pitch = reinterpret_cast<float *>(b + off[4]);
+    s.yaw = reinterpret_cast<float *>(b + off[5]);
+    return s;
 }
 
-void free_state(StateView &s)
+int alloc_slab(auvpf_handle *h)
 {
-    cudaFree(s.x);
-    cudaFree(s.y);
-    cudaFree(s.z);
-    cudaFree(s.roll);
-    cudaFree(s.pitch);
-    cudaFree(s.yaw);
+    const size_t n = (size_t)h->N;
+    const size_t sizes[14] = {8 * n, 8 * n, 4 * n, 4 * n, 4 * n, 4 * n, 8 * n, 8 * n, 4 * n, 4 * n, 4 * n, 4 * n,
+                              8 * n, 8 * (size_t)h->tiles_per_filter * h->F};
+    size_t off = 0;
+    for (int k = 0; k < 14; ++k) {
+        h->slab_off[k] = (int64_t)off;
+        off += (sizes[k] + 255) & ~size_t(255);
+    }
+    h->slab_bytes = off;
+    CU(cudaMalloc(&h->slab, off));
+    h->st[0] = state_at(h->slab, h->slab_off);
+    h->st[1] = state_at(h->slab, h->slab_off + 6);
+    h->cdf = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->slab) + h->slab_off[12]);
+    h->status = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->slab) + h->slab_off[13]);
+    return AUVPF_OK;
 }
 
 __global__ void k_reset_scalars(long long *wmax_ordered, unsigned long long *limbs, double *sumsq,
@@ -710,9 +729,9 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
     int rc = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         int rc2;
-        if ((rc2 = alloc_state(h->st[0], h->N)) || (rc2 = alloc_state(h->st[1], h->N))) return rc2;
+        h->tiles_per_filter = (int)((h->M + kScanTile - 1) / kScanTile);
+        if ((rc2 = alloc_slab(h))) return rc2;
         CU(cudaMalloc(&h->logw, sizeof(float) * h->N));
-        CU(cudaMalloc(&h->cdf, sizeof(unsigned long long) * h->N));
         CU(cudaMalloc(&h->wmax_ordered, sizeof(long long) * F));
         CU(cudaMalloc(&h->wmax, sizeof(double) * F));
         CU(cudaMalloc(&h->wmax_f32, sizeof(int) * 2 * F));   // [F] max log-weight | [F] flagged-particle counters
@@ -730,8 +749,6 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         CU(cudaMalloc(&h->gps, sizeof(double) * 2 * F));
         CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F));
         CU(cudaMalloc(&h->degenerate, sizeof(int) * F));
-        h->tiles_per_filter = (int)((h->M + kScanTile - 1) / kScanTile);
-        CU(cudaMalloc(&h->status, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * F));
         CU(cudaMalloc(&h->tile_counter, sizeof(unsigned int)));
         CU(cudaMallocHost(&h->pinned, h->pinned_cap));
         for (int b = 0; b < 2; ++b) {
@@ -773,11 +790,14 @@ int auvpf_destroy(auvpf_handle *h)
     if (!h) return AUVPF_OK;
     Guard g(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    free_state(h->st[0]);
-    free_state(h->st[1]);
-    void *bufs[] = {h->logw,    h->cdf,   h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
+    for (int r = 0; r < h->n_peers; ++r)
+        if (r != h->my_peer && h->peer_slab[r]) cudaIpcCloseMemHandle(h->peer_slab[r]);
+    cudaFree(h->slab);
+    cudaFree(h->shard_meta);
+    cudaFree(h->peer_tables);
+    void *bufs[] = {h->logw,    h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
                     h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
-                    h->status,  h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
+                    h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
                     h->wmax_f32, h->done, h->scan3,
                     h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->probe_flags.p};
     for (void *b : bufs) cudaFree(b);
@@ -1381,6 +1401,110 @@ int auvpf_shard_scan_dev(auvpf_handle *h)
     h->last_src_kind = 0;
     h->wmax_valid = false;      // the maximum in the buffer is not this shard's: recompute next time unless an update refreshes it
     return rc;
+}
+
+// ---- peer-memory exchange (CUDA IPC): one kernel does select + gather + exchange -----------------
+namespace {
+struct IpcBlob {            // what a rank publishes: AUVPF_IPC_BLOB_BYTES
+    cudaIpcMemHandle_t handle;
+    int64_t M, slab_bytes;
+    int64_t off[14];
+    int32_t tiles, device;
+};
+static_assert(sizeof(IpcBlob) <= AUVPF_IPC_BLOB_BYTES, "IpcBlob must fit the ABI's blob size");
+}   // namespace
+
+int auvpf_ipc_export(auvpf_handle *h, void *blob)
+{
+    if (!h || !blob) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (h->F != 1) return fail(AUVPF_ERR_BADARG, "particle sharding is for a single filter (n_filters == 1)");
+    Guard g(h);
+    IpcBlob b{};
+    CU(cudaIpcGetMemHandle(&b.handle, h->slab));
+    b.M = h->M;
+    b.slab_bytes = (int64_t)h->slab_bytes;
+    for (int k = 0; k < 14; ++k) b.off[k] = h->slab_off[k];
+    b.tiles = h->tiles_per_filter;
+    b.device = h->device;
+    memset(blob, 0, AUVPF_IPC_BLOB_BYTES);
+    memcpy(blob, &b, sizeof b);
+    return AUVPF_OK;
+}
+
+int auvpf_ipc_import(auvpf_handle *h, const void *blobs, int32_t n_ranks, int32_t my_rank)
+{
+    if (!h || !blobs) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
+        return fail(AUVPF_ERR_BADARG, "ranks: 1..%d, got %d (my rank %d)", kMaxPeers, n_ranks, my_rank);
+    if (h->n_peers) return fail(AUVPF_ERR_STATE, "peers already imported");
+    Guard g(h);
+    PeerTable tab[2];
+    memset(tab, 0, sizeof tab);
+    for (int r = 0; r < n_ranks; ++r) {
+        IpcBlob b;
+        memcpy(&b, static_cast<const char *>(blobs) + (size_t)r * AUVPF_IPC_BLOB_BYTES, sizeof b);
+        if (b.M != h->M || b.tiles != h->tiles_per_filter)
+            return fail(AUVPF_ERR_BADARG, "rank %d holds %lld particles, this rank %lld", r, (long long)b.M, (long long)h->M);
+        void *base = h->slab;
+        if (r != my_rank) {
+            if (b.device != h->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, h->device, b.device));
+                if (!can) return fail(AUVPF_ERR_CUDA, "device %d cannot access device %d's memory", h->device, b.device);
+            }
+            CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
+        }
+        h->peer_slab[r] = base;
+        char *c = static_cast<char *>(base);
+        for (int buf = 0; buf < 2; ++buf) {
+            tab[buf].cdf[r] = reinterpret_cast<unsigned long long *>(c + b.off[12]);
+            tab[buf].status[r] = reinterpret_cast<unsigned long long *>(c + b.off[13]);
+            tab[buf].st[r] = state_at(base, b.off + 6 * buf);
+            tab[buf].G = n_ranks;
+        }
+    }
+    h->n_peers = n_ranks;
+    h->my_peer = my_rank;
+    CU(cudaMalloc(&h->peer_tables, sizeof tab));
+    CU(cudaMemcpy(h->peer_tables, tab, sizeof tab, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&h->shard_meta, sizeof(unsigned long long) * (n_ranks + 2)));
+    return AUVPF_OK;
+}
+
+int auvpf_shard_gather_p2p(auvpf_handle *h, double u, const int64_t *q_all_dev, const double *rough_var,
+                           const float *rough_noise, int64_t *ancestors_out_dev)
+{
+    if (!h || !q_all_dev) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!h->n_peers) return fail(AUVPF_ERR_STATE, "auvpf_ipc_import first");
+    Guard g(h);
+    int rc;
+    const float *rn = nullptr;
+    if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
+    NoiseParams rough = make_noise(h, rough_var, nullptr, rough_var ? 1 : 0, h->step_rough, kStreamRoughen);
+    {
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        k_shard_meta<<<1, 32, 0, h->stream>>>(reinterpret_cast<const long long *>(q_all_dev), h->n_peers, h->shard_meta);
+        k_select_gather_p2p<<<grid1(h->M, kSelTile, 1), kSelThreads, 0, h->stream>>>(
+            h->peer_tables + h->cur, h->M, h->my_peer, h->tiles_per_filter, u, h->shard_meta, h->st[1 - h->cur],
+            ancestors_out_dev, rough, rn);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 2);
+        CU(cudaGetLastError());
+    }
+    h->cur = 1 - h->cur;
+    if (rough_var) h->step_rough++;
+    return AUVPF_OK;
+}
+
+int auvpf_shard_degenerate(auvpf_handle *h, int32_t *flag)
+{
+    if (!h || !flag) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!h->n_peers) return fail(AUVPF_ERR_STATE, "auvpf_ipc_import first");
+    Guard g(h);
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, h->shard_meta + h->n_peers + 1, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *flag = v ? 1 : 0;
+    return AUVPF_OK;
 }
 
 int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t deficit, int64_t out_lo, int64_t out_hi,

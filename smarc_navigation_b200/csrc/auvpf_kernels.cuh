@@ -1194,6 +1194,224 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Particle-sharded filter: select + gather + exchange in ONE kernel over NVLink peer memory.
+// Every rank maps the other ranks' slabs (state, integer CDF, scan tile table) through CUDA IPC.
+// Output slot i of rank r finds its ancestor in the GLOBAL CDF -- the concatenation of the shards'
+// CDFs, each shifted by the integer mass of the shards before it -- by reading the owners' tile
+// tables and CDF tiles directly, then loads the ancestor's state from its owner's memory and writes
+// its own new state: no records, no all-to-all, no host in the loop.  (Ancestors are globally
+// sorted, so a block's reads are contiguous runs in at most a few shards.)
+constexpr int kMaxPeers = 8;
+
+struct PeerTable {
+    const unsigned long long *cdf[kMaxPeers];
+    const unsigned long long *status[kMaxPeers];
+    StateView st[kMaxPeers];            // the buffer that is CURRENT (source of the gather) on each rank
+    int G;
+};
+
+// meta[0..G) = integer CDF mass below shard g, meta[G] = deficit D, meta[G+1] = 1 if no shard has weight
+__global__ void k_shard_meta(const long long *q_all, int G, unsigned long long *meta)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    unsigned long long acc = 0;
+    for (int g = 0; g < G; ++g) {
+        meta[g] = acc;
+        acc += (unsigned long long)q_all[g];
+    }
+    meta[G] = (1ull << kQBits) - acc;
+    meta[G + 1] = acc == 0 ? 1ull : 0ull;
+}
+
+struct GlobalCdf {
+    const PeerTable *pt;
+    const unsigned long long *meta;
+    int64_t M;
+    unsigned long long D;
+    __device__ __forceinline__ unsigned long long at(int64_t J) const
+    {
+        int g = (int)(J / M);
+        const int64_t j = J - (int64_t)g * M;
+        const unsigned long long J1 = (unsigned long long)(J + 1);
+        return meta[g] + pt->cdf[g][j] + (J1 < D ? J1 : D);
+    }
+};
+
+__global__ void __launch_bounds__(kSelThreads, 4)
+k_select_gather_p2p(const PeerTable *__restrict__ pt, int64_t M, int rank, int tiles, double u,
+                    const unsigned long long *__restrict__ meta, StateView dst, int64_t *anc64, NoiseParams rough,
+                    const float *rough_noise)
+{
+    __shared__ unsigned long long s_cdf[kSelSpan];
+    __shared__ int64_t s_j[2];
+    const int G = pt->G;
+    const int64_t n_global = M * G;
+    const double n = (double)n_global;
+    const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
+    if (k0 >= M) return;
+    const int64_t k1 = min(k0 + (int64_t)kSelTile, M) - 1;
+    const int64_t out_lo = (int64_t)rank * M;
+    if (meta[G + 1]) {            // no finite weight on any shard: the state is carried over unchanged
+        const StateView own = pt->st[rank];
+        for (int64_t k = k0 + threadIdx.x; k <= k1; k += kSelThreads) {
+            dst.x[k] = own.x[k];
+            dst.y[k] = own.y[k];
+            dst.z[k] = own.z[k];
+            dst.roll[k] = own.roll[k];
+            dst.pitch[k] = own.pitch[k];
+            dst.yaw[k] = own.yaw[k];
+        }
+        return;
+    }
+    GlobalCdf gc;
+    gc.pt = pt;
+    gc.meta = meta;
+    gc.M = M;
+    gc.D = meta[G];
+    const unsigned long long D = gc.D;
+    const unsigned long long key_lo = pos_key(sys_position(u, out_lo + k0, n)),
+                             key_hi = pos_key(sys_position(u, out_lo + k1, n));
+    // level 1: the global tile table (G x tiles entries, read from the owners)
+    const int n_tiles = G * tiles;
+    int T_lo = 0, T_hi = 0;
+    for (int T0 = 0; T0 < n_tiles; T0 += kSelThreads) {
+        const int T = T0 + threadIdx.x;
+        bool below_lo = false, below_hi = false;
+        if (T < n_tiles) {
+            const int g = T / tiles, t = T - g * tiles;
+            const int64_t je = min((int64_t)(t + 1) * kScanTile, M) - 1;
+            const unsigned long long J1 = (unsigned long long)((int64_t)g * M + je + 1);
+            const unsigned long long c = meta[g] + (pt->status[g][t] & kValMask) + (J1 < D ? J1 : D);
+            below_lo = !(key_lo < c);
+            below_hi = !(key_hi < c);
+        }
+        const int c_lo = __syncthreads_count(below_lo), c_hi = __syncthreads_count(below_hi);
+        T_lo += c_lo;
+        T_hi += c_hi;
+        if (c_hi < kSelThreads) break;
+    }
+    T_lo = min(T_lo, n_tiles - 1);
+    T_hi = min(T_hi, n_tiles - 1);
+    int64_t J_lo = (int64_t)(T_lo / tiles) * M + (int64_t)(T_lo % tiles) * kScanTile;
+    int64_t J_hi = (int64_t)(T_hi / tiles) * M + min((int64_t)(T_hi % tiles + 1) * kScanTile, M) - 1;
+    if (J_hi - J_lo + 1 > kSelSpan) {
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            const unsigned long long key = threadIdx.x == 0 ? key_lo : key_hi;
+            int64_t lo = J_lo, hi = J_hi + 1;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (key < gc.at(mid)) hi = mid;
+                else lo = mid + 1;
+            }
+            s_j[threadIdx.x == 0 ? 0 : 1] = lo;
+        }
+        __syncthreads();
+        J_lo = min(s_j[0], n_global - 1);
+        J_hi = min(s_j[1], n_global - 1);
+    }
+    const int64_t span = J_hi - J_lo + 1;
+    const bool staged = span <= kSelSpan;
+    if (staged)
+        for (int64_t t = threadIdx.x; t < span; t += kSelThreads) s_cdf[t] = gc.at(J_lo + t);
+    __syncthreads();
+
+    const int64_t kb = k0 + (int64_t)threadIdx.x * kSelItems;
+    if (kb > k1) return;
+    int64_t JJ[kSelItems];
+    {
+        int64_t prev = 0;
+#pragma unroll
+        for (int r = 0; r < kSelItems; ++r) {
+            const int64_t k = kb + r;
+            if (k > k1) {
+                JJ[r] = 0;
+                continue;
+            }
+            const unsigned long long key = pos_key(sys_position(u, out_lo + k, n));
+            int64_t J;
+            if (staged) {
+                int lo = (int)prev, hi = (int)span;
+                if (r > 0) {
+                    int w = 0;
+                    while (w < 4 && lo < hi && !(key < s_cdf[lo])) {
+                        ++lo;
+                        ++w;
+                    }
+                    if (lo < hi && key < s_cdf[lo]) hi = lo;
+                }
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (key < s_cdf[mid]) hi = mid;
+                    else lo = mid + 1;
+                }
+                prev = lo;
+                J = J_lo + lo;
+            } else {
+                int64_t lo = J_lo + prev, hi = J_hi + 1;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (key < gc.at(mid)) hi = mid;
+                    else lo = mid + 1;
+                }
+                J = lo;
+                prev = J - J_lo;
+            }
+            JJ[r] = min(J, n_global - 1);
+        }
+    }
+    const bool full4 = kb + kSelItems - 1 <= k1;
+    double x[kSelItems], y[kSelItems];
+    float z[kSelItems], ro[kSelItems], pi[kSelItems], ya[kSelItems];
+#pragma unroll
+    for (int r = 0; r < kSelItems; ++r) {
+        const int g = (int)(JJ[r] / M);
+        const int64_t j = JJ[r] - (int64_t)g * M;
+        const StateView src = pt->st[g];                 // the owner's memory: local or over NVLink
+        x[r] = src.x[j];
+        y[r] = src.y[j];
+        z[r] = src.z[j];
+        ro[r] = src.roll[j];
+        pi[r] = src.pitch[j];
+        ya[r] = src.yaw[j];
+    }
+    if (anc64)
+        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) anc64[kb + r] = JJ[r];
+    if (rough.mode == 1) {
+#pragma unroll
+        for (int r = 0; r < kSelItems; ++r) {
+            if (kb + r > k1) break;
+            float nn[6];
+            six_normals(rough, out_lo + kb + r, rough_noise, kb + r, nn);
+            x[r] += (double)(rough.sigma[0] * nn[0]);
+            y[r] += (double)(rough.sigma[1] * nn[1]);
+            z[r] += rough.sigma[2] * nn[2];
+            ro[r] += rough.sigma[3] * nn[3];
+            pi[r] += rough.sigma[4] * nn[4];
+            ya[r] += rough.sigma[5] * nn[5];
+        }
+    }
+    if (full4 && (kb & 3) == 0) {
+        *reinterpret_cast<double2 *>(dst.x + kb) = make_double2(x[0], x[1]);
+        *reinterpret_cast<double2 *>(dst.x + kb + 2) = make_double2(x[2], x[3]);
+        *reinterpret_cast<double2 *>(dst.y + kb) = make_double2(y[0], y[1]);
+        *reinterpret_cast<double2 *>(dst.y + kb + 2) = make_double2(y[2], y[3]);
+        *reinterpret_cast<float4 *>(dst.z + kb) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<float4 *>(dst.roll + kb) = make_float4(ro[0], ro[1], ro[2], ro[3]);
+        *reinterpret_cast<float4 *>(dst.pitch + kb) = make_float4(pi[0], pi[1], pi[2], pi[3]);
+        *reinterpret_cast<float4 *>(dst.yaw + kb) = make_float4(ya[0], ya[1], ya[2], ya[3]);
+    } else {
+        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) {
+            dst.x[kb + r] = x[r];
+            dst.y[kb + r] = y[r];
+            dst.z[kb + r] = z[r];
+            dst.roll[kb + r] = ro[r];
+            dst.pitch[kb + r] = pi[r];
+            dst.yaw[kb + r] = ya[r];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // residual_resample (a6, resampling.py:27-76) on the fixed-point weights w_i = q_i 2^-52.
 // q_i is recovered from the integer CDF the scan left behind (+ the deficit unit).
 __device__ __forceinline__ unsigned long long q_from_cdf(const unsigned long long *cdf, int64_t base, int64_t i,

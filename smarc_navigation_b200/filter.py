@@ -190,15 +190,21 @@ class ParticleFilter(object):
     def predict(self, odom_t, dt=None, noise=None):
         """``dt`` defaults to ``self.time - self.old_time`` like the reference
         (:214) when the caller maintains those, else must be given (or carried by
-        the odom object).  ``odom_t`` may be a list of F odoms (one per filter)."""
+        the odom object).  ``odom_t`` may be a list of F odoms (one per filter), or an ``(F, 11)``
+        float64 array of ready-made ABI rows ``[vx vy vz wz qx qy qz qw z dt 0]``."""
         if dt is None and self.time is not None and self.old_time is not None:
             dt = self.time - self.old_time
-        many = isinstance(odom_t, (list, tuple)) and len(odom_t) == self.n_filters and self.n_filters > 1 \
-            and not np.isscalar(odom_t[1])
-        rows = [_odom_row(o, dt) for o in odom_t] if many else [_odom_row(odom_t, dt)]
-        if any(r[9] is None for r in rows):
-            raise ValueError("predict needs dt")
-        od = np.ascontiguousarray(rows, np.float64)
+        if isinstance(odom_t, np.ndarray) and odom_t.ndim == 2 and odom_t.shape[1] == 11:
+            od = np.ascontiguousarray(odom_t, np.float64)         # ready-made (F, 11) / (1, 11) rows of the C ABI
+            if od.shape[0] not in (1, self.n_filters):
+                raise ValueError("odometry rows: 1 or n_filters")
+        else:
+            many = isinstance(odom_t, (list, tuple)) and len(odom_t) == self.n_filters and self.n_filters > 1 \
+                and not np.isscalar(odom_t[1])
+            rows = [_odom_row(o, dt) for o in odom_t] if many else [_odom_row(odom_t, dt)]
+            if any(r[9] is None for r in rows):
+                raise ValueError("predict needs dt")
+            od = np.ascontiguousarray(rows, np.float64)
         nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(self.n_rows, 6)
         with self._lock:
             _lib.check(self._lib.auvpf_predict(self._h, _ptr(od), od.shape[0], _ptr(nz)))

@@ -151,6 +151,27 @@ def resample_sharded_device(ops, dist, u, group=None, rough_var=None):
     return dict(Q_all=Q_all, D=D, bounds=bounds, send=send_counts, recv=recv_counts)
 
 
+def resample_sharded_p2p(ops, dist, u, group=None, rough_var=None):
+    """Sharded resample with NO host synchronisation: the three scalar collectives run in place on
+    the library's device buffers, and ONE kernel then selects this rank's ancestors in the global
+    CDF and gathers their state straight from the owners' memory over NVLink (CUDA IPC peer
+    mappings set up by ``GpuShardOps.connect``).  Returns nothing the host would have to wait for."""
+    import torch
+    L, h = ops.L, ops.pf._h
+    with torch.cuda.stream(ops.stream):
+        ops._lib.check(L.auvpf_shard_max_dev(h))
+        dist.all_reduce(ops.t_wmax, op=dist.ReduceOp.MAX, group=group)          # order-preserving int32 == float max
+        ops._lib.check(L.auvpf_shard_sum_dev(h))
+        dist.all_reduce(ops.t_limbs, op=dist.ReduceOp.SUM, group=group)         # exact integer limbs of A
+        ops._lib.check(L.auvpf_shard_scan_dev(h))
+        # this all-gather is also the cross-GPU barrier that makes every shard's CDF and tile table
+        # complete before any rank reads them
+        dist.all_gather_into_tensor(ops.t_qall, ops.t_q, group=group)
+        rv = None if rough_var is None else (C.c_double * 6)(*rough_var)
+        ops._lib.check(L.auvpf_shard_gather_p2p(h, u, C.c_void_p(ops.t_qall.data_ptr()), rv, None, None))
+    return {}
+
+
 class GpuShardOps(object):
     """Per-shard stages on the GPU through the C ABI (auvpf_shard_*)."""
 
@@ -172,6 +193,7 @@ class GpuShardOps(object):
         self.t_q = torch.as_tensor(_DeviceArray(pq.value, (1,), "<i8"), device=self.device)
         self.t_qall = None
         self.send_buf = self.recv_buf = None
+        self.p2p = False
 
     def prepare(self, world_size):
         if self.t_qall is None:
@@ -179,6 +201,26 @@ class GpuShardOps(object):
             self.t_qall = t.zeros(world_size, dtype=t.int64, device=self.device)
             self.send_buf = t.empty((2 * self.M, 4), dtype=t.float64, device=self.device)
             self.recv_buf = t.empty((self.M, 4), dtype=t.float64, device=self.device)
+
+    def connect(self, dist, group=None):
+        """Exchange CUDA IPC handles of the state / CDF slabs and map the peers' memory."""
+        t = self.torch
+        G, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.prepare(G)
+        blob = (C.c_ubyte * self._lib.IPC_BLOB_BYTES)()
+        self._lib.check(self.L.auvpf_ipc_export(self.pf._h, blob))
+        mine = t.tensor(list(bytes(blob)), dtype=t.uint8, device=self.device)
+        everyone = t.empty(G * self._lib.IPC_BLOB_BYTES, dtype=t.uint8, device=self.device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        raw = bytes(everyone.cpu().numpy().tobytes())
+        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+        self._lib.check(self.L.auvpf_ipc_import(self.pf._h, buf, G, rank))
+        self.p2p = True
+
+    def degenerate(self):
+        flag = C.c_int32(0)
+        self._lib.check(self.L.auvpf_shard_degenerate(self.pf._h, C.byref(flag)))
+        return bool(flag.value)
 
     def send_records(self, n_out):
         """(n_out, 4) float64 = n_out 32-byte records; grows when this shard's particles own more than
@@ -223,7 +265,9 @@ class ShardedParticleFilter(object):
     """``ParticleFilter`` over G ranks: same predict/update/resample methods; every rank
     calls them collectively with the same arguments."""
 
-    def __init__(self, particles_per_rank, dist, group=None, **kw):
+    def __init__(self, particles_per_rank, dist, group=None, exchange="p2p", **kw):
+        """``exchange``: "p2p" (default; one kernel over CUDA-IPC peer memory, up to 8 ranks of one
+        node) or "nccl" (records + ``all_to_all_single``; any topology NCCL supports)."""
         import torch
         from .filter import ParticleFilter
         self.dist, self.group = dist, group
@@ -233,6 +277,10 @@ class ShardedParticleFilter(object):
         kw.setdefault("device", torch.cuda.current_device())
         self.pf = ParticleFilter(particle_count=self.M, global_offset=self.rank * self.M, global_count=self.N, **kw)
         self.ops = GpuShardOps(self.pf)
+        if exchange == "p2p":
+            self.ops.connect(dist, group)
+        elif exchange != "nccl":
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
         self._step = 0
         self._seed = int(kw.get("seed", 0))
 
@@ -248,14 +296,19 @@ class ShardedParticleFilter(object):
     def update_mbes(self, ranges):
         self.pf.update_mbes(ranges, return_weights=False)
 
-    def resample(self, u=None, roughen=True):
+    def resample(self, u=None, roughen=True, check=False):
         if u is None:      # same Philox-derived uniform on every rank, no communication
             from .rng import resample_uniform
             u = resample_uniform(self._seed, 0, self._step)
         self._step += 1
         self.ops.prepare(self.G)
-        return resample_sharded_device(self.ops, self.dist, float(u), self.group,
-                                       rough_var=self.pf.res_noise_cov if roughen else None)
+        rv = self.pf.res_noise_cov if roughen else None
+        if self.ops.p2p:
+            plan = resample_sharded_p2p(self.ops, self.dist, float(u), self.group, rough_var=rv)
+            if check and self.ops.degenerate():
+                raise FloatingPointError("degenerate weights on every shard")
+            return plan
+        return resample_sharded_device(self.ops, self.dist, float(u), self.group, rough_var=rv)
 
     def mean_cov(self):
         import torch

@@ -27,7 +27,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, M, seed, tmp):
+def _worker(rank, world, port, M, seed, tmp, exchange):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -45,29 +45,45 @@ def _worker(rank, world, port, M, seed, tmp):
     poses[:, 1] = -0.25 * np.arange(N)
     poses[:, 5] = rng.uniform(-3, 3, N).astype(np.float32)
     u = float(rng.uniform())
-    sp = ShardedParticleFilter(M, dist, device=rank, seed=seed, resampling_noise_covariance=[0.0] * 6)
+    sp = ShardedParticleFilter(M, dist, device=rank, seed=seed, resampling_noise_covariance=[0.0] * 6,
+                               exchange=exchange)
     sp.pf.set_poses(poses[rank * M:(rank + 1) * M])
     sp.pf.set_log_weights(logw[rank * M:(rank + 1) * M])
-    plan = sp.resample(u=u, roughen=False)
+    sp.resample(u=u, roughen=False, check=True)
     got = sp.poses()
     mean, cov = sp.mean_cov()
-    np.savez(os.path.join(tmp, "r%d.npz" % rank), poses=got, bounds=np.array(plan["bounds"]), u=u, logw=logw,
-             all_poses=poses, mean=mean, cov=cov)
+    # a second cycle on the new state: the double buffers and the peers' views flip together
+    logw2 = (np.random.default_rng(seed + 100).normal(0, 2.0, N) - 50).astype(np.float32)
+    sp.pf.set_log_weights(logw2[rank * M:(rank + 1) * M])
+    u2 = 0.618
+    sp.resample(u=u2, roughen=False)
+    got2 = sp.poses()
+    # degenerate weights on every shard: state carried over, flag raised
+    sp.pf.set_log_weights(np.full(M, -np.inf, np.float32))
+    deg = False
+    try:
+        sp.resample(u=0.5, roughen=False, check=True)
+    except FloatingPointError:
+        deg = True
+    got3 = sp.poses()
+    np.savez(os.path.join(tmp, "r%d.npz" % rank), poses=got, poses2=got2, poses3=got3, deg=deg, u=u, logw=logw,
+             logw2=logw2, u2=u2, all_poses=poses, mean=mean, cov=cov)
     sp.close()
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("M,seed", [(4096, 0), (100000, 1), (1 << 20, 2)])
-def test_sharded_resample_on_gpus(tmp_path, M, seed):
+def test_sharded_resample_on_gpus(tmp_path, M, seed, exchange):
     world = min(_n_gpus(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
     import torch.multiprocessing as mp
     from oracle import c_oracle, pf_oracle as o
     from smarc_navigation_b200 import ParticleFilter
-    mp.spawn(_worker, args=(world, _free_port(), M, seed, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), M, seed, str(tmp_path), exchange), nprocs=world, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "r%d.npz" % r)) for r in range(world)]
     logw, u, poses = parts[0]["logw"], float(parts[0]["u"]), parts[0]["all_poses"]
     N = M * world
@@ -86,6 +102,13 @@ def test_sharded_resample_on_gpus(tmp_path, M, seed):
     m1, c1 = pf.mean_cov()
     np.testing.assert_allclose(parts[0]["mean"][:3], m1[0, :3], rtol=1e-9, atol=1e-6)
     np.testing.assert_allclose(parts[0]["cov"], c1[0], rtol=1e-6, atol=1e-6)
+    # second cycle
+    logw2, u2 = parts[0]["logw2"], float(parts[0]["u2"])
+    anc2 = c_oracle.systematic(o.weights_from_q(c_oracle.quantise_logw(logw2)[0]), u2)
+    got2 = np.concatenate([p["poses2"] for p in parts])
+    np.testing.assert_array_equal(got2[:, 0], got[anc2, 0])
+    np.testing.assert_array_equal(got2[:, 5], got[anc2, 5])
+    # degenerate cycle: flagged on every rank, state untouched
+    assert all(bool(p["deg"]) for p in parts)
+    np.testing.assert_array_equal(np.concatenate([p["poses3"] for p in parts]), got2)
     pf.close()
-    b = parts[0]["bounds"]
-    assert b[0] == 0 and b[-1] == N and np.all(np.diff(b) >= 0)
