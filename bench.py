@@ -264,9 +264,7 @@ def run_ours(args):
     L = _lib.load()
 
     def cycle_device(s):
-        odoms = cycles[s][0]
-        for od in odoms:
-            filt.predict(od)
+        filt.predict_many(cycles[s][0])            # the 5 odometry messages between two pings, one pass over the state
         _lib.check(L.auvpf_update_mbes(pf._h, C.c_void_p(pings_dev[s].data_ptr()), None))
         filt.resample()
 
@@ -314,16 +312,14 @@ def run_ours(args):
     # ---- end to end through the public API, host buffers ----------------------------------------
     base = W + K
     for s in range(base, base + W):
-        for od in cycles[s][0]:
-            filt.predict(od)
+        filt.predict_many(cycles[s][0])
         filt.update_mbes(pings_pin[s].numpy()) if (G > 1 and F == 1) else pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
         filt.resample()
         filt.mean_cov()
     barrier()
     t0 = time.perf_counter()
     for s in range(base + W, base + W + K):
-        for od in cycles[s][0]:
-            filt.predict(od)
+        filt.predict_many(cycles[s][0])
         if G > 1 and F == 1:
             filt.update_mbes(pings_pin[s].numpy())
         else:
@@ -353,6 +349,7 @@ def run_ours(args):
     alg_rs = M * F * RS_BYTES                                   # normalise 4 + scan 12 + select 12 + gather 4+32+32
     ach_rs = alg_rs / (rs_ms / rs_n * 1e-3) / 1e9 if rs_ms > 0 else 0.0
     prop_ms, prop_n = prof["propagate"]
+    # one launch runs the P predicts of a cycle in registers: algorithmic traffic = one read (x, y, yaw) + one write
     ach_prop = M * F * 52 / (prop_ms / max(prop_n, 1) * 1e-3) / 1e9 if prop_n else 0.0
     launches = int(sum(v[1] for v in prof.values()))
 

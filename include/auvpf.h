@@ -131,6 +131,11 @@ int auvpf_set_logw(auvpf_handle *h, const float *logw);      /* (F*M)    */
  * row to every filter.  noise: (F*M, 6) float32 normals (columns 0, 1, 5 are
  * consumed, like the reference) or NULL for Philox. */
 int auvpf_predict(auvpf_handle *h, const double *odom, int32_t n_odom, const float *noise);
+/* n_steps consecutive predicts (the odometry messages queued between two pings) in one pass
+ * over the state: odom is (n_steps, n_odom, 11), noise (n_steps, F*M, 6) or NULL.  Bit-identical
+ * to n_steps calls of auvpf_predict. */
+#define AUVPF_MAX_PREDICT_STEPS 16
+int auvpf_predict_many(auvpf_handle *h, const double *odom, int32_t n_steps, int32_t n_odom, const float *noise);
 
 /* -- update ----------------------------------------------------------------- */
 /* auv_pf.update (auv_pf.py:135-167) -> Particle.compute_weight

@@ -55,6 +55,7 @@ SYMBOLS = [
     ("auvpf_get_logw", C.c_int, [_vp, _vp]),
     ("auvpf_set_logw", C.c_int, [_vp, _vp]),
     ("auvpf_predict", C.c_int, [_vp, _vp, _i32, _vp]),
+    ("auvpf_predict_many", C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     ("auvpf_update_gps", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_update_mbes", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_raycast", C.c_int, [_vp, _vp, _i64, _vp]),

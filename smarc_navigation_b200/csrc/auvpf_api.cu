@@ -747,7 +747,7 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         CU(cudaMalloc(&h->sums, sizeof(double) * 16 * F));
         h->mom = h->sums + 8 * F;
         CU(cudaMalloc(&h->gps, sizeof(double) * 2 * F));
-        CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F));
+        CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F * AUVPF_MAX_PREDICT_STEPS));
         CU(cudaMalloc(&h->degenerate, sizeof(int) * F));
         CU(cudaMalloc(&h->tile_counter, sizeof(unsigned int)));
         CU(cudaMallocHost(&h->pinned, h->pinned_cap));
@@ -1090,29 +1090,40 @@ int auvpf_set_logw(auvpf_handle *h, const float *logw)
 }
 
 // ------------------------------------------------------------------------------------------------
-int auvpf_predict(auvpf_handle *h, const double *odom, int32_t n_odom, const float *noise)
+int auvpf_predict_many(auvpf_handle *h, const double *odom, int32_t n_steps, int32_t n_odom, const float *noise)
 {
     if (!h || !odom) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (n_steps < 1 || n_steps > AUVPF_MAX_PREDICT_STEPS)
+        return fail(AUVPF_ERR_BADARG, "n_steps must be 1..%d", AUVPF_MAX_PREDICT_STEPS);
     if (n_odom != 1 && n_odom != h->F) return fail(AUVPF_ERR_BADARG, "n_odom must be 1 or n_filters");
-    if (is_device_ptr(odom)) return fail(AUVPF_ERR_BADARG, "odom must be host memory (11 scalars per filter)");
+    if (is_device_ptr(odom)) return fail(AUVPF_ERR_BADARG, "odom must be host memory (11 scalars per filter and step)");
     Guard g(h);
     int rc;
     const float *nd = nullptr;
-    if (noise && (rc = stage_in(h, S_IN0, noise, (size_t)h->N * 6, &nd))) return rc;
+    if (noise && (rc = stage_in(h, S_IN0, noise, (size_t)h->N * 6 * n_steps, &nd))) return rc;
     PredictParams p0 = make_predict(odom, h->cfg.motion_cov);
     const PredictParams *pp = nullptr;
-    if (n_odom > 1) {
-        std::vector<PredictParams> all(h->F);
-        for (int f = 0; f < h->F; ++f) all[f] = make_predict(odom + 11 * f, h->cfg.motion_cov);
-        if ((rc = tiny_upload(h, h->pparams, all.data(), sizeof(PredictParams) * h->F))) return rc;
+    if (n_odom > 1 || n_steps > 1) {
+        std::vector<PredictParams> all((size_t)h->F * n_steps);
+        for (int t = 0; t < n_steps; ++t)
+            for (int f = 0; f < h->F; ++f)
+                all[(size_t)t * h->F + f] =
+                    make_predict(odom + 11 * ((size_t)t * n_odom + (n_odom > 1 ? f : 0)), h->cfg.motion_cov);
+        if ((rc = tiny_upload(h, h->pparams, all.data(), sizeof(PredictParams) * all.size()))) return rc;
         pp = h->pparams;
     }
     Prof pr(h, AUVPF_K_PROPAGATE);
     k_propagate<<<grid1(h->M, kThreads * 4, h->F), kThreads, 0, h->stream>>>(
-        h->st[h->cur], h->M, p0, pp, h->cfg.seed, h->step_predict++, h->global_offset, h->global_count, nd);
+        h->st[h->cur], h->M, p0, pp, n_steps, h->cfg.seed, h->step_predict, h->global_offset, h->global_count, nd);
+    h->step_predict += (uint32_t)n_steps;
     LAUNCHED(h, AUVPF_K_PROPAGATE, 1);
     CU(cudaGetLastError());
     return AUVPF_OK;
+}
+
+int auvpf_predict(auvpf_handle *h, const double *odom, int32_t n_odom, const float *noise)
+{
+    return auvpf_predict_many(h, odom, 1, n_odom, noise);
 }
 
 int auvpf_update_gps(auvpf_handle *h, const double *gps_xy, float *logw_out)

@@ -150,16 +150,19 @@ __device__ __forceinline__ void predict_normals(uint64_t seed, int64_t gid, uint
     }
 }
 
+// n_steps > 1 runs that many consecutive predicts in ONE pass over the state (the 50 Hz odometry
+// messages between two pings): same arithmetic and RNG counters as n_steps separate launches, the
+// state is read and written once.  params: (n_steps, F) rows, or nullptr for one broadcast odom (p0).
 __global__ void __launch_bounds__(kThreads)
-k_propagate(StateView s, int64_t M, PredictParams p0, const PredictParams *params, uint64_t seed, uint32_t step, int64_t global_offset,
-            int64_t global_stride, const float *noise)
+k_propagate(StateView s, int64_t M, PredictParams p0, const PredictParams *params, int n_steps, uint64_t seed,
+            uint32_t step, int64_t global_offset, int64_t global_stride, const float *noise)
 {
-    const int f = blockIdx.y;
-    const PredictParams p = params ? params[f] : p0;   // one odom broadcast to all filters travels by value
+    const int f = blockIdx.y, F = gridDim.y;
     const int64_t base = (int64_t)f * M;
     const int64_t i0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
     if (i0 >= M) return;
     const int64_t gid0 = (int64_t)f * global_stride + global_offset + i0;
+    const int64_t noise_stride = (int64_t)F * M * 6;
     if (i0 + 3 < M && ((base + i0) & 3) == 0) {
         double2 xa = *reinterpret_cast<const double2 *>(s.x + base + i0);
         double2 xb = *reinterpret_cast<const double2 *>(s.x + base + i0 + 2);
@@ -168,29 +171,37 @@ k_propagate(StateView s, int64_t M, PredictParams p0, const PredictParams *param
         float4 yw = *reinterpret_cast<const float4 *>(s.yaw + base + i0);
         double x[4] = {xa.x, xa.y, xb.x, xb.y}, y[4] = {ya.x, ya.y, yb.x, yb.y};
         float w[4] = {yw.x, yw.y, yw.z, yw.w};
-        float z, r, pt;
+        float z = 0.f, r = 0.f, pt = 0.f;
+        for (int t = 0; t < n_steps; ++t) {
+            const PredictParams p = params ? params[(int64_t)t * F + f] : p0;
+            const float *nz = noise ? noise + t * noise_stride : nullptr;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float n0, n1, n5;
-            predict_normals(seed, gid0 + k, step, noise, base + i0 + k, n0, n1, n5);
-            propagate_one(p, x[k], y[k], z, r, pt, w[k], n0, n1, n5);
+            for (int k = 0; k < 4; ++k) {
+                float n0, n1, n5;
+                predict_normals(seed, gid0 + k, step + t, nz, base + i0 + k, n0, n1, n5);
+                propagate_one(p, x[k], y[k], z, r, pt, w[k], n0, n1, n5);
+            }
         }
         *reinterpret_cast<double2 *>(s.x + base + i0) = make_double2(x[0], x[1]);
         *reinterpret_cast<double2 *>(s.x + base + i0 + 2) = make_double2(x[2], x[3]);
         *reinterpret_cast<double2 *>(s.y + base + i0) = make_double2(y[0], y[1]);
         *reinterpret_cast<double2 *>(s.y + base + i0 + 2) = make_double2(y[2], y[3]);
         *reinterpret_cast<float4 *>(s.yaw + base + i0) = make_float4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<float4 *>(s.z + base + i0) = make_float4(p.z, p.z, p.z, p.z);
-        *reinterpret_cast<float4 *>(s.roll + base + i0) = make_float4(p.roll, p.roll, p.roll, p.roll);
-        *reinterpret_cast<float4 *>(s.pitch + base + i0) = make_float4(p.pitch, p.pitch, p.pitch, p.pitch);
+        *reinterpret_cast<float4 *>(s.z + base + i0) = make_float4(z, z, z, z);
+        *reinterpret_cast<float4 *>(s.roll + base + i0) = make_float4(r, r, r, r);
+        *reinterpret_cast<float4 *>(s.pitch + base + i0) = make_float4(pt, pt, pt, pt);
     } else {
         for (int k = 0; k < 4 && i0 + k < M; ++k) {
             int64_t row = base + i0 + k;
             double x = s.x[row], y = s.y[row];
-            float z, r, pt, w = s.yaw[row];
-            float n0, n1, n5;
-            predict_normals(seed, gid0 + k, step, noise, row, n0, n1, n5);
-            propagate_one(p, x, y, z, r, pt, w, n0, n1, n5);
+            float z = 0.f, r = 0.f, pt = 0.f, w = s.yaw[row];
+            for (int t = 0; t < n_steps; ++t) {
+                const PredictParams p = params ? params[(int64_t)t * F + f] : p0;
+                const float *nz = noise ? noise + t * noise_stride : nullptr;
+                float n0, n1, n5;
+                predict_normals(seed, gid0 + k, step + t, nz, row, n0, n1, n5);
+                propagate_one(p, x, y, z, r, pt, w, n0, n1, n5);
+            }
             s.x[row] = x;
             s.y[row] = y;
             s.z[row] = z;

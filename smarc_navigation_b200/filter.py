@@ -209,6 +209,31 @@ class ParticleFilter(object):
         with self._lock:
             _lib.check(self._lib.auvpf_predict(self._h, _ptr(od), od.shape[0], _ptr(nz)))
 
+    def predict_many(self, odoms, dt=None, noise=None):
+        """Several consecutive ``predict`` calls (the odometry messages queued between two pings) in
+        ONE pass over the particle state; bit-identical to calling ``predict`` for each.  ``odoms``:
+        a list of what ``predict`` accepts, or an ``(n_steps, F or 1, 11)`` array of ABI rows."""
+        if isinstance(odoms, np.ndarray) and odoms.ndim == 3 and odoms.shape[2] == 11:
+            od = np.ascontiguousarray(odoms, np.float64)
+        else:
+            steps = []
+            for o in odoms:
+                if isinstance(o, np.ndarray) and o.ndim == 2 and o.shape[1] == 11:
+                    steps.append(np.asarray(o, np.float64))
+                else:
+                    many = isinstance(o, (list, tuple)) and len(o) == self.n_filters and self.n_filters > 1 \
+                        and not np.isscalar(o[1])
+                    rows = [_odom_row(x, dt) for x in o] if many else [_odom_row(o, dt)]
+                    if any(r[9] is None for r in rows):
+                        raise ValueError("predict needs dt")
+                    steps.append(np.asarray(rows, np.float64))
+            od = np.ascontiguousarray(np.stack(steps), np.float64)
+        if od.shape[1] not in (1, self.n_filters):
+            raise ValueError("odometry rows per step: 1 or n_filters")
+        nz = None if noise is None else np.ascontiguousarray(noise, np.float32).reshape(od.shape[0], self.n_rows, 6)
+        with self._lock:
+            _lib.check(self._lib.auvpf_predict_many(self._h, _ptr(od), od.shape[0], od.shape[1], _ptr(nz)))
+
     # -- update: auv_pf.update (auv_pf.py:135-167) -------------------------------------------
     def update(self, meas, return_weights=True):
         """GPS form (what the reference does): ``meas`` is a ROS Odometry-shaped GPS

@@ -293,6 +293,9 @@ class ShardedParticleFilter(object):
     def predict(self, odom_t, dt=None, noise=None):
         self.pf.predict(odom_t, dt=dt, noise=noise)
 
+    def predict_many(self, odoms, dt=None, noise=None):
+        self.pf.predict_many(odoms, dt=dt, noise=noise)
+
     def update_mbes(self, ranges):
         self.pf.update_mbes(ranges, return_weights=False)
 

@@ -82,6 +82,32 @@ def test_particle_golden_init_predict_gps_roughen(golden, case):
     pf.close()
 
 
+def test_predict_many_equals_sequential_predicts():
+    """One fused pass over the state == the same predicts one by one (state and RNG counters)."""
+    N, F = 5000, 3
+    rng = np.random.default_rng(9)
+    odoms = [[world.Odom(rng.normal(1.0, 0.1, 3), 0.05 * rng.normal(), world.quat_from_rpy(0.02, -0.01, 0.3), -5.0, 0.02)
+              for _ in range(F)] for _ in range(5)]
+    a = _pf(particle_count=N, n_filters=F, init_covariance=[1.0, 1.0, 0, 0, 0, 0.1],
+            motion_covariance=[1e-3, 1e-3, 0, 0, 0, 1e-5], seed=77)
+    b = _pf(particle_count=N, n_filters=F, init_covariance=[1.0, 1.0, 0, 0, 0, 0.1],
+            motion_covariance=[1e-3, 1e-3, 0, 0, 0, 1e-5], seed=77)
+    for od in odoms:
+        a.predict(od)
+    b.predict_many(odoms)
+    np.testing.assert_array_equal(a.poses(), b.poses())
+    a.predict(odoms[0])                      # the step counters advanced identically
+    b.predict_many(odoms[:1])
+    np.testing.assert_array_equal(a.poses(), b.poses())
+    nz = rng.normal(size=(2, F * N, 6)).astype(np.float32)
+    a.predict(odoms[1], noise=nz[0])
+    a.predict(odoms[2], noise=nz[1])
+    b.predict_many(odoms[1:3], noise=nz)
+    np.testing.assert_array_equal(a.poses(), b.poses())
+    a.close()
+    b.close()
+
+
 def test_philox_streams_match_spec():
     """Device-generated normals follow the documented Philox contract."""
     N, seed = 4096, 0x1234567890ABCDEF
