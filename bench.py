@@ -266,7 +266,7 @@ def run_ours(args):
     def cycle_device(s):
         filt.predict_many(cycles[s][0])            # the 5 odometry messages between two pings, one pass over the state
         _lib.check(L.auvpf_update_mbes(pf._h, C.c_void_p(pings_dev[s].data_ptr()), None))
-        filt.resample()
+        filt.resample(wait=False) if (G == 1 or F > 1) else filt.resample()     # enqueue only: no host wait in the cycle
 
     def barrier():
         if dist is not None:
@@ -314,7 +314,7 @@ def run_ours(args):
     for s in range(base, base + W):
         filt.predict_many(cycles[s][0])
         filt.update_mbes(pings_pin[s].numpy()) if (G > 1 and F == 1) else pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
-        filt.resample()
+        filt.resample(wait=False) if (G == 1 or F > 1) else filt.resample()
         filt.mean_cov()
     barrier()
     t0 = time.perf_counter()
@@ -324,7 +324,7 @@ def run_ours(args):
             filt.update_mbes(pings_pin[s].numpy())
         else:
             pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
-        filt.resample()
+        filt.resample(wait=False) if (G == 1 or F > 1) else filt.resample()
         est = filt.mean_cov()
     barrier()
     e2e_s = time.perf_counter() - t0

@@ -62,6 +62,11 @@ extern "C" {
                                   hinted searchsorted on the non-monotone result) for lock-step
                                   parity at the reference's particle counts (<= 65536)   */
 
+#define AUVPF_RS_ASYNC 4       /* return after enqueueing: do not wait for the degenerate-weights
+                                  flag (a filter without any finite weight keeps its state; query
+                                  with auvpf_resample_status).  Ignored when ancestors are read
+                                  back or with AUVPF_RS_INPLACE_REF.                          */
+
 /* kernel classes for auvpf_profile_read */
 enum {
     AUVPF_K_PROPAGATE = 0,
@@ -157,7 +162,8 @@ int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges
  * variances of the post-resample add_noise (auv_pf.py:191-192) fused into the
  * gather, or NULL for none; rough_noise as in auvpf_init_particles.
  * Returns AUVPF_ERR_DEGENERATE (state untouched) when a filter has no finite
- * weight. */
+ * weight -- reading that flag back is the one host synchronisation of the call;
+ * AUVPF_RS_ASYNC skips it. */
 int auvpf_resample(auvpf_handle *h, int32_t mode, int32_t flags, const double *u, int32_t *ancestors_out,
                    const double *rough_var, const float *rough_noise);
 /* Same, from caller-supplied LINEAR float64 weights (F*M) -- the literal
@@ -177,6 +183,8 @@ int auvpf_roughen(auvpf_handle *h, const double var[6], const float *noise);
 /* mean: (F, 6) [x y z roll pitch yaw_mean_of_wrapped]; cov: (F, 9) row-major
  * 3x3 with the reference's fill pattern ([2,0], [2,1] left 0). */
 int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov);
+/* degenerate-weights flag per filter of the last resample, (F) int32; synchronises */
+int auvpf_resample_status(auvpf_handle *h, int32_t *degenerate);
 /* effective sample size 1 / sum w^2 of the last normalisation, (F) */
 int auvpf_neff(auvpf_handle *h, double *neff);
 

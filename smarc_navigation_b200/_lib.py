@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("AUVPF_LIB") or os.path.join(_HERE, "libauvpf.so")   #
 
 OK, ERR_BADARG, ERR_CUDA, ERR_STATE, ERR_DEGENERATE, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 SYSTEMATIC, RESIDUAL = 0, 1
-RS_SORTED, RS_INPLACE_REF, RS_STRICT_REF = 0, 1, 2
+RS_SORTED, RS_INPLACE_REF, RS_STRICT_REF, RS_ASYNC = 0, 1, 2, 4
 IPC_BLOB_BYTES = 256
 K_NAMES = ("propagate", "update_mbes", "update_gps", "normalise", "scan", "select_gather", "roughen",
            "estimate", "other")
@@ -65,6 +65,7 @@ SYMBOLS = [
     ("auvpf_apply_indices", C.c_int, [_vp, _vp, _i32]),
     ("auvpf_roughen", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_mean_cov", C.c_int, [_vp, _vp, _vp]),
+    ("auvpf_resample_status", C.c_int, [_vp, _vp]),
     ("auvpf_neff", C.c_int, [_vp, _vp]),
     ("auvpf_shard_max", C.c_int, [_vp, _vp]),
     ("auvpf_shard_sum", C.c_int, [_vp, _vp, _vp]),

@@ -85,7 +85,7 @@ struct auvpf_handle {
     unsigned int *done = nullptr; // [F] ticket counters of k_normalise
     double *wmax = nullptr;
     unsigned long long *limbs = nullptr, *A = nullptr, *Q = nullptr, *deficit = nullptr;
-    double *u = nullptr, *sumsq = nullptr, *sums = nullptr, *mom = nullptr, *gps = nullptr;
+    double *u = nullptr, *sumsq = nullptr, *sums = nullptr, *gps = nullptr;
     PredictParams *pparams = nullptr;
     int *degenerate = nullptr;
 
@@ -390,12 +390,6 @@ __global__ void k_finish_max(const long long *wmax_ordered, double *wmax, int *d
     degenerate[f] = bad ? 1 : 0;
 }
 
-__global__ void k_zero_f64(double *p, int n)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = 0.0;
-}
-
 // ---- normalisation + scan on the handle's stream ---------------------------------------------
 int run_max(auvpf_handle *h, const WeightSrc &src)
 {
@@ -673,12 +667,15 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
-    // one small read-back at the END of the enqueued cycle: a filter without any finite weight made
-    // the kernels above skip it, the state is untouched and the call fails
-    if ((rc = check_degenerate(h))) return rc;
+    // A filter without any finite weight made the kernels above carry its state over unchanged, so the
+    // buffers flip either way; the flag is read back (one 4-byte copy at the END of the enqueued cycle,
+    // the only host synchronisation of a resample) unless the caller asked not to wait.
     if (!inplace) {
         h->cur = 1 - h->cur;
         if (rough_var) h->step_rough++;
+    }
+    if (!(flags & AUVPF_RS_ASYNC) || inplace || ancestors_out) {
+        if ((rc = check_degenerate(h))) return rc;
     }
     if (ancestors_out && anc_dev != ancestors_out) {
         if (is_device_ptr(ancestors_out))
@@ -745,7 +742,6 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         CU(cudaMalloc(&h->u, sizeof(double) * F));
         CU(cudaMalloc(&h->sumsq, sizeof(double) * F));
         CU(cudaMalloc(&h->sums, sizeof(double) * 16 * F));
-        h->mom = h->sums + 8 * F;
         CU(cudaMalloc(&h->gps, sizeof(double) * 2 * F));
         CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F * AUVPF_MAX_PREDICT_STEPS));
         CU(cudaMalloc(&h->degenerate, sizeof(int) * F));
@@ -1282,31 +1278,42 @@ int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov)
     std::vector<double> host(16 * h->F);
     {
         Prof pr(h, AUVPF_K_ESTIMATE);
-        k_zero_f64<<<(16 * h->F + 127) / 128, 128, 0, h->stream>>>(h->sums, 16 * h->F);
-        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 592);
-        k_pose_sums<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
-        k_pose_moments<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums, h->mom);
-        LAUNCHED(h, AUVPF_K_ESTIMATE, 3);
+        CU(cudaMemsetAsync(h->sums, 0, sizeof(double) * 16 * h->F, h->stream));
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 1184 / h->F));
+        k_pose_stats<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
+        LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
         CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(host.data(), h->sums, sizeof(double) * 16 * h->F, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     const double inv = 1.0 / (double)h->M;
     for (int f = 0; f < h->F; ++f) {
-        const double *s = host.data() + 8 * f, *m = host.data() + 8 * h->F + 8 * f;
-        for (int c = 0; c < 5; ++c) mean[6 * f + c] = s[c] * inv;
+        const double *s = host.data() + 16 * f;
+        const double md[3] = {s[0] * inv, s[1] * inv, s[2] * inv};      // mean relative to the first particle
+        for (int c = 0; c < 3; ++c) mean[6 * f + c] = s[13 + c] + md[c];
+        mean[6 * f + 3] = s[3] * inv;
+        mean[6 * f + 4] = s[4] * inv;
         mean[6 * f + 5] = s[6] * inv;   // mean of the wrapped yaws (auv_pf.py:229-231)
         double *C = cov + 9 * f;
-        C[0] = m[0] * inv;
-        C[4] = m[1] * inv;
-        C[8] = m[2] * inv;
-        C[1] = m[3] * inv;
-        C[2] = m[4] * inv;
-        C[5] = m[5] * inv;
+        C[0] = s[7] * inv - md[0] * md[0];
+        C[4] = s[8] * inv - md[1] * md[1];
+        C[8] = s[9] * inv - md[2] * md[2];
+        C[1] = s[10] * inv - md[0] * md[1];
+        C[2] = s[11] * inv - md[0] * md[2];
+        C[5] = s[12] * inv - md[1] * md[2];
         C[3] = C[1];          // only [1,0] is mirrored (auv_pf.py:246)
         C[6] = 0.0;
         C[7] = 0.0;
     }
+    return AUVPF_OK;
+}
+
+int auvpf_resample_status(auvpf_handle *h, int32_t *degenerate)
+{
+    if (!h || !degenerate) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    CU(cudaMemcpyAsync(degenerate, h->degenerate, sizeof(int) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return AUVPF_OK;
 }
 

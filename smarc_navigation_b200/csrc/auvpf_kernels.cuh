@@ -1047,13 +1047,28 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
     __shared__ unsigned long long s_cdf[kSelSpan];
     __shared__ int64_t s_j[2];
     const int f = blockIdx.y;
-    if (degenerate && degenerate[f]) return;            // no finite weight: nothing is emitted, the caller keeps the state
     const unsigned long long *cdf = cdf_all + (size_t)f * p.M;
     const unsigned long long D = deficit[f];
     const double u = u_all[f], n = (double)p.n_global;
     const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
     if (k0 >= p.n_out) return;
     const int64_t k1 = min(k0 + (int64_t)kSelTile, p.n_out) - 1;
+    if (degenerate && degenerate[f]) {
+        // no finite weight in this filter: its state is carried over unchanged (identity ancestors),
+        // so the buffers can flip without the host having to look at the flag first
+        if (!kRecords && dst.x != nullptr && p.n_out == p.M)
+            for (int64_t k = k0 + threadIdx.x; k <= k1; k += kSelThreads) {
+                const int64_t row = (int64_t)f * p.M + k;
+                dst.x[row] = src.x[row];
+                dst.y[row] = src.y[row];
+                dst.z[row] = src.z[row];
+                dst.roll[row] = src.roll[row];
+                dst.pitch[row] = src.pitch[row];
+                dst.yaw[row] = src.yaw[row];
+                if (anc32) anc32[row] = (int32_t)k;
+            }
+        return;
+    }
     // Level 1: the scan tiles holding the ancestors of the block's first and last output.  The
     // tile table (inclusive prefix per tile, left in the status words by the scan) is read with
     // coalesced loads and COUNTED (tiles whose end lies at or below the position), so there is no
@@ -1673,49 +1688,43 @@ __device__ __forceinline__ double wrap_pi_d(double a)
     return t - kPi;
 }
 
-__global__ void __launch_bounds__(kThreads) k_pose_sums(StateView s, int64_t M, double *sums /* F x 8 */)
+// ONE pass: positions are accumulated relative to the filter's first particle c (first and second
+// moments of d = pos - c), so  mean = c + sum d / N  and  cov = sum d d^T / N - mean_d mean_d^T  keep
+// full precision on a 2 km map.  stats: F x 16 = [sum d_xyz, sum roll, pitch, yaw, wrapped yaw,
+// sum d d^T (xx yy zz xy xz yz), c_xyz].
+__global__ void __launch_bounds__(kThreads) k_pose_stats(StateView s, int64_t M, double *stats)
 {
     const int f = blockIdx.y;
-    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int64_t base = (int64_t)f * M;
+    const double cx = s.x[base], cy = s.y[base], cz = (double)s.z[base];
+    double a[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
-        int64_t row = (int64_t)f * M + i;
-        a[0] += s.x[row];
-        a[1] += s.y[row];
-        a[2] += (double)s.z[row];
+        const int64_t row = base + i;
+        const double dx = s.x[row] - cx, dy = s.y[row] - cy, dz = (double)s.z[row] - cz;
+        const double yw = (double)s.yaw[row];
+        a[0] += dx;
+        a[1] += dy;
+        a[2] += dz;
         a[3] += (double)s.roll[row];
         a[4] += (double)s.pitch[row];
-        double yw = (double)s.yaw[row];
         a[5] += yw;
         a[6] += wrap_pi_d(yw);
+        a[7] += dx * dx;
+        a[8] += dy * dy;
+        a[9] += dz * dz;
+        a[10] += dx * dy;
+        a[11] += dx * dz;
+        a[12] += dy * dz;
     }
 #pragma unroll
-    for (int c = 0; c < 7; ++c) {
-        double v = warp_sum_f64(a[c]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(sums + 8 * f + c, v);
+    for (int c = 0; c < 13; ++c) {
+        const double v = warp_sum_f64(a[c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(stats + 16 * f + c, v);
     }
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_pose_moments(StateView s, int64_t M, const double *sums, double *mom /* F x 8: xx yy zz xy xz yz */)
-{
-    const int f = blockIdx.y;
-    const double inv = 1.0 / (double)M;
-    const double mx = sums[8 * f] * inv, my = sums[8 * f + 1] * inv, mz = sums[8 * f + 2] * inv;
-    double a[6] = {0, 0, 0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
-        int64_t row = (int64_t)f * M + i;
-        double dx = s.x[row] - mx, dy = s.y[row] - my, dz = (double)s.z[row] - mz;
-        a[0] += dx * dx;
-        a[1] += dy * dy;
-        a[2] += dz * dz;
-        a[3] += dx * dy;
-        a[4] += dx * dz;
-        a[5] += dy * dz;
-    }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) {
-        double v = warp_sum_f64(a[c]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(mom + 8 * f + c, v);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[16 * f + 13] = cx;
+        stats[16 * f + 14] = cy;
+        stats[16 * f + 15] = cz;
     }
 }
 

@@ -281,7 +281,7 @@ class ParticleFilter(object):
         return out
 
     # -- resample: auv_pf.resample (auv_pf.py:169-192) ---------------------------------------
-    def resample(self, weights=None, u=None, noise=None, return_ancestors=False, roughen=True):
+    def resample(self, weights=None, u=None, noise=None, return_ancestors=False, roughen=True, wait=True):
         """Normalise (:172), draw ancestors, reassign poses (:183-189,195-198) and add
         ``resampling_noise_covariance`` noise to every particle (:191-192).
         ``weights=None`` uses the device-resident log-weights of the last update;
@@ -303,6 +303,8 @@ class ParticleFilter(object):
         flags = _lib.RS_INPLACE_REF if self.inplace_reference else _lib.RS_SORTED
         if self.strict_reference and self.resampler == _lib.RESIDUAL:
             flags |= _lib.RS_STRICT_REF
+        if not wait:          # enqueue only; degenerate filters keep their state, see resample_status()
+            flags |= _lib.RS_ASYNC
         with self._lock:
             if weights is None:
                 rc = self._lib.auvpf_resample(self._h, self.resampler, flags, _ptr(uu), _ptr(anc), rv, _ptr(nz))
@@ -312,6 +314,13 @@ class ParticleFilter(object):
                                                       _ptr(anc), rv, _ptr(nz))
             _lib.check(rc)
         return anc
+
+    def resample_status(self):
+        """Per-filter degenerate-weights flag of the last resample (synchronises)."""
+        out = np.zeros(self.n_filters, np.int32)
+        with self._lock:
+            _lib.check(self._lib.auvpf_resample_status(self._h, _ptr(out)))
+        return out.astype(bool)
 
     def weights_q(self):
         """Fixed-point normalised weights of the last resample: uint64 q, w = q * 2^-52."""

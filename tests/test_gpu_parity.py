@@ -362,6 +362,14 @@ def test_degenerate_weights_raise_and_leave_state():
     with pytest.raises(DegenerateWeights):
         pf.resample(weights=np.zeros(N), u=0.5)
     np.testing.assert_array_equal(pf.poses(), p0)
+    # enqueue-only mode: no exception, the state is carried over, the flag can be queried
+    pf.resample(u=0.5, wait=False)
+    assert pf.resample_status()[0]
+    np.testing.assert_array_equal(pf.poses(), p0)
+    pf.set_log_weights(np.zeros(N, np.float32))
+    pf.resample(u=0.5, wait=False, roughen=False)
+    assert not pf.resample_status()[0]
+    np.testing.assert_array_equal(pf.poses(), p0)          # uniform weights: identity ancestors
     pf.close()
 
 
