@@ -676,16 +676,6 @@ k_weight_sum(WeightSrc w, int64_t M, const double *wmax, unsigned long long *lim
     }
 }
 
-// limbs -> 128-bit A as (lo64, hi64)
-__global__ void k_combine_limbs(const unsigned long long *limbs, unsigned long long *A, int F)
-{
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    unsigned __int128 a = (unsigned __int128)limbs[2 * f] + ((unsigned __int128)limbs[2 * f + 1] << 32);
-    A[2 * f] = (unsigned long long)a;
-    A[2 * f + 1] = (unsigned long long)(a >> 64);
-}
-
 // Single-GPU normalisation in ONE launch: the maximum arrives from the update kernel
 // (wmax_f32, ordered int) or from k_weight_max (wmax already float64 when wmax_f32 == nullptr);
 // every block adds its exact integer partial of A = sum_i a_i; the LAST block of a filter
@@ -981,12 +971,6 @@ k_emit_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A
     int64_t row = (int64_t)f * M + i;
     unsigned long long q = q_from_a(src_a(w, row, wmax[f]), A[2 * f], A[2 * f + 1]);
     q_out[row] = q + (((unsigned long long)(global_offset + i) < deficit[f]) ? 1ull : 0ull);
-}
-
-__global__ void k_deficit(const unsigned long long *Q, unsigned long long *deficit, int F)
-{
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f < F) deficit[f] = (1ull << kQBits) - Q[f];
 }
 
 // ---------------------------------------------------------------------------------------------
