@@ -1004,7 +1004,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 entry = be == 2 ? 2 : 1 - be;
             }
         }
-        AUVPF_WARP_SYNC();
+        // (the full-mask ballot at the top of the next iteration is the end-of-step convergence point)
     }
     if (running) {                           // ran out of steps: not certified
         AUVPF_REASON(3);
