@@ -48,7 +48,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4", "C5"])
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work per reference step / baseline")
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="target CPU work per reference step / baseline sample (default: 15 s for the baseline "
+                         "sample; for --impl reference about 75 s split over the steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -180,7 +182,9 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = workload(args, args.gpus)
-    n, cores = cpu_sample_size(cfg, args.cpu_seconds)
+    # bounded sample: the whole --steps K --warmup W run should end within a couple of minutes
+    per_step = args.cpu_seconds if args.cpu_seconds else min(15.0, max(0.5, 75.0 / (args.steps + min(args.warmup, 1))))
+    n, cores = cpu_sample_size(cfg, per_step)
     t, cores = cpu_run(cfg, n, args.steps, min(args.warmup, 1))
     v = n * cfg["beams"] / t
     sample = "%d of %d particles x %d beams per step, C/OpenMP float64 oracle port, %d threads" % (
@@ -383,7 +387,7 @@ def run_ours(args):
         "track_error_m": track_err,
     }
     if rank == 0 and G == 1 and not args.no_cpu_baseline:
-        n, cores = cpu_sample_size(cfg, args.cpu_seconds)
+        n, cores = cpu_sample_size(cfg, args.cpu_seconds or 15.0)
         t, cores = cpu_run(cfg, n, 1, 0)
         line["cpu_baseline"] = {"value": n * B / t, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "%d of %d particles x %d beams, 1 cycle, C/OpenMP float64 oracle port" % (

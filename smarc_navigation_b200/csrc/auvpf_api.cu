@@ -1279,7 +1279,7 @@ int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov)
     {
         Prof pr(h, AUVPF_K_ESTIMATE);
         CU(cudaMemsetAsync(h->sums, 0, sizeof(double) * 16 * h->F, h->stream));
-        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 1184 / h->F));
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 592 / h->F));
         k_pose_stats<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
         LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
         CU(cudaGetLastError());

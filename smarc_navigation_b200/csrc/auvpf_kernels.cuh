@@ -1700,10 +1700,19 @@ __global__ void __launch_bounds__(kThreads) k_pose_stats(StateView s, int64_t M,
         a[11] += dx * dz;
         a[12] += dy * dz;
     }
+    // warp -> block -> 13 atomics per block (one per warp on the same 13 addresses cost 130 us at 1 M particles)
+    __shared__ double s_part[kThreads / 32][13];
 #pragma unroll
     for (int c = 0; c < 13; ++c) {
         const double v = warp_sum_f64(a[c]);
-        if ((threadIdx.x & 31) == 0) atomicAdd(stats + 16 * f + c, v);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 13) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v += s_part[w][threadIdx.x];
+        atomicAdd(stats + 16 * f + threadIdx.x, v);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         stats[16 * f + 13] = cx;

@@ -1004,7 +1004,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 entry = be == 2 ? 2 : 1 - be;
             }
         }
-        // (the full-mask ballot at the top of the next iteration is the end-of-step convergence point)
+        AUVPF_WARP_SYNC();      // (measured: relying on the next iteration's ballot alone is 1.2 % slower)
     }
     if (running) {                           // ran out of steps: not certified
         AUVPF_REASON(3);
