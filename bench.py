@@ -37,7 +37,11 @@ UNIT = "evals/s"
 P_PREDICTS = 5
 # dram__bytes_read.sum + dram__bytes_write.sum of k_update_mbes_profile per launch, from the committed ncu --set full
 # capture (profiles/r1_ncu_update_mbes_profile.txt); only the workload that was captured has a figure
-NCU_DRAM_TRAFFIC = {"C3": 33.64e6 + 0.89e6}
+NCU_DRAM_TRAFFIC = {"C3": 33.64e6 + 0.81e6}
+# what bounds that kernel, from the same capture (SURVEY 8d asks for these instead of a %-of-HBM figure)
+NCU_DOMINANT = {"C3": {"issue_slots_used": 0.70, "ipc_per_sm": 2.8, "active_lanes_of_32": 23.3, "l1_hit_rate": 0.988,
+                       "l2_hit_rate": 0.77, "registers": 96, "warps_per_sm": 18, "top_stall": "wait (dependent issue)",
+                       "source": "profiles/r1_ncu_update_mbes_profile.txt"}}
 RS_BYTES = 96        # algorithmic HBM bytes per particle of normalise + scan + select + gather
 
 
@@ -373,6 +377,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "k_update_mbes_profile (+ k_update_mbes for flagged particles): fused raycast + beam likelihood",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": NCU_DRAM_TRAFFIC.get(cfg["name"]) if G == 1 else None,
+                     "ncu": NCU_DOMINANT.get(cfg["name"]),
                      "peak_source": peak_src, "ms_per_launch": mbes_ms / max(mbes_n, 1),
                      "evals_per_s": M * F * B / (mbes_ms / max(mbes_n, 1) * 1e-3) if mbes_n else None,
                      "note": "dominant kernel is instruction-issue-bound (ncu: 74 % of issue slots, 2.9 IPC/SM, L1 hit "

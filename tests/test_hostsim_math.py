@@ -340,3 +340,31 @@ def test_profile_merge_vs_oracle(name):
         assert n_prof == r.size                 # every particle certified by the profile march
     if name == "short_range":
         assert (ro == rmax).any() and (ro < rmax).any()
+
+
+def test_profile_merge_random_fans():
+    """Random planar fans -- plane rotated about the vertical, asymmetric and one-sided angle ranges,
+    1 to 200 beams, either beam order, short and long range_max, small and large roll/pitch -- keep
+    the oracle's first hits within the range tolerance (per-ray fallback where the march declines)."""
+    rng = np.random.default_rng(123)
+    dem = world.make_dem(600, 1.0)
+    for trial in range(40):
+        B = int(rng.choice([1, 2, 3, 5, 17, 64, 200]))
+        a0 = rng.uniform(-70, 10)
+        a1 = a0 + rng.uniform(5, 60) if B > 1 else a0
+        th = np.radians(np.linspace(a0, a1, B))
+        psi = rng.uniform(0, 2 * np.pi)
+        lat = np.array([np.cos(psi), np.sin(psi), 0.0])
+        beams = np.sin(th)[:, None] * lat[None, :] + np.cos(th)[:, None] * np.array([0, 0, -1.0])[None, :]
+        if rng.uniform() < 0.3:
+            beams = beams[::-1].copy()
+        b32 = beams.astype(np.float32)
+        poses = _cloud(rng, 24, (300.0, 300.0), 5.0, roll_pitch=float(rng.choice([0.02, 0.15])))
+        rmax = float(rng.choice([40.0, 120.0]))
+        out = c_oracle.update_mbes(dem, poses, np.eye(4), b32.astype(np.float64), None, 1.0, 0.5, rmax,
+                                   want_ranges=True, want_diag=True)
+        r = hs.raycast_poses(dem, 1, rmax, np.eye(4), poses, b32, shift_hi=4, fan=2)
+        ro, dg = out["ranges"], out["diag"]
+        sturdy = ~((dg[..., 0] < FRAGILE) | (dg[..., 1] < FRAGILE) | (dg[..., 2] < FRAGILE))
+        assert sturdy.mean() > 0.97
+        assert np.abs(r - ro)[sturdy].max() <= RANGE_TOL, (trial, B, a0, a1, psi, rmax)
