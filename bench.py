@@ -353,7 +353,7 @@ def run_ours(args):
     alg_mbes = M * F * (32 + 4) + dem_bytes + 16 * B        # state read + logw write, DEM once, beam table
     ach = alg_mbes / (mbes_ms / max(mbes_n, 1) * 1e-3) / 1e9 if mbes_n else 0.0
     rs_ms = prof["normalise"][0] + prof["scan"][0] + prof["select_gather"][0]
-    rs_n = max(prof["scan"][1], 1)
+    rs_n = K                                                # one resample per cycle
     alg_rs = M * F * RS_BYTES                                   # normalise 4 + scan 12 + select 12 + gather 4+32+32
     ach_rs = alg_rs / (rs_ms / rs_n * 1e-3) / 1e9 if rs_ms > 0 else 0.0
     prop_ms, prop_n = prof["propagate"]
