@@ -470,6 +470,34 @@ def test_residual_resample_default(N, scale):
     pf.close()
 
 
+def test_residual_resample_batched_filters(golden):
+    """Residual resampling of several filters in one handle: every filter equals its own
+    single-filter result -- fixed-point default mode vs the oracle, strict mode vs the unmodified
+    reference's golden indices."""
+    g = golden("residual_quantised")
+    names = ("n1000", "n1000", "n1000")
+    N, F = 1000, 3
+    rng = np.random.default_rng(55)
+    logw = np.stack([g["n1000_logw"], g["n1000_logw"][::-1], (rng.normal(0, 1.5, N) - 20).astype(np.float32)])
+    U = np.stack([g["n1000_U"], rng.uniform(size=N), rng.uniform(size=N)])
+    p = np.zeros((F * N, 6))
+    p[:, 0] = np.arange(F * N)
+    for strict in (False, True):
+        pf = _pf(particle_count=N, n_filters=F, resampler="residual", strict_reference=strict)
+        pf.set_poses(p)
+        pf.set_log_weights(logw.reshape(-1))
+        anc = pf.resample(u=U, return_ancestors=True, roughen=False).reshape(F, N)
+        qq = pf.weights_q().reshape(F, N)
+        for f in range(F):
+            np.testing.assert_array_equal(qq[f], o.quantise_logw(logw[f])[0])
+            want = o.residual_resample(o.weights_from_q(qq[f]), U[f]) if strict else o.residual_resample_fixed(qq[f], U[f])
+            np.testing.assert_array_equal(anc[f], want)
+            np.testing.assert_array_equal(pf.poses()[f * N:(f + 1) * N, 0], p[f * N + anc[f], 0])
+        if strict:
+            np.testing.assert_array_equal(anc[0], g["n1000_idx"])            # the unmodified reference
+        pf.close()
+
+
 # --------------------------------------------------------------------------- a10 estimate
 def test_estimate_vs_reference_golden(golden):
     g = golden("auv_pf_cycle")
