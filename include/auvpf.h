@@ -117,6 +117,14 @@ int64_t auvpf_particle_count(auvpf_handle *h); /* F*M rows held by this handle *
 /* H x W float32 vertex heights, row i at y0 + i*res, column j at x0 + j*res;
  * builds the max-mip pyramid on the device. */
 int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double x0, double y0, double res);
+/* Map ingestion: rasterise a triangle mesh (n_vertices x 3 float32 map-frame points, n_faces x 3
+ * int32 vertex indices) onto the H x W vertex grid of a DEM; where surfaces overlap in plan
+ * view the highest wins, vertices no triangle covers get `fill`.  z_out: (H, W) float32, host or
+ * device; pass it to auvpf_set_dem.  (The reference has no map format, SURVEY.md section 8f-4;
+ * BASELINE config C1 describes its bathymetry as a mesh.) */
+int auvpf_rasterise_mesh(auvpf_handle *h, const float *vertices, int64_t n_vertices, const int32_t *faces,
+                         int64_t n_faces, int32_t H, int32_t W, double x0, double y0, double res, float fill,
+                         float *z_out);
 /* B unit beam directions in the sensor (= particle body) frame, (B,3) float32 */
 int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B);
 

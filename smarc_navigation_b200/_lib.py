@@ -48,6 +48,7 @@ SYMBOLS = [
     ("auvpf_stream", _vp, [_vp]),
     ("auvpf_particle_count", _i64, [_vp]),
     ("auvpf_set_dem", C.c_int, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl]),
+    ("auvpf_rasterise_mesh", C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _dbl, _dbl, _dbl, C.c_float, _vp]),
     ("auvpf_set_beams", C.c_int, [_vp, _vp, _i32]),
     ("auvpf_init_particles", C.c_int, [_vp, _vp, _vp, _vp]),
     ("auvpf_set_poses", C.c_int, [_vp, _vp]),

@@ -961,6 +961,31 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
     return AUVPF_OK;
 }
 
+int auvpf_rasterise_mesh(auvpf_handle *h, const float *vertices, int64_t n_vertices, const int32_t *faces,
+                         int64_t n_faces, int32_t H, int32_t W, double x0, double y0, double res, float fill,
+                         float *z_out)
+{
+    if (!h || !vertices || !faces || !z_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (H < 2 || W < 2 || !(res > 0.0) || n_vertices < 3 || n_faces < 1)
+        return fail(AUVPF_ERR_BADARG, "mesh needs >= 3 vertices and >= 1 face, grid at least 2x2 with res > 0");
+    Guard g(h);
+    int rc;
+    const float *vd;
+    const int32_t *fd;
+    float *zd;
+    if ((rc = stage_in(h, S_IN0, vertices, (size_t)n_vertices * 3, &vd))) return rc;
+    if ((rc = stage_in(h, S_IN1, faces, (size_t)n_faces * 3, &fd))) return rc;
+    const int64_t n = (int64_t)H * W;
+    if ((rc = stage_out(h, S_OUT0, z_out, (size_t)n, &zd))) return rc;
+    int *zi = reinterpret_cast<int *>(zd);
+    k_fill_ordered<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(zi, n);
+    k_rasterise_mesh<<<(unsigned)((n_faces + 127) / 128), 128, 0, h->stream>>>(vd, fd, n_faces, H, W, x0, y0, 1.0 / res, zi);
+    k_unorder<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(zi, n, fill);
+    LAUNCHED(h, AUVPF_K_OTHER, 3);
+    CU(cudaGetLastError());
+    return finish_out(h, z_out, (const float *)zd, (size_t)n);
+}
+
 int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
 {
     if (!h || !dirs_xyz || B <= 0 || B > 4096) return fail(AUVPF_ERR_BADARG, "bad beam table (1..4096 beams)");

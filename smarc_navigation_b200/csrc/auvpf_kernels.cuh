@@ -587,6 +587,55 @@ __global__ void k_mip_down(const float *in, int iH, int iW, float *out, int oH, 
     out[(size_t)bi * oW + bj] = m;
 }
 
+// Map ingestion: rasterise a triangle mesh onto the DEM's vertex grid.  One thread per
+// triangle walks the grid vertices of its bounding box; a vertex inside the triangle (edges
+// included) takes the interpolated height, the highest surface wins (atomicMax on the
+// order-preserving int encoding).  Vertices no triangle covers keep `fill`.
+constexpr int kUncovered = (int)0x80000000;     // below the encoding of every float, -inf included
+
+__global__ void k_fill_ordered(int *z, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = kUncovered;
+}
+
+__global__ void k_rasterise_mesh(const float *__restrict__ verts, const int *__restrict__ faces, int64_t n_faces,
+                                 int H, int W, double x0, double y0, double inv_res, int *z_ordered)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_faces) return;
+    double gx[3], gy[3], gz[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float *v = verts + 3 * (int64_t)faces[3 * t + k];
+        gx[k] = ((double)v[0] - x0) * inv_res;
+        gy[k] = ((double)v[1] - y0) * inv_res;
+        gz[k] = (double)v[2];
+    }
+    const double det = (gy[1] - gy[2]) * (gx[0] - gx[2]) + (gx[2] - gx[1]) * (gy[0] - gy[2]);
+    if (det == 0.0) return;                                   // degenerate in plan view
+    const int j0 = max(0, (int)ceil(fmin(gx[0], fmin(gx[1], gx[2])) - 1e-9));
+    const int j1 = min(W - 1, (int)floor(fmax(gx[0], fmax(gx[1], gx[2])) + 1e-9));
+    const int i0 = max(0, (int)ceil(fmin(gy[0], fmin(gy[1], gy[2])) - 1e-9));
+    const int i1 = min(H - 1, (int)floor(fmax(gy[0], fmax(gy[1], gy[2])) + 1e-9));
+    const double eps = 1e-9;
+    for (int i = i0; i <= i1; ++i)
+        for (int j = j0; j <= j1; ++j) {
+            const double l0 = ((gy[1] - gy[2]) * ((double)j - gx[2]) + (gx[2] - gx[1]) * ((double)i - gy[2])) / det;
+            const double l1 = ((gy[2] - gy[0]) * ((double)j - gx[2]) + (gx[0] - gx[2]) * ((double)i - gy[2])) / det;
+            const double l2 = 1.0 - l0 - l1;
+            if (l0 < -eps || l1 < -eps || l2 < -eps) continue;
+            const float zz = (float)(l0 * gz[0] + l1 * gz[1] + l2 * gz[2]);
+            atomicMax(z_ordered + (int64_t)i * W + j, float_to_ordered(zz));
+        }
+}
+
+__global__ void k_unorder(int *z, int64_t n, float fill)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = __float_as_int(z[i] == kUncovered ? fill : ordered_to_float(z[i]));
+}
+
 // largest triangle gradient norm of the DEM (two triangles per cell, diagonal (i,j)->(i+1,j+1))
 __global__ void k_max_slope(const float *z, int pitch, int H, int W, float inv_res, int *out_ordered)
 {

@@ -141,6 +141,19 @@ class ParticleFilter(object):
         with self._lock:
             _lib.check(self._lib.auvpf_set_dem(self._h, _ptr(z), z.shape[0], z.shape[1], x0, y0, res))
 
+    def rasterise_mesh(self, vertices, faces, shape, x0=0.0, y0=0.0, res=1.0, fill=np.nan):
+        """Triangle mesh -> (H, W) float32 DEM on the GPU (highest surface wins; uncovered vertices
+        get ``fill``); feed the result to ``set_dem``."""
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        f = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+        if f.size and (f.min() < 0 or f.max() >= v.shape[0]):
+            raise ValueError("face index out of range")
+        z = np.empty((int(shape[0]), int(shape[1])), np.float32)
+        with self._lock:
+            _lib.check(self._lib.auvpf_rasterise_mesh(self._h, _ptr(v), v.shape[0], _ptr(f), f.shape[0], z.shape[0],
+                                                      z.shape[1], x0, y0, res, fill, _ptr(z)))
+        return z
+
     def set_beams(self, dirs_xyz):
         d = np.ascontiguousarray(dirs_xyz, np.float32).reshape(-1, 3)
         with self._lock:

@@ -53,6 +53,19 @@ def make_dem(n, res, seed=1, chunk=512):
     return {"z": z, "x0": 0.0, "y0": 0.0, "res": float(res)}
 
 
+def dem_to_mesh(dem):
+    """The DEM's own triangulation as a mesh (vertices (H*W, 3), faces (2 (H-1)(W-1), 3)): two triangles
+    per cell split along (i, j) -> (i+1, j+1), the surface of the raycast spec."""
+    z = dem["z"]
+    H, W = z.shape
+    jj, ii = np.meshgrid(np.arange(W), np.arange(H))
+    v = np.stack([dem["x0"] + jj * dem["res"], dem["y0"] + ii * dem["res"], z], -1).reshape(-1, 3).astype(np.float32)
+    idx = (ii * W + jj)[:-1, :-1].reshape(-1)
+    lower = np.stack([idx, idx + 1, idx + W + 1], -1)
+    upper = np.stack([idx, idx + W + 1, idx + W], -1)
+    return v, np.concatenate([lower, upper]).astype(np.int32)
+
+
 def make_beams(B, half_angle_deg=60.0):
     """Fan in the sensor y-z plane: d_b = (0, sin th, -cos th)."""
     th = np.linspace(-math.radians(half_angle_deg), math.radians(half_angle_deg), B)

@@ -267,6 +267,33 @@ def test_update_mbes_mixed_profile_and_per_ray_particles():
     pf.close()
 
 
+def test_mesh_rasteriser_round_trip_and_overlap():
+    """Map ingestion: the DEM's own triangulation rasterises back to the DEM bit for bit; a coarser
+    mesh interpolates linearly; where two sheets overlap the higher one wins; uncovered vertices
+    keep the fill value."""
+    dem = _dem(120, 2.0)
+    pf = _pf(particle_count=4)
+    v, f = world.dem_to_mesh(dem)
+    z = pf.rasterise_mesh(v, f, dem["z"].shape, dem["x0"], dem["y0"], dem["res"])
+    np.testing.assert_array_equal(z, dem["z"])
+    # one big tilted triangle pair over part of the grid + a higher small sheet, finer grid than the mesh
+    verts = np.array([[10, 10, -30], [110, 10, -20], [110, 90, -25], [10, 90, -35],
+                      [40, 40, -5], [60, 40, -5], [60, 60, -5], [40, 60, -5]], np.float32)
+    faces = np.array([[0, 1, 2], [0, 2, 3], [4, 5, 6], [4, 6, 7]], np.int32)
+    zz = pf.rasterise_mesh(verts, faces, (101, 121), 0.0, 0.0, 1.0, fill=-999.0)
+    assert zz[5, 5] == -999.0 and zz[95, 115] == -999.0                       # outside every triangle
+    assert zz[50, 50] == -5.0 and zz[40, 60] == -5.0                          # the higher sheet, edges included
+    np.testing.assert_allclose(zz[10, 10], -30.0, atol=1e-5)
+    np.testing.assert_allclose(zz[10, 60], -25.0, atol=1e-5)                  # halfway along the first edge
+    # the lower triangle (0,1,2) is the plane z = -30 + 0.1 (x - 10) - 0.0625 (y - 10)
+    np.testing.assert_allclose(zz[30, 100], -30.0 + 0.1 * 90 - 0.0625 * 20, atol=1e-4)
+    pf.set_dem(np.where(zz == -999.0, -40.0, zz).astype(np.float32), 0.0, 0.0, 1.0)
+    pf.set_scan_geometry(-0.5, 0.1, 11)
+    r = pf.raycast(np.array([[50.0, 50.0, 0.0, 0.0, 0.0, 0.0]]))
+    np.testing.assert_allclose(r[0, 5], 5.0, atol=1e-4)                        # nadir beam lands on the upper sheet
+    pf.close()
+
+
 # --------------------------------------------------------------------------- a5 / a7 / a8(sorted) / a9
 @pytest.mark.parametrize("N,scale", [(1, 1.0), (100, 3.0), (4097, 10.0), (65536, 25.0), (1048576, 6.0),
                                      (16777216, 4.0)])
