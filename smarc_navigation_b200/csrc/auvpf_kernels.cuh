@@ -1150,6 +1150,7 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
     for (int grp = 0; grp < kSelGroups; ++grp) {
     const int64_t kb = k0 + ((int64_t)grp * kSelThreads + threadIdx.x) * kSelItems;
     if (kb > k1) return;
+    const SysPos spos = make_sys_pos(u, n);
     int64_t jj[kSelItems];
     {
         int64_t prev = 0;       // index into the staged window / offset from j_lo
@@ -1160,7 +1161,7 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
                 jj[r] = 0;
                 continue;
             }
-            const unsigned long long key = pos_key(sys_position(u, p.out_lo + k, n));
+            const unsigned long long key = pos_key(sys_position(spos, p.out_lo + k));
             int64_t j;
             if (staged) {
                 int lo = (int)prev, hi = (int)span;
@@ -1376,6 +1377,7 @@ k_select_gather_p2p(const PeerTable *__restrict__ pt, int64_t M, int rank, int t
 
     const int64_t kb = k0 + (int64_t)threadIdx.x * kSelItems;
     if (kb > k1) return;
+    const SysPos spos = make_sys_pos(u, n);
     int64_t JJ[kSelItems];
     {
         int64_t prev = 0;
@@ -1386,7 +1388,7 @@ k_select_gather_p2p(const PeerTable *__restrict__ pt, int64_t M, int rank, int t
                 JJ[r] = 0;
                 continue;
             }
-            const unsigned long long key = pos_key(sys_position(u, out_lo + k, n));
+            const unsigned long long key = pos_key(sys_position(spos, out_lo + k));
             int64_t J;
             if (staged) {
                 int lo = (int)prev, hi = (int)span;
