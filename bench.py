@@ -368,7 +368,8 @@ def run_ours(args):
         "config": {"workload": "%s: %s%d particles/GPU x %d beams (%d total), %.1f m DEM %dx%d, %d predicts per cycle" % (
             cfg["name"], ("%d filters x " % F) if F > 1 else "", M, B, M * F * G, cfg["res"], cfg["dem_n"], cfg["dem_n"],
             P_PREDICTS),
-            "parallelism": ("filter-sharded x%d (%d filters/GPU, no communication)" % (G, F)) if F > 1 else "particle-sharded x%d" % G, "l2": "flushed between steps (256 MiB memset)",
+            "parallelism": ("filter-sharded x%d (%d filters/GPU, no communication)" % (G, F)) if F > 1 else
+            "particle-sharded x%d%s" % (G, (", exchange=%s" % filt.exchange) if G > 1 else ""), "l2": "flushed between steps (256 MiB memset)",
             "resampler": "systematic", "cycle_hz": 1e3 / ms_per_step},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

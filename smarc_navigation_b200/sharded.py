@@ -203,19 +203,34 @@ class GpuShardOps(object):
             self.recv_buf = t.empty((self.M, 4), dtype=t.float64, device=self.device)
 
     def connect(self, dist, group=None):
-        """Exchange CUDA IPC handles of the state / CDF slabs and map the peers' memory."""
+        """Exchange CUDA IPC handles of the state / CDF slabs and map the peers' memory.  Collective:
+        every rank takes part in the all-gather even when its own export failed, and no rank imports
+        unless every export succeeded.  Returns an error (or None); the caller agrees on the outcome."""
         t = self.torch
         G, rank = dist.get_world_size(group), dist.get_rank(group)
         self.prepare(G)
-        blob = (C.c_ubyte * self._lib.IPC_BLOB_BYTES)()
-        self._lib.check(self.L.auvpf_ipc_export(self.pf._h, blob))
-        mine = t.tensor(list(bytes(blob)), dtype=t.uint8, device=self.device)
-        everyone = t.empty(G * self._lib.IPC_BLOB_BYTES, dtype=t.uint8, device=self.device)
+        nb = self._lib.IPC_BLOB_BYTES
+        blob = (C.c_ubyte * nb)()
+        err = None
+        try:
+            self._lib.check(self.L.auvpf_ipc_export(self.pf._h, blob))
+        except Exception as e:              # noqa: BLE001
+            err = e
+        mine = t.tensor(list(bytes(blob)) + [0 if err else 1], dtype=t.uint8, device=self.device)
+        everyone = t.empty(G * (nb + 1), dtype=t.uint8, device=self.device)
         dist.all_gather_into_tensor(everyone, mine, group=group)
-        raw = bytes(everyone.cpu().numpy().tobytes())
-        buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
-        self._lib.check(self.L.auvpf_ipc_import(self.pf._h, buf, G, rank))
-        self.p2p = True
+        rows = everyone.cpu().numpy().reshape(G, nb + 1)
+        if err is None and not rows[:, nb].all():
+            err = RuntimeError("a peer could not export its memory")
+        if err is None:
+            raw = rows[:, :nb].tobytes()
+            buf = (C.c_ubyte * len(raw)).from_buffer_copy(raw)
+            try:
+                self._lib.check(self.L.auvpf_ipc_import(self.pf._h, buf, G, rank))
+                self.p2p = True
+            except Exception as e:          # noqa: BLE001
+                err = e
+        return err
 
     def degenerate(self):
         flag = C.c_int32(0)
@@ -277,10 +292,22 @@ class ShardedParticleFilter(object):
         kw.setdefault("device", torch.cuda.current_device())
         self.pf = ParticleFilter(particle_count=self.M, global_offset=self.rank * self.M, global_count=self.N, **kw)
         self.ops = GpuShardOps(self.pf)
-        if exchange == "p2p":
-            self.ops.connect(dist, group)
-        elif exchange != "nccl":
+        if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
+        self.exchange = exchange
+        if exchange == "p2p":
+            # every rank must end up on the same path: if mapping the peers' memory fails anywhere
+            # (no peer access between two devices, IPC not permitted in this container) all ranks
+            # use the NCCL record exchange instead -- still the GPU path, only with a host-sized plan
+            err = self.ops.connect(dist, group)
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=self.ops.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self.ops.p2p = False
+                self.exchange = "nccl"
+                if self.rank == 0:
+                    import warnings
+                    warnings.warn("peer-memory exchange unavailable (%s); using the NCCL record exchange" % (err,))
         self._step = 0
         self._seed = int(kw.get("seed", 0))
 
