@@ -195,6 +195,36 @@ int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov);
 int auvpf_resample_status(auvpf_handle *h, int32_t *degenerate);
 /* effective sample size 1 / sum w^2 of the last normalisation, (F) */
 int auvpf_neff(auvpf_handle *h, double *neff);
+/* N_eff-gated resampling -- the block the reference carries commented out, auv_pf.py:174-181
+ * (N_eff = 1/np.sum(np.square(weights)); resample only "if N_eff < self.pc/2.").  ratio = 0
+ * (default) resamples on every call like the live reference code; ratio in (0, 1] makes
+ * auvpf_resample* hold a filter's resample back -- poses, weights and roughening untouched,
+ * identity ancestors -- whenever its N_eff is NOT below ratio * particle_count (the reference's
+ * commented value is 0.5).  The decision is taken on the device inside the select kernel (no host
+ * round trip on the systematic path) from an exact integer sum of squares, so it is reproducible:
+ * N_eff here is auvpf_neff_fixed = 2^64 / sum_i min(q_i >> 20, 2^32 - 1)^2 over the fixed-point
+ * weights q_i = floor(a_i 2^52 / A).  With AUVPF_RESIDUAL or
+ * AUVPF_RS_INPLACE_REF the handle must hold one filter; particle-sharded filters are not gated. */
+int auvpf_set_neff_gate(auvpf_handle *h, double ratio);
+int auvpf_neff_fixed(auvpf_handle *h, double *neff);          /* (F); synchronises */
+/* 1 per filter whose last resample the gate held back, (F) int32; synchronises */
+int auvpf_resample_skipped(auvpf_handle *h, int32_t *skipped);
+
+/* -- replay of a recorded sequence -------------------------------- */
+/* n_cycles filter cycles enqueued back to back without the host in the loop: cycle c runs the
+ * n_steps odometry messages odom[c] ((n_cycles, n_steps, n_odom, 11) float64, HOST memory, rows as
+ * in auvpf_predict) in one pass, the MBES update on ranges[c] ((n_cycles, F, B) float32, host or
+ * device), the systematic resample with the roughening fused (AUVPF_RS_ASYNC semantics: a filter
+ * without any finite weight, or held back by the N_eff gate, carries its state over) and the
+ * estimate of auv_pf.update_loc_pose.  The sequence is uploaded once and the estimates -- mean_out
+ * (n_cycles, F, 6), cov_out (n_cycles, F, 9), host memory, or both NULL -- are read back once at the
+ * end (the call's only synchronisation; without them it returns after enqueueing).  u: (n_cycles, F)
+ * uniforms or NULL for Philox.  The result is bit-identical to n_cycles x [auvpf_predict_many,
+ * auvpf_update_mbes, auvpf_resample, auvpf_mean_cov]: odom_callback x n_steps + the measurement
+ * callback + loc_loop of the reference node (auv_pf.py:201-211,125-133,264-285) per cycle. */
+int auvpf_replay(auvpf_handle *h, int32_t n_cycles, int32_t n_steps, int32_t n_odom, const double *odom,
+                 const float *ranges, int32_t mode, int32_t flags, const double *u, const double *rough_var,
+                 double *mean_out, double *cov_out);
 
 /* -- multi-GPU staging (particle-sharded single filter) - */
 /* stage 1: local max of logw (F floats) */

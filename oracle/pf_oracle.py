@@ -275,6 +275,43 @@ def weights_from_q(qq):
     return np.ldexp(qq.astype(np.float64), -Q_BITS)
 
 
+def neff(weights):
+    """``N_eff = 1/np.sum(np.square(weights))`` -- the block the reference carries commented out
+    (auv_pf.py:174-178), for normalised weights."""
+    w = np.asarray(weights, np.float64)
+    return 1.0 / np.sum(np.square(w))
+
+
+def neff_fixed_raw(q_raw):
+    """The integer-exact N_eff the library's gate compares (include/auvpf.h,
+    ``auvpf_set_neff_gate``; csrc/auvpf_math.cuh ``neff_fixed``), defined on the RAW quotients
+    ``q_i = floor(a_i 2^52 / A)`` (before the deficit units): ``s_i = min(q_i >> 20, 2^32 - 1)``,
+    ``S = sum s_i^2`` kept as two limb sums (low 32 bits, high bits) and
+    ``2^64 / (float(S_hi) * 2^32 + float(S_lo))`` in float64."""
+    q = np.asarray(q_raw, np.uint64)
+    s = np.minimum(q >> np.uint64(20), np.uint64(0xFFFFFFFF))
+    s2 = s * s                                            # < 2^64, no wrap
+    lo = int((s2 & np.uint64(0xFFFFFFFF)).sum(dtype=np.uint64))
+    hi = int((s2 >> np.uint64(32)).sum(dtype=np.uint64))
+    S = np.float64(hi) * np.float64(4294967296.0) + np.float64(lo)
+    return float(np.float64(18446744073709551616.0) / S) if S > 0 else 0.0
+
+
+def raw_quotients(a):
+    """``floor(a_i 2^52 / A)`` without the deficit units (what the scan kernel sums)."""
+    A = _sum_u64(a)
+    ao = np.asarray(a, np.uint64).astype(object)
+    return np.array([(int(v) << Q_BITS) // A for v in ao], dtype=np.uint64)
+
+
+def resample_gate(a, ratio):
+    """True = resample (``N_eff < ratio * pc``, the ``if`` of auv_pf.py:181); ``a`` as returned by
+    ``quantise_logw`` / ``quantise_linear``.  ratio == 0: always resample (the live reference code)."""
+    if not ratio > 0.0:
+        return True
+    return neff_fixed_raw(raw_quotients(a)) < ratio * float(len(a))
+
+
 # --------------------------------------------------------------------------- resamplers
 def systematic_resample(weights, u):
     """``systematic_resample`` (resampling.py:135-168) with ``random()`` = u.

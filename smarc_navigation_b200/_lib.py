@@ -68,6 +68,10 @@ SYMBOLS = [
     ("auvpf_mean_cov", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_resample_status", C.c_int, [_vp, _vp]),
     ("auvpf_neff", C.c_int, [_vp, _vp]),
+    ("auvpf_set_neff_gate", C.c_int, [_vp, _dbl]),
+    ("auvpf_neff_fixed", C.c_int, [_vp, _vp]),
+    ("auvpf_resample_skipped", C.c_int, [_vp, _vp]),
+    ("auvpf_replay", C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     ("auvpf_shard_max", C.c_int, [_vp, _vp]),
     ("auvpf_shard_sum", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_shard_scan", C.c_int, [_vp, _vp, _vp, _vp]),

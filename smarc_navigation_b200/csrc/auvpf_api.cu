@@ -88,6 +88,10 @@ struct auvpf_handle {
     double *u = nullptr, *sumsq = nullptr, *sums = nullptr, *gps = nullptr;
     PredictParams *pparams = nullptr;
     int *degenerate = nullptr;
+    unsigned long long *sqlimbs = nullptr;   // [2F] exact integer sum of squared weights (N_eff gate)
+    int *skipped = nullptr;                  // [F] 1 = the N_eff gate held the last resample back
+    double neff_ratio = 0.0;                 // resample only when N_eff < neff_ratio * N; 0 = always
+    DevBuf replay_params, replay_ranges, replay_u, replay_stats;   // auvpf_replay: a whole recorded sequence
 
     // scan machinery
     unsigned long long *status = nullptr;
@@ -427,7 +431,7 @@ int run_scan(auvpf_handle *h, const WeightSrc &src, bool fused = false)
     if (fused)      // a_i were left in h->cdf by k_normalise
         k_scan_q_from_a<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
             h->M, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq, h->deficit,
-            h->degenerate);
+            h->degenerate, h->sqlimbs);
     else
         k_scan_q<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
             src, h->M, h->wmax, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq,
@@ -468,6 +472,7 @@ int run_normalise(auvpf_handle *h, const WeightSrc &src, bool finalise = true)
     ns.A = h->A;
     ns.degenerate = h->degenerate;
     ns.sumsq = h->sumsq;
+    ns.sqlimbs = h->sqlimbs;
     ns.status = h->status;
     ns.tile_counter = h->tile_counter;
     ns.tiles_total = (long long)h->tiles_per_filter * h->F;
@@ -537,6 +542,35 @@ int reset_scan_state(auvpf_handle *h)
     return AUVPF_OK;
 }
 
+// N_eff gate for the paths that synchronise anyway (residual resampling, reference slot map; one
+// filter per handle): the same integers and the same expression as the select kernel's gate.
+// Call after check_degenerate (the stream is idle).  *skip = the resample is held back.
+int host_neff_gate(auvpf_handle *h, bool *skip)
+{
+    *skip = false;
+    if (!(h->neff_ratio > 0.0)) {
+        CU(cudaMemsetAsync(h->skipped, 0, sizeof(int) * h->F, h->stream));
+        return AUVPF_OK;
+    }
+    unsigned long long S[2];
+    CU(cudaMemcpyAsync(S, h->sqlimbs, sizeof(S), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *skip = neff_fixed(S[0], S[1]) >= h->neff_ratio * (double)h->M;
+    const int flag = *skip ? 1 : 0;
+    return tiny_upload(h, h->skipped, &flag, sizeof(int));
+}
+
+int emit_identity_ancestors(auvpf_handle *h, int32_t *ancestors_out)
+{
+    if (!ancestors_out) return AUVPF_OK;
+    if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
+    int32_t *dev = is_device_ptr(ancestors_out) ? ancestors_out : h->anc;
+    k_identity_indices<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(dev, h->M);
+    CU(cudaGetLastError());
+    if (dev != ancestors_out) return finish_out(h, ancestors_out, (const int32_t *)dev, (size_t)h->N);
+    return AUVPF_OK;
+}
+
 // residual_resample (resampling.py:27-76) + the reference's application of its indices.
 // u: (F, M) float64 uniforms -- the random(N - k) of :74, first M - k of each row consumed -- or
 // nullptr for Philox.
@@ -549,6 +583,8 @@ int do_resample_residual(auvpf_handle *h, const WeightSrc &src, int32_t flags, c
     const bool inplace = (flags & AUVPF_RS_INPLACE_REF) != 0;
     if (strict && h->M > 65536)
         return fail(AUVPF_ERR_BADARG, "AUVPF_RS_STRICT_REF emulates the reference's sequential draw: particle_count <= 65536");
+    if (h->neff_ratio > 0.0 && h->F > 1)
+        return fail(AUVPF_ERR_BADARG, "the N_eff gate with residual resampling needs one filter per handle");
     int rc;
     if ((rc = run_normalise(h, src))) return rc;
     if ((rc = run_scan(h, src, /*fused=*/true))) return rc;
@@ -556,6 +592,11 @@ int do_resample_residual(auvpf_handle *h, const WeightSrc &src, int32_t flags, c
     h->last_src_kind = src.kind;
     h->lin_weights = src.lin;
     if ((rc = check_degenerate(h))) return rc;
+    {
+        bool skip;
+        if ((rc = host_neff_gate(h, &skip))) return rc;
+        if (skip) return emit_identity_ancestors(h, ancestors_out);     // state, weights and RNG counters untouched
+    }
     if ((rc = ensure_inplace_buffers(h))) return rc;
     if (!h->scan3) CU(cudaMalloc(&h->scan3, sizeof(unsigned long long) * h->N));
     if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
@@ -620,6 +661,10 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
 {
     if (mode == AUVPF_RESIDUAL) return do_resample_residual(h, src, flags, u, ancestors_out, rough_var, rough_noise);
     if (mode != AUVPF_SYSTEMATIC) return fail(AUVPF_ERR_BADARG, "unknown resample mode %d", mode);
+    if (h->neff_ratio > 0.0 && h->F > 1 && (flags & AUVPF_RS_INPLACE_REF))
+        return fail(AUVPF_ERR_BADARG, "the N_eff gate with AUVPF_RS_INPLACE_REF needs one filter per handle");
+    if (h->neff_ratio > 0.0 && h->global_count != h->M)
+        return fail(AUVPF_ERR_BADARG, "the N_eff gate is not available for a particle-sharded filter");
     int rc;
     if ((rc = run_normalise(h, src))) return rc;
     if ((rc = run_scan(h, src, /*fused=*/true))) return rc;
@@ -663,7 +708,7 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
         if (inplace) dst.x = nullptr;   // ancestors only
         k_select_gather<false><<<grid1(h->M, kSelTile, h->F), kSelThreads, 0, h->stream>>>(
             h->cdf, sp, h->u, h->deficit, h->st[h->cur], dst, nullptr, anc_dev, nullptr, rough, rn, h->status,
-            h->degenerate);
+            h->degenerate, NeffGate{h->sqlimbs, h->neff_ratio * (double)h->M, h->skipped});
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
@@ -684,6 +729,12 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
             return rc;
     }
     if (inplace) {
+        if (h->neff_ratio > 0.0) {      // the kernel's decision (identity ancestors were written): nothing to apply
+            int skipped = 0;
+            CU(cudaMemcpyAsync(&skipped, h->skipped, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            if (skipped) return AUVPF_OK;
+        }
         if ((rc = apply_indices_dev(h, anc_dev))) return rc;
         if (rough_var && (rc = auvpf_roughen(h, rough_var, rough_noise))) return rc;
     }
@@ -745,6 +796,10 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         CU(cudaMalloc(&h->gps, sizeof(double) * 2 * F));
         CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F * AUVPF_MAX_PREDICT_STEPS));
         CU(cudaMalloc(&h->degenerate, sizeof(int) * F));
+        CU(cudaMalloc(&h->sqlimbs, sizeof(unsigned long long) * 2 * F));
+        CU(cudaMemsetAsync(h->sqlimbs, 0, sizeof(unsigned long long) * 2 * F, h->stream));
+        CU(cudaMalloc(&h->skipped, sizeof(int) * F));
+        CU(cudaMemsetAsync(h->skipped, 0, sizeof(int) * F, h->stream));
         CU(cudaMalloc(&h->tile_counter, sizeof(unsigned int)));
         CU(cudaMallocHost(&h->pinned, h->pinned_cap));
         for (int b = 0; b < 2; ++b) {
@@ -794,8 +849,9 @@ int auvpf_destroy(auvpf_handle *h)
     void *bufs[] = {h->logw,    h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
                     h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
-                    h->wmax_f32, h->done, h->scan3,
-                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->probe_flags.p};
+                    h->wmax_f32, h->done, h->scan3, h->sqlimbs, h->skipped,
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->probe_flags.p,
+                    h->replay_params.p, h->replay_ranges.p, h->replay_u.p, h->replay_stats.p};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
     if (h->pinned) cudaFreeHost(h->pinned);
@@ -1296,24 +1352,13 @@ int auvpf_apply_indices(auvpf_handle *h, const int32_t *indices, int32_t flags)
 }
 
 // ------------------------------------------------------------------------------------------------
-int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov)
+namespace {
+// update_loc_pose's numbers from the 16 sums k_pose_stats leaves per filter (auv_pf.py:218-252)
+void finish_mean_cov(const auvpf_handle *h, const double *sums, double *mean, double *cov)
 {
-    if (!h || !mean || !cov) return fail(AUVPF_ERR_BADARG, "null argument");
-    Guard g(h);
-    std::vector<double> host(16 * h->F);
-    {
-        Prof pr(h, AUVPF_K_ESTIMATE);
-        CU(cudaMemsetAsync(h->sums, 0, sizeof(double) * 16 * h->F, h->stream));
-        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 592 / h->F));
-        k_pose_stats<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
-        LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
-        CU(cudaGetLastError());
-    }
-    CU(cudaMemcpyAsync(host.data(), h->sums, sizeof(double) * 16 * h->F, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
     const double inv = 1.0 / (double)h->M;
     for (int f = 0; f < h->F; ++f) {
-        const double *s = host.data() + 16 * f;
+        const double *s = sums + 16 * f;
         const double md[3] = {s[0] * inv, s[1] * inv, s[2] * inv};      // mean relative to the first particle
         for (int c = 0; c < 3; ++c) mean[6 * f + c] = s[13 + c] + md[c];
         mean[6 * f + 3] = s[3] * inv;
@@ -1330,6 +1375,129 @@ int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov)
         C[6] = 0.0;
         C[7] = 0.0;
     }
+}
+
+int reserve(DevBuf &b, size_t bytes)
+{
+    if (b.cap >= bytes) return AUVPF_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CU(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return AUVPF_OK;
+}
+}   // namespace
+
+int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov)
+{
+    if (!h || !mean || !cov) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    std::vector<double> host(16 * h->F);
+    {
+        Prof pr(h, AUVPF_K_ESTIMATE);
+        CU(cudaMemsetAsync(h->sums, 0, sizeof(double) * 16 * h->F, h->stream));
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 592 / h->F));
+        k_pose_stats<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
+        LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(host.data(), h->sums, sizeof(double) * 16 * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    finish_mean_cov(h, host.data(), mean, cov);
+    return AUVPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Replay of a recorded sequence: n_cycles x [n_steps predicts, MBES update, resample,
+// estimate] enqueued back to back from device-resident inputs.  The host uploads the sequence once,
+// reads the estimates back once, and does not wait in between.
+int auvpf_replay(auvpf_handle *h, int32_t n_cycles, int32_t n_steps, int32_t n_odom, const double *odom,
+                 const float *ranges, int32_t mode, int32_t flags, const double *u, const double *rough_var,
+                 double *mean_out, double *cov_out)
+{
+    if (!h || !odom || !ranges) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (n_cycles < 1) return fail(AUVPF_ERR_BADARG, "n_cycles must be positive");
+    if (n_steps < 1 || n_steps > AUVPF_MAX_PREDICT_STEPS)
+        return fail(AUVPF_ERR_BADARG, "n_steps must be 1..%d", AUVPF_MAX_PREDICT_STEPS);
+    if (n_odom != 1 && n_odom != h->F) return fail(AUVPF_ERR_BADARG, "n_odom must be 1 or n_filters");
+    if (is_device_ptr(odom)) return fail(AUVPF_ERR_BADARG, "odom must be host memory (11 scalars per filter and step)");
+    if (mode != AUVPF_SYSTEMATIC || (flags & (AUVPF_RS_INPLACE_REF | AUVPF_RS_STRICT_REF)))
+        return fail(AUVPF_ERR_BADARG, "replay runs the enqueue-only cycle: AUVPF_SYSTEMATIC, AUVPF_RS_SORTED");
+    if (h->global_count != h->M) return fail(AUVPF_ERR_BADARG, "replay is not available for a particle-sharded filter");
+    if (!h->have_dem || h->B <= 0) return fail(AUVPF_ERR_STATE, "replay needs set_dem and set_beams first");
+    if ((mean_out == nullptr) != (cov_out == nullptr)) return fail(AUVPF_ERR_BADARG, "mean_out and cov_out go together");
+    if (mean_out && (is_device_ptr(mean_out) || is_device_ptr(cov_out)))
+        return fail(AUVPF_ERR_BADARG, "mean_out / cov_out must be host memory");
+    Guard g(h);
+    int rc;
+    const int F = h->F;
+    // every step's motion parameters (make_predict: quaternion -> roll, pitch on the host), one upload
+    std::vector<PredictParams> all((size_t)n_cycles * n_steps * F);
+    for (int64_t t = 0; t < (int64_t)n_cycles * n_steps; ++t)
+        for (int f = 0; f < F; ++f)
+            all[(size_t)t * F + f] = make_predict(odom + 11 * ((size_t)t * n_odom + (n_odom > 1 ? f : 0)), h->cfg.motion_cov);
+    if ((rc = reserve(h->replay_params, sizeof(PredictParams) * all.size()))) return rc;
+    CU(cudaMemcpyAsync(h->replay_params.p, all.data(), sizeof(PredictParams) * all.size(), cudaMemcpyHostToDevice, h->stream));
+    const PredictParams *pp_all = static_cast<const PredictParams *>(h->replay_params.p);
+    // pings
+    const float *rg = ranges;
+    const size_t ping = (size_t)F * h->B;
+    if (!is_device_ptr(ranges)) {
+        if ((rc = reserve(h->replay_ranges, sizeof(float) * ping * n_cycles))) return rc;
+        CU(cudaMemcpyAsync(h->replay_ranges.p, ranges, sizeof(float) * ping * n_cycles, cudaMemcpyHostToDevice, h->stream));
+        rg = static_cast<const float *>(h->replay_ranges.p);
+    }
+    // the resamplers' uniforms: the caller's, or the same Philox draws the cycle-by-cycle calls make
+    const double *ud = u;
+    std::vector<double> uh;
+    if (!u || !is_device_ptr(u)) {
+        uh.resize((size_t)n_cycles * F);
+        for (int c = 0; c < n_cycles; ++c)
+            for (int f = 0; f < F; ++f)
+                uh[(size_t)c * F + f] =
+                    u ? u[(size_t)c * F + f] : uniform53(philox_for(h->cfg.seed, f, h->step_resample + (uint32_t)c, kStreamResample, 0));
+        if ((rc = reserve(h->replay_u, sizeof(double) * uh.size()))) return rc;
+        CU(cudaMemcpyAsync(h->replay_u.p, uh.data(), sizeof(double) * uh.size(), cudaMemcpyHostToDevice, h->stream));
+        ud = static_cast<const double *>(h->replay_u.p);
+    }
+    double *stats = nullptr;
+    if (mean_out) {
+        if ((rc = reserve(h->replay_stats, sizeof(double) * 16 * F * n_cycles))) return rc;
+        stats = static_cast<double *>(h->replay_stats.p);
+        CU(cudaMemsetAsync(stats, 0, sizeof(double) * 16 * F * n_cycles, h->stream));
+    }
+    // the staging vectors above must outlive their (pageable-memory) copies: those are synchronous with
+    // respect to the host buffer, so they are safe to drop when this function returns
+    const WeightSrc src{h->logw, nullptr, 0};
+    for (int c = 0; c < n_cycles; ++c) {
+        {
+            Prof pr(h, AUVPF_K_PROPAGATE);
+            const PredictParams *pp = pp_all + (size_t)c * n_steps * F;
+            k_propagate<<<grid1(h->M, kThreads * 4, F), kThreads, 0, h->stream>>>(
+                h->st[h->cur], h->M, all[(size_t)c * n_steps * F], (n_odom > 1 || n_steps > 1) ? pp : nullptr, n_steps,
+                h->cfg.seed, h->step_predict, h->global_offset, h->global_count, nullptr);
+            h->step_predict += (uint32_t)n_steps;
+            LAUNCHED(h, AUVPF_K_PROPAGATE, 1);
+            CU(cudaGetLastError());
+        }
+        if ((rc = auvpf_update_mbes(h, rg + (size_t)c * ping, nullptr))) return rc;
+        if ((rc = do_resample(h, src, mode, flags | AUVPF_RS_ASYNC, ud + (size_t)c * F, nullptr, rough_var, nullptr))) return rc;
+        if (stats) {
+            Prof pr(h, AUVPF_K_ESTIMATE);
+            int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 592 / F));
+            k_pose_stats<<<dim3(blocks, F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, stats + (size_t)c * 16 * F);
+            LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
+            CU(cudaGetLastError());
+        }
+    }
+    if (stats) {
+        std::vector<double> host((size_t)16 * F * n_cycles);
+        CU(cudaMemcpyAsync(host.data(), stats, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int c = 0; c < n_cycles; ++c)
+            finish_mean_cov(h, host.data() + (size_t)c * 16 * F, mean_out + (size_t)c * 6 * F, cov_out + (size_t)c * 9 * F);
+    }
     return AUVPF_OK;
 }
 
@@ -1339,6 +1507,36 @@ int auvpf_resample_status(auvpf_handle *h, int32_t *degenerate)
     Guard g(h);
     CU(cudaMemcpyAsync(degenerate, h->degenerate, sizeof(int) * h->F, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
+int auvpf_set_neff_gate(auvpf_handle *h, double ratio)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    if (!(ratio >= 0.0) || ratio > 1.0) return fail(AUVPF_ERR_BADARG, "N_eff gate ratio must lie in [0, 1]");
+    h->neff_ratio = ratio;
+    return AUVPF_OK;
+}
+
+int auvpf_resample_skipped(auvpf_handle *h, int32_t *skipped)
+{
+    if (!h || !skipped) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    CU(cudaMemcpyAsync(skipped, h->skipped, sizeof(int) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
+int auvpf_neff_fixed(auvpf_handle *h, double *neff)
+{
+    if (!h || !neff) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!h->have_norm) return fail(AUVPF_ERR_STATE, "no normalisation available: call auvpf_resample first");
+    if (h->global_count != h->M) return fail(AUVPF_ERR_STATE, "not available for a particle-sharded filter");
+    Guard g(h);
+    std::vector<unsigned long long> S(2 * (size_t)h->F);
+    CU(cudaMemcpyAsync(S.data(), h->sqlimbs, sizeof(unsigned long long) * 2 * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < h->F; ++f) neff[f] = neff_fixed(S[2 * f], S[2 * f + 1]);
     return AUVPF_OK;
 }
 
@@ -1581,7 +1779,8 @@ int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t defi
         Prof pr(h, AUVPF_K_SELECT_GATHER);
         StateView nodst{};
         k_select_gather<true><<<grid1(n_out, kSelTile, 1), kSelThreads, 0, h->stream>>>(
-            h->cdf, sp, h->u, h->deficit, h->st[h->cur], nodst, rd, nullptr, ad, none, nullptr, h->status, nullptr);
+            h->cdf, sp, h->u, h->deficit, h->st[h->cur], nodst, rd, nullptr, ad, none, nullptr, h->status, nullptr,
+            NeffGate{nullptr, 0.0, nullptr});
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }

@@ -739,6 +739,7 @@ struct NormState {
     unsigned long long *A;          // [2F] out
     int *degenerate;                // [F]  out
     double *sumsq;                  // [F]  zeroed
+    unsigned long long *sqlimbs;    // [2F] zeroed (integer sum of squares for the N_eff gate)
     unsigned long long *status;     // [tiles_total] zeroed
     unsigned int *tile_counter;     // zeroed
     long long tiles_total;
@@ -814,6 +815,8 @@ __global__ void __launch_bounds__(kThreads) k_normalise(WeightSrc w, int64_t M, 
             ns.wmax[f] = m;
             ns.degenerate[f] = (bad || a == 0) ? 1 : 0;
             ns.sumsq[f] = 0.0;
+            ns.sqlimbs[2 * f] = 0ull;
+            ns.sqlimbs[2 * f + 1] = 0ull;
             ns.done[f] = 0u;
         }
     }
@@ -864,7 +867,9 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
                                                volatile unsigned long long *status, unsigned int *tile_counter,
                                                int tiles_per_filter, unsigned long long *totals,
                                                double *sumsq /* optional: sum of (v 2^-52)^2 */,
-                                               unsigned long long *deficit = nullptr /* optional: 2^52 - total */)
+                                               unsigned long long *deficit = nullptr /* optional: 2^52 - total */,
+                                               unsigned long long *sqlimbs = nullptr /* optional: exact integer
+                                                   sum of (v >> 20)^2 as [low 32 bits, high bits] (neff_fixed) */)
 {
     __shared__ unsigned int s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
@@ -879,6 +884,7 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
     unsigned long long v[kScanItems];
     unsigned long long tsum = 0;
     double sq = 0.0;
+    unsigned long long sq_lo = 0, sq_hi = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         v[k] = (i0 + k < M) ? value(base + i0 + k, f) : 0ull;
@@ -886,6 +892,11 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
         if (sumsq) {
             double w = (double)v[k] * 2.220446049250313e-16;
             sq += w * w;
+        }
+        if (sqlimbs) {
+            const unsigned long long s2 = neff_square(v[k]);
+            sq_lo += s2 & 0xFFFFFFFFull;
+            sq_hi += s2 >> 32;
         }
     }
     // block exclusive scan of per-thread sums
@@ -962,6 +973,14 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
         sq = warp_sum_f64(sq);
         if (lane == 0) atomicAdd(sumsq + f, sq);
     }
+    if (sqlimbs) {      // integer atomics: the sum does not depend on the order the tiles arrive in
+        sq_lo = warp_sum_u64(sq_lo);
+        sq_hi = warp_sum_u64(sq_hi);
+        if (lane == 0) {
+            if (sq_lo) atomicAdd(sqlimbs + 2 * f, sq_lo);
+            if (sq_hi) atomicAdd(sqlimbs + 2 * f + 1, sq_hi);
+        }
+    }
 }
 
 // stage 3: q_i = floor(a_i 2^52 / A); inclusive integer CDF (raw: before the deficit units).
@@ -993,7 +1012,7 @@ k_scan_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A
 __global__ void __launch_bounds__(kThreads, 4)
 k_scan_q_from_a(int64_t M, const unsigned long long *A, unsigned long long *cdf, unsigned long long *status,
                 unsigned int *tile_counter, int tiles_per_filter, unsigned long long *Q, double *sumsq,
-                unsigned long long *deficit, const int *degenerate)
+                unsigned long long *deficit, const int *degenerate, unsigned long long *sqlimbs)
 {
     int cached_f = -1;
     QDiv d{};
@@ -1006,7 +1025,7 @@ k_scan_q_from_a(int64_t M, const unsigned long long *A, unsigned long long *cdf,
         }
         return dead ? 0ull : q_from_a(cdf[row], d);
     };
-    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit);
+    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit, sqlimbs);
 }
 
 // q_i itself (parity read-back): q_i + (i_global < D)
@@ -1070,12 +1089,23 @@ __device__ __forceinline__ int64_t search_cdf(const unsigned long long *cdf, int
     return lo;
 }
 
+// N_eff gate (auv_pf.py:174-181, commented out in the reference): with thresh = ratio * N > 0 a
+// filter whose neff_fixed (auvpf_math.cuh) is NOT below thresh skips the resample -- its state is
+// carried over unchanged, exactly like a filter without any finite weight.  Every block evaluates
+// the same integers, so the decision is uniform over the grid; block 0 records it in skipped[f].
+struct NeffGate {
+    const unsigned long long *sqlimbs;   // [2F] left by the scan; nullptr = no gate
+    double thresh;                       // ratio * N; 0 = always resample
+    int *skipped;                        // [F] out
+};
+
 template <bool kRecords>
 __global__ void __launch_bounds__(kSelThreads, 4)
 k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, const double *__restrict__ u_all,
                 const unsigned long long *__restrict__ deficit, StateView src, StateView dst, Record *records,
                 int32_t *anc32, int64_t *anc64, NoiseParams rough, const float *rough_noise,
-                const unsigned long long *__restrict__ tile_table, const int *__restrict__ degenerate)
+                const unsigned long long *__restrict__ tile_table, const int *__restrict__ degenerate,
+                NeffGate gate)
 {
     __shared__ unsigned long long s_cdf[kSelSpan];
     __shared__ int64_t s_j[2];
@@ -1086,18 +1116,26 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
     const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
     if (k0 >= p.n_out) return;
     const int64_t k1 = min(k0 + (int64_t)kSelTile, p.n_out) - 1;
-    if (degenerate && degenerate[f]) {
-        // no finite weight in this filter: its state is carried over unchanged (identity ancestors),
-        // so the buffers can flip without the host having to look at the flag first
-        if (!kRecords && dst.x != nullptr && p.n_out == p.M)
+    bool gated = false;
+    if (gate.sqlimbs) {
+        gated = gate.thresh > 0.0 && neff_fixed(gate.sqlimbs[2 * f], gate.sqlimbs[2 * f + 1]) >= gate.thresh;
+        if (blockIdx.x == 0 && threadIdx.x == 0) gate.skipped[f] = gated ? 1 : 0;
+    }
+    if ((degenerate && degenerate[f]) || gated) {
+        // no finite weight in this filter (or the N_eff gate holds the resample back): its state is
+        // carried over unchanged (identity ancestors), so the buffers can flip without the host
+        // having to look at the flag first
+        if (!kRecords && (dst.x != nullptr || anc32 != nullptr) && p.n_out == p.M)
             for (int64_t k = k0 + threadIdx.x; k <= k1; k += kSelThreads) {
                 const int64_t row = (int64_t)f * p.M + k;
-                dst.x[row] = src.x[row];
-                dst.y[row] = src.y[row];
-                dst.z[row] = src.z[row];
-                dst.roll[row] = src.roll[row];
-                dst.pitch[row] = src.pitch[row];
-                dst.yaw[row] = src.yaw[row];
+                if (dst.x != nullptr) {
+                    dst.x[row] = src.x[row];
+                    dst.y[row] = src.y[row];
+                    dst.z[row] = src.z[row];
+                    dst.roll[row] = src.roll[row];
+                    dst.pitch[row] = src.pitch[row];
+                    dst.yaw[row] = src.yaw[row];
+                }
                 if (anc32) anc32[row] = (int32_t)k;
             }
         return;
@@ -1652,6 +1690,13 @@ k_load_records(const Record *__restrict__ rec, int64_t n, StateView dst, NoisePa
 // ---------------------------------------------------------------------------------------------
 // Reference in-place slot map (a8): auv_pf.py:183-189 keep/lost/dupes + reassign_poses :195-198.
 constexpr int kNoFirst = 0x7f7f7f7f;
+
+// ancestors of a resample the N_eff gate held back: every particle is its own
+__global__ void __launch_bounds__(kThreads) k_identity_indices(int32_t *idx, int64_t M)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < M) idx[(int64_t)blockIdx.y * M + i] = (int32_t)i;
+}
 
 __global__ void __launch_bounds__(kThreads) k_first_occurrence(const int32_t *idx, int64_t M, int *first)
 {

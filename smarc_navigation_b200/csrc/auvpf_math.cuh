@@ -1189,6 +1189,24 @@ AUVPF_HD uint64_t q_from_a(uint64_t a, const QDiv &d)
 
 AUVPF_HD uint64_t q_from_a(uint64_t a, uint64_t A_lo, uint64_t A_hi) { return q_from_a(a, make_qdiv(A_lo, A_hi)); }
 
+// Effective sample size for the resampling gate (the block commented out at auv_pf.py:174-181:
+// N_eff = 1 / sum w^2, resample only when N_eff < pc / 2).  So that every block, every GPU and the
+// CPU oracle take the SAME decision, the sum of squares is an exact integer: s_i = min(q_i >> 20,
+// 2^32 - 1), S = sum s_i^2 accumulated as two limbs (low 32 bits, high bits), and
+//   neff_fixed = 2^64 / (double(S_hi) 2^32 + double(S_lo))
+// (w_i = q_i 2^-52, so sum w^2 ~= S 2^-64; relative error < 2^-7 even at 16 M equal weights).
+AUVPF_HD uint64_t neff_square(uint64_t q)
+{
+    uint64_t s = q >> 20;
+    if (s > 0xFFFFFFFFull) s = 0xFFFFFFFFull;
+    return s * s;
+}
+AUVPF_HD double neff_fixed(uint64_t S_lo, uint64_t S_hi)
+{
+    const double S = add_rn(mul_rn((double)S_hi, 4294967296.0), (double)S_lo);
+    return S > 0.0 ? 18446744073709551616.0 / S : 0.0;
+}
+
 // positions[i] = (u + i) / N of resampling.py:157, as the reference rounds it
 AUVPF_HD double sys_position(double u, int64_t i, double n)
 {

@@ -68,6 +68,9 @@ class ParticleFilter(object):
     ``strict_reference`` (residual only: reproduce resampling.py:70-74 literally,
     particle_count <= 65536).  ``resampler="residual", inplace_reference=True,
     strict_reference=True`` is the reference's ``resample()`` bit for bit.
+    ``resample_neff_ratio``: the gate the reference carries commented out
+    (auv_pf.py:174-181, ``if N_eff < self.pc/2.``): 0 (default) resamples on every call like
+    the live reference code, 0.5 is the commented value; see ``set_neff_gate``.
     """
 
     def __init__(self, particle_count=10, init_covariance=(0.,) * 6, motion_covariance=(0.,) * 6,
@@ -75,7 +78,7 @@ class ParticleFilter(object):
                  n_filters=1, seed=0, device=0, range_min=0.0, range_max=120.0, coarse_level=-1,
                  resampler="systematic", inplace_reference=False, strict_reference=False, init_mean=None,
                  init_noise=None,
-                 global_offset=0, global_count=0):
+                 global_offset=0, global_count=0, resample_neff_ratio=0.0):
         self._lib = _lib.load()
         self.pc = int(particle_count)
         self.n_filters = int(n_filters)
@@ -110,6 +113,9 @@ class ParticleFilter(object):
         _lib.check(self._lib.auvpf_create(C.byref(cfg), C.byref(self._h)))
         self.n_rows = self.pc * self.n_filters
         self.n_beams = 0
+        self.resample_neff_ratio = 0.0
+        if resample_neff_ratio:
+            self.set_neff_gate(resample_neff_ratio)
         # Particle.__init__: zero pose + add_noise(init_cov) (auv_particle.py:24,30)
         mean = np.zeros(6) if init_mean is None else np.asarray(init_mean, np.float64)
         self.init_particles(mean, self.init_cov, init_noise)
@@ -378,6 +384,59 @@ class ParticleFilter(object):
         with self._lock:
             _lib.check(self._lib.auvpf_neff(self._h, _ptr(out)))
         return out
+
+    # -- N_eff-gated resampling: the block commented out at auv_pf.py:174-181 -------------------
+    def set_neff_gate(self, ratio):
+        """``resample()`` holds a filter's resample back (poses, weights and roughening untouched)
+        whenever its ``N_eff = 1 / sum w^2`` is NOT below ``ratio * particle_count``; 0 switches the
+        gate off.  The decision is taken on the device (``neff_fixed``: exact integer arithmetic, so
+        it is reproducible and the CPU oracle takes the same one)."""
+        with self._lock:
+            _lib.check(self._lib.auvpf_set_neff_gate(self._h, float(ratio)))
+        self.resample_neff_ratio = float(ratio)
+
+    def neff_fixed(self):
+        """The integer-exact N_eff the gate compares (per filter) of the last normalisation."""
+        out = np.empty(self.n_filters, np.float64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_neff_fixed(self._h, _ptr(out)))
+        return out
+
+    def resample_skipped(self):
+        """Per filter: did the N_eff gate hold the last ``resample()`` back?  (synchronises)"""
+        out = np.zeros(self.n_filters, np.int32)
+        with self._lock:
+            _lib.check(self._lib.auvpf_resample_skipped(self._h, _ptr(out)))
+        return out.astype(bool)
+
+    # -- replay of a recorded sequence -------------------------------------------------------
+    def replay(self, odoms, ranges, u=None, roughen=True, estimates=True):
+        """Run ``n_cycles`` whole filter cycles -- per cycle: the odometry messages between two
+        pings (``predict_many``), the MBES ``update``, ``resample`` and the ``mean_cov`` estimate --
+        without the host in the loop: the sequence is uploaded once, the estimates are read back once.
+        ``odoms``: ``(n_cycles, n_steps, F or 1, 11)`` ABI rows (see ``predict``); ``ranges``:
+        ``(n_cycles, F or 1, B)``; ``u``: ``(n_cycles, F)`` uniforms or None (Philox).  Returns
+        ``(means (n_cycles, F, 6), covs (n_cycles, F, 3, 3))`` or None with ``estimates=False``
+        (enqueue only).  Bit-identical to making the calls one by one."""
+        if self.resampler != _lib.SYSTEMATIC or self.inplace_reference:
+            raise ValueError("replay runs the enqueue-only cycle: systematic resampler, sorted gather")
+        od = np.ascontiguousarray(odoms, np.float64)
+        if od.ndim != 4 or od.shape[3] != 11 or od.shape[2] not in (1, self.n_filters):
+            raise ValueError("odoms: (n_cycles, n_steps, F or 1, 11)")
+        n_cycles = od.shape[0]
+        r = np.asarray(ranges, np.float32).reshape(n_cycles, -1, self.n_beams)
+        r = np.ascontiguousarray(np.broadcast_to(r, (n_cycles, self.n_filters, self.n_beams)))
+        uu = None if u is None else np.ascontiguousarray(
+            np.broadcast_to(np.asarray(u, np.float64).reshape(n_cycles, -1), (n_cycles, self.n_filters)))
+        rv = (C.c_double * 6)(*self.res_noise_cov) if roughen else None
+        mean = np.empty((n_cycles, self.n_filters, 6), np.float64) if estimates else None
+        cov = np.empty((n_cycles, self.n_filters, 9), np.float64) if estimates else None
+        with self._lock:
+            _lib.check(self._lib.auvpf_replay(self._h, n_cycles, od.shape[1], od.shape[2], _ptr(od), _ptr(r),
+                                              self.resampler, _lib.RS_SORTED, _ptr(uu), rv, _ptr(mean), _ptr(cov)))
+        if not estimates:
+            return None
+        return mean, cov.reshape(n_cycles, self.n_filters, 3, 3)
 
     # -- measurement support -----------------------------------------------------------------
     def profile(self, on=True):

@@ -46,6 +46,8 @@ DEFAULTS = {
     "range_max": 120.0,
     "seed": 0,
     "device": 0,
+    "resample_neff_ratio": 0.0,                # 0 = resample at every fix like the live code; 0.5 = the gate
+                                               # the reference carries commented out (:174-181)
 }
 
 
@@ -79,7 +81,8 @@ class AuvPfNode(object):
                                  measurement_std=float(param("measurement_std")), m2o_matrix=m2o_matrix,
                                  resampler=param("resampler"), inplace_reference=bool(param("inplace_reference")),
                                  range_min=float(param("range_min")), range_max=float(param("range_max")),
-                                 seed=int(param("seed")), device=int(param("device")))
+                                 seed=int(param("seed")), device=int(param("device")),
+                                 resample_neff_ratio=float(param("resample_neff_ratio")))
         self.utm_to_map = utm_to_map or (lambda x, y: (x, y))
         self.publish_estimate = publish_estimate or (lambda est: None)
         self.publish_particles = publish_particles or (lambda poses: None)

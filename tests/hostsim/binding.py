@@ -124,3 +124,10 @@ def count_below(u, N, c):
 
 def wrap_pi(a):
     return float(lib().hs_wrap_pi(C.c_float(a)))
+
+
+def neff_fixed(q_raw):
+    q = np.ascontiguousarray(q_raw, np.uint64)
+    fn = lib().hs_neff_fixed
+    fn.restype = C.c_double
+    return float(fn(_p(q), C.c_long(len(q))))

@@ -365,4 +365,16 @@ void hs_prof_reasons(long *out, int reset)
 long hs_count_below(double u, long N, uint64_t c) { return (long)sys_count_below(u, N, c); }
 
 float hs_wrap_pi(float a) { return wrap_pi(a); }
+
+// the N_eff gate's integer sum of squares, accumulated like the scan kernel does (two limbs)
+double hs_neff_fixed(const uint64_t *q_raw, long n)
+{
+    uint64_t lo = 0, hi = 0;
+    for (long i = 0; i < n; ++i) {
+        const uint64_t s2 = neff_square(q_raw[i]);
+        lo += s2 & 0xFFFFFFFFull;
+        hi += s2 >> 32;
+    }
+    return neff_fixed(lo, hi);
+}
 }

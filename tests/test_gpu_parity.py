@@ -401,6 +401,65 @@ def test_degenerate_weights_raise_and_leave_state():
 
 
 # --------------------------------------------------------------------------- a8 reference slot map
+def test_neff_gated_resample_matches_the_oracle_gate():
+    """The gate the reference carries commented out (auv_pf.py:174-181: resample only when
+    N_eff < pc/2), decided on the device.  Per filter of one handle: the decision equals the
+    oracle's, a held-back filter keeps poses bit for bit (no roughening, identity ancestors), a
+    resampled one is exactly what the ungated filter produces."""
+    F, M = 4, 6000
+    rng = np.random.default_rng(21)
+    scales = [0.05, 0.7, 1.6, 8.0]                      # N_eff / M from ~1 down to a handful of particles
+    logw = np.concatenate([(rng.normal(0, s, M) - 30.0) for s in scales]).astype(np.float32)
+    poses = np.zeros((F * M, 6))
+    poses[:, 0] = np.arange(F * M)
+    poses[:, 1] = 0.5 * np.arange(F * M)
+    u = rng.uniform(size=F)
+    res = [0.01, 0.01, 0.0, 0.0, 0.0, 1e-5]
+    out = {}
+    for ratio in (0.0, 0.5):
+        pf = _pf(particle_count=M, n_filters=F, resampling_noise_covariance=res, seed=3, resample_neff_ratio=ratio)
+        pf.set_poses(poses)
+        pf.set_log_weights(logw)
+        anc = pf.resample(u=u, return_ancestors=True)
+        out[ratio] = (anc.reshape(F, M), pf.poses().reshape(F, M, 6), pf.resample_skipped(), pf.neff_fixed(), pf.neff())
+        pf.close()
+    anc0, p0, sk0, nf0, ne0 = out[0.0]
+    anc1, p1, sk1, nf1, ne1 = out[0.5]
+    assert not sk0.any()
+    want_skip = []
+    for f in range(F):
+        qq, a, A, m = o.quantise_logw(logw[f * M:(f + 1) * M])
+        raw = o.raw_quotients(a)
+        assert nf1[f] == o.neff_fixed_raw(raw) == nf0[f]
+        np.testing.assert_allclose(nf1[f], ne1[f], rtol=1e-2)
+        want_skip.append(not o.resample_gate(a, 0.5))
+    assert want_skip == [True, True, False, False]       # the cases straddle the gate
+    np.testing.assert_array_equal(sk1, want_skip)
+    for f in range(F):
+        if want_skip[f]:
+            np.testing.assert_array_equal(anc1[f], np.arange(M))
+            np.testing.assert_array_equal(p1[f], poses.reshape(F, M, 6)[f])
+        else:
+            np.testing.assert_array_equal(anc1[f], anc0[f])
+            np.testing.assert_array_equal(p1[f], p0[f])
+    # the synchronising paths (residual draw, reference slot map) take the same decision on the host
+    for kw in (dict(resampler="residual"), dict(inplace_reference=True), dict(resampler="residual", inplace_reference=True)):
+        for f in (1, 2):
+            pf = _pf(particle_count=M, resampling_noise_covariance=res, seed=3, resample_neff_ratio=0.5, **kw)
+            pf.set_poses(poses[f * M:(f + 1) * M])
+            pf.set_log_weights(logw[f * M:(f + 1) * M])
+            a = pf.resample(return_ancestors=True)
+            assert bool(pf.resample_skipped()[0]) == want_skip[f]
+            if want_skip[f]:
+                np.testing.assert_array_equal(a, np.arange(M))
+                np.testing.assert_array_equal(pf.poses(), poses[f * M:(f + 1) * M])
+            else:
+                assert not np.array_equal(pf.poses(), poses[f * M:(f + 1) * M])
+            pf.close()
+    with pytest.raises(Exception):
+        _pf(particle_count=64, n_filters=2, resampler="residual", resample_neff_ratio=0.5).resample()
+
+
 def test_inplace_reference_map(golden):
     """auv_pf.resample's keep/lost/dupes reassignment (auv_pf.py:183-198) on the golden
     residual_resample indices, then roughening with the reference's own draws."""
@@ -691,6 +750,63 @@ def test_c3_full_size_properties():
     np.testing.assert_array_equal(anc2, np.arange(N, dtype=np.int32))
     np.testing.assert_array_equal(pf.poses(), after)
     pf.close()
+
+
+def test_replay_equals_cycle_by_cycle():
+    """auvpf_replay (a recorded odometry / ping sequence run without the host in the loop) is the
+    same filter as predict_many + update + resample + mean_cov called cycle by cycle: poses and
+    estimates, two filters with their own odometry rows, the N_eff gate active."""
+    from smarc_navigation_b200.filter import _odom_row
+    dem = _dem(300, 2.0)
+    B, M, F, K, P = 96, 3000, 2, 7, 4
+    beams = world.make_beams(B)
+    MP = world.MBES_PARAMS
+    trajs = [world.Trajectory(600.0, seed=2 + f, predicts_per_cycle=P, offset=(3.0 * f, -2.0 * f)) for f in range(F)]
+    odoms = np.zeros((K, P, F, 11))
+    ranges = np.zeros((K, F, B), np.float32)
+    for c in range(K):
+        for f, tr in enumerate(trajs):
+            od, truth = tr.cycle()
+            odoms[c, :, f] = [_odom_row(x, None) for x in od]
+            r = c_oracle.update_mbes(dem, truth[None, :], np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX,
+                                     want_ranges=True)["ranges"][0]
+            ranges[c, f] = r + world.ping_noise(B, c + 100 * f)
+    ranges[3, 1, ::2] = np.nan                  # half of one ping unusable
+    kw = dict(particle_count=M, n_filters=F, init_covariance=MP["init_covariance"],
+              motion_covariance=MP["motion_covariance"], resampling_noise_covariance=MP["resampling_noise_covariance"],
+              measurement_std=MP["measurement_std"], range_min=world.RANGE_MIN, range_max=world.RANGE_MAX,
+              init_mean=np.array([0.3 * 600.0, 0.3 * 600.0, -5.0, 0, 0, 0]), seed=9,
+              resample_neff_ratio=0.5)
+    a, b = _pf(**kw), _pf(**kw)
+    for pf in (a, b):
+        pf.set_dem(dem)
+        pf.set_beams(beams)
+    np.testing.assert_array_equal(a.poses(), b.poses())
+    means, covs, skipped = [], [], []
+    for c in range(K):
+        a.predict_many(odoms[c])
+        a.update(ranges[c], return_weights=False)
+        a.resample(wait=False)
+        skipped.append(a.resample_skipped())
+        m, cv = a.mean_cov()
+        means.append(m)
+        covs.append(cv)
+    got_m, got_c = b.replay(odoms, ranges)
+    np.testing.assert_array_equal(b.poses(), a.poses())
+    # (the estimate's block partials meet in float64 atomics: equal up to the order of the additions)
+    np.testing.assert_allclose(got_m, np.stack(means), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got_c, np.stack(covs), rtol=1e-9, atol=1e-12)
+    np.testing.assert_array_equal(b.resample_skipped(), skipped[-1])
+    # enqueue-only form, caller's uniforms, no roughening: still the same as the calls one by one
+    u = np.random.default_rng(1).uniform(size=(K, F))
+    for c in range(K):
+        a.predict_many(odoms[c])
+        a.update(ranges[c], return_weights=False)
+        a.resample(u=u[c], roughen=False, wait=False)
+    assert b.replay(odoms, ranges, u=u, roughen=False, estimates=False) is None
+    np.testing.assert_array_equal(b.poses(), a.poses())
+    a.close()
+    b.close()
 
 
 def test_device_pointer_inputs():

@@ -368,3 +368,21 @@ def test_profile_merge_random_fans():
         sturdy = ~((dg[..., 0] < FRAGILE) | (dg[..., 1] < FRAGILE) | (dg[..., 2] < FRAGILE))
         assert sturdy.mean() > 0.97
         assert np.abs(r - ro)[sturdy].max() <= RANGE_TOL, (trial, B, a0, a1, psi, rmax)
+
+
+def test_neff_gate_arithmetic_is_the_oracles():
+    """auvpf_math.cuh neff_square / neff_fixed (the device gate of auv_pf.py:174-181) against the
+    oracle's restatement, and against the textbook 1 / sum w^2 it approximates."""
+    rng = np.random.default_rng(11)
+    cases = [(rng.standard_normal(4096) * s).astype(np.float32) for s in (0.0, 0.3, 3.0, 30.0)]
+    cases.append(np.r_[np.float32(0.0), np.full(999, -np.inf, np.float32)])        # one particle holds everything
+    cases.append(np.zeros(1, np.float32))
+    for lw in cases:
+        qq, a, A, m = o.quantise_logw(lw)
+        raw = o.raw_quotients(a)
+        got = hs.neff_fixed(raw)
+        assert got == o.neff_fixed_raw(raw)
+        ref = o.neff(o.weights_from_q(qq))
+        assert abs(got - ref) <= 1e-2 * ref
+        for ratio in (0.0, 0.1, 0.5, 1.0):
+            assert o.resample_gate(a, ratio) == (not (ratio > 0.0 and got >= ratio * len(lw)))
