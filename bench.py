@@ -326,14 +326,17 @@ def run_ours(args):
         filt.mean_cov()
     barrier()
     t0 = time.perf_counter()
+    e2e_lat = []
     for s in range(base + W, base + W + K):
+        t1 = time.perf_counter()
         filt.predict_many(cycles[s][0])
         if G > 1 and F == 1:
             filt.update_mbes(pings_pin[s].numpy())
         else:
             pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
         filt.resample(wait=False) if (G == 1 or F > 1) else filt.resample()
-        est = filt.mean_cov()
+        est = filt.mean_cov()                   # reads the estimate back: the cycle's results are on the host here
+        e2e_lat.append(1e3 * (time.perf_counter() - t1))
     barrier()
     e2e_s = time.perf_counter() - t0
     clk = clocks.stop()                         # sampled over both timed regions (device-resident and end-to-end)
@@ -398,7 +401,12 @@ def run_ours(args):
             "resampler": "systematic", "cycle_hz": 1e3 / ms_per_step},
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / K},
+                "ms_per_step": 1e3 * e2e_s / K,
+                # filter-cycle latency, host call to estimate on the host (BASELINE metric, second half)
+                "latency_ms": {"median": float(np.median(e2e_lat)), "p99": float(np.percentile(e2e_lat, 99)),
+                               "max": float(np.max(e2e_lat))}},
+        "cycle_latency_ms": {"median": float(np.median(step_ms)), "p99": float(np.percentile(step_ms, 99)),
+                             "max": float(np.max(step_ms)), "of": "device time per cycle (CUDA events), this rank"},
         "e2e_replay": replay,
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_update_mbes_profile (+ k_update_mbes for flagged particles): fused raycast + beam likelihood",
