@@ -91,6 +91,7 @@ struct auvpf_handle {
     unsigned long long *sqlimbs = nullptr;   // [2F] exact integer sum of squared weights (N_eff gate)
     int *skipped = nullptr;                  // [F] 1 = the N_eff gate held the last resample back
     double neff_ratio = 0.0;                 // resample only when N_eff < neff_ratio * N; 0 = always
+    bool sumsq_lazy = false;                 // the last scan was the fused one: sumsq is computed on request
     DevBuf replay_params, replay_ranges, replay_u, replay_stats;   // auvpf_replay: a whole recorded sequence
 
     // scan machinery
@@ -430,12 +431,13 @@ int run_scan(auvpf_handle *h, const WeightSrc &src, bool fused = false)
     }
     if (fused)      // a_i were left in h->cdf by k_normalise
         k_scan_q_from_a<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
-            h->M, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq, h->deficit,
+            h->M, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, nullptr, h->deficit,
             h->degenerate, h->sqlimbs);
     else
         k_scan_q<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
             src, h->M, h->wmax, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq,
             nullptr, nullptr);
+    h->sumsq_lazy = fused;
     LAUNCHED(h, AUVPF_K_SCAN, 1);
     CU(cudaGetLastError());
     return AUVPF_OK;
@@ -1546,6 +1548,15 @@ int auvpf_neff(auvpf_handle *h, double *neff)
     if (!h->have_norm) return fail(AUVPF_ERR_STATE, "no normalisation available: call auvpf_resample first");
     Guard g(h);
     std::vector<double> s(h->F);
+    if (h->sumsq_lazy) {        // valid while the weights of the last resample are still in place (like auvpf_get_weights_q)
+        CU(cudaMemsetAsync(h->sumsq, 0, sizeof(double) * h->F, h->stream));
+        WeightSrc src{h->logw, h->lin_weights, h->last_src_kind};
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
+        k_sumsq_from_src<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->A, h->degenerate, h->sumsq);
+        LAUNCHED(h, AUVPF_K_OTHER, 1);
+        CU(cudaGetLastError());
+        h->sumsq_lazy = false;
+    }
     CU(cudaMemcpyAsync(s.data(), h->sumsq, sizeof(double) * h->F, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (int f = 0; f < h->F; ++f) neff[f] = s[f] > 0.0 ? 1.0 / s[f] : 0.0;

@@ -766,19 +766,26 @@ __global__ void __launch_bounds__(kThreads) k_normalise(WeightSrc w, int64_t M, 
     const bool bad = !isfinite(m) || (w.kind == 1 && !(m > 0.0));
     unsigned long long lo = 0, hi = 0;
     if (!bad) {
-        // four independent loads in flight per thread before the long float64 exp chains start
-        const int64_t stride = (int64_t)gridDim.x * kThreads;
-        for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += 4 * stride) {
+        // A block owns ONE contiguous chunk of ceil(M / gridDim.x) particles (rounded up to 32 for sector
+        // alignment), so every block -- and with one wave of blocks every SM -- does the same work to
+        // within one element per thread.  (With a grid-stride loop over 4-element groups, 1 M particles
+        // on 740 blocks gave 284 blocks two trips and 456 blocks one: ncu showed the SMs busy for 58 %
+        // of the kernel.)  Four independent loads are in flight per thread before the long float64
+        // exp chains start.
+        const int64_t chunk = ((M + gridDim.x - 1) / gridDim.x + 31) & ~(int64_t)31;
+        const int64_t c0 = (int64_t)blockIdx.x * chunk, c1 = min(c0 + chunk, M);
+        for (int64_t i = c0 + threadIdx.x; i < c1; i += 4 * kThreads) {
             double xv[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const int64_t ii = i + k * stride;
-                xv[k] = ii < M ? src_value(w, (int64_t)f * M + ii) : (w.kind == 0 ? -INFINITY : 0.0);
+                const int64_t ii = i + k * kThreads;
+                xv[k] = ii < c1 ? src_value(w, (int64_t)f * M + ii) : (w.kind == 0 ? -INFINITY : 0.0);
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
+                if (i + k * kThreads >= c1) break;
                 const uint64_t a = w.kind == 0 ? a_from_x(xv[k] - (double)(float)m) : a_from_linear(xv[k], m);
-                if (i + k * stride < M) ns.a_out[(int64_t)f * M + i + k * stride] = a;
+                ns.a_out[(int64_t)f * M + i + k * kThreads] = a;
                 lo += a & 0xFFFFFFFFull;
                 hi += a >> 32;
             }
@@ -862,7 +869,10 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kThreads * kScanItems;
 constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (1ull << 62) - 1;
 
-template <class ValueFn>
+// kStaticTile: the tile is blockIdx.x (blocks are dispatched in index order, the assumption CUB's
+// single-pass scan makes too) instead of a ticket drawn from tile_counter, so a block can issue
+// its loads before anything else -- the ticket (atomic + barrier) was ~6 % of the stall samples.
+template <bool kStaticTile = false, class ValueFn>
 __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigned long long *__restrict__ out,
                                                volatile unsigned long long *status, unsigned int *tile_counter,
                                                int tiles_per_filter, unsigned long long *totals,
@@ -874,9 +884,11 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
     __shared__ unsigned int s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
     __shared__ unsigned long long s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    const unsigned int gtile = s_tile;
+    if (!kStaticTile) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        __syncthreads();
+    }
+    const unsigned int gtile = kStaticTile ? blockIdx.x : s_tile;
     const int f = gtile / tiles_per_filter, tile = gtile % tiles_per_filter;
     const int64_t base = (int64_t)f * M;
     const int64_t i0 = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
@@ -887,7 +899,7 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
     unsigned long long sq_lo = 0, sq_hi = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        v[k] = (i0 + k < M) ? value(base + i0 + k, f) : 0ull;
+        v[k] = (i0 + k < M) ? value(base + i0 + k, f, k) : 0ull;
         tsum += v[k];
         if (sumsq) {
             double w = (double)v[k] * 2.220446049250313e-16;
@@ -995,7 +1007,7 @@ k_scan_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A
     QDiv d{};
     double m = 0.0;
     bool dead = false;
-    auto value = [&](int64_t row, int f) -> unsigned long long {
+    auto value = [&](int64_t row, int f, int) -> unsigned long long {
         if (f != cached_f) {
             cached_f = f;
             d = make_qdiv(A[2 * f], A[2 * f + 1]);
@@ -1014,18 +1026,31 @@ k_scan_q_from_a(int64_t M, const unsigned long long *A, unsigned long long *cdf,
                 unsigned int *tile_counter, int tiles_per_filter, unsigned long long *Q, double *sumsq,
                 unsigned long long *deficit, const int *degenerate, unsigned long long *sqlimbs)
 {
-    int cached_f = -1;
-    QDiv d{};
-    bool dead = false;
-    auto value = [&](int64_t row, int f) -> unsigned long long {
-        if (f != cached_f) {
-            cached_f = f;
-            d = make_qdiv(A[2 * f], A[2 * f + 1]);
-            dead = degenerate[f] != 0;
+    // this block's a_i first (one tile = one filter), then the divisor: all loads are in flight together
+    const int f = blockIdx.x / tiles_per_filter, tile = blockIdx.x % tiles_per_filter;
+    const int64_t row0 = (int64_t)f * M + (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    const int64_t left = M - ((int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems);
+    unsigned long long raw[kScanItems];
+    if (left >= kScanItems) {           // 64 contiguous, 64-byte aligned bytes per thread (M is not assumed even)
+        if ((row0 & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < kScanItems; k += 2) {
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(cdf + row0 + k);
+                raw[k] = t.x;
+                raw[k + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k) raw[k] = cdf[row0 + k];
         }
-        return dead ? 0ull : q_from_a(cdf[row], d);
-    };
-    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit, sqlimbs);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) raw[k] = k < left ? cdf[row0 + k] : 0ull;
+    }
+    const QDiv d = make_qdiv(A[2 * f], A[2 * f + 1]);
+    const bool dead = degenerate[f] != 0;
+    auto value = [&](int64_t, int, int k) -> unsigned long long { return dead ? 0ull : q_from_a(raw[k], d); };
+    scan_tile_body<true>(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit, sqlimbs);
 }
 
 // q_i itself (parity read-back): q_i + (i_global < D)
@@ -1039,6 +1064,25 @@ k_emit_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A
     int64_t row = (int64_t)f * M + i;
     unsigned long long q = q_from_a(src_a(w, row, wmax[f]), A[2 * f], A[2 * f + 1]);
     q_out[row] = q + (((unsigned long long)(global_offset + i) < deficit[f]) ? 1ull : 0ull);
+}
+
+// sum_i (q_i 2^-52)^2 of the raw quotients (auvpf_neff = 1 / that), recomputed from the weight source on
+// request: the fused scan no longer carries this float64 reduction in the filter cycle
+__global__ void __launch_bounds__(kThreads)
+k_sumsq_from_src(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A, const int *degenerate,
+                 double *sumsq)
+{
+    const int f = blockIdx.y;
+    if (degenerate[f]) return;
+    const QDiv d = make_qdiv(A[2 * f], A[2 * f + 1]);
+    const double m = wmax[f];
+    double sq = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        const double v = (double)q_from_a(src_a(w, (int64_t)f * M + i, m), d) * 2.220446049250313e-16;
+        sq += v * v;
+    }
+    sq = warp_sum_f64(sq);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sumsq + f, sq);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1526,7 +1570,7 @@ k_scan_copies(const unsigned long long *cdf, int64_t M, const unsigned long long
               unsigned long long *out, unsigned long long *status, unsigned int *tile_counter, int tiles_per_filter,
               unsigned long long *totals)
 {
-    auto value = [&](int64_t row, int f) -> unsigned long long {
+    auto value = [&](int64_t row, int f, int) -> unsigned long long {
         const int64_t base = (int64_t)f * M;
         return residual_copies(q_from_cdf(cdf, base, row - base, deficit[f], global_offset), M);
     };
@@ -1539,7 +1583,7 @@ k_scan_fracs(const unsigned long long *cdf, int64_t M, const unsigned long long 
              unsigned long long *out, unsigned long long *status, unsigned int *tile_counter, int tiles_per_filter,
              unsigned long long *totals)
 {
-    auto value = [&](int64_t row, int f) -> unsigned long long {
+    auto value = [&](int64_t row, int f, int) -> unsigned long long {
         const int64_t base = (int64_t)f * M;
         const unsigned long long q = q_from_cdf(cdf, base, row - base, deficit[f], global_offset);
         return residual_frac(q, residual_copies(q, M), M);
@@ -1712,7 +1756,7 @@ __global__ void __launch_bounds__(kThreads)
 k_scan_lost(const int *first, int64_t M, unsigned long long *out, unsigned long long *status,
             unsigned int *tile_counter, int tiles_per_filter, unsigned long long *totals)
 {
-    auto value = [&](int64_t row, int) -> unsigned long long { return first[row] == kNoFirst ? 1ull : 0ull; };
+    auto value = [&](int64_t row, int, int) -> unsigned long long { return first[row] == kNoFirst ? 1ull : 0ull; };
     scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
 }
 
@@ -1720,7 +1764,7 @@ __global__ void __launch_bounds__(kThreads)
 k_scan_dupes(const int *first, const int32_t *idx, int64_t M, unsigned long long *out, unsigned long long *status,
              unsigned int *tile_counter, int tiles_per_filter, unsigned long long *totals)
 {
-    auto value = [&](int64_t row, int f) -> unsigned long long {
+    auto value = [&](int64_t row, int f, int) -> unsigned long long {
         int64_t base = (int64_t)f * M;
         int j = idx[row];
         return first[base + j] != (int)(row - base) ? 1ull : 0ull;
