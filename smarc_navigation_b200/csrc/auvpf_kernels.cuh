@@ -1094,7 +1094,8 @@ constexpr int kSelThreads = 256;  // (128 threads x 2 groups, one wave of 7 bloc
 constexpr int kSelItems = 4;      // adjacent outputs a thread resolves together
 constexpr int kSelGroups = 1;     // groups of kSelItems per thread
 constexpr int kSelTile = kSelThreads * kSelItems * kSelGroups;
-constexpr int kSelSpan = 2 * kScanTile;   // CDF entries staged per block: two scan tiles (32 KB)
+constexpr int kSelSpan = 2 * kScanTile;   // CDF entries staged per block by the peer-memory variant: two scan tiles (32 KB)
+constexpr int kSrcItems = 8;              // consecutive source particles per thread and pass of k_select_gather
 
 struct SelectParams {
     int64_t M;             // local particles per filter (CDF length)
@@ -1105,6 +1106,7 @@ struct SelectParams {
     unsigned long long q_offset;   // integer CDF mass of lower shards
     int tiles_per_filter;  // scan tiles per filter (tile table = the scan's status words)
 };
+
 
 // Integer form of the reference's comparison positions[i] < cumsum[j] (resampling.py:163):
 // cumsum[j] = c 2^-52 exactly and pos 2^52 is an exact float64, so  pos < c 2^-52  <=>
@@ -1143,16 +1145,20 @@ struct NeffGate {
     int *skipped;                        // [F] out
 };
 
+#ifndef AUVPF_SEL_MINB
+#define AUVPF_SEL_MINB 4     // resident blocks per SM the select kernel is compiled for (tuning builds override)
+#endif
 template <bool kRecords>
-__global__ void __launch_bounds__(kSelThreads, 4)
+__global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB)
 k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, const double *__restrict__ u_all,
                 const unsigned long long *__restrict__ deficit, StateView src, StateView dst, Record *records,
                 int32_t *anc32, int64_t *anc64, NoiseParams rough, const float *rough_noise,
                 const unsigned long long *__restrict__ tile_table, const int *__restrict__ degenerate,
                 NeffGate gate)
 {
-    __shared__ unsigned long long s_cdf[kSelSpan];
-    __shared__ int64_t s_j[2];
+    __shared__ int s_head[kSelTile];              // output slot -> 1 + (first ancestor whose run of offspring starts there - j_lo), else 0
+    __shared__ int s_wmax[kSelThreads / 32];
+    __shared__ int s_t[2];
     const int f = blockIdx.y;
     const unsigned long long *cdf = cdf_all + (size_t)f * p.M;
     const unsigned long long D = deficit[f];
@@ -1184,91 +1190,146 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
             }
         return;
     }
-    // Level 1: the scan tiles holding the ancestors of the block's first and last output.  The
-    // tile table (inclusive prefix per tile, left in the status words by the scan) is read with
-    // coalesced loads and COUNTED (tiles whose end lies at or below the position), so there is no
-    // dependent chain of global loads.
-    const unsigned long long key_lo = pos_key(sys_position(u, p.out_lo + k0, n)),
-                             key_hi = pos_key(sys_position(u, p.out_lo + k1, n));
-    int t_lo = 0, t_hi = 0;
-    {
+    // Level 1: the scan tiles holding the ancestors of the block's first (warp 0) and last (warp 1) output:
+    // a 32-ary search of the tile table (inclusive prefix per tile, left in the status words by the scan) --
+    // 32 evenly spaced entries per step, one ballot -- so 1024 tiles take two dependent loads.  While the
+    // two warps search, everybody clears the run heads; ONE barrier publishes both.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < kSelItems; ++r) s_head[threadIdx.x * kSelItems + r] = 0;
+    if (warp < 2) {
+        const unsigned long long key = pos_key(sys_position(u, p.out_lo + (warp == 0 ? k0 : k1), n));
         const unsigned long long *tab = tile_table + (size_t)f * p.tiles_per_filter;
-        for (int t0 = 0; t0 < p.tiles_per_filter; t0 += kSelThreads) {
-            const int t = t0 + threadIdx.x;
-            bool below_lo = false, below_hi = false;
-            if (t < p.tiles_per_filter) {
+        int lo = 0, hi = p.tiles_per_filter;           // tiles [0, lo) end at or below the key, tile hi (if any) above
+        while (lo < hi) {
+            const int step = (hi - lo + 31) >> 5;
+            const int t = lo + (lane + 1) * step - 1;  // last tile of this lane's chunk
+            bool below = false;
+            if (t < hi) {
                 const int64_t je = min((int64_t)(t + 1) * kScanTile, p.M) - 1;
                 const unsigned long long jg1 = (unsigned long long)(p.j_global0 + je + 1);
                 const unsigned long long c = p.q_offset + (tab[t] & kValMask) + (jg1 < D ? jg1 : D);
-                below_lo = !(key_lo < c);
-                below_hi = !(key_hi < c);
+                below = !(key < c);
             }
-            const int c_lo = __syncthreads_count(below_lo), c_hi = __syncthreads_count(below_hi);
-            t_lo += c_lo;
-            t_hi += c_hi;
-            if (c_hi < kSelThreads) break;                 // monotone table: nothing further can be below
+            const int nb = __popc(__ballot_sync(0xffffffffu, below));   // monotone table: a prefix of the lanes
+            lo += nb * step;
+            hi = min(lo + step - 1, hi);               // the chunk's last tile is known to lie above (or past the end)
         }
-        t_lo = min(t_lo, p.tiles_per_filter - 1);
-        t_hi = min(t_hi, p.tiles_per_filter - 1);
+        if (lane == 0) s_t[warp] = min(lo, p.tiles_per_filter - 1);
     }
-    // Level 2: stage the CDF of those tiles (usually one or two) and search it in shared memory.
-    int64_t j_lo = (int64_t)t_lo * kScanTile, j_hi = min((int64_t)(t_hi + 1) * kScanTile, p.M) - 1;
-    if (j_hi - j_lo + 1 > kSelSpan) {
-        // many low-weight particles between the two ends: locate them exactly (global search)
-        if (threadIdx.x == 0) s_j[0] = search_cdf(cdf, j_lo, j_hi + 1, key_lo, p, D);
-        if (threadIdx.x == 32) s_j[1] = search_cdf(cdf, j_lo, j_hi + 1, key_hi, p, D);
-        __syncthreads();
-        j_lo = min(s_j[0], p.M - 1);
-        j_hi = min(s_j[1], p.M - 1);
-    }
-    const int64_t span = j_hi - j_lo + 1;
-    const bool staged = span <= kSelSpan;
-    if (staged)
-        for (int64_t t = threadIdx.x; t < span; t += kSelThreads) s_cdf[t] = full_cdf(cdf, j_lo + t, p, D);
     __syncthreads();
-
-    // Each thread resolves kSelItems ADJACENT outputs: the first by binary search, the others by
-    // walking on from it (ancestors of consecutive outputs are equal or adjacent most of the time).
-    for (int grp = 0; grp < kSelGroups; ++grp) {
-    const int64_t kb = k0 + ((int64_t)grp * kSelThreads + threadIdx.x) * kSelItems;
-    if (kb > k1) return;
+    const int t_lo = s_t[0], t_hi = s_t[1];
+    // Level 2, from the SOURCE side: output slot i descends from particle j iff
+    //   count_below(cdf[j-1]) <= i < count_below(cdf[j]),   count_below(c) = #{i : positions[i] < c}
+    // (positions and the CDF are both non-decreasing), and count_below is a closed form
+    // (sys_count_below: one fma + ceil; the reference's own expression only when the estimate is within
+    // 1e-5 of an integer).  So the block walks the particles of the located tiles once -- coalesced
+    // 128-bit loads, kSrcItems consecutive particles per thread -- and every particle that has offspring
+    // in this block marks the slot where its run starts; an inclusive max-scan over the slots then
+    // names every output's ancestor.  No position is evaluated per output and nothing is searched.
+    // (The previous version staged the tiles' CDF in shared memory and ran a binary search + short walk
+    // per output: 458 thread instructions per particle, ncu.)
+    const int64_t j_lo = (int64_t)t_lo * kScanTile, j_hi = min((int64_t)(t_hi + 1) * kScanTile, p.M) - 1;
+    const int nblk = (int)(k1 - k0 + 1);
+    const int64_t g0 = p.out_lo + k0;                  // global index of the block's first output
     const SysPos spos = make_sys_pos(u, n);
-    int64_t jj[kSelItems];
+    const double n_scaled = n * 2.220446049250313e-16, g0d = (double)g0, nblk_d = (double)nblk;   // n 2^-52: exact
+    // block-relative end of source j's run: clamp(count_below(cdf[j]) - g0, 0, nblk).  Only values inside
+    // (0, nblk) need the count itself; x = estimate - g0 decides the rest (same 1e-5 margin as
+    // sys_count_below, which is called when x is that close to an integer).
+    auto rel_end = [&](unsigned long long cdfv, int64_t j) -> int {
+        const unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
+        const unsigned long long c = p.q_offset + cdfv + (jg1 < D ? jg1 : D);
+        // (double)c for c <= 2^52 without a 64-bit conversion: 2^52 + c is exact in the mantissa
+        const double cd = __longlong_as_double((long long)(0x4330000000000000ull + c)) - 4503599627370496.0;
+        const double x = fma(cd, n_scaled, -u) - g0d;
+        if (x < -1.0e-5) return 0;
+        if (x > nblk_d + 1.0e-5) return nblk;
+        const int ie = __double2int_ru(x);
+        const double r = (double)ie - x;                       // in [0, 1)
+        if (r > 1.0e-5 && r < 1.0 - 1.0e-5) return min(max(ie, 0), nblk);
+        const int64_t g = sys_count_below(spos, p.n_global, c) - g0;
+        return (int)(g < 0 ? 0 : (g > nblk ? nblk : g));
+    };
+    for (int64_t jb = j_lo; jb <= j_hi; jb += (int64_t)kSelThreads * kSrcItems) {
+        // all the outputs of the block are handed out once the pass's first particle already ends at nblk
+        // (block-uniform: every thread evaluates the same entry)
+        if (jb > j_lo && rel_end(cdf[jb - 1], jb - 1) >= nblk) break;
+        const int64_t j0 = jb + (int64_t)threadIdx.x * kSrcItems;
+        unsigned long long cv[kSrcItems];
+        const bool has_prev = lane == 0 && j0 > j_lo && j0 - 1 <= j_hi;
+        const unsigned long long cprev = has_prev ? cdf[j0 - 1] : 0ull;      // in flight with the thread's own entries
+        if (j0 + kSrcItems - 1 <= j_hi && ((reinterpret_cast<uintptr_t>(cdf + j0) & 15) == 0)) {
+#pragma unroll
+            for (int k = 0; k < kSrcItems; k += 2) {
+                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(cdf + j0 + k);
+                cv[k] = t.x;
+                cv[k + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSrcItems; ++k) cv[k] = j0 + k <= j_hi ? cdf[j0 + k] : 0ull;
+        }
+        // the ends are non-decreasing in j: a thread whose LAST particle ends at 0 lies before the block, one
+        // whose FIRST particle ends at nblk lies behind it; only threads across the block evaluate all
+        int e[kSrcItems];
+        const bool whole = j0 + kSrcItems - 1 <= j_hi;
+        const int e_last = whole ? rel_end(cv[kSrcItems - 1], j0 + kSrcItems - 1) : nblk;
+        const int e_first = (e_last == 0) ? 0 : (j0 <= j_hi ? rel_end(cv[0], j0) : nblk);
+        if (e_last == 0 || e_first == nblk) {
+#pragma unroll
+            for (int k = 0; k < kSrcItems; ++k) e[k] = e_first;
+        } else {
+            e[0] = e_first;
+#pragma unroll
+            for (int k = 1; k < kSrcItems - 1; ++k) e[k] = j0 + k <= j_hi ? rel_end(cv[k], j0 + k) : nblk;
+            e[kSrcItems - 1] = e_last;
+        }
+        // where this thread's first run starts = where the previous particle's run ends: the lane below
+        // has it; lane 0 evaluates the particle before its own (no block barrier for the hand-over), and
+        // the block's first located particle starts at slot 0
+        int start = __shfl_up_sync(0xffffffffu, e[kSrcItems - 1], 1);
+        if (lane == 0) start = has_prev ? rel_end(cprev, j0 - 1) : (j0 > j_lo ? nblk : 0);
+#pragma unroll
+        for (int k = 0; k < kSrcItems; ++k) {
+            if (e[k] > start) s_head[start] = (int)(j0 + k - j_lo) + 1;   // starts are distinct: one writer per slot
+            start = e[k];
+        }
+    }
+    __syncthreads();
+    // inclusive max-scan of the run heads (ancestor indices increase with the slot): thread-local over its
+    // kSelItems adjacent outputs, warp shuffle, then the warps' maxima
+    int head[kSelItems];
     {
-        int64_t prev = 0;       // index into the staged window / offset from j_lo
+        int m = 0;
 #pragma unroll
         for (int r = 0; r < kSelItems; ++r) {
-            const int64_t k = kb + r;
-            if (k > k1) {
-                jj[r] = 0;
-                continue;
-            }
-            const unsigned long long key = pos_key(sys_position(spos, p.out_lo + k));
-            int64_t j;
-            if (staged) {
-                int lo = (int)prev, hi = (int)span;
-                if (r > 0) {                                   // short walk first
-                    int w = 0;
-                    while (w < 4 && lo < hi && !(key < s_cdf[lo])) {
-                        ++lo;
-                        ++w;
-                    }
-                    if (lo < hi && key < s_cdf[lo]) hi = lo;   // found
-                }
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (key < s_cdf[mid]) hi = mid;
-                    else lo = mid + 1;
-                }
-                prev = lo;
-                j = j_lo + lo;
-            } else {
-                j = search_cdf(cdf, j_lo + prev, j_hi + 1, key, p, D);
-                prev = j - j_lo;
-            }
-            jj[r] = min(j, p.M - 1);                           // reference would run off the end (IndexError); clamp
+            m = max(m, s_head[threadIdx.x * kSelItems + r]);
+            head[r] = m;
         }
+        int incl = m;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl = max(incl, t);
+        }
+        int pre = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) pre = 0;
+        if (lane == 31) s_wmax[warp] = incl;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSelThreads / 32; ++k)
+            if (k < warp) pre = max(pre, s_wmax[k]);
+#pragma unroll
+        for (int r = 0; r < kSelItems; ++r) head[r] = max(head[r], pre);
     }
+    const int64_t kb = k0 + (int64_t)threadIdx.x * kSelItems;
+    if (kb > k1) return;
+    int64_t jj[kSelItems];
+#pragma unroll
+    for (int r = 0; r < kSelItems; ++r)               // (a slot before every head cannot occur: the first located particle
+        jj[r] = min(j_lo + max(head[r] - 1, 0), p.M - 1);   //  with offspring here starts at slot 0; the clamp mirrors the old code)
+    {
     const int64_t orow0 = (int64_t)f * p.n_out + kb;
     const bool full4 = kb + kSelItems - 1 <= k1;
     double x[kSelItems], y[kSelItems];
@@ -1296,9 +1357,9 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
             Record rec = {x[r], y[r], z[r], ro[r], pi[r], ya[r]};
             records[orow0 + r] = rec;
         }
-        continue;
+        return;
     }
-    if (dst.x == nullptr) continue;
+    if (dst.x == nullptr) return;
     if (rough.mode == 1) {       // fused add_noise (auv_pf.py:191-192)
 #pragma unroll
         for (int r = 0; r < kSelItems; ++r) {
@@ -1332,7 +1393,7 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
             dst.yaw[orow0 + r] = ya[r];
         }
     }
-    }   // groups
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1245,19 +1245,32 @@ AUVPF_HD double sys_position(const SysPos &p, int64_t i)
 // exact float64 value of an integer CDF entry (<= 2^52)
 AUVPF_HD double cdf_value(uint64_t c) { return (double)c * 2.220446049250313e-16; }
 
-// number of outputs i in [0, N) with positions[i] < cdf(c): the first i with positions[i] >= c 2^-52
-AUVPF_HD int64_t sys_count_below(double u, int64_t N, uint64_t c)
+// number of outputs i in [0, N) with positions[i] < cdf(c), positions[i] = RN(RN(u + i) / N) as the
+// reference rounds them (resampling.py:157).
+// Fast path: est = fma(cv, N, -u) differs from the real threshold T_i of "positions[i] < cv <=> i < T_i"
+// by the roundings of u + i, of the quotient and of est itself: at most 3 N 2^-53 (< 7.2e-7 for
+// N < 2^31).  So when est is further than 1e-5 from every integer, i < T_i <=> i < est for all i and
+// the count is ceil(est) -- no position has to be evaluated.  Otherwise (2e-5 of the cases) the count
+// is fixed up with the reference's own expression, which is monotone in i.
+AUVPF_HD int64_t sys_count_below(const SysPos &sp, int64_t N, uint64_t c)
 {
-    double n = (double)N;
-    double cv = cdf_value(c);
-    double est = cv * n - u;
+    const double cv = cdf_value(c);
+    const double est = fma(cv, sp.n, -sp.u);
+    if (fabs(est - rint(est)) > 1.0e-5) {
+        const int64_t i = (int64_t)ceil(est);
+        return i < 0 ? 0 : (i > N ? N : i);
+    }
     int64_t i = (int64_t)floor(est);
     if (i < 0) i = 0;
     if (i > N) i = N;
-    // fix up with the reference's own expression (monotone in i)
-    while (i > 0 && !(sys_position(u, i - 1, n) < cv)) --i;
-    while (i < N && sys_position(u, i, n) < cv) ++i;
+    while (i > 0 && !(sys_position(sp, i - 1) < cv)) --i;
+    while (i < N && sys_position(sp, i) < cv) ++i;
     return i;
+}
+
+AUVPF_HD int64_t sys_count_below(double u, int64_t N, uint64_t c)
+{
+    return sys_count_below(make_sys_pos(u, (double)N), N, c);
 }
 
 // ---------------------------------------------------------------------------------------------

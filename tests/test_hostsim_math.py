@@ -250,12 +250,38 @@ def test_residual_resample_strict_and_fixed(golden):
 
 
 def test_count_below_matches_positions():
+    """sys_count_below (closed form, fixed up with the reference's expression only when the estimate is
+    within 1e-5 of an integer) == counting positions[i] < cdf, including CDF values that sit exactly on,
+    one unit below and one unit above a position (the estimate is then an integer up to rounding)."""
     rng = np.random.default_rng(1)
-    for N in (1, 7, 1000, 1 << 20):
-        u = float(rng.uniform())
-        pos = (u + np.arange(N)) / float(N)
-        for c in [0, 1, 1 << 51, (1 << 52) - 1, 1 << 52] + [int(x) for x in rng.integers(0, 1 << 52, 20)]:
-            assert hs.count_below(u, N, c) == int((pos < np.ldexp(float(c), -52)).sum())
+    for N in (1, 7, 1000, 1 << 20, (1 << 24) + 3):
+        for u in (float(rng.uniform()), 0.0, 1.0 - 2.0 ** -53, 2.0 ** -30):
+            pos = (u + np.arange(N)) / float(N)
+            cs = [0, 1, 1 << 51, (1 << 52) - 1, 1 << 52] + [int(x) for x in rng.integers(0, 1 << 52, 20)]
+            for i in [0, N - 1] + [int(x) for x in rng.integers(0, N, 12)]:
+                k = int(np.floor(np.ldexp(pos[i], 52)))
+                cs += [max(k - 1, 0), k, min(k + 1, 1 << 52)]
+            for c in cs:
+                want = int(np.searchsorted(pos, np.ldexp(float(c), -52), side="left"))     # pos is non-decreasing
+                assert hs.count_below(u, N, c) == want, (N, u, c)
+
+
+def test_count_below_beyond_array_sizes():
+    """N near 2^31 (no array of positions): the count must satisfy its definition at the boundary."""
+    rng = np.random.default_rng(2)
+    N = (1 << 31) - 5
+    for u in (float(rng.uniform()), 0.0, 0.999999):
+        position = lambda i: (u + float(i)) / float(N)
+        for t in range(40):
+            i = int(rng.integers(0, N))
+            k = int(np.floor(np.ldexp(position(i), 52)))
+            for c in (k - 1, k, k + 1, int(rng.integers(0, 1 << 52))):
+                c = min(max(c, 0), 1 << 52)
+                cv = np.ldexp(float(c), -52)
+                g = hs.count_below(u, N, c)
+                assert 0 <= g <= N
+                assert g == 0 or position(g - 1) < cv
+                assert g == N or not (position(g) < cv)
 
 
 def _ridged_dem(n=400, res=0.5, seed=5):
