@@ -112,3 +112,56 @@ def test_sharded_resample_on_gpus(tmp_path, M, seed, exchange):
     assert all(bool(p["deg"]) for p in parts)
     np.testing.assert_array_equal(np.concatenate([p["poses3"] for p in parts]), got2)
     pf.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,M,seed", [(2, 5000, 0), (3, 70001, 1), (4, 1 << 18, 2)])
+def test_shard_stages_on_one_gpu(G, M, seed):
+    """The shard stages of the C ABI (max / exact sum / scan / emit / load: the NCCL-exchange variant's
+    kernels, k_select_gather<records> with non-trivial q_offset, j_global0 and output ranges) driven
+    by hand for G handles that share ONE GPU, so the single-GPU test run covers them too: ancestors
+    bit-exact against the oracle and against one handle holding every particle."""
+    import torch
+    from oracle import c_oracle, pf_oracle as o
+    from smarc_navigation_b200 import ParticleFilter
+    from smarc_navigation_b200.sharded import GpuShardOps, plan_exchange, splits_for
+    rng = np.random.default_rng(seed)
+    N = G * M
+    logw = (rng.normal(0, 4.0, N) - 150).astype(np.float32)
+    if seed % 2:
+        logw[: N // 2 + 3] -= 60.0                      # almost all mass on the upper shards
+    logw[7] = -np.inf
+    poses = np.zeros((N, 6))
+    poses[:, 0] = np.arange(N)
+    poses[:, 1] = -0.25 * np.arange(N)
+    poses[:, 5] = rng.uniform(-3, 3, N).astype(np.float32)
+    u = float(rng.uniform())
+    pfs = [ParticleFilter(particle_count=M, global_offset=g * M, global_count=N, seed=seed,
+                          resampling_noise_covariance=[0.0] * 6) for g in range(G)]
+    ops = [GpuShardOps(pf) for pf in pfs]
+    for g, pf in enumerate(pfs):
+        pf.set_poses(poses[g * M:(g + 1) * M])
+        pf.set_log_weights(logw[g * M:(g + 1) * M])
+    m = max(op.shard_max() for op in ops)
+    limbs = np.sum([op.shard_sum(m) for op in ops], axis=0, dtype=object)
+    A = int(limbs[0]) + (int(limbs[1]) << 32)
+    Q_all = [op.shard_scan(m, A) for op in ops]
+    D, q_offsets, bounds = plan_exchange(Q_all, M, u)
+    sends = [ops[g].shard_emit(u, q_offsets[g], D, bounds[g], bounds[g + 1]) for g in range(G)]
+    everything = torch.cat(sends)                        # offspring in global output order
+    assert everything.shape[0] == N
+    for g in range(G):
+        send_counts, recv_counts = splits_for(bounds, M, g)
+        assert sum(recv_counts) == M and sum(send_counts) == sends[g].shape[0]
+        ops[g].shard_load(everything[g * M:(g + 1) * M].contiguous())
+    got = np.concatenate([pf.poses() for pf in pfs])
+    anc = c_oracle.systematic(o.weights_from_q(c_oracle.quantise_logw(logw)[0]), u)
+    np.testing.assert_array_equal(got[:, 0], poses[anc, 0])
+    np.testing.assert_array_equal(got[:, 1], poses[anc, 1])
+    np.testing.assert_array_equal(got[:, 5], poses[anc, 5])
+    one = ParticleFilter(particle_count=N, resampling_noise_covariance=[0.0] * 6, seed=seed)
+    one.set_poses(poses)
+    one.set_log_weights(logw)
+    np.testing.assert_array_equal(one.resample(u=u, return_ancestors=True, roughen=False), anc)
+    for pf in pfs + [one]:
+        pf.close()
