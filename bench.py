@@ -37,10 +37,10 @@ UNIT = "evals/s"
 P_PREDICTS = 5
 # dram__bytes_read.sum + dram__bytes_write.sum of k_update_mbes_profile per launch, from the committed ncu --set full
 # capture (profiles/r1_ncu_update_mbes_profile.txt); only the workload that was captured has a figure
-NCU_DRAM_TRAFFIC = {"C3": 33.64e6 + 0.81e6}
+NCU_DRAM_TRAFFIC = {"C3": 33.64e6 + 0.87e6}
 # what bounds that kernel, from the same capture (SURVEY 8d asks for these instead of a %-of-HBM figure)
-NCU_DOMINANT = {"C3": {"issue_slots_used": 0.70, "ipc_per_sm": 2.8, "active_lanes_of_32": 23.3, "l1_hit_rate": 0.988,
-                       "l2_hit_rate": 0.77, "registers": 96, "warps_per_sm": 18, "top_stall": "wait (dependent issue)",
+NCU_DOMINANT = {"C3": {"issue_slots_used": 0.72, "ipc_per_sm": 2.85, "active_lanes_of_32": 23.5, "l1_hit_rate": 0.988,
+                       "l2_hit_rate": 0.76, "registers": 96, "warps_per_sm": 18, "top_stall": "wait (dependent issue)",
                        "source": "profiles/r1_ncu_update_mbes_profile.txt"}}
 RS_BYTES = 96        # algorithmic HBM bytes per particle of normalise + scan + select + gather
 
@@ -250,7 +250,7 @@ def run_ours(args):
     filt.set_beams(beams)
 
     # synthetic ping sequence: ground-truth ranges raycast on the GPU (the product path), + noise
-    n_steps = 3 * (K + W) + 2
+    n_steps = 2 * (K + W) + 2 * K + 2
     cycles = []
     for s in range(n_steps):
         per = [t.cycle() for t in trajs]
@@ -355,9 +355,9 @@ def run_ours(args):
             od = np.array([[([_odom_row(o, None)] if F == 1 else o) for o in cycles[s][0]] for s in range(s0, s1)], np.float64)
             return od.reshape(s1 - s0, P_PREDICTS, F, 11), np.stack([cycles[s][1] for s in range(s0, s1)]).reshape(s1 - s0, F, B)
         b2 = base + W + K
-        od_w, rg_w = rows(b2, b2 + W)
+        od_w, rg_w = rows(b2, b2 + K)           # warm-up of the same length: the replay buffers are sized once
         pf.replay(od_w, rg_w)
-        od_k, rg_k = rows(b2 + W, b2 + W + K)
+        od_k, rg_k = rows(b2 + K, b2 + 2 * K)
         barrier()
         t0 = time.perf_counter()
         rmean, rcov = pf.replay(od_k, rg_k)
@@ -415,7 +415,7 @@ def run_ours(args):
                      "ncu": NCU_DOMINANT.get(cfg["name"]),
                      "peak_source": peak_src, "ms_per_launch": mbes_ms / max(mbes_n, 1),
                      "evals_per_s": M * F * B / (mbes_ms / max(mbes_n, 1) * 1e-3) if mbes_n else None,
-                     "note": "dominant kernel is instruction-issue-bound (ncu: 74 % of issue slots, 2.9 IPC/SM, L1 hit "
+                     "note": "dominant kernel is instruction-issue-bound (ncu: 72 % of issue slots, 2.85 IPC/SM, L1 hit "
                              "99 %) on an L1/L2-resident DEM footprint, not HBM-bound (SURVEY 8d): its algorithmic HBM "
                              "bytes are 0.2 % of what the measured time could move; the HBM-bound path is roofline_resample"},
         "roofline_resample": {"bound": "hbm", "kernel": "k_normalise + k_scan_q_from_a + k_select_gather",
