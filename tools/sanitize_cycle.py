@@ -43,6 +43,16 @@ def main():
         pf.set_poses(p)
         pf.update_mbes(np.stack([r[0], r[0]]), return_weights=False)
         pf.resample()
+        if resampler == "systematic" and not inplace:
+            # the N_eff gate (held back and let through) and a replayed sequence of three cycles
+            from smarc_navigation_b200.filter import _odom_row
+            pf.set_neff_gate(0.5)
+            pf.set_log_weights(np.zeros(N * F, np.float32))
+            pf.resample(wait=False)
+            assert pf.resample_skipped().all()
+            rows = np.array([[[_odom_row(o, None)] for o in odoms]] * 3)
+            pf.replay(rows, np.stack([np.stack([r[0], r[0]])] * 3))
+            pf.neff_fixed()
         pf.close()
     print("sanitize cycle ok")
 
