@@ -418,7 +418,7 @@ def run_ours(args):
                      "note": "dominant kernel is instruction-issue-bound (ncu: 72 % of issue slots, 2.85 IPC/SM, L1 hit "
                              "99 %) on an L1/L2-resident DEM footprint, not HBM-bound (SURVEY 8d): its algorithmic HBM "
                              "bytes are 0.2 % of what the measured time could move; the HBM-bound path is roofline_resample"},
-        "roofline_resample": {"bound": "hbm", "kernel": "k_normalise + k_scan_q_from_a + k_select_gather",
+        "roofline_resample": {"bound": "hbm", "kernel": "k_normalise + k_quotients + k_select_gather",
                               "achieved": ach_rs, "peak": peak, "unit": "GB/s", "frac": ach_rs / peak,
                               "ms_per_cycle": rs_ms / rs_n, "bytes_per_particle": RS_BYTES},
         "roofline_propagate": {"bound": "hbm", "achieved": ach_prop, "peak": peak, "unit": "GB/s",

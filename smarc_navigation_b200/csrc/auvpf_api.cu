@@ -429,10 +429,9 @@ int run_scan(auvpf_handle *h, const WeightSrc &src, bool fused = false)
         CU(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * h->F, h->stream));
         CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
     }
-    if (fused)      // a_i were left in h->cdf by k_normalise
-        k_scan_q_from_a<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
-            h->M, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, nullptr, h->deficit,
-            h->degenerate, h->sqlimbs);
+    if (fused)      // a_i were left in h->cdf by k_normalise; they become the raw quotients, the status words the tile table
+        k_quotients<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
+            h->M, h->A, h->cdf, h->status, h->done, h->tiles_per_filter, h->Q, h->deficit, h->degenerate, h->sqlimbs);
     else
         k_scan_q<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
             src, h->M, h->wmax, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq,

@@ -1019,38 +1019,115 @@ k_scan_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A
     scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit);
 }
 
-// Same scan on the a_i left in `cdf` by k_normalise (in place: a tile reads its own entries before
-// it writes them), so the float64 exp is not evaluated a second time.
+// Single-GPU stage 3 WITHOUT look-back: q_i = floor(a_i 2^52 / A) stored in place of a_i, one sum per tile;
+// the LAST block of a filter (ticket) turns the filter's tile sums into the tile table (inclusive
+// prefixes) and writes Q and the deficit.  The prefix INSIDE a tile is not stored: k_select_gather walks
+// whole tiles anyway and rebuilds it with one block scan per tile.  This is a streaming kernel -- in the
+// look-back scan the spin on the predecessors' status words and its barriers were ~40 % of the stall
+// samples, and a tile lived for ~14 us at 16 M particles.  (The particle-sharded filter keeps the
+// look-back scan k_scan_q: its peers read a finished CDF.)
 __global__ void __launch_bounds__(kThreads, 4)
-k_scan_q_from_a(int64_t M, const unsigned long long *A, unsigned long long *cdf, unsigned long long *status,
-                unsigned int *tile_counter, int tiles_per_filter, unsigned long long *Q, double *sumsq,
-                unsigned long long *deficit, const int *degenerate, unsigned long long *sqlimbs)
+k_quotients(int64_t M, const unsigned long long *A, unsigned long long *qv, unsigned long long *table,
+            unsigned int *done, int tiles_per_filter, unsigned long long *Q, unsigned long long *deficit,
+            const int *degenerate, unsigned long long *sqlimbs)
 {
-    // this block's a_i first (one tile = one filter), then the divisor: all loads are in flight together
+    __shared__ unsigned long long s_w[kThreads / 32], s_lo[kThreads / 32], s_hi[kThreads / 32];
+    __shared__ bool s_last;
     const int f = blockIdx.x / tiles_per_filter, tile = blockIdx.x % tiles_per_filter;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t row0 = (int64_t)f * M + (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
     const int64_t left = M - ((int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems);
-    unsigned long long raw[kScanItems];
-    if (left >= kScanItems) {           // 64 contiguous, 64-byte aligned bytes per thread (M is not assumed even)
-        if ((row0 & 1) == 0) {
+    const bool vec = left >= kScanItems && (row0 & 1) == 0;
+    unsigned long long v[kScanItems];
+    if (vec) {
 #pragma unroll
-            for (int k = 0; k < kScanItems; k += 2) {
-                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(cdf + row0 + k);
-                raw[k] = t.x;
-                raw[k + 1] = t.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kScanItems; ++k) raw[k] = cdf[row0 + k];
+        for (int k = 0; k < kScanItems; k += 2) {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(qv + row0 + k);
+            v[k] = t.x;
+            v[k + 1] = t.y;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < kScanItems; ++k) raw[k] = k < left ? cdf[row0 + k] : 0ull;
+        for (int k = 0; k < kScanItems; ++k) v[k] = k < left ? qv[row0 + k] : 0ull;
     }
     const QDiv d = make_qdiv(A[2 * f], A[2 * f + 1]);
     const bool dead = degenerate[f] != 0;
-    auto value = [&](int64_t, int, int k) -> unsigned long long { return dead ? 0ull : q_from_a(raw[k], d); };
-    scan_tile_body<true>(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit, sqlimbs);
+    unsigned long long tsum = 0, sq_lo = 0, sq_hi = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = dead ? 0ull : q_from_a(v[k], d);
+        tsum += v[k];
+        const unsigned long long s2 = neff_square(v[k]);
+        sq_lo += s2 & 0xFFFFFFFFull;
+        sq_hi += s2 >> 32;
+    }
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < kScanItems; k += 2)
+            *reinterpret_cast<ulonglong2 *>(qv + row0 + k) = make_ulonglong2(v[k], v[k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+            if (k < left) qv[row0 + k] = v[k];
+    }
+    tsum = warp_sum_u64(tsum);
+    sq_lo = warp_sum_u64(sq_lo);
+    sq_hi = warp_sum_u64(sq_hi);
+    if (lane == 0) {
+        s_w[warp] = tsum;
+        s_lo[warp] = sq_lo;
+        s_hi[warp] = sq_hi;
+    }
+    __syncthreads();
+    unsigned long long *tab = table + (size_t)f * tiles_per_filter;
+    if (threadIdx.x == 0) {
+        unsigned long long tot = 0, lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) {
+            tot += s_w[k];
+            lo += s_lo[k];
+            hi += s_hi[k];
+        }
+        if (lo) atomicAdd(sqlimbs + 2 * f, lo);            // integer atomics, two per block: independent of the arrival order
+        if (hi) atomicAdd(sqlimbs + 2 * f + 1, hi);
+        tab[tile] = tot;
+        __threadfence();
+        s_last = atomicAdd(done + f, 1u) == (unsigned int)tiles_per_filter - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the filter's tile sums -> inclusive prefixes, in place: a run of consecutive tiles per thread
+    const int per = (tiles_per_filter + kThreads - 1) / kThreads;
+    const int t0 = threadIdx.x * per;
+    unsigned long long run = 0;
+    for (int k = 0; k < per; ++k)
+        if (t0 + k < tiles_per_filter) run += *reinterpret_cast<volatile unsigned long long *>(tab + t0 + k);
+    unsigned long long incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    __syncthreads();                                   // s_w is reused
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    unsigned long long acc = incl - run, total = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) {
+        if (k < warp) acc += s_w[k];
+        total += s_w[k];
+    }
+    for (int k = 0; k < per; ++k)
+        if (t0 + k < tiles_per_filter) {
+            acc += *reinterpret_cast<volatile unsigned long long *>(tab + t0 + k);
+            tab[t0 + k] = acc;
+        }
+    if (threadIdx.x == 0) {
+        Q[f] = total;
+        deficit[f] = (1ull << kQBits) - total;
+        done[f] = 0u;
+    }
 }
 
 // q_i itself (parity read-back): q_i + (i_global < D)
@@ -1159,6 +1236,7 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
     __shared__ int s_head[kSelTile];              // output slot -> 1 + (first ancestor whose run of offspring starts there - j_lo), else 0
     __shared__ int s_wmax[kSelThreads / 32];
     __shared__ int s_t[2];
+    __shared__ unsigned long long s_wsum[2][kSelThreads / 32];
     const int f = blockIdx.y;
     const unsigned long long *cdf = cdf_all + (size_t)f * p.M;
     const unsigned long long D = deficit[f];
@@ -1251,14 +1329,22 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
         const int64_t g = sys_count_below(spos, p.n_global, c) - g0;
         return (int)(g < 0 ? 0 : (g > nblk ? nblk : g));
     };
+    // kRecords (a shard of a particle-sharded filter): `cdf` holds the finished inclusive CDF of the look-back
+    // scan.  Otherwise (single GPU) it holds the raw quotients k_quotients left, and the inclusive prefix of
+    // a tile is rebuilt here -- one pass walks exactly one scan tile -- from the tile table's prefix of the
+    // tile before, a thread-local running sum, a warp shuffle scan and the warps' totals (one barrier).
+    static_assert(kSelThreads * kSrcItems == kScanTile, "one pass of the source walk = one scan tile");
+    const unsigned long long *tab2 = tile_table + (size_t)f * p.tiles_per_filter;
     for (int64_t jb = j_lo; jb <= j_hi; jb += (int64_t)kSelThreads * kSrcItems) {
+        const int64_t tile = jb / kScanTile;
+        const unsigned long long tile_excl = (!kRecords && tile > 0) ? (tab2[tile - 1] & kValMask) : 0ull;
         // all the outputs of the block are handed out once the pass's first particle already ends at nblk
         // (block-uniform: every thread evaluates the same entry)
-        if (jb > j_lo && rel_end(cdf[jb - 1], jb - 1) >= nblk) break;
+        if (jb > j_lo && rel_end(kRecords ? cdf[jb - 1] : tile_excl, jb - 1) >= nblk) break;
         const int64_t j0 = jb + (int64_t)threadIdx.x * kSrcItems;
         unsigned long long cv[kSrcItems];
         const bool has_prev = lane == 0 && j0 > j_lo && j0 - 1 <= j_hi;
-        const unsigned long long cprev = has_prev ? cdf[j0 - 1] : 0ull;      // in flight with the thread's own entries
+        unsigned long long cprev = (kRecords && has_prev) ? cdf[j0 - 1] : 0ull;   // in flight with the thread's own entries
         if (j0 + kSrcItems - 1 <= j_hi && ((reinterpret_cast<uintptr_t>(cdf + j0) & 15) == 0)) {
 #pragma unroll
             for (int k = 0; k < kSrcItems; k += 2) {
@@ -1269,6 +1355,30 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
         } else {
 #pragma unroll
             for (int k = 0; k < kSrcItems; ++k) cv[k] = j0 + k <= j_hi ? cdf[j0 + k] : 0ull;
+        }
+        if (!kRecords) {
+            unsigned long long run = 0;
+#pragma unroll
+            for (int k = 0; k < kSrcItems; ++k) {
+                run += cv[k];
+                cv[k] = run;
+            }
+            unsigned long long incl = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            unsigned long long *ws = s_wsum[tile & 1];      // two buffers: no barrier between consecutive passes
+            if (lane == 31) ws[warp] = incl;
+            __syncthreads();
+            unsigned long long before = tile_excl + (incl - run);
+#pragma unroll
+            for (int k = 0; k < kSelThreads / 32; ++k)
+                if (k < warp) before += ws[k];
+#pragma unroll
+            for (int k = 0; k < kSrcItems; ++k) cv[k] += before;
+            cprev = before;                                   // the CDF just before this thread's first particle
         }
         // the ends are non-decreasing in j: a thread whose LAST particle ends at 0 lies before the block, one
         // whose FIRST particle ends at nblk lies behind it; only threads across the block evaluate all
@@ -1617,12 +1727,12 @@ k_select_gather_p2p(const PeerTable *__restrict__ pt, int64_t M, int rank, int t
 
 // ---------------------------------------------------------------------------------------------
 // residual_resample (a6, resampling.py:27-76) on the fixed-point weights w_i = q_i 2^-52.
-// q_i is recovered from the integer CDF the scan left behind (+ the deficit unit).
+// q_i = the raw quotient k_quotients left behind + the deficit unit.
 __device__ __forceinline__ unsigned long long q_from_cdf(const unsigned long long *cdf, int64_t base, int64_t i,
                                                         unsigned long long D, int64_t global_offset)
 {
-    const unsigned long long c = cdf[base + i], prev = i > 0 ? cdf[base + i - 1] : 0ull;
-    return c - prev + ((unsigned long long)(global_offset + i) < D ? 1ull : 0ull);
+    // (the single-GPU stage 3, k_quotients, leaves the raw quotients themselves in this array)
+    return cdf[base + i] + ((unsigned long long)(global_offset + i) < D ? 1ull : 0ull);
 }
 
 // inclusive scan of the deterministic copy counts floor(N w_i) (:61); totals = k per filter

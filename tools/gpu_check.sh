@@ -13,6 +13,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_update_mbes_profile -s 4 -c 1 -f -o gpurun_out/prof_mbes_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_normalise|k_scan_q_from_a|k_select_gather|k_propagate" -s 12 -c 8 -f -o gpurun_out/prof_resample_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:"k_normalise|k_quotients|k_select_gather|k_propagate" -s 12 -c 8 -f -o gpurun_out/prof_resample_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full2_$TAG.log 2>&1
 echo done
