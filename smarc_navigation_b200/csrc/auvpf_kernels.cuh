@@ -869,10 +869,7 @@ constexpr int kScanItems = 8;
 constexpr int kScanTile = kThreads * kScanItems;
 constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (1ull << 62) - 1;
 
-// kStaticTile: the tile is blockIdx.x (blocks are dispatched in index order, the assumption CUB's
-// single-pass scan makes too) instead of a ticket drawn from tile_counter, so a block can issue
-// its loads before anything else -- the ticket (atomic + barrier) was ~6 % of the stall samples.
-template <bool kStaticTile = false, class ValueFn>
+template <class ValueFn>
 __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigned long long *__restrict__ out,
                                                volatile unsigned long long *status, unsigned int *tile_counter,
                                                int tiles_per_filter, unsigned long long *totals,
@@ -884,11 +881,9 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
     __shared__ unsigned int s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
     __shared__ unsigned long long s_prefix;
-    if (!kStaticTile) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-        __syncthreads();
-    }
-    const unsigned int gtile = kStaticTile ? blockIdx.x : s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const unsigned int gtile = s_tile;
     const int f = gtile / tiles_per_filter, tile = gtile % tiles_per_filter;
     const int64_t base = (int64_t)f * M;
     const int64_t i0 = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;

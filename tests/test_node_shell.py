@@ -78,6 +78,7 @@ def test_parameters_follow_the_reference_names_and_defaults():
     assert kw["particle_count"] == 64 and kw["measurement_std"] == 1.0
     assert kw["init_covariance"] == PARAMS["init_covariance"]          # covariance STRINGS pass through (auv_pf.py:40-56)
     assert kw["resampler"] == "residual" and kw["inplace_reference"] is True    # the reference's choices (:182-198)
+    assert kw["resample_neff_ratio"] == 0.0     # the gate of :174-181 is commented out in the reference: off by default
     assert n.odom_frame == "sam/odom" and n.base_frame == "base_link" and n.diving is True
     PARAMS.pop("motion_covariance")
     try:
