@@ -1306,23 +1306,11 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
     const int nblk = (int)(k1 - k0 + 1);
     const int64_t g0 = p.out_lo + k0;                  // global index of the block's first output
     const SysPos spos = make_sys_pos(u, n);
-    const double n_scaled = n * 2.220446049250313e-16, g0d = (double)g0, nblk_d = (double)nblk;   // n 2^-52: exact
-    // block-relative end of source j's run: clamp(count_below(cdf[j]) - g0, 0, nblk).  Only values inside
-    // (0, nblk) need the count itself; x = estimate - g0 decides the rest (same 1e-5 margin as
-    // sys_count_below, which is called when x is that close to an integer).
+    // block-relative end of source j's run (rel_end_of, auvpf_math.cuh): clamp(count_below(cdf[j]) - g0, 0, nblk)
+    const RelEndCtx rctx = make_rel_end(u, n, g0, nblk);
     auto rel_end = [&](unsigned long long cdfv, int64_t j) -> int {
         const unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
-        const unsigned long long c = p.q_offset + cdfv + (jg1 < D ? jg1 : D);
-        // (double)c for c <= 2^52 without a 64-bit conversion: 2^52 + c is exact in the mantissa
-        const double cd = __longlong_as_double((long long)(0x4330000000000000ull + c)) - 4503599627370496.0;
-        const double x = fma(cd, n_scaled, -u) - g0d;
-        if (x < -1.0e-5) return 0;
-        if (x > nblk_d + 1.0e-5) return nblk;
-        const int ie = __double2int_ru(x);
-        const double r = (double)ie - x;                       // in [0, 1)
-        if (r > 1.0e-5 && r < 1.0 - 1.0e-5) return min(max(ie, 0), nblk);
-        const int64_t g = sys_count_below(spos, p.n_global, c) - g0;
-        return (int)(g < 0 ? 0 : (g > nblk ? nblk : g));
+        return rel_end_of(spos, p.n_global, rctx, p.q_offset + cdfv + (jg1 < D ? jg1 : D));
     };
     // kRecords (a shard of a particle-sharded filter): `cdf` holds the finished inclusive CDF of the look-back
     // scan.  Otherwise (single GPU) it holds the raw quotients k_quotients left, and the inclusive prefix of

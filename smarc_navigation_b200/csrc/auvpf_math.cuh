@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define AUVPF_HD __host__ __device__ __forceinline__
@@ -1272,6 +1273,59 @@ AUVPF_HD int64_t sys_count_below(double u, int64_t N, uint64_t c)
 {
     return sys_count_below(make_sys_pos(u, (double)N), N, c);
 }
+
+// Block-relative end of a particle's run of offspring in k_select_gather: with c the particle's inclusive
+// CDF value and a block that owns the outputs [g0, g0 + nblk),
+//   rel_end = clamp(sys_count_below(c) - g0, 0, nblk).
+// Only values inside (0, nblk) need the count itself; x = estimate - g0 decides the rest, with the same
+// 1e-5 margin as sys_count_below, which is called when x is that close to an integer.
+struct RelEndCtx {
+    double n_scaled;     // N 2^-52 (exact)
+    double u;
+    double g0d, nblk_d;  // (double)g0, (double)nblk
+    int64_t g0;
+    int nblk;
+};
+AUVPF_HD RelEndCtx make_rel_end(double u, double n, int64_t g0, int nblk)
+{
+    RelEndCtx r;
+    r.n_scaled = n * 2.220446049250313e-16;
+    r.u = u;
+    r.g0d = (double)g0;
+    r.nblk_d = (double)nblk;
+    r.g0 = g0;
+    r.nblk = nblk;
+    return r;
+}
+AUVPF_HD int rel_end_of(const SysPos &sp, int64_t n_global, const RelEndCtx &r, unsigned long long c)
+{
+    // (double)c for c <= 2^52 without a 64-bit conversion: 2^52 + c is exact in the mantissa
+#if defined(__CUDA_ARCH__)
+    const double cd = __longlong_as_double((long long)(0x4330000000000000ull + c)) - 4503599627370496.0;
+#else
+    const unsigned long long bits = 0x4330000000000000ull + c;
+    double cd0;
+    memcpy(&cd0, &bits, sizeof(cd0));
+    const double cd = cd0 - 4503599627370496.0;
+#endif
+    const double x = fma(cd, r.n_scaled, -r.u) - r.g0d;
+    if (x < -1.0e-5) return 0;
+    if (x > r.nblk_d + 1.0e-5) return r.nblk;
+#if defined(__CUDA_ARCH__)
+    const int ie = __double2int_ru(x);
+#else
+    const int ie = (int)ceil(x);
+#endif
+    const double d = (double)ie - x;                       // in [0, 1)
+#if defined(__CUDA_ARCH__)
+    if (d > 1.0e-5 && d < 1.0 - 1.0e-5) return min(max(ie, 0), r.nblk);
+#else
+    if (d > 1.0e-5 && d < 1.0 - 1.0e-5) return ie < 0 ? 0 : (ie > r.nblk ? r.nblk : ie);
+#endif
+    const int64_t g = sys_count_below(sp, n_global, c) - r.g0;
+    return (int)(g < 0 ? 0 : (g > r.nblk ? r.nblk : g));
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // residual_resample (resampling.py:27-76) on fixed-point weights w = q 2^-52.

@@ -131,3 +131,11 @@ def neff_fixed(q_raw):
     fn = lib().hs_neff_fixed
     fn.restype = C.c_double
     return float(fn(_p(q), C.c_long(len(q))))
+
+
+def select_source_side(q_raw, u, D):
+    """Ancestors by the host twin of k_select_gather (source-side run heads + max-scan)."""
+    q = np.ascontiguousarray(q_raw, np.uint64)
+    anc = np.zeros(len(q), np.int32)
+    lib().hs_select_source_side(_p(q), C.c_long(len(q)), C.c_double(u), C.c_uint64(int(D)), _p(anc))
+    return anc

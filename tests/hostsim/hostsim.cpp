@@ -366,6 +366,101 @@ long hs_count_below(double u, long N, uint64_t c) { return (long)sys_count_below
 
 float hs_wrap_pi(float a) { return wrap_pi(a); }
 
+// Host twin of k_select_gather's ancestor selection (single-GPU form): tile table from the raw quotients,
+// 32-ary tile location, source-side walk with rel_end_of (the SAME function the kernel calls), pruning
+// by thread, run heads, inclusive max-scan -- block by block, "thread" by "thread", in the kernel's order.
+void hs_select_source_side(const uint64_t *q_raw, long M, double u, uint64_t D, int32_t *anc)
+{
+    const int kTile = 2048, kItems = 8, kThreads = 256, kOut = 1024;
+    const long tiles = (M + kTile - 1) / kTile;
+    std::vector<uint64_t> tab(tiles);
+    {
+        uint64_t acc = 0;
+        for (long t = 0; t < tiles; ++t) {
+            for (long j = t * kTile; j < std::min<long>((t + 1) * kTile, M); ++j) acc += q_raw[j];
+            tab[t] = acc;
+        }
+    }
+    const double n = (double)M;
+    const SysPos spos = make_sys_pos(u, n);
+    auto full = [&](uint64_t raw_cdf, long j) { const uint64_t jg1 = (uint64_t)(j + 1); return raw_cdf + (jg1 < D ? jg1 : D); };
+    for (long k0 = 0; k0 < M; k0 += kOut) {
+        const long k1 = std::min<long>(k0 + kOut, M) - 1;
+        const int nblk = (int)(k1 - k0 + 1);
+        // level 1: 32-ary search, one "warp" per key
+        long tl[2];
+        for (int w = 0; w < 2; ++w) {
+            const uint64_t key = (uint64_t)floor(sys_position(u, w == 0 ? k0 : k1, n) * 4503599627370496.0);
+            long lo = 0, hi = tiles;
+            while (lo < hi) {
+                const long step = (hi - lo + 31) >> 5;
+                int nb = 0;
+                for (int lane = 0; lane < 32; ++lane) {
+                    const long t = lo + (lane + 1) * step - 1;
+                    bool below = false;
+                    if (t < hi) {
+                        const long je = std::min<long>((t + 1) * kTile, M) - 1;
+                        below = !(key < full(tab[t], je));
+                    }
+                    nb += below ? 1 : 0;
+                }
+                lo += nb * step;
+                hi = std::min(lo + step - 1, hi);
+            }
+            tl[w] = std::min(lo, tiles - 1);
+        }
+        const long j_lo = tl[0] * kTile, j_hi = std::min<long>((tl[1] + 1) * kTile, M) - 1;
+        const RelEndCtx rctx = make_rel_end(u, n, k0, nblk);
+        auto rel_end = [&](uint64_t raw_cdf, long j) { return rel_end_of(spos, M, rctx, full(raw_cdf, j)); };
+        std::vector<int> head(kOut, 0);
+        for (long jb = j_lo; jb <= j_hi; jb += (long)kThreads * kItems) {
+            const long tile = jb / kTile;
+            const uint64_t tile_excl = tile > 0 ? tab[tile - 1] : 0;
+            if (jb > j_lo && rel_end(tile_excl, jb - 1) >= nblk) break;
+            uint64_t run_before = tile_excl;
+            int prev_thread_last = 0;
+            for (int tid = 0; tid < kThreads; ++tid) {
+                const long j0 = jb + (long)tid * kItems;
+                uint64_t cv[kItems];
+                uint64_t acc = run_before;
+                for (int k = 0; k < kItems; ++k) {
+                    acc += (j0 + k <= j_hi) ? q_raw[j0 + k] : 0;
+                    cv[k] = acc;
+                }
+                const uint64_t before = run_before;
+                run_before = acc;
+                int e[kItems];
+                const bool whole = j0 + kItems - 1 <= j_hi;
+                const int e_last = whole ? rel_end(cv[kItems - 1], j0 + kItems - 1) : nblk;
+                const int e_first = (e_last == 0) ? 0 : (j0 <= j_hi ? rel_end(cv[0], j0) : nblk);
+                if (e_last == 0 || e_first == nblk) {
+                    for (int k = 0; k < kItems; ++k) e[k] = e_first;
+                } else {
+                    e[0] = e_first;
+                    for (int k = 1; k < kItems - 1; ++k) e[k] = j0 + k <= j_hi ? rel_end(cv[k], j0 + k) : nblk;
+                    e[kItems - 1] = e_last;
+                }
+                int start;
+                if ((tid & 31) == 0) {
+                    const bool has_prev = j0 > j_lo && j0 - 1 <= j_hi;
+                    start = has_prev ? rel_end(before, j0 - 1) : (j0 > j_lo ? nblk : 0);
+                } else
+                    start = prev_thread_last;
+                for (int k = 0; k < kItems; ++k) {
+                    if (e[k] > start) head[start] = (int)(j0 + k - j_lo) + 1;
+                    start = e[k];
+                }
+                prev_thread_last = e[kItems - 1];
+            }
+        }
+        int m = 0;
+        for (int k = 0; k < nblk; ++k) {
+            m = std::max(m, head[k]);
+            anc[k0 + k] = (int32_t)std::min<long>(j_lo + std::max(m - 1, 0), M - 1);
+        }
+    }
+}
+
 // the N_eff gate's integer sum of squares, accumulated like the scan kernel does (two limbs)
 double hs_neff_fixed(const uint64_t *q_raw, long n)
 {

@@ -412,3 +412,59 @@ def test_neff_gate_arithmetic_is_the_oracles():
         assert abs(got - ref) <= 1e-2 * ref
         for ratio in (0.0, 0.1, 0.5, 1.0):
             assert o.resample_gate(a, ratio) == (not (ratio > 0.0 and got >= ratio * len(lw)))
+
+
+def _quantised(logw):
+    qq, a, A, m = o.quantise_logw(np.asarray(logw, np.float32))
+    raw = o.raw_quotients(a)
+    D = (1 << 52) - int(raw.astype(object).sum())
+    assert np.array_equal(raw + (np.arange(len(raw)) < D).astype(np.uint64), qq)
+    return qq, raw, D
+
+
+@pytest.mark.parametrize("N", [1, 5, 1023, 1024, 1025, 2047, 2048, 2049, 5000, 70001])
+def test_source_side_select_is_the_references_systematic_resample(N):
+    """The ancestor selection of k_select_gather, run on the host from the same header functions
+    (rel_end_of / sys_count_below): tile table, 32-ary tile location, per-particle closed-form run
+    ends, run heads, max-scan.  Must equal the reference's systematic_resample (resampling.py:135-168)
+    on the same fixed-point weights for diffuse, concentrated, one-hot and mostly-zero weights
+    (zero-weight stretches longer than a scan tile), at the edges of the scan-tile / output-block sizes."""
+    rng = np.random.default_rng(N)
+    cases = [rng.normal(0, s, N) for s in (0.0, 0.1, 3.0, 12.0)]
+    onehot = np.full(N, -np.inf)
+    onehot[N // 2] = 0.0
+    cases.append(onehot)
+    sparse = np.full(N, -np.inf)
+    sparse[rng.choice(N, max(1, N // 300), replace=False)] = rng.normal(0, 1, max(1, N // 300))
+    cases.append(sparse)
+    ends = rng.normal(0, 0.5, N) - 40.0
+    ends[0] = ends[-1] = 0.0                             # almost all the mass on the first and the last particle
+    cases.append(ends)
+    for logw in cases:
+        qq, raw, D = _quantised(logw)
+        w = o.weights_from_q(qq)
+        for u in (float(rng.uniform()), 0.0, 1.0 - 2.0 ** -20):
+            np.testing.assert_array_equal(hs.select_source_side(raw, u, D), o.systematic_resample(w, u))
+        # u so close to 1 that positions[-1] rounds to 1.0 (u >= 1 - N 2^-54): the reference walks off the end
+        # (IndexError, :162-167); the kernel hands such an output to the last particle, or -- when the particle
+        # count is a multiple of the 8 particles a thread walks -- to the last particle that has offspring
+        u = 1.0 - 2.0 ** -53
+        pos = (u + np.arange(N)) / float(N)
+        idx = np.searchsorted(np.cumsum(w), pos, side="right")
+        got = hs.select_source_side(raw, u, D)
+        inside = idx < N
+        np.testing.assert_array_equal(got[inside], idx[inside])
+        assert np.all(np.diff(got) >= 0) and np.all((w[got[~inside]] > 0) | (got[~inside] == N - 1))
+
+
+def test_source_side_select_one_million():
+    """The same at 1 M + 3 particles with 300 k dead ones in a row (~146 scan tiles without any mass),
+    against the C oracle's systematic resampler."""
+    N = (1 << 20) + 3
+    rng = np.random.default_rng(7)
+    logw = rng.normal(0, 4.0, N).astype(np.float32)
+    logw[100000:400000] = -np.inf
+    qq, raw, D = _quantised(logw)
+    np.testing.assert_array_equal(qq, c_oracle.quantise_logw(logw)[0])
+    u = float(rng.uniform())
+    np.testing.assert_array_equal(hs.select_source_side(raw, u, D), c_oracle.systematic(o.weights_from_q(qq), u))
