@@ -1647,7 +1647,9 @@ int auvpf_shard_scan_dev(auvpf_handle *h)
                                                                   h->F);
     LAUNCHED(h, AUVPF_K_NORMALISE, 1);
     WeightSrc src{h->logw, nullptr, 0};
-    int rc = run_scan(h, src, /*fused=*/true);
+    // a shard's peers (k_select_gather_p2p) and auvpf_shard_emit read a FINISHED inclusive CDF and a flagged tile
+    // table: the look-back scan k_scan_q, not the single-GPU k_quotients (raw quotients + per-tile sums)
+    int rc = run_scan(h, src, /*fused=*/false);
     h->have_norm = true;
     h->last_src_kind = 0;
     h->wmax_valid = false;      // the maximum in the buffer is not this shard's: recompute next time unless an update refreshes it

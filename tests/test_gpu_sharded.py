@@ -165,3 +165,63 @@ def test_shard_stages_on_one_gpu(G, M, seed):
     np.testing.assert_array_equal(one.resample(u=u, return_ancestors=True, roughen=False), anc)
     for pf in pfs + [one]:
         pf.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,M,seed", [(2, 6000, 3), (3, 1 << 17, 4)])
+def test_device_resident_shard_stages_on_one_gpu(G, M, seed):
+    """The DEVICE-resident stages ShardedParticleFilter uses (auvpf_shard_max_dev / sum_dev / scan_dev:
+    scalars reduced in place on the library's buffers, then auvpf_shard_emit), with the collectives
+    done by hand for G handles on ONE GPU.  scan_dev must leave a finished inclusive CDF and a tile
+    table -- what a shard's peers and auvpf_shard_emit read -- not the single-GPU kernel's layout."""
+    import torch
+    from oracle import c_oracle, pf_oracle as o
+    from smarc_navigation_b200 import ParticleFilter, _lib
+    from smarc_navigation_b200.sharded import GpuShardOps, plan_exchange
+    rng = np.random.default_rng(seed)
+    N = G * M
+    logw = (rng.normal(0, 3.0, N) - 90).astype(np.float32)
+    if seed % 2:
+        logw[: N // 2 + 3] -= 50.0
+    poses = np.zeros((N, 6))
+    poses[:, 0] = np.arange(N)
+    poses[:, 1] = 0.5 * np.arange(N)
+    u = float(rng.uniform())
+    pfs = [ParticleFilter(particle_count=M, global_offset=g * M, global_count=N, seed=seed,
+                          resampling_noise_covariance=[0.0] * 6) for g in range(G)]
+    ops = [GpuShardOps(pf) for pf in pfs]
+    L = _lib.load()
+    for g, pf in enumerate(pfs):
+        pf.set_poses(poses[g * M:(g + 1) * M])
+        pf.set_log_weights(logw[g * M:(g + 1) * M])
+
+    def everyone(call):
+        for pf in pfs:
+            _lib.check(call(pf._h))
+        for pf in pfs:
+            pf.sync()
+
+    everyone(L.auvpf_shard_max_dev)
+    m = torch.stack([op.t_wmax for op in ops]).max(0).values          # all-reduce MAX on the order-preserving int32
+    for op in ops:
+        op.t_wmax.copy_(m)
+    torch.cuda.synchronize()
+    everyone(L.auvpf_shard_sum_dev)
+    limbs = torch.stack([op.t_limbs for op in ops]).sum(0)            # all-reduce SUM of the exact integer limbs
+    for op in ops:
+        op.t_limbs.copy_(limbs)
+    torch.cuda.synchronize()
+    everyone(L.auvpf_shard_scan_dev)
+    Q_all = [int(op.t_q.item()) for op in ops]                        # all-gather of the shards' CDF totals
+    D, q_offsets, bounds = plan_exchange(Q_all, M, u)
+    sends = [ops[g].shard_emit(u, q_offsets[g], D, bounds[g], bounds[g + 1]) for g in range(G)]
+    everything = torch.cat(sends)
+    assert everything.shape[0] == N
+    for g in range(G):
+        ops[g].shard_load(everything[g * M:(g + 1) * M].contiguous())
+    got = np.concatenate([pf.poses() for pf in pfs])
+    anc = c_oracle.systematic(o.weights_from_q(c_oracle.quantise_logw(logw)[0]), u)
+    np.testing.assert_array_equal(got[:, 0], poses[anc, 0])
+    np.testing.assert_array_equal(got[:, 1], poses[anc, 1])
+    for pf in pfs:
+        pf.close()
