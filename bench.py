@@ -3,19 +3,26 @@
 particle-beam likelihood evaluations/s and filter-cycle latency).
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port, all host threads)
 
 A "step" is one filter cycle on one ping: P=5 predicts (50 Hz odometry between
 10 Hz pings) + MBES update (raycast + beam likelihood) + normalise + systematic
 resample + gather with fused roughening.  Workload at 1 GPU = BASELINE config C3
 (1,048,576 particles x 512 beams, 0.5 m DEM over 4 km^2); with N GPUs every rank
-holds that many particles of ONE filter (weak scaling; `--workload C4` gives the
-16M x 512 target configuration at 8 GPUs).
+holds that many particles of ONE filter (weak scaling).  At --gpus 8 the same JSON
+line carries two sub-records, `c4` (BASELINE config 4: 16,777,216 x 512 sharded over
+the 8 GPUs) and `c5` (config 5: 256 filters x 65,536, 32 whole filters per GPU), each
+measured the same way in the same process; `--workload C4|C5` makes one of them the line.
 
 Prints ONE JSON line (rank 0).  `value` = whole-job evals/s with the pings already
 resident in HBM, timed with CUDA events on the library's stream per step (L2 flushed
 between steps), max over ranks; `e2e` = the same through the public Python API with
-pinned HOST buffers (ping H2D, estimate D2H inside the timed region).
+pinned HOST buffers (ping H2D, estimate D2H inside the timed region).  `parity_check`:
+after the timed loops one extra resample on seeded log-weights is compared, bit for bit,
+with the CPU oracle's systematic ancestors on rank 0 (every N, every exchange path).
+`clouds` (1 GPU): the update and resample kernels on the cloud shapes the configs name
+(converged / init / diffuse / kidnapped), since the timed cycle itself only ever sees a
+converged cloud.
 """
 import argparse
 import json
@@ -23,6 +30,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import threading
 import time
 
 import numpy as np
@@ -35,14 +43,10 @@ from smarc_navigation_b200 import world  # noqa: E402
 METRIC = "particle_beam_evals_per_s"
 UNIT = "evals/s"
 P_PREDICTS = 5
-# dram__bytes_read.sum + dram__bytes_write.sum of k_update_mbes_profile per launch, from the committed ncu --set full
-# capture (profiles/r1_ncu_update_mbes_profile.txt); only the workload that was captured has a figure
-NCU_DRAM_TRAFFIC = {"C3": 33.64e6 + 0.87e6}
-# what bounds that kernel, from the same capture (SURVEY 8d asks for these instead of a %-of-HBM figure)
-NCU_DOMINANT = {"C3": {"issue_slots_used": 0.72, "ipc_per_sm": 2.85, "active_lanes_of_32": 23.5, "l1_hit_rate": 0.988,
-                       "l2_hit_rate": 0.76, "registers": 96, "warps_per_sm": 18, "top_stall": "wait (dependent issue)",
-                       "source": "profiles/r1_ncu_update_mbes_profile.txt"}}
 RS_BYTES = 96        # algorithmic HBM bytes per particle of normalise + scan + select + gather
+RS_BYTES_SURVEY = 80 # the same with SURVEY 8d's float32 x, y (the figure BASELINE.md's 60 % target is quoted on)
+NCU_FILE = os.path.join(ROOT, "profiles", "ncu_dominant.json")
+CLOUDS = {"converged": 0.1, "init": 2.0, "diffuse": 20.0, "kidnapped": None}     # sigma_xy [m]; None = uniform over the map
 
 
 def parse():
@@ -52,27 +56,27 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--cloud", default=None, choices=sorted(CLOUDS),
+                    help="only run the update + resample kernels on this cloud shape (for ncu captures)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=None,
                     help="target CPU work per reference step / baseline sample (default: 15 s for the baseline "
                          "sample; for --impl reference about 75 s split over the steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c4/c5 sub-records and the cloud sweep")
     return ap.parse_args()
 
 
-def workload(args, n_gpus):
-    name = args.workload
+def workload(name, n_gpus):
     if name == "auto":
         name = "C3"
     c = dict(world.CONFIGS[name])
-    if name == "C4":
-        per_gpu = c["particles"] // 8
-    else:
-        per_gpu = c["particles"]
+    per_gpu = c["particles"] // 8 if name == "C4" else c["particles"]
     # C5: 256 independent filters over 8 GPUs = 32 whole filters per GPU, no cross-GPU traffic
     c["filters_per_gpu"] = c.get("filters", 8) // 8 if name == "C5" else 1
     c["name"] = name
     c["per_gpu"] = per_gpu
-    c["total"] = per_gpu * n_gpus
+    c["total"] = per_gpu * n_gpus * c["filters_per_gpu"]
     return c
 
 
@@ -84,14 +88,74 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_record(name):
+    """ncu figures of the dominant kernel (dram traffic per launch, issue, lanes, hit rates) from the dated,
+    commit-stamped capture summary under profiles/ -- not measured in this run, and labelled so."""
+    try:
+        d = json.load(open(NCU_FILE))
+    except (OSError, ValueError):
+        return None
+    return d.get(name)
+
+
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML in this process (a thread, 10 ms
+    period -- an `nvidia-smi -lms` child needs seconds to start on an 8-GPU box and returned nothing there),
+    `nvidia-smi` as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, local_rank):
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = False
+        self.active = True              # pause() / resume(): only the timed regions are sampled
+        self.thread = self.p = self.f = None
+        self.how = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            except Exception:           # noqa: BLE001
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+                h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv, self.h = pynvml, h
+            self._sample()              # fails here rather than in the thread
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception:               # noqa: BLE001
+            self._start_smi(local_rank)
+
+    def _sample(self):
+        nv, h = self.nv, self.h
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _loop(self):
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self._sample()
+                except Exception:       # noqa: BLE001
+                    pass
+            time.sleep(0.005)
+
+    def _start_smi(self, gpu_index):
+        self.how = "nvidia-smi"
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.idx = gpu_index
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "25"], stdout=self.f,
@@ -99,40 +163,67 @@ class ClockSampler(object):
         except OSError:
             self.p = None
 
+    def pause(self):
+        self.active = False
+
+    def resume(self, forget=False):
+        """Sample from here on; forget=True drops what was sampled so far (set-up, warm-up)."""
+        if forget and self.how == "nvml":
+            self.sm, self.mx, self.reasons = [], [], set()
+        self.active = True
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
+        if self.how == "nvml":
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if not self.sm:
+                try:
+                    self._sample()
+                except Exception:       # noqa: BLE001
+                    pass
+        elif self.p is not None:
+            self.p.terminate()
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        os.unlink(self.f.name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+            self.f.flush()
+            self.f.seek(0)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for line in self.f.read().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    self.sm.append(float(c[1]))
+                    self.mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            os.unlink(self.f.name)
+        if self.sm:
+            # median over the samples taken while the GPU was busy (clock above idle), else over all
+            sm = np.asarray(self.sm)
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(self.mx)), reasons=sorted(self.reasons),
+                       samples=len(self.sm))
         return out
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_cycle_setup(cfg, seed_particles=4):
+def cpu_threads():
+    """All the host threads the CPU arm can use -- set explicitly: torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_cycle_setup(cfg):
     from oracle import c_oracle
+    c_oracle.set_num_threads(cpu_threads())
     dem = world.make_dem(cfg["dem_n"], cfg["res"])
     beams = world.make_beams(cfg["beams"])
     ext = cfg["dem_n"] * cfg["res"]
@@ -181,12 +272,32 @@ def cpu_sample_size(cfg, seconds):
     return n, cores
 
 
+def reference_python_record():
+    """CPU-A / CPU-B of BASELINE.md section 3: the UNMODIFIED reference Python at config C1, timed live when
+    the reference checkout is reachable (the build container), else the committed build-container record."""
+    from oracle import ref_timing
+    if ref_timing.reachable():
+        r = ref_timing.run()
+        r["source"] = "measured live in this run (reference checkout reachable)"
+        return r
+    r = ref_timing.recorded()
+    if r is None:
+        return {"kind": "reference-python", "reachable": False, "why": "no reference checkout and no committed record"}
+    r = dict(r)
+    r["reachable"] = False
+    r["source"] = ("NOT measured in this run: /root/reference does not exist on this machine; these are the numbers "
+                   "committed in profiles/r2_reference_python_c1.json, measured in the build container on '%s'"
+                   % r.get("cpu_model"))
+    return r
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = workload(args, args.gpus)
-    # bounded sample: the whole --steps K --warmup W run should end within a couple of minutes
+    cfg = workload(args.workload, args.gpus)
+    # bounded sample: the whole --steps K --warmup W run should end within a couple of minutes; the SAME target
+    # of CPU work per step at every N, and every host thread whatever the launcher exported
     per_step = args.cpu_seconds if args.cpu_seconds else min(15.0, max(0.5, 75.0 / (args.steps + min(args.warmup, 1))))
     n, cores = cpu_sample_size(cfg, per_step)
     t, cores = cpu_run(cfg, n, args.steps, min(args.warmup, 1))
@@ -200,41 +311,38 @@ def run_reference(args):
             "config": {"workload": "%s: %d particles x %d beams, %.1f m DEM %dx%d" % (
                 cfg["name"], cfg["total"], cfg["beams"], cfg["res"], cfg["dem_n"], cfg["dem_n"]),
                 "predicts_per_cycle": P_PREDICTS},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
+                             "sample": sample,
+                             "note": "throughput of the host CPU on this path does not grow with the number of GPUs: "
+                                     "the same box, the same threads at every N"},
+            "cpu_baseline_reference": reference_python_record(),
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
+class Ctx(object):
+    pass
+
+
+def make_filter(ctx, cfg, exchange):
+    """The filter (single handle, filter batch or particle-sharded) for one workload, map and fan loaded."""
     import torch
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world_size > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    G = world_size
-    cfg = workload(args, G)
-    M, B, F = cfg["per_gpu"], cfg["beams"], cfg["filters_per_gpu"]
-    K, W = args.steps, max(args.warmup, 3)
     P = world.MBES_PARAMS
+    G, rank, local_rank, dist = ctx.G, ctx.rank, ctx.local_rank, ctx.dist
+    M, B, F = cfg["per_gpu"], cfg["beams"], cfg["filters_per_gpu"]
     ext = cfg["dem_n"] * cfg["res"]
-    dem = world.make_dem(cfg["dem_n"], cfg["res"])
+    dem = ctx.dems.setdefault((cfg["dem_n"], cfg["res"]), world.make_dem(cfg["dem_n"], cfg["res"]))
     beams = world.make_beams(B)
     # one trajectory per filter (C5: offset starts, own odometry noise seed)
     trajs = [world.Trajectory(ext, seed=2 + (rank * F + f if F > 1 else 0),
                               offset=(12.0 * ((rank * F + f) % 16), 12.0 * ((rank * F + f) // 16)) if F > 1 else (0.0, 0.0))
              for f in range(F)]
-    traj = trajs[0]
-
     from smarc_navigation_b200 import ParticleFilter
     common = dict(init_covariance=P["init_covariance"], motion_covariance=P["motion_covariance"],
                   resampling_noise_covariance=P["resampling_noise_covariance"],
                   measurement_std=P["measurement_std"], range_min=world.RANGE_MIN, range_max=world.RANGE_MAX,
-                  init_mean=traj.truth, seed=4, coarse_level=int(os.environ.get("AUVPF_COARSE_LEVEL", "-1"), 0))
+                  init_mean=trajs[0].truth, seed=4, coarse_level=int(os.environ.get("AUVPF_COARSE_LEVEL", "-1"), 0))
     if G == 1 or F > 1:
         pf = ParticleFilter(particle_count=M, n_filters=F, device=local_rank, **common)
         filt = pf
@@ -244,10 +352,129 @@ def run_ours(args):
             pf.set_poses(p0)
     else:
         from smarc_navigation_b200.sharded import ShardedParticleFilter
-        filt = ShardedParticleFilter(M, dist, device=local_rank, **common)
+        filt = ShardedParticleFilter(M, dist, device=local_rank, exchange=exchange, **common)
         pf = filt.pf
     filt.set_dem(dem)
     filt.set_beams(beams)
+    return filt, pf, dem, trajs
+
+
+def parity_check(ctx, cfg, filt, pf):
+    """One extra resample on seeded log-weights and a known state (x = global particle id), compared bit for
+    bit with the CPU oracle's systematic ancestors: 'ok' / 'FAIL'.  Runs through exactly the resample path that
+    was timed (single handle, filter batch, peer-memory or NCCL exchange), at every N."""
+    import torch
+    from oracle import c_oracle, pf_oracle as o
+    G, rank, dist = ctx.G, ctx.rank, ctx.dist
+    M, F = cfg["per_gpu"], cfg["filters_per_gpu"]
+    sharded = G > 1 and F == 1
+    u = 0.3721
+    rows = M * F
+    lw = (np.random.default_rng([1234, rank]).normal(0.0, 3.0, rows) - 40.0).astype(np.float32)
+    lw[::1000] = -np.inf
+    poses = np.zeros((rows, 6))
+    base = rank * M if sharded else 0
+    poses[:, 0] = base + (np.arange(rows) % M if F > 1 else np.arange(rows))
+    pf.set_poses(poses)
+    pf.set_log_weights(lw)
+    if sharded:
+        filt.resample(u=u, roughen=False)
+    else:
+        pf.resample(u=u, roughen=False)
+    got = np.rint(pf.poses()[:, 0]).astype(np.int64)
+    ok = True
+    if sharded:
+        t_lw = torch.from_numpy(lw).cuda()
+        t_an = torch.from_numpy(got).cuda()
+        all_lw = torch.empty(G * M, dtype=torch.float32, device="cuda")
+        all_an = torch.empty(G * M, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(all_lw, t_lw)
+        dist.all_gather_into_tensor(all_an, t_an)
+        if rank == 0:
+            qq = c_oracle.quantise_logw(all_lw.cpu().numpy())[0]
+            want = c_oracle.systematic(o.weights_from_q(qq), u)
+            ok = bool(np.array_equal(all_an.cpu().numpy(), want.astype(np.int64)))
+    else:
+        for f in range(F):
+            qq = c_oracle.quantise_logw(lw[f * M:(f + 1) * M])[0]
+            want = c_oracle.systematic(o.weights_from_q(qq), u)
+            ok = ok and bool(np.array_equal(got[f * M:(f + 1) * M], want.astype(np.int64)))
+    if dist is not None:
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    return "ok" if ok else "FAIL"
+
+
+def cloud_poses(shape, n, truth, ext, rng):
+    p = np.tile(truth, (n, 1))
+    sig = CLOUDS[shape]
+    if sig is None:       # kidnapped: uniform over the map, any heading
+        p[:, 0] = rng.uniform(0.0, ext, n)
+        p[:, 1] = rng.uniform(0.0, ext, n)
+        p[:, 5] = rng.uniform(-np.pi, np.pi, n)
+    else:
+        p[:, 0] += rng.normal(0.0, sig, n)
+        p[:, 1] += rng.normal(0.0, sig, n)
+        p[:, 5] += rng.normal(0.0, 0.1 if sig > 0.5 else 0.003, n)
+    return p
+
+
+def cloud_sweep(ctx, cfg, pf, traj, shapes, K):
+    """The update (raycast + likelihood) and resample kernels on the cloud shapes the configs name.  Per step the
+    cloud is put back (device copy, untimed), L2 is flushed, then the update and the resample are timed with
+    CUDA events on the library's stream."""
+    import ctypes as C
+    import torch
+    from smarc_navigation_b200 import _lib
+    L = _lib.load()
+    M, B = cfg["per_gpu"], cfg["beams"]
+    ext = cfg["dem_n"] * cfg["res"]
+    truth = traj.truth.copy()
+    meas = torch.from_numpy((pf.raycast(truth[None, :])[0] + world.ping_noise(B, 999)).astype(np.float32)).cuda()
+    stream = torch.cuda.ExternalStream(pf.stream_ptr)
+    out = {}
+    rng = np.random.default_rng(77)
+    for shape in shapes:
+        cloud = torch.from_numpy(cloud_poses(shape, M, truth, ext, rng)).cuda()
+        torch.cuda.synchronize()
+        t_up, t_rs = [], []
+        flagged = 0
+        for s in range(K + 2):
+            _lib.check(L.auvpf_set_poses(pf._h, C.c_void_p(cloud.data_ptr())))
+            with torch.cuda.stream(stream):
+                ctx.flush.zero_()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record(stream)
+            _lib.check(L.auvpf_update_mbes(pf._h, C.c_void_p(meas.data_ptr()), None))
+            e1.record(stream)
+            pf.resample(wait=False)
+            e2.record(stream)
+            pf.sync()
+            if s >= 2:
+                t_up.append(e0.elapsed_time(e1))
+                t_rs.append(e1.elapsed_time(e2))
+            flagged = int(pf.mbes_flagged()[0])
+        up = float(np.median(t_up))
+        out[shape] = {"sigma_xy_m": CLOUDS[shape], "update_ms": up, "evals_per_s": M * B / (up * 1e-3),
+                      "flagged_particle_frac": flagged / float(M), "resample_ms": float(np.median(t_rs)),
+                      "neff_frac": float(pf.neff()[0]) / M if shape != "kidnapped" else None}
+    ref = out.get("converged")
+    if ref:
+        for shape, r in out.items():
+            r["vs_converged"] = r["evals_per_s"] / ref["evals_per_s"]
+    return out
+
+
+def measure(ctx, args, cfg, with_cpu, with_clouds):
+    import ctypes as C
+    import torch
+    from smarc_navigation_b200 import _lib
+    G, rank, dist = ctx.G, ctx.rank, ctx.dist
+    M, B, F = cfg["per_gpu"], cfg["beams"], cfg["filters_per_gpu"]
+    K, W = args.steps, max(args.warmup, 3)
+    filt, pf, dem, trajs = make_filter(ctx, cfg, args.exchange)
+    sharded = G > 1 and F == 1
 
     # synthetic ping sequence: ground-truth ranges raycast on the GPU (the product path), + noise
     n_steps = 2 * (K + W) + 2 * K + 2
@@ -266,15 +493,15 @@ def run_ours(args):
     pings_dev = torch.from_numpy(np.stack([c[1] for c in cycles])).cuda()
     pings_pin = torch.from_numpy(np.stack([c[1] for c in cycles])).pin_memory()
     stream = torch.cuda.ExternalStream(pf.stream_ptr)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    import ctypes as C
-    from smarc_navigation_b200 import _lib
     L = _lib.load()
+
+    def resample():
+        filt.resample() if sharded else filt.resample(wait=False)       # enqueue only: no host wait in the cycle
 
     def cycle_device(s):
         filt.predict_many(cycles[s][0])            # the 5 odometry messages between two pings, one pass over the state
         _lib.check(L.auvpf_update_mbes(pf._h, C.c_void_p(pings_dev[s].data_ptr()), None))
-        filt.resample(wait=False) if (G == 1 or F > 1) else filt.resample()     # enqueue only: no host wait in the cycle
+        resample()
 
     def barrier():
         if dist is not None:
@@ -283,7 +510,14 @@ def run_ours(args):
 
     def flush_l2():
         with torch.cuda.stream(stream):
-            flush.zero_()
+            ctx.flush.zero_()
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- device-resident timing --------------------------------------------------------------
     for s in range(W):
@@ -291,8 +525,9 @@ def run_ours(args):
     pf.sync()
     pf.profile(True)
     pf.profile_read(reset=True)
-    clocks = ClockSampler(local_rank)
     barrier()
+    ctx.clocks.resume(forget=not ctx.timed_once)
+    ctx.timed_once = True
     evs = []
     for s in range(W, W + K):
         flush_l2()
@@ -302,15 +537,11 @@ def run_ours(args):
         e1.record(stream)
         evs.append((e0, e1))
     barrier()
+    ctx.clocks.pause()
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = float(np.sum(step_ms))
     prof = pf.profile_read(reset=True)
     pf.profile(False)
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / K
+    ms_per_step = max_over_ranks(float(np.sum(step_ms))) / K
     value = M * F * G * B / (ms_per_step * 1e-3)
     mean, cov = filt.mean_cov()
     mean = np.asarray(mean).reshape(-1, 6) if F > 1 else np.asarray(mean).reshape(1, -1)
@@ -318,39 +549,37 @@ def run_ours(args):
     track_err = float(np.max(np.hypot(mean[:, 0] - tr[:len(mean), 0], mean[:, 1] - tr[:len(mean), 1])))
 
     # ---- end to end through the public API, host buffers ----------------------------------------
+    def cycle_host(s):
+        filt.predict_many(cycles[s][0])
+        if sharded:
+            filt.update_mbes(pings_pin[s].numpy())
+        else:
+            pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
+        resample()
+        return filt.mean_cov()                  # reads the estimate back: the cycle's results are on the host here
+
     base = W + K
     for s in range(base, base + W):
-        filt.predict_many(cycles[s][0])
-        filt.update_mbes(pings_pin[s].numpy()) if (G > 1 and F == 1) else pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
-        filt.resample(wait=False) if (G == 1 or F > 1) else filt.resample()
-        filt.mean_cov()
+        cycle_host(s)
     barrier()
+    ctx.clocks.resume()
     t0 = time.perf_counter()
     e2e_lat = []
     for s in range(base + W, base + W + K):
         t1 = time.perf_counter()
-        filt.predict_many(cycles[s][0])
-        if G > 1 and F == 1:
-            filt.update_mbes(pings_pin[s].numpy())
-        else:
-            pf.update_mbes(pings_pin[s].numpy(), return_weights=False)
-        filt.resample(wait=False) if (G == 1 or F > 1) else filt.resample()
-        est = filt.mean_cov()                   # reads the estimate back: the cycle's results are on the host here
+        cycle_host(s)
         e2e_lat.append(1e3 * (time.perf_counter() - t1))
     barrier()
-    e2e_s = time.perf_counter() - t0
-    clk = clocks.stop()                         # sampled over both timed regions (device-resident and end-to-end)
-    if dist is not None:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    ctx.clocks.pause()
     e2e_value = M * F * G * B * K / e2e_s
 
     # ---- the same K cycles as ONE replay call (auvpf_replay): the sequence goes up once from host
     # memory, K cycles are enqueued back to back, the K estimates come back once ------------------------
     replay = None
-    if G == 1 or F > 1:
+    if not sharded:
         from smarc_navigation_b200.filter import _odom_row
+
         def rows(s0, s1):
             od = np.array([[([_odom_row(o, None)] if F == 1 else o) for o in cycles[s][0]] for s in range(s0, s1)], np.float64)
             return od.reshape(s1 - s0, P_PREDICTS, F, 11), np.stack([cycles[s][1] for s in range(s0, s1)]).reshape(s1 - s0, F, B)
@@ -360,13 +589,9 @@ def run_ours(args):
         od_k, rg_k = rows(b2 + K, b2 + 2 * K)
         barrier()
         t0 = time.perf_counter()
-        rmean, rcov = pf.replay(od_k, rg_k)
+        pf.replay(od_k, rg_k)
         barrier()
-        rp_s = time.perf_counter() - t0
-        if dist is not None:
-            t = torch.tensor([rp_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            rp_s = float(t.item())
+        rp_s = max_over_ranks(time.perf_counter() - t0)
         replay = {"value": M * F * G * B * K / rp_s, "unit": UNIT, "ms_per_step": 1e3 * rp_s / K,
                   "h2d_bytes_per_step": F * (B * 4 + 8 + P_PREDICTS * 40), "d2h_bytes_per_step": F * 16 * 8,
                   "note": "ParticleFilter.replay: one upload, K cycles enqueued back to back, one read-back"}
@@ -376,20 +601,19 @@ def run_ours(args):
     # ---- roofline of the dominant kernel + the HBM-bound resample path ----------------------------
     peak, peak_src = peaks()
     dem_bytes = dem["z"].size * 4
-    mbes_ms, mbes_n = prof["update_mbes"]
-    mbes_n = K                                               # per update (profile-merge kernel + per-ray kernel for flagged particles)
+    mbes_ms = prof["update_mbes"][0] / K                    # per update (profile-merge kernel + per-ray kernel for flagged particles)
     alg_mbes = M * F * (32 + 4) + dem_bytes + 16 * B        # state read + logw write, DEM once, beam table
-    ach = alg_mbes / (mbes_ms / max(mbes_n, 1) * 1e-3) / 1e9 if mbes_n else 0.0
-    rs_ms = prof["normalise"][0] + prof["scan"][0] + prof["select_gather"][0]
-    rs_n = K                                                # one resample per cycle
-    alg_rs = M * F * RS_BYTES                                   # normalise 4 + scan 12 + select 12 + gather 4+32+32
-    ach_rs = alg_rs / (rs_ms / rs_n * 1e-3) / 1e9 if rs_ms > 0 else 0.0
+    ach = alg_mbes / (mbes_ms * 1e-3) / 1e9 if mbes_ms > 0 else 0.0
+    rs_ms = (prof["normalise"][0] + prof["scan"][0] + prof["select_gather"][0]) / K      # one resample per cycle
+    ach_rs = M * F * RS_BYTES / (rs_ms * 1e-3) / 1e9 if rs_ms > 0 else 0.0
     prop_ms, prop_n = prof["propagate"]
     # one launch runs the P predicts of a cycle in registers: algorithmic traffic = one read (x, y, yaw) + one write
     ach_prop = M * F * 52 / (prop_ms / max(prop_n, 1) * 1e-3) / 1e9 if prop_n else 0.0
     launches = int(sum(v[1] for v in prof.values()))
+    ncu = ncu_record(cfg["name"]) if G == 1 else None
+    rs_kernels = getattr(filt, "resample_kernels", None) or "k_normalise + k_quotients + k_select_gather"
 
-    line = {
+    rec = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": G, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -397,9 +621,9 @@ def run_ours(args):
             cfg["name"], ("%d filters x " % F) if F > 1 else "", M, B, M * F * G, cfg["res"], cfg["dem_n"], cfg["dem_n"],
             P_PREDICTS),
             "parallelism": ("filter-sharded x%d (%d filters/GPU, no communication)" % (G, F)) if F > 1 else
-            "particle-sharded x%d%s" % (G, (", exchange=%s" % filt.exchange) if G > 1 else ""), "l2": "flushed between steps (256 MiB memset)",
-            "resampler": "systematic", "cycle_hz": 1e3 / ms_per_step},
-        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"]},
+            "particle-sharded x%d%s" % (G, (", exchange=%s" % filt.exchange) if sharded else ""),
+            "l2": "flushed between steps (256 MiB memset)", "cloud": "converged (steady state of the tracking filter; "
+            "other shapes: `clouds`)", "resampler": "systematic", "cycle_hz": 1e3 / ms_per_step},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / K,
                 # filter-cycle latency, host call to estimate on the host (BASELINE metric, second half)
@@ -411,32 +635,74 @@ def run_ours(args):
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "kernel": "k_update_mbes_profile (+ k_update_mbes for flagged particles): fused raycast + beam likelihood",
                      "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": NCU_DRAM_TRAFFIC.get(cfg["name"]) if G == 1 else None,
-                     "ncu": NCU_DOMINANT.get(cfg["name"]),
-                     "peak_source": peak_src, "ms_per_launch": mbes_ms / max(mbes_n, 1),
-                     "evals_per_s": M * F * B / (mbes_ms / max(mbes_n, 1) * 1e-3) if mbes_n else None,
-                     "note": "dominant kernel is instruction-issue-bound (ncu: 72 % of issue slots, 2.85 IPC/SM, L1 hit "
-                             "99 %) on an L1/L2-resident DEM footprint, not HBM-bound (SURVEY 8d): its algorithmic HBM "
-                             "bytes are 0.2 % of what the measured time could move; the HBM-bound path is roofline_resample"},
-        "roofline_resample": {"bound": "hbm", "kernel": "k_normalise + k_quotients + k_select_gather",
+                     "traffic": (ncu or {}).get("dram_bytes_per_launch"),
+                     "ncu": ncu,
+                     "peak_source": peak_src, "ms_per_launch": mbes_ms,
+                     "evals_per_s": M * F * B / (mbes_ms * 1e-3) if mbes_ms > 0 else None,
+                     "note": "the dominant kernel is instruction-issue-bound on an L1/L2-resident DEM footprint, not "
+                             "HBM-bound (SURVEY 8d): its algorithmic HBM bytes are a fraction of a percent of what the "
+                             "measured time could move; `ncu` holds the issue / lane / hit-rate figures of the dated "
+                             "capture under profiles/; the HBM-bound path is roofline_resample"},
+        "roofline_resample": {"bound": "hbm", "kernel": rs_kernels,
                               "achieved": ach_rs, "peak": peak, "unit": "GB/s", "frac": ach_rs / peak,
-                              "ms_per_cycle": rs_ms / rs_n, "bytes_per_particle": RS_BYTES},
+                              "frac_survey_80B": (M * F * RS_BYTES_SURVEY / (rs_ms * 1e-3) / 1e9 / peak) if rs_ms > 0 else 0.0,
+                              "ms_per_cycle": rs_ms, "bytes_per_particle": RS_BYTES},
         "roofline_propagate": {"bound": "hbm", "achieved": ach_prop, "peak": peak, "unit": "GB/s",
                                "frac": ach_prop / peak, "ms_per_launch": prop_ms / max(prop_n, 1)},
         "kernel_ms_per_cycle": {k: v[0] / K for k, v in prof.items() if v[1]},
         "track_error_m": track_err,
     }
-    if rank == 0 and G == 1 and not args.no_cpu_baseline:
+    if with_clouds and G == 1 and F == 1:
+        rec["clouds"] = cloud_sweep(ctx, cfg, pf, trajs[0], list(CLOUDS), max(5, min(K, 10)))
+    rec["parity_check"] = parity_check(ctx, cfg, filt, pf)
+    if with_cpu and rank == 0 and G == 1:
         n, cores = cpu_sample_size(cfg, args.cpu_seconds or 15.0)
         t, cores = cpu_run(cfg, n, 1, 0)
-        line["cpu_baseline"] = {"value": n * B / t, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "%d of %d particles x %d beams, 1 cycle, C/OpenMP float64 oracle port" % (
-                                    n, M, B)}
-    if rank == 0:
-        print(json.dumps(line))
+        rec["cpu_baseline"] = {"value": n * B / t, "unit": UNIT, "cores": cores, "host_cpus": os.cpu_count(), "kind": "port",
+                               "sample": "%d of %d particles x %d beams, 1 cycle, C/OpenMP float64 oracle port" % (n, M, B)}
+        rec["cpu_baseline_reference"] = reference_python_record()
     filt.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    return rec
+
+
+def run_ours(args):
+    import torch
+    ctx = Ctx()
+    ctx.rank = int(os.environ.get("RANK", "0"))
+    ctx.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    ctx.G = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(ctx.local_rank)
+    ctx.dist = None
+    if ctx.G > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", ctx.local_rank))
+        ctx.dist = dist
+    ctx.dems = {}
+    ctx.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ctx.clocks = ClockSampler(ctx.local_rank)
+    ctx.timed_once = False
+    cfg = workload(args.workload, ctx.G)
+    if args.cloud:          # ncu helper: only the two kernels on one cloud shape
+        filt, pf, dem, trajs = make_filter(ctx, cfg, args.exchange)
+        out = cloud_sweep(ctx, cfg, pf, trajs[0], [args.cloud], max(2, args.steps))
+        print(json.dumps({"cloud_only": out}))
+        filt.close()
+        return
+    line = measure(ctx, args, cfg, with_cpu=not args.no_cpu_baseline, with_clouds=not args.no_extras)
+    if ctx.G == 8 and args.workload == "auto" and not args.no_extras:
+        # the two north-star configurations that need the whole box, observed in the same run
+        for key in ("C4", "C5"):
+            sub = measure(ctx, args, workload(key, ctx.G), with_cpu=False, with_clouds=False)
+            line[key.lower()] = {k: sub[k] for k in ("value", "unit", "ms_per_step", "e2e", "cycle_latency_ms", "config",
+                                                     "roofline_resample", "kernel_ms_per_cycle", "parity_check",
+                                                     "track_error_m", "gpu_launches")}
+    clk = ctx.clocks.stop()                         # sampled over the timed regions of every workload of this run
+    line["clocks"] = {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
+                      "samples": clk["samples"], "how": clk["how"]}
+    if ctx.rank == 0:
+        print(json.dumps(line))
+    if ctx.dist is not None:
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -160,6 +160,11 @@ int auvpf_update_gps(auvpf_handle *h, const double *gps_xy, float *logw_out);
  * logw = -1/(2 std^2) sum_b (r_b - rhat_b)^2 - B_valid log(std sqrt(2 pi)).
  * ranges: (F, B) float32 measured ranges (a LaserScan's ranges[]). */
 int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out);
+/* Particles per filter ((F) int64) that the last auvpf_update_mbes could not certify for the
+ * one-march-per-fan-side kernel (sensor reach leaves the map, centre beam missed, a facet steeper than
+ * the fan tilt allows) and recast ray by ray; synchronises.  A measurement aid (bench.py reports the
+ * fraction per cloud shape). */
+int auvpf_mbes_flagged(auvpf_handle *h, int64_t *count);
 /* Parity probe: expected ranges (n, B) float32 for n explicit poses (n, 6). */
 int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges_out);
 

@@ -59,6 +59,7 @@ SYMBOLS = [
     ("auvpf_predict_many", C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     ("auvpf_update_gps", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_update_mbes", C.c_int, [_vp, _vp, _vp]),
+    ("auvpf_mbes_flagged", C.c_int, [_vp, _vp]),
     ("auvpf_raycast", C.c_int, [_vp, _vp, _i64, _vp]),
     ("auvpf_resample", C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     ("auvpf_resample_weights", C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),

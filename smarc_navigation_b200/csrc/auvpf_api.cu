@@ -1273,6 +1273,17 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
     return AUVPF_OK;
 }
 
+int auvpf_mbes_flagged(auvpf_handle *h, int64_t *count)
+{
+    if (!h || !count) return fail(AUVPF_ERR_BADARG, "null argument");
+    Guard g(h);
+    std::vector<unsigned int> c(h->F);
+    CU(cudaMemcpyAsync(c.data(), h->wmax_f32 + h->F, sizeof(unsigned int) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < h->F; ++f) count[f] = (h->fan.planar && h->use_profile) ? (int64_t)(c[f] - (unsigned int)kWmaxReset) : h->M;
+    return AUVPF_OK;
+}
+
 int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges_out)
 {
     if (!h || !poses || !ranges_out || n <= 0) return fail(AUVPF_ERR_BADARG, "bad argument");

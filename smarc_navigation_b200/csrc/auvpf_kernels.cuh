@@ -1308,6 +1308,7 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
     const SysPos spos = make_sys_pos(u, n);
     // block-relative end of source j's run (rel_end_of, auvpf_math.cuh): clamp(count_below(cdf[j]) - g0, 0, nblk)
     const RelEndCtx rctx = make_rel_end(u, n, g0, nblk);
+    const int64_t j_last = p.n_global - 1 - p.j_global0;      // local index of the filter's last particle (>= M on the other shards)
     auto rel_end = [&](unsigned long long cdfv, int64_t j) -> int {
         const unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
         return rel_end_of(spos, p.n_global, rctx, p.q_offset + cdfv + (jg1 < D ? jg1 : D));
@@ -1378,6 +1379,13 @@ k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, 
             for (int k = 1; k < kSrcItems - 1; ++k) e[k] = j0 + k <= j_hi ? rel_end(cv[k], j0 + k) : nblk;
             e[kSrcItems - 1] = e_last;
         }
+        // The filter's LAST particle ends where the outputs end, whatever its CDF value says: for
+        // u >= 1 - N 2^-54 the last position rounds to 1.0 = cumsum[-1], the reference walks off the end
+        // (IndexError, resampling.py:162-167), and every path here -- this kernel, its records form and
+        // k_select_gather_p2p's clamp -- gives that output to the last particle.
+#pragma unroll
+        for (int k = 0; k < kSrcItems; ++k)
+            if (j0 + k == j_last) e[k] = nblk;
         // where this thread's first run starts = where the previous particle's run ends: the lane below
         // has it; lane 0 evaluates the particle before its own (no block barrier for the hand-over), and
         // the block's first located particle starts at slot 0

@@ -291,6 +291,13 @@ class ParticleFilter(object):
             _lib.check(self._lib.auvpf_update_mbes(self._h, _ptr(r), _ptr(out)))
         return self._weights_out(out) if return_weights else None
 
+    def mbes_flagged(self):
+        """Per filter: particles of the last ``update_mbes`` that were recast ray by ray (synchronises)."""
+        out = np.zeros(self.n_filters, np.int64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_mbes_flagged(self._h, _ptr(out)))
+        return out
+
     def raycast(self, poses):
         """Expected ranges (n, B) float32 for explicit poses (parity probe)."""
         p = np.ascontiguousarray(poses, np.float64).reshape(-1, 6)

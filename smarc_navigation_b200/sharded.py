@@ -311,6 +311,15 @@ class ShardedParticleFilter(object):
         self._step = 0
         self._seed = int(kw.get("seed", 0))
 
+    @property
+    def resample_kernels(self):
+        """What a resample launches on this path (bench.py labels its roofline line with it)."""
+        if self.ops.p2p:
+            return ("k_normalise + all_reduce(MAX, SUM) + k_scan_q (look-back) + all_gather(Q) + k_shard_meta + "
+                    "k_select_gather_p2p (select + gather + exchange over peer memory)")
+        return ("k_normalise + all_reduce(MAX, SUM) + k_scan_q (look-back) + all_gather(Q) + k_select_gather<records> + "
+                "all_to_all_single + k_load_records")
+
     def set_dem(self, *a, **k):
         self.pf.set_dem(*a, **k)
 

@@ -440,6 +440,8 @@ void hs_select_source_side(const uint64_t *q_raw, long M, double u, uint64_t D, 
                     for (int k = 1; k < kItems - 1; ++k) e[k] = j0 + k <= j_hi ? rel_end(cv[k], j0 + k) : nblk;
                     e[kItems - 1] = e_last;
                 }
+                for (int k = 0; k < kItems; ++k)
+                    if (j0 + k == M - 1) e[k] = nblk;       // the last particle ends where the outputs end (kernel: j_last)
                 int start;
                 if ((tid & 31) == 0) {
                     const bool has_prev = j0 > j_lo && j0 - 1 <= j_hi;

@@ -163,6 +163,54 @@ def test_raycast_ranges_vs_oracle(cfg, coarse):
     pf.close()
 
 
+def _ridged_dem(n, res, seed=5):
+    """Steep short-wavelength ridges on top of the synthetic bathymetry: outer beams are occluded
+    (first-hit jumps of metres), near misses over crests are common -- the terrain on which the
+    fragile-ray accounting matters."""
+    d = world.make_dem(n, res, seed=seed)
+    x = np.arange(n, dtype=np.float32) * np.float32(res)
+    X, Y = np.meshgrid(x, x)
+    d["z"] = (d["z"] + 2.5 * np.sin(2 * np.pi * X / 9.0) * np.cos(2 * np.pi * Y / 13.0)
+              + 1.0 * np.sin(2 * np.pi * (X + Y) / 4.0)).astype(np.float32)
+    return d
+
+
+def test_raycast_and_logw_on_ridged_terrain_c3_size():
+    """C3-size map (4000^2 at 0.5 m) with occluding ridges, C3 beam count: ranges of > 1e5 rays and the
+    log-weights of their particles against the oracle, fragile rays bounded by their bracket and counted."""
+    c = world.CONFIGS["C3"]
+    dem = _ridged_dem(c["dem_n"], c["res"])
+    B = c["beams"]
+    beams = world.make_beams(B).astype(np.float32).astype(np.float64)
+    rng = np.random.default_rng(17)
+    poses = np.concatenate([_cloud(rng, 128, (600.0, 600.0), 4.0, roll_pitch=0.04),
+                            _cloud(rng, 128, (1500.0, 400.0), 25.0, roll_pitch=0.04)])
+    pf = _pf(particle_count=len(poses), measurement_std=1.0, range_min=world.RANGE_MIN, range_max=world.RANGE_MAX)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    ro, r = _check_ranges(pf, dem, poses, beams, np.eye(4), world.RANGE_MAX, max_fragile=5e-2, label="ridged C3-size")
+    assert ro.size >= 100000
+    assert (np.abs(np.diff(ro, axis=1)) > 2.0).sum() > 100          # occlusion jumps are present
+    truth = np.array([[600.0, 600.0, -5.0, 0.0, 0.0, 0.3]])
+    meas = (c_oracle.update_mbes(dem, truth, np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX, want_ranges=True)["ranges"][0]
+            + rng.normal(0, 0.05, B)).astype(np.float32)
+    pf.set_poses(poses)
+    pf.update_mbes(meas, return_weights=False)
+    got = pf.log_weights().astype(np.float64)
+    out = c_oracle.update_mbes(dem, poses, np.eye(4), beams, meas.astype(np.float64), 1.0, world.RANGE_MIN,
+                               world.RANGE_MAX, want_ranges=True, want_diag=True)
+    extra, fr = fragile.logw_bound(dem, poses, np.eye(4), beams, meas, 1.0, world.RANGE_MIN, world.RANGE_MAX, out)
+    lognorm = -B * np.log(np.sqrt(2 * np.pi))
+    tol = LOGW_RTOL * (np.abs(out["logw"] - lognorm) + abs(lognorm)) + extra
+    d = np.abs(got - out["logw"])
+    assert np.all(d <= tol), np.max(d / tol)
+    fragile.report({"label": "ridged C3-size log-weights", "particles": len(poses), "fragile_frac": float(fr.mean()),
+                    "particles_with_fragile_beam": float((extra > 0).mean()),
+                    "max_dlogw_fragile_owners": float(d[extra > 0].max()) if (extra > 0).any() else 0.0,
+                    "max_dlogw_sturdy": float(d[extra == 0].max()) if (extra == 0).any() else 0.0})
+    pf.close()
+
+
 def test_raycast_edge_cases():
     dem = world.make_dem(300, 2.0, seed=11)
     beams = world.make_beams(128, half_angle_deg=75.0)

@@ -444,15 +444,14 @@ def test_source_side_select_is_the_references_systematic_resample(N):
         for u in (float(rng.uniform()), 0.0, 1.0 - 2.0 ** -20):
             np.testing.assert_array_equal(hs.select_source_side(raw, u, D), o.systematic_resample(w, u))
         # u so close to 1 that positions[-1] rounds to 1.0 (u >= 1 - N 2^-54): the reference walks off the end
-        # (IndexError, :162-167); the kernel hands such an output to the last particle, or -- when the particle
-        # count is a multiple of the 8 particles a thread walks -- to the last particle that has offspring
+        # (IndexError, :162-167); every select path hands such an output to the LAST particle
         u = 1.0 - 2.0 ** -53
         pos = (u + np.arange(N)) / float(N)
         idx = np.searchsorted(np.cumsum(w), pos, side="right")
         got = hs.select_source_side(raw, u, D)
         inside = idx < N
         np.testing.assert_array_equal(got[inside], idx[inside])
-        assert np.all(np.diff(got) >= 0) and np.all((w[got[~inside]] > 0) | (got[~inside] == N - 1))
+        assert (~inside).sum() == (1 if N > 1 else 0) and np.all(got[~inside] == N - 1)
 
 
 def test_source_side_select_one_million():
