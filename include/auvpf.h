@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define AUVPF_VERSION 100
+#define AUVPF_VERSION 200
 
 /* status codes */
 #define AUVPF_OK 0
@@ -72,8 +72,8 @@ enum {
     AUVPF_K_PROPAGATE = 0,
     AUVPF_K_UPDATE_MBES = 1,
     AUVPF_K_UPDATE_GPS = 2,
-    AUVPF_K_NORMALISE = 3,   /* max + fixed-point sum                                */
-    AUVPF_K_SCAN = 4,        /* decoupled-lookback prefix scan of quantised weights  */
+    AUVPF_K_NORMALISE = 3,   /* k_weights: integer weights, chunk / tile sums, total   */
+    AUVPF_K_SCAN = 4,        /* scans of the residual resampler / reference slot map   */
     AUVPF_K_SELECT_GATHER = 5, /* ancestor select + particle gather (+ roughening)   */
     AUVPF_K_ROUGHEN = 6,
     AUVPF_K_ESTIMATE = 7,
@@ -183,8 +183,10 @@ int auvpf_resample(auvpf_handle *h, int32_t mode, int32_t flags, const double *u
  * resample(weights) of the reference (normalisation auv_pf.py:172 included). */
 int auvpf_resample_weights(auvpf_handle *h, const double *weights, int32_t mode, int32_t flags, const double *u,
                            int32_t *ancestors_out, const double *rough_var, const float *rough_noise);
-/* The fixed-point normalised weights of the last resample: (F*M) uint64,
- * w_i = q_i * 2^-52, sum_i q_i == 2^52 exactly per filter. */
+/* The fixed-point normalised weights of the last resample: (F*M) uint64, w_j = q_j * 2^-52 with
+ * q_j = cdf_j - cdf_{j-1}, cdf_j = floor(C_j 2^52 / A), C_j = sum_{i<=j} a_i, a_i = floor(exp(logw_i - max) 2^60):
+ * sum_j q_j == 2^52 exactly per filter, and np.cumsum(w) is cdf 2^-52 bit for bit.
+ * On a shard of a sharded filter: this shard's slice of the GLOBAL weights. */
 int auvpf_get_weights_q(auvpf_handle *h, uint64_t *q);
 /* Apply caller-supplied ancestor indices with the reference's in-place slot
  * map (auv_pf.py:183-189 keep/lost/dupes + reassign_poses :195-198). */
@@ -196,6 +198,30 @@ int auvpf_roughen(auvpf_handle *h, const double var[6], const float *noise);
 /* mean: (F, 6) [x y z roll pitch yaw_mean_of_wrapped]; cov: (F, 9) row-major
  * 3x3 with the reference's fill pattern ([2,0], [2,1] left 0). */
 int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov);
+/* The estimate with options.  flags == AUVPF_EST_REFERENCE is auvpf_mean_cov.
+ * AUVPF_EST_WEIGHTED: weighted by the current log-weights (w_i = exp(logw_i - max); meaningful between an
+ * update and the resample that consumes it).  AUVPF_EST_CIRCULAR_YAW: mean[5] = atan2(sum w sin yaw,
+ * sum w cos yaw) instead of the reference's arithmetic mean of wrapped yaws (:229-231), which is wrong for
+ * a cloud that straddles +-pi.  AUVPF_EST_FULL_COV: all nine entries of the symmetric 3x3 covariance
+ * (the reference leaves [2,0] and [2,1] zero, :238-246). */
+#define AUVPF_EST_REFERENCE 0
+#define AUVPF_EST_WEIGHTED 1
+#define AUVPF_EST_CIRCULAR_YAW 2
+#define AUVPF_EST_FULL_COV 4
+int auvpf_estimate(auvpf_handle *h, int32_t flags, double *mean, double *cov);
+/* The PoseArray of auv_pf.loc_loop (auv_pf.py:264-285: every particle's position and
+ * quaternion_from_euler(roll, pitch, yaw), :272-275) for a STRIDED subsample, built on the device:
+ * poses7_out (F, n, 7) float64 rows [x y z qx qy qz qw], particles 0, stride, 2 stride, ... of every
+ * filter, n = min(ceil(M / stride), max_poses) returned in *n_out; stride <= 0 picks the stride that yields at
+ * most max_poses.  (After a resample every particle has the same weight, so a stride IS a fair subsample; the
+ * reference publishes all of them -- 48 MB per 10 Hz tick at 1 M particles.) */
+int auvpf_pose_array(auvpf_handle *h, int64_t stride, int64_t max_poses, double *poses7_out, int64_t *n_out);
+/* The same without leaving the device (a sharded filter reduces its ranks' sums with one collective and
+ * reads them back once, sharded.py::combine_pose_sums): auvpf_pose_sums_dev enqueues the pass, the 16
+ * float64 sums per filter land in the library buffer auvpf_pose_sums_buffer returns -- [sum d_xyz, sum roll,
+ * pitch, yaw, wrapped yaw, sum d d^T (xx yy zz xy xz yz), c_xyz], d = position - c, c = the first particle. */
+int auvpf_pose_sums_buffer(auvpf_handle *h, void **sums_f64);
+int auvpf_pose_sums_dev(auvpf_handle *h);
 /* degenerate-weights flag per filter of the last resample, (F) int32; synchronises */
 int auvpf_resample_status(auvpf_handle *h, int32_t *degenerate);
 /* effective sample size 1 / sum w^2 of the last normalisation, (F) */
@@ -207,9 +233,9 @@ int auvpf_neff(auvpf_handle *h, double *neff);
  * identity ancestors -- whenever its N_eff is NOT below ratio * particle_count (the reference's
  * commented value is 0.5).  The decision is taken on the device inside the select kernel (no host
  * round trip on the systematic path) from an exact integer sum of squares, so it is reproducible:
- * N_eff here is auvpf_neff_fixed = 2^64 / sum_i min(q_i >> 20, 2^32 - 1)^2 over the fixed-point
- * weights q_i = floor(a_i 2^52 / A).  With AUVPF_RESIDUAL or
- * AUVPF_RS_INPLACE_REF the handle must hold one filter; particle-sharded filters are not gated. */
+ * N_eff here is auvpf_neff_fixed = (sum_i s_i)^2 / sum_i s_i^2 over s_i = a_i >> 29, a_i the 60-bit integer
+ * weights: sums of integers, the same on one GPU or eight.  With AUVPF_RESIDUAL or
+ * AUVPF_RS_INPLACE_REF the handle must hold one filter.  A particle-sharded filter is gated on the global sums. */
 int auvpf_set_neff_gate(auvpf_handle *h, double ratio);
 int auvpf_neff_fixed(auvpf_handle *h, double *neff);          /* (F); synchronises */
 /* 1 per filter whose last resample the gate held back, (F) int32; synchronises */
@@ -231,47 +257,49 @@ int auvpf_replay(auvpf_handle *h, int32_t n_cycles, int32_t n_steps, int32_t n_o
                  const float *ranges, int32_t mode, int32_t flags, const double *u, const double *rough_var,
                  double *mean_out, double *cov_out);
 
-/* -- multi-GPU staging (particle-sharded single filter) - */
-/* stage 1: local max of logw (F floats) */
-int auvpf_shard_max(auvpf_handle *h, float *m_out);
-/* stage 2: given the GLOBAL max, local fixed-point sums: (F, 2) uint64 limbs
- * [sum of low 32 bits, sum of high bits]; A = lo + (hi << 32). */
-int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *limbs_out);
-/* stage 3: given global max and global A (F,2: lo64, hi64), quantise and scan
- * locally; returns the local total Q (F). */
-int auvpf_shard_scan(auvpf_handle *h, const float *m_global, const uint64_t *A_global, uint64_t *Q_out);
-/* Device-resident variant of stages 1-3 (no host round trip per scalar): the library
- * exposes its per-filter device scalars -- max log-weight as ORDER-PRESERVING int32 (so an
- * integer MAX all-reduce is the float max), the two uint64 limbs of A, the local CDF total Q --
- * and the caller reduces / gathers them in place between the calls, ordered on the handle's
- * stream:  max_dev; all-reduce MAX(wmax_i32);  sum_dev; all-reduce SUM(limbs);  scan_dev;
- * all-gather(Q). */
-int auvpf_shard_buffers(auvpf_handle *h, void **wmax_i32, void **limbs_u64, void **q_u64);
-int auvpf_shard_max_dev(auvpf_handle *h);
-int auvpf_shard_sum_dev(auvpf_handle *h);
-int auvpf_shard_scan_dev(auvpf_handle *h);
-/* Peer-memory exchange: stages 4-5 in ONE kernel over NVLink.  Each rank exports a CUDA IPC
- * handle of its state / CDF / tile-table slab (auvpf_ipc_export, AUVPF_IPC_BLOB_BYTES per
- * rank), the blobs of all ranks are gathered by the caller (rank order) and imported once
- * (auvpf_ipc_import; <= 8 ranks of one node).  After scan_dev and the all-gather of Q,
- * auvpf_shard_gather_p2p(u, q_all) -- q_all: the gathered int64 totals, DEVICE memory -- selects
- * this rank's ancestors in the global CDF reading the owners' tile tables and CDF directly,
- * loads their state from the owners' memory, adds the roughening noise and writes this rank's
- * new state: no records, no all-to-all, no host synchronisation.  Calls must be made by every
- * rank in the same order.  When no shard has any finite weight the state is carried over
- * unchanged and auvpf_shard_degenerate() reports 1 (that call synchronises). */
+/* -- multi-GPU: ONE filter sharded by particles ------------------------------
+ * Rank r of G holds the global particles [r*M, (r+1)*M) (auvpf_config.global_offset / global_count).
+ * Only two things cross GPUs (north_star): the global maximum / sum of the weights, and the particles of
+ * cross-shard ancestors.  The normalised CDF is a quotient of prefix sums, cdf_j = floor(C_j 2^52 / A)
+ * (C_j = sum of the integer weights a_i up to j over ALL shards, A the global total), so a shard's CDF is
+ * its local prefix shifted by the integer mass of the shards below it: what travels is 6 integers per rank.
+ *
+ * Peer-memory path (default): every rank maps the other ranks' slab (state, log-weights, chunk tables and
+ * a mailbox) -- auvpf_ipc_export / auvpf_ipc_import between processes (one per GPU; <= 8 ranks of one
+ * node), auvpf_peer_attach between handles of one process (several GPUs driven by one process, or several
+ * handles on one GPU).  auvpf_shard_resample is then the WHOLE resample of auv_pf.resample
+ * (auv_pf.py:169-192) in two kernels and without any host or NCCL call: the weights kernel posts this
+ * shard's maximum and, at its end, its totals into every peer's mailbox (payload, system fence, flag);
+ * the select kernel waits for the G totals, selects this rank's ancestors in the global CDF by rebuilding
+ * the owners' prefix sums from their log-weights, loads the ancestors' state from the owners' memory over
+ * NVLink, adds the roughening noise and writes this rank's new state.  Calls must be made by every rank
+ * the same number of times.  The N_eff gate (auvpf_set_neff_gate) works on the global sums.  When no shard
+ * has any finite weight (or the gate holds the resample back) the state is carried over unchanged;
+ * auvpf_shard_degenerate reports the former (that call synchronises).
+ * ancestors_out_dev: (M) int64 GLOBAL ancestor ids, device memory, or NULL. */
 #define AUVPF_IPC_BLOB_BYTES 256
 int auvpf_ipc_export(auvpf_handle *h, void *blob);
 int auvpf_ipc_import(auvpf_handle *h, const void *blobs, int32_t n_ranks, int32_t my_rank);
-int auvpf_shard_gather_p2p(auvpf_handle *h, double u, const int64_t *q_all_dev, const double *rough_var,
-                           const float *rough_noise, int64_t *ancestors_out_dev);
+int auvpf_peer_attach(auvpf_handle *h, auvpf_handle *const *handles, int32_t n_ranks, int32_t my_rank);
+int auvpf_shard_resample(auvpf_handle *h, double u, const double *rough_var, const float *rough_noise,
+                         int64_t *ancestors_out_dev);
 int auvpf_shard_degenerate(auvpf_handle *h, int32_t *flag);
-/* stage 4: emit the n_out = out_hi - out_lo offspring whose ancestors live in
- * this shard: global output slots [out_lo, out_hi) as 32-byte records
- * {double x, y; float z, roll, pitch, yaw} into `records` (device or host) and,
- * optionally, their GLOBAL ancestor ids.  q_offset = sum of Q of lower shards,
- * deficit = 2^52 - sum of all Q. */
-int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t deficit, int64_t out_lo,
+/* Staged path (no peer memory: any topology a collective library reaches).  The caller moves the scalars:
+ *   auvpf_shard_max_dev;  all-reduce MAX in place on wmax_i32 (ORDER-PRESERVING int32: an integer MAX is
+ *   the float max);  auvpf_shard_weights_dev;  all-gather of totals_u64 (6 uint64: A low, A high, the
+ *   three integer sums of the N_eff gate, log-weight buffer id) into (G, 6);  auvpf_shard_emit with the
+ *   gathered totals (host or device memory) emits the n_out = out_hi - out_lo offspring whose ancestors
+ *   live in this shard -- global output slots [out_lo, out_hi), as 32-byte records {double x, y; float z,
+ *   roll, pitch, yaw} and optionally their GLOBAL ancestor ids -- for an all-to-all with contiguous
+ *   splits;  auvpf_shard_load_roughen takes the M records this rank received.
+ * auvpf_shard_max / auvpf_shard_sum are the same two first stages with the scalars returned to the host
+ * (totals_out: 6 uint64). */
+int auvpf_shard_buffers(auvpf_handle *h, void **wmax_i32, void **totals_u64);
+int auvpf_shard_max_dev(auvpf_handle *h);
+int auvpf_shard_weights_dev(auvpf_handle *h);
+int auvpf_shard_max(auvpf_handle *h, float *m_out);
+int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *totals_out);
+int auvpf_shard_emit(auvpf_handle *h, double u, const uint64_t *totals_all, int32_t n_ranks, int32_t my_rank, int64_t out_lo,
                      int64_t out_hi, void *records, int64_t *ancestors_out);
 /* stage 5: replace the local state by M records received from the exchange */
 int auvpf_shard_load(auvpf_handle *h, const void *records, int64_t n);

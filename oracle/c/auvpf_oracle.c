@@ -261,7 +261,20 @@ static uint64_t a_from_logw(float lw, float m, int abits)
     return (uint64_t)floor(ldexp(p, s));
 }
 
-/* returns 0 ok, -1 degenerate.  qq: uint64[N] with sum == 2^52. */
+/* floor(C 2^52 / A) for C <= A < 2^90 in 128-bit arithmetic, by two 26-bit steps of long division:
+ * C 2^26 = q1 A + r1,  r1 2^26 = q2 A + r2  =>  floor(C 2^52 / A) = q1 2^26 + q2.
+ * (The device takes a float64 estimate and corrects it with a wrapping multiply-back instead,
+ * csrc/auvpf_math.cuh cdf_exact; the two formulations check each other.) */
+static uint64_t cdf_floor(unsigned __int128 C, unsigned __int128 A)
+{
+    unsigned __int128 t = C << 26;
+    unsigned __int128 q1 = t / A, r1 = t - q1 * A;
+    unsigned __int128 q2 = (r1 << 26) / A;
+    return (uint64_t)((q1 << 26) + q2);
+}
+
+/* returns 0 ok, -1 degenerate.  qq: uint64[N] with sum == 2^52: q_j = cdf_j - cdf_{j-1},
+ * cdf_j = floor(C_j 2^52 / A), C_j = sum_{i<=j} a_i (pf_oracle.quantise_a). */
 int orc_quantise_logw(const float *logw, long N, uint64_t *qq, float *m_out, uint64_t A_out[2])
 {
     float m = -INFINITY;
@@ -269,16 +282,24 @@ int orc_quantise_logw(const float *logw, long N, uint64_t *qq, float *m_out, uin
     if (!isfinite(m)) return -1;
     unsigned __int128 A = 0;
     for (long i = 0; i < N; ++i) { qq[i] = a_from_logw(logw[i], m, A_BITS); A += qq[i]; }
-    uint64_t Q = 0;
+    if (A == 0) return -1;
+    unsigned __int128 C = 0;
+    uint64_t prev = 0;
     for (long i = 0; i < N; ++i) {
-        unsigned __int128 t = (unsigned __int128)qq[i] << 52;
-        qq[i] = (uint64_t)(t / A);
-        Q += qq[i];
+        C += qq[i];
+        uint64_t c = cdf_floor(C, A);
+        qq[i] = c - prev;
+        prev = c;
     }
-    uint64_t D = ((uint64_t)1 << 52) - Q;
-    for (uint64_t i = 0; i < D; ++i) qq[i] += 1;
     if (m_out) *m_out = m;
     if (A_out) { A_out[0] = (uint64_t)A; A_out[1] = (uint64_t)(A >> 64); }
+    return 0;
+}
+
+/* the integer weights a_i themselves (for the gate sums and for sharded-total checks) */
+int orc_integer_weights(const float *logw, long N, float m, uint64_t *a)
+{
+    for (long i = 0; i < N; ++i) a[i] = a_from_logw(logw[i], m, A_BITS);
     return 0;
 }
 

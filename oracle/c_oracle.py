@@ -107,6 +107,16 @@ def quantise_logw(logw32):
     return qq, np.float32(m.value), int(A[0]) | (int(A[1]) << 64)
 
 
+def integer_weights(logw32, m):
+    """a_i = floor(exp(logw_i - m) 2^60) for a GIVEN maximum m (a shard of a sharded filter)."""
+    L = lib()
+    lw = np.ascontiguousarray(logw32, np.float32)
+    a = np.empty(lw.shape[0], np.uint64)
+    L.orc_integer_weights(lw.ctypes.data_as(C.c_void_p), C.c_long(lw.shape[0]), C.c_float(float(m)),
+                          a.ctypes.data_as(C.c_void_p))
+    return a
+
+
 def systematic(w, u):
     L = lib()
     w = np.ascontiguousarray(w, np.float64)

@@ -213,7 +213,7 @@ A_BITS = 60      # a_i = floor(exp(logw_i - max) * 2^60); A = sum a_i is kept ex
 
 def quantise_logw(logw32):
     """fp32 log-weights -> integer weights ``qq`` (uint64) with sum == 2^52.
-    Returns ``(qq, m, a, A)``; raises FloatingPointError when degenerate."""
+    Returns ``(qq, a, A, m)``; raises FloatingPointError when degenerate."""
     lw = np.asarray(logw32, np.float32)
     M = lw.shape[0]
     finite = lw[~np.isnan(lw)]
@@ -246,20 +246,19 @@ def quantise_linear(w):
 
 
 def quantise_a(a):
-    """Integer stage: ``q_i = floor(a_i 2^52 / A)`` (128-bit), deficit
-    ``D = 2^52 - sum q`` in [0, M) spread one unit each over the first D
-    particles.  Returns ``(qq, a, A)``.  Python-int division: fine for the
-    N <= ~1M the tests use; larger N go through ``c/auvpf_oracle.c``."""
-    A = _sum_u64(a)
-    q = np.empty(a.shape[0], np.uint64)
-    ao = a.astype(object)
-    for s in range(0, a.shape[0], 1 << 16):
-        q[s:s + (1 << 16)] = np.array([(int(v) << Q_BITS) // A for v in ao[s:s + (1 << 16)]],
-                                      dtype=np.uint64)
-    D = (1 << Q_BITS) - _sum_u64(q)
-    assert 0 <= D < a.shape[0] or (a.shape[0] == 1 and D == 0)
-    qq = q.copy()
-    qq[:D] += np.uint64(1)
+    """Integer stage: the CDF as a quotient of PREFIX SUMS, ``cdf_j = floor(C_j 2^52 / A)`` with
+    ``C_j = sum_{i<=j} a_i`` and ``A = C_{N-1}``; ``q_j = cdf_j - cdf_{j-1}``.  ``cdf_{N-1} = 2^52``
+    exactly, so the weights ``q 2^-52`` sum to exactly 1 and ``np.cumsum`` of them is ``cdf 2^-52`` bit for
+    bit in any summation order.  Returns ``(qq, a, A)``.  Python-int arithmetic: fine for the N <= ~1M the
+    tests use; larger N go through ``c/auvpf_oracle.c``."""
+    a = np.asarray(a, np.uint64)
+    C = np.cumsum(a.astype(object))
+    A = int(C[-1])
+    if A == 0:
+        raise FloatingPointError("degenerate weights")
+    cdf = np.array([(int(c) << Q_BITS) // A for c in C], dtype=np.uint64)
+    qq = np.diff(cdf, prepend=np.uint64(0))
+    assert int(cdf[-1]) == 1 << Q_BITS
     return qq, a, A
 
 
@@ -282,26 +281,31 @@ def neff(weights):
     return 1.0 / np.sum(np.square(w))
 
 
-def neff_fixed_raw(q_raw):
-    """The integer-exact N_eff the library's gate compares (include/auvpf.h,
-    ``auvpf_set_neff_gate``; csrc/auvpf_math.cuh ``neff_fixed``), defined on the RAW quotients
-    ``q_i = floor(a_i 2^52 / A)`` (before the deficit units): ``s_i = min(q_i >> 20, 2^32 - 1)``,
-    ``S = sum s_i^2`` kept as two limb sums (low 32 bits, high bits) and
-    ``2^64 / (float(S_hi) * 2^32 + float(S_lo))`` in float64."""
-    q = np.asarray(q_raw, np.uint64)
-    s = np.minimum(q >> np.uint64(20), np.uint64(0xFFFFFFFF))
-    s2 = s * s                                            # < 2^64, no wrap
+NEFF_SHIFT = 29
+
+
+def neff_sums(a):
+    """The exact integer sums of the library's N_eff gate over the 60-bit integer weights ``a``:
+    ``s_i = a_i >> 29`` (<= 2^31), ``S1 = sum s_i``, ``S2 = sum s_i^2`` as two limb sums (low 32 bits, high
+    bits).  Sums of integers: independent of the order and of the sharding."""
+    s = np.asarray(a, np.uint64) >> np.uint64(NEFF_SHIFT)
+    s2 = s * s                                            # <= 2^62, no wrap
+    S1 = int(s.sum(dtype=np.uint64))
     lo = int((s2 & np.uint64(0xFFFFFFFF)).sum(dtype=np.uint64))
     hi = int((s2 >> np.uint64(32)).sum(dtype=np.uint64))
-    S = np.float64(hi) * np.float64(4294967296.0) + np.float64(lo)
-    return float(np.float64(18446744073709551616.0) / S) if S > 0 else 0.0
+    return S1, lo, hi
 
 
-def raw_quotients(a):
-    """``floor(a_i 2^52 / A)`` without the deficit units (what the scan kernel sums)."""
-    A = _sum_u64(a)
-    ao = np.asarray(a, np.uint64).astype(object)
-    return np.array([(int(v) << Q_BITS) // A for v in ao], dtype=np.uint64)
+def neff_fixed_from_sums(S1, S2_lo, S2_hi):
+    """``float(S1)^2 / (float(S2_hi) 2^32 + float(S2_lo))`` in float64 (csrc/auvpf_math.cuh ``neff_fixed_a``;
+    include/auvpf.h ``auvpf_set_neff_gate``): ``(sum w)^2 / sum w^2`` of the integer weights."""
+    S2 = np.float64(S2_hi) * np.float64(4294967296.0) + np.float64(S2_lo)
+    s1 = np.float64(S1)
+    return float(s1 * s1 / S2) if S2 > 0 else 0.0
+
+
+def neff_fixed_a(a):
+    return neff_fixed_from_sums(*neff_sums(a))
 
 
 def resample_gate(a, ratio):
@@ -309,7 +313,7 @@ def resample_gate(a, ratio):
     ``quantise_logw`` / ``quantise_linear``.  ratio == 0: always resample (the live reference code)."""
     if not ratio > 0.0:
         return True
-    return neff_fixed_raw(raw_quotients(a)) < ratio * float(len(a))
+    return neff_fixed_a(a) < ratio * float(len(a))
 
 
 # --------------------------------------------------------------------------- resamplers
@@ -469,6 +473,27 @@ def estimate(poses):
     out = ave.copy()
     out[5] = yaw
     return out, cov, quat
+
+
+def estimate_options(poses, logw=None, circular_yaw=False, full_cov=False):
+    """``estimate`` with the options of ``auvpf_estimate`` (include/auvpf.h; no reference counterpart beyond
+    the unweighted form): weights ``exp(logw - max)`` normalised, circular yaw mean
+    ``atan2(sum w sin yaw, sum w cos yaw)``, all nine covariance entries."""
+    P = np.array(poses, dtype=np.float64, copy=True)
+    if logw is None:
+        w = np.full(P.shape[0], 1.0 / P.shape[0])
+    else:
+        lw = np.asarray(logw, np.float64)
+        w = np.where(np.isnan(lw), 0.0, np.exp(lw - np.nanmax(lw)))
+        w = w / w.sum()
+    ave = (w[:, None] * P).sum(0)
+    yw = (P[:, 5] + np.pi) % (2 * np.pi) - np.pi
+    ave[5] = np.arctan2((w * np.sin(yw)).sum(), (w * np.cos(yw)).sum()) if circular_yaw else (w * yw).sum()
+    dx = P[:, 0:3] - ave[0:3]
+    cov = (w[:, None, None] * dx[:, :, None] * dx[:, None, :]).sum(0)
+    if not full_cov:
+        cov[2, 0] = cov[2, 1] = 0.0
+    return ave, cov
 
 
 def covariance36(cov):

@@ -14,6 +14,7 @@ OK, ERR_BADARG, ERR_CUDA, ERR_STATE, ERR_DEGENERATE, ERR_NOMEM = 0, -1, -2, -3, 
 SYSTEMATIC, RESIDUAL = 0, 1
 RS_SORTED, RS_INPLACE_REF, RS_STRICT_REF, RS_ASYNC = 0, 1, 2, 4
 IPC_BLOB_BYTES = 256
+EST_REFERENCE, EST_WEIGHTED, EST_CIRCULAR_YAW, EST_FULL_COV = 0, 1, 2, 4
 K_NAMES = ("propagate", "update_mbes", "update_gps", "normalise", "scan", "select_gather", "roughen",
            "estimate", "other")
 
@@ -67,24 +68,27 @@ SYMBOLS = [
     ("auvpf_apply_indices", C.c_int, [_vp, _vp, _i32]),
     ("auvpf_roughen", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_mean_cov", C.c_int, [_vp, _vp, _vp]),
+    ("auvpf_estimate", C.c_int, [_vp, _i32, _vp, _vp]),
+    ("auvpf_pose_array", C.c_int, [_vp, _i64, _i64, _vp, C.POINTER(_i64)]),
+    ("auvpf_pose_sums_buffer", C.c_int, [_vp, C.POINTER(_vp)]),
+    ("auvpf_pose_sums_dev", C.c_int, [_vp]),
     ("auvpf_resample_status", C.c_int, [_vp, _vp]),
     ("auvpf_neff", C.c_int, [_vp, _vp]),
     ("auvpf_set_neff_gate", C.c_int, [_vp, _dbl]),
     ("auvpf_neff_fixed", C.c_int, [_vp, _vp]),
     ("auvpf_resample_skipped", C.c_int, [_vp, _vp]),
     ("auvpf_replay", C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
-    ("auvpf_shard_max", C.c_int, [_vp, _vp]),
-    ("auvpf_shard_sum", C.c_int, [_vp, _vp, _vp]),
-    ("auvpf_shard_scan", C.c_int, [_vp, _vp, _vp, _vp]),
-    ("auvpf_shard_buffers", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
-    ("auvpf_shard_max_dev", C.c_int, [_vp]),
-    ("auvpf_shard_sum_dev", C.c_int, [_vp]),
-    ("auvpf_shard_scan_dev", C.c_int, [_vp]),
     ("auvpf_ipc_export", C.c_int, [_vp, _vp]),
     ("auvpf_ipc_import", C.c_int, [_vp, _vp, _i32, _i32]),
-    ("auvpf_shard_gather_p2p", C.c_int, [_vp, _dbl, _vp, _vp, _vp, _vp]),
+    ("auvpf_peer_attach", C.c_int, [_vp, C.POINTER(_vp), _i32, _i32]),
+    ("auvpf_shard_resample", C.c_int, [_vp, _dbl, _vp, _vp, _vp]),
     ("auvpf_shard_degenerate", C.c_int, [_vp, C.POINTER(_i32)]),
-    ("auvpf_shard_emit", C.c_int, [_vp, _dbl, _u64, _u64, _i64, _i64, _vp, _vp]),
+    ("auvpf_shard_buffers", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    ("auvpf_shard_max_dev", C.c_int, [_vp]),
+    ("auvpf_shard_weights_dev", C.c_int, [_vp]),
+    ("auvpf_shard_max", C.c_int, [_vp, _vp]),
+    ("auvpf_shard_sum", C.c_int, [_vp, _vp, _vp]),
+    ("auvpf_shard_emit", C.c_int, [_vp, _dbl, _vp, _i32, _i32, _i64, _i64, _vp, _vp]),
     ("auvpf_shard_load", C.c_int, [_vp, _vp, _i64]),
     ("auvpf_shard_load_roughen", C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     ("auvpf_profile_enable", C.c_int, [_vp, _i32]),

@@ -16,6 +16,7 @@
 
 #include "../../include/auvpf.h"
 #include "auvpf_kernels.cuh"
+#include "auvpf_resample.cuh"
 
 using namespace auvpf;
 
@@ -49,6 +50,10 @@ struct DevBuf {
 
 enum Slot { S_IN0 = 0, S_IN1, S_IN2, S_IN3, S_OUT0, S_OUT1, S_COUNT };
 
+// parts of the slab: st[0].{x,y,z,roll,pitch,yaw}, st[1].{...}, logw[0], logw[1], cdf, status, tile_prefix, chunk_sum, mailbox
+enum { P_ST0 = 0, P_ST1 = 6, P_LOGW0 = 12, P_LOGW1 = 13, P_CDF = 14, P_STATUS = 15, P_TILE = 16, P_CHUNK = 17, P_MBOX = 18 };
+constexpr int kSlabParts = 19;
+
 struct ProfEvent {
     cudaEvent_t a, b;
     int klass;
@@ -64,34 +69,47 @@ struct auvpf_handle {
     int F = 1;
     int64_t global_offset = 0, global_count = 0;
 
-    // state (double-buffered SoA), integer CDF and scan tile table live in ONE allocation (the
-    // slab) so that a single CUDA IPC handle exposes them to the other ranks of a sharded filter
+    // state (double-buffered SoA), the two log-weight buffers, the resampler's chunk / tile tables and the
+    // mailbox live in ONE allocation (the slab) so that a single CUDA IPC handle exposes them to the other
+    // ranks of a sharded filter
     void *slab = nullptr;
     size_t slab_bytes = 0;
-    int64_t slab_off[14] = {0};            // st[0].{x,y,z,roll,pitch,yaw}, st[1].{...}, cdf, status
-    void *peer_slab[8] = {nullptr};        // peers' slabs opened through IPC ([rank] == own slab)
+    int64_t slab_off[kSlabParts] = {0};    // see alloc_slab
+    void *peer_slab[8] = {nullptr};        // peers' slabs: opened through IPC, or in-process handles' ([rank] == own slab)
+    bool peer_ipc[8] = {false};            // opened with cudaIpcOpenMemHandle (to be closed)
     int n_peers = 0, my_peer = 0;
-    unsigned long long *shard_meta = nullptr;   // [n_peers + 2]: per-shard CDF offsets, deficit, degenerate flag
-    PeerTable *peer_tables = nullptr;           // [2] device: peers' pointers with buffer 0 / 1 as the gather source
+    SelShard *peer_shards = nullptr;            // [n_peers] device: what the select kernel reads of every shard
+    MailboxView mbox{};                         // peers' mailboxes (G = 1 until peers are attached)
+    unsigned long long *mailbox = nullptr;      // this rank's mailbox (inside the slab)
+    unsigned int epoch = 0;                     // resamples of the sharded filter so far
+    int *shard_degenerate = nullptr;            // [1] device: no shard had any finite weight (written by k_select)
+    unsigned long long *shard_totals = nullptr; // [6] device: A lo, A hi, S1, S2 lo, S2 hi, log-weight buffer (staged variant)
+    U128 *c_off = nullptr;                      // [kMaxPeers + 1] device: mass below every shard, [G] = the global total
+    bool have_global = false;                   // c_off describes the last sharded resample
+    int n_ranks_global = 1, my_rank_global = 0;
     StateView st[2];
     int cur = 0;
-    float *logw = nullptr;
-    unsigned long long *cdf = nullptr;
+    float *logw_buf[2] = {nullptr, nullptr};    // a shard's update writes the buffer its peers are not reading
+    int lw = 0;                                 // the current log-weight buffer
+    float *logw = nullptr;                      // == logw_buf[lw]
+    unsigned long long *cdf = nullptr;          // [N] scratch: the weights q_j (residual resampler), flag scans (slot map)
+    U128 *tile_prefix = nullptr, *chunk_sum = nullptr;
 
     // per-filter scalars
     long long *wmax_ordered = nullptr;
     int *wmax_f32 = nullptr;      // [F] max log-weight published by the update kernels (ordered int)
     bool wmax_valid = false;      // wmax_f32 describes the current logw
-    unsigned int *done = nullptr; // [F] ticket counters of k_normalise
+    unsigned int *done = nullptr; // [F] ticket counters of k_weights
     double *wmax = nullptr;
-    unsigned long long *limbs = nullptr, *A = nullptr, *Q = nullptr, *deficit = nullptr;
+    U128 *A = nullptr;
+    unsigned long long *deficit = nullptr;     // [F] zero: kept for the residual kernels' q_i + (i < D) form
     double *u = nullptr, *sumsq = nullptr, *sums = nullptr, *gps = nullptr;
     PredictParams *pparams = nullptr;
     int *degenerate = nullptr;
-    unsigned long long *sqlimbs = nullptr;   // [2F] exact integer sum of squared weights (N_eff gate)
+    unsigned long long *neff_acc = nullptr, *neff_pub = nullptr;   // [3F] integer sums of the N_eff gate (S1, S2 lo, S2 hi)
     int *skipped = nullptr;                  // [F] 1 = the N_eff gate held the last resample back
     double neff_ratio = 0.0;                 // resample only when N_eff < neff_ratio * N; 0 = always
-    bool sumsq_lazy = false;                 // the last scan was the fused one: sumsq is computed on request
+    bool sumsq_lazy = false;                 // sumsq is computed on request
     DevBuf replay_params, replay_ranges, replay_u, replay_stats;   // auvpf_replay: a whole recorded sequence
 
     // scan machinery
@@ -355,94 +373,73 @@ StateView state_at(void *slab, const int64_t *off)
 
 int alloc_slab(auvpf_handle *h)
 {
-    const size_t n = (size_t)h->N;
-    const size_t sizes[14] = {8 * n, 8 * n, 4 * n, 4 * n, 4 * n, 4 * n, 8 * n, 8 * n, 4 * n, 4 * n, 4 * n, 4 * n,
-                              8 * n, 8 * (size_t)h->tiles_per_filter * h->F};
+    const size_t n = (size_t)h->N, tiles = (size_t)h->tiles_per_filter * h->F;
+    size_t sizes[kSlabParts];
+    for (int b = 0; b < 2; ++b) {
+        sizes[P_ST0 + 6 * b + 0] = sizes[P_ST0 + 6 * b + 1] = 8 * n;
+        for (int c = 2; c < 6; ++c) sizes[P_ST0 + 6 * b + c] = 4 * n;
+    }
+    sizes[P_LOGW0] = sizes[P_LOGW1] = 4 * n;
+    sizes[P_CDF] = 8 * n;
+    sizes[P_STATUS] = 8 * tiles;
+    sizes[P_TILE] = sizeof(U128) * tiles;
+    sizes[P_CHUNK] = sizeof(U128) * tiles * kChunksPerTile;
+    sizes[P_MBOX] = kMboxBytes;
     size_t off = 0;
-    for (int k = 0; k < 14; ++k) {
+    for (int k = 0; k < kSlabParts; ++k) {
         h->slab_off[k] = (int64_t)off;
         off += (sizes[k] + 255) & ~size_t(255);
     }
     h->slab_bytes = off;
     CU(cudaMalloc(&h->slab, off));
-    h->st[0] = state_at(h->slab, h->slab_off);
-    h->st[1] = state_at(h->slab, h->slab_off + 6);
-    h->cdf = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->slab) + h->slab_off[12]);
-    h->status = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->slab) + h->slab_off[13]);
+    char *base = static_cast<char *>(h->slab);
+    h->st[0] = state_at(h->slab, h->slab_off + P_ST0);
+    h->st[1] = state_at(h->slab, h->slab_off + P_ST1);
+    h->logw_buf[0] = reinterpret_cast<float *>(base + h->slab_off[P_LOGW0]);
+    h->logw_buf[1] = reinterpret_cast<float *>(base + h->slab_off[P_LOGW1]);
+    h->logw = h->logw_buf[h->lw];
+    h->cdf = reinterpret_cast<unsigned long long *>(base + h->slab_off[P_CDF]);
+    h->status = reinterpret_cast<unsigned long long *>(base + h->slab_off[P_STATUS]);
+    h->tile_prefix = reinterpret_cast<U128 *>(base + h->slab_off[P_TILE]);
+    h->chunk_sum = reinterpret_cast<U128 *>(base + h->slab_off[P_CHUNK]);
+    h->mailbox = reinterpret_cast<unsigned long long *>(base + h->slab_off[P_MBOX]);
+    CU(cudaMemsetAsync(h->mailbox, 0, kMboxBytes, h->stream));
+    h->mbox.G = 1;
+    h->mbox.rank = 0;
+    h->mbox.epoch = 0;
+    h->mbox.peer[0] = h->mailbox;
     return AUVPF_OK;
 }
 
-__global__ void k_reset_scalars(long long *wmax_ordered, unsigned long long *limbs, double *sumsq,
-                                unsigned int *tile_counter, int F)
+// what the select kernel reads of a shard whose slab is mapped at `base` with the part offsets `off`
+SelShard shard_at(void *base, const int64_t *off)
 {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f == 0) *tile_counter = 0;
-    if (f >= F) return;
-    wmax_ordered[f] = double_to_ordered(-INFINITY);
-    limbs[2 * f] = 0;
-    limbs[2 * f + 1] = 0;
-    sumsq[f] = 0.0;
+    char *c = static_cast<char *>(base);
+    SelShard s{};
+    s.logw[0] = reinterpret_cast<const float *>(c + off[P_LOGW0]);
+    s.logw[1] = reinterpret_cast<const float *>(c + off[P_LOGW1]);
+    s.lin = nullptr;
+    s.tile_prefix = reinterpret_cast<const U128 *>(c + off[P_TILE]);
+    s.chunk_sum = reinterpret_cast<const U128 *>(c + off[P_CHUNK]);
+    s.st[0] = state_at(base, off + P_ST0);
+    s.st[1] = state_at(base, off + P_ST1);
+    return s;
 }
 
-// ordered max -> double, and the degenerate flag (no finite / positive weight)
-__global__ void k_finish_max(const long long *wmax_ordered, double *wmax, int *degenerate, int kind, int F)
+// A producer of log-weights (update, set_logw) of a SHARDED filter writes the buffer its peers are not
+// reading: a fast rank may already be in its next update while a slow one still rebuilds prefix sums from
+// this rank's previous log-weights (k_select reads them over NVLink).  The buffer alternates per producer
+// call; the one a resample used is named in the mailbox.  One GPU: a single buffer.
+void flip_logw(auvpf_handle *h)
 {
-    int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    double m = ordered_to_double(wmax_ordered[f]);
-    wmax[f] = m;
-    bool bad = !isfinite(m) || (kind == 1 && !(m > 0.0));
-    degenerate[f] = bad ? 1 : 0;
-}
-
-// ---- normalisation + scan on the handle's stream ---------------------------------------------
-int run_max(auvpf_handle *h, const WeightSrc &src)
-{
-    Prof pr(h, AUVPF_K_NORMALISE);
-    k_reset_scalars<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->wmax_ordered, h->limbs, h->sumsq, h->tile_counter,
-                                                               h->F);
-    int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
-    k_weight_max<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax_ordered);
-    k_finish_max<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->wmax_ordered, h->wmax, h->degenerate, src.kind, h->F);
-    LAUNCHED(h, AUVPF_K_NORMALISE, 3);
-    CU(cudaGetLastError());
-    return AUVPF_OK;
-}
-
-int run_sum(auvpf_handle *h, const WeightSrc &src)
-{
-    Prof pr(h, AUVPF_K_NORMALISE);
-    int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
-    k_weight_sum<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->limbs);
-    LAUNCHED(h, AUVPF_K_NORMALISE, 1);
-    CU(cudaGetLastError());
-    return AUVPF_OK;
-}
-
-// fused = the status words and the tile counter were cleared by k_normalise, the scan writes the
-// deficit itself and skips degenerate filters (single-GPU path); otherwise (sharded path) the
-// caller supplies max / A and reads Q back.
-int run_scan(auvpf_handle *h, const WeightSrc &src, bool fused = false)
-{
-    Prof pr(h, AUVPF_K_SCAN);
-    if (!fused) {
-        CU(cudaMemsetAsync(h->status, 0, sizeof(unsigned long long) * (size_t)h->tiles_per_filter * h->F, h->stream));
-        CU(cudaMemsetAsync(h->tile_counter, 0, sizeof(unsigned int), h->stream));
+    if (h->n_peers > 1 || h->global_count != h->M) {
+        h->lw ^= 1;
+        h->logw = h->logw_buf[h->lw];
     }
-    if (fused)      // a_i were left in h->cdf by k_normalise; they become the raw quotients, the status words the tile table
-        k_quotients<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
-            h->M, h->A, h->cdf, h->status, h->done, h->tiles_per_filter, h->Q, h->deficit, h->degenerate, h->sqlimbs);
-    else
-        k_scan_q<<<h->tiles_per_filter * h->F, kThreads, 0, h->stream>>>(
-            src, h->M, h->wmax, h->A, h->cdf, h->status, h->tile_counter, h->tiles_per_filter, h->Q, h->sumsq,
-            nullptr, nullptr);
-    h->sumsq_lazy = fused;
-    LAUNCHED(h, AUVPF_K_SCAN, 1);
-    CU(cudaGetLastError());
-    return AUVPF_OK;
 }
 
-// Single-GPU normalisation: max (from the update kernel when it is current) + exact sum + A.
+// ---- normalisation on the handle's stream -----------------------------------------------------
+// float32 log-weights that did not come from an update kernel (auvpf_set_logw): max pass
 int ensure_wmax_f32(auvpf_handle *h)
 {
     if (h->wmax_valid) return AUVPF_OK;
@@ -456,36 +453,88 @@ int ensure_wmax_f32(auvpf_handle *h)
     return AUVPF_OK;
 }
 
-int run_normalise(auvpf_handle *h, const WeightSrc &src, bool finalise = true)
+// k_weights: a_i, chunk / tile sums, tile prefix, total, gate sums.  use_mailbox: a sharded filter whose
+// peers are attached exchanges the maximum (and afterwards its totals) through the mailbox inside the
+// kernel; otherwise the maximum in wmax_f32 is taken as it is (local, or already reduced by the caller).
+int run_weights(auvpf_handle *h, const WeightSrc &src, bool use_mailbox)
 {
     int rc;
-    NormState ns{};
+    WeightState ws{};
     if (src.kind == 0) {
         if ((rc = ensure_wmax_f32(h))) return rc;
-        ns.wmax_f32 = h->wmax_f32;
-    } else {
-        if ((rc = run_max(h, src))) return rc;      // float64 linear weights: separate max pass
-        ns.wmax_f32 = nullptr;
+        ws.wmax_f32 = h->wmax_f32;
+    } else {        // float64 linear weights: separate max pass
+        Prof pr(h, AUVPF_K_NORMALISE);
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
+        k_weight_max_lin<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src.lin, h->M, h->wmax_ordered);
+        k_finish_max_lin<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->wmax_ordered, h->wmax, h->F);
+        LAUNCHED(h, AUVPF_K_NORMALISE, 2);
+        ws.wmax_f32 = nullptr;
     }
-    ns.wmax = h->wmax;
-    ns.limbs = h->limbs;
-    ns.done = h->done;
-    ns.A = h->A;
-    ns.degenerate = h->degenerate;
-    ns.sumsq = h->sumsq;
-    ns.sqlimbs = h->sqlimbs;
-    ns.status = h->status;
-    ns.tile_counter = h->tile_counter;
-    ns.tiles_total = (long long)h->tiles_per_filter * h->F;
-    ns.a_out = h->cdf;
-    ns.finalise = finalise ? 1 : 0;
+    ws.wmax = h->wmax;
+    ws.done = h->done;
+    ws.neff_acc = h->neff_acc;
+    ws.neff_pub = h->neff_pub;
+    ws.A = h->A;
+    ws.degenerate = h->degenerate;
+    ws.tile_prefix = h->tile_prefix;
+    ws.chunk_sum = h->chunk_sum;
+    ws.tiles = h->tiles_per_filter;
+    ws.logw_parity = h->lw;
+    MailboxView mb = h->mbox;
+    if (!use_mailbox) mb.G = 1;
+    mb.epoch = h->epoch;
     Prof pr(h, AUVPF_K_NORMALISE);
-    int blocks = (int)std::min<int64_t>((h->M + kThreads * 4 - 1) / (kThreads * 4), 740);   // one wave: 148 SMs x 5
-    if (blocks < 1) blocks = 1;
-    k_normalise<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, ns);
+    k_weights<<<dim3((unsigned)h->tiles_per_filter, (unsigned)h->F), kThreads, 0, h->stream>>>(src, h->M, ws, mb);
     LAUNCHED(h, AUVPF_K_NORMALISE, 1);
     CU(cudaGetLastError());
+    h->have_norm = true;
+    h->last_src_kind = src.kind;
+    h->lin_weights = src.lin;
+    h->sumsq_lazy = true;
     return AUVPF_OK;
+}
+
+// the weights q_j = cdf_j - cdf_{j-1} of the last k_weights into `q_out` (and / or their sum of squares)
+int run_exact_q(auvpf_handle *h, unsigned long long *q_out, double *sumsq, const U128 *A, const U128 *c_off)
+{
+    WeightSrc src{h->logw, h->lin_weights, h->last_src_kind};
+    if (sumsq) CU(cudaMemsetAsync(sumsq, 0, sizeof(double) * h->F, h->stream));
+    k_exact_q<<<dim3((unsigned)h->tiles_per_filter, (unsigned)h->F), kThreads, 0, h->stream>>>(
+        src, h->M, h->wmax, h->tile_prefix, A, c_off, h->tiles_per_filter, h->degenerate, q_out, sumsq);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+
+SelArgs select_args(auvpf_handle *h, const WeightSrc &src)
+{
+    SelArgs a{};
+    a.M = h->M;
+    a.n_global = h->global_count;
+    a.out_lo = h->global_offset;
+    a.n_out = h->M;
+    a.tiles = h->tiles_per_filter;
+    a.G = 1;
+    a.rank = 0;
+    a.kind = src.kind;
+    a.cur = h->cur;
+    a.logw_parity = h->lw;
+    a.local = shard_at(h->slab, h->slab_off);
+    a.local.lin = src.lin;
+    a.peers = nullptr;
+    a.A = h->A;
+    a.c_off = nullptr;
+    a.wmax = h->wmax;
+    a.u = h->u;
+    a.degenerate = h->degenerate;
+    a.neff_pub = h->neff_pub;
+    a.gate_thresh = h->neff_ratio * (double)h->global_count;
+    a.skipped = h->skipped;
+    a.degenerate_out = h->shard_degenerate;
+    a.mb = h->mbox;
+    a.mb.epoch = h->epoch;
+    return a;
 }
 
 int check_degenerate(auvpf_handle *h)
@@ -553,10 +602,10 @@ int host_neff_gate(auvpf_handle *h, bool *skip)
         CU(cudaMemsetAsync(h->skipped, 0, sizeof(int) * h->F, h->stream));
         return AUVPF_OK;
     }
-    unsigned long long S[2];
-    CU(cudaMemcpyAsync(S, h->sqlimbs, sizeof(S), cudaMemcpyDeviceToHost, h->stream));
+    unsigned long long S[3];
+    CU(cudaMemcpyAsync(S, h->neff_pub, sizeof(S), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    *skip = neff_fixed(S[0], S[1]) >= h->neff_ratio * (double)h->M;
+    *skip = neff_fixed_a(S[0], S[1], S[2]) >= h->neff_ratio * (double)h->M;
     const int flag = *skip ? 1 : 0;
     return tiny_upload(h, h->skipped, &flag, sizeof(int));
 }
@@ -587,16 +636,17 @@ int do_resample_residual(auvpf_handle *h, const WeightSrc &src, int32_t flags, c
     if (h->neff_ratio > 0.0 && h->F > 1)
         return fail(AUVPF_ERR_BADARG, "the N_eff gate with residual resampling needs one filter per handle");
     int rc;
-    if ((rc = run_normalise(h, src))) return rc;
-    if ((rc = run_scan(h, src, /*fused=*/true))) return rc;
-    h->have_norm = true;
-    h->last_src_kind = src.kind;
-    h->lin_weights = src.lin;
+    if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
     if ((rc = check_degenerate(h))) return rc;
     {
         bool skip;
         if ((rc = host_neff_gate(h, &skip))) return rc;
         if (skip) return emit_identity_ancestors(h, ancestors_out);     // state, weights and RNG counters untouched
+    }
+    // the weights themselves, q_j = cdf_j - cdf_{j-1} (sum exactly 2^52: no deficit units to hand out)
+    {
+        Prof pr(h, AUVPF_K_SCAN);
+        if ((rc = run_exact_q(h, h->cdf, nullptr, h->A, nullptr))) return rc;
     }
     if ((rc = ensure_inplace_buffers(h))) return rc;
     if (!h->scan3) CU(cudaMalloc(&h->scan3, sizeof(unsigned long long) * h->N));
@@ -664,14 +714,10 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     if (mode != AUVPF_SYSTEMATIC) return fail(AUVPF_ERR_BADARG, "unknown resample mode %d", mode);
     if (h->neff_ratio > 0.0 && h->F > 1 && (flags & AUVPF_RS_INPLACE_REF))
         return fail(AUVPF_ERR_BADARG, "the N_eff gate with AUVPF_RS_INPLACE_REF needs one filter per handle");
-    if (h->neff_ratio > 0.0 && h->global_count != h->M)
-        return fail(AUVPF_ERR_BADARG, "the N_eff gate is not available for a particle-sharded filter");
+    if (h->global_count != h->M)
+        return fail(AUVPF_ERR_BADARG, "a particle-sharded filter resamples through auvpf_shard_resample / the staged auvpf_shard_* calls");
     int rc;
-    if ((rc = run_normalise(h, src))) return rc;
-    if ((rc = run_scan(h, src, /*fused=*/true))) return rc;
-    h->have_norm = true;
-    h->last_src_kind = src.kind;
-    h->lin_weights = src.lin;
+    if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
 
     // uniforms: resampling.py:157 random()
     std::vector<double> uh(h->F);
@@ -688,32 +734,25 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     const bool inplace = (flags & AUVPF_RS_INPLACE_REF) != 0;
     const float *rn = nullptr;
     if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
-    NoiseParams rough = make_noise(h, rough_var, nullptr, (rough_var && !inplace) ? 1 : 0, h->step_rough, kStreamRoughen);
     int32_t *anc_dev = nullptr;
     if (ancestors_out || inplace) {
         if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
         anc_dev = h->anc;
         if (ancestors_out && is_device_ptr(ancestors_out) && !inplace) anc_dev = ancestors_out;
     }
-    SelectParams sp;
-    sp.M = h->M;
-    sp.n_global = h->M;
-    sp.j_global0 = 0;
-    sp.out_lo = 0;
-    sp.n_out = h->M;
-    sp.q_offset = 0;
-    sp.tiles_per_filter = h->tiles_per_filter;
+    SelArgs sa = select_args(h, src);
+    sa.rough = make_noise(h, rough_var, nullptr, (rough_var && !inplace) ? 1 : 0, h->step_rough, kStreamRoughen);
+    sa.rough_noise = rn;
+    sa.anc32 = anc_dev;
+    sa.dst = h->st[1 - h->cur];
+    if (inplace) sa.dst.x = nullptr;   // ancestors only
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
-        StateView dst = h->st[1 - h->cur];
-        if (inplace) dst.x = nullptr;   // ancestors only
-        k_select_gather<false><<<grid1(h->M, kSelTile, h->F), kSelThreads, 0, h->stream>>>(
-            h->cdf, sp, h->u, h->deficit, h->st[h->cur], dst, nullptr, anc_dev, nullptr, rough, rn, h->status,
-            h->degenerate, NeffGate{h->sqlimbs, h->neff_ratio * (double)h->M, h->skipped});
+        k_select<kSelLocal><<<grid1(h->M, kSelTile, h->F), kSelThreads, 0, h->stream>>>(sa);
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
-    // A filter without any finite weight made the kernels above carry its state over unchanged, so the
+    // A filter without any finite weight made the kernel above carry its state over unchanged, so the
     // buffers flip either way; the flag is read back (one 4-byte copy at the END of the enqueued cycle,
     // the only host synchronisation of a resample) unless the caller asked not to wait.
     if (!inplace) {
@@ -758,6 +797,8 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         return fail(AUVPF_ERR_BADARG, "auvpf_config.struct_size %d != %zu", cfg->struct_size, sizeof(auvpf_config));
     if (cfg->particle_count <= 0 || cfg->particle_count > (1ll << 30))
         return fail(AUVPF_ERR_BADARG, "particle_count %lld out of range", (long long)cfg->particle_count);
+    if (cfg->global_count < 0 || cfg->global_count > (1ll << 30))
+        return fail(AUVPF_ERR_BADARG, "global_count %lld out of range (a filter holds at most 2^30 particles over all shards)", (long long)cfg->global_count);
     const int F = cfg->n_filters <= 0 ? 1 : cfg->n_filters;
     if (!(cfg->meas_std > 0.0)) return fail(AUVPF_ERR_BADARG, "measurement_std must be > 0");
     if (!(cfg->range_max > 0.0)) return fail(AUVPF_ERR_BADARG, "range_max must be > 0");
@@ -780,25 +821,34 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         int rc2;
         h->tiles_per_filter = (int)((h->M + kScanTile - 1) / kScanTile);
         if ((rc2 = alloc_slab(h))) return rc2;
-        CU(cudaMalloc(&h->logw, sizeof(float) * h->N));
         CU(cudaMalloc(&h->wmax_ordered, sizeof(long long) * F));
+        {
+            std::vector<long long> init((size_t)F, (long long)0xFFF0000000000000ull ^ 0x7FFFFFFFFFFFFFFFll);   // ordered(-inf)
+            CU(cudaMemcpy(h->wmax_ordered, init.data(), sizeof(long long) * F, cudaMemcpyHostToDevice));
+        }
         CU(cudaMalloc(&h->wmax, sizeof(double) * F));
         CU(cudaMalloc(&h->wmax_f32, sizeof(int) * 2 * F));   // [F] max log-weight | [F] flagged-particle counters
         CU(cudaMalloc(&h->done, sizeof(unsigned int) * F));
         CU(cudaMemsetAsync(h->done, 0, sizeof(unsigned int) * F, h->stream));
-        CU(cudaMalloc(&h->limbs, sizeof(unsigned long long) * 2 * F));
-        CU(cudaMemsetAsync(h->limbs, 0, sizeof(unsigned long long) * 2 * F, h->stream));
-        CU(cudaMalloc(&h->A, sizeof(unsigned long long) * 2 * F));
-        CU(cudaMalloc(&h->Q, sizeof(unsigned long long) * F));
+        CU(cudaMalloc(&h->A, sizeof(U128) * F));
+        CU(cudaMemsetAsync(h->A, 0, sizeof(U128) * F, h->stream));
         CU(cudaMalloc(&h->deficit, sizeof(unsigned long long) * F));
+        CU(cudaMemsetAsync(h->deficit, 0, sizeof(unsigned long long) * F, h->stream));
         CU(cudaMalloc(&h->u, sizeof(double) * F));
         CU(cudaMalloc(&h->sumsq, sizeof(double) * F));
         CU(cudaMalloc(&h->sums, sizeof(double) * 16 * F));
         CU(cudaMalloc(&h->gps, sizeof(double) * 2 * F));
         CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F * AUVPF_MAX_PREDICT_STEPS));
         CU(cudaMalloc(&h->degenerate, sizeof(int) * F));
-        CU(cudaMalloc(&h->sqlimbs, sizeof(unsigned long long) * 2 * F));
-        CU(cudaMemsetAsync(h->sqlimbs, 0, sizeof(unsigned long long) * 2 * F, h->stream));
+        CU(cudaMemsetAsync(h->degenerate, 0, sizeof(int) * F, h->stream));
+        CU(cudaMalloc(&h->neff_acc, sizeof(unsigned long long) * 3 * F));
+        CU(cudaMemsetAsync(h->neff_acc, 0, sizeof(unsigned long long) * 3 * F, h->stream));
+        CU(cudaMalloc(&h->neff_pub, sizeof(unsigned long long) * 3 * F));
+        CU(cudaMemsetAsync(h->neff_pub, 0, sizeof(unsigned long long) * 3 * F, h->stream));
+        CU(cudaMalloc(&h->shard_degenerate, sizeof(int)));
+        CU(cudaMemsetAsync(h->shard_degenerate, 0, sizeof(int), h->stream));
+        CU(cudaMalloc(&h->shard_totals, sizeof(unsigned long long) * 6));
+        CU(cudaMalloc(&h->c_off, sizeof(U128) * (kMaxPeers + 1)));
         CU(cudaMalloc(&h->skipped, sizeof(int) * F));
         CU(cudaMemsetAsync(h->skipped, 0, sizeof(int) * F, h->stream));
         CU(cudaMalloc(&h->tile_counter, sizeof(unsigned int)));
@@ -811,7 +861,8 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
             CU(cudaMemsetAsync(h->st[b].pitch, 0, sizeof(float) * h->N, h->stream));
             CU(cudaMemsetAsync(h->st[b].yaw, 0, sizeof(float) * h->N, h->stream));
         }
-        CU(cudaMemsetAsync(h->logw, 0, sizeof(float) * h->N, h->stream));
+        CU(cudaMemsetAsync(h->logw_buf[0], 0, sizeof(float) * h->N, h->stream));
+        CU(cudaMemsetAsync(h->logw_buf[1], 0, sizeof(float) * h->N, h->stream));
         return AUVPF_OK;
     }();
     if (rc) {
@@ -843,14 +894,13 @@ int auvpf_destroy(auvpf_handle *h)
     Guard g(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int r = 0; r < h->n_peers; ++r)
-        if (r != h->my_peer && h->peer_slab[r]) cudaIpcCloseMemHandle(h->peer_slab[r]);
+        if (r != h->my_peer && h->peer_slab[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_slab[r]);
     cudaFree(h->slab);
-    cudaFree(h->shard_meta);
-    cudaFree(h->peer_tables);
-    void *bufs[] = {h->logw,    h->wmax_ordered, h->wmax,    h->limbs,  h->A,      h->Q,
+    cudaFree(h->peer_shards);
+    void *bufs[] = {h->wmax_ordered, h->wmax,    h->A,      h->neff_acc, h->neff_pub, h->shard_degenerate, h->shard_totals, h->c_off,
                     h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
-                    h->wmax_f32, h->done, h->scan3, h->sqlimbs, h->skipped,
+                    h->wmax_f32, h->done, h->scan3, h->skipped,
                     h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->probe_flags.p,
                     h->replay_params.p, h->replay_ranges.p, h->replay_u.p, h->replay_stats.p};
     for (void *b : bufs) cudaFree(b);
@@ -1161,6 +1211,7 @@ int auvpf_set_logw(auvpf_handle *h, const float *logw)
 {
     if (!h || !logw) return fail(AUVPF_ERR_BADARG, "null argument");
     Guard g(h);
+    flip_logw(h);
     CU(cudaMemcpyAsync(h->logw, logw, sizeof(float) * h->N,
                        is_device_ptr(logw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     h->wmax_valid = false;
@@ -1212,6 +1263,7 @@ int auvpf_update_gps(auvpf_handle *h, const double *gps_xy, float *logw_out)
     if (is_device_ptr(gps_xy)) CU(cudaMemcpyAsync(h->gps, gps_xy, sizeof(double) * 2 * h->F, cudaMemcpyDeviceToDevice, h->stream));
     else if ((rc = tiny_upload(h, h->gps, gps_xy, sizeof(double) * 2 * h->F))) return rc;
     const double var = h->cfg.meas_std * h->cfg.meas_std;
+    flip_logw(h);
     CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * h->F, h->stream));
     h->wmax_valid = true;
     {
@@ -1234,6 +1286,7 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
     CU(cudaMemcpyAsync(h->meas, ranges, sizeof(float) * (size_t)h->B * h->F,
                        is_device_ptr(ranges) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     const double var = h->cfg.meas_std * h->cfg.meas_std;
+    flip_logw(h);
     // one fill resets the maxima AND the flagged-particle counters (both count from kWmaxReset)
     CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * 2 * h->F, h->stream));
     h->wmax_valid = true;
@@ -1344,11 +1397,13 @@ int auvpf_get_weights_q(auvpf_handle *h, uint64_t *q)
     unsigned long long *qd;
     int rc = stage_out(h, S_OUT0, reinterpret_cast<unsigned long long *>(q), (size_t)h->N, &qd);
     if (rc) return rc;
-    WeightSrc src{h->logw, h->lin_weights, h->last_src_kind};
-    k_emit_q<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->A, h->deficit,
-                                                                     h->global_offset, qd);
-    LAUNCHED(h, AUVPF_K_OTHER, 1);
-    CU(cudaGetLastError());
+    if (h->global_count != h->M && !h->have_global)
+        return fail(AUVPF_ERR_STATE, "sharded filter: the global total is known after auvpf_shard_resample / auvpf_shard_emit");
+    {
+        int rc2 = run_exact_q(h, qd, nullptr, h->global_count != h->M ? h->c_off + h->n_ranks_global : h->A,
+                              h->global_count != h->M ? h->c_off + h->my_rank_global : nullptr);
+        if (rc2) return rc2;
+    }
     return finish_out(h, reinterpret_cast<unsigned long long *>(q), (const unsigned long long *)qd, (size_t)h->N);
 }
 
@@ -1400,6 +1455,97 @@ int reserve(DevBuf &b, size_t bytes)
     return AUVPF_OK;
 }
 }   // namespace
+
+// auv_pf.update_loc_pose with options: weighted by the current log-weights, circular yaw mean,
+// full symmetric covariance.  flags == 0 is auvpf_mean_cov (the reference's numbers).
+int auvpf_estimate(auvpf_handle *h, int32_t flags, double *mean, double *cov)
+{
+    if (!h || !mean || !cov) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (flags == AUVPF_EST_REFERENCE) return auvpf_mean_cov(h, mean, cov);
+    if (flags & ~(AUVPF_EST_WEIGHTED | AUVPF_EST_CIRCULAR_YAW | AUVPF_EST_FULL_COV)) return fail(AUVPF_ERR_BADARG, "unknown estimate flags %d", flags);
+    Guard g(h);
+    int rc;
+    const bool weighted = (flags & AUVPF_EST_WEIGHTED) != 0;
+    if (weighted && (rc = ensure_wmax_f32(h))) return rc;
+    void *buf;
+    if ((rc = slot_reserve(h, S_OUT1, sizeof(double) * 20 * h->F, &buf))) return rc;
+    double *stats = static_cast<double *>(buf);
+    std::vector<double> host(20 * (size_t)h->F);
+    {
+        Prof pr(h, AUVPF_K_ESTIMATE);
+        CU(cudaMemsetAsync(stats, 0, sizeof(double) * 20 * h->F, h->stream));
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 592 / h->F));
+        k_pose_stats_w<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->logw, h->wmax_f32, weighted ? 1 : 0, stats);
+        LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(host.data(), stats, sizeof(double) * 20 * h->F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int f = 0; f < h->F; ++f) {
+        const double *s = host.data() + 20 * f;
+        if (!(s[0] > 0.0)) return fail(AUVPF_ERR_DEGENERATE, "filter %d: no finite positive weight; estimate undefined", f);
+        const double inv = 1.0 / s[0];
+        const double md[3] = {s[1] * inv, s[2] * inv, s[3] * inv};
+        for (int c = 0; c < 3; ++c) mean[6 * f + c] = s[15 + c] + md[c];
+        mean[6 * f + 3] = s[4] * inv;
+        mean[6 * f + 4] = s[5] * inv;
+        mean[6 * f + 5] = (flags & AUVPF_EST_CIRCULAR_YAW) ? std::atan2(s[7], s[8]) : s[6] * inv;
+        double *C = cov + 9 * f;
+        C[0] = s[9] * inv - md[0] * md[0];
+        C[4] = s[10] * inv - md[1] * md[1];
+        C[8] = s[11] * inv - md[2] * md[2];
+        C[1] = C[3] = s[12] * inv - md[0] * md[1];
+        C[2] = s[13] * inv - md[0] * md[2];
+        C[5] = s[14] * inv - md[1] * md[2];
+        if (flags & AUVPF_EST_FULL_COV) {
+            C[6] = C[2];
+            C[7] = C[5];
+        } else {
+            C[6] = 0.0;          // the reference's fill pattern (auv_pf.py:238-246)
+            C[7] = 0.0;
+        }
+    }
+    return AUVPF_OK;
+}
+
+// PoseArray of auv_pf.loc_loop (auv_pf.py:264-285) for a strided subsample: (F, n, 7) float64 rows
+// [x y z qx qy qz qw], n = min(ceil(M / stride), max_poses) per filter (stride <= 0: chosen so that n <= max_poses).
+int auvpf_pose_array(auvpf_handle *h, int64_t stride, int64_t max_poses, double *poses7_out, int64_t *n_out)
+{
+    if (!h || !poses7_out || !n_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (max_poses < 1) return fail(AUVPF_ERR_BADARG, "max_poses must be positive");
+    if (stride <= 0) stride = (h->M + max_poses - 1) / max_poses;
+    const int64_t n = std::min<int64_t>((h->M + stride - 1) / stride, max_poses);
+    Guard g(h);
+    double *od;
+    int rc = stage_out(h, S_OUT0, poses7_out, (size_t)n * 7 * h->F, &od);
+    if (rc) return rc;
+    k_pose_array<<<grid1(n, kThreads, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, stride, n, od);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    *n_out = n;
+    return finish_out(h, poses7_out, (const double *)od, (size_t)n * 7 * h->F);
+}
+
+int auvpf_pose_sums_buffer(auvpf_handle *h, void **sums_f64)
+{
+    if (!h || !sums_f64) return fail(AUVPF_ERR_BADARG, "null argument");
+    *sums_f64 = h->sums;
+    return AUVPF_OK;
+}
+
+int auvpf_pose_sums_dev(auvpf_handle *h)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    Prof pr(h, AUVPF_K_ESTIMATE);
+    CU(cudaMemsetAsync(h->sums, 0, sizeof(double) * 16 * h->F, h->stream));
+    int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 592 / h->F));
+    k_pose_stats<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
+    LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
 
 int auvpf_mean_cov(auvpf_handle *h, double *mean, double *cov)
 {
@@ -1545,10 +1691,10 @@ int auvpf_neff_fixed(auvpf_handle *h, double *neff)
     if (!h->have_norm) return fail(AUVPF_ERR_STATE, "no normalisation available: call auvpf_resample first");
     if (h->global_count != h->M) return fail(AUVPF_ERR_STATE, "not available for a particle-sharded filter");
     Guard g(h);
-    std::vector<unsigned long long> S(2 * (size_t)h->F);
-    CU(cudaMemcpyAsync(S.data(), h->sqlimbs, sizeof(unsigned long long) * 2 * h->F, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<unsigned long long> S(3 * (size_t)h->F);
+    CU(cudaMemcpyAsync(S.data(), h->neff_pub, sizeof(unsigned long long) * 3 * h->F, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (int f = 0; f < h->F; ++f) neff[f] = neff_fixed(S[2 * f], S[2 * f + 1]);
+    for (int f = 0; f < h->F; ++f) neff[f] = neff_fixed_a(S[3 * f], S[3 * f + 1], S[3 * f + 2]);
     return AUVPF_OK;
 }
 
@@ -1558,13 +1704,10 @@ int auvpf_neff(auvpf_handle *h, double *neff)
     if (!h->have_norm) return fail(AUVPF_ERR_STATE, "no normalisation available: call auvpf_resample first");
     Guard g(h);
     std::vector<double> s(h->F);
+    if (h->global_count != h->M) return fail(AUVPF_ERR_STATE, "not available for a particle-sharded filter");
     if (h->sumsq_lazy) {        // valid while the weights of the last resample are still in place (like auvpf_get_weights_q)
-        CU(cudaMemsetAsync(h->sumsq, 0, sizeof(double) * h->F, h->stream));
-        WeightSrc src{h->logw, h->lin_weights, h->last_src_kind};
-        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
-        k_sumsq_from_src<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src, h->M, h->wmax, h->A, h->degenerate, h->sumsq);
-        LAUNCHED(h, AUVPF_K_OTHER, 1);
-        CU(cudaGetLastError());
+        int rc = run_exact_q(h, nullptr, h->sumsq, h->A, nullptr);
+        if (rc) return rc;
         h->sumsq_lazy = false;
     }
     CU(cudaMemcpyAsync(s.data(), h->sumsq, sizeof(double) * h->F, cudaMemcpyDeviceToHost, h->stream));
@@ -1574,63 +1717,105 @@ int auvpf_neff(auvpf_handle *h, double *neff)
 }
 
 // ------------------------------------------------------------------------------------------------
-// multi-GPU staging (particle-sharded single filter)
+// multi-GPU (particle-sharded single filter)
+namespace {
+// per-shard totals (G x 6 words: A lo, A hi, S1, S2 lo, S2 hi, log-weight buffer) -> mass below every shard
+__global__ void k_build_coff(const unsigned long long *totals_all, int G, U128 *c_off)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    U128 acc = u128(0);
+    for (int g = 0; g < G; ++g) {
+        c_off[g] = acc;
+        acc = acc + u128(totals_all[6 * g], totals_all[6 * g + 1]);
+    }
+    c_off[G] = acc;
+}
+
+__global__ void k_pack_totals(const U128 *A, const unsigned long long *neff_pub, int parity, unsigned long long *out)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    out[0] = A[0].lo;
+    out[1] = A[0].hi;
+    out[2] = neff_pub[0];
+    out[3] = neff_pub[1];
+    out[4] = neff_pub[2];
+    out[5] = (unsigned long long)parity;
+}
+
+int float_to_ordered_host(float f)
+{
+    int b;
+    memcpy(&b, &f, sizeof b);
+    return b >= 0 ? b : b ^ 0x7FFFFFFF;
+}
+
+int need_single_filter(auvpf_handle *h)
+{
+    if (h->F != 1) return fail(AUVPF_ERR_BADARG, "particle sharding is for a single filter (n_filters == 1)");
+    return AUVPF_OK;
+}
+
+// peers' slabs are known (h->peer_slab, offsets in `offs`): build what the kernels read
+int finish_attach(auvpf_handle *h, const int64_t (*offs)[kSlabParts], int n_ranks, int my_rank)
+{
+    std::vector<SelShard> sh((size_t)n_ranks);
+    h->mbox.G = n_ranks;
+    h->mbox.rank = my_rank;
+    for (int r = 0; r < n_ranks; ++r) {
+        sh[r] = shard_at(h->peer_slab[r], offs[r]);
+        h->mbox.peer[r] = reinterpret_cast<unsigned long long *>(static_cast<char *>(h->peer_slab[r]) + offs[r][P_MBOX]);
+    }
+    h->n_peers = n_ranks;
+    h->my_peer = my_rank;
+    CU(cudaMalloc(&h->peer_shards, sizeof(SelShard) * n_ranks));
+    CU(cudaMemcpy(h->peer_shards, sh.data(), sizeof(SelShard) * n_ranks, cudaMemcpyHostToDevice));
+    return AUVPF_OK;
+}
+}   // namespace
+
+// ---- staged variant: the scalars travel through the caller (host, or device buffers it reduces in place) --------
 int auvpf_shard_max(auvpf_handle *h, float *m_out)
 {
     if (!h || !m_out) return fail(AUVPF_ERR_BADARG, "null argument");
     Guard g(h);
-    WeightSrc src{h->logw, nullptr, 0};
-    int rc = run_max(h, src);
+    int rc = need_single_filter(h);
     if (rc) return rc;
-    std::vector<double> m(h->F);
-    CU(cudaMemcpyAsync(m.data(), h->wmax, sizeof(double) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = ensure_wmax_f32(h))) return rc;
+    int k;
+    CU(cudaMemcpyAsync(&k, h->wmax_f32, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (int f = 0; f < h->F; ++f) m_out[f] = (float)m[f];
+    if (k > kWmaxReset) {
+        const int b = k >= 0 ? k : k ^ 0x7FFFFFFF;
+        memcpy(m_out, &b, sizeof(float));
+    } else
+        *m_out = -INFINITY;
     return AUVPF_OK;
 }
 
-int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *limbs_out)
+int auvpf_shard_sum(auvpf_handle *h, const float *m_global, uint64_t *totals_out)
 {
-    if (!h || !m_global || !limbs_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!h || !m_global || !totals_out) return fail(AUVPF_ERR_BADARG, "null argument");
     Guard g(h);
-    std::vector<double> m(h->F);
-    for (int f = 0; f < h->F; ++f) m[f] = (double)m_global[f];
-    int rc = tiny_upload(h, h->wmax, m.data(), sizeof(double) * h->F);
+    int rc = need_single_filter(h);
     if (rc) return rc;
-    CU(cudaMemsetAsync(h->limbs, 0, sizeof(unsigned long long) * 2 * h->F, h->stream));
-    CU(cudaMemsetAsync(h->sumsq, 0, sizeof(double) * h->F, h->stream));
+    const int k = std::isfinite(*m_global) ? float_to_ordered_host(*m_global) : kWmaxReset;
+    if ((rc = tiny_upload(h, h->wmax_f32, &k, sizeof(int)))) return rc;
+    h->wmax_valid = true;       // the buffer now holds the GLOBAL maximum
     WeightSrc src{h->logw, nullptr, 0};
-    if ((rc = run_sum(h, src))) return rc;
-    CU(cudaMemcpyAsync(limbs_out, h->limbs, sizeof(unsigned long long) * 2 * h->F, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemsetAsync(h->limbs, 0, sizeof(unsigned long long) * 2 * h->F, h->stream));   // k_normalise expects zeros
+    if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
+    h->wmax_valid = false;      // ... which is not this shard's: recompute next time unless an update refreshes it
+    k_pack_totals<<<1, 32, 0, h->stream>>>(h->A, h->neff_pub, h->lw, h->shard_totals);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(totals_out, h->shard_totals, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return AUVPF_OK;
 }
 
-int auvpf_shard_scan(auvpf_handle *h, const float *m_global, const uint64_t *A_global, uint64_t *Q_out)
-{
-    if (!h || !m_global || !A_global || !Q_out) return fail(AUVPF_ERR_BADARG, "null argument");
-    Guard g(h);
-    int rc = tiny_upload(h, h->A, A_global, sizeof(unsigned long long) * 2 * h->F);
-    if (rc) return rc;
-    WeightSrc src{h->logw, nullptr, 0};
-    if ((rc = run_scan(h, src))) return rc;
-    h->have_norm = true;
-    h->last_src_kind = 0;
-    CU(cudaMemcpyAsync(Q_out, h->Q, sizeof(unsigned long long) * h->F, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    return AUVPF_OK;
-}
-
-// Device-resident variant of stages 1-3: the three scalars never visit the host.  The caller
-// all-reduces / all-gathers them IN PLACE on the device between the calls, ordered on the
-// handle's stream (torch.cuda.ExternalStream + torch.distributed, sharded.py).
-int auvpf_shard_buffers(auvpf_handle *h, void **wmax_i32, void **limbs_u64, void **q_u64)
+int auvpf_shard_buffers(auvpf_handle *h, void **wmax_i32, void **totals_u64)
 {
     if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
     if (wmax_i32) *wmax_i32 = h->wmax_f32;
-    if (limbs_u64) *limbs_u64 = h->limbs;
-    if (q_u64) *q_u64 = h->Q;
+    if (totals_u64) *totals_u64 = h->shard_totals;
     return AUVPF_OK;
 }
 
@@ -1641,38 +1826,75 @@ int auvpf_shard_max_dev(auvpf_handle *h)
     return ensure_wmax_f32(h);
 }
 
-int auvpf_shard_sum_dev(auvpf_handle *h)
+int auvpf_shard_weights_dev(auvpf_handle *h)
 {
     if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
     Guard g(h);
+    int rc = need_single_filter(h);
+    if (rc) return rc;
     WeightSrc src{h->logw, nullptr, 0};
     h->wmax_valid = true;       // the buffer now holds the GLOBAL maximum
-    return run_normalise(h, src, /*finalise=*/false);
-}
-
-int auvpf_shard_scan_dev(auvpf_handle *h)
-{
-    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
-    Guard g(h);
-    k_shard_finish_sum<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->limbs, h->A, h->wmax, h->degenerate, h->sumsq,
-                                                                  h->F);
+    if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
+    h->wmax_valid = false;
+    k_pack_totals<<<1, 32, 0, h->stream>>>(h->A, h->neff_pub, h->lw, h->shard_totals);
     LAUNCHED(h, AUVPF_K_NORMALISE, 1);
-    WeightSrc src{h->logw, nullptr, 0};
-    // a shard's peers (k_select_gather_p2p) and auvpf_shard_emit read a FINISHED inclusive CDF and a flagged tile
-    // table: the look-back scan k_scan_q, not the single-GPU k_quotients (raw quotients + per-tile sums)
-    int rc = run_scan(h, src, /*fused=*/false);
-    h->have_norm = true;
-    h->last_src_kind = 0;
-    h->wmax_valid = false;      // the maximum in the buffer is not this shard's: recompute next time unless an update refreshes it
-    return rc;
+    CU(cudaGetLastError());
+    return AUVPF_OK;
 }
 
-// ---- peer-memory exchange (CUDA IPC): one kernel does select + gather + exchange -----------------
+int auvpf_shard_emit(auvpf_handle *h, double u, const uint64_t *totals_all, int32_t n_ranks, int32_t my_rank, int64_t out_lo,
+                     int64_t out_hi, void *records, int64_t *ancestors_out)
+{
+    if (!h || !totals_all) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
+        return fail(AUVPF_ERR_BADARG, "ranks: 1..%d, got %d (my rank %d)", kMaxPeers, n_ranks, my_rank);
+    const int64_t n_out = out_hi - out_lo;
+    if (n_out < 0) return fail(AUVPF_ERR_BADARG, "out_hi < out_lo");
+    Guard g(h);
+    int rc = need_single_filter(h);
+    if (rc) return rc;
+    const unsigned long long *td = nullptr;
+    if ((rc = stage_in(h, S_IN2, reinterpret_cast<const unsigned long long *>(totals_all), (size_t)n_ranks * 6, &td))) return rc;
+    k_build_coff<<<1, 32, 0, h->stream>>>(td, n_ranks, h->c_off);
+    CU(cudaGetLastError());
+    h->have_global = true;
+    h->n_ranks_global = n_ranks;
+    h->my_rank_global = my_rank;
+    if ((rc = tiny_upload(h, h->u, &u, sizeof u))) return rc;
+    if (n_out == 0) return AUVPF_OK;
+    if (!records) return fail(AUVPF_ERR_BADARG, "null records");
+    Record *rd = nullptr;
+    int64_t *ad = nullptr;
+    if ((rc = stage_out(h, S_OUT0, static_cast<Record *>(records), (size_t)n_out, &rd))) return rc;
+    if (ancestors_out && (rc = stage_out(h, S_OUT1, ancestors_out, (size_t)n_out, &ad))) return rc;
+    WeightSrc src{h->logw, nullptr, 0};
+    SelArgs sa = select_args(h, src);
+    sa.G = n_ranks;
+    sa.rank = my_rank;
+    sa.out_lo = out_lo;
+    sa.n_out = n_out;
+    sa.c_off = h->c_off;
+    sa.records = rd;
+    sa.anc64 = ad;
+    sa.rough = make_noise(h, nullptr, nullptr, 0, 0, kStreamRoughen);
+    sa.dst = StateView{};
+    {
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        k_select<kSelRecords><<<grid1(n_out, kSelTile, 1), kSelThreads, 0, h->stream>>>(sa);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 2);
+        CU(cudaGetLastError());
+    }
+    if ((rc = finish_out(h, static_cast<Record *>(records), (const Record *)rd, (size_t)n_out))) return rc;
+    if (ancestors_out && (rc = finish_out(h, ancestors_out, (const int64_t *)ad, (size_t)n_out))) return rc;
+    return AUVPF_OK;
+}
+
+// ---- peer memory: the slabs of all ranks mapped into every rank ----------------------------------------
 namespace {
 struct IpcBlob {            // what a rank publishes: AUVPF_IPC_BLOB_BYTES
     cudaIpcMemHandle_t handle;
     int64_t M, slab_bytes;
-    int64_t off[14];
+    int64_t off[kSlabParts];
     int32_t tiles, device;
 };
 static_assert(sizeof(IpcBlob) <= AUVPF_IPC_BLOB_BYTES, "IpcBlob must fit the ABI's blob size");
@@ -1681,13 +1903,14 @@ static_assert(sizeof(IpcBlob) <= AUVPF_IPC_BLOB_BYTES, "IpcBlob must fit the ABI
 int auvpf_ipc_export(auvpf_handle *h, void *blob)
 {
     if (!h || !blob) return fail(AUVPF_ERR_BADARG, "null argument");
-    if (h->F != 1) return fail(AUVPF_ERR_BADARG, "particle sharding is for a single filter (n_filters == 1)");
     Guard g(h);
+    int rc = need_single_filter(h);
+    if (rc) return rc;
     IpcBlob b{};
     CU(cudaIpcGetMemHandle(&b.handle, h->slab));
     b.M = h->M;
     b.slab_bytes = (int64_t)h->slab_bytes;
-    for (int k = 0; k < 14; ++k) b.off[k] = h->slab_off[k];
+    for (int k = 0; k < kSlabParts; ++k) b.off[k] = h->slab_off[k];
     b.tiles = h->tiles_per_filter;
     b.device = h->device;
     memset(blob, 0, AUVPF_IPC_BLOB_BYTES);
@@ -1700,10 +1923,9 @@ int auvpf_ipc_import(auvpf_handle *h, const void *blobs, int32_t n_ranks, int32_
     if (!h || !blobs) return fail(AUVPF_ERR_BADARG, "null argument");
     if (n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
         return fail(AUVPF_ERR_BADARG, "ranks: 1..%d, got %d (my rank %d)", kMaxPeers, n_ranks, my_rank);
-    if (h->n_peers) return fail(AUVPF_ERR_STATE, "peers already imported");
+    if (h->n_peers) return fail(AUVPF_ERR_STATE, "peers already attached");
     Guard g(h);
-    PeerTable tab[2];
-    memset(tab, 0, sizeof tab);
+    int64_t offs[kMaxPeers][kSlabParts];
     for (int r = 0; r < n_ranks; ++r) {
         IpcBlob b;
         memcpy(&b, static_cast<const char *>(blobs) + (size_t)r * AUVPF_IPC_BLOB_BYTES, sizeof b);
@@ -1717,43 +1939,78 @@ int auvpf_ipc_import(auvpf_handle *h, const void *blobs, int32_t n_ranks, int32_
                 if (!can) return fail(AUVPF_ERR_CUDA, "device %d cannot access device %d's memory", h->device, b.device);
             }
             CU(cudaIpcOpenMemHandle(&base, b.handle, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_ipc[r] = true;
         }
         h->peer_slab[r] = base;
-        char *c = static_cast<char *>(base);
-        for (int buf = 0; buf < 2; ++buf) {
-            tab[buf].cdf[r] = reinterpret_cast<unsigned long long *>(c + b.off[12]);
-            tab[buf].status[r] = reinterpret_cast<unsigned long long *>(c + b.off[13]);
-            tab[buf].st[r] = state_at(base, b.off + 6 * buf);
-            tab[buf].G = n_ranks;
-        }
+        for (int k = 0; k < kSlabParts; ++k) offs[r][k] = b.off[k];
     }
-    h->n_peers = n_ranks;
-    h->my_peer = my_rank;
-    CU(cudaMalloc(&h->peer_tables, sizeof tab));
-    CU(cudaMemcpy(h->peer_tables, tab, sizeof tab, cudaMemcpyHostToDevice));
-    CU(cudaMalloc(&h->shard_meta, sizeof(unsigned long long) * (n_ranks + 2)));
-    return AUVPF_OK;
+    return finish_attach(h, offs, n_ranks, my_rank);
 }
 
-int auvpf_shard_gather_p2p(auvpf_handle *h, double u, const int64_t *q_all_dev, const double *rough_var,
-                           const float *rough_noise, int64_t *ancestors_out_dev)
+int auvpf_peer_attach(auvpf_handle *h, auvpf_handle *const *handles, int32_t n_ranks, int32_t my_rank)
 {
-    if (!h || !q_all_dev) return fail(AUVPF_ERR_BADARG, "null argument");
-    if (!h->n_peers) return fail(AUVPF_ERR_STATE, "auvpf_ipc_import first");
+    if (!h || !handles) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks || handles[my_rank] != h)
+        return fail(AUVPF_ERR_BADARG, "ranks: 1..%d, got %d (my rank %d), handles[my_rank] must be this handle", kMaxPeers,
+                    n_ranks, my_rank);
+    if (h->n_peers) return fail(AUVPF_ERR_STATE, "peers already attached");
+    Guard g(h);
+    int rc = need_single_filter(h);
+    if (rc) return rc;
+    int64_t offs[kMaxPeers][kSlabParts];
+    for (int r = 0; r < n_ranks; ++r) {
+        auvpf_handle *p = handles[r];
+        if (!p || p->M != h->M || p->F != 1)
+            return fail(AUVPF_ERR_BADARG, "rank %d must hold one filter of %lld particles", r, (long long)h->M);
+        if (p->device != h->device) {
+            int can = 0;
+            CU(cudaDeviceCanAccessPeer(&can, h->device, p->device));
+            if (!can) return fail(AUVPF_ERR_CUDA, "device %d cannot access device %d's memory", h->device, p->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(p->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(AUVPF_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", p->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+        h->peer_slab[r] = p->slab;
+        for (int k = 0; k < kSlabParts; ++k) offs[r][k] = p->slab_off[k];
+    }
+    return finish_attach(h, offs, n_ranks, my_rank);
+}
+
+int auvpf_shard_resample(auvpf_handle *h, double u, const double *rough_var, const float *rough_noise,
+                         int64_t *ancestors_out_dev)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    if (h->n_peers < 1) return fail(AUVPF_ERR_STATE, "attach the peers first (auvpf_ipc_import / auvpf_peer_attach)");
+    if (h->global_count != h->M * h->n_peers || h->global_offset != h->M * h->my_peer)
+        return fail(AUVPF_ERR_STATE, "global_offset / global_count of the handle do not match its rank among the peers");
     Guard g(h);
     int rc;
     const float *rn = nullptr;
     if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
-    NoiseParams rough = make_noise(h, rough_var, nullptr, rough_var ? 1 : 0, h->step_rough, kStreamRoughen);
+    h->epoch++;                 // every rank calls this the same number of times: the mailbox's epoch
+    WeightSrc src{h->logw, nullptr, 0};
+    if ((rc = run_weights(h, src, /*use_mailbox=*/true))) return rc;
+    h->wmax_valid = false;      // (k_weights used the global maximum; the local one is refreshed by the next update)
+    if ((rc = tiny_upload(h, h->u, &u, sizeof u))) return rc;
+    SelArgs sa = select_args(h, src);
+    sa.G = h->n_peers;
+    sa.rank = h->my_peer;
+    sa.peers = h->peer_shards;
+    sa.coff_out = h->c_off;
+    sa.rough = make_noise(h, rough_var, nullptr, rough_var ? 1 : 0, h->step_rough, kStreamRoughen);
+    sa.rough_noise = rn;
+    sa.anc64 = ancestors_out_dev;
+    sa.dst = h->st[1 - h->cur];
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
-        k_shard_meta<<<1, 32, 0, h->stream>>>(reinterpret_cast<const long long *>(q_all_dev), h->n_peers, h->shard_meta);
-        k_select_gather_p2p<<<grid1(h->M, kSelTile, 1), kSelThreads, 0, h->stream>>>(
-            h->peer_tables + h->cur, h->M, h->my_peer, h->tiles_per_filter, u, h->shard_meta, h->st[1 - h->cur],
-            ancestors_out_dev, rough, rn);
-        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 2);
+        k_select<kSelPeers><<<grid1(h->M, kSelTile, 1), kSelThreads, 0, h->stream>>>(sa);
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
+    h->have_global = true;
+    h->n_ranks_global = h->n_peers;
+    h->my_rank_global = h->my_peer;
     h->cur = 1 - h->cur;
     if (rough_var) h->step_rough++;
     return AUVPF_OK;
@@ -1762,53 +2019,12 @@ int auvpf_shard_gather_p2p(auvpf_handle *h, double u, const int64_t *q_all_dev, 
 int auvpf_shard_degenerate(auvpf_handle *h, int32_t *flag)
 {
     if (!h || !flag) return fail(AUVPF_ERR_BADARG, "null argument");
-    if (!h->n_peers) return fail(AUVPF_ERR_STATE, "auvpf_ipc_import first");
+    if (!h->n_peers) return fail(AUVPF_ERR_STATE, "attach the peers first");
     Guard g(h);
-    unsigned long long v = 0;
-    CU(cudaMemcpyAsync(&v, h->shard_meta + h->n_peers + 1, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    int v = 0;
+    CU(cudaMemcpyAsync(&v, h->shard_degenerate, sizeof v, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     *flag = v ? 1 : 0;
-    return AUVPF_OK;
-}
-
-int auvpf_shard_emit(auvpf_handle *h, double u, uint64_t q_offset, uint64_t deficit, int64_t out_lo, int64_t out_hi,
-                     void *records, int64_t *ancestors_out)
-{
-    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
-    if (h->F != 1) return fail(AUVPF_ERR_BADARG, "particle sharding is for a single filter (n_filters == 1)");
-    const int64_t n_out = out_hi - out_lo;
-    if (n_out < 0) return fail(AUVPF_ERR_BADARG, "out_hi < out_lo");
-    Guard g(h);
-    int rc;
-    unsigned long long d = deficit;
-    if ((rc = tiny_upload(h, h->deficit, &d, sizeof d))) return rc;
-    if ((rc = tiny_upload(h, h->u, &u, sizeof u))) return rc;
-    if (n_out == 0) return AUVPF_OK;
-    if (!records) return fail(AUVPF_ERR_BADARG, "null records");
-    Record *rd = nullptr;
-    int64_t *ad = nullptr;
-    if ((rc = stage_out(h, S_OUT0, static_cast<Record *>(records), (size_t)n_out, &rd))) return rc;
-    if (ancestors_out && (rc = stage_out(h, S_OUT1, ancestors_out, (size_t)n_out, &ad))) return rc;
-    SelectParams sp;
-    sp.M = h->M;
-    sp.n_global = h->global_count;
-    sp.j_global0 = h->global_offset;
-    sp.out_lo = out_lo;
-    sp.n_out = n_out;
-    sp.q_offset = q_offset;
-    sp.tiles_per_filter = h->tiles_per_filter;
-    NoiseParams none = make_noise(h, nullptr, nullptr, 0, 0, kStreamRoughen);
-    {
-        Prof pr(h, AUVPF_K_SELECT_GATHER);
-        StateView nodst{};
-        k_select_gather<true><<<grid1(n_out, kSelTile, 1), kSelThreads, 0, h->stream>>>(
-            h->cdf, sp, h->u, h->deficit, h->st[h->cur], nodst, rd, nullptr, ad, none, nullptr, h->status, nullptr,
-            NeffGate{nullptr, 0.0, nullptr});
-        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
-        CU(cudaGetLastError());
-    }
-    if ((rc = finish_out(h, static_cast<Record *>(records), (const Record *)rd, (size_t)n_out))) return rc;
-    if (ancestors_out && (rc = finish_out(h, ancestors_out, (const int64_t *)ad, (size_t)n_out))) return rc;
     return AUVPF_OK;
 }
 

@@ -662,188 +662,14 @@ __global__ void k_max_f32(const float *in, int64_t n, int *out_ordered)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Normalisation, stage 1: per-filter maximum of the weight source.
-//   kind 0: float32 log-weights  -> wmax[f] = max logw (as double, ordered-int atomics)
+// Weight source of a resample:
+//   kind 0: float32 log-weights (the update kernels' output)
 //   kind 1: float64 linear weights (the reference's resample(weights) argument)
 struct WeightSrc {
     const float *logw;
     const double *lin;
     int kind;
 };
-
-__device__ __forceinline__ double src_value(const WeightSrc &w, int64_t row)
-{
-    return w.kind == 0 ? (double)w.logw[row] : w.lin[row];
-}
-
-__global__ void __launch_bounds__(kThreads) k_weight_max(WeightSrc w, int64_t M, long long *wmax_ordered)
-{
-    const int f = blockIdx.y;
-    double m = -INFINITY;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
-        double v = src_value(w, (int64_t)f * M + i);
-        if (v == v) m = fmax(m, v);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(wmax_ordered + f, double_to_ordered(m));
-}
-
-__device__ __forceinline__ uint64_t src_a(const WeightSrc &w, int64_t row, double wmax)
-{
-    return w.kind == 0 ? a_from_logw(w.logw[row], (float)wmax) : a_from_linear(w.lin[row], wmax);
-}
-
-// stage 2: A = sum_i a_i exactly, as two limb sums (low 32 bits, high bits) per filter
-__global__ void __launch_bounds__(kThreads)
-k_weight_sum(WeightSrc w, int64_t M, const double *wmax, unsigned long long *limbs)
-{
-    const int f = blockIdx.y;
-    const double m = wmax[f];
-    unsigned long long lo = 0, hi = 0;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
-        uint64_t a = src_a(w, (int64_t)f * M + i, m);
-        lo += a & 0xFFFFFFFFull;
-        hi += a >> 32;
-    }
-    lo = warp_sum_u64(lo);
-    hi = warp_sum_u64(hi);
-    __shared__ unsigned long long slo[kThreads / 32], shi[kThreads / 32];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        slo[warp] = lo;
-        shi[warp] = hi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < kThreads / 32; ++k) {
-            lo += slo[k];
-            hi += shi[k];
-        }
-        atomicAdd(limbs + 2 * f, lo);
-        atomicAdd(limbs + 2 * f + 1, hi);
-    }
-}
-
-// Single-GPU normalisation in ONE launch: the maximum arrives from the update kernel
-// (wmax_f32, ordered int) or from k_weight_max (wmax already float64 when wmax_f32 == nullptr);
-// every block adds its exact integer partial of A = sum_i a_i; the LAST block of a filter
-// (ticket counter) folds the limbs into A, publishes max / A / the degenerate flag and cleans
-// the accumulators for the next cycle.  The blocks also clear the scan's tile status words, so
-// the scan kernel needs no memset in front of it.
-struct NormState {
-    int *wmax_f32;                  // [F] ordered-int float32 max (update kernels), or nullptr
-    double *wmax;                   // [F] in (wmax_f32 == nullptr) / out
-    unsigned long long *limbs;      // [2F] zero on entry, zero on exit
-    unsigned int *done;             // [F]  zero on entry, zero on exit
-    unsigned long long *A;          // [2F] out
-    int *degenerate;                // [F]  out
-    double *sumsq;                  // [F]  zeroed
-    unsigned long long *sqlimbs;    // [2F] zeroed (integer sum of squares for the N_eff gate)
-    unsigned long long *status;     // [tiles_total] zeroed
-    unsigned int *tile_counter;     // zeroed
-    long long tiles_total;
-    unsigned long long *a_out;      // [F*M] a_i, kept for the scan (which overwrites it in place with the CDF)
-    int finalise;                   // 0: particle-sharded filter -- leave the limbs for the cross-GPU sum
-};
-
-__global__ void __launch_bounds__(kThreads) k_normalise(WeightSrc w, int64_t M, NormState ns)
-{
-    const int f = blockIdx.y;
-    // clear the scan machinery (any block, grid-stride)
-    {
-        const long long nth = (long long)gridDim.x * gridDim.y * kThreads;
-        const long long tid = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * kThreads + threadIdx.x;
-        for (long long t = tid; t < ns.tiles_total; t += nth) ns.status[t] = 0ull;
-        if (tid == 0) *ns.tile_counter = 0u;
-    }
-    double m;
-    if (ns.wmax_f32) {
-        const int k = ns.wmax_f32[f];
-        m = k > kWmaxReset ? (double)ordered_to_float(k) : -INFINITY;
-    } else
-        m = ns.wmax[f];
-    const bool bad = !isfinite(m) || (w.kind == 1 && !(m > 0.0));
-    unsigned long long lo = 0, hi = 0;
-    if (!bad) {
-        // A block owns ONE contiguous chunk of ceil(M / gridDim.x) particles (rounded up to 32 for sector
-        // alignment), so every block -- and with one wave of blocks every SM -- does the same work to
-        // within one element per thread.  (With a grid-stride loop over 4-element groups, 1 M particles
-        // on 740 blocks gave 284 blocks two trips and 456 blocks one: ncu showed the SMs busy for 58 %
-        // of the kernel.)  Four independent loads are in flight per thread before the long float64
-        // exp chains start.
-        const int64_t chunk = ((M + gridDim.x - 1) / gridDim.x + 31) & ~(int64_t)31;
-        const int64_t c0 = (int64_t)blockIdx.x * chunk, c1 = min(c0 + chunk, M);
-        for (int64_t i = c0 + threadIdx.x; i < c1; i += 4 * kThreads) {
-            double xv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int64_t ii = i + k * kThreads;
-                xv[k] = ii < c1 ? src_value(w, (int64_t)f * M + ii) : (w.kind == 0 ? -INFINITY : 0.0);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (i + k * kThreads >= c1) break;
-                const uint64_t a = w.kind == 0 ? a_from_x(xv[k] - (double)(float)m) : a_from_linear(xv[k], m);
-                ns.a_out[(int64_t)f * M + i + k * kThreads] = a;
-                lo += a & 0xFFFFFFFFull;
-                hi += a >> 32;
-            }
-        }
-    }
-    lo = warp_sum_u64(lo);
-    hi = warp_sum_u64(hi);
-    __shared__ unsigned long long slo[kThreads / 32], shi[kThreads / 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-        slo[warp] = lo;
-        shi[warp] = hi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int k = 1; k < kThreads / 32; ++k) {
-            lo += slo[k];
-            hi += shi[k];
-        }
-        if (lo) atomicAdd(ns.limbs + 2 * f, lo);
-        if (hi) atomicAdd(ns.limbs + 2 * f + 1, hi);
-        if (!ns.finalise) {
-            if (blockIdx.x == 0) ns.wmax[f] = m;
-            return;
-        }
-        __threadfence();
-        const unsigned int ticket = atomicAdd(ns.done + f, 1u);
-        if (ticket == gridDim.x - 1) {
-            __threadfence();
-            const unsigned long long l0 = atomicExch(ns.limbs + 2 * f, 0ull), l1 = atomicExch(ns.limbs + 2 * f + 1, 0ull);
-            const unsigned __int128 a = (unsigned __int128)l0 + ((unsigned __int128)l1 << 32);
-            ns.A[2 * f] = (unsigned long long)a;
-            ns.A[2 * f + 1] = (unsigned long long)(a >> 64);
-            ns.wmax[f] = m;
-            ns.degenerate[f] = (bad || a == 0) ? 1 : 0;
-            ns.sumsq[f] = 0.0;
-            ns.sqlimbs[2 * f] = 0ull;
-            ns.sqlimbs[2 * f + 1] = 0ull;
-            ns.done[f] = 0u;
-        }
-    }
-}
-
-// Particle-sharded filter: after the cross-GPU all-reduce of the limbs, fold them into A and set
-// the degenerate flag (the single-GPU path does this in k_normalise's last block).
-__global__ void k_shard_finish_sum(unsigned long long *limbs, unsigned long long *A, const double *wmax,
-                                   int *degenerate, double *sumsq, int F)
-{
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    const unsigned __int128 a = (unsigned __int128)limbs[2 * f] + ((unsigned __int128)limbs[2 * f + 1] << 32);
-    A[2 * f] = (unsigned long long)a;
-    A[2 * f + 1] = (unsigned long long)(a >> 64);
-    limbs[2 * f] = 0ull;
-    limbs[2 * f + 1] = 0ull;
-    degenerate[f] = (!isfinite(wmax[f]) || a == 0) ? 1 : 0;
-    sumsq[f] = 0.0;
-}
 
 // float32 log-weights that did not come from an update kernel (auvpf_set_logw): max pass
 __global__ void __launch_bounds__(kThreads) k_weight_max_f32(const float *logw, int64_t M, int *wmax_f32)
@@ -872,11 +698,7 @@ constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kV
 template <class ValueFn>
 __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigned long long *__restrict__ out,
                                                volatile unsigned long long *status, unsigned int *tile_counter,
-                                               int tiles_per_filter, unsigned long long *totals,
-                                               double *sumsq /* optional: sum of (v 2^-52)^2 */,
-                                               unsigned long long *deficit = nullptr /* optional: 2^52 - total */,
-                                               unsigned long long *sqlimbs = nullptr /* optional: exact integer
-                                                   sum of (v >> 20)^2 as [low 32 bits, high bits] (neff_fixed) */)
+                                               int tiles_per_filter, unsigned long long *totals)
 {
     __shared__ unsigned int s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
@@ -890,21 +712,10 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
 
     unsigned long long v[kScanItems];
     unsigned long long tsum = 0;
-    double sq = 0.0;
-    unsigned long long sq_lo = 0, sq_hi = 0;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         v[k] = (i0 + k < M) ? value(base + i0 + k, f, k) : 0ull;
         tsum += v[k];
-        if (sumsq) {
-            double w = (double)v[k] * 2.220446049250313e-16;
-            sq += w * w;
-        }
-        if (sqlimbs) {
-            const unsigned long long s2 = neff_square(v[k]);
-            sq_lo += s2 & 0xFFFFFFFFull;
-            sq_hi += s2 >> 32;
-        }
     }
     // block exclusive scan of per-thread sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -967,762 +778,31 @@ __device__ __forceinline__ void scan_tile_body(ValueFn value, int64_t M, unsigne
     }
     __syncthreads();
     unsigned long long acc = s_prefix + excl;
-    if (totals && threadIdx.x == 0 && tile == tiles_per_filter - 1) {
-        totals[f] = s_prefix + block_total;
-        if (deficit) deficit[f] = (1ull << kQBits) - (s_prefix + block_total);
-    }
+    if (totals && threadIdx.x == 0 && tile == tiles_per_filter - 1) totals[f] = s_prefix + block_total;
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         acc += v[k];
         if (i0 + k < M) out[base + i0 + k] = acc;
     }
-    if (sumsq) {
-        sq = warp_sum_f64(sq);
-        if (lane == 0) atomicAdd(sumsq + f, sq);
-    }
-    if (sqlimbs) {      // integer atomics: the sum does not depend on the order the tiles arrive in
-        sq_lo = warp_sum_u64(sq_lo);
-        sq_hi = warp_sum_u64(sq_hi);
-        if (lane == 0) {
-            if (sq_lo) atomicAdd(sqlimbs + 2 * f, sq_lo);
-            if (sq_hi) atomicAdd(sqlimbs + 2 * f + 1, sq_hi);
-        }
-    }
-}
-
-// stage 3: q_i = floor(a_i 2^52 / A); inclusive integer CDF (raw: before the deficit units).
-// After the kernel every tile's status word holds its inclusive prefix: the tile table that the
-// select kernel searches first.  `deficit` (optional) = 2^52 - Q, written with the total.
-__global__ void __launch_bounds__(kThreads)
-k_scan_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A, unsigned long long *cdf,
-         unsigned long long *status, unsigned int *tile_counter, int tiles_per_filter, unsigned long long *Q,
-         double *sumsq, unsigned long long *deficit, const int *degenerate)
-{
-    int cached_f = -1;          // a tile belongs to one filter: the divisor is set up once per thread
-    QDiv d{};
-    double m = 0.0;
-    bool dead = false;
-    auto value = [&](int64_t row, int f, int) -> unsigned long long {
-        if (f != cached_f) {
-            cached_f = f;
-            d = make_qdiv(A[2 * f], A[2 * f + 1]);
-            m = wmax[f];
-            dead = degenerate && degenerate[f];
-        }
-        return dead ? 0ull : q_from_a(src_a(w, row, m), d);
-    };
-    scan_tile_body(value, M, cdf, status, tile_counter, tiles_per_filter, Q, sumsq, deficit);
-}
-
-// Single-GPU stage 3 WITHOUT look-back: q_i = floor(a_i 2^52 / A) stored in place of a_i, one sum per tile;
-// the LAST block of a filter (ticket) turns the filter's tile sums into the tile table (inclusive
-// prefixes) and writes Q and the deficit.  The prefix INSIDE a tile is not stored: k_select_gather walks
-// whole tiles anyway and rebuilds it with one block scan per tile.  This is a streaming kernel -- in the
-// look-back scan the spin on the predecessors' status words and its barriers were ~40 % of the stall
-// samples, and a tile lived for ~14 us at 16 M particles.  (The particle-sharded filter keeps the
-// look-back scan k_scan_q: its peers read a finished CDF.)
-__global__ void __launch_bounds__(kThreads, 4)
-k_quotients(int64_t M, const unsigned long long *A, unsigned long long *qv, unsigned long long *table,
-            unsigned int *done, int tiles_per_filter, unsigned long long *Q, unsigned long long *deficit,
-            const int *degenerate, unsigned long long *sqlimbs)
-{
-    __shared__ unsigned long long s_w[kThreads / 32], s_lo[kThreads / 32], s_hi[kThreads / 32];
-    __shared__ bool s_last;
-    const int f = blockIdx.x / tiles_per_filter, tile = blockIdx.x % tiles_per_filter;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t row0 = (int64_t)f * M + (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems;
-    const int64_t left = M - ((int64_t)tile * kScanTile + (int64_t)threadIdx.x * kScanItems);
-    const bool vec = left >= kScanItems && (row0 & 1) == 0;
-    unsigned long long v[kScanItems];
-    if (vec) {
-#pragma unroll
-        for (int k = 0; k < kScanItems; k += 2) {
-            const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(qv + row0 + k);
-            v[k] = t.x;
-            v[k + 1] = t.y;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k) v[k] = k < left ? qv[row0 + k] : 0ull;
-    }
-    const QDiv d = make_qdiv(A[2 * f], A[2 * f + 1]);
-    const bool dead = degenerate[f] != 0;
-    unsigned long long tsum = 0, sq_lo = 0, sq_hi = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        v[k] = dead ? 0ull : q_from_a(v[k], d);
-        tsum += v[k];
-        const unsigned long long s2 = neff_square(v[k]);
-        sq_lo += s2 & 0xFFFFFFFFull;
-        sq_hi += s2 >> 32;
-    }
-    if (vec) {
-#pragma unroll
-        for (int k = 0; k < kScanItems; k += 2)
-            *reinterpret_cast<ulonglong2 *>(qv + row0 + k) = make_ulonglong2(v[k], v[k + 1]);
-    } else {
-#pragma unroll
-        for (int k = 0; k < kScanItems; ++k)
-            if (k < left) qv[row0 + k] = v[k];
-    }
-    tsum = warp_sum_u64(tsum);
-    sq_lo = warp_sum_u64(sq_lo);
-    sq_hi = warp_sum_u64(sq_hi);
-    if (lane == 0) {
-        s_w[warp] = tsum;
-        s_lo[warp] = sq_lo;
-        s_hi[warp] = sq_hi;
-    }
-    __syncthreads();
-    unsigned long long *tab = table + (size_t)f * tiles_per_filter;
-    if (threadIdx.x == 0) {
-        unsigned long long tot = 0, lo = 0, hi = 0;
-#pragma unroll
-        for (int k = 0; k < kThreads / 32; ++k) {
-            tot += s_w[k];
-            lo += s_lo[k];
-            hi += s_hi[k];
-        }
-        if (lo) atomicAdd(sqlimbs + 2 * f, lo);            // integer atomics, two per block: independent of the arrival order
-        if (hi) atomicAdd(sqlimbs + 2 * f + 1, hi);
-        tab[tile] = tot;
-        __threadfence();
-        s_last = atomicAdd(done + f, 1u) == (unsigned int)tiles_per_filter - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // the filter's tile sums -> inclusive prefixes, in place: a run of consecutive tiles per thread
-    const int per = (tiles_per_filter + kThreads - 1) / kThreads;
-    const int t0 = threadIdx.x * per;
-    unsigned long long run = 0;
-    for (int k = 0; k < per; ++k)
-        if (t0 + k < tiles_per_filter) run += *reinterpret_cast<volatile unsigned long long *>(tab + t0 + k);
-    unsigned long long incl = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-    }
-    __syncthreads();                                   // s_w is reused
-    if (lane == 31) s_w[warp] = incl;
-    __syncthreads();
-    unsigned long long acc = incl - run, total = 0;
-#pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) {
-        if (k < warp) acc += s_w[k];
-        total += s_w[k];
-    }
-    for (int k = 0; k < per; ++k)
-        if (t0 + k < tiles_per_filter) {
-            acc += *reinterpret_cast<volatile unsigned long long *>(tab + t0 + k);
-            tab[t0 + k] = acc;
-        }
-    if (threadIdx.x == 0) {
-        Q[f] = total;
-        deficit[f] = (1ull << kQBits) - total;
-        done[f] = 0u;
-    }
-}
-
-// q_i itself (parity read-back): q_i + (i_global < D)
-__global__ void __launch_bounds__(kThreads)
-k_emit_q(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A, const unsigned long long *deficit,
-         int64_t global_offset, unsigned long long *q_out)
-{
-    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (i >= M) return;
-    int f = blockIdx.y;
-    int64_t row = (int64_t)f * M + i;
-    unsigned long long q = q_from_a(src_a(w, row, wmax[f]), A[2 * f], A[2 * f + 1]);
-    q_out[row] = q + (((unsigned long long)(global_offset + i) < deficit[f]) ? 1ull : 0ull);
-}
-
-// sum_i (q_i 2^-52)^2 of the raw quotients (auvpf_neff = 1 / that), recomputed from the weight source on
-// request: the fused scan no longer carries this float64 reduction in the filter cycle
-__global__ void __launch_bounds__(kThreads)
-k_sumsq_from_src(WeightSrc w, int64_t M, const double *wmax, const unsigned long long *A, const int *degenerate,
-                 double *sumsq)
-{
-    const int f = blockIdx.y;
-    if (degenerate[f]) return;
-    const QDiv d = make_qdiv(A[2 * f], A[2 * f + 1]);
-    const double m = wmax[f];
-    double sq = 0.0;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
-        const double v = (double)q_from_a(src_a(w, (int64_t)f * M + i, m), d) * 2.220446049250313e-16;
-        sq += v * v;
-    }
-    sq = warp_sum_f64(sq);
-    if ((threadIdx.x & 31) == 0) atomicAdd(sumsq + f, sq);
 }
 
 // ---------------------------------------------------------------------------------------------
-// stage 4: systematic ancestor select (a7) + particle gather (a8, sorted form) + roughening (a9).
-// Output slot i (global) finds the first particle j with positions[i] < cdf[j]
-// (resampling.py:161-167).  A block owns kSelTile consecutive outputs; their ancestors form a
-// contiguous CDF interval that is staged in shared memory and searched there.
+// Shapes shared with the select kernel (auvpf_resample.cuh): a block owns kSelTile consecutive output slots,
+// a thread kSelItems adjacent ones.
 constexpr int kSelThreads = 256;  // (128 threads x 2 groups, one wave of 7 blocks per SM, measured 30 % slower)
 constexpr int kSelItems = 4;      // adjacent outputs a thread resolves together
-constexpr int kSelGroups = 1;     // groups of kSelItems per thread
-constexpr int kSelTile = kSelThreads * kSelItems * kSelGroups;
-constexpr int kSelSpan = 2 * kScanTile;   // CDF entries staged per block by the peer-memory variant: two scan tiles (32 KB)
-constexpr int kSrcItems = 8;              // consecutive source particles per thread and pass of k_select_gather
-
-struct SelectParams {
-    int64_t M;             // local particles per filter (CDF length)
-    int64_t n_global;      // N of positions = (u + i) / N
-    int64_t j_global0;     // global id of local particle 0
-    int64_t out_lo;        // first global output slot emitted by this launch
-    int64_t n_out;         // outputs per filter emitted by this launch
-    unsigned long long q_offset;   // integer CDF mass of lower shards
-    int tiles_per_filter;  // scan tiles per filter (tile table = the scan's status words)
-};
-
-
-// Integer form of the reference's comparison positions[i] < cumsum[j] (resampling.py:163):
-// cumsum[j] = c 2^-52 exactly and pos 2^52 is an exact float64, so  pos < c 2^-52  <=>
-// floor(pos 2^52) < c.  The search therefore runs on 64-bit integers.
-__device__ __forceinline__ unsigned long long pos_key(double pos)
-{
-    return (unsigned long long)floor(pos * 4503599627370496.0);
-}
-
-__device__ __forceinline__ unsigned long long full_cdf(const unsigned long long *cdf, int64_t j, const SelectParams &p,
-                                                       unsigned long long D)
-{
-    unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
-    return p.q_offset + cdf[j] + (jg1 < D ? jg1 : D);
-}
-
-// first j in [lo, hi) with key < cdf(j); hi if none
-__device__ __forceinline__ int64_t search_cdf(const unsigned long long *cdf, int64_t lo, int64_t hi,
-                                              unsigned long long key, const SelectParams &p, unsigned long long D)
-{
-    while (lo < hi) {
-        int64_t mid = (lo + hi) >> 1;
-        if (key < full_cdf(cdf, mid, p, D)) hi = mid;
-        else lo = mid + 1;
-    }
-    return lo;
-}
-
-// N_eff gate (auv_pf.py:174-181, commented out in the reference): with thresh = ratio * N > 0 a
-// filter whose neff_fixed (auvpf_math.cuh) is NOT below thresh skips the resample -- its state is
-// carried over unchanged, exactly like a filter without any finite weight.  Every block evaluates
-// the same integers, so the decision is uniform over the grid; block 0 records it in skipped[f].
-struct NeffGate {
-    const unsigned long long *sqlimbs;   // [2F] left by the scan; nullptr = no gate
-    double thresh;                       // ratio * N; 0 = always resample
-    int *skipped;                        // [F] out
-};
-
+constexpr int kSelTile = kSelThreads * kSelItems;
+constexpr int kMaxPeers = 8;      // ranks of one sharded filter (one node)
 #ifndef AUVPF_SEL_MINB
-#define AUVPF_SEL_MINB 4     // resident blocks per SM the select kernel is compiled for (tuning builds override)
+#define AUVPF_SEL_MINB 4          // resident blocks per SM the select kernel is compiled for (tuning builds override)
 #endif
-template <bool kRecords>
-__global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB)
-k_select_gather(const unsigned long long *__restrict__ cdf_all, SelectParams p, const double *__restrict__ u_all,
-                const unsigned long long *__restrict__ deficit, StateView src, StateView dst, Record *records,
-                int32_t *anc32, int64_t *anc64, NoiseParams rough, const float *rough_noise,
-                const unsigned long long *__restrict__ tile_table, const int *__restrict__ degenerate,
-                NeffGate gate)
-{
-    __shared__ int s_head[kSelTile];              // output slot -> 1 + (first ancestor whose run of offspring starts there - j_lo), else 0
-    __shared__ int s_wmax[kSelThreads / 32];
-    __shared__ int s_t[2];
-    __shared__ unsigned long long s_wsum[2][kSelThreads / 32];
-    const int f = blockIdx.y;
-    const unsigned long long *cdf = cdf_all + (size_t)f * p.M;
-    const unsigned long long D = deficit[f];
-    const double u = u_all[f], n = (double)p.n_global;
-    const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
-    if (k0 >= p.n_out) return;
-    const int64_t k1 = min(k0 + (int64_t)kSelTile, p.n_out) - 1;
-    bool gated = false;
-    if (gate.sqlimbs) {
-        gated = gate.thresh > 0.0 && neff_fixed(gate.sqlimbs[2 * f], gate.sqlimbs[2 * f + 1]) >= gate.thresh;
-        if (blockIdx.x == 0 && threadIdx.x == 0) gate.skipped[f] = gated ? 1 : 0;
-    }
-    if ((degenerate && degenerate[f]) || gated) {
-        // no finite weight in this filter (or the N_eff gate holds the resample back): its state is
-        // carried over unchanged (identity ancestors), so the buffers can flip without the host
-        // having to look at the flag first
-        if (!kRecords && (dst.x != nullptr || anc32 != nullptr) && p.n_out == p.M)
-            for (int64_t k = k0 + threadIdx.x; k <= k1; k += kSelThreads) {
-                const int64_t row = (int64_t)f * p.M + k;
-                if (dst.x != nullptr) {
-                    dst.x[row] = src.x[row];
-                    dst.y[row] = src.y[row];
-                    dst.z[row] = src.z[row];
-                    dst.roll[row] = src.roll[row];
-                    dst.pitch[row] = src.pitch[row];
-                    dst.yaw[row] = src.yaw[row];
-                }
-                if (anc32) anc32[row] = (int32_t)k;
-            }
-        return;
-    }
-    // Level 1: the scan tiles holding the ancestors of the block's first (warp 0) and last (warp 1) output:
-    // a 32-ary search of the tile table (inclusive prefix per tile, left in the status words by the scan) --
-    // 32 evenly spaced entries per step, one ballot -- so 1024 tiles take two dependent loads.  While the
-    // two warps search, everybody clears the run heads; ONE barrier publishes both.
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int r = 0; r < kSelItems; ++r) s_head[threadIdx.x * kSelItems + r] = 0;
-    if (warp < 2) {
-        const unsigned long long key = pos_key(sys_position(u, p.out_lo + (warp == 0 ? k0 : k1), n));
-        const unsigned long long *tab = tile_table + (size_t)f * p.tiles_per_filter;
-        int lo = 0, hi = p.tiles_per_filter;           // tiles [0, lo) end at or below the key, tile hi (if any) above
-        while (lo < hi) {
-            const int step = (hi - lo + 31) >> 5;
-            const int t = lo + (lane + 1) * step - 1;  // last tile of this lane's chunk
-            bool below = false;
-            if (t < hi) {
-                const int64_t je = min((int64_t)(t + 1) * kScanTile, p.M) - 1;
-                const unsigned long long jg1 = (unsigned long long)(p.j_global0 + je + 1);
-                const unsigned long long c = p.q_offset + (tab[t] & kValMask) + (jg1 < D ? jg1 : D);
-                below = !(key < c);
-            }
-            const int nb = __popc(__ballot_sync(0xffffffffu, below));   // monotone table: a prefix of the lanes
-            lo += nb * step;
-            hi = min(lo + step - 1, hi);               // the chunk's last tile is known to lie above (or past the end)
-        }
-        if (lane == 0) s_t[warp] = min(lo, p.tiles_per_filter - 1);
-    }
-    __syncthreads();
-    const int t_lo = s_t[0], t_hi = s_t[1];
-    // Level 2, from the SOURCE side: output slot i descends from particle j iff
-    //   count_below(cdf[j-1]) <= i < count_below(cdf[j]),   count_below(c) = #{i : positions[i] < c}
-    // (positions and the CDF are both non-decreasing), and count_below is a closed form
-    // (sys_count_below: one fma + ceil; the reference's own expression only when the estimate is within
-    // 1e-5 of an integer).  So the block walks the particles of the located tiles once -- coalesced
-    // 128-bit loads, kSrcItems consecutive particles per thread -- and every particle that has offspring
-    // in this block marks the slot where its run starts; an inclusive max-scan over the slots then
-    // names every output's ancestor.  No position is evaluated per output and nothing is searched.
-    // (The previous version staged the tiles' CDF in shared memory and ran a binary search + short walk
-    // per output: 458 thread instructions per particle, ncu.)
-    const int64_t j_lo = (int64_t)t_lo * kScanTile, j_hi = min((int64_t)(t_hi + 1) * kScanTile, p.M) - 1;
-    const int nblk = (int)(k1 - k0 + 1);
-    const int64_t g0 = p.out_lo + k0;                  // global index of the block's first output
-    const SysPos spos = make_sys_pos(u, n);
-    // block-relative end of source j's run (rel_end_of, auvpf_math.cuh): clamp(count_below(cdf[j]) - g0, 0, nblk)
-    const RelEndCtx rctx = make_rel_end(u, n, g0, nblk);
-    const int64_t j_last = p.n_global - 1 - p.j_global0;      // local index of the filter's last particle (>= M on the other shards)
-    auto rel_end = [&](unsigned long long cdfv, int64_t j) -> int {
-        const unsigned long long jg1 = (unsigned long long)(p.j_global0 + j + 1);
-        return rel_end_of(spos, p.n_global, rctx, p.q_offset + cdfv + (jg1 < D ? jg1 : D));
-    };
-    // kRecords (a shard of a particle-sharded filter): `cdf` holds the finished inclusive CDF of the look-back
-    // scan.  Otherwise (single GPU) it holds the raw quotients k_quotients left, and the inclusive prefix of
-    // a tile is rebuilt here -- one pass walks exactly one scan tile -- from the tile table's prefix of the
-    // tile before, a thread-local running sum, a warp shuffle scan and the warps' totals (one barrier).
-    static_assert(kSelThreads * kSrcItems == kScanTile, "one pass of the source walk = one scan tile");
-    const unsigned long long *tab2 = tile_table + (size_t)f * p.tiles_per_filter;
-    for (int64_t jb = j_lo; jb <= j_hi; jb += (int64_t)kSelThreads * kSrcItems) {
-        const int64_t tile = jb / kScanTile;
-        const unsigned long long tile_excl = (!kRecords && tile > 0) ? (tab2[tile - 1] & kValMask) : 0ull;
-        // all the outputs of the block are handed out once the pass's first particle already ends at nblk
-        // (block-uniform: every thread evaluates the same entry)
-        if (jb > j_lo && rel_end(kRecords ? cdf[jb - 1] : tile_excl, jb - 1) >= nblk) break;
-        const int64_t j0 = jb + (int64_t)threadIdx.x * kSrcItems;
-        unsigned long long cv[kSrcItems];
-        const bool has_prev = lane == 0 && j0 > j_lo && j0 - 1 <= j_hi;
-        unsigned long long cprev = (kRecords && has_prev) ? cdf[j0 - 1] : 0ull;   // in flight with the thread's own entries
-        if (j0 + kSrcItems - 1 <= j_hi && ((reinterpret_cast<uintptr_t>(cdf + j0) & 15) == 0)) {
-#pragma unroll
-            for (int k = 0; k < kSrcItems; k += 2) {
-                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(cdf + j0 + k);
-                cv[k] = t.x;
-                cv[k + 1] = t.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kSrcItems; ++k) cv[k] = j0 + k <= j_hi ? cdf[j0 + k] : 0ull;
-        }
-        if (!kRecords) {
-            unsigned long long run = 0;
-#pragma unroll
-            for (int k = 0; k < kSrcItems; ++k) {
-                run += cv[k];
-                cv[k] = run;
-            }
-            unsigned long long incl = run;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            unsigned long long *ws = s_wsum[tile & 1];      // two buffers: no barrier between consecutive passes
-            if (lane == 31) ws[warp] = incl;
-            __syncthreads();
-            unsigned long long before = tile_excl + (incl - run);
-#pragma unroll
-            for (int k = 0; k < kSelThreads / 32; ++k)
-                if (k < warp) before += ws[k];
-#pragma unroll
-            for (int k = 0; k < kSrcItems; ++k) cv[k] += before;
-            cprev = before;                                   // the CDF just before this thread's first particle
-        }
-        // the ends are non-decreasing in j: a thread whose LAST particle ends at 0 lies before the block, one
-        // whose FIRST particle ends at nblk lies behind it; only threads across the block evaluate all
-        int e[kSrcItems];
-        const bool whole = j0 + kSrcItems - 1 <= j_hi;
-        const int e_last = whole ? rel_end(cv[kSrcItems - 1], j0 + kSrcItems - 1) : nblk;
-        const int e_first = (e_last == 0) ? 0 : (j0 <= j_hi ? rel_end(cv[0], j0) : nblk);
-        if (e_last == 0 || e_first == nblk) {
-#pragma unroll
-            for (int k = 0; k < kSrcItems; ++k) e[k] = e_first;
-        } else {
-            e[0] = e_first;
-#pragma unroll
-            for (int k = 1; k < kSrcItems - 1; ++k) e[k] = j0 + k <= j_hi ? rel_end(cv[k], j0 + k) : nblk;
-            e[kSrcItems - 1] = e_last;
-        }
-        // The filter's LAST particle ends where the outputs end, whatever its CDF value says: for
-        // u >= 1 - N 2^-54 the last position rounds to 1.0 = cumsum[-1], the reference walks off the end
-        // (IndexError, resampling.py:162-167), and every path here -- this kernel, its records form and
-        // k_select_gather_p2p's clamp -- gives that output to the last particle.
-#pragma unroll
-        for (int k = 0; k < kSrcItems; ++k)
-            if (j0 + k == j_last) e[k] = nblk;
-        // where this thread's first run starts = where the previous particle's run ends: the lane below
-        // has it; lane 0 evaluates the particle before its own (no block barrier for the hand-over), and
-        // the block's first located particle starts at slot 0
-        int start = __shfl_up_sync(0xffffffffu, e[kSrcItems - 1], 1);
-        if (lane == 0) start = has_prev ? rel_end(cprev, j0 - 1) : (j0 > j_lo ? nblk : 0);
-#pragma unroll
-        for (int k = 0; k < kSrcItems; ++k) {
-            if (e[k] > start) s_head[start] = (int)(j0 + k - j_lo) + 1;   // starts are distinct: one writer per slot
-            start = e[k];
-        }
-    }
-    __syncthreads();
-    // inclusive max-scan of the run heads (ancestor indices increase with the slot): thread-local over its
-    // kSelItems adjacent outputs, warp shuffle, then the warps' maxima
-    int head[kSelItems];
-    {
-        int m = 0;
-#pragma unroll
-        for (int r = 0; r < kSelItems; ++r) {
-            m = max(m, s_head[threadIdx.x * kSelItems + r]);
-            head[r] = m;
-        }
-        int incl = m;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl = max(incl, t);
-        }
-        int pre = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) pre = 0;
-        if (lane == 31) s_wmax[warp] = incl;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < kSelThreads / 32; ++k)
-            if (k < warp) pre = max(pre, s_wmax[k]);
-#pragma unroll
-        for (int r = 0; r < kSelItems; ++r) head[r] = max(head[r], pre);
-    }
-    const int64_t kb = k0 + (int64_t)threadIdx.x * kSelItems;
-    if (kb > k1) return;
-    int64_t jj[kSelItems];
-#pragma unroll
-    for (int r = 0; r < kSelItems; ++r)               // (a slot before every head cannot occur: the first located particle
-        jj[r] = min(j_lo + max(head[r] - 1, 0), p.M - 1);   //  with offspring here starts at slot 0; the clamp mirrors the old code)
-    {
-    const int64_t orow0 = (int64_t)f * p.n_out + kb;
-    const bool full4 = kb + kSelItems - 1 <= k1;
-    double x[kSelItems], y[kSelItems];
-    float z[kSelItems], ro[kSelItems], pi[kSelItems], ya[kSelItems];
-#pragma unroll
-    for (int r = 0; r < kSelItems; ++r) {
-        const int64_t srow = (int64_t)f * p.M + jj[r];
-        x[r] = src.x[srow];
-        y[r] = src.y[srow];
-        z[r] = src.z[srow];
-        ro[r] = src.roll[srow];
-        pi[r] = src.pitch[srow];
-        ya[r] = src.yaw[srow];
-    }
-    if (anc32) {
-        if (full4 && (orow0 & 3) == 0)
-            *reinterpret_cast<int4 *>(anc32 + orow0) = make_int4((int)jj[0], (int)jj[1], (int)jj[2], (int)jj[3]);
-        else
-            for (int r = 0; r < kSelItems && kb + r <= k1; ++r) anc32[orow0 + r] = (int32_t)jj[r];
-    }
-    if (anc64)
-        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) anc64[orow0 + r] = p.j_global0 + jj[r];
-    if (kRecords) {
-        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) {
-            Record rec = {x[r], y[r], z[r], ro[r], pi[r], ya[r]};
-            records[orow0 + r] = rec;
-        }
-        return;
-    }
-    if (dst.x == nullptr) return;
-    if (rough.mode == 1) {       // fused add_noise (auv_pf.py:191-192)
-#pragma unroll
-        for (int r = 0; r < kSelItems; ++r) {
-            if (kb + r > k1) break;
-            float nn[6];
-            six_normals(rough, (int64_t)f * rough.global_stride + p.out_lo + kb + r, rough_noise, orow0 + r, nn);
-            x[r] += (double)(rough.sigma[0] * nn[0]);
-            y[r] += (double)(rough.sigma[1] * nn[1]);
-            z[r] += rough.sigma[2] * nn[2];
-            ro[r] += rough.sigma[3] * nn[3];
-            pi[r] += rough.sigma[4] * nn[4];
-            ya[r] += rough.sigma[5] * nn[5];
-        }
-    }
-    if (full4 && (orow0 & 3) == 0) {
-        *reinterpret_cast<double2 *>(dst.x + orow0) = make_double2(x[0], x[1]);
-        *reinterpret_cast<double2 *>(dst.x + orow0 + 2) = make_double2(x[2], x[3]);
-        *reinterpret_cast<double2 *>(dst.y + orow0) = make_double2(y[0], y[1]);
-        *reinterpret_cast<double2 *>(dst.y + orow0 + 2) = make_double2(y[2], y[3]);
-        *reinterpret_cast<float4 *>(dst.z + orow0) = make_float4(z[0], z[1], z[2], z[3]);
-        *reinterpret_cast<float4 *>(dst.roll + orow0) = make_float4(ro[0], ro[1], ro[2], ro[3]);
-        *reinterpret_cast<float4 *>(dst.pitch + orow0) = make_float4(pi[0], pi[1], pi[2], pi[3]);
-        *reinterpret_cast<float4 *>(dst.yaw + orow0) = make_float4(ya[0], ya[1], ya[2], ya[3]);
-    } else {
-        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) {
-            dst.x[orow0 + r] = x[r];
-            dst.y[orow0 + r] = y[r];
-            dst.z[orow0 + r] = z[r];
-            dst.roll[orow0 + r] = ro[r];
-            dst.pitch[orow0 + r] = pi[r];
-            dst.yaw[orow0 + r] = ya[r];
-        }
-    }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Particle-sharded filter: select + gather + exchange in ONE kernel over NVLink peer memory.
-// Every rank maps the other ranks' slabs (state, integer CDF, scan tile table) through CUDA IPC.
-// Output slot i of rank r finds its ancestor in the GLOBAL CDF -- the concatenation of the shards'
-// CDFs, each shifted by the integer mass of the shards before it -- by reading the owners' tile
-// tables and CDF tiles directly, then loads the ancestor's state from its owner's memory and writes
-// its own new state: no records, no all-to-all, no host in the loop.  (Ancestors are globally
-// sorted, so a block's reads are contiguous runs in at most a few shards.)
-constexpr int kMaxPeers = 8;
-
-struct PeerTable {
-    const unsigned long long *cdf[kMaxPeers];
-    const unsigned long long *status[kMaxPeers];
-    StateView st[kMaxPeers];            // the buffer that is CURRENT (source of the gather) on each rank
-    int G;
-};
-
-// meta[0..G) = integer CDF mass below shard g, meta[G] = deficit D, meta[G+1] = 1 if no shard has weight
-__global__ void k_shard_meta(const long long *q_all, int G, unsigned long long *meta)
-{
-    if (threadIdx.x || blockIdx.x) return;
-    unsigned long long acc = 0;
-    for (int g = 0; g < G; ++g) {
-        meta[g] = acc;
-        acc += (unsigned long long)q_all[g];
-    }
-    meta[G] = (1ull << kQBits) - acc;
-    meta[G + 1] = acc == 0 ? 1ull : 0ull;
-}
-
-struct GlobalCdf {
-    const PeerTable *pt;
-    const unsigned long long *meta;
-    int64_t M;
-    unsigned long long D;
-    __device__ __forceinline__ unsigned long long at(int64_t J) const
-    {
-        int g = (int)(J / M);
-        const int64_t j = J - (int64_t)g * M;
-        const unsigned long long J1 = (unsigned long long)(J + 1);
-        return meta[g] + pt->cdf[g][j] + (J1 < D ? J1 : D);
-    }
-};
-
-__global__ void __launch_bounds__(kSelThreads, 4)
-k_select_gather_p2p(const PeerTable *__restrict__ pt, int64_t M, int rank, int tiles, double u,
-                    const unsigned long long *__restrict__ meta, StateView dst, int64_t *anc64, NoiseParams rough,
-                    const float *rough_noise)
-{
-    __shared__ unsigned long long s_cdf[kSelSpan];
-    __shared__ int64_t s_j[2];
-    const int G = pt->G;
-    const int64_t n_global = M * G;
-    const double n = (double)n_global;
-    const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
-    if (k0 >= M) return;
-    const int64_t k1 = min(k0 + (int64_t)kSelTile, M) - 1;
-    const int64_t out_lo = (int64_t)rank * M;
-    if (meta[G + 1]) {            // no finite weight on any shard: the state is carried over unchanged
-        const StateView own = pt->st[rank];
-        for (int64_t k = k0 + threadIdx.x; k <= k1; k += kSelThreads) {
-            dst.x[k] = own.x[k];
-            dst.y[k] = own.y[k];
-            dst.z[k] = own.z[k];
-            dst.roll[k] = own.roll[k];
-            dst.pitch[k] = own.pitch[k];
-            dst.yaw[k] = own.yaw[k];
-        }
-        return;
-    }
-    GlobalCdf gc;
-    gc.pt = pt;
-    gc.meta = meta;
-    gc.M = M;
-    gc.D = meta[G];
-    const unsigned long long D = gc.D;
-    const unsigned long long key_lo = pos_key(sys_position(u, out_lo + k0, n)),
-                             key_hi = pos_key(sys_position(u, out_lo + k1, n));
-    // level 1: the global tile table (G x tiles entries, read from the owners)
-    const int n_tiles = G * tiles;
-    int T_lo = 0, T_hi = 0;
-    for (int T0 = 0; T0 < n_tiles; T0 += kSelThreads) {
-        const int T = T0 + threadIdx.x;
-        bool below_lo = false, below_hi = false;
-        if (T < n_tiles) {
-            const int g = T / tiles, t = T - g * tiles;
-            const int64_t je = min((int64_t)(t + 1) * kScanTile, M) - 1;
-            const unsigned long long J1 = (unsigned long long)((int64_t)g * M + je + 1);
-            const unsigned long long c = meta[g] + (pt->status[g][t] & kValMask) + (J1 < D ? J1 : D);
-            below_lo = !(key_lo < c);
-            below_hi = !(key_hi < c);
-        }
-        const int c_lo = __syncthreads_count(below_lo), c_hi = __syncthreads_count(below_hi);
-        T_lo += c_lo;
-        T_hi += c_hi;
-        if (c_hi < kSelThreads) break;
-    }
-    T_lo = min(T_lo, n_tiles - 1);
-    T_hi = min(T_hi, n_tiles - 1);
-    int64_t J_lo = (int64_t)(T_lo / tiles) * M + (int64_t)(T_lo % tiles) * kScanTile;
-    int64_t J_hi = (int64_t)(T_hi / tiles) * M + min((int64_t)(T_hi % tiles + 1) * kScanTile, M) - 1;
-    if (J_hi - J_lo + 1 > kSelSpan) {
-        if (threadIdx.x == 0 || threadIdx.x == 32) {
-            const unsigned long long key = threadIdx.x == 0 ? key_lo : key_hi;
-            int64_t lo = J_lo, hi = J_hi + 1;
-            while (lo < hi) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (key < gc.at(mid)) hi = mid;
-                else lo = mid + 1;
-            }
-            s_j[threadIdx.x == 0 ? 0 : 1] = lo;
-        }
-        __syncthreads();
-        J_lo = min(s_j[0], n_global - 1);
-        J_hi = min(s_j[1], n_global - 1);
-    }
-    const int64_t span = J_hi - J_lo + 1;
-    const bool staged = span <= kSelSpan;
-    if (staged)
-        for (int64_t t = threadIdx.x; t < span; t += kSelThreads) s_cdf[t] = gc.at(J_lo + t);
-    __syncthreads();
-
-    const int64_t kb = k0 + (int64_t)threadIdx.x * kSelItems;
-    if (kb > k1) return;
-    const SysPos spos = make_sys_pos(u, n);
-    int64_t JJ[kSelItems];
-    {
-        int64_t prev = 0;
-#pragma unroll
-        for (int r = 0; r < kSelItems; ++r) {
-            const int64_t k = kb + r;
-            if (k > k1) {
-                JJ[r] = 0;
-                continue;
-            }
-            const unsigned long long key = pos_key(sys_position(spos, out_lo + k));
-            int64_t J;
-            if (staged) {
-                int lo = (int)prev, hi = (int)span;
-                if (r > 0) {
-                    int w = 0;
-                    while (w < 4 && lo < hi && !(key < s_cdf[lo])) {
-                        ++lo;
-                        ++w;
-                    }
-                    if (lo < hi && key < s_cdf[lo]) hi = lo;
-                }
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (key < s_cdf[mid]) hi = mid;
-                    else lo = mid + 1;
-                }
-                prev = lo;
-                J = J_lo + lo;
-            } else {
-                int64_t lo = J_lo + prev, hi = J_hi + 1;
-                while (lo < hi) {
-                    const int64_t mid = (lo + hi) >> 1;
-                    if (key < gc.at(mid)) hi = mid;
-                    else lo = mid + 1;
-                }
-                J = lo;
-                prev = J - J_lo;
-            }
-            JJ[r] = min(J, n_global - 1);
-        }
-    }
-    const bool full4 = kb + kSelItems - 1 <= k1;
-    double x[kSelItems], y[kSelItems];
-    float z[kSelItems], ro[kSelItems], pi[kSelItems], ya[kSelItems];
-#pragma unroll
-    for (int r = 0; r < kSelItems; ++r) {
-        const int g = (int)(JJ[r] / M);
-        const int64_t j = JJ[r] - (int64_t)g * M;
-        const StateView src = pt->st[g];                 // the owner's memory: local or over NVLink
-        x[r] = src.x[j];
-        y[r] = src.y[j];
-        z[r] = src.z[j];
-        ro[r] = src.roll[j];
-        pi[r] = src.pitch[j];
-        ya[r] = src.yaw[j];
-    }
-    if (anc64)
-        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) anc64[kb + r] = JJ[r];
-    if (rough.mode == 1) {
-#pragma unroll
-        for (int r = 0; r < kSelItems; ++r) {
-            if (kb + r > k1) break;
-            float nn[6];
-            six_normals(rough, out_lo + kb + r, rough_noise, kb + r, nn);
-            x[r] += (double)(rough.sigma[0] * nn[0]);
-            y[r] += (double)(rough.sigma[1] * nn[1]);
-            z[r] += rough.sigma[2] * nn[2];
-            ro[r] += rough.sigma[3] * nn[3];
-            pi[r] += rough.sigma[4] * nn[4];
-            ya[r] += rough.sigma[5] * nn[5];
-        }
-    }
-    if (full4 && (kb & 3) == 0) {
-        *reinterpret_cast<double2 *>(dst.x + kb) = make_double2(x[0], x[1]);
-        *reinterpret_cast<double2 *>(dst.x + kb + 2) = make_double2(x[2], x[3]);
-        *reinterpret_cast<double2 *>(dst.y + kb) = make_double2(y[0], y[1]);
-        *reinterpret_cast<double2 *>(dst.y + kb + 2) = make_double2(y[2], y[3]);
-        *reinterpret_cast<float4 *>(dst.z + kb) = make_float4(z[0], z[1], z[2], z[3]);
-        *reinterpret_cast<float4 *>(dst.roll + kb) = make_float4(ro[0], ro[1], ro[2], ro[3]);
-        *reinterpret_cast<float4 *>(dst.pitch + kb) = make_float4(pi[0], pi[1], pi[2], pi[3]);
-        *reinterpret_cast<float4 *>(dst.yaw + kb) = make_float4(ya[0], ya[1], ya[2], ya[3]);
-    } else {
-        for (int r = 0; r < kSelItems && kb + r <= k1; ++r) {
-            dst.x[kb + r] = x[r];
-            dst.y[kb + r] = y[r];
-            dst.z[kb + r] = z[r];
-            dst.roll[kb + r] = ro[r];
-            dst.pitch[kb + r] = pi[r];
-            dst.yaw[kb + r] = ya[r];
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // residual_resample (a6, resampling.py:27-76) on the fixed-point weights w_i = q_i 2^-52.
-// q_i = the raw quotient k_quotients left behind + the deficit unit.
+// q_i as k_exact_q left it in `cdf` (the deficit D of the old formulation is always 0 now: sum q == 2^52).
 __device__ __forceinline__ unsigned long long q_from_cdf(const unsigned long long *cdf, int64_t base, int64_t i,
                                                         unsigned long long D, int64_t global_offset)
 {
-    // (the single-GPU stage 3, k_quotients, leaves the raw quotients themselves in this array)
     return cdf[base + i] + ((unsigned long long)(global_offset + i) < D ? 1ull : 0ull);
 }
 
@@ -1736,7 +816,7 @@ k_scan_copies(const unsigned long long *cdf, int64_t M, const unsigned long long
         const int64_t base = (int64_t)f * M;
         return residual_copies(q_from_cdf(cdf, base, row - base, deficit[f], global_offset), M);
     };
-    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals);
 }
 
 // inclusive scan of the fractional parts N w_i - k_i on the 2^-38 grid; totals = R per filter
@@ -1750,7 +830,7 @@ k_scan_fracs(const unsigned long long *cdf, int64_t M, const unsigned long long 
         const unsigned long long q = q_from_cdf(cdf, base, row - base, deficit[f], global_offset);
         return residual_frac(q, residual_copies(q, M), M);
     };
-    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals);
 }
 
 // first j in [0, M) with key < c[j]; M if none
@@ -1919,7 +999,7 @@ k_scan_lost(const int *first, int64_t M, unsigned long long *out, unsigned long 
             unsigned int *tile_counter, int tiles_per_filter, unsigned long long *totals)
 {
     auto value = [&](int64_t row, int, int) -> unsigned long long { return first[row] == kNoFirst ? 1ull : 0ull; };
-    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -1931,7 +1011,7 @@ k_scan_dupes(const int *first, const int32_t *idx, int64_t M, unsigned long long
         int j = idx[row];
         return first[base + j] != (int)(row - base) ? 1ull : 0ull;
     };
-    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals, nullptr);
+    scan_tile_body(value, M, out, status, tile_counter, tiles_per_filter, totals);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -2021,6 +1101,94 @@ __global__ void __launch_bounds__(kThreads) k_pose_stats(StateView s, int64_t M,
         stats[16 * f + 14] = cy;
         stats[16 * f + 15] = cz;
     }
+}
+
+// Estimate options: WEIGHTED by the current log-weights (w_i = exp(logw_i - max), float64) and / or
+// with the CIRCULAR yaw mean atan2(sum w sin yaw, sum w cos yaw) instead of the reference's arithmetic mean of
+// wrapped yaws (which is wrong for a cloud that straddles +-pi).  stats: F x 20 = [sum w, sum w d_xyz, sum w roll,
+// sum w pitch, sum w wrapped yaw, sum w sin yaw, sum w cos yaw, sum w d d^T (xx yy zz xy xz yz), c_xyz, unused].
+__global__ void __launch_bounds__(kThreads)
+k_pose_stats_w(StateView s, int64_t M, const float *__restrict__ logw, const int *__restrict__ wmax_f32, int weighted,
+               double *stats)
+{
+    const int f = blockIdx.y;
+    const int64_t base = (int64_t)f * M;
+    const double cx = s.x[base], cy = s.y[base], cz = (double)s.z[base];
+    double m = 0.0;
+    if (weighted) {
+        const int k = wmax_f32[f];
+        m = k > kWmaxReset ? (double)ordered_to_float(k) : 0.0;
+    }
+    double a[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        const int64_t row = base + i;
+        double w = 1.0;
+        if (weighted) {
+            const double x = (double)logw[row] - m;
+            w = x == x ? exp(x) : 0.0;
+        }
+        const double dx = s.x[row] - cx, dy = s.y[row] - cy, dz = (double)s.z[row] - cz;
+        const double yw = wrap_pi_d((double)s.yaw[row]);
+        double sy, cyw;
+        sincos(yw, &sy, &cyw);
+        a[0] += w;
+        a[1] += w * dx;
+        a[2] += w * dy;
+        a[3] += w * dz;
+        a[4] += w * (double)s.roll[row];
+        a[5] += w * (double)s.pitch[row];
+        a[6] += w * yw;
+        a[7] += w * sy;
+        a[8] += w * cyw;
+        a[9] += w * dx * dx;
+        a[10] += w * dy * dy;
+        a[11] += w * dz * dz;
+        a[12] += w * dx * dy;
+        a[13] += w * dx * dz;
+        a[14] += w * dy * dz;
+    }
+    __shared__ double s_part[kThreads / 32][15];
+#pragma unroll
+    for (int c = 0; c < 15; ++c) {
+        const double v = warp_sum_f64(a[c]);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 15) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) v += s_part[w][threadIdx.x];
+        atomicAdd(stats + 20 * f + threadIdx.x, v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        stats[20 * f + 15] = cx;
+        stats[20 * f + 16] = cy;
+        stats[20 * f + 17] = cz;
+    }
+}
+
+// The PoseArray of auv_pf.loc_loop (auv_pf.py:264-285) for a STRIDED subsample, built on the device: per
+// published particle [x, y, z, qx, qy, qz, qw] with quaternion_from_euler(roll, pitch, yaw) ('sxyz', :272-275).
+// Publishing every particle costs 48 MB per tick at 1 M particles; RViz shows a few thousand arrows.
+__global__ void __launch_bounds__(kThreads)
+k_pose_array(StateView s, int64_t M, int64_t stride, int64_t n, double *__restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= n) return;
+    const int f = blockIdx.y;
+    const int64_t row = (int64_t)f * M + min(k * stride, M - 1);
+    double sr, cr, sp, cp, sy, cy;
+    sincos(0.5 * (double)s.roll[row], &sr, &cr);
+    sincos(0.5 * (double)s.pitch[row], &sp, &cp);
+    sincos(0.5 * (double)s.yaw[row], &sy, &cy);
+    double *o = out + ((int64_t)f * n + k) * 7;
+    o[0] = s.x[row];
+    o[1] = s.y[row];
+    o[2] = (double)s.z[row];
+    o[3] = sr * cp * cy - cr * sp * sy;
+    o[4] = cr * sp * cy + sr * cp * sy;
+    o[5] = cr * cp * sy - sr * sp * cy;
+    o[6] = cr * cp * cy + sr * sp * sy;
 }
 
 // pack / unpack between the ABI's (n,6) float64 rows and the SoA state

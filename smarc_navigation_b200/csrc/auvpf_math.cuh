@@ -818,6 +818,41 @@ struct FanTables {
     float c0[3], a0[3];                      // fan centre / lateral unit vectors, sensor frame
 };
 
+// The profile curve of one side left the map footprint while beams of that side are still unresolved
+// (sensor closer to the border than its reach).  Those beams are clear of the terrain up to the lateral
+// distance p_clear the curve was marched to -- at equal p they are above it -- so each is finished on its
+// own: a ray clipped to the footprint (spec: no surface outside, a clipped ray that ends clear MISSES),
+// started at the certified clear prefix and walked the few cells that remain to the border.  The ray is
+// rebuilt from the float64 fan frame D (sensor in grid units, centre / lateral unit vectors):
+// dir = cos th c + sgn sin th a.
+template <class Sink>
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+void finish_side_by_rays(const DemView &m, const FanTables &T, const ProfFrameD *D, float sgf, int j, int n_side, int bb,
+                         int bstep, float p_clear, Sink &sink)
+{
+    const double fx = floor(D->gox), fy = floor(D->goy);
+    Ray r;
+    r.ix0 = (int)fx;
+    r.iy0 = (int)fy;
+    r.lx0 = (float)(D->gox - fx);
+    r.ly0 = (float)(D->goy - fy);
+    r.oz = (float)D->oz;
+    const double sg = (double)sgf;
+    for (; j < n_side; ++j, bb += bstep) {
+        const double tn = T.tan_t[bb], ct = 1.0 / T.sec_t[bb], st = tn * ct;
+        r.dgx = (float)(ct * D->cgx + sg * st * D->agx);
+        r.dgy = (float)(ct * D->cgy + sg * st * D->agy);
+        r.dz = (float)(ct * D->cz + sg * st * D->az);
+        const float t_lo = st > 0.0 ? sweep_bound(p_clear, (float)(1.0 / st)) : 0.f;
+        const float range = raycast_from(m, r, t_lo, false);
+        sink(bb, range, T.aux[bb].meas);
+    }
+}
+
 // Marches both sides of the fan, one after the other, inside ONE warp-uniform step loop (a lane
 // that finishes its first side starts its second while its neighbours are still on their first,
 // so the warp waits for the longest SUM of the two sides, not the sum of the longest).
@@ -856,6 +891,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     float p_f = 0.f, q_f = (float)S.q0;    // float32 copies of the two accumulators
     bool running = active && T.B > 0;
     bool ok = true;
+    int ex_j[2] = {-1, -1}, ex_bb[2] = {0, 0};     // a side whose curve ran off the map: first unresolved beam (count, index) ...
+    float ex_p[2] = {0.f, 0.f};                    // ... and the lateral distance the curve was marched to
     const int max_steps = 2 * (8 * (int)(m.range_max / m.res) + 256);
     float z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
     if (running) {
@@ -873,10 +910,11 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         if (!act) break;
         if (running) {
             bool fail = false;
+            const bool fresh = j < n_side;     // false only in the step after finish_side_by_rays: nothing left to march
             const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
             const float Dv = lower ? z11 - z01 : z10 - z00;
             const float gamma = F0.cz - F0.cgx * Du - F0.cgy * Dv;
-            if (!(gamma < -kGammaMin)) { AUVPF_REASON(0); fail = true; }
+            if (!(gamma < -kGammaMin) && fresh) { AUVPF_REASON(0); fail = true; }
             const float beta = sgf * (F0.agx * Du + F0.agy * Dv - F0.az);
             const float s = fast_div(beta, gamma);                // profile slope dT/dp
             const float X1 = fmaf(s, F0.cgx, sgf * F0.agx), Y1 = fmaf(s, F0.cgy, sgf * F0.agy);   // d(u,v)/dp
@@ -901,7 +939,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 bd = B1 - A1;
                 be = 2;
             }
-            if (be < 0 && !fail) { AUVPF_REASON(1); fail = true; }   // curve turns back through its entry edge
+            if (be < 0 && !fail && fresh) { AUVPF_REASON(1); fail = true; }   // curve turns back through its entry edge
             const float dp = fast_div(bn, bd);
             const float p_out_f = p_f + dp;
             // beams whose line meets the profile inside this segment.  gap = lateral distance of the
@@ -994,8 +1032,15 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 v = diag ? mid : (vedge ? nc : v);
                 if ((unsigned)cx > (unsigned)(m.W - 2) || (unsigned)cy > (unsigned)(m.H - 2)) {   // left the map
                     AUVPF_REASON(2);
-                    ok = false;
-                    running = false;
+                    // the rest of this side is finished ray by ray AFTER the march loop (finish_side_by_rays: a call
+                    // in here cost the hot loop 11 % through its register allocation); remember where it stopped
+                    ex_j[side] = j;
+                    ex_bb[side] = bb;
+                    ex_p[side] = p_f;
+                    j = n_side;                                    // the side switch happens in the next step
+                    cx = S.cx;                                     // (any cell inside the map: the step's loads stay in bounds)
+                    cy = S.cy;
+                    zi = cy * m.pitch + cx;
                 } else if (!diag) {
                     z00 = ldg_f(m.z + zi);
                     z01 = ldg_f(m.z + zi + 1);
@@ -1012,6 +1057,12 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         AUVPF_REASON(3);
         ok = false;
     }
+    if (ok && (ex_j[0] >= 0 || ex_j[1] >= 0)) {
+        for (int sd = 0; sd < 2; ++sd)
+            if (ex_j[sd] >= 0)
+                finish_side_by_rays(m, T, D, (float)(sd == 0 ? T.sgn1 : -T.sgn1), ex_j[sd], sd == 0 ? T.n1 : T.B - T.n1,
+                                    ex_bb[sd], sd == 0 ? -1 : 1, ex_p[sd], sink);
+    }
     return ok;
 }
 
@@ -1027,7 +1078,10 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
     bool ok = active;
     const double reach = (double)m.range_max;
     const double xmax = m.x0 + (double)(m.W - 1) * (double)m.res, ymax = m.y0 + (double)(m.H - 1) * (double)m.res;
-    if (!(p[0] - reach > m.x0 && p[0] + reach < xmax && p[1] - reach > m.y0 && p[1] + reach < ymax)) ok = false;
+    // the sensor must stand over the map; its REACH may leave it (the march finishes a side whose curve
+    // runs off the map ray by ray, finish_side_by_rays), the rays are then clipped to the footprint
+    if (!(p[0] > m.x0 && p[0] < xmax && p[1] > m.y0 && p[1] < ymax)) ok = false;
+    const bool interior = p[0] - reach > m.x0 && p[0] + reach < xmax && p[1] - reach > m.y0 && p[1] + reach < ymax;
     // centre beam from the sensor: q0 = T(0)
     float q0f = 0.f;
     if (ok) {
@@ -1035,7 +1089,7 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
         float lx0, ly0;
         origin_cell(m, p, ix0, iy0, lx0, ly0);
         Ray rc = make_ray(m, p, ix0, iy0, lx0, ly0, R, T.c0[0], T.c0[1], T.c0[2]);
-        q0f = raycast_from(m, rc, 0.f, true);
+        q0f = raycast_from(m, rc, 0.f, interior);
     }
     AUVPF_WARP_SYNC();
     bool all_zero = false;
@@ -1147,65 +1201,99 @@ AUVPF_HD uint64_t a_from_linear(double w, double wmax)
     return (uint64_t)floor(ldexp(w / wmax, kABits));
 }
 
-// q = floor(a * 2^52 / A), A given as two 64-bit halves.  A generic 128-bit division costs
-// several hundred instructions per particle on the GPU (it was most of the scan kernel), so the
-// quotient is ESTIMATED in float64 (a * (2^52 / A), good to a couple of units) and then made
-// EXACT with a 128-bit multiply-back and a correction walk.  The result is the same integer
-// floor for every input; tests/hostsim checks it against Python big integers.
-struct QDiv {
-    uint64_t A_lo, A_hi;
+// ---------------------------------------------------------------------------------------------
+// The normalised CDF as a quotient of PREFIX SUMS:
+//   C_j = sum_{i <= j} a_i (exact integer, < 2^90),  A = C_{N-1},  cdf_j = floor(C_j 2^52 / A),
+//   q_j = cdf_j - cdf_{j-1},  w_j = q_j 2^-52.
+// cdf_{N-1} = 2^52 exactly, every cdf_j is an integer <= 2^52 (exact in float64), so np.cumsum(w) is
+// cdf 2^-52 bit for bit in any summation order.  Because the CDF is a function of the prefix of the a_i
+// alone, nothing per particle has to be stored between the pass that sums the a_i and the pass that
+// selects ancestors: the select kernel rebuilds C_j from the log-weights and a table of per-chunk sums.
+struct U128 {
+    uint64_t lo, hi;
+};
+AUVPF_HD U128 u128(uint64_t lo, uint64_t hi = 0)
+{
+    U128 r;
+    r.lo = lo;
+    r.hi = hi;
+    return r;
+}
+AUVPF_HD U128 operator+(U128 a, U128 b)
+{
+    U128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+AUVPF_HD U128 operator+(U128 a, uint64_t b)
+{
+    U128 r;
+    r.lo = a.lo + b;
+    r.hi = a.hi + (r.lo < b ? 1ull : 0ull);
+    return r;
+}
+AUVPF_HD bool operator==(U128 a, U128 b) { return a.lo == b.lo && a.hi == b.hi; }
+AUVPF_HD unsigned __int128 u128_int(U128 a) { return ((unsigned __int128)a.hi << 64) | a.lo; }
+AUVPF_HD U128 u128_from(unsigned __int128 v) { return u128((uint64_t)v, (uint64_t)(v >> 64)); }
+// two-limb form used by the warp / block reductions: lo = sum of the low 32 bits, hi = sum of the high bits
+AUVPF_HD U128 u128_from_limbs(uint64_t lo32_sum, uint64_t hi_sum)
+{
+    return u128_from((unsigned __int128)lo32_sum + ((unsigned __int128)hi_sum << 32));
+}
+AUVPF_HD double u128_to_double(U128 c) { return (double)c.hi * 18446744073709551616.0 + (double)c.lo; }
+
+struct CdfDiv {
+    U128 A;
     double scale;        // 2^52 / A, rounded
 };
-
-AUVPF_HD QDiv make_qdiv(uint64_t A_lo, uint64_t A_hi)
+AUVPF_HD CdfDiv make_cdfdiv(U128 A)
 {
-    QDiv d;
-    d.A_lo = A_lo;
-    d.A_hi = A_hi;
-    const double Ad = (double)A_hi * 18446744073709551616.0 + (double)A_lo;
+    CdfDiv d;
+    d.A = A;
+    const double Ad = u128_to_double(A);
     d.scale = Ad > 0.0 ? 4503599627370496.0 / Ad : 0.0;
     return d;
 }
-
-AUVPF_HD uint64_t q_from_a(uint64_t a, const QDiv &d)
+// cdf estimate: within kCdfEstErr units of floor(C 2^52 / A) (roundings of the conversion, of `scale` and of
+// the product: < 2^-50.5 relative, i.e. < 3 units at the top of the range)
+constexpr double kCdfEstErr = 3.0;
+AUVPF_HD double cdf_estimate(U128 C, const CdfDiv &d) { return u128_to_double(C) * d.scale; }
+// the exact floor: the estimate is corrected with a multiply-back.  t = C 2^52 and q A both exceed 128
+// bits, but their difference r = t - q A lies in (-4 A, 5 A), |r| < 2^93, so it is exact in WRAPPING
+// 128-bit arithmetic read as a signed number.  tests/hostsim checks it against Python integers.
+AUVPF_HD uint64_t cdf_exact(U128 C, const CdfDiv &d)
 {
-    if (a == 0) return 0;
-    const unsigned __int128 A = ((unsigned __int128)d.A_hi << 64) | d.A_lo;
-    const unsigned __int128 t = (unsigned __int128)a << kQBits;
-    double qe = (double)a * d.scale;
-    if (!(qe < 4503599627370496.0)) qe = 4503599627370496.0;      // a <= A, so q <= 2^52
+    const unsigned __int128 A = u128_int(d.A), Ci = u128_int(C);
+    if (A == 0) return 0;
+    double qe = cdf_estimate(C, d);
+    if (!(qe < 4503599627370496.0)) qe = 4503599627370496.0;      // C <= A, so the quotient is <= 2^52
+    if (!(qe > 0.0)) qe = 0.0;
     uint64_t q = (uint64_t)qe;
-    // q * A <= t + 3 A < 2^128: the high product q * A_hi stays below 2^64
-    unsigned __int128 prod = (unsigned __int128)q * d.A_lo + (((unsigned __int128)(q * d.A_hi)) << 64);
-    while (prod > t) {
+    __int128 r = (__int128)((Ci << kQBits) - (unsigned __int128)q * A);
+    while (r < 0) {
         --q;
-        prod -= A;
+        r += (__int128)A;
     }
-    while (t - prod >= A) {
+    while (r >= (__int128)A) {
         ++q;
-        prod += A;
+        r -= (__int128)A;
     }
     return q;
 }
 
-AUVPF_HD uint64_t q_from_a(uint64_t a, uint64_t A_lo, uint64_t A_hi) { return q_from_a(a, make_qdiv(A_lo, A_hi)); }
-
-// Effective sample size for the resampling gate (the block commented out at auv_pf.py:174-181:
-// N_eff = 1 / sum w^2, resample only when N_eff < pc / 2).  So that every block, every GPU and the
-// CPU oracle take the SAME decision, the sum of squares is an exact integer: s_i = min(q_i >> 20,
-// 2^32 - 1), S = sum s_i^2 accumulated as two limbs (low 32 bits, high bits), and
-//   neff_fixed = 2^64 / (double(S_hi) 2^32 + double(S_lo))
-// (w_i = q_i 2^-52, so sum w^2 ~= S 2^-64; relative error < 2^-7 even at 16 M equal weights).
-AUVPF_HD uint64_t neff_square(uint64_t q)
+// Effective sample size for the resampling gate (the block commented out at auv_pf.py:174-181), on exact
+// integers so that every block, every GPU and the CPU oracle take the SAME decision: s_i = a_i >> 28
+// (a_i <= 2^60, so s_i <= 2^31 and s_i^2 fits 64 bits), S1 = sum s_i, S2 = sum s_i^2 as two limbs (low 32 bits, high bits);
+//   neff_fixed = double(S1)^2 / (double(S2_hi) 2^32 + double(S2_lo))     (= (sum w)^2 / sum w^2)
+// Sums of integers do not depend on the order or on the sharding.
+constexpr int kNeffShift = 29;
+AUVPF_HD uint64_t neff_s(uint64_t a) { return a >> kNeffShift; }
+AUVPF_HD double neff_fixed_a(uint64_t S1, uint64_t S2_lo, uint64_t S2_hi)
 {
-    uint64_t s = q >> 20;
-    if (s > 0xFFFFFFFFull) s = 0xFFFFFFFFull;
-    return s * s;
-}
-AUVPF_HD double neff_fixed(uint64_t S_lo, uint64_t S_hi)
-{
-    const double S = add_rn(mul_rn((double)S_hi, 4294967296.0), (double)S_lo);
-    return S > 0.0 ? 18446744073709551616.0 / S : 0.0;
+    const double S2 = add_rn(mul_rn((double)S2_hi, 4294967296.0), (double)S2_lo);
+    const double s1 = (double)S1;
+    return S2 > 0.0 ? mul_rn(s1, s1) / S2 : 0.0;
 }
 
 // positions[i] = (u + i) / N of resampling.py:157, as the reference rounds it
@@ -1324,6 +1412,24 @@ AUVPF_HD int rel_end_of(const SysPos &sp, int64_t n_global, const RelEndCtx &r, 
 #endif
     const int64_t g = sys_count_below(sp, n_global, c) - r.g0;
     return (int)(g < 0 ? 0 : (g > r.nblk ? r.nblk : g));
+}
+
+// The same from an ESTIMATE of the cdf value (cdf_estimate plus float64 running sums: within a few units of
+// the exact integer, i.e. within ~3e-6 of the true x for N <= 2^30): decided whenever x is further than 1e-5
+// from an integer; -1 = too close to call, the caller evaluates the exact cdf and takes rel_end_of.
+AUVPF_HD int rel_end_fast(const RelEndCtx &r, double est)
+{
+    const double x = fma(est, r.n_scaled, -r.u) - r.g0d;
+    if (x < -1.0e-5) return 0;
+    if (x > r.nblk_d + 1.0e-5) return r.nblk;
+#if defined(__CUDA_ARCH__)
+    const int ie = __double2int_ru(x);
+#else
+    const int ie = (int)ceil(x);
+#endif
+    const double d = (double)ie - x;                       // in [0, 1)
+    if (d > 1.0e-5 && d < 1.0 - 1.0e-5) return ie < 0 ? 0 : (ie > r.nblk ? r.nblk : ie);
+    return -1;
 }
 
 

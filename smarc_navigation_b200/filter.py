@@ -386,6 +386,28 @@ class ParticleFilter(object):
             _lib.check(self._lib.auvpf_mean_cov(self._h, _ptr(mean), _ptr(cov)))
         return mean, cov.reshape(self.n_filters, 3, 3)
 
+    def estimate(self, weighted=False, circular_yaw=False, full_cov=False):
+        """``mean_cov`` with options: weighted by the log-weights of the last update,
+        circular yaw mean (the reference's arithmetic mean of wrapped yaws breaks at +-pi), full symmetric
+        covariance.  All False = the reference's numbers."""
+        flags = (_lib.EST_WEIGHTED if weighted else 0) | (_lib.EST_CIRCULAR_YAW if circular_yaw else 0) | \
+            (_lib.EST_FULL_COV if full_cov else 0)
+        mean = np.empty((self.n_filters, 6), np.float64)
+        cov = np.empty((self.n_filters, 9), np.float64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_estimate(self._h, flags, _ptr(mean), _ptr(cov)))
+        return mean, cov.reshape(self.n_filters, 3, 3)
+
+    def pose_array(self, max_poses=2000, stride=0):
+        """The ``PoseArray`` of ``loc_loop`` (auv_pf.py:264-285) for a strided subsample, quaternions computed on
+        the device: ``(F, n, 7)`` rows ``[x y z qx qy qz qw]``, ``n <= max_poses``."""
+        n_max = min(int(max_poses), self.pc)
+        out = np.empty((self.n_filters, n_max, 7), np.float64)
+        n = C.c_int64(0)
+        with self._lock:
+            _lib.check(self._lib.auvpf_pose_array(self._h, int(stride), n_max, _ptr(out), C.byref(n)))
+        return out.reshape(-1)[: self.n_filters * n.value * 7].reshape(self.n_filters, n.value, 7)
+
     def neff(self):
         out = np.empty(self.n_filters, np.float64)
         with self._lock:

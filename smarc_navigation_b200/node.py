@@ -48,6 +48,9 @@ DEFAULTS = {
     "device": 0,
     "resample_neff_ratio": 0.0,                # 0 = resample at every fix like the live code; 0.5 = the gate
                                                # the reference carries commented out (:174-181)
+    "publish_max_particles": 2000,             # PoseArray size: a strided subsample built on the device (the reference
+                                               # publishes every particle, :264-285; >= particle_count does the same)
+    "estimate_circular_yaw": False,            # True: circular yaw mean instead of the mean of wrapped yaws (:229-231)
 }
 
 
@@ -95,6 +98,8 @@ class AuvPfNode(object):
         self._lock = threading.Lock()
         self._scan_geometry = None
         self.updates = 0
+        self.publish_max = int(param("publish_max_particles"))
+        self.circular_yaw = bool(param("estimate_circular_yaw"))
 
     # -- map / sensor (GPU additions) ---------------------------------------------------------
     def set_map(self, z, x0=0.0, y0=0.0, res=1.0):
@@ -145,14 +150,16 @@ class AuvPfNode(object):
     def loc_loop(self, event=None):                                              # :264-285
         """10 Hz timer: publish the particle poses and the mean estimate."""
         with self._lock:
-            poses = self.pf.poses()
+            # (n, 7) [x y z qx qy qz qw]: the Pose entries of the reference's PoseArray (:267-275), for a strided
+            # subsample assembled on the device -- not 48 MB of raw state per tick at 1 M particles
+            poses = self.pf.pose_array(max_poses=self.publish_max)[0]
             est = self.update_loc_pose()
         self.publish_particles(poses)
         self.publish_estimate(est)
         return est
 
     def update_loc_pose(self):                                                   # :218-260
-        mean, cov = self.pf.mean_cov()
+        mean, cov = self.pf.estimate(circular_yaw=True) if self.circular_yaw else self.pf.mean_cov()
         ave_pose, self.cov = mean[0], cov[0]
         quat_t = quaternion_from_euler(ave_pose[3], ave_pose[4], ave_pose[5])    # :233 (yaw = mean of wrapped yaws)
         covariance = [0.0] * 36

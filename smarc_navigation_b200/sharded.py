@@ -1,31 +1,42 @@
 """Particle-sharded filter: one process per GPU, particles split in contiguous
-global ranges, ``torch.distributed`` (NCCL over NVLink) for the three things that
-cross GPUs:
+global ranges.
 
-1. the global log-sum-exp of the weights -- ``all_reduce(MAX)`` of the local
-   maxima, then ``all_reduce(SUM)`` of the local fixed-point sums (two integer
-   limbs, so the total is EXACT and independent of the number of GPUs);
-2. the resampling CDF offsets -- ``all_gather`` of the per-shard integer CDF
-   totals;
-3. the particle exchange for cross-shard ancestors -- systematic ancestors are
-   globally sorted, so the offspring of shard g's particles are ONE contiguous
-   range of global output slots; shard g gathers them locally into 32-byte
-   records and an ``all_to_all_single`` with contiguous splits delivers each
-   output slot to its owner.
+The normalised CDF is a quotient of prefix sums, ``cdf_j = floor(C_j 2^52 / A)`` with
+``C_j`` the sum of the integer weights ``a_i`` up to ``j`` over ALL shards and ``A`` the global
+total, so a shard's CDF is its local prefix shifted by the integer mass of the shards below it.
+What crosses GPUs is therefore
 
-Because every cross-GPU quantity is an integer, the ancestors are bit-identical
-to the single-GPU (and to the reference's ``systematic_resample``) result for
-any number of GPUs.
+1. the global maximum of the log-weights (the ``a_i`` refer to it),
+2. six integers per rank: its total (two words), the three integer sums of the N_eff gate, and
+   which log-weight buffer it used,
+3. the particles of cross-shard ancestors.
 
-The per-shard compute is behind a small ``ops`` interface so that the
-orchestration can be exercised with ``gloo`` on CPU (tests/test_sharded_gloo.py
-plugs the oracle in); the product ``GpuShardOps`` calls the C ABI.
+``exchange="p2p"`` (default): all three through peer memory (CUDA IPC mappings of the ranks' slabs):
+the weights kernel posts (1) and (2) into every peer's mailbox, the select kernel waits for them and
+reads the owners' log-weights, chunk tables and state over NVLink -- ``auvpf_shard_resample``, two
+kernels, no NCCL call and no host round trip in the cycle.  The estimate is reduced the same way:
+every rank's 16 pose sums are gathered with ONE small ``all_gather`` on the device and read back once.
+
+``exchange="nccl"``: the portable variant.  (1) ``all_reduce(MAX)`` in place on the library's
+order-preserving int32 maximum, (2) ``all_gather`` of the six integers, then the host plans contiguous
+splits (systematic ancestors are globally sorted, so the offspring of shard g's particles are ONE
+contiguous range of global output slots), each shard emits its offspring as 32-byte records and one
+``all_to_all_single`` delivers them.
+
+Because every cross-GPU quantity is an integer, the ancestors are bit-identical to the single-GPU
+(and to the reference's ``systematic_resample``) result for any number of GPUs.
+
+The per-shard compute of the staged variant is behind a small ``ops`` interface so that the
+orchestration can be exercised with ``gloo`` on CPU (tests/test_sharded_gloo.py plugs the oracle in);
+the product ``GpuShardOps`` calls the C ABI.
 """
 import ctypes as C
 
 import numpy as np
 
-Q_ONE = 1 << 52
+Q_BITS = 52
+Q_ONE = 1 << Q_BITS
+TOTAL_WORDS = 6         # A low, A high, S1, S2 low, S2 high, log-weight buffer id
 
 
 def sys_position(u, i, n):
@@ -46,24 +57,41 @@ def count_below(u, n, c):
     return i
 
 
-def plan_exchange(Q_all, M, u):
-    """From the gathered per-shard CDF totals compute, identically on every rank:
-    deficit D, per-shard q_offset, and ``bounds[g] .. bounds[g+1]`` = the global
-    output slots produced by shard g's particles."""
-    G = len(Q_all)
+def totals_to_ints(row):
+    """One rank's six words -> (A, S1, S2_lo, S2_hi, buffer)."""
+    r = [int(v) & 0xFFFFFFFFFFFFFFFF for v in row]
+    return r[0] | (r[1] << 64), r[2], r[3], r[4], r[5]
+
+
+def neff_fixed(S1, S2_lo, S2_hi):
+    """``auvpf_neff_fixed`` from the summed integers (csrc/auvpf_math.cuh ``neff_fixed_a``)."""
+    S2 = np.float64(S2_hi) * np.float64(4294967296.0) + np.float64(S2_lo)
+    s1 = np.float64(S1)
+    return float(s1 * s1 / S2) if S2 > 0 else 0.0
+
+
+def plan_exchange(A_all, M, u):
+    """From the gathered per-shard integer totals compute, identically on every rank: the mass
+    ``c_off[g]`` below every shard (``c_off[G]`` = the global total) and ``bounds[g] .. bounds[g+1]`` =
+    the global output slots produced by shard g's particles (``count_below`` of the cdf value at the
+    shard's end, ``floor(c_off[g+1] 2^52 / A)``)."""
+    G = len(A_all)
     N = G * M
-    D = Q_ONE - sum(int(q) for q in Q_all)
-    if not (0 <= D < max(N, 1) + 1):
-        raise ArithmeticError("inconsistent CDF totals (deficit %d)" % D)
-    q_offsets, bounds, acc = [], [0], 0
+    c_off, acc = [], 0
     for g in range(G):
-        q_offsets.append(acc)
-        acc += int(Q_all[g])
-        c_end = acc + min((g + 1) * M, D)
-        bounds.append(count_below(u, N, c_end) if g < G - 1 else N)
+        c_off.append(acc)
+        acc += int(A_all[g])
+    c_off.append(acc)
+    A = acc
+    if A <= 0:
+        raise FloatingPointError("degenerate weights on every shard")
+    bounds = [0]
+    for g in range(G):
+        cdf_end = (c_off[g + 1] << Q_BITS) // A
+        bounds.append(count_below(u, N, cdf_end) if g < G - 1 else N)
     for g in range(G):
         bounds[g + 1] = max(bounds[g + 1], bounds[g])
-    return D, q_offsets, bounds
+    return c_off, bounds
 
 
 def splits_for(bounds, M, rank):
@@ -77,9 +105,14 @@ def splits_for(bounds, M, rank):
     return send, recv
 
 
-def resample_sharded(ops, dist, u, group=None):
-    """Run one sharded normalise + systematic resample.  ``ops`` provides the
-    per-shard stages (see ``GpuShardOps``); ``dist`` is ``torch.distributed``.
+def _as_i64(v):
+    v = int(v) & 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def resample_sharded(ops, dist, u, group=None, neff_ratio=0.0):
+    """One sharded normalise + systematic resample with the scalars staged through the host.
+    ``ops`` provides the per-shard stages (see ``GpuShardOps``); ``dist`` is ``torch.distributed``.
     Returns the plan (for tests / diagnostics)."""
     import torch
     rank, G = dist.get_rank(group), dist.get_world_size(group)
@@ -91,25 +124,23 @@ def resample_sharded(ops, dist, u, group=None):
     m = float(m.item())
     if not np.isfinite(m):
         raise FloatingPointError("degenerate weights on every shard")
-    # 2. exact global fixed-point sum
-    limbs = torch.tensor(ops.shard_sum(m), dtype=torch.int64, device=dev)
-    dist.all_reduce(limbs, op=dist.ReduceOp.SUM, group=group)
-    lo, hi = (int(v) for v in limbs.tolist())
-    A = lo + (hi << 32)
-    # 3. local scan, gather the totals
-    Q = torch.tensor([ops.shard_scan(m, A)], dtype=torch.int64, device=dev)
-    Q_all = [torch.zeros_like(Q) for _ in range(G)]
-    dist.all_gather(Q_all, Q, group=group)
-    Q_all = [int(q.item()) for q in Q_all]
-    D, q_offsets, bounds = plan_exchange(Q_all, M, u)
-    # 4. emit this shard's offspring, 5. exchange, 6. load
+    # 2. integer weights against the global max: this shard's totals; gather everybody's
+    mine = torch.tensor([_as_i64(v) for v in ops.shard_sum(m)], dtype=torch.int64, device=dev)
+    everyone = [torch.zeros_like(mine) for _ in range(G)]
+    dist.all_gather(everyone, mine, group=group)
+    table = [t.tolist() for t in everyone]
+    rows = [totals_to_ints(r) for r in table]
+    c_off, bounds = plan_exchange([r[0] for r in rows], M, u)
+    if neff_ratio > 0.0 and neff_fixed(sum(r[1] for r in rows), sum(r[2] for r in rows), sum(r[3] for r in rows)) >= neff_ratio * G * M:
+        return dict(m=m, c_off=c_off, bounds=bounds, skipped=True)
+    # 3. emit this shard's offspring, 4. exchange, 5. load
     send_counts, recv_counts = splits_for(bounds, M, rank)
-    send = ops.shard_emit(u, q_offsets[rank], D, bounds[rank], bounds[rank + 1])     # (n_out, 4) float64 records
+    send = ops.shard_emit(u, table, bounds[rank], bounds[rank + 1], rank)     # (n_out, 4) float64 records
     recv = torch.empty((M, 4), dtype=torch.float64, device=dev)
     assert sum(recv_counts) == M and sum(send_counts) == send.shape[0]
     dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=group)
     ops.shard_load(recv)
-    return dict(m=m, A=A, Q_all=Q_all, D=D, bounds=bounds, send=send_counts, recv=recv_counts)
+    return dict(m=m, c_off=c_off, bounds=bounds, send=send_counts, recv=recv_counts, skipped=False)
 
 
 class _DeviceArray(object):
@@ -119,10 +150,10 @@ class _DeviceArray(object):
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def resample_sharded_device(ops, dist, u, group=None, rough_var=None):
-    """The same resample with the three cross-GPU scalars kept ON THE DEVICE: the collectives run
-    in place on the library's own buffers, ordered on the library's stream, and the only host
-    read-back is the list of per-shard CDF totals that sizes the exchange."""
+def resample_sharded_device(ops, dist, u, group=None, rough_var=None, neff_ratio=0.0):
+    """The staged resample with the scalars kept ON THE DEVICE: the collectives run in place on the
+    library's own buffers, ordered on the library's stream, and the only host read-back is the G x 6
+    table of integers that sizes the exchange."""
     import torch
     rank, G = dist.get_rank(group), dist.get_world_size(group)
     M = ops.M
@@ -130,45 +161,33 @@ def resample_sharded_device(ops, dist, u, group=None, rough_var=None):
     with torch.cuda.stream(ops.stream):
         ops._lib.check(L.auvpf_shard_max_dev(h))
         dist.all_reduce(ops.t_wmax, op=dist.ReduceOp.MAX, group=group)          # order-preserving int32 == float max
-        ops._lib.check(L.auvpf_shard_sum_dev(h))
-        dist.all_reduce(ops.t_limbs, op=dist.ReduceOp.SUM, group=group)         # exact integer limbs of A
-        ops._lib.check(L.auvpf_shard_scan_dev(h))
-        dist.all_gather_into_tensor(ops.t_qall, ops.t_q, group=group)
-        Q_all = [int(q) for q in ops.t_qall.tolist()]                           # the one host synchronisation
-        if sum(Q_all) == 0:
+        ops._lib.check(L.auvpf_shard_weights_dev(h))
+        dist.all_gather_into_tensor(ops.t_totals_all, ops.t_totals, group=group)
+        rows = [totals_to_ints(r) for r in ops.t_totals_all.view(G, TOTAL_WORDS).tolist()]     # the one host synchronisation
+        if sum(r[0] for r in rows) == 0:
             raise FloatingPointError("degenerate weights on every shard")
-        D, q_offsets, bounds = plan_exchange(Q_all, M, u)
+        c_off, bounds = plan_exchange([r[0] for r in rows], M, u)
+        if neff_ratio > 0.0 and neff_fixed(sum(r[1] for r in rows), sum(r[2] for r in rows), sum(r[3] for r in rows)) >= neff_ratio * G * M:
+            return dict(c_off=c_off, bounds=bounds, skipped=True)
         send_counts, recv_counts = splits_for(bounds, M, rank)
         n_out = bounds[rank + 1] - bounds[rank]
         send = ops.send_records(n_out)
-        ops._lib.check(L.auvpf_shard_emit(h, u, q_offsets[rank], D, bounds[rank], bounds[rank + 1],
+        ops._lib.check(L.auvpf_shard_emit(h, u, C.c_void_p(ops.t_totals_all.data_ptr()), G, rank, bounds[rank], bounds[rank + 1],
                                           C.c_void_p(send.data_ptr()) if n_out > 0 else None, None))
         assert sum(recv_counts) == M and sum(send_counts) == n_out
         dist.all_to_all_single(ops.recv_buf, send, output_split_sizes=recv_counts, input_split_sizes=send_counts,
                                group=group)
         rv = None if rough_var is None else (C.c_double * 6)(*rough_var)
         ops._lib.check(L.auvpf_shard_load_roughen(h, C.c_void_p(ops.recv_buf.data_ptr()), M, rv, None))
-    return dict(Q_all=Q_all, D=D, bounds=bounds, send=send_counts, recv=recv_counts)
+    return dict(c_off=c_off, bounds=bounds, send=send_counts, recv=recv_counts, skipped=False)
 
 
-def resample_sharded_p2p(ops, dist, u, group=None, rough_var=None):
-    """Sharded resample with NO host synchronisation: the three scalar collectives run in place on
-    the library's device buffers, and ONE kernel then selects this rank's ancestors in the global
-    CDF and gathers their state straight from the owners' memory over NVLink (CUDA IPC peer
-    mappings set up by ``GpuShardOps.connect``).  Returns nothing the host would have to wait for."""
-    import torch
-    L, h = ops.L, ops.pf._h
-    with torch.cuda.stream(ops.stream):
-        ops._lib.check(L.auvpf_shard_max_dev(h))
-        dist.all_reduce(ops.t_wmax, op=dist.ReduceOp.MAX, group=group)          # order-preserving int32 == float max
-        ops._lib.check(L.auvpf_shard_sum_dev(h))
-        dist.all_reduce(ops.t_limbs, op=dist.ReduceOp.SUM, group=group)         # exact integer limbs of A
-        ops._lib.check(L.auvpf_shard_scan_dev(h))
-        # this all-gather is also the cross-GPU barrier that makes every shard's CDF and tile table
-        # complete before any rank reads them
-        dist.all_gather_into_tensor(ops.t_qall, ops.t_q, group=group)
-        rv = None if rough_var is None else (C.c_double * 6)(*rough_var)
-        ops._lib.check(L.auvpf_shard_gather_p2p(h, u, C.c_void_p(ops.t_qall.data_ptr()), rv, None, None))
+def resample_sharded_p2p(ops, u, rough_var=None, ancestors=None):
+    """Sharded resample over peer memory: ONE library call, two kernels, nothing the host or NCCL has to
+    do (``auvpf_shard_resample``; the peers were mapped by ``GpuShardOps.connect``)."""
+    rv = None if rough_var is None else (C.c_double * 6)(*rough_var)
+    ops._lib.check(ops.L.auvpf_shard_resample(ops.pf._h, u, rv, None,
+                                             None if ancestors is None else C.c_void_p(ancestors.data_ptr())))
     return {}
 
 
@@ -186,29 +205,28 @@ class GpuShardOps(object):
         self.torch = torch
         # device-resident flow: torch views of the library's scalars + persistent exchange buffers
         self.stream = torch.cuda.ExternalStream(pf.stream_ptr, device=self.device)
-        pw, pl, pq = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        _lib.check(self.L.auvpf_shard_buffers(pf._h, C.byref(pw), C.byref(pl), C.byref(pq)))
+        pw, pt = C.c_void_p(), C.c_void_p()
+        _lib.check(self.L.auvpf_shard_buffers(pf._h, C.byref(pw), C.byref(pt)))
         self.t_wmax = torch.as_tensor(_DeviceArray(pw.value, (1,), "<i4"), device=self.device)
-        self.t_limbs = torch.as_tensor(_DeviceArray(pl.value, (2,), "<i8"), device=self.device)
-        self.t_q = torch.as_tensor(_DeviceArray(pq.value, (1,), "<i8"), device=self.device)
-        self.t_qall = None
+        self.t_totals = torch.as_tensor(_DeviceArray(pt.value, (TOTAL_WORDS,), "<i8"), device=self.device)
+        self.t_totals_all = None
         self.send_buf = self.recv_buf = None
         self.p2p = False
 
     def prepare(self, world_size):
-        if self.t_qall is None:
-            t = self.torch
-            self.t_qall = t.zeros(world_size, dtype=t.int64, device=self.device)
+        t = self.torch
+        if self.t_totals_all is None:
+            self.t_totals_all = t.zeros(world_size * TOTAL_WORDS, dtype=t.int64, device=self.device)
+        if self.send_buf is None and not self.p2p:
             self.send_buf = t.empty((2 * self.M, 4), dtype=t.float64, device=self.device)
             self.recv_buf = t.empty((self.M, 4), dtype=t.float64, device=self.device)
 
     def connect(self, dist, group=None):
-        """Exchange CUDA IPC handles of the state / CDF slabs and map the peers' memory.  Collective:
+        """Exchange CUDA IPC handles of the slabs and map the peers' memory.  Collective:
         every rank takes part in the all-gather even when its own export failed, and no rank imports
         unless every export succeeded.  Returns an error (or None); the caller agrees on the outcome."""
         t = self.torch
         G, rank = dist.get_world_size(group), dist.get_rank(group)
-        self.prepare(G)
         nb = self._lib.IPC_BLOB_BYTES
         blob = (C.c_ubyte * nb)()
         err = None
@@ -245,6 +263,7 @@ class GpuShardOps(object):
             self.send_buf = self.torch.empty((n_out + n_out // 4, 4), dtype=self.torch.float64, device=self.device)
         return self.send_buf[:max(n_out, 0)]
 
+    # -- host-staged stages (tests, and the gloo-testable orchestration `resample_sharded`) --------------
     def shard_max(self):
         out = (C.c_float * 1)()
         self._lib.check(self.L.auvpf_shard_max(self.pf._h, out))
@@ -252,20 +271,15 @@ class GpuShardOps(object):
 
     def shard_sum(self, m):
         mm = (C.c_float * 1)(m)
-        out = (C.c_uint64 * 2)()
+        out = (C.c_uint64 * TOTAL_WORDS)()
         self._lib.check(self.L.auvpf_shard_sum(self.pf._h, mm, out))
-        return [int(out[0]), int(out[1])]
+        return [int(v) for v in out]
 
-    def shard_scan(self, m, A):
-        mm = (C.c_float * 1)(m)
-        AA = (C.c_uint64 * 2)(A & 0xFFFFFFFFFFFFFFFF, A >> 64)
-        out = (C.c_uint64 * 1)()
-        self._lib.check(self.L.auvpf_shard_scan(self.pf._h, mm, AA, out))
-        return int(out[0])
-
-    def shard_emit(self, u, q_offset, D, lo, hi):
+    def shard_emit(self, u, totals_all, lo, hi, rank):
+        G = len(totals_all)
+        flat = (C.c_uint64 * (G * TOTAL_WORDS))(*[int(v) & 0xFFFFFFFFFFFFFFFF for row in totals_all for v in row])
         rec = self.torch.empty((max(hi - lo, 0), 4), dtype=self.torch.float64, device=self.device)
-        self._lib.check(self.L.auvpf_shard_emit(self.pf._h, u, q_offset, D, lo, hi,
+        self._lib.check(self.L.auvpf_shard_emit(self.pf._h, u, flat, G, rank, lo, hi,
                                                C.c_void_p(rec.data_ptr()) if hi > lo else None, None))
         self.pf.sync()                       # records complete before NCCL reads them on its own stream
         return rec
@@ -280,9 +294,10 @@ class ShardedParticleFilter(object):
     """``ParticleFilter`` over G ranks: same predict/update/resample methods; every rank
     calls them collectively with the same arguments."""
 
-    def __init__(self, particles_per_rank, dist, group=None, exchange="p2p", **kw):
-        """``exchange``: "p2p" (default; one kernel over CUDA-IPC peer memory, up to 8 ranks of one
-        node) or "nccl" (records + ``all_to_all_single``; any topology NCCL supports)."""
+    def __init__(self, particles_per_rank, dist, group=None, exchange="p2p", resample_neff_ratio=0.0, **kw):
+        """``exchange``: "p2p" (default; mailbox + one select kernel over CUDA-IPC peer memory, up to 8
+        ranks of one node) or "nccl" (scalar collectives + records + ``all_to_all_single``; any topology
+        NCCL supports).  ``resample_neff_ratio``: the N_eff gate (auv_pf.py:174-181) on the GLOBAL sums."""
         import torch
         from .filter import ParticleFilter
         self.dist, self.group = dist, group
@@ -290,7 +305,9 @@ class ShardedParticleFilter(object):
         self.M = int(particles_per_rank)
         self.N = self.M * self.G
         kw.setdefault("device", torch.cuda.current_device())
-        self.pf = ParticleFilter(particle_count=self.M, global_offset=self.rank * self.M, global_count=self.N, **kw)
+        self.pf = ParticleFilter(particle_count=self.M, global_offset=self.rank * self.M, global_count=self.N,
+                                 resample_neff_ratio=resample_neff_ratio, **kw)
+        self.neff_ratio = float(resample_neff_ratio)
         self.ops = GpuShardOps(self.pf)
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
@@ -310,15 +327,16 @@ class ShardedParticleFilter(object):
                     warnings.warn("peer-memory exchange unavailable (%s); using the NCCL record exchange" % (err,))
         self._step = 0
         self._seed = int(kw.get("seed", 0))
+        self._sums = None
 
     @property
     def resample_kernels(self):
         """What a resample launches on this path (bench.py labels its roofline line with it)."""
         if self.ops.p2p:
-            return ("k_normalise + all_reduce(MAX, SUM) + k_scan_q (look-back) + all_gather(Q) + k_shard_meta + "
-                    "k_select_gather_p2p (select + gather + exchange over peer memory)")
-        return ("k_normalise + all_reduce(MAX, SUM) + k_scan_q (look-back) + all_gather(Q) + k_select_gather<records> + "
-                "all_to_all_single + k_load_records")
+            return ("k_weights (maximum and totals exchanged through the peer-memory mailbox) + k_select<peers> "
+                    "(select + gather + exchange over NVLink)")
+        return ("k_weights + all_reduce(MAX) + all_gather(totals) + k_select<records> + all_to_all_single + "
+                "k_load_records")
 
     def set_dem(self, *a, **k):
         self.pf.set_dem(*a, **k)
@@ -335,36 +353,70 @@ class ShardedParticleFilter(object):
     def update_mbes(self, ranges):
         self.pf.update_mbes(ranges, return_weights=False)
 
-    def resample(self, u=None, roughen=True, check=False):
+    def resample(self, u=None, roughen=True, check=False, ancestors=None):
+        """``ancestors``: optional (M,) int64 CUDA tensor for this rank's GLOBAL ancestor ids (p2p only)."""
         if u is None:      # same Philox-derived uniform on every rank, no communication
             from .rng import resample_uniform
             u = resample_uniform(self._seed, 0, self._step)
         self._step += 1
-        self.ops.prepare(self.G)
         rv = self.pf.res_noise_cov if roughen else None
         if self.ops.p2p:
-            plan = resample_sharded_p2p(self.ops, self.dist, float(u), self.group, rough_var=rv)
+            plan = resample_sharded_p2p(self.ops, float(u), rough_var=rv, ancestors=ancestors)
             if check and self.ops.degenerate():
                 raise FloatingPointError("degenerate weights on every shard")
             return plan
-        return resample_sharded_device(self.ops, self.dist, float(u), self.group, rough_var=rv)
+        self.ops.prepare(self.G)
+        return resample_sharded_device(self.ops, self.dist, float(u), self.group, rough_var=rv, neff_ratio=self.neff_ratio)
+
+    def resample_skipped(self):
+        return bool(self.pf.resample_skipped()[0])
 
     def mean_cov(self):
-        import torch
-        mean, cov = self.pf.mean_cov()
-        t = torch.tensor(np.concatenate([mean[0], cov[0].reshape(9)]), dtype=torch.float64, device=self.ops.device)
-        allt = [torch.zeros_like(t) for _ in range(self.G)]
-        self.dist.all_gather(allt, t, group=self.group)
-        arr = np.stack([a.cpu().numpy() for a in allt])
-        means, covs = arr[:, :6], arr[:, 6:].reshape(-1, 3, 3)
-        gm = means.mean(0)
-        d = means[:, :3] - gm[:3]
-        gc = (covs + d[:, :, None] * d[:, None, :]).mean(0)
-        gc[2, 0] = gc[2, 1] = 0.0          # the reference's fill pattern (auv_pf.py:238-246)
-        return gm, gc
+        """Global estimate (auv_pf.py:218-252): every rank's 16 pose sums stay on the device, ONE small
+        collective on the library's stream gathers them and they are read back ONCE; combined in float64
+        in rank order, so every rank returns the same numbers."""
+        torch = self.ops.torch
+        L, h = self.ops.L, self.pf._h
+        if self._sums is None:
+            p = C.c_void_p()
+            self.ops._lib.check(L.auvpf_pose_sums_buffer(h, C.byref(p)))
+            self._sums = torch.as_tensor(_DeviceArray(p.value, (16,), "<f8"), device=self.ops.device)
+            self._sums_all = torch.empty(16 * self.G, dtype=torch.float64, device=self.ops.device)
+        with torch.cuda.stream(self.ops.stream):
+            self.ops._lib.check(L.auvpf_pose_sums_dev(h))
+            self.dist.all_gather_into_tensor(self._sums_all, self._sums, group=self.group)
+            s = self._sums_all.cpu().numpy().reshape(self.G, 16)               # the one read-back (stream-ordered)
+        return combine_pose_sums(s, self.M)
 
     def poses(self):
         return self.pf.poses()
 
     def close(self):
         self.pf.close()
+
+
+def combine_pose_sums(s, M):
+    """(G, 16) per-shard sums of ``k_pose_stats`` -- [sum d_xyz, sum roll, pitch, yaw, wrapped yaw, sum d d^T
+    (xx yy zz xy xz yz), c_xyz] with d = position - c, c the shard's first particle -- -> the global
+    ``(mean(6), cov(3,3))`` of auv_pf.update_loc_pose with the reference's fill pattern."""
+    s = np.asarray(s, np.float64)
+    G = s.shape[0]
+    n = float(G * M)
+    c = s[:, 13:16]
+    c0 = c[0]
+    off = c - c0                                          # every shard's reference point relative to shard 0's
+    sd = s[:, 0:3] + M * off                              # sums of (pos - c0)
+    mean_d = sd.sum(0) / n
+    mean = np.empty(6)
+    mean[0:3] = c0 + mean_d
+    mean[3] = s[:, 3].sum() / n
+    mean[4] = s[:, 4].sum() / n
+    mean[5] = s[:, 6].sum() / n                           # mean of the wrapped yaws (auv_pf.py:229-231)
+    # second moments about c0: sum (d + off)(d + off)^T = sum d d^T + off sum d^T + sum d off^T + M off off^T
+    pairs = [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)]
+    cov = np.zeros((3, 3))
+    for k, (i, j) in enumerate(pairs):
+        m2 = (s[:, 7 + k] + off[:, i] * s[:, j] + s[:, i] * off[:, j] + M * off[:, i] * off[:, j]).sum() / n
+        cov[i, j] = m2 - mean_d[i] * mean_d[j]
+    cov[1, 0] = cov[0, 1]                                 # only [1,0] is mirrored (auv_pf.py:246)
+    return mean, cov

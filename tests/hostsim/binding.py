@@ -21,7 +21,8 @@ def lib():
         _lib.hs_resample.restype = C.c_int
         _lib.hs_count_below.restype = C.c_long
         _lib.hs_wrap_pi.restype = C.c_float
-        _lib.hs_q_from_a.restype = C.c_uint64
+        _lib.hs_cdf_exact.restype = C.c_uint64
+        _lib.hs_cdf_estimate.restype = C.c_double
     return _lib
 
 
@@ -114,8 +115,15 @@ def searchsorted(arr, keys):
     return out
 
 
-def q_from_a(a, A):
-    return int(lib().hs_q_from_a(C.c_uint64(a), C.c_uint64(A & 0xFFFFFFFFFFFFFFFF), C.c_uint64(A >> 64)))
+def cdf_exact(Cv, A):
+    """floor(C 2^52 / A) by the device function (float64 estimate + wrapping 128-bit multiply-back)."""
+    m = 0xFFFFFFFFFFFFFFFF
+    return int(lib().hs_cdf_exact(C.c_uint64(Cv & m), C.c_uint64(Cv >> 64), C.c_uint64(A & m), C.c_uint64(A >> 64)))
+
+
+def cdf_estimate(Cv, A):
+    m = 0xFFFFFFFFFFFFFFFF
+    return float(lib().hs_cdf_estimate(C.c_uint64(Cv & m), C.c_uint64(Cv >> 64), C.c_uint64(A & m), C.c_uint64(A >> 64)))
 
 
 def count_below(u, N, c):
@@ -126,16 +134,19 @@ def wrap_pi(a):
     return float(lib().hs_wrap_pi(C.c_float(a)))
 
 
-def neff_fixed(q_raw):
-    q = np.ascontiguousarray(q_raw, np.uint64)
+def neff_fixed(a):
+    q = np.ascontiguousarray(a, np.uint64)
     fn = lib().hs_neff_fixed
     fn.restype = C.c_double
     return float(fn(_p(q), C.c_long(len(q))))
 
 
-def select_source_side(q_raw, u, D):
-    """Ancestors by the host twin of k_select_gather (source-side run heads + max-scan)."""
-    q = np.ascontiguousarray(q_raw, np.uint64)
-    anc = np.zeros(len(q), np.int32)
-    lib().hs_select_source_side(_p(q), C.c_long(len(q)), C.c_double(u), C.c_uint64(int(D)), _p(anc))
-    return anc
+def select_source_side(a, u, G=1, want_stats=False):
+    """Ancestors by the host twin of k_select (chunk tables, source-side run ends from the cdf estimate,
+    exact fix-up, run heads + max-scan) for ``G`` shards; ``a``: the integer weights of all G*M sources."""
+    a = np.ascontiguousarray(a, np.uint64)
+    assert len(a) % G == 0
+    anc = np.zeros(len(a), np.int32)
+    stats = (C.c_long * 2)()
+    lib().hs_select_source_side(_p(a), C.c_long(len(a) // G), C.c_int(G), C.c_double(u), _p(anc), stats)
+    return (anc, (int(stats[0]), int(stats[1]))) if want_stats else anc

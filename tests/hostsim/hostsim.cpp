@@ -256,24 +256,18 @@ int hs_resample(const float *logw, long M, double u, uint64_t *qq_out, int32_t *
     for (long i = 0; i < M; ++i)
         if (logw[i] == logw[i] && logw[i] > m) m = logw[i];
     if (!std::isfinite(m)) return -1;
-    uint64_t lo = 0, hi = 0;
-    for (long i = 0; i < M; ++i) {
-        uint64_t a = a_from_logw(logw[i], m);
-        lo += a & 0xFFFFFFFFull;
-        hi += a >> 32;
-    }
-    unsigned __int128 A = (unsigned __int128)lo + ((unsigned __int128)hi << 32);
-    uint64_t A_lo = (uint64_t)A, A_hi = (uint64_t)(A >> 64);
+    unsigned __int128 A = 0;
+    for (long i = 0; i < M; ++i) A += a_from_logw(logw[i], m);
+    if (A == 0) return -1;
+    const CdfDiv div = make_cdfdiv(u128_from(A));
     std::vector<uint64_t> cdf(M);
-    uint64_t acc = 0;
+    unsigned __int128 C = 0;
+    uint64_t prev = 0;
     for (long i = 0; i < M; ++i) {
-        acc += q_from_a(a_from_logw(logw[i], m), A_lo, A_hi);
-        cdf[i] = acc;
-    }
-    uint64_t D = (1ull << kQBits) - acc;
-    for (long i = 0; i < M; ++i) {
-        uint64_t q = q_from_a(a_from_logw(logw[i], m), A_lo, A_hi);
-        if (qq_out) qq_out[i] = q + ((uint64_t)i < D ? 1 : 0);
+        C += a_from_logw(logw[i], m);
+        cdf[i] = cdf_exact(u128_from(C), div);
+        if (qq_out) qq_out[i] = cdf[i] - prev;
+        prev = cdf[i];
     }
     double n = (double)M;
     for (long i = 0; i < M; ++i) {
@@ -281,9 +275,7 @@ int hs_resample(const float *logw, long M, double u, uint64_t *qq_out, int32_t *
         long l = 0, h = M;
         while (l < h) {
             long mid = (l + h) >> 1;
-            uint64_t jg1 = (uint64_t)(mid + 1);
-            double c = cdf_value(cdf[mid] + (jg1 < D ? jg1 : D));
-            if (pos < c) h = mid;
+            if (pos < cdf_value(cdf[mid])) h = mid;
             else l = mid + 1;
         }
         anc_out[i] = (int32_t)std::min(l, M - 1);
@@ -352,7 +344,14 @@ void hs_searchsorted(const double *arr, long n, const double *keys, long nk, lon
     for (long t = 0; t < nk; ++t) out[t] = (long)searchsorted_left_hinted(arr, n, keys[t], h);
 }
 
-uint64_t hs_q_from_a(uint64_t a, uint64_t A_lo, uint64_t A_hi) { return q_from_a(a, A_lo, A_hi); }
+uint64_t hs_cdf_exact(uint64_t C_lo, uint64_t C_hi, uint64_t A_lo, uint64_t A_hi)
+{
+    return cdf_exact(u128(C_lo, C_hi), make_cdfdiv(u128(A_lo, A_hi)));
+}
+double hs_cdf_estimate(uint64_t C_lo, uint64_t C_hi, uint64_t A_lo, uint64_t A_hi)
+{
+    return cdf_estimate(u128(C_lo, C_hi), make_cdfdiv(u128(A_lo, A_hi)));
+}
 
 void hs_prof_reasons(long *out, int reset)
 {
@@ -366,112 +365,182 @@ long hs_count_below(double u, long N, uint64_t c) { return (long)sys_count_below
 
 float hs_wrap_pi(float a) { return wrap_pi(a); }
 
-// Host twin of k_select_gather's ancestor selection (single-GPU form): tile table from the raw quotients,
-// 32-ary tile location, source-side walk with rel_end_of (the SAME function the kernel calls), pruning
-// by thread, run heads, inclusive max-scan -- block by block, "thread" by "thread", in the kernel's order.
-void hs_select_source_side(const uint64_t *q_raw, long M, double u, uint64_t D, int32_t *anc)
+// Host twin of k_select's ancestor selection for G shards of M sources each (G = 1: one GPU): chunk / tile
+// tables as k_weights leaves them, the conservative 32-ary tile location on the cdf ESTIMATE, then block by
+// block, "warp" by "warp", "lane" by "lane" in the kernel's order: chunk bases from the tables, float64 running
+// sums and the warp scan's order of additions, rel_end_fast, the exact fix-up (cdf_exact + rel_end_of) only where
+// the estimate cannot decide, run heads, inclusive max-scan.  a: the integer weights of all G*M sources.
+// stats (optional, 2 longs): sources evaluated by the fast path / by the exact path.
+void hs_select_source_side(const uint64_t *a, long M, int G, double u, int32_t *anc, long *stats)
 {
-    const int kTile = 2048, kItems = 8, kThreads = 256, kOut = 1024;
-    const long tiles = (M + kTile - 1) / kTile;
-    std::vector<uint64_t> tab(tiles);
+    const int kTile = 2048, kItems = 8, kOut = 1024, kCh = 256, kCpt = 8;
+    const long tiles = (M + kTile - 1) / kTile, n_tiles = G * tiles, N = (long)G * M;
+    std::vector<U128> chunk((size_t)n_tiles * kCpt), tprefix((size_t)n_tiles), coff(G + 1);
     {
-        uint64_t acc = 0;
-        for (long t = 0; t < tiles; ++t) {
-            for (long j = t * kTile; j < std::min<long>((t + 1) * kTile, M); ++j) acc += q_raw[j];
-            tab[t] = acc;
+        unsigned __int128 acc_all = 0;
+        for (int g = 0; g < G; ++g) {
+            coff[g] = u128_from(acc_all);
+            unsigned __int128 acc = 0;
+            for (long t = 0; t < tiles; ++t) {
+                for (int c = 0; c < kCpt; ++c) {
+                    unsigned __int128 cs = 0;
+                    for (long j = t * kTile + c * kCh; j < std::min<long>(t * kTile + (c + 1) * kCh, M); ++j) cs += a[(long)g * M + j];
+                    chunk[((size_t)g * tiles + t) * kCpt + c] = u128_from(cs);
+                    acc += cs;
+                }
+                tprefix[(size_t)g * tiles + t] = u128_from(acc);
+            }
+            acc_all += acc;
         }
+        coff[G] = u128_from(acc_all);
     }
-    const double n = (double)M;
+    const CdfDiv div = make_cdfdiv(coff[G]);
+    const double n = (double)N;
     const SysPos spos = make_sys_pos(u, n);
-    auto full = [&](uint64_t raw_cdf, long j) { const uint64_t jg1 = (uint64_t)(j + 1); return raw_cdf + (jg1 < D ? jg1 : D); };
-    for (long k0 = 0; k0 < M; k0 += kOut) {
-        const long k1 = std::min<long>(k0 + kOut, M) - 1;
+    long n_fast = 0, n_exact = 0;
+    for (long k0 = 0; k0 < N; k0 += kOut) {
+        const long k1 = std::min<long>(k0 + kOut, N) - 1;
         const int nblk = (int)(k1 - k0 + 1);
-        // level 1: 32-ary search, one "warp" per key
+        const RelEndCtx rctx = make_rel_end(u, n, k0, nblk);
+        auto rel_end = [&](U128 C) -> int {
+            const int e = rel_end_fast(rctx, cdf_estimate(C, div));
+            return e >= 0 ? e : rel_end_of(spos, N, rctx, cdf_exact(C, div));
+        };
         long tl[2];
         for (int w = 0; w < 2; ++w) {
-            const uint64_t key = (uint64_t)floor(sys_position(u, w == 0 ? k0 : k1, n) * 4503599627370496.0);
-            long lo = 0, hi = tiles;
+            long lo = 0, hi = n_tiles;
             while (lo < hi) {
                 const long step = (hi - lo + 31) >> 5;
                 int nb = 0;
                 for (int lane = 0; lane < 32; ++lane) {
-                    const long t = lo + (lane + 1) * step - 1;
-                    bool below = false;
-                    if (t < hi) {
-                        const long je = std::min<long>((t + 1) * kTile, M) - 1;
-                        below = !(key < full(tab[t], je));
+                    const long T = lo + (lane + 1) * step - 1;
+                    bool before = false;
+                    if (T < hi) {
+                        const int g = (int)(T / tiles);
+                        const U128 C = coff[g] + tprefix[T];
+                        const double x = fma(cdf_estimate(C, div), rctx.n_scaled, -rctx.u) - rctx.g0d;
+                        before = w == 0 ? (x <= -1.0e-5) : (x < rctx.nblk_d + 1.0e-5);
                     }
-                    nb += below ? 1 : 0;
+                    nb += before ? 1 : 0;
                 }
                 lo += nb * step;
                 hi = std::min(lo + step - 1, hi);
             }
-            tl[w] = std::min(lo, tiles - 1);
+            tl[w] = std::min(lo, n_tiles - 1);
         }
-        const long j_lo = tl[0] * kTile, j_hi = std::min<long>((tl[1] + 1) * kTile, M) - 1;
-        const RelEndCtx rctx = make_rel_end(u, n, k0, nblk);
-        auto rel_end = [&](uint64_t raw_cdf, long j) { return rel_end_of(spos, M, rctx, full(raw_cdf, j)); };
+        const long T_lo = tl[0], T_hi = tl[1];
         std::vector<int> head(kOut, 0);
-        for (long jb = j_lo; jb <= j_hi; jb += (long)kThreads * kItems) {
-            const long tile = jb / kTile;
-            const uint64_t tile_excl = tile > 0 ? tab[tile - 1] : 0;
-            if (jb > j_lo && rel_end(tile_excl, jb - 1) >= nblk) break;
-            uint64_t run_before = tile_excl;
-            int prev_thread_last = 0;
-            for (int tid = 0; tid < kThreads; ++tid) {
-                const long j0 = jb + (long)tid * kItems;
-                uint64_t cv[kItems];
-                uint64_t acc = run_before;
-                for (int k = 0; k < kItems; ++k) {
-                    acc += (j0 + k <= j_hi) ? q_raw[j0 + k] : 0;
-                    cv[k] = acc;
+        for (int warp = 0; warp < 8; ++warp) {
+            for (long T = T_lo; T <= T_hi; ++T) {
+                const int g = (int)(T / tiles);
+                const long t = T - (long)g * tiles;
+                U128 incl[kCpt];
+                U128 run = u128(0);
+                for (int c = 0; c < kCpt; ++c) {
+                    run = run + chunk[(size_t)T * kCpt + c];
+                    incl[c] = run;
                 }
-                const uint64_t before = run_before;
-                run_before = acc;
-                int e[kItems];
-                const bool whole = j0 + kItems - 1 <= j_hi;
-                const int e_last = whole ? rel_end(cv[kItems - 1], j0 + kItems - 1) : nblk;
-                const int e_first = (e_last == 0) ? 0 : (j0 <= j_hi ? rel_end(cv[0], j0) : nblk);
-                if (e_last == 0 || e_first == nblk) {
-                    for (int k = 0; k < kItems; ++k) e[k] = e_first;
-                } else {
-                    e[0] = e_first;
-                    for (int k = 1; k < kItems - 1; ++k) e[k] = j0 + k <= j_hi ? rel_end(cv[k], j0 + k) : nblk;
-                    e[kItems - 1] = e_last;
+                U128 tile_base = coff[g];
+                if (t > 0) tile_base = tile_base + tprefix[T - 1];
+                const U128 C_before = tile_base + (warp > 0 ? incl[warp - 1] : u128(0)), C_after = tile_base + incl[warp];
+                const long jc = t * kTile + (long)warp * kCh;
+                if (jc >= M) continue;
+                const bool has_last = (long)g * M + std::min<long>(jc + kCh, M) - 1 == N - 1;
+                if (C_after == C_before && !has_last) continue;
+                const int e_begin = rel_end(C_before);
+                if (e_begin == nblk) break;
+                const int e_end = has_last ? nblk : rel_end(C_after);
+                if (e_end == 0) continue;
+                // the 32 lanes: thread-local float64 running sums, then the warp scan in the kernel's order
+                double cd[32][kItems], tot[32];
+                uint64_t av[32][kItems];
+                for (int lane = 0; lane < 32; ++lane) {
+                    double r = 0.0;
+                    for (int k = 0; k < kItems; ++k) {
+                        const long j = jc + lane * kItems + k;
+                        av[lane][k] = j < M ? a[(long)g * M + j] : 0;
+                        r += (double)av[lane][k];
+                        cd[lane][k] = r;
+                    }
+                    tot[lane] = r;
                 }
-                for (int k = 0; k < kItems; ++k)
-                    if (j0 + k == M - 1) e[k] = nblk;       // the last particle ends where the outputs end (kernel: j_last)
-                int start;
-                if ((tid & 31) == 0) {
-                    const bool has_prev = j0 > j_lo && j0 - 1 <= j_hi;
-                    start = has_prev ? rel_end(before, j0 - 1) : (j0 > j_lo ? nblk : 0);
-                } else
-                    start = prev_thread_last;
-                for (int k = 0; k < kItems; ++k) {
-                    if (e[k] > start) head[start] = (int)(j0 + k - j_lo) + 1;
-                    start = e[k];
+                double sc[32];
+                for (int lane = 0; lane < 32; ++lane) sc[lane] = tot[lane];
+                for (int o = 1; o < 32; o <<= 1) {
+                    double nx[32];
+                    for (int lane = 0; lane < 32; ++lane) nx[lane] = lane >= o ? sc[lane] + sc[lane - o] : sc[lane];
+                    for (int lane = 0; lane < 32; ++lane) sc[lane] = nx[lane];
                 }
-                prev_thread_last = e[kItems - 1];
+                int prev_last = e_begin;
+                unsigned __int128 Cint = u128_int(C_before);
+                for (int lane = 0; lane < 32; ++lane) {
+                    const double before_d = sc[lane] - tot[lane] + u128_to_double(C_before);
+                    int e[kItems];
+                    unsigned need = 0;
+                    auto fast = [&](int k) -> int {
+                        const int r = rel_end_fast(rctx, (before_d + cd[lane][k]) * div.scale);
+                        if (r < 0) need |= 1u << k;
+                        return r;
+                    };
+                    const int e_lastk = fast(kItems - 1);
+                    const int e_first = e_lastk == 0 ? 0 : fast(0);
+                    if ((e_lastk == 0 || e_first == nblk) && need == 0) {
+                        for (int k = 0; k < kItems; ++k) e[k] = e_first;
+                        n_fast += 2;
+                    } else {
+                        e[0] = e_first;
+                        for (int k = 1; k < kItems - 1; ++k) e[k] = fast(k);
+                        e[kItems - 1] = e_lastk;
+                        n_fast += kItems;
+                    }
+                    unsigned __int128 Ck = Cint;
+                    for (int k = 0; k < kItems; ++k) {
+                        Ck += av[lane][k];
+                        if (need & (1u << k)) {
+                            e[k] = rel_end_of(spos, N, rctx, cdf_exact(u128_from(Ck), div));
+                            ++n_exact;
+                        }
+                    }
+                    Cint = Ck;
+                    for (int k = 0; k < kItems; ++k)
+                        if ((long)g * M + jc + lane * kItems + k == N - 1) e[k] = nblk;
+                    int start = prev_last;
+                    const int wbase = (int)((T - T_lo) * kTile + warp * kCh + lane * kItems);
+                    for (int k = 0; k < kItems; ++k) {
+                        if (e[k] > start) head[start] = wbase + k + 1;
+                        start = e[k];
+                    }
+                    prev_last = e[kItems - 1];
+                }
             }
         }
-        int m = 0;
+        int mx = 0;
         for (int k = 0; k < nblk; ++k) {
-            m = std::max(m, head[k]);
-            anc[k0 + k] = (int32_t)std::min<long>(j_lo + std::max(m - 1, 0), M - 1);
+            mx = std::max(mx, head[k]);
+            const int wi = std::max(mx - 1, 0);
+            const long T = T_lo + wi / kTile;
+            const int g = (int)(T / tiles);
+            long j = (T - (long)g * tiles) * kTile + (wi % kTile);
+            if (j > M - 1) j = M - 1;
+            anc[k0 + k] = (int32_t)((long)g * M + j);
         }
+    }
+    if (stats) {
+        stats[0] = n_fast;
+        stats[1] = n_exact;
     }
 }
 
-// the N_eff gate's integer sum of squares, accumulated like the scan kernel does (two limbs)
-double hs_neff_fixed(const uint64_t *q_raw, long n)
+// the N_eff gate's integer sums over the integer weights, accumulated like k_weights does
+double hs_neff_fixed(const uint64_t *a, long n)
 {
-    uint64_t lo = 0, hi = 0;
+    uint64_t s1 = 0, lo = 0, hi = 0;
     for (long i = 0; i < n; ++i) {
-        const uint64_t s2 = neff_square(q_raw[i]);
-        lo += s2 & 0xFFFFFFFFull;
-        hi += s2 >> 32;
+        const uint64_t s = neff_s(a[i]);
+        s1 += s;
+        lo += (s * s) & 0xFFFFFFFFull;
+        hi += (s * s) >> 32;
     }
-    return neff_fixed(lo, hi);
+    return neff_fixed_a(s1, lo, hi);
 }
 }

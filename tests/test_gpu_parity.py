@@ -481,8 +481,7 @@ def test_neff_gated_resample_matches_the_oracle_gate():
     want_skip = []
     for f in range(F):
         qq, a, A, m = o.quantise_logw(logw[f * M:(f + 1) * M])
-        raw = o.raw_quotients(a)
-        assert nf1[f] == o.neff_fixed_raw(raw) == nf0[f]
+        assert nf1[f] == o.neff_fixed_a(a) == nf0[f]
         np.testing.assert_allclose(nf1[f], ne1[f], rtol=1e-2)
         want_skip.append(not o.resample_gate(a, 0.5))
     assert want_skip == [True, True, False, False]       # the cases straddle the gate
@@ -763,6 +762,48 @@ def test_c1_cycle_lockstep_and_convergence():
     assert n_fragile <= 0.02 * 200 * N, n_fragile
     fragile.report({"label": "C1 200 cycles", "particle_updates": 200 * N, "with_fragile_beam": n_fragile,
                     "max_dlogw_fragile_owners": max_dlogw_fragile})
+    pf.close()
+
+
+def test_estimate_options_and_pose_array():
+    """weighted / circular-yaw / full-covariance estimate against the oracle, the reference form
+    unchanged by default, and the PoseArray of loc_loop (auv_pf.py:264-285) for a strided subsample."""
+    M, F = 20000, 2
+    rng = np.random.default_rng(8)
+    poses = np.column_stack([1500.0 + rng.normal(0, 3, F * M), -800.0 + rng.normal(0, 2, F * M), -5 + rng.normal(0, 0.1, F * M),
+                             rng.normal(0, 0.02, F * M), rng.normal(0, 0.02, F * M), rng.normal(np.pi, 0.2, F * M)])   # yaw straddles +-pi
+    poses[:, 2:6] = poses[:, 2:6].astype(np.float32)
+    logw = (rng.normal(0, 2.0, F * M) - 300).astype(np.float32)
+    logw[5] = -np.inf
+    pf = _pf(particle_count=M, n_filters=F)
+    pf.set_poses(poses)
+    pf.set_log_weights(logw)
+    m0, c0 = pf.mean_cov()
+    for f in range(F):
+        sl = slice(f * M, (f + 1) * M)
+        ave, cref, _ = o.estimate(poses[sl])
+        np.testing.assert_allclose(m0[f], ave, atol=1e-9)
+        np.testing.assert_allclose(c0[f], cref, atol=1e-9)
+        for weighted, circ, full in ((True, False, False), (False, True, False), (True, True, True), (False, False, True)):
+            m, c = pf.estimate(weighted=weighted, circular_yaw=circ, full_cov=full)
+            wm, wc = o.estimate_options(poses[sl], logw[sl] if weighted else None, circ, full)
+            np.testing.assert_allclose(m[f, 0:5], wm[0:5], rtol=0, atol=1e-8)
+            assert abs(_dyaw(m[f, 5], wm[5])) < 1e-9
+            np.testing.assert_allclose(c[f], wc, rtol=1e-8, atol=1e-9)
+        # the arithmetic mean of wrapped yaws is meaningless for this cloud, the circular one is not
+        mc, _ = pf.estimate(circular_yaw=True)
+        assert abs(_dyaw(mc[f, 5], np.pi)) < 0.01 and abs(_dyaw(m0[f, 5], np.pi)) > 1.0
+    # PoseArray: strided subsample, quaternion_from_euler on the device
+    for max_poses, stride in ((500, 0), (100000, 0), (64, 7)):
+        pa = pf.pose_array(max_poses=max_poses, stride=stride)
+        st = stride if stride > 0 else -(-M // min(max_poses, M))
+        n = min(-(-M // st), max_poses)
+        assert pa.shape == (F, n, 7)
+        for f in range(F):
+            src = poses[f * M:(f + 1) * M][::st][:n]
+            np.testing.assert_allclose(pa[f, :, 0:3], src[:, 0:3], atol=1e-9)
+            q = np.array([tf_stub.quaternion_from_euler(r, p, y) for r, p, y in src[:50, 3:6]])
+            np.testing.assert_allclose(pa[f, :50, 3:7], q, atol=1e-12)
     pf.close()
 
 

@@ -210,19 +210,34 @@ def test_fixed_point_resample_is_bit_exact(N, scale):
     np.testing.assert_array_equal(anc, c_oracle.systematic(w, u))
 
 
-def test_q_from_a_is_the_exact_floor():
-    """float64 estimate + 128-bit multiply-back == Python big-integer floor division."""
+def test_cdf_exact_is_the_exact_floor():
+    """floor(C 2^52 / A) for prefix sums up to 2^90: float64 estimate + WRAPPING 128-bit multiply-back (the
+    products exceed 128 bits; only their difference has to fit) == Python big-integer floor division, and
+    the estimate is within its documented error of it."""
     rng = np.random.default_rng(11)
     cases = [(1, 1), (5, 5), (1, (1 << 84) + 12345), ((1 << 60), (1 << 60)), ((1 << 60), (1 << 84)),
-             ((1 << 60) - 1, (1 << 60) + 1), (3, 7), ((1 << 59) + 1, 3 * (1 << 59) + 2)]
-    for _ in range(3000):
-        abits = int(rng.integers(1, 61))
-        a = int(rng.integers(1, 1 << abits))
-        extra = int(rng.integers(0, 25))
-        A = a + int(rng.integers(0, 1 << min(abits + extra, 62))) * int(rng.integers(1, 1 << 20))
-        cases.append((a, max(A, a)))
-    for a, A in cases:
-        assert hs.q_from_a(a, A) == (a << 52) // A, (a, A)
+             ((1 << 60) - 1, (1 << 60) + 1), (3, 7), ((1 << 59) + 1, 3 * (1 << 59) + 2), (0, 17),
+             ((1 << 90) - 1, (1 << 90) - 1), ((1 << 90) - 2, (1 << 90) - 1), ((1 << 89) + 1, (1 << 90) - 1),
+             ((1 << 64) - 1, (1 << 64)), ((1 << 64), (1 << 64) + 1), ((1 << 64) + 1, (1 << 65))]
+    for _ in range(6000):
+        abits = int(rng.integers(1, 91))
+        A = int(rng.integers(1, 1 << min(abits, 62))) << max(0, abits - 62) | int(rng.integers(0, 1 << 20))
+        A = max(A, 1)
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            Cv = int(rng.integers(0, 1 << 62)) % (A + 1)
+        elif kind == 1:
+            Cv = A - int(rng.integers(0, min(A, 1000)))
+        elif kind == 2:                                  # right at a quotient boundary: C = ceil(k A / 2^52) +- 1
+            k = int(rng.integers(0, 1 << 52))
+            Cv = min(A, max(0, -((-k * A) >> 52) + int(rng.integers(-1, 2))))
+        else:
+            Cv = (A * int(rng.integers(0, 1 << 30))) >> 30
+        cases.append((Cv, A))
+    for Cv, A in cases:
+        want = (Cv << 52) // A
+        assert hs.cdf_exact(Cv, A) == want, (Cv, A)
+        assert abs(hs.cdf_estimate(Cv, A) - want) <= 3.0 + 1.0, (Cv, A)
 
 
 def test_hinted_searchsorted_is_numpys():
@@ -350,20 +365,43 @@ def test_profile_merge_vs_oracle(name):
     elif name == "ridged_tilted":
         dem, poses, beams, rmax, frag = _ridged_dem(), _cloud(rng, 48, (100.0, 100.0), 8.0, roll_pitch=0.2, z=-21.0), \
             world.make_beams(512, 70.0), 60.0, 5e-2
-    elif name == "border":          # reach leaves the map: every particle falls back to per-ray traversal
+    elif name == "border":          # reach leaves the map: the march finishes the exiting side ray by ray; sensors outside fall back
         dem, poses, beams, frag = world.make_dem(300, 2.0, seed=11), _cloud(rng, 32, (8.0, 590.0), 6.0), world.make_beams(128, 75.0), 2e-2
     else:                           # short range_max: outer beams miss
         dem, poses, beams, rmax = world.make_dem(500, 2.0), _cloud(rng, 48, (450.0, 450.0), 3.0), world.make_beams(256), 30.0
     r, n_prof = hs.raycast_poses(dem, lo, rmax, np.eye(4), poses, beams.astype(np.float32), shift_hi=hi, fan=2, want_swept=True)
     ro, err, fragile = _compare(dem, lo, poses, beams, np.eye(4), rmax, max_fragile_frac=frag, shift_hi=hi, fan=2)
     if name == "border":
-        assert n_prof == 0
+        inside = (poses[:, 0] > 0.0).sum()
+        assert n_prof == inside * r.shape[1]          # every sensor that stands over the map is certified by the march
     elif name in ("tilted", "ridged_tilted"):
         assert n_prof >= 0.75 * r.size          # steep triangle x large tilt: some particles fall back
     else:
         assert n_prof == r.size                 # every particle certified by the profile march
     if name == "short_range":
         assert (ro == rmax).any() and (ro < rmax).any()
+
+
+@pytest.mark.parametrize("terrain", ["smooth", "ridged"])
+def test_profile_merge_near_every_border_and_corner(terrain):
+    """Sensors closer to the map border than their reach: the profile curve runs off the map, the march
+    finishes that side ray by ray (finish_side_by_rays) with the rays clipped to the footprint -- hits
+    right up to the border, misses beyond it, on all four borders and in the corners, any heading."""
+    rng = np.random.default_rng(31)
+    if terrain == "smooth":
+        dem, rmax, z, frag = world.make_dem(400, 1.0, seed=3), 120.0, -5.0, 2e-2
+    else:
+        dem, rmax, z, frag = _ridged_dem(n=400, res=0.5), 60.0, -21.0, 5e-2
+    ext = (dem["z"].shape[0] - 1) * dem["res"]
+    spots = [(0.04, 0.5), (0.96, 0.5), (0.5, 0.03), (0.5, 0.97), (0.05, 0.06), (0.95, 0.04), (0.04, 0.95), (0.97, 0.96),
+             (0.2, 0.5), (0.5, 0.8)]
+    poses = np.concatenate([_cloud(rng, 20, (a * ext, b * ext), 0.01 * ext, roll_pitch=0.05, z=z) for a, b in spots])
+    poses = poses[(poses[:, 0] > 0) & (poses[:, 0] < ext) & (poses[:, 1] > 0) & (poses[:, 1] < ext)]
+    beams = world.make_beams(256, 70.0)
+    r, n_prof = hs.raycast_poses(dem, 2, rmax, np.eye(4), poses, beams.astype(np.float32), shift_hi=5, fan=2, want_swept=True)
+    ro, err, fragile_ = _compare(dem, 2, poses, beams, np.eye(4), rmax, max_fragile_frac=frag, shift_hi=5, fan=2)
+    assert n_prof >= (0.95 if terrain == "smooth" else 0.7) * r.size      # the march, not the per-ray fallback
+    assert (ro >= rmax).mean() > 0.1 and (ro < rmax).mean() > 0.3       # misses beyond the border and hits before it
 
 
 def test_profile_merge_random_fans():
@@ -395,39 +433,32 @@ def test_profile_merge_random_fans():
 
 
 def test_neff_gate_arithmetic_is_the_oracles():
-    """auvpf_math.cuh neff_square / neff_fixed (the device gate of auv_pf.py:174-181) against the
-    oracle's restatement, and against the textbook 1 / sum w^2 it approximates."""
+    """auvpf_math.cuh neff_s / neff_fixed_a (the device gate of auv_pf.py:174-181) against the oracle's
+    restatement, and against the textbook 1 / sum w^2 it approximates; the sums are integers, so any
+    sharding of the particles adds up to the same decision."""
     rng = np.random.default_rng(11)
     cases = [(rng.standard_normal(4096) * s).astype(np.float32) for s in (0.0, 0.3, 3.0, 30.0)]
     cases.append(np.r_[np.float32(0.0), np.full(999, -np.inf, np.float32)])        # one particle holds everything
     cases.append(np.zeros(1, np.float32))
     for lw in cases:
         qq, a, A, m = o.quantise_logw(lw)
-        raw = o.raw_quotients(a)
-        got = hs.neff_fixed(raw)
-        assert got == o.neff_fixed_raw(raw)
+        got = hs.neff_fixed(a)
+        assert got == o.neff_fixed_a(a)
         ref = o.neff(o.weights_from_q(qq))
         assert abs(got - ref) <= 1e-2 * ref
         for ratio in (0.0, 0.1, 0.5, 1.0):
             assert o.resample_gate(a, ratio) == (not (ratio > 0.0 and got >= ratio * len(lw)))
+        if len(a) >= 4:
+            parts = [o.neff_sums(p) for p in np.array_split(a, 4)]
+            assert o.neff_fixed_from_sums(*[sum(x) for x in zip(*parts)]) == got
 
 
 def _quantised(logw):
     qq, a, A, m = o.quantise_logw(np.asarray(logw, np.float32))
-    raw = o.raw_quotients(a)
-    D = (1 << 52) - int(raw.astype(object).sum())
-    assert np.array_equal(raw + (np.arange(len(raw)) < D).astype(np.uint64), qq)
-    return qq, raw, D
+    return qq, a
 
 
-@pytest.mark.parametrize("N", [1, 5, 1023, 1024, 1025, 2047, 2048, 2049, 5000, 70001])
-def test_source_side_select_is_the_references_systematic_resample(N):
-    """The ancestor selection of k_select_gather, run on the host from the same header functions
-    (rel_end_of / sys_count_below): tile table, 32-ary tile location, per-particle closed-form run
-    ends, run heads, max-scan.  Must equal the reference's systematic_resample (resampling.py:135-168)
-    on the same fixed-point weights for diffuse, concentrated, one-hot and mostly-zero weights
-    (zero-weight stretches longer than a scan tile), at the edges of the scan-tile / output-block sizes."""
-    rng = np.random.default_rng(N)
+def _cases(N, rng):
     cases = [rng.normal(0, s, N) for s in (0.0, 0.1, 3.0, 12.0)]
     onehot = np.full(N, -np.inf)
     onehot[N // 2] = 0.0
@@ -438,30 +469,78 @@ def test_source_side_select_is_the_references_systematic_resample(N):
     ends = rng.normal(0, 0.5, N) - 40.0
     ends[0] = ends[-1] = 0.0                             # almost all the mass on the first and the last particle
     cases.append(ends)
-    for logw in cases:
-        qq, raw, D = _quantised(logw)
+    return cases
+
+
+@pytest.mark.parametrize("N", [1, 5, 255, 256, 257, 1023, 1024, 1025, 2047, 2048, 2049, 5000, 70001])
+def test_source_side_select_is_the_references_systematic_resample(N):
+    """The ancestor selection of k_select, run on the host from the same header functions (cdf_estimate /
+    rel_end_fast / cdf_exact / rel_end_of): chunk and tile tables, conservative 32-ary tile location, prefix
+    sums rebuilt chunk by chunk in float64 with the exact fix-up, run heads, max-scan.  Must equal the
+    reference's systematic_resample (resampling.py:135-168) on the same fixed-point weights for diffuse,
+    concentrated, one-hot and mostly-zero weights (zero-weight stretches longer than a tile), at the edges
+    of the chunk / tile / output-block sizes."""
+    rng = np.random.default_rng(N)
+    for logw in _cases(N, rng):
+        qq, a = _quantised(logw)
         w = o.weights_from_q(qq)
         for u in (float(rng.uniform()), 0.0, 1.0 - 2.0 ** -20):
-            np.testing.assert_array_equal(hs.select_source_side(raw, u, D), o.systematic_resample(w, u))
+            np.testing.assert_array_equal(hs.select_source_side(a, u), o.systematic_resample(w, u))
         # u so close to 1 that positions[-1] rounds to 1.0 (u >= 1 - N 2^-54): the reference walks off the end
         # (IndexError, :162-167); every select path hands such an output to the LAST particle
         u = 1.0 - 2.0 ** -53
         pos = (u + np.arange(N)) / float(N)
         idx = np.searchsorted(np.cumsum(w), pos, side="right")
-        got = hs.select_source_side(raw, u, D)
+        got = hs.select_source_side(a, u)
         inside = idx < N
         np.testing.assert_array_equal(got[inside], idx[inside])
         assert (~inside).sum() == (1 if N > 1 else 0) and np.all(got[~inside] == N - 1)
 
 
+@pytest.mark.parametrize("G,M", [(2, 1000), (3, 2048), (4, 5000), (8, 2500), (2, 70001)])
+def test_source_side_select_over_shards(G, M):
+    """The same selection over G shards of M sources (ragged last tile per shard, shard offsets of the
+    prefix sums, ancestors that cross shards): the particle-sharded filter's kernel walk."""
+    rng = np.random.default_rng(G * 1000 + M)
+    N = G * M
+    for logw in _cases(N, rng)[1:]:
+        lw = np.asarray(logw, np.float64)
+        lw[: N // 2 + 3] -= 30.0 * rng.integers(0, 2)                  # sometimes almost all mass on the upper shards
+        qq, a = _quantised(lw)
+        w = o.weights_from_q(qq)
+        for u in (float(rng.uniform()), 0.0):
+            np.testing.assert_array_equal(hs.select_source_side(a, u, G=G), o.systematic_resample(w, u))
+        got = hs.select_source_side(a, 1.0 - 2.0 ** -53, G=G)
+        assert got[-1] == N - 1
+
+
+def test_source_side_select_exact_fixups_are_exercised():
+    """Weights built so that many run ends land EXACTLY on an output position (cdf N 2^-52 - u integral):
+    the estimate cannot decide those, the exact path must, and the result is still the reference's."""
+    N = 4096
+    a = np.full(N, 1 << 40, np.uint64)                   # uniform: cdf_j = (j+1) 2^52 / N exactly
+    qq = o.quantise_a(a)[0]
+    w = o.weights_from_q(qq)
+    for u in (0.0, 0.5, 2.0 ** -30):
+        got, (n_fast, n_exact) = hs.select_source_side(a, u, want_stats=True)
+        np.testing.assert_array_equal(got, o.systematic_resample(w, u))
+        if u == 0.0:
+            assert n_exact > N // 2                      # positions[i] = i / N sit on the cdf grid
+    rng = np.random.default_rng(3)
+    a = (rng.integers(1, 1 << 20, N).astype(np.uint64)) << np.uint64(30)
+    got, (n_fast, n_exact) = hs.select_source_side(a, float(rng.uniform()), want_stats=True)
+    assert n_exact < 0.01 * n_fast + 10                  # generic weights: the exact path is rare
+
+
 def test_source_side_select_one_million():
-    """The same at 1 M + 3 particles with 300 k dead ones in a row (~146 scan tiles without any mass),
+    """The same at 1 M + 3 particles with 300 k dead ones in a row (~146 tiles without any mass),
     against the C oracle's systematic resampler."""
     N = (1 << 20) + 3
     rng = np.random.default_rng(7)
     logw = rng.normal(0, 4.0, N).astype(np.float32)
     logw[100000:400000] = -np.inf
-    qq, raw, D = _quantised(logw)
-    np.testing.assert_array_equal(qq, c_oracle.quantise_logw(logw)[0])
+    qq, m, A = c_oracle.quantise_logw(logw)
+    a = c_oracle.integer_weights(logw, m)
     u = float(rng.uniform())
-    np.testing.assert_array_equal(hs.select_source_side(raw, u, D), c_oracle.systematic(o.weights_from_q(qq), u))
+    np.testing.assert_array_equal(hs.select_source_side(a, u), c_oracle.systematic(o.weights_from_q(qq), u))
+    np.testing.assert_array_equal(hs.select_source_side(a, u, G=8 if N % 8 == 0 else 1), c_oracle.systematic(o.weights_from_q(qq), u))

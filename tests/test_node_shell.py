@@ -55,6 +55,14 @@ class FakeFilter(object):
     def poses(self):
         return np.zeros((self.kw["particle_count"], 6))
 
+    def pose_array(self, max_poses=2000, stride=0):
+        self.calls.append(("pose_array", max_poses))
+        return np.zeros((1, min(max_poses, self.kw["particle_count"]), 7))
+
+    def estimate(self, circular_yaw=False, **kw):
+        self.calls.append(("estimate", circular_yaw))
+        return self.mean_cov()
+
     def mean_cov(self):
         return np.array([[1.0, 2.0, -5.0, 0.01, 0.02, 0.5]]), np.arange(9.0).reshape(1, 3, 3)
 
@@ -125,7 +133,8 @@ def test_loc_loop_publishes_the_reference_layout():
     out = {}
     n = make(publish_estimate=lambda e: out.setdefault("est", e), publish_particles=lambda p: out.setdefault("p", p))
     est = n.loc_loop()
-    assert out["p"].shape == (64, 6) and out["est"] is est
+    assert out["p"].shape == (64, 7) and out["est"] is est         # PoseArray entries [x y z qx qy qz qw] (auv_pf.py:267-275)
+    assert ("pose_array", 2000) in n.pf.calls                      # a bounded, device-built subsample, not pf.poses()
     np.testing.assert_array_equal(est["position"], [1.0, 2.0, -5.0])
     cov = est["covariance"]
     assert len(cov) == 36 and cov[:9] == list(np.arange(9.0)) and cov[9:] == [0.0] * 27   # stride-3 fill (auv_pf.py:249-252)

@@ -42,23 +42,24 @@ class OracleShardOps(object):
         return a
 
     def shard_sum(self, m):
+        """This shard's six words: total of the integer weights (low, high), the gate sums, buffer id."""
         a = self._a(m)
-        return [int((a & np.uint64(0xFFFFFFFF)).sum(dtype=np.uint64)), int((a >> np.uint64(32)).sum(dtype=np.uint64))]
+        self.a = a
+        A = int(a.astype(object).sum())
+        S1, S2lo, S2hi = self.o.neff_sums(a)
+        return [A & 0xFFFFFFFFFFFFFFFF, A >> 64, S1, S2lo, S2hi, 0]
 
-    def shard_scan(self, m, A):
-        a = self._a(m)
-        self.q = np.array([(int(v) << 52) // A for v in a.astype(object)], dtype=np.uint64)
-        self.cdf = np.cumsum(self.q)
-        return int(self.cdf[-1])
-
-    def shard_emit(self, u, q_offset, D, lo, hi):
-        from smarc_navigation_b200.sharded import sys_position
-        G_N = self.N_global
-        jg1 = self.rank * self.M + np.arange(self.M) + 1
-        full = (q_offset + self.cdf.astype(object) + np.minimum(jg1, D)).astype(np.float64) * 2.0 ** -52
+    def shard_emit(self, u, totals_all, lo, hi, rank):
+        """Offspring [lo, hi) of this shard's sources in the GLOBAL cdf = floor((c_off + local prefix) 2^52 / A)."""
+        from smarc_navigation_b200.sharded import sys_position, totals_to_ints
+        assert rank == self.rank
+        As = [totals_to_ints(r)[0] for r in totals_all]
+        c_off, A = sum(As[:rank]), sum(As)
+        C = c_off + np.cumsum(self.a.astype(object))
+        full = np.array([(int(c) << 52) // A for c in C], dtype=np.uint64).astype(np.float64) * 2.0 ** -52
         rec = np.empty((hi - lo, 4))
         for k, i in enumerate(range(lo, hi)):
-            pos = sys_position(u, i, G_N)
+            pos = sys_position(u, i, self.N_global)
             j = min(int(np.searchsorted(full, pos, side="right")), self.M - 1)
             rec[k, 0:2] = self.poses[j, 0:2]
             rec[k, 2] = self.rank * self.M + j          # smuggle the global ancestor id for the check
@@ -86,8 +87,11 @@ def _worker(rank, world, port, M, seed, tmp):
     ops = OracleShardOps(logw[rank * M:(rank + 1) * M], poses[rank * M:(rank + 1) * M], rank, M)
     ops.N_global = N
     plan = resample_sharded(ops, dist, u)
+    # the N_eff gate on the GLOBAL integer sums: every rank takes the same decision, the oracle's
+    gated_lo = resample_sharded(ops, dist, u, neff_ratio=1e-9)["skipped"]       # N_eff is never below 1e-9 N: held back
+    gated_hi = resample_sharded(ops, dist, u, neff_ratio=1.0)["skipped"]        # ... and (almost) always below N
     np.savez(os.path.join(tmp, "r%d.npz" % rank), rec=ops.received, bounds=np.array(plan["bounds"]), u=u, logw=logw,
-             D=plan["D"])
+             gated_lo=gated_lo, gated_hi=gated_hi)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -115,6 +119,9 @@ def test_sharded_resample_equals_single_process(tmp_path, world, M, seed):
     assert b[0] == 0 and b[-1] == world * M and np.all(np.diff(b) >= 0)
     for g in range(world):                                                   # bounds == ancestors' shard ownership
         assert np.all(anc[b[g]:b[g + 1]] // M == g)
+    a = o.quantise_logw(logw)[1]
+    assert all(bool(p["gated_lo"]) for p in parts)
+    assert all(bool(p["gated_hi"]) == (not o.resample_gate(a, 1.0)) for p in parts)
 
 
 def test_plan_exchange_properties():
@@ -122,14 +129,11 @@ def test_plan_exchange_properties():
     rng = np.random.default_rng(0)
     for _ in range(50):
         G, M = int(rng.integers(1, 9)), int(rng.integers(1, 5000))
-        w = rng.dirichlet(np.ones(G) * 0.3)
-        Q = np.floor(w * (1 << 52)).astype(np.int64)
-        Q[-1] -= int(rng.integers(0, G * M))                                  # leave a deficit < N
-        if Q[-1] < 0:
-            continue
+        A_all = [int(v) for v in (rng.dirichlet(np.ones(G) * 0.3) * float(1 << 70)).astype(object)]
+        A_all = [int(a) * int(rng.integers(0, 2) if G > 1 else 1) + (1 if g == 0 else 0) for g, a in enumerate(A_all)]
         u = float(rng.uniform())
-        D, off, bounds = plan_exchange(list(Q), M, u)
-        assert D == (1 << 52) - int(Q.sum()) and bounds[0] == 0 and bounds[-1] == G * M
+        c_off, bounds = plan_exchange(A_all, M, u)
+        assert c_off[0] == 0 and c_off[-1] == sum(A_all) and bounds[0] == 0 and bounds[-1] == G * M
         tot_send = np.zeros((G, G), int)
         for r in range(G):
             s, rc = splits_for(bounds, M, r)
@@ -139,3 +143,28 @@ def test_plan_exchange_properties():
             s, rc = splits_for(bounds, M, r)
             assert list(tot_send[:, r]) == rc
     assert count_below(0.5, 10, 1 << 52) == 10 and count_below(0.5, 10, 0) == 0
+
+
+def test_combine_pose_sums_is_the_global_estimate():
+    """The sharded estimate: per-shard one-pass sums about the shard's own first particle, combined about
+    shard 0's -- equals update_loc_pose's numbers on the concatenated particle set."""
+    from oracle import pf_oracle as o
+    from smarc_navigation_b200.sharded import combine_pose_sums
+    rng = np.random.default_rng(5)
+    G, M = 4, 777
+    poses = np.column_stack([1500.0 + rng.normal(0, 3, G * M), -800.0 + rng.normal(0, 2, G * M), -5 + rng.normal(0, 0.1, G * M),
+                             rng.normal(0, 0.02, G * M), rng.normal(0, 0.02, G * M), rng.uniform(-3.5, 3.5, G * M)])
+    sums = np.zeros((G, 16))
+    for g in range(G):
+        p = poses[g * M:(g + 1) * M]
+        c = p[0, 0:3]
+        d = p[:, 0:3] - c
+        sums[g, 0:3] = d.sum(0)
+        sums[g, 3:6] = p[:, 3:6].sum(0)
+        sums[g, 6] = ((p[:, 5] + np.pi) % (2 * np.pi) - np.pi).sum()
+        sums[g, 7:13] = [(d[:, i] * d[:, j]).sum() for i, j in ((0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2))]
+        sums[g, 13:16] = c
+    mean, cov = combine_pose_sums(sums, M)
+    em, ec, _ = o.estimate(poses)
+    np.testing.assert_allclose(mean, em, atol=1e-9)
+    np.testing.assert_allclose(cov, ec, atol=1e-9)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Resample path alone (k_normalise + k_quotients + k_select_gather with the roughening fused)
+"""Resample path alone (k_weights + k_select with the roughening fused)
 over particle counts: per-kernel CUDA-event times from the library's own profile counters and the
 achieved fraction of the HBM roofline (96 algorithmic bytes per particle).
 One JSON line per size.  L2 is flushed before every resample; the log-weights are rewritten by
