@@ -160,10 +160,11 @@ int auvpf_update_gps(auvpf_handle *h, const double *gps_xy, float *logw_out);
  * logw = -1/(2 std^2) sum_b (r_b - rhat_b)^2 - B_valid log(std sqrt(2 pi)).
  * ranges: (F, B) float32 measured ranges (a LaserScan's ranges[]). */
 int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out);
-/* Particles per filter ((F) int64) that the last auvpf_update_mbes could not certify for the
- * one-march-per-fan-side kernel (sensor reach leaves the map, centre beam missed, a facet steeper than
- * the fan tilt allows) and recast ray by ray; synchronises.  A measurement aid (bench.py reports the
- * fraction per cloud shape). */
+/* How the last auvpf_update_mbes treated the particles, (F, 2) int64 per filter: [0] those whose sensor reach
+ * leaves the map (second pass of the one-march-per-fan-side kernel, with the map-border handling), [1] those
+ * that could not be certified at all (sensor outside the map, centre beam missed, a facet steeper than the fan
+ * tilt allows) and were recast ray by ray; synchronises.  A measurement aid (bench.py reports the fractions per
+ * cloud shape). */
 int auvpf_mbes_flagged(auvpf_handle *h, int64_t *count);
 /* Parity probe: expected ranges (n, B) float32 for n explicit poses (n, 6). */
 int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges_out);
@@ -284,6 +285,13 @@ int auvpf_peer_attach(auvpf_handle *h, auvpf_handle *const *handles, int32_t n_r
 int auvpf_shard_resample(auvpf_handle *h, double u, const double *rough_var, const float *rough_noise,
                          int64_t *ancestors_out_dev);
 int auvpf_shard_degenerate(auvpf_handle *h, int32_t *flag);
+/* The same resample for ALL ranks of one process (handles attached with auvpf_peer_attach; handles[r] is rank
+ * r): enqueued stage by stage over the ranks, so that it cannot deadlock when the ranks' streams share a GPU
+ * or a hardware queue (kernels of different streams are not guaranteed to run concurrently; a rank that
+ * called auvpf_shard_resample alone would wait inside its kernel for posts that are queued behind it).
+ * ancestors_out_dev: n_ranks device pointers ((M) int64 each) or NULL. */
+int auvpf_group_resample(auvpf_handle *const *handles, int32_t n_ranks, double u, const double *rough_var,
+                         int64_t *const *ancestors_out_dev);
 /* Staged path (no peer memory: any topology a collective library reaches).  The caller moves the scalars:
  *   auvpf_shard_max_dev;  all-reduce MAX in place on wmax_i32 (ORDER-PRESERVING int32: an integer MAX is
  *   the float max);  auvpf_shard_weights_dev;  all-gather of totals_u64 (6 uint64: A low, A high, the

@@ -239,26 +239,30 @@ void orc_motion_pred(double *poses, long N, const double v[3], double wz, double
 }
 
 /* ------------------------------------------------------------------ exact normalise spec
- * Mirrors pf_oracle.quantise_logw.  Built with
- * -ffp-contract=off so that no FMA is formed. */
-static const double LOG2E = 0x1.71547652b82fep+0, LN2_HI = 0x1.62e42fee00000p-1, LN2_LO = 0x1.a39ef35793c76p-33;
-static const double EXP_C[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040,
-                                 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
-                                 1.0 / 479001600, 1.0 / 6227020800.0};
-
-#define A_BITS 60   /* a_i = floor(exp(logw_i - max) * 2^60); A = sum a_i kept exactly in 128 bits */
+ * Mirrors pf_oracle.integer_weights / quantise_a.  Built with
+ * -ffp-contract=off so that no FMA is formed: every float operation below is one IEEE single
+ * multiply or add, exactly what NumPy float32 arithmetic and the CUDA __fmul_rn / __fadd_rn do. */
+#define A_BITS 60   /* a_i = floor(E(logw_i - max) * 2^60); A = sum a_i kept exactly in 128 bits */
 
 static uint64_t a_from_logw(float lw, float m, int abits)
 {
-    double x = (double)lw - (double)m;
-    if (!(x >= -745.0)) return 0;                 /* also NaN, -inf */
-    double k = rint(x * LOG2E);
-    double r = (x - k * LN2_HI) - k * LN2_LO;
-    double p = EXP_C[13];
-    for (int n = 12; n >= 0; --n) p = p * r + EXP_C[n];
-    int s = (int)k + abits;
-    if (s < -1) return 0;
-    return (uint64_t)floor(ldexp(p, s));
+    volatile float x = lw - m;
+    if (!(x >= -41.5f)) return 0;                 /* also NaN, -inf */
+    volatile float t = x * 1.44269502f;
+    volatile float k0 = t + 12582912.0f;          /* rint(t) by the 1.5 * 2^23 trick */
+    volatile float k = k0 - 12582912.0f;
+    volatile float h = k * 0.693359375f, l = k * -2.12194440e-4f;
+    volatile float r0 = x - h;
+    volatile float r = r0 - l;
+    static const float C[8] = {1.0f / 5040.0f, 1.0f / 720.0f, 1.0f / 120.0f, 1.0f / 24.0f, 1.0f / 6.0f, 0.5f, 1.0f, 1.0f};
+    volatile float p = C[0];
+    for (int n = 1; n < 8; ++n) { volatile float q = p * r; p = q + C[n]; }
+    float pf = p;
+    uint32_t bits;
+    memcpy(&bits, &pf, sizeof bits);
+    int shift = (int)k + abits - 23 + ((int)(bits >> 23) - 127);
+    uint64_t mant = (uint64_t)((bits & 0x7FFFFFu) | 0x800000u);
+    return shift >= 0 ? mant << shift : (shift > -24 ? mant >> -shift : 0);
 }
 
 /* floor(C 2^52 / A) for C <= A < 2^90 in 128-bit arithmetic, by two 26-bit steps of long division:

@@ -188,48 +188,49 @@ def normalise_logw(logw):
 # The build's own specification: turns fp32 log-weights into
 # float64 weights on a 2^-52 grid that sum to EXACTLY 1 in any summation order,
 # so np.cumsum (sequential), a blocked GPU scan and a cross-GPU offset scan all
-# give bit-identical CDFs.  Uses only IEEE +,* (no FMA), rint, ldexp, floor and
-# integer arithmetic, so C, CUDA and NumPy agree bit for bit.
-_LOG2E = float.fromhex('0x1.71547652b82fep+0')
-_LN2_HI = float.fromhex('0x1.62e42fee00000p-1')
-_LN2_LO = float.fromhex('0x1.a39ef35793c76p-33')
-_EXP_COEF = [1.0 / math.factorial(n) for n in range(14)]   # correctly rounded: n! exact in f64 for n<=13
+# give bit-identical CDFs.  Uses only IEEE single +,* (no FMA) and integer
+# arithmetic, so C, CUDA and NumPy agree bit for bit.
 Q_BITS = 52
+A_BITS = 60      # a_i = floor(E(logw_i - max) * 2^60); A = sum a_i is kept exactly (Python ints / int128)
+_F = np.float32
+_EXP_COEF32 = [_F(1.0) / _F(5040.0), _F(1.0) / _F(720.0), _F(1.0) / _F(120.0), _F(1.0) / _F(24.0), _F(1.0) / _F(6.0),
+               _F(0.5), _F(1.0), _F(1.0)]
 
 
-def exp_det(x):
-    """Deterministic exp for x <= 0: returns ``(p, k)`` with exp(x) ~= p * 2^k."""
-    x = np.asarray(x, np.float64)
-    k = np.rint(x * _LOG2E)
-    r = (x - k * _LN2_HI) - k * _LN2_LO
-    p = np.full_like(r, _EXP_COEF[13])
-    for c in _EXP_COEF[12::-1]:
-        p = p * r + c
-    return p, k
-
-
-A_BITS = 60      # a_i = floor(exp(logw_i - max) * 2^60); A = sum a_i is kept exactly (two 32-bit limbs / int128)
+def integer_weights(logw32, m):
+    """``a_i = floor(E(logw_i - m) 2^60)`` with E the library's fixed float32 evaluation of exp
+    (csrc/auvpf_math.cuh ``a_from_logw``): IEEE single multiplies and adds only -- NumPy float32 arithmetic
+    is exactly that -- then the significand is shifted into place with integers.  ``m``: the float32 maximum
+    the weights refer to (the GLOBAL one for a shard of a sharded filter)."""
+    lw = np.asarray(logw32, np.float32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        x = lw - _F(m)
+        live = x >= _F(-41.5)                                     # NaN compares false
+        x = np.where(live, x, _F(0.0)).astype(np.float32)
+        t = x * _F(1.44269502)
+        k = (t + _F(12582912.0)) - _F(12582912.0)                 # rint(t) for |t| < 2^22
+        r = (x - k * _F(0.693359375)) - k * _F(-2.12194440e-4)
+        p = np.full_like(r, _EXP_COEF32[0])
+        for c in _EXP_COEF32[1:]:
+            p = p * r + c
+    assert p.dtype == np.float32 and r.dtype == np.float32
+    bits = p.view(np.uint32).astype(np.int64)
+    shift = k.astype(np.int64) + (A_BITS - 23) + ((bits >> 23) - 127)
+    mant = ((bits & 0x7FFFFF) | 0x800000).astype(np.uint64)
+    a = np.where(shift >= 0, mant << np.clip(shift, 0, 63).astype(np.uint64),
+                 np.where(shift > -24, mant >> np.clip(-shift, 0, 63).astype(np.uint64), np.uint64(0)))
+    return np.where(live, a, np.uint64(0)).astype(np.uint64)
 
 
 def quantise_logw(logw32):
     """fp32 log-weights -> integer weights ``qq`` (uint64) with sum == 2^52.
     Returns ``(qq, a, A, m)``; raises FloatingPointError when degenerate."""
     lw = np.asarray(logw32, np.float32)
-    M = lw.shape[0]
     finite = lw[~np.isnan(lw)]
     if finite.size == 0 or not np.isfinite(finite.max()):
         raise FloatingPointError("degenerate weights")
     m = np.float32(finite.max())
-    x = lw.astype(np.float64) - np.float64(m)
-    x = np.where(np.isnan(x), -np.inf, x)
-    ab = A_BITS
-    live = x >= -745.0
-    p, k = exp_det(np.where(live, x, 0.0))
-    s = k + ab
-    live &= s >= -1
-    a = np.zeros(M, np.uint64)
-    a[live] = np.floor(np.ldexp(p[live], s[live].astype(np.int64))).astype(np.uint64)
-    return quantise_a(a) + (m,)
+    return quantise_a(integer_weights(lw, m)) + (m,)
 
 
 def quantise_linear(w):

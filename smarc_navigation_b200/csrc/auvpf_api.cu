@@ -106,7 +106,8 @@ struct auvpf_handle {
     double *u = nullptr, *sumsq = nullptr, *sums = nullptr, *gps = nullptr;
     PredictParams *pparams = nullptr;
     int *degenerate = nullptr;
-    unsigned long long *neff_acc = nullptr, *neff_pub = nullptr;   // [3F] integer sums of the N_eff gate (S1, S2 lo, S2 hi)
+    unsigned long long *neff_acc = nullptr;    // [3 F tiles] per-tile partial sums of the N_eff gate (scratch of k_weights)
+    unsigned long long *neff_pub = nullptr;    // [3F] integer sums of the N_eff gate (S1, S2 lo, S2 hi)
     int *skipped = nullptr;                  // [F] 1 = the N_eff gate held the last resample back
     double neff_ratio = 0.0;                 // resample only when N_eff < neff_ratio * N; 0 = always
     bool sumsq_lazy = false;                 // sumsq is computed on request
@@ -123,7 +124,7 @@ struct auvpf_handle {
     unsigned long long *scan2 = nullptr, *totals2 = nullptr;
     unsigned long long *scan3 = nullptr;   // residual resampling: scan of the fractional parts
     int32_t *lost = nullptr, *dupes = nullptr;
-    const double *lin_weights = nullptr;   // device pointer of the last linear weight source
+    unsigned long long *a_pre = nullptr;   // [N] integer weights of the last LINEAR weight source (auvpf_resample_weights)
     int last_src_kind = 0;
     bool have_norm = false;
 
@@ -131,13 +132,14 @@ struct auvpf_handle {
     float *dem_z = nullptr, *mip = nullptr, *mip_hi = nullptr, *beams = nullptr, *meas = nullptr;
     float *beam_aux = nullptr;   // [3B]: |sin th|, 1/|sin th|, 1/cos th
     double *beam_tan = nullptr;  // [2B]: tan |th|, 1 / cos th (profile merge)
-    int *flagged = nullptr;           // [N]: per filter, the particles that need the per-ray kernel
+    int *flagged = nullptr, *flagged2 = nullptr;   // [N] each, per filter: particles for the map-border pass / for the per-ray kernel
     DevBuf probe_flags;
     int *beam_order = nullptr;   // [32 * chunk]
     FanParams fan{};
     DemView dem{};
     bool have_dem = false;
     bool use_profile = true;   // AUVPF_NO_PROFILE=1 in the environment forces the per-ray kernel
+    bool use_pdl = true;       // AUVPF_NO_PDL=1: launch the select kernel without programmatic stream serialisation
     int B = 0;
     FrameParams frame{};
 
@@ -418,7 +420,7 @@ SelShard shard_at(void *base, const int64_t *off)
     SelShard s{};
     s.logw[0] = reinterpret_cast<const float *>(c + off[P_LOGW0]);
     s.logw[1] = reinterpret_cast<const float *>(c + off[P_LOGW1]);
-    s.lin = nullptr;
+    s.apre = nullptr;
     s.tile_prefix = reinterpret_cast<const U128 *>(c + off[P_TILE]);
     s.chunk_sum = reinterpret_cast<const U128 *>(c + off[P_CHUNK]);
     s.st[0] = state_at(base, off + P_ST0);
@@ -456,24 +458,18 @@ int ensure_wmax_f32(auvpf_handle *h)
 // k_weights: a_i, chunk / tile sums, tile prefix, total, gate sums.  use_mailbox: a sharded filter whose
 // peers are attached exchanges the maximum (and afterwards its totals) through the mailbox inside the
 // kernel; otherwise the maximum in wmax_f32 is taken as it is (local, or already reduced by the caller).
-int run_weights(auvpf_handle *h, const WeightSrc &src, bool use_mailbox)
+int run_weights(auvpf_handle *h, const WeightSrc &src, bool use_mailbox, bool post_max = true)
 {
     int rc;
     WeightState ws{};
     if (src.kind == 0) {
         if ((rc = ensure_wmax_f32(h))) return rc;
         ws.wmax_f32 = h->wmax_f32;
-    } else {        // float64 linear weights: separate max pass
-        Prof pr(h, AUVPF_K_NORMALISE);
-        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
-        k_weight_max_lin<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(src.lin, h->M, h->wmax_ordered);
-        k_finish_max_lin<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->wmax_ordered, h->wmax, h->F);
-        LAUNCHED(h, AUVPF_K_NORMALISE, 2);
-        ws.wmax_f32 = nullptr;
-    }
+    } else
+        ws.wmax_f32 = nullptr;      // linear weights: run_linear_prepass left their float64 maximum in h->wmax
     ws.wmax = h->wmax;
     ws.done = h->done;
-    ws.neff_acc = h->neff_acc;
+    ws.tile_neff = h->neff_acc;
     ws.neff_pub = h->neff_pub;
     ws.A = h->A;
     ws.degenerate = h->degenerate;
@@ -481,6 +477,7 @@ int run_weights(auvpf_handle *h, const WeightSrc &src, bool use_mailbox)
     ws.chunk_sum = h->chunk_sum;
     ws.tiles = h->tiles_per_filter;
     ws.logw_parity = h->lw;
+    ws.post_max = post_max ? 1 : 0;
     MailboxView mb = h->mbox;
     if (!use_mailbox) mb.G = 1;
     mb.epoch = h->epoch;
@@ -490,7 +487,6 @@ int run_weights(auvpf_handle *h, const WeightSrc &src, bool use_mailbox)
     CU(cudaGetLastError());
     h->have_norm = true;
     h->last_src_kind = src.kind;
-    h->lin_weights = src.lin;
     h->sumsq_lazy = true;
     return AUVPF_OK;
 }
@@ -498,13 +494,31 @@ int run_weights(auvpf_handle *h, const WeightSrc &src, bool use_mailbox)
 // the weights q_j = cdf_j - cdf_{j-1} of the last k_weights into `q_out` (and / or their sum of squares)
 int run_exact_q(auvpf_handle *h, unsigned long long *q_out, double *sumsq, const U128 *A, const U128 *c_off)
 {
-    WeightSrc src{h->logw, h->lin_weights, h->last_src_kind};
+    WeightSrc src{h->logw, h->a_pre, h->last_src_kind};
     if (sumsq) CU(cudaMemsetAsync(sumsq, 0, sizeof(double) * h->F, h->stream));
     k_exact_q<<<dim3((unsigned)h->tiles_per_filter, (unsigned)h->F), kThreads, 0, h->stream>>>(
         src, h->M, h->wmax, h->tile_prefix, A, c_off, h->tiles_per_filter, h->degenerate, q_out, sumsq);
     LAUNCHED(h, AUVPF_K_OTHER, 1);
     CU(cudaGetLastError());
     return AUVPF_OK;
+}
+
+// launch right behind k_weights with programmatic stream serialisation (the prologue of the select kernel
+// overlaps the tail of the weights kernel; cudaGridDependencySynchronize inside orders the rest)
+template <int kMode>
+cudaError_t launch_select(auvpf_handle *h, dim3 grid, const SelArgs &sa)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kSelThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_select<kMode>, sa);
 }
 
 SelArgs select_args(auvpf_handle *h, const WeightSrc &src)
@@ -521,7 +535,7 @@ SelArgs select_args(auvpf_handle *h, const WeightSrc &src)
     a.cur = h->cur;
     a.logw_parity = h->lw;
     a.local = shard_at(h->slab, h->slab_off);
-    a.local.lin = src.lin;
+    a.local.apre = src.apre;
     a.peers = nullptr;
     a.A = h->A;
     a.c_off = nullptr;
@@ -717,9 +731,7 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     if (h->global_count != h->M)
         return fail(AUVPF_ERR_BADARG, "a particle-sharded filter resamples through auvpf_shard_resample / the staged auvpf_shard_* calls");
     int rc;
-    if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
-
-    // uniforms: resampling.py:157 random()
+    // uniforms: resampling.py:157 random() (uploaded first, so that the two kernels are adjacent in the stream)
     std::vector<double> uh(h->F);
     if (u) {
         if (is_device_ptr(u)) CU(cudaMemcpyAsync(h->u, u, sizeof(double) * h->F, cudaMemcpyDeviceToDevice, h->stream));
@@ -734,6 +746,7 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     const bool inplace = (flags & AUVPF_RS_INPLACE_REF) != 0;
     const float *rn = nullptr;
     if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
+    if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
     int32_t *anc_dev = nullptr;
     if (ancestors_out || inplace) {
         if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
@@ -748,7 +761,7 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     if (inplace) sa.dst.x = nullptr;   // ancestors only
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
-        k_select<kSelLocal><<<grid1(h->M, kSelTile, h->F), kSelThreads, 0, h->stream>>>(sa);
+        CU(launch_select<kSelLocal>(h, grid1(h->M, kSelTile, h->F), sa));
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
@@ -827,7 +840,7 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
             CU(cudaMemcpy(h->wmax_ordered, init.data(), sizeof(long long) * F, cudaMemcpyHostToDevice));
         }
         CU(cudaMalloc(&h->wmax, sizeof(double) * F));
-        CU(cudaMalloc(&h->wmax_f32, sizeof(int) * 2 * F));   // [F] max log-weight | [F] flagged-particle counters
+        CU(cudaMalloc(&h->wmax_f32, sizeof(int) * 3 * F));   // [F] max log-weight | [F] + [F] counters of the two particle lists
         CU(cudaMalloc(&h->done, sizeof(unsigned int) * F));
         CU(cudaMemsetAsync(h->done, 0, sizeof(unsigned int) * F, h->stream));
         CU(cudaMalloc(&h->A, sizeof(U128) * F));
@@ -841,8 +854,7 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
         CU(cudaMalloc(&h->pparams, sizeof(PredictParams) * F * AUVPF_MAX_PREDICT_STEPS));
         CU(cudaMalloc(&h->degenerate, sizeof(int) * F));
         CU(cudaMemsetAsync(h->degenerate, 0, sizeof(int) * F, h->stream));
-        CU(cudaMalloc(&h->neff_acc, sizeof(unsigned long long) * 3 * F));
-        CU(cudaMemsetAsync(h->neff_acc, 0, sizeof(unsigned long long) * 3 * F, h->stream));
+        CU(cudaMalloc(&h->neff_acc, sizeof(unsigned long long) * 3 * F * (size_t)h->tiles_per_filter));
         CU(cudaMalloc(&h->neff_pub, sizeof(unsigned long long) * 3 * F));
         CU(cudaMemsetAsync(h->neff_pub, 0, sizeof(unsigned long long) * 3 * F, h->stream));
         CU(cudaMalloc(&h->shard_degenerate, sizeof(int)));
@@ -883,6 +895,8 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
     {
         const char *np = getenv("AUVPF_NO_PROFILE");
         h->use_profile = !(np && np[0] == '1');
+        const char *nd = getenv("AUVPF_NO_PDL");
+        h->use_pdl = !(nd && nd[0] == '1');
     }
     *out = h;
     return AUVPF_OK;
@@ -898,10 +912,10 @@ int auvpf_destroy(auvpf_handle *h)
     cudaFree(h->slab);
     cudaFree(h->peer_shards);
     void *bufs[] = {h->wmax_ordered, h->wmax,    h->A,      h->neff_acc, h->neff_pub, h->shard_degenerate, h->shard_totals, h->c_off,
-                    h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
+                    h->a_pre, h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
                     h->wmax_f32, h->done, h->scan3, h->skipped,
-                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->probe_flags.p,
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->flagged2, h->probe_flags.p,
                     h->replay_params.p, h->replay_ranges.p, h->replay_u.p, h->replay_stats.p};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
@@ -1125,6 +1139,7 @@ int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
     CU(cudaMemcpy(h->beam_tan, plan.tan_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->beam_tan + B, plan.sec_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
     if (!h->flagged) CU(cudaMalloc(&h->flagged, sizeof(int) * (size_t)h->N));
+    if (!h->flagged2) CU(cudaMalloc(&h->flagged2, sizeof(int) * (size_t)h->N));
     CU(cudaMalloc(&h->beam_order, sizeof(int) * plan.order.size()));
     CU(cudaMemcpy(h->beams, host.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->beam_aux, aux.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
@@ -1287,31 +1302,43 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
                        is_device_ptr(ranges) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
     const double var = h->cfg.meas_std * h->cfg.meas_std;
     flip_logw(h);
-    // one fill resets the maxima AND the flagged-particle counters (both count from kWmaxReset)
-    CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * 2 * h->F, h->stream));
+    // one fill resets the maxima AND the two list counters (all count from kWmaxReset)
+    CU(cudaMemsetAsync(h->wmax_f32, 0x80, sizeof(int) * 3 * h->F, h->stream));
     h->wmax_valid = true;
     {
         Prof pr(h, AUVPF_K_UPDATE_MBES);
         const float nhiv = (float)(-0.5 / var), lnb = (float)std::log(h->cfg.meas_std * std::sqrt(2.0 * kPi));
         const int *list = nullptr;
-        unsigned int *count = reinterpret_cast<unsigned int *>(h->wmax_f32 + h->F);
+        unsigned int *count1 = reinterpret_cast<unsigned int *>(h->wmax_f32 + h->F);        // sensors whose reach leaves the map
+        unsigned int *count2 = reinterpret_cast<unsigned int *>(h->wmax_f32 + 2 * h->F);    // not certified at all: ray by ray
+        const unsigned int *count = count2;
         int64_t ray_blocks = (h->M + kMbesWarps - 1) / kMbesWarps;
         if (h->fan.planar && h->use_profile) {
-            // profile merge: one thread per particle; what it cannot certify goes on a list ...
+            // profile merge, one thread per particle.  Pass 1: every particle, the lean interior variant; a sensor
+            // closer to the border than its reach goes on list 1 ...
             const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B;
             if (h->N <= kProfSmallLimit)
-                k_update_mbes_profile<kProfThreadsSmall, kProfMinBlocksSmall>
+                k_update_mbes_profile<kProfThreadsSmall, kProfMinBlocksSmall, false>
                     <<<grid1(h->M, kProfThreadsSmall, h->F), kProfThreadsSmall, smp, h->stream>>>(
                         h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
-                        (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count, h->wmax_f32);
+                        (float)h->cfg.range_min, nhiv, lnb, h->logw, nullptr, nullptr, h->flagged, count1, h->wmax_f32);
             else
-                k_update_mbes_profile<kProfThreads, kProfMinBlocks>
+                k_update_mbes_profile<kProfThreads, kProfMinBlocks, false>
                     <<<grid1(h->M, kProfThreads, h->F), kProfThreads, smp, h->stream>>>(
                         h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
-                        (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count, h->wmax_f32);
-            LAUNCHED(h, AUVPF_K_UPDATE_MBES, 1);
-            list = h->flagged;
-            // ... that a SMALL grid walks (a full-size grid of early-exit blocks cost 0.35 ms at C3)
+                        (float)h->cfg.range_min, nhiv, lnb, h->logw, nullptr, nullptr, h->flagged, count1, h->wmax_f32);
+            // ... pass 2: list 1 with the map-border variant (a side whose curve runs off the map is finished ray by
+            // ray); a SMALL grid strides over the list (usually empty: its blocks leave at once).  What even that
+            // cannot certify (sensor outside the map, centre beam missed, a facet steeper than the fan tilt allows)
+            // goes on list 2 ...
+            const int blocks2 = (int)std::min<int64_t>((h->M + kProfThreads - 1) / kProfThreads, std::max<int64_t>(1, (148 * kProfMinBlocks) / h->F));
+            k_update_mbes_profile<kProfThreads, kProfMinBlocks, true>
+                <<<dim3((unsigned)blocks2, (unsigned)h->F), kProfThreads, smp, h->stream>>>(
+                    h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
+                    (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count1, h->flagged2, count2, h->wmax_f32);
+            LAUNCHED(h, AUVPF_K_UPDATE_MBES, 2);
+            list = h->flagged2;
+            // ... that another small grid walks ray by ray (a full-size grid of early-exit blocks cost 0.35 ms at C3)
             ray_blocks = std::min<int64_t>(ray_blocks, std::max<int64_t>(1, (148 * 8) / h->F));
         }
         // per-ray kernel: the listed particles (everything, when the beam set is not a planar fan)
@@ -1330,10 +1357,14 @@ int auvpf_mbes_flagged(auvpf_handle *h, int64_t *count)
 {
     if (!h || !count) return fail(AUVPF_ERR_BADARG, "null argument");
     Guard g(h);
-    std::vector<unsigned int> c(h->F);
-    CU(cudaMemcpyAsync(c.data(), h->wmax_f32 + h->F, sizeof(unsigned int) * h->F, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<unsigned int> c(2 * (size_t)h->F);
+    CU(cudaMemcpyAsync(c.data(), h->wmax_f32 + h->F, sizeof(unsigned int) * 2 * h->F, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    for (int f = 0; f < h->F; ++f) count[f] = (h->fan.planar && h->use_profile) ? (int64_t)(c[f] - (unsigned int)kWmaxReset) : h->M;
+    const bool prof = h->fan.planar && h->use_profile;
+    for (int f = 0; f < h->F; ++f) {
+        count[2 * f] = prof ? (int64_t)(c[f] - (unsigned int)kWmaxReset) : 0;                    // second pass (map-border variant)
+        count[2 * f + 1] = prof ? (int64_t)(c[h->F + f] - (unsigned int)kWmaxReset) : h->M;      // recast ray by ray
+    }
     return AUVPF_OK;
 }
 
@@ -1385,7 +1416,18 @@ int auvpf_resample_weights(auvpf_handle *h, const double *weights, int32_t mode,
     const double *wd;
     int rc = stage_in(h, S_IN2, weights, (size_t)h->N, &wd);
     if (rc) return rc;
-    WeightSrc src{nullptr, wd, 1};
+    // float64 maximum, then a_i = floor(w_i / max * 2^60) into a scratch array: the resample kernels read integers
+    if (!h->a_pre) CU(cudaMalloc(&h->a_pre, sizeof(unsigned long long) * h->N));
+    {
+        Prof pr(h, AUVPF_K_NORMALISE);
+        int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
+        k_weight_max_lin<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(wd, h->M, h->wmax_ordered);
+        k_finish_max_lin<<<(h->F + 127) / 128, 128, 0, h->stream>>>(h->wmax_ordered, h->wmax, h->F);
+        k_linear_to_a<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(wd, h->M, h->wmax, h->a_pre);
+        LAUNCHED(h, AUVPF_K_NORMALISE, 3);
+        CU(cudaGetLastError());
+    }
+    WeightSrc src{nullptr, h->a_pre, 1};
     return do_resample(h, src, mode, flags, u, ancestors_out, rough_var, rough_noise);
 }
 
@@ -1977,22 +2019,50 @@ int auvpf_peer_attach(auvpf_handle *h, auvpf_handle *const *handles, int32_t n_r
     return finish_attach(h, offs, n_ranks, my_rank);
 }
 
-int auvpf_shard_resample(auvpf_handle *h, double u, const double *rough_var, const float *rough_noise,
-                         int64_t *ancestors_out_dev)
+namespace {
+int shard_check(auvpf_handle *h)
 {
     if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
     if (h->n_peers < 1) return fail(AUVPF_ERR_STATE, "attach the peers first (auvpf_ipc_import / auvpf_peer_attach)");
     if (h->global_count != h->M * h->n_peers || h->global_offset != h->M * h->my_peer)
         return fail(AUVPF_ERR_STATE, "global_offset / global_count of the handle do not match its rank among the peers");
+    return AUVPF_OK;
+}
+
+// the three stages of a peer-memory resample on one rank
+int shard_stage_max(auvpf_handle *h, bool separate_post, double u)
+{
+    Guard g(h);
+    int rc;
+    h->epoch++;                 // every rank resamples the same number of times: the mailbox's epoch
+    if ((rc = tiny_upload(h, h->u, &u, sizeof u))) return rc;      // (ahead of the kernels: they stay adjacent in the stream)
+    if ((rc = ensure_wmax_f32(h))) return rc;
+    if (separate_post) {
+        MailboxView mb = h->mbox;
+        mb.epoch = h->epoch;
+        k_post_max<<<1, 32, 0, h->stream>>>(h->wmax_f32, mb);
+        LAUNCHED(h, AUVPF_K_NORMALISE, 1);
+        CU(cudaGetLastError());
+    }
+    return AUVPF_OK;
+}
+
+int shard_stage_weights(auvpf_handle *h, bool post_inside)
+{
+    Guard g(h);
+    WeightSrc src{h->logw, nullptr, 0};
+    int rc = run_weights(h, src, /*use_mailbox=*/true, post_inside);
+    h->wmax_valid = false;      // (k_weights used the global maximum; the local one is refreshed by the next update)
+    return rc;
+}
+
+int shard_stage_select(auvpf_handle *h, const double *rough_var, const float *rough_noise, int64_t *ancestors_out_dev)
+{
     Guard g(h);
     int rc;
     const float *rn = nullptr;
     if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
-    h->epoch++;                 // every rank calls this the same number of times: the mailbox's epoch
     WeightSrc src{h->logw, nullptr, 0};
-    if ((rc = run_weights(h, src, /*use_mailbox=*/true))) return rc;
-    h->wmax_valid = false;      // (k_weights used the global maximum; the local one is refreshed by the next update)
-    if ((rc = tiny_upload(h, h->u, &u, sizeof u))) return rc;
     SelArgs sa = select_args(h, src);
     sa.G = h->n_peers;
     sa.rank = h->my_peer;
@@ -2004,7 +2074,7 @@ int auvpf_shard_resample(auvpf_handle *h, double u, const double *rough_var, con
     sa.dst = h->st[1 - h->cur];
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
-        k_select<kSelPeers><<<grid1(h->M, kSelTile, 1), kSelThreads, 0, h->stream>>>(sa);
+        CU(launch_select<kSelPeers>(h, grid1(h->M, kSelTile, 1), sa));
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
@@ -2013,6 +2083,41 @@ int auvpf_shard_resample(auvpf_handle *h, double u, const double *rough_var, con
     h->my_rank_global = h->my_peer;
     h->cur = 1 - h->cur;
     if (rough_var) h->step_rough++;
+    return AUVPF_OK;
+}
+}   // namespace
+
+int auvpf_shard_resample(auvpf_handle *h, double u, const double *rough_var, const float *rough_noise,
+                         int64_t *ancestors_out_dev)
+{
+    int rc = shard_check(h);
+    if (rc) return rc;
+    if ((rc = shard_stage_max(h, /*separate_post=*/false, u))) return rc;
+    if ((rc = shard_stage_weights(h, /*post_inside=*/true))) return rc;
+    return shard_stage_select(h, rough_var, rough_noise, ancestors_out_dev);
+}
+
+// All ranks of ONE process (several GPUs driven by one process, or several handles on one GPU): the same
+// resample, enqueued stage by stage over the ranks -- every rank's post of a stage is in its stream before any
+// rank's kernel that waits for that stage is enqueued.  Kernels of different streams are not guaranteed to run
+// concurrently (streams can share a hardware queue), and with this order a waiting kernel never sits in front
+// of the post it waits for, whatever the mapping.
+int auvpf_group_resample(auvpf_handle *const *handles, int32_t n_ranks, double u, const double *rough_var,
+                         int64_t *const *ancestors_out_dev)
+{
+    if (!handles || n_ranks < 1 || n_ranks > kMaxPeers) return fail(AUVPF_ERR_BADARG, "bad handle list");
+    int rc;
+    for (int r = 0; r < n_ranks; ++r) {
+        if ((rc = shard_check(handles[r]))) return rc;
+        if (handles[r]->n_peers != n_ranks || handles[r]->my_peer != r)
+            return fail(AUVPF_ERR_BADARG, "handles[%d] is not rank %d of %d", r, r, n_ranks);
+    }
+    for (int r = 0; r < n_ranks; ++r)
+        if ((rc = shard_stage_max(handles[r], /*separate_post=*/true, u))) return rc;
+    for (int r = 0; r < n_ranks; ++r)
+        if ((rc = shard_stage_weights(handles[r], /*post_inside=*/false))) return rc;
+    for (int r = 0; r < n_ranks; ++r)
+        if ((rc = shard_stage_select(handles[r], rough_var, nullptr, ancestors_out_dev ? ancestors_out_dev[r] : nullptr))) return rc;
     return AUVPF_OK;
 }
 

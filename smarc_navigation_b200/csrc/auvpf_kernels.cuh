@@ -467,12 +467,17 @@ __device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, co
     return T;
 }
 
-template <int kT, int kMinB>
+// kBorder = false: every particle of the filter (grid over M); a sensor whose reach leaves the map -- or that
+// cannot be certified for another reason -- is put on `flagged_list`.  kBorder = true: the second pass over
+// such a list (`in_list`, `in_count`; the blocks stride over it), with the map-border handling compiled in;
+// what even that cannot certify goes on the next list, for the per-ray kernel.
+template <int kT, int kMinB, bool kBorder>
 __global__ void __launch_bounds__(kT, kMinB)
 k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanParams fan,
                       const double *__restrict__ beam_tan, const float *__restrict__ beam_aux,
                       const float *__restrict__ meas, int B, float range_min, float neg_half_inv_var,
-                      float log_norm_per_beam, float *__restrict__ logw, int *__restrict__ flagged_list,
+                      float log_norm_per_beam, float *__restrict__ logw, const int *__restrict__ in_list,
+                      const unsigned int *__restrict__ in_count, int *__restrict__ flagged_list,
                       unsigned int *__restrict__ flagged_count, int *__restrict__ wmax_f32)
 {
     extern __shared__ double smd[];
@@ -480,6 +485,8 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
     BeamAux *s_aux = reinterpret_cast<BeamAux *>(smd + 2 * B);
     __shared__ int s_valid;
     const int f = blockIdx.y;
+    const int64_t n_work = kBorder ? (int64_t)(in_count[f] - (unsigned int)kWmaxReset) : M;
+    if ((int64_t)blockIdx.x * kT >= n_work) return;
     if (threadIdx.x == 0) s_valid = 0;
     __syncthreads();
     int nv = 0;
@@ -498,24 +505,36 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
     }
     if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
-    const bool active = i < M;              // lanes past the end still walk through (warp-uniform march)
-    const int64_t row = (int64_t)f * M + (active ? i : 0);
-    double p[3];
-    double R[9];
-    particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
     const FanTables T = make_tables(fan, B, s_tan, s_sec, s_aux);
-    float acc = 0.f;
-    const bool ok = profile_particle(dem, T, p, R, active, [&](int, float range, float rm) {
-        const float e = rm - range;
-        if (rm == rm) acc = fmaf(e, e, acc);
-    });
-    const float lw = fmaf(neg_half_inv_var, acc, -(float)s_valid * log_norm_per_beam);
-    if (active) {
-        if (ok) logw[row] = lw;
-        else flagged_list[(int64_t)f * M + (atomicAdd(flagged_count + f, 1u) - (unsigned int)kWmaxReset)] = (int)i;
+    const float lognorm = -(float)s_valid * log_norm_per_beam;
+    // (whole warps enter every trip: the march is a warp-uniform loop, lanes past the end walk through inactive)
+    const int64_t n_round = (n_work + 31) & ~(int64_t)31;
+    for (int64_t w = (int64_t)blockIdx.x * kT + threadIdx.x; w < n_round; w += kBorder ? (int64_t)gridDim.x * kT : n_round) {
+        const bool active = w < n_work;
+        const int64_t i = kBorder ? (active ? (int64_t)in_list[(int64_t)f * M + w] : 0) : w;
+        const int64_t row = (int64_t)f * M + (active ? i : 0);
+        double p[3];
+        double R[9];
+        particle_frame(fp, s.x[row], s.y[row], s.z[row], s.roll[row], s.pitch[row], s.yaw[row], p, R);
+        float acc = 0.f, acc_exit = 0.f;    // acc_exit: beams finished ray by ray at the map border (lives in local memory)
+        const bool ok = profile_particle<kBorder>(
+            dem, T, p, R, active,
+            [&acc](int, float range, float rm) {
+                const float e = rm - range;
+                if (rm == rm) acc = fmaf(e, e, acc);
+            },
+            [&acc_exit](int, float range, float rm) {
+                const float e = rm - range;
+                if (rm == rm) acc_exit = fmaf(e, e, acc_exit);
+            });
+        if (kBorder) acc += acc_exit;
+        const float lw = fmaf(neg_half_inv_var, acc, lognorm);
+        if (active) {
+            if (ok) logw[row] = lw;
+            else flagged_list[(int64_t)f * M + (atomicAdd(flagged_count + f, 1u) - (unsigned int)kWmaxReset)] = (int)i;
+        }
+        warp_publish_max(lw, active && ok, wmax_f32 + f);
     }
-    warp_publish_max(lw, active && ok, wmax_f32 + f);
 }
 
 __global__ void __launch_bounds__(kProfThreads)
@@ -545,7 +564,8 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
     particle_frame(fp, ps[0], ps[1], (float)ps[2], (float)ps[3], (float)ps[4], (float)ps[5], p, R);
     const FanTables T = make_tables(fan, B, s_tan, s_sec, s_aux);
     float *row = out + (size_t)(active ? i : 0) * B;
-    const bool ok = profile_particle(dem, T, p, R, active, [&](int b, float range, float) { row[b] = range; });
+    const bool ok = profile_particle<true>(dem, T, p, R, active, [row](int b, float range, float) { row[b] = range; },
+                                           [row](int b, float range, float) { row[b] = range; });
     if (active) flags[i] = ok ? 0 : 1;
 }
 
@@ -664,10 +684,12 @@ __global__ void k_max_f32(const float *in, int64_t n, int *out_ordered)
 // ---------------------------------------------------------------------------------------------
 // Weight source of a resample:
 //   kind 0: float32 log-weights (the update kernels' output)
-//   kind 1: float64 linear weights (the reference's resample(weights) argument)
+//   kind 1: integer weights a_i = floor(w_i / max w * 2^60) already in memory -- float64 LINEAR weights (the
+//           reference's resample(weights) argument) are converted by a pre-pass (k_linear_to_a), so that their
+//           float64 divisions stay out of the two resample kernels
 struct WeightSrc {
     const float *logw;
-    const double *lin;
+    const unsigned long long *apre;
     int kind;
 };
 

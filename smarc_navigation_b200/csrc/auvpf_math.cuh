@@ -824,14 +824,15 @@ struct FanTables {
 // own: a ray clipped to the footprint (spec: no surface outside, a clipped ray that ends clear MISSES),
 // started at the certified clear prefix and walked the few cells that remain to the border.  The ray is
 // rebuilt from the float64 fan frame D (sensor in grid units, centre / lateral unit vectors):
-// dir = cos th c + sgn sin th a.
+// dir = cos th c + sgn sin th a.  (The map and the tables come BY VALUE: a reference would force the caller's copies --
+// kernel parameters in the constant bank -- into local memory for the whole hot loop.)
 template <class Sink>
 #if defined(__CUDACC__)
 __host__ __device__ __noinline__
 #else
 inline
 #endif
-void finish_side_by_rays(const DemView &m, const FanTables &T, const ProfFrameD *D, float sgf, int j, int n_side, int bb,
+void finish_side_by_rays(const DemView m, const FanTables T, const ProfFrameD *D, float sgf, int j, int n_side, int bb,
                          int bstep, float p_clear, Sink &sink)
 {
     const double fx = floor(D->gox), fy = floor(D->goy);
@@ -858,9 +859,13 @@ void finish_side_by_rays(const DemView &m, const FanTables &T, const ProfFrameD 
 // so the warp waits for the longest SUM of the two sides, not the sum of the longest).
 // Calls sink(beam, range) for every beam in outward order per side.  Returns false if the
 // particle cannot be certified (caller must recast its beams ray by ray).
-template <class Sink>
+// kBorder: the variant for sensors whose reach leaves the map (the curve of a side may run off the map and the
+// side is then finished ray by ray).  It is a COMPILE-TIME variant because its bookkeeping costs the hot loop 15 %
+// (30 more instructions per step and two more live values): interior particles -- normally all of them -- run the
+// lean instantiation, the few near the border are listed and run the other one.
+template <bool kBorder, class Sink, class ExitSink>
 AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFrame &F0, const ProfFrameD *D,
-                            const ProfStart &S, bool active, Sink sink)
+                            const ProfStart &S, bool active, Sink sink, ExitSink &exit_sink)
 {
     // per-side state
     int side = T.n1 > 0 ? 0 : 1;
@@ -910,7 +915,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         if (!act) break;
         if (running) {
             bool fail = false;
-            const bool fresh = j < n_side;     // false only in the step after finish_side_by_rays: nothing left to march
+            const bool fresh = !kBorder || j < n_side;     // false only in the step after a side ran off the map: nothing left to march
             const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
             const float Dv = lower ? z11 - z01 : z10 - z00;
             const float gamma = F0.cz - F0.cgx * Du - F0.cgy * Dv;
@@ -1032,15 +1037,20 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 v = diag ? mid : (vedge ? nc : v);
                 if ((unsigned)cx > (unsigned)(m.W - 2) || (unsigned)cy > (unsigned)(m.H - 2)) {   // left the map
                     AUVPF_REASON(2);
-                    // the rest of this side is finished ray by ray AFTER the march loop (finish_side_by_rays: a call
-                    // in here cost the hot loop 11 % through its register allocation); remember where it stopped
-                    ex_j[side] = j;
-                    ex_bb[side] = bb;
-                    ex_p[side] = p_f;
-                    j = n_side;                                    // the side switch happens in the next step
-                    cx = S.cx;                                     // (any cell inside the map: the step's loads stay in bounds)
-                    cy = S.cy;
-                    zi = cy * m.pitch + cx;
+                    if (kBorder) {
+                        // the rest of this side is finished ray by ray AFTER the march loop (finish_side_by_rays);
+                        // remember where it stopped
+                        ex_j[side] = j;
+                        ex_bb[side] = bb;
+                        ex_p[side] = p_f;
+                        j = n_side;                                // the side switch happens in the next step
+                        cx = S.cx;                                 // (any cell inside the map: the step's loads stay in bounds)
+                        cy = S.cy;
+                        zi = cy * m.pitch + cx;
+                    } else {
+                        ok = false;
+                        running = false;
+                    }
                 } else if (!diag) {
                     z00 = ldg_f(m.z + zi);
                     z01 = ldg_f(m.z + zi + 1);
@@ -1057,11 +1067,11 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         AUVPF_REASON(3);
         ok = false;
     }
-    if (ok && (ex_j[0] >= 0 || ex_j[1] >= 0)) {
+    if (kBorder && ok && (ex_j[0] >= 0 || ex_j[1] >= 0)) {
         for (int sd = 0; sd < 2; ++sd)
             if (ex_j[sd] >= 0)
                 finish_side_by_rays(m, T, D, (float)(sd == 0 ? T.sgn1 : -T.sgn1), ex_j[sd], sd == 0 ? T.n1 : T.B - T.n1,
-                                    ex_bb[sd], sd == 0 ? -1 : 1, ex_p[sd], sink);
+                                    ex_bb[sd], sd == 0 ? -1 : 1, ex_p[sd], exit_sink);
     }
     return ok;
 }
@@ -1071,17 +1081,21 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
 // (not inside the map's interior, centre beam missed, a triangle with gamma >= 0): the caller
 // must then cast its beams ray by ray.  sink(beam, range) may have been called for some beams
 // before a failure; callers discard those.
-template <class Sink>
+// `exit_sink` receives the beams of a side that had to be finished ray by ray (finish_side_by_rays, a
+// __noinline__ call that takes it by reference): it must NOT share captured state with `sink` -- a variable
+// whose address escapes into that call lives in local memory, and the hot loop's accumulator must stay in a
+// register (sharing them cost the kernel 15 %).
+template <bool kBorder, class Sink, class ExitSink>
 AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const double p[3], const double R[9], bool active,
-                               Sink sink)
+                               Sink sink, ExitSink exit_sink)
 {
     bool ok = active;
     const double reach = (double)m.range_max;
     const double xmax = m.x0 + (double)(m.W - 1) * (double)m.res, ymax = m.y0 + (double)(m.H - 1) * (double)m.res;
     // the sensor must stand over the map; its REACH may leave it (the march finishes a side whose curve
     // runs off the map ray by ray, finish_side_by_rays), the rays are then clipped to the footprint
-    if (!(p[0] > m.x0 && p[0] < xmax && p[1] > m.y0 && p[1] < ymax)) ok = false;
     const bool interior = p[0] - reach > m.x0 && p[0] + reach < xmax && p[1] - reach > m.y0 && p[1] + reach < ymax;
+    if (kBorder ? !(p[0] > m.x0 && p[0] < xmax && p[1] > m.y0 && p[1] < ymax) : !interior) ok = false;
     // centre beam from the sensor: q0 = T(0)
     float q0f = 0.f;
     if (ok) {
@@ -1089,7 +1103,7 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
         float lx0, ly0;
         origin_cell(m, p, ix0, iy0, lx0, ly0);
         Ray rc = make_ray(m, p, ix0, iy0, lx0, ly0, R, T.c0[0], T.c0[1], T.c0[2]);
-        q0f = raycast_from(m, rc, 0.f, interior);
+        q0f = raycast_from(m, rc, 0.f, kBorder ? interior : true);
     }
     AUVPF_WARP_SYNC();
     bool all_zero = false;
@@ -1151,13 +1165,13 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
     AUVPF_WARP_SYNC();
     if (all_zero)
         for (int b = 0; b < T.B; ++b) sink(b, 0.f, T.aux[b].meas);
-    const bool marched = profile_march(m, T, F, &D, S, ok && !all_zero, sink);
+    const bool marched = profile_march<kBorder>(m, T, F, &D, S, ok && !all_zero, sink, exit_sink);
     return ok && (all_zero || marched);
 }
 
 // ---------------------------------------------------------------------------------------------
 // Exact fixed-point normalisation (spec: oracle/pf_oracle.py quantise_logw).
-// Only IEEE mul/add with explicit no-FMA intrinsics, rint, floor and integers.
+// Only IEEE mul/add with explicit no-FMA intrinsics and integers.
 AUVPF_HD double mul_rn(double a, double b)
 {
 #if defined(__CUDA_ARCH__)
@@ -1177,23 +1191,58 @@ AUVPF_HD double add_rn(double a, double b)
 #endif
 }
 
-AUVPF_HD uint64_t a_from_x(double x)   // x = logw - max <= 0 (or NaN / -inf)
+AUVPF_HD float fmul_rn(float a, float b)
 {
-    if (!(x >= -745.0)) return 0;
-    const double LOG2E = 0x1.71547652b82fep+0, LN2_HI = 0x1.62e42fee00000p-1, LN2_LO = 0x1.a39ef35793c76p-33;
-    const double C[14] = {1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320,
-                          1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0};
-    double k = rint(mul_rn(x, LOG2E));
-    double r = add_rn(add_rn(x, -mul_rn(k, LN2_HI)), -mul_rn(k, LN2_LO));
-    double p = C[13];
-#pragma unroll
-    for (int n = 12; n >= 0; --n) p = add_rn(mul_rn(p, r), C[n]);
-    int s = (int)k + kABits;
-    if (s < -1) return 0;
-    return (uint64_t)floor(ldexp(p, s));
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b;
+    return r;
+#endif
+}
+AUVPF_HD float fadd_rn(float a, float b)
+{
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b;
+    return r;
+#endif
 }
 
-AUVPF_HD uint64_t a_from_logw(float lw, float m) { return a_from_x((double)lw - (double)m); }
+// The integer weight a = floor(E(lw - m) 2^60) with E a FIXED float32 evaluation of exp: IEEE single
+// multiplies and adds only (no FMA contraction), so NumPy float32 arithmetic (the oracle), C and CUDA agree
+// bit for bit.  x = lw - m <= 0 (float32 subtract), k = rint(x log2 e) by the 1.5 2^23 trick, r = x - k ln2 in
+// two pieces (k LN2_HI is exact), degree-7 Horner, then the float's 24-bit significand is shifted into place
+// with integer operations -- no float64, no ldexp / floor calls.  a carries 24 significant bits: the
+// float32 log-weight it comes from carries fewer (one ulp of logw ~ -600 moves the weight by 6e-5 relative).
+// Round 1 evaluated exp in float64 (26 dependent double operations per particle); the two resample kernels
+// were bound by exactly that arithmetic.
+AUVPF_HD uint64_t a_from_logw(float lw, float m)
+{
+    const float x = fadd_rn(lw, -m);
+    if (!(x >= -41.5f)) return 0;                 // NaN, -inf and everything below 2^-59.9 of the maximum
+    const float t = fmul_rn(x, 1.44269502f);
+    const float k = fadd_rn(fadd_rn(t, 12582912.0f), -12582912.0f);
+    const float r = fadd_rn(fadd_rn(x, -fmul_rn(k, 0.693359375f)), -fmul_rn(k, -2.12194440e-4f));
+    float p = 1.0f / 5040.0f;
+    p = fadd_rn(fmul_rn(p, r), 1.0f / 720.0f);
+    p = fadd_rn(fmul_rn(p, r), 1.0f / 120.0f);
+    p = fadd_rn(fmul_rn(p, r), 1.0f / 24.0f);
+    p = fadd_rn(fmul_rn(p, r), 1.0f / 6.0f);
+    p = fadd_rn(fmul_rn(p, r), 0.5f);
+    p = fadd_rn(fmul_rn(p, r), 1.0f);
+    p = fadd_rn(fmul_rn(p, r), 1.0f);
+    uint32_t bits;
+#if defined(__CUDA_ARCH__)
+    bits = __float_as_uint(p);
+#else
+    memcpy(&bits, &p, sizeof bits);
+#endif
+    const int shift = (int)k + kABits - 23 + ((int)(bits >> 23) - 127);       // p in [0.70, 1.42]: always a normal float
+    const uint64_t mant = (uint64_t)((bits & 0x7FFFFFu) | 0x800000u);
+    return shift >= 0 ? mant << shift : (shift > -24 ? mant >> -shift : 0ull);
+}
 
 AUVPF_HD uint64_t a_from_linear(double w, double wmax)
 {

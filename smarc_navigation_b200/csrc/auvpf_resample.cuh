@@ -15,6 +15,8 @@
 // front of k_weights, one for the totals in front of k_select), the select kernel reads the owners'
 // log-weights, chunk tables and state over NVLink.  No NCCL call and no host round trip in the cycle.
 #pragma once
+#include <cstdio>
+
 #include "auvpf_kernels.cuh"
 
 namespace auvpf {
@@ -33,6 +35,10 @@ static_assert(kChunksPerTile == kThreads / 32, "one chunk per warp of the weight
 // after all its blocks consumed stage 0 of epoch e (and the same one stage later).
 constexpr int kMboxStages = 2, kMboxWords = 8, kMboxFlag = 7;
 constexpr size_t kMboxBytes = sizeof(unsigned long long) * kMboxStages * kMaxPeers * kMboxWords;
+#ifndef AUVPF_MBOX_TIMEOUT_MS
+#define AUVPF_MBOX_TIMEOUT_MS 20000
+#endif
+constexpr unsigned long long kMboxTimeoutNs = (unsigned long long)AUVPF_MBOX_TIMEOUT_MS * 1000000ull;
 
 struct MailboxView {
     unsigned long long *peer[kMaxPeers];      // every rank's mailbox (own included), mapped into this process
@@ -76,8 +82,24 @@ __device__ __forceinline__ void mbox_post(const MailboxView &mb, int stage, cons
 __device__ __forceinline__ const unsigned long long *mbox_wait(const MailboxView &mb, int stage, int src)
 {
     const unsigned long long *slot = mb.peer[mb.rank] + (size_t)(stage * kMaxPeers + src) * kMboxWords;
-    while (ld_acquire_sys(slot + kMboxFlag) != (unsigned long long)mb.epoch) __nanosleep(64);
-    return slot;
+    if (ld_acquire_sys(slot + kMboxFlag) == (unsigned long long)mb.epoch) return slot;
+    // A peer that never posts (a rank died, or the ranks' calls got out of step) must not hang the GPU: after
+    // kMboxTimeoutNs the kernel reports and traps, which fails the stream with an error the host sees.
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        for (int i = 0; i < 64; ++i) {
+            if (ld_acquire_sys(slot + kMboxFlag) == (unsigned long long)mb.epoch) return slot;
+            __nanosleep(64);
+        }
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > kMboxTimeoutNs) {
+            printf("auvpf mailbox: rank %d waited %llu ms for rank %d, stage %d, epoch %u (flag holds %llu)\n", mb.rank,
+                   (t1 - t0) / 1000000ull, src, stage, mb.epoch, ld_acquire_sys(slot + kMboxFlag));
+            __trap();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -86,7 +108,7 @@ struct WeightState {
     int *wmax_f32;                  // [F] ordered-int float32 max published by the update kernels, or nullptr ...
     double *wmax;                   // [F] ... in: the float64 max of a linear source (k_weight_max); out: the max used
     unsigned int *done;             // [F] ticket, zero on entry and on exit
-    unsigned long long *neff_acc;   // [3F] S1, S2 low, S2 high accumulators, zero on entry and on exit
+    unsigned long long *tile_neff;  // [F * tiles * 3] scratch: per tile S1, S2 low, S2 high of the N_eff gate
     unsigned long long *neff_pub;   // [3F] out: this shard's sums
     U128 *A;                        // [F] out: this shard's total
     int *degenerate;                // [F] out (single GPU: no finite weight; sharded: decided by the select kernel)
@@ -94,11 +116,21 @@ struct WeightState {
     U128 *chunk_sum;                // [F * tiles * 8] out: raw sums of 256 particles
     int tiles;
     int logw_parity;                // which of the two log-weight buffers the source is (told to the peers)
+    int post_max;                   // sharded: this kernel posts the shard's maximum itself (0: k_post_max did, see auvpf_group_resample)
 };
 
-__device__ __forceinline__ uint64_t weight_a(const WeightSrc &w, int64_t row, double m)
+// the 8 raw log-weights of one lane (kind 0): rows [row0, row0 + 8), the first `left` of them exist
+__device__ __forceinline__ void load_logw8(const float *logw, int64_t row0, int64_t left, float v[kChunkItems])
 {
-    return w.kind == 0 ? a_from_x((double)w.logw[row] - m) : a_from_linear(w.lin[row], m);
+    if (left >= kChunkItems && (reinterpret_cast<uintptr_t>(logw + row0) & 15) == 0) {
+        const float4 p = *reinterpret_cast<const float4 *>(logw + row0);
+        const float4 q = *reinterpret_cast<const float4 *>(logw + row0 + 4);
+        v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w;
+        v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kChunkItems; ++k) v[k] = k < left ? logw[row0 + k] : -INFINITY;
+    }
 }
 
 // the 8 consecutive a_i of one lane: rows [row0, row0 + 8), the first `left` of them exist
@@ -106,20 +138,13 @@ __device__ __forceinline__ void load_a8(const WeightSrc &w, int64_t row0, int64_
 {
     if (w.kind == 0) {
         float v[kChunkItems];
-        if (left >= kChunkItems && (reinterpret_cast<uintptr_t>(w.logw + row0) & 15) == 0) {
-            const float4 p = *reinterpret_cast<const float4 *>(w.logw + row0);
-            const float4 q = *reinterpret_cast<const float4 *>(w.logw + row0 + 4);
-            v[0] = p.x; v[1] = p.y; v[2] = p.z; v[3] = p.w;
-            v[4] = q.x; v[5] = q.y; v[6] = q.z; v[7] = q.w;
-        } else {
+        load_logw8(w.logw, row0, left, v);
+        const float mf = (float)m;           // (the maximum of float32 log-weights: exact)
 #pragma unroll
-            for (int k = 0; k < kChunkItems; ++k) v[k] = k < left ? w.logw[row0 + k] : -INFINITY;
-        }
-#pragma unroll
-        for (int k = 0; k < kChunkItems; ++k) a[k] = a_from_x((double)v[k] - m);
+        for (int k = 0; k < kChunkItems; ++k) a[k] = a_from_logw(v[k], mf);
     } else {
 #pragma unroll
-        for (int k = 0; k < kChunkItems; ++k) a[k] = k < left ? a_from_linear(w.lin[row0 + k], m) : 0ull;
+        for (int k = 0; k < kChunkItems; ++k) a[k] = k < left ? w.apre[row0 + k] : 0ull;
     }
 }
 
@@ -138,6 +163,10 @@ __device__ __forceinline__ U128 shfl_up_u128(U128 v, int delta)
     return r;
 }
 
+// The kernel is ONE wave of blocks (a tile of 2048 particles each) and as long as one block's chain of dependent
+// global round trips, so the chain is kept short: the log-weights are requested before the maximum is known, the
+// gate's partial sums travel with the tile sum as plain stores (no atomics besides the ticket), and on one GPU
+// every thread reads the maximum itself (no thread-0 prologue, no barrier in front of the loads).
 __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M, WeightState ws, MailboxView mb)
 {
     __shared__ unsigned long long s_part[kThreads / 32][5];
@@ -145,36 +174,43 @@ __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M,
     __shared__ bool s_last;
     const int f = blockIdx.y, tile = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // programmatic dependent launch: the select kernel behind this one may be scheduled now -- its blocks set up
+    // and then wait (cudaGridDependencySynchronize) until this grid has completed and its writes are visible
+    cudaTriggerProgrammaticLaunchCompletion();
+    const int64_t j0 = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kChunkItems;
+    float v[kChunkItems];
+    if (w.kind == 0) load_logw8(w.logw, (int64_t)f * M + j0, M - j0, v);
     // ---- the maximum: local, or exchanged through the mailbox (stage 0) ----
-    if (threadIdx.x == 0) {
-        double m;
-        if (mb.G > 1) {
-            if (tile == 0) {
+    double m;
+    if (mb.G > 1) {
+        if (threadIdx.x == 0) {
+            if (tile == 0 && ws.post_max) {
                 const unsigned long long mine = (unsigned long long)(unsigned int)ws.wmax_f32[0];
                 mbox_post(mb, 0, &mine, 1);
             }
             int k = kWmaxReset;
             for (int g = 0; g < mb.G; ++g) k = max(k, (int)(unsigned int)ld_relaxed_sys(mbox_wait(mb, 0, g)));
-            m = k > kWmaxReset ? (double)ordered_to_float(k) : -INFINITY;
-        } else if (ws.wmax_f32) {
-            const int k = ws.wmax_f32[f];
-            m = k > kWmaxReset ? (double)ordered_to_float(k) : -INFINITY;
-        } else
-            m = ws.wmax[f];
-        s_m = m;
-    }
-    __syncthreads();
-    const double m = s_m;
+            s_m = k > kWmaxReset ? (double)ordered_to_float(k) : -INFINITY;
+        }
+        __syncthreads();
+        m = s_m;
+    } else if (ws.wmax_f32) {
+        const int k = ws.wmax_f32[f];
+        m = k > kWmaxReset ? (double)ordered_to_float(k) : -INFINITY;
+    } else
+        m = ws.wmax[f];
     const bool bad = !isfinite(m) || (w.kind == 1 && !(m > 0.0));
     // ---- a_i of this tile: one chunk of 256 per warp, 8 consecutive particles per lane ----
-    const int64_t j0 = (int64_t)tile * kScanTile + (int64_t)threadIdx.x * kChunkItems;
     uint64_t a[kChunkItems];
-    if (!bad)
-        load_a8(w, (int64_t)f * M + j0, M - j0, m, a);
-    else {
+    if (bad) {
 #pragma unroll
         for (int k = 0; k < kChunkItems; ++k) a[k] = 0ull;
-    }
+    } else if (w.kind == 0) {
+        const float mf = (float)m;
+#pragma unroll
+        for (int k = 0; k < kChunkItems; ++k) a[k] = a_from_logw(v[k], mf);
+    } else
+        load_a8(w, (int64_t)f * M + j0, M - j0, m, a);
     unsigned long long lo = 0, hi = 0, s1 = 0, s2lo = 0, s2hi = 0;
 #pragma unroll
     for (int k = 0; k < kChunkItems; ++k) {
@@ -200,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M,
     }
     __syncthreads();
     U128 *tab = ws.tile_prefix + (size_t)f * ws.tiles;
+    unsigned long long *tneff = ws.tile_neff + (size_t)f * ws.tiles * 3;
     if (threadIdx.x == 0) {
         unsigned long long t[5] = {0, 0, 0, 0, 0};
 #pragma unroll
@@ -207,26 +244,31 @@ __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M,
 #pragma unroll
             for (int c = 0; c < 5; ++c) t[c] += s_part[k][c];
         const U128 tot = u128_from_limbs(t[0], t[1]);
-        // (two 64-bit stores: the reader below is ordered behind the ticket)
+        // (plain 64-bit stores: the reader below is ordered behind the fence and the ticket)
         reinterpret_cast<volatile unsigned long long *>(tab + tile)[0] = tot.lo;
         reinterpret_cast<volatile unsigned long long *>(tab + tile)[1] = tot.hi;
-        if (t[2]) atomicAdd(ws.neff_acc + 3 * f, t[2]);          // integer atomics: independent of the arrival order
-        if (t[3]) atomicAdd(ws.neff_acc + 3 * f + 1, t[3]);
-        if (t[4]) atomicAdd(ws.neff_acc + 3 * f + 2, t[4]);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) reinterpret_cast<volatile unsigned long long *>(tneff)[3 * tile + c] = t[2 + c];
         __threadfence();
         s_last = atomicAdd(ws.done + f, 1u) == (unsigned int)ws.tiles - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // ---- last block of the filter: tile sums -> inclusive prefixes (a run of consecutive tiles per thread) ----
+    // ---- last block of the filter: tile sums -> inclusive prefixes (a run of consecutive tiles per thread),
+    // the gate's sums added up (integers: the order does not matter) ----
     const int per = (ws.tiles + kThreads - 1) / kThreads;
     const int t0 = threadIdx.x * per;
     U128 run = u128(0);
+    unsigned long long n1 = 0, n2lo = 0, n2hi = 0;
     for (int k = 0; k < per; ++k)
         if (t0 + k < ws.tiles) {
             const volatile unsigned long long *p = reinterpret_cast<volatile unsigned long long *>(tab + t0 + k);
             run = run + u128(p[0], p[1]);
+            const volatile unsigned long long *q = reinterpret_cast<volatile unsigned long long *>(tneff) + 3 * (t0 + k);
+            n1 += q[0];
+            n2lo += q[1];
+            n2hi += q[2];
         }
     U128 incl = run;
 #pragma unroll
@@ -234,8 +276,16 @@ __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M,
         const U128 n = shfl_up_u128(incl, o);
         if (lane >= o) incl = incl + n;
     }
+    n1 = warp_sum_u64(n1);
+    n2lo = warp_sum_u64(n2lo);
+    n2hi = warp_sum_u64(n2hi);
     __shared__ U128 s_w[kThreads / 32];
     if (lane == 31) s_w[warp] = incl;
+    if (lane == 0) {                         // (s_part is free: every warp passed the barrier above)
+        s_part[warp][2] = n1;
+        s_part[warp][3] = n2lo;
+        s_part[warp][4] = n2hi;
+    }
     __syncthreads();
     U128 acc = u128(0), total = u128(0);
 #pragma unroll
@@ -243,8 +293,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M,
         if (k < warp) acc = acc + s_w[k];
         total = total + s_w[k];
     }
-    // exclusive offset of this thread's run = acc + (incl - run): add the lower lanes' runs
-    {
+    {   // exclusive offset of this thread's run: the warps below + the lanes below
         U128 below = shfl_up_u128(incl, 1);
         if (lane == 0) below = u128(0);
         acc = acc + below;
@@ -259,12 +308,16 @@ __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M,
         ws.A[f] = total;
         ws.wmax[f] = m;
         ws.degenerate[f] = (bad || (total.lo == 0 && total.hi == 0)) ? 1 : 0;
-        unsigned long long pay[7];
+        unsigned long long pay[6];
         pay[0] = total.lo;
         pay[1] = total.hi;
+#pragma unroll
         for (int c = 0; c < 3; ++c) {
-            pay[2 + c] = atomicExch(ws.neff_acc + 3 * f + c, 0ull);
-            ws.neff_pub[3 * f + c] = pay[2 + c];
+            unsigned long long v3 = 0;
+#pragma unroll
+            for (int k = 0; k < kThreads / 32; ++k) v3 += s_part[k][2 + c];
+            pay[2 + c] = v3;
+            ws.neff_pub[3 * f + c] = v3;
         }
         pay[5] = (unsigned long long)ws.logw_parity;
         ws.done[f] = 0u;
@@ -273,6 +326,24 @@ __global__ void __launch_bounds__(kThreads, 4) k_weights(WeightSrc w, int64_t M,
             mbox_post(mb, 1, pay, 6);
         }
     }
+}
+
+// stage 0 on its own (auvpf_group_resample: every rank's post is enqueued before any rank's wait)
+__global__ void k_post_max(const int *wmax_f32, MailboxView mb)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const unsigned long long mine = (unsigned long long)(unsigned int)wmax_f32[0];
+    mbox_post(mb, 0, &mine, 1);
+}
+
+// linear float64 weights -> integer weights (pre-pass of auvpf_resample_weights)
+__global__ void __launch_bounds__(kThreads) k_linear_to_a(const double *lin, int64_t M, const double *wmax, unsigned long long *a)
+{
+    const int f = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= M) return;
+    const double m = wmax[f];
+    a[(int64_t)f * M + i] = (isfinite(m) && m > 0.0) ? a_from_linear(lin[(int64_t)f * M + i], m) : 0ull;
 }
 
 // float64 maximum of a linear weight source (the reference's resample(weights) argument)
@@ -300,7 +371,7 @@ __global__ void k_finish_max_lin(long long *wmax_ordered, double *wmax, int F)
 // k_select
 struct SelShard {                       // what the select kernel reads of one shard
     const float *logw[2];               // the two log-weight buffers (a shard's update writes the one its peers are not reading)
-    const double *lin;                  // linear float64 source (kind 1; single GPU only)
+    const unsigned long long *apre;     // integer weights of a linear source (kind 1; single GPU only)
     const U128 *tile_prefix, *chunk_sum;
     StateView st[2];                    // the double-buffered state
 };
@@ -336,6 +407,16 @@ struct SelArgs {
 
 enum SelMode : int { kSelLocal = 0, kSelPeers = 1, kSelRecords = 2 };
 
+// the rare exact path (the estimate landed within 1e-5 of an integer): kept out of line, it is 128-bit arithmetic
+// and two search loops that would otherwise be inlined ten times into the select kernel (its instruction-cache
+// misses were 2.4 stall cycles per issued instruction)
+__device__ __noinline__ int rel_end_exact(double u, double n, int64_t n_global, int64_t g0, int nblk, U128 C, U128 A)
+{
+    const SysPos spos = make_sys_pos(u, n);
+    const RelEndCtx rctx = make_rel_end(u, n, g0, nblk);
+    return rel_end_of(spos, n_global, rctx, cdf_exact(C, make_cdfdiv(A)));
+}
+
 template <int kMode>
 __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs a)
 {
@@ -352,63 +433,72 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     if (k0 >= a.n_out) return;
     const int64_t k1 = min(k0 + (int64_t)kSelTile, a.n_out) - 1;
     const int G = kMode == kSelLocal ? 1 : a.G;
-    // ---- shard offsets, total, gate ----
-    if (threadIdx.x == 0) {
-        unsigned long long S1 = 0, S2lo = 0, S2hi = 0;
-        int skip = 0;
-        if (kMode == kSelPeers) {
-            U128 acc = u128(0);
-            for (int g = 0; g < G; ++g) {
-                const unsigned long long *slot = mbox_wait(a.mb, 1, g);
-                s_coff[g] = acc;
-                acc = acc + u128(ld_relaxed_sys(slot), ld_relaxed_sys(slot + 1));
-                S1 += ld_relaxed_sys(slot + 2);
-                S2lo += ld_relaxed_sys(slot + 3);
-                S2hi += ld_relaxed_sys(slot + 4);
-                s_parity[g] = (int)ld_relaxed_sys(slot + 5);
-            }
-            s_coff[G] = acc;
-            if (acc.lo == 0 && acc.hi == 0) skip = 1;
-            if (blockIdx.x == 0) {
-                *a.degenerate_out = skip;
-                if (a.coff_out)
-                    for (int g = 0; g <= G; ++g) a.coff_out[g] = s_coff[g];
-            }
-        } else if (kMode == kSelRecords) {
-            for (int g = 0; g <= G; ++g) s_coff[g] = a.c_off[g];
-            s_parity[a.rank] = a.logw_parity;
-        } else {
-            s_coff[0] = u128(0);
-            s_coff[1] = a.A[f];
-            s_parity[0] = a.logw_parity;
-            if (a.degenerate[f]) skip = 1;
-            S1 = a.neff_pub[3 * f];
-            S2lo = a.neff_pub[3 * f + 1];
-            S2hi = a.neff_pub[3 * f + 2];
-        }
-        if (kMode != kSelRecords && !skip) {
-            // N_eff gate (auv_pf.py:174-181, commented out in the reference): every block evaluates the same integers
-            const bool gated = a.gate_thresh > 0.0 && neff_fixed_a(S1, S2lo, S2hi) >= a.gate_thresh;
-            if (blockIdx.x == 0 && a.skipped) a.skipped[f] = gated ? 1 : 0;
-            if (gated) skip = 1;
-        } else if (kMode != kSelRecords && blockIdx.x == 0 && a.skipped)
-            a.skipped[f] = 0;
-        s_skip = skip;
-    }
-    if (kMode == kSelPeers) {
-        if (threadIdx.x < G * (int)(sizeof(SelShard) / sizeof(unsigned long long))) {
-            const int g = threadIdx.x / (int)(sizeof(SelShard) / sizeof(unsigned long long));
-            const int wd = threadIdx.x % (int)(sizeof(SelShard) / sizeof(unsigned long long));
-            reinterpret_cast<unsigned long long *>(&s_shard[g])[wd] = reinterpret_cast<const unsigned long long *>(a.peers + g)[wd];
-        }
-    } else if (threadIdx.x == 0)
-        s_shard[0] = a.local;
 #pragma unroll
     for (int r = 0; r < kSelItems; ++r) s_head[threadIdx.x * kSelItems + r] = 0;
-    __syncthreads();
-    auto shard = [&](int g) -> const SelShard & { return s_shard[kMode == kSelPeers ? g : 0]; };
+    // launched with programmatic stream serialisation right behind k_weights: everything above overlapped its tail;
+    // from here on its results are complete and visible
+    cudaGridDependencySynchronize();
+    // ---- shard offsets, total, gate ----
+    bool skip_local = false;
+    if (kMode == kSelLocal) {
+        // one GPU: every thread reads the filter's scalars itself (uniform loads) -- no thread-0 prologue, and the
+        // block's first barrier is the one behind the tile search
+        skip_local = a.degenerate[f] != 0;
+        const bool gated = !skip_local && a.gate_thresh > 0.0 &&
+                           neff_fixed_a(a.neff_pub[3 * f], a.neff_pub[3 * f + 1], a.neff_pub[3 * f + 2]) >= a.gate_thresh;
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.skipped) a.skipped[f] = gated ? 1 : 0;
+        skip_local = skip_local || gated;
+    } else {
+        if (threadIdx.x == 0) {
+            unsigned long long S1 = 0, S2lo = 0, S2hi = 0;
+            int skip = 0;
+            if (kMode == kSelPeers) {
+                U128 acc = u128(0);
+                for (int g = 0; g < G; ++g) {
+                    const unsigned long long *slot = mbox_wait(a.mb, 1, g);
+                    s_coff[g] = acc;
+                    acc = acc + u128(ld_relaxed_sys(slot), ld_relaxed_sys(slot + 1));
+                    S1 += ld_relaxed_sys(slot + 2);
+                    S2lo += ld_relaxed_sys(slot + 3);
+                    S2hi += ld_relaxed_sys(slot + 4);
+                    s_parity[g] = (int)ld_relaxed_sys(slot + 5);
+                }
+                s_coff[G] = acc;
+                if (acc.lo == 0 && acc.hi == 0) skip = 1;
+                if (blockIdx.x == 0) {
+                    *a.degenerate_out = skip;
+                    if (a.coff_out)
+                        for (int g = 0; g <= G; ++g) a.coff_out[g] = s_coff[g];
+                }
+                if (!skip) {
+                    // N_eff gate (auv_pf.py:174-181, commented out in the reference) on the GLOBAL integer sums
+                    const bool gated = a.gate_thresh > 0.0 && neff_fixed_a(S1, S2lo, S2hi) >= a.gate_thresh;
+                    if (blockIdx.x == 0 && a.skipped) a.skipped[f] = gated ? 1 : 0;
+                    if (gated) skip = 1;
+                } else if (blockIdx.x == 0 && a.skipped)
+                    a.skipped[f] = 0;
+            } else {
+                for (int g = 0; g <= G; ++g) s_coff[g] = a.c_off[g];
+                s_parity[a.rank] = a.logw_parity;
+            }
+            s_skip = skip;
+        }
+        if (kMode == kSelPeers) {
+            if (threadIdx.x < G * (int)(sizeof(SelShard) / sizeof(unsigned long long))) {
+                const int g = threadIdx.x / (int)(sizeof(SelShard) / sizeof(unsigned long long));
+                const int wd = threadIdx.x % (int)(sizeof(SelShard) / sizeof(unsigned long long));
+                reinterpret_cast<unsigned long long *>(&s_shard[g])[wd] = reinterpret_cast<const unsigned long long *>(a.peers + g)[wd];
+            }
+        } else if (threadIdx.x == 0)
+            s_shard[0] = a.local;
+    }
+    if (kMode != kSelLocal) __syncthreads();
+    // (local mode reads the shard straight from the kernel parameters: the constant bank)
+    auto shard = [&](int g) -> const SelShard & { return kMode == kSelLocal ? a.local : s_shard[kMode == kSelPeers ? g : 0]; };
+    auto coff = [&](int g) -> U128 { return kMode == kSelLocal ? (g == 0 ? u128(0) : a.A[f]) : s_coff[g]; };
+    auto parity = [&](int g) -> int { return kMode == kSelLocal ? a.logw_parity : s_parity[kMode == kSelPeers ? g : a.rank]; };
     const int my_g = kMode == kSelLocal ? 0 : a.rank;
-    if (s_skip) {
+    if (kMode == kSelLocal ? skip_local : (s_skip != 0)) {
         // no finite weight (or the N_eff gate holds the resample back): the state is carried over unchanged
         // (identity ancestors), so the buffers can flip without the host having to look at a flag first
         if (kMode != kSelRecords && (a.dst.x != nullptr || a.anc32 != nullptr || a.anc64 != nullptr) && a.n_out == a.M) {
@@ -432,14 +522,14 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     const double u = a.u[f], n = (double)a.n_global, m = a.wmax[f];
     const int nblk = (int)(k1 - k0 + 1);
     const int64_t g0 = a.out_lo + k0;                  // global index of the block's first output
-    const SysPos spos = make_sys_pos(u, n);
     const RelEndCtx rctx = make_rel_end(u, n, g0, nblk);
-    const CdfDiv div = make_cdfdiv(s_coff[G]);
+    const U128 A_total = coff(G);
+    const CdfDiv div = make_cdfdiv(A_total);
     const int tiles = a.tiles, n_tiles = G * tiles;
     // run end of the source whose inclusive prefix is C (exact path only when the estimate cannot decide)
     auto rel_end = [&](U128 C) -> int {
         const int e = rel_end_fast(rctx, cdf_estimate(C, div));
-        return e >= 0 ? e : rel_end_of(spos, a.n_global, rctx, cdf_exact(C, div));
+        return e >= 0 ? e : rel_end_exact(u, n, a.n_global, g0, nblk, C, A_total);
     };
     // Level 1: the tiles that can hold ancestors of this block's outputs.  Global tile T = shard g = T / tiles,
     // tile t = T % tiles; its inclusive prefix is c_off[g] + tile_prefix_g[t].  Warp 0 finds the first tile whose
@@ -455,8 +545,8 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
             const int T = lo + (lane + 1) * step - 1;
             bool before = false;
             if (T < hi) {
-                const int g = T / tiles, t = T - g * tiles;
-                const U128 C = s_coff[g] + shard(g).tile_prefix[(size_t)f * tiles + t];
+                const int g = kMode == kSelLocal ? 0 : T / tiles, t = T - g * tiles;
+                const U128 C = coff(g) + shard(g).tile_prefix[(size_t)f * tiles + t];
                 const double x = fma(cdf_estimate(C, div), rctx.n_scaled, -rctx.u) - rctx.g0d;
                 before = warp == 0 ? (x <= -1.0e-5) : (x < rctx.nblk_d + 1.0e-5);
             }
@@ -476,7 +566,7 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     // integer.  No barrier inside the walk: the warps do not depend on each other.
     const int64_t J_last = a.n_global - 1;             // the filter's last particle (see the note at its use)
     for (int T = T_lo; T <= T_hi; ++T) {
-        const int g = T / tiles, t = T - g * tiles;
+        const int g = kMode == kSelLocal ? 0 : T / tiles, t = T - g * tiles;
         const SelShard &S = shard(g);
         U128 cs = u128(0);
         if (lane < kChunksPerTile) cs = S.chunk_sum[((size_t)f * tiles + t) * kChunksPerTile + lane];
@@ -485,7 +575,7 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
             const U128 v = shfl_up_u128(cs, o);
             if (lane >= o) cs = cs + v;
         }
-        U128 tile_base = s_coff[g];
+        U128 tile_base = coff(g);
         if (t > 0) tile_base = tile_base + S.tile_prefix[(size_t)f * tiles + t - 1];
         U128 C_before = shfl_u128(cs, max(warp - 1, 0));
         if (warp == 0) C_before = u128(0);
@@ -504,8 +594,8 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
         uint64_t av[kChunkItems];
         {
             WeightSrc w;
-            w.logw = S.logw[s_parity[kMode == kSelPeers ? g : my_g]];
-            w.lin = S.lin;
+            w.logw = S.logw[parity(g)];
+            w.apre = S.apre;
             w.kind = a.kind;
             load_a8(w, (int64_t)f * a.M + j0, a.M - j0, m, av);
         }
@@ -564,7 +654,7 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
 #pragma unroll
             for (int k = 0; k < kChunkItems; ++k) {
                 Ck = Ck + av[k];
-                if (need & (1u << k)) e[k] = rel_end_of(spos, a.n_global, rctx, cdf_exact(Ck, div));
+                if (need & (1u << k)) e[k] = rel_end_exact(u, n, a.n_global, g0, nblk, Ck, A_total);
             }
         }
         // The filter's LAST particle ends where the outputs end, whatever its CDF value says: for
@@ -621,7 +711,7 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     for (int r = 0; r < kSelItems; ++r) {
         const int wi = max(head[r] - 1, 0);
         const int T = T_lo + wi / kScanTile;
-        int g = T / tiles;
+        const int g = kMode == kSelLocal ? 0 : T / tiles;
         int64_t j = (int64_t)(T - g * tiles) * kScanTile + (wi % kScanTile);
         if (j > a.M - 1) j = a.M - 1;
         const StateView src = shard(g).st[a.cur];         // the owner's memory: local, or over NVLink

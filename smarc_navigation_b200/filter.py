@@ -292,8 +292,9 @@ class ParticleFilter(object):
         return self._weights_out(out) if return_weights else None
 
     def mbes_flagged(self):
-        """Per filter: particles of the last ``update_mbes`` that were recast ray by ray (synchronises)."""
-        out = np.zeros(self.n_filters, np.int64)
+        """Per filter ``[second-pass (map-border) particles, particles recast ray by ray]`` of the last
+        ``update_mbes`` (synchronises)."""
+        out = np.zeros((self.n_filters, 2), np.int64)
         with self._lock:
             _lib.check(self._lib.auvpf_mbes_flagged(self._h, _ptr(out)))
         return out

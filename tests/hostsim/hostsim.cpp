@@ -153,7 +153,8 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
                 T.a0[a] = plan.a0[a];
             }
             float *row = out + (size_t)i * B;
-            bool ok = plan.planar && profile_particle(v, T, p, R, true, [&](int b, float range, float) { row[b] = range; });
+            bool ok = plan.planar && profile_particle<true>(v, T, p, R, true, [&](int b, float range, float) { row[b] = range; },
+                                                      [row](int b, float range, float) { row[b] = range; });
             if (ok) *n_swept += B;
             else
                 for (int b = 0; b < B; ++b) {

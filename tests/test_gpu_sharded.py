@@ -166,14 +166,12 @@ def test_sharded_resample_on_gpus(tmp_path, M, seed, exchange):
 
 
 @pytest.mark.gpu
-# (sizes: all ranks' kernels must be co-resident on the ONE device -- they wait on each other; G * (M / 2048 + M / 1024)
-# blocks stay below the 592 resident slots.  Real GPUs have no such limit: test_sharded_resample_on_gpus runs 1 M per rank.)
-@pytest.mark.parametrize("G,M,seed", [(2, 5000, 0), (3, 70001, 1), (4, 1 << 16, 2), (8, 2500, 3), (8, 1 << 15, 5)])
+@pytest.mark.parametrize("G,M,seed", [(2, 5000, 0), (3, 70001, 1), (4, 1 << 18, 2), (8, 2500, 3), (8, 1 << 17, 5)])
 def test_peer_memory_resample_on_one_gpu(G, M, seed):
     """The peer-memory path -- mailbox exchange of the maximum and of the totals inside k_weights / k_select<peers>,
     prefix sums rebuilt from the OWNERS' log-weights, state gathered from the owners' buffers -- with G handles
-    on one device attached in-process.  Every rank's resample is enqueued (each on its own stream) before any is
-    waited for, so the kernels of different ranks really wait on each other's mailbox posts.  Ancestors, the
+    on one device attached in-process and driven by auvpf_group_resample (stage-interleaved enqueue: the kernels of
+    the ranks wait on each other's mailbox posts, in whatever order the device runs the streams).  Ancestors, the
     weights, three chained cycles, the roughening keyed by the GLOBAL slot, the gate and the degenerate case
     against the oracle and against one handle holding every particle."""
     import torch
@@ -193,10 +191,11 @@ def test_peer_memory_resample_on_one_gpu(G, M, seed):
     ancs = [torch.full((M,), -1, dtype=torch.int64, device="cuda") for _ in range(G)]
 
     def everyone(uu, rough=None, anc=None):
+        # all ranks live in this process and on one device: auvpf_group_resample enqueues the stages rank by rank
+        # (a lone auvpf_shard_resample would wait inside its kernel for posts that may be queued behind it)
         rv = None if rough is None else (C.c_double * 6)(*rough)
-        order = list(range(G))[::-1] if seed % 2 else list(range(G))           # enqueue order must not matter
-        for g in order:
-            _lib.check(L.auvpf_shard_resample(pfs[g]._h, uu, rv, None, None if anc is None else C.c_void_p(anc[g].data_ptr())))
+        ap = None if anc is None else (C.c_void_p * G)(*[a.data_ptr() for a in anc])
+        _lib.check(L.auvpf_group_resample(handles, G, uu, rv, ap))
         for pf in pfs:
             pf.sync()
 
@@ -288,8 +287,8 @@ def test_peer_memory_last_particle_edge():
             _lib.check(L.auvpf_peer_attach(pf._h, handles, G, g))
             pf.set_poses(poses[g * M:(g + 1) * M])
             pf.set_log_weights(logw[g * M:(g + 1) * M])
-        for g, pf in enumerate(pfs):
-            _lib.check(L.auvpf_shard_resample(pf._h, u, None, None, C.c_void_p(ancs[g].data_ptr())))
+        ap = (C.c_void_p * G)(*[a.data_ptr() for a in ancs])
+        _lib.check(L.auvpf_group_resample(handles, G, u, None, ap))
         for pf in pfs:
             pf.sync()
         np.testing.assert_array_equal(np.concatenate([a.cpu().numpy() for a in ancs]), want)

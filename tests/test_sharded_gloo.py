@@ -30,16 +30,7 @@ class OracleShardOps(object):
         return float(f.max()) if f.size else -np.inf
 
     def _a(self, m):
-        o = self.o
-        x = self.logw.astype(np.float64) - np.float64(np.float32(m))
-        x = np.where(np.isnan(x), -np.inf, x)
-        live = x >= -745.0
-        p, k = o.exp_det(np.where(live, x, 0.0))
-        s = k + o.A_BITS
-        live &= s >= -1
-        a = np.zeros(self.M, np.uint64)
-        a[live] = np.floor(np.ldexp(p[live], s[live].astype(np.int64))).astype(np.uint64)
-        return a
+        return self.o.integer_weights(self.logw, np.float32(m))
 
     def shard_sum(self, m):
         """This shard's six words: total of the integer weights (low, high), the gate sums, buffer id."""

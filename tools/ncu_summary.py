@@ -48,7 +48,12 @@ def lines(rep, kernel_id, top):
         elif r and r[0] == "Line No":
             hdr = r
         elif r and r[0] and r[0].isdigit() and hdr:
-            i, s = float(r[hdr.index("Instructions Executed")]), float(r[hdr.index("# Samples")])
+            def num(v):
+                try:
+                    return float(v)
+                except ValueError:
+                    return 0.0
+            i, s = num(r[hdr.index("Instructions Executed")]), num(r[hdr.index("# Samples")])
             a = agg.get((cur, int(r[0])), (0.0, 0.0, ""))
             agg[(cur, int(r[0]))] = (a[0] + i, a[1] + s, r[1].strip()[:100])
     ti = sum(v[0] for v in agg.values()) or 1.0
