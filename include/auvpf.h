@@ -236,7 +236,10 @@ int auvpf_neff(auvpf_handle *h, double *neff);
  * round trip on the systematic path) from an exact integer sum of squares, so it is reproducible:
  * N_eff here is auvpf_neff_fixed = (sum_i s_i)^2 / sum_i s_i^2 over s_i = a_i >> 29, a_i the 60-bit integer
  * weights: sums of integers, the same on one GPU or eight.  With AUVPF_RESIDUAL or
- * AUVPF_RS_INPLACE_REF the handle must hold one filter.  A particle-sharded filter is gated on the global sums. */
+ * AUVPF_RS_INPLACE_REF the handle must hold one filter.  A particle-sharded filter is gated on the global sums.
+ * A held-back resample still CONSUMES its draws on every path alike (systematic, residual, slot map, sharded):
+ * the Philox step counters of the resample uniform and of the roughening advance as if it had happened, so a
+ * gated run stays in step with an ungated one that is fed the same explicit draws. */
 int auvpf_set_neff_gate(auvpf_handle *h, double ratio);
 int auvpf_neff_fixed(auvpf_handle *h, double *neff);          /* (F); synchronises */
 /* 1 per filter whose last resample the gate held back, (F) int32; synchronises */

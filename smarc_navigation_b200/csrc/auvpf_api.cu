@@ -655,7 +655,11 @@ int do_resample_residual(auvpf_handle *h, const WeightSrc &src, int32_t flags, c
     {
         bool skip;
         if ((rc = host_neff_gate(h, &skip))) return rc;
-        if (skip) return emit_identity_ancestors(h, ancestors_out);     // state, weights and RNG counters untouched
+        if (skip) {     // state and weights untouched; the draws count as consumed, like on the systematic path
+            h->step_resample++;
+            if (rough_var) h->step_rough++;
+            return emit_identity_ancestors(h, ancestors_out);
+        }
     }
     // the weights themselves, q_j = cdf_j - cdf_{j-1} (sum exactly 2^52: no deficit units to hand out)
     {
@@ -786,7 +790,10 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
             int skipped = 0;
             CU(cudaMemcpyAsync(&skipped, h->skipped, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
-            if (skipped) return AUVPF_OK;
+            if (skipped) {
+                if (rough_var) h->step_rough++;      // (auvpf_roughen below would have advanced it)
+                return AUVPF_OK;
+            }
         }
         if ((rc = apply_indices_dev(h, anc_dev))) return rc;
         if (rough_var && (rc = auvpf_roughen(h, rough_var, rough_noise))) return rc;

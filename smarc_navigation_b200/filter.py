@@ -147,6 +147,14 @@ class ParticleFilter(object):
         with self._lock:
             _lib.check(self._lib.auvpf_set_dem(self._h, _ptr(z), z.shape[0], z.shape[1], x0, y0, res))
 
+    def load_dem(self, path):
+        """Read a DEM file (``dem_io``: float32 or uint16-quantised heights + georeference) and make it the map.
+        Returns the dict that was loaded -- the float32 heights in it are exactly what the kernels see."""
+        from . import dem_io
+        dem = dem_io.load_dem(path)
+        self.set_dem(dem)
+        return dem
+
     def rasterise_mesh(self, vertices, faces, shape, x0=0.0, y0=0.0, res=1.0, fill=np.nan):
         """Triangle mesh -> (H, W) float32 DEM on the GPU (highest surface wins; uncovered vertices
         get ``fill``); feed the result to ``set_dem``."""

@@ -391,3 +391,18 @@ if __name__ == "__main__":
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+def golden_sam_motion(path):
+    """sam_dead_reckoning/scripts/sam_mm.py SAM.motion (the motion-model fallback of dr_node.py:191-201) on
+    random thruster commands; imported unmodified (it needs only NumPy)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(REF)), "sam_dead_reckoning", "scripts"))
+    import sam_mm
+    sam = sam_mm.SAM()
+    rng = np.random.default_rng(0)
+    ctrl = np.column_stack([rng.uniform(-1500, 1500, 64), rng.uniform(-0.13, 0.13, 64)])
+    np.savez_compressed(path, control=ctrl, nudot=np.array([sam.motion(list(c)) for c in ctrl]))
+
+
+if __name__ == "__main__":
+    golden_sam_motion(os.path.join(HERE, "sam_motion.npz"))

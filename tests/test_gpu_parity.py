@@ -319,6 +319,24 @@ def test_update_mbes_mixed_profile_and_per_ray_particles():
     pf.close()
 
 
+def test_quantised_dem_file_parity(tmp_path):
+    """Map ingestion: a DEM file with uint16 heights.  The library and the oracle both see the
+    dequantised float32 map, so ranges and log-weights keep the usual tolerances ON THAT MAP."""
+    from smarc_navigation_b200 import dem_io
+    dem = _dem(500, 2.0)
+    path = str(tmp_path / "map_u16.npz")
+    dem_io.save_dem(path, dem, quantised=True)
+    beams = world.make_beams(128)
+    rng = np.random.default_rng(3)
+    poses = _cloud(rng, 200, (500.0, 500.0), 3.0)
+    pf = _pf(particle_count=200, range_min=world.RANGE_MIN, range_max=world.RANGE_MAX)
+    loaded = pf.load_dem(path)
+    assert loaded["z"].dtype == np.float32 and np.abs(loaded["z"] - dem["z"]).max() < 1e-3 and not np.array_equal(loaded["z"], dem["z"])
+    pf.set_beams(beams)
+    _check_ranges(pf, loaded, poses, beams, np.eye(4), world.RANGE_MAX, label="uint16 DEM file")
+    pf.close()
+
+
 def test_mesh_rasteriser_round_trip_and_overlap():
     """Map ingestion: the DEM's own triangulation rasterises back to the DEM bit for bit; a coarser
     mesh interpolates linearly; where two sheets overlap the higher one wins; uncovered vertices

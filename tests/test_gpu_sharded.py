@@ -227,9 +227,12 @@ def test_peer_memory_resample_on_one_gpu(G, M, seed):
         pf.set_neff_gate(0.5)
     for g, pf in enumerate(pfs):
         pf.set_log_weights(np.zeros(M, np.float32))
+    one.set_log_weights(np.zeros(N, np.float32))
     everyone(0.4, rough=res)
-    assert all(bool(pf.resample_skipped()[0]) for pf in pfs)
+    one.resample(u=0.4)             # (a held-back resample still advances the noise counters, on every path alike)
+    assert all(bool(pf.resample_skipped()[0]) for pf in pfs) and bool(one.resample_skipped()[0])
     np.testing.assert_array_equal(np.concatenate([pf.poses() for pf in pfs]), state)
+    np.testing.assert_array_equal(one.poses(), state)
     lw = (np.random.default_rng(seed + 99).normal(0, 6.0, N) - 30).astype(np.float32)
     for g, pf in enumerate(pfs):
         pf.set_log_weights(lw[g * M:(g + 1) * M])
