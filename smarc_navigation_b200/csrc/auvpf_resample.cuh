@@ -422,7 +422,6 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
 {
     __shared__ int s_head[kSelTile];              // output slot -> 1 + walk index of the source whose run starts there, else 0
     __shared__ int s_wmax[kSelThreads / 32];
-    __shared__ int s_t[2];
     __shared__ U128 s_coff[kMaxPeers + 1];
     __shared__ SelShard s_shard[kMode == kSelPeers ? kMaxPeers : 1];
     __shared__ int s_parity[kMaxPeers];
@@ -538,7 +537,11 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     // a tile too few would be wrong).
     // (records mode emits the offspring of THIS shard's sources only: its own tiles)
     const int T_min = kMode == kSelRecords ? a.rank * tiles : 0, T_max = kMode == kSelRecords ? T_min + tiles : n_tiles;
-    if (warp < 2) {
+    // (EVERY warp runs both searches itself: the table entries are a few cache lines shared by all of them, and the
+    // block saves the barrier -- and the six idle warps -- of handing two integers over through shared memory)
+    int T_lo, T_hi;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {
         int lo = T_min, hi = T_max;
         while (lo < hi) {
             const int step = (hi - lo + 31) >> 5;
@@ -548,16 +551,16 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
                 const int g = kMode == kSelLocal ? 0 : T / tiles, t = T - g * tiles;
                 const U128 C = coff(g) + shard(g).tile_prefix[(size_t)f * tiles + t];
                 const double x = fma(cdf_estimate(C, div), rctx.n_scaled, -rctx.u) - rctx.g0d;
-                before = warp == 0 ? (x <= -1.0e-5) : (x < rctx.nblk_d + 1.0e-5);
+                before = which == 0 ? (x <= -1.0e-5) : (x < rctx.nblk_d + 1.0e-5);
             }
             const int nb = __popc(__ballot_sync(0xffffffffu, before));     // monotone: a prefix of the lanes
             lo += nb * step;
             hi = min(lo + step - 1, hi);
         }
-        if (lane == 0) s_t[warp] = min(lo, T_max - 1);
+        if (which == 0) T_lo = min(lo, T_max - 1);
+        else T_hi = min(lo, T_max - 1);
     }
-    __syncthreads();
-    const int T_lo = s_t[0], T_hi = s_t[1];
+    __syncthreads();            // the run heads are cleared (every warp arrives here at about the same time)
     // Level 2, from the SOURCE side (resampling.py:161-167 read from the other side): output slot i descends from
     // source j iff count_below(cdf[j-1]) <= i < count_below(cdf[j]).  Warp w rebuilds chunk w of every located
     // tile: 8 consecutive sources per lane, a_i from the log-weights, prefix by a thread-local running sum and a
@@ -660,9 +663,11 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
         // The filter's LAST particle ends where the outputs end, whatever its CDF value says: for
         // u >= 1 - N 2^-54 the last position rounds to 1.0 = cumsum[-1], the reference walks off the end
         // (IndexError, resampling.py:162-167); every path here gives that output to the last particle.
+        if (has_last) {
 #pragma unroll
-        for (int k = 0; k < kChunkItems; ++k)
-            if ((int64_t)g * a.M + j0 + k == J_last) e[k] = nblk;
+            for (int k = 0; k < kChunkItems; ++k)
+                if ((int64_t)g * a.M + j0 + k == J_last) e[k] = nblk;
+        }
         // where this lane's first run starts = where the previous source's run ends
         int start = __shfl_up_sync(0xffffffffu, e[kChunkItems - 1], 1);
         if (lane == 0) start = e_begin;
