@@ -4,6 +4,7 @@
 // device buffer; callers own what they pass.  No CPU fallback exists: every entry point either
 // enqueues kernels on the handle's stream or fails with an error code.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only; a no-op unless a profiler (nsys, ncu --nvtx) is attached
 
 #include <cmath>
 #include <cstdarg>
@@ -173,12 +174,17 @@ struct Guard {   // make the handle's device current for the duration of a call
     }
 };
 
-struct Prof {   // CUDA-event bracket around the kernels of one class
+const char *const kClassName[AUVPF_K_COUNT] = {"auvpf:propagate", "auvpf:update_mbes", "auvpf:update_gps", "auvpf:weights",
+                                               "auvpf:scan",      "auvpf:select_gather", "auvpf:roughen",  "auvpf:estimate",
+                                               "auvpf:other"};
+
+struct Prof {   // NVTX range (always) + CUDA-event bracket (profiling mode) around the kernels of one class
     auvpf_handle *h;
     ProfEvent ev{};
     bool on;
     Prof(auvpf_handle *h_, int klass) : h(h_), on(h_->prof)
     {
+        nvtxRangePushA(kClassName[klass]);
         if (!on) return;
         if (!h->prof_pool.empty()) {
             ev = h->prof_pool.back();
@@ -192,9 +198,11 @@ struct Prof {   // CUDA-event bracket around the kernels of one class
     }
     ~Prof()
     {
-        if (!on) return;
-        cudaEventRecord(ev.b, h->stream);
-        h->prof_events.push_back(ev);
+        if (on) {
+            cudaEventRecord(ev.b, h->stream);
+            h->prof_events.push_back(ev);
+        }
+        nvtxRangePop();
     }
 };
 

@@ -53,7 +53,33 @@ def main():
             rows = np.array([[[_odom_row(o, None)] for o in odoms]] * 3)
             pf.replay(rows, np.stack([np.stack([r[0], r[0]])] * 3))
             pf.neff_fixed()
+        pf.estimate(weighted=True, circular_yaw=True, full_cov=True)
+        pf.pose_array(max_poses=100)
         pf.close()
+    # linear weights (resample(weights)) and a particle-sharded filter: 3 ranks on this device, peer-memory path
+    import ctypes as C
+    from smarc_navigation_b200 import _lib
+    L = _lib.load()
+    pf = ParticleFilter(particle_count=N, resampling_noise_covariance=P["resampling_noise_covariance"], seed=3)
+    pf.resample(weights=np.random.default_rng(0).uniform(0.0, 1.0, N))
+    pf.weights_q()
+    pf.close()
+    G, M = 3, 2500
+    pfs = [ParticleFilter(particle_count=M, global_offset=g * M, global_count=G * M, seed=5,
+                          resampling_noise_covariance=P["resampling_noise_covariance"]) for g in range(G)]
+    handles = (C.c_void_p * G)(*[p_._h for p_ in pfs])
+    rng = np.random.default_rng(1)
+    for g, p_ in enumerate(pfs):
+        _lib.check(L.auvpf_peer_attach(p_._h, handles, G, g))
+        p_.set_log_weights(rng.normal(0, 3, M).astype(np.float32))
+    rv = (C.c_double * 6)(*P["resampling_noise_covariance"])
+    for c in range(2):
+        _lib.check(L.auvpf_group_resample(handles, G, 0.3 + 0.2 * c, rv, None))
+        for g, p_ in enumerate(pfs):
+            p_.sync()
+            p_.set_log_weights(rng.normal(0, 3, M).astype(np.float32))
+    for p_ in pfs:
+        p_.close()
     print("sanitize cycle ok")
 
 
