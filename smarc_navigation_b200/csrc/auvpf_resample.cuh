@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
 {
     __shared__ int s_head[kSelTile];              // output slot -> 1 + walk index of the source whose run starts there, else 0
     __shared__ int s_wmax[kSelThreads / 32];
+    __shared__ int s_t[2];
     __shared__ U128 s_coff[kMaxPeers + 1];
     __shared__ SelShard s_shard[kMode == kSelPeers ? kMaxPeers : 1];
     __shared__ int s_parity[kMaxPeers];
@@ -537,11 +538,10 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     // a tile too few would be wrong).
     // (records mode emits the offspring of THIS shard's sources only: its own tiles)
     const int T_min = kMode == kSelRecords ? a.rank * tiles : 0, T_max = kMode == kSelRecords ? T_min + tiles : n_tiles;
-    // (EVERY warp runs both searches itself: the table entries are a few cache lines shared by all of them, and the
-    // block saves the barrier -- and the six idle warps -- of handing two integers over through shared memory)
-    int T_lo, T_hi;
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
+    // (Two warps search, one barrier hands the two tiles over -- and orders the clearing of the run heads before the
+    // walk.  Letting every warp run both searches itself saves that hand-over but was measured 6-14 % slower: eight
+    // times the table probes.)
+    if (warp < 2) {
         int lo = T_min, hi = T_max;
         while (lo < hi) {
             const int step = (hi - lo + 31) >> 5;
@@ -551,16 +551,16 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
                 const int g = kMode == kSelLocal ? 0 : T / tiles, t = T - g * tiles;
                 const U128 C = coff(g) + shard(g).tile_prefix[(size_t)f * tiles + t];
                 const double x = fma(cdf_estimate(C, div), rctx.n_scaled, -rctx.u) - rctx.g0d;
-                before = which == 0 ? (x <= -1.0e-5) : (x < rctx.nblk_d + 1.0e-5);
+                before = warp == 0 ? (x <= -1.0e-5) : (x < rctx.nblk_d + 1.0e-5);
             }
             const int nb = __popc(__ballot_sync(0xffffffffu, before));     // monotone: a prefix of the lanes
             lo += nb * step;
             hi = min(lo + step - 1, hi);
         }
-        if (which == 0) T_lo = min(lo, T_max - 1);
-        else T_hi = min(lo, T_max - 1);
+        if (lane == 0) s_t[warp] = min(lo, T_max - 1);
     }
-    __syncthreads();            // the run heads are cleared (every warp arrives here at about the same time)
+    __syncthreads();
+    const int T_lo = s_t[0], T_hi = s_t[1];
     // Level 2, from the SOURCE side (resampling.py:161-167 read from the other side): output slot i descends from
     // source j iff count_below(cdf[j-1]) <= i < count_below(cdf[j]).  Warp w rebuilds chunk w of every located
     // tile: 8 consecutive sources per lane, a_i from the log-weights, prefix by a thread-local running sum and a
