@@ -478,7 +478,8 @@ def measure(ctx, args, cfg, with_cpu, with_clouds):
     sharded = G > 1 and F == 1
 
     # synthetic ping sequence: ground-truth ranges raycast on the GPU (the product path), + noise
-    n_steps = 2 * (K + W) + 2 * K + 2
+    KB = min(K, 10)                                    # cycles of the phase-timed and of the per-kernel-bracketed loop
+    n_steps = 2 * (K + W) + 2 * KB + 2 * K + 2
     cycles = []
     for s in range(n_steps):
         per = [t.cycle() for t in trajs]
@@ -543,9 +544,12 @@ def measure(ctx, args, cfg, with_cpu, with_clouds):
     # ---- the same cycles once more with CUDA events between the three phases (the resample's two kernels stay
     # adjacent, so their programmatic overlap is part of the figure), then with the library's own per-kernel
     # brackets for the breakdown and the launch count -----------------------------------------------------
-    KB = min(K, 10)
+    mean, cov = filt.mean_cov()                     # (the estimate the timed cycles ended on, against the truth of the last one)
+    mean = np.asarray(mean).reshape(-1, 6) if F > 1 else np.asarray(mean).reshape(1, -1)
+    tr = cycles[W + K - 1][3]
+    track_err = float(np.max(np.hypot(mean[:, 0] - tr[:len(mean), 0], mean[:, 1] - tr[:len(mean), 1])))
     ph = []
-    for s in range(KB):
+    for s in range(W + K, W + K + KB):              # (the sequence goes on: every loop below consumes the next cycles)
         flush_l2()
         ee = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ee[0].record(stream)
@@ -561,16 +565,12 @@ def measure(ctx, args, cfg, with_cpu, with_clouds):
                 for i, name in enumerate(("propagate", "update_mbes", "resample"))}
     pf.profile(True)
     pf.profile_read(reset=True)
-    for s in range(KB):
+    for s in range(W + K + KB, W + K + 2 * KB):
         flush_l2()
         cycle_device(s)
     barrier()
     prof = pf.profile_read(reset=True)
     pf.profile(False)
-    mean, cov = filt.mean_cov()
-    mean = np.asarray(mean).reshape(-1, 6) if F > 1 else np.asarray(mean).reshape(1, -1)
-    tr = cycles[W + K - 1][3]
-    track_err = float(np.max(np.hypot(mean[:, 0] - tr[:len(mean), 0], mean[:, 1] - tr[:len(mean), 1])))
 
     # ---- end to end through the public API, host buffers ----------------------------------------
     def cycle_host(s):
@@ -582,7 +582,7 @@ def measure(ctx, args, cfg, with_cpu, with_clouds):
         resample()
         return filt.mean_cov()                  # reads the estimate back: the cycle's results are on the host here
 
-    base = W + K
+    base = W + K + 2 * KB
     for s in range(base, base + W):
         cycle_host(s)
     barrier()
@@ -677,6 +677,10 @@ def measure(ctx, args, cfg, with_cpu, with_clouds):
         "kernel_ms_per_cycle": {k: v[0] / KB for k, v in prof.items() if v[1]},
         "track_error_m": track_err,
     }
+    if not sharded:
+        fm, _ = pf.mean_cov()
+        ft = cycles[b2 + 2 * K - 1][3]
+        rec["track_error_m_final"] = float(np.max(np.hypot(fm[:, 0] - ft[:len(fm), 0], fm[:, 1] - ft[:len(fm), 1])))
     if with_clouds and G == 1 and F == 1:
         rec["clouds"] = cloud_sweep(ctx, cfg, pf, trajs[0], list(CLOUDS), max(5, min(K, 10)))
     rec["parity_check"] = parity_check(ctx, cfg, filt, pf)
