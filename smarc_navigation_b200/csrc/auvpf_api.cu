@@ -140,7 +140,6 @@ struct auvpf_handle {
     DemView dem{};
     bool have_dem = false;
     bool use_profile = true;   // AUVPF_NO_PROFILE=1 in the environment forces the per-ray kernel
-    int sel_slots = 0;         // resident blocks of the select kernel on this device (sel_tile())
     bool use_pdl = true;       // AUVPF_NO_PDL=1: launch the select kernel without programmatic stream serialisation
     int B = 0;
     FrameParams frame{};
@@ -530,29 +529,6 @@ cudaError_t launch_select(auvpf_handle *h, dim3 grid, const SelArgs &sa)
     return cudaLaunchKernelEx(&cfg, k_select<kMode>, sa);
 }
 
-// Output slots per block of the select kernel.  Blocks take the same time whatever they hold, so the grid is
-// shaped to whole waves of the resident slots (SMs x blocks per SM): ceil(F n_out / (slots kSelTile)) waves, the
-// tile shrunk until the blocks fill the last one (1 M outputs: 1184 blocks of 888 instead of 1024 of 1024 = 1.73
-// waves).  AUVPF_SEL_TILE pins it (measurements).
-int sel_tile(auvpf_handle *h, int64_t n_out, int F)
-{
-    static const int pinned = [] { const char *e = getenv("AUVPF_SEL_TILE"); return e ? atoi(e) : 0; }();
-    if (pinned >= kSelItems && pinned <= kSelTile) return pinned / kSelItems * kSelItems;
-    if (h->sel_slots <= 0) {
-        int per_sm = 0, sms = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_select<kSelLocal>, kSelThreads, 0) != cudaSuccess) per_sm = 1;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-        h->sel_slots = std::max(1, per_sm) * std::max(1, sms);
-    }
-    const int64_t slots = h->sel_slots;
-    for (int64_t w = (F * n_out + slots * kSelTile - 1) / (slots * kSelTile);; ++w) {
-        const int64_t per_filter = std::max<int64_t>(1, w * slots / F);          // blocks each filter may use
-        int64_t tile = (n_out + per_filter - 1) / per_filter;
-        tile = (tile + kSelItems - 1) / kSelItems * kSelItems;
-        if (tile <= kSelTile) return (int)std::max<int64_t>(tile, kSelItems);
-    }
-}
-
 SelArgs select_args(auvpf_handle *h, const WeightSrc &src)
 {
     SelArgs a{};
@@ -561,7 +537,6 @@ SelArgs select_args(auvpf_handle *h, const WeightSrc &src)
     a.out_lo = h->global_offset;
     a.n_out = h->M;
     a.tiles = h->tiles_per_filter;
-    a.tile = sel_tile(h, h->M, h->F);
     a.G = 1;
     a.rank = 0;
     a.kind = src.kind;
@@ -798,7 +773,7 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     if (inplace) sa.dst.x = nullptr;   // ancestors only
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
-        CU(launch_select<kSelLocal>(h, grid1(h->M, sa.tile, h->F), sa));
+        CU(launch_select<kSelLocal>(h, grid1(h->M, kSelTile, h->F), sa));
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }
@@ -1955,7 +1930,6 @@ int auvpf_shard_emit(auvpf_handle *h, double u, const uint64_t *totals_all, int3
     sa.rank = my_rank;
     sa.out_lo = out_lo;
     sa.n_out = n_out;
-    sa.tile = sel_tile(h, n_out, 1);
     sa.c_off = h->c_off;
     sa.records = rd;
     sa.anc64 = ad;
@@ -1963,7 +1937,7 @@ int auvpf_shard_emit(auvpf_handle *h, double u, const uint64_t *totals_all, int3
     sa.dst = StateView{};
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
-        k_select<kSelRecords><<<grid1(n_out, sa.tile, 1), kSelThreads, 0, h->stream>>>(sa);
+        k_select<kSelRecords><<<grid1(n_out, kSelTile, 1), kSelThreads, 0, h->stream>>>(sa);
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 2);
         CU(cudaGetLastError());
     }
@@ -2115,7 +2089,7 @@ int shard_stage_select(auvpf_handle *h, const double *rough_var, const float *ro
     sa.dst = h->st[1 - h->cur];
     {
         Prof pr(h, AUVPF_K_SELECT_GATHER);
-        CU(launch_select<kSelPeers>(h, grid1(h->M, sa.tile, 1), sa));
+        CU(launch_select<kSelPeers>(h, grid1(h->M, kSelTile, 1), sa));
         LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
         CU(cudaGetLastError());
     }

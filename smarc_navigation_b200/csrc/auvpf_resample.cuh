@@ -381,7 +381,6 @@ struct SelArgs {
     int64_t n_global;                   // N of positions = (u + i) / N
     int64_t out_lo, n_out;              // this launch emits the outputs [out_lo, out_lo + n_out) of every filter
     int tiles;                          // tiles per shard and filter
-    int tile;                           // output slots per block (<= kSelTile; the grid is ceil(n_out / tile) x F)
     int G, rank, kind;
     int cur;                            // state buffer that is the SOURCE of the gather (same on every rank)
     int logw_parity;                    // local / records mode: which log-weight buffer is current
@@ -430,9 +429,9 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     __shared__ int s_skip;
     const int f = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t k0 = (int64_t)blockIdx.x * a.tile;         // a.tile <= kSelTile, a multiple of kSelItems (sel_tile())
+    const int64_t k0 = (int64_t)blockIdx.x * kSelTile;
     if (k0 >= a.n_out) return;
-    const int64_t k1 = min(k0 + (int64_t)a.tile, a.n_out) - 1;
+    const int64_t k1 = min(k0 + (int64_t)kSelTile, a.n_out) - 1;
     const int G = kMode == kSelLocal ? 1 : a.G;
 #pragma unroll
     for (int r = 0; r < kSelItems; ++r) s_head[threadIdx.x * kSelItems + r] = 0;
