@@ -460,6 +460,9 @@ __device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, co
     T.B = B;
     T.n1 = fan.n1;
     T.sgn1 = fan.sgn1;
+    // outermost beam of a side: beam 0 of [0, n1), beam B - 1 of [n1, B)
+    T.s_lim[0] = fan.n1 > 0 ? (1.0f - kDenPrecise) / fmaxf(s_aux[0].tn, 1.0e-6f) : 0.f;
+    T.s_lim[1] = B > fan.n1 ? (1.0f - kDenPrecise) / fmaxf(s_aux[B - 1].tn, 1.0e-6f) : 0.f;
     for (int a = 0; a < 3; ++a) {
         T.c0[a] = fan.c0[a];
         T.a0[a] = fan.a0[a];
@@ -499,7 +502,7 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
         a.sec = (float)beam_tan[B + b];
         a.reach = beam_aux[b] * dem.range_max;
         a.meas = ok ? r : __int_as_float(0x7fc00000);        // invalid measured beam: skipped in the sum
-        a.rmax = dem.range_max;
+        a.tn = (float)beam_tan[b];
         s_aux[b] = a;
         nv += ok ? 1 : 0;
     }
@@ -552,7 +555,7 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
         a.sec = (float)beam_tan[B + b];
         a.reach = beam_aux[b] * dem.range_max;
         a.meas = 0.f;
-        a.rmax = dem.range_max;
+        a.tn = (float)beam_tan[b];
         s_aux[b] = a;
     }
     __syncthreads();

@@ -10,6 +10,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 
 #if defined(__CUDACC__)
 #define AUVPF_HD __host__ __device__ __forceinline__
@@ -725,7 +726,7 @@ extern long g_prof_reasons[8];      // test-only: why profile marches gave up (t
 #endif
 
 constexpr float kGammaMin = 0.05f;       // -gamma must exceed this (|cos| of the worst slope/tilt combination)
-constexpr float kDenPrecise = 0.1f;     // a beam closing on the profile slower than this is re-solved in float64
+constexpr float kDenPrecise = 0.25f;    // a beam closing on the profile slower than this is re-solved in float64
 
 // A beam that meets a facet at a grazing angle amplifies the ~1e-6 m drift of the incremental
 // (p_cur, q_cur) by 1 / den.  Such hits are re-solved from scratch on the facet's plane:
@@ -767,46 +768,38 @@ double precise_hit(const ProfFrameD *D, float sgf, int cx, int cy, float z00, fl
 #endif
 
 // Beam tables of a planar fan as the profile merge needs them (device: shared memory).
-struct BeamAux {                             // one 16-byte load per beam
+struct BeamAux {                             // one 16-byte load per beam: everything the beam loop reads
     float sec;                               // 1 / along-centre component (float32 copy)
     float reach;                             // |lateral component| * range_max: lateral distance the beam can cover
     float meas;                              // measured range of the ping (NaN = beam not used); 0 for probes
-    float rmax;                              // range_max, carried here so the beam loop reads no constant-bank value
+    float tn;                                // |lateral| / along-centre component (float32 copy of tan_t)
 };
 
-// Per-beam table reads.  On the device the tables are in shared memory and are read with explicit
-// 32-bit shared addresses: through the generic pointers the compiler re-derived the shared window
-// base (S2R SR_CgaCtaId + LEA) in every trip of the beam loop (ncu: 3 % of the stall samples).
+// Per-beam table reads.  The march counts beams by ADDRESS: ba = base + 16 * beam, stepped by +-16, compared with
+// the address one past the side's last beam -- the counter is the load address.  On the device the table is in
+// shared memory and `base` is its 32-bit shared address (through the generic pointer the compiler re-derived
+// the shared window base, S2R SR_CgaCtaId + LEA, in every trip of the beam loop: 3 % of the stall samples);
+// on the host base = 0.
 struct BeamTabs {
 #if defined(__CUDA_ARCH__)
-    uint32_t tan_s, aux_s;
+    uint32_t base;
 #else
-    const double *tan_t;
     const BeamAux *aux;
+    static constexpr uint32_t base = 0;
 #endif
 };
 
-AUVPF_HD double beam_tan(const BeamTabs &t, int b)
-{
-#if defined(__CUDA_ARCH__)
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(t.tan_s + 8u * (uint32_t)b));
-    return v;
-#else
-    return t.tan_t[b];
-#endif
-}
+AUVPF_HD uint32_t beam_addr(const BeamTabs &t, int b) { return t.base + 16u * (uint32_t)b; }
+AUVPF_HD int beam_index(const BeamTabs &t, uint32_t ba) { return (int)(ba - t.base) >> 4; }
 
-AUVPF_HD BeamAux beam_aux(const BeamTabs &t, int b)
+AUVPF_HD BeamAux beam_aux(const BeamTabs &t, uint32_t ba)
 {
 #if defined(__CUDA_ARCH__)
     BeamAux a;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                 : "=f"(a.sec), "=f"(a.reach), "=f"(a.meas), "=f"(a.rmax)
-                 : "r"(t.aux_s + 16u * (uint32_t)b));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.sec), "=f"(a.reach), "=f"(a.meas), "=f"(a.tn) : "r"(ba));
     return a;
 #else
-    return t.aux[b];
+    return t.aux[ba >> 4];
 #endif
 }
 
@@ -815,6 +808,8 @@ struct FanTables {
     const double *sec_t;                     // 1 / along-centre component (float64: grazing hits only)
     const BeamAux *aux;
     int B, n1, sgn1;                         // beams [0,n1) on the side sign sgn1, [n1,B) on the other
+    float s_lim[2];                          // per side: profile slope up to which NO beam of the side is grazing
+                                             // (den = 1 - slope tan >= kDenPrecise for the side's outermost tan)
     float c0[3], a0[3];                      // fan centre / lateral unit vectors, sensor frame
 };
 
@@ -869,24 +864,23 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
 {
     // per-side state
     int side = T.n1 > 0 ? 0 : 1;
-    int n_side = side == 0 ? T.n1 : T.B - T.n1;
-    int bb = side == 0 ? T.n1 - 1 : T.n1, bstep = side == 0 ? -1 : 1;   // current beam, next one outward
-    float sgf = (float)(side == 0 ? T.sgn1 : -T.sgn1);
-    int j = 0;
-    double tn = 0.0;                       // the current beam's tan ...
-    float tn_f = 0.f, gap = 0.f;           // ... its float32 copy, and the beam line's lead over the curve point
-    BeamAux ax;                            // ... and its float32 constants; reloaded only when the beam changes
-    ax.sec = 1.f;
-    ax.reach = ax.meas = 0.f;
-    ax.rmax = m.range_max;
     BeamTabs tabs;
 #if defined(__CUDA_ARCH__)
-    tabs.tan_s = (uint32_t)__cvta_generic_to_shared(T.tan_t);
-    tabs.aux_s = (uint32_t)__cvta_generic_to_shared(T.aux);
+    tabs.base = (uint32_t)__cvta_generic_to_shared(T.aux);
 #else
-    tabs.tan_t = T.tan_t;
     tabs.aux = T.aux;
 #endif
+    // current beam (as its table address, see BeamTabs), the step to the next one outward, and the address one past
+    // the side's last beam: the side is done when ba == ba_end (one counter: the loop below is the hottest code of
+    // the library)
+    uint32_t ba = beam_addr(tabs, side == 0 ? T.n1 - 1 : T.n1), ba_end = beam_addr(tabs, side == 0 ? -1 : T.B);
+    uint32_t bstep = side == 0 ? (uint32_t)-16 : 16u;
+    float s_lim = T.s_lim[side];
+    float sgf = (float)(side == 0 ? T.sgn1 : -T.sgn1);
+    BeamAux ax;                            // the current beam's float32 constants; reloaded only when the beam changes
+    ax.sec = 1.f;
+    ax.reach = ax.meas = ax.tn = 0.f;
+    const float rmax = m.range_max;
     int cx = S.cx, cy = S.cy;
     int zi = cy * m.pitch + cx;            // index of the cell's vertex (0, 0) in the padded DEM
     float u = S.u, v = S.v;
@@ -905,17 +899,14 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         z01 = ldg_f(m.z + zi + 1);
         z10 = ldg_f(m.z + zi + m.pitch);
         z11 = ldg_f(m.z + zi + m.pitch + 1);
-        tn = beam_tan(tabs, bb);
-        ax = beam_aux(tabs, bb);
-        tn_f = (float)tn;
-        gap = (float)(q_cur * tn);
+        ax = beam_aux(tabs, ba);
     }
     for (int step = 0; step < max_steps; ++step) {
         const unsigned act = AUVPF_WARP_BALLOT(running);
         if (!act) break;
         if (running) {
             bool fail = false;
-            const bool fresh = !kBorder || j < n_side;     // false only in the step after a side ran off the map: nothing left to march
+            const bool fresh = !kBorder || ba != ba_end;     // false only in the step after a side ran off the map: nothing left to march
             const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
             const float Dv = lower ? z11 - z01 : z10 - z00;
             const float gamma = F0.cz - F0.cgx * Du - F0.cgy * Dv;
@@ -951,32 +942,39 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             // beam line ahead of the curve point at q_cur; it closes at the rate den per unit p.
             // A beam is resolved here when it hits inside the segment, or when the segment's end is
             // beyond what the beam can reach within range_max (miss).
-            // gap is carried in float32: set in float64 when the beam changes (the product q tan and p
-            // cancel), then moved along with the curve point segment by segment (gap -= dp den), so the
-            // test below has no float64 and no conversion in it.
-            while (!fail && j < n_side) {
-                const float den = fmaf(-s, tn_f, 1.0f);
-                const bool hit = gap <= dp * den;
-                if (!(hit || p_out_f > ax.reach)) break;
-                // range = (q at the hit) / cos th.  float32 from the float32 copy of q_cur: three
-                // roundings at <= 120 m, < 2e-5 m (tolerance 1e-4 m); grazing hits go the float64 way
-                const float dph = gap > 0.f ? fast_div(gap, den) : 0.f;
-                float t = fmaf(s, dph, q_f) * ax.sec;
-                if (hit && den < kDenPrecise)
-                    t = (float)(precise_hit(D, sgf, cx, cy, z00, z01, z10, z11, lower, tn) * T.sec_t[bb]);
-                const float rmax = ax.rmax;
-                const float range = (hit && t <= rmax) ? fmaxf(t, 0.f) : rmax;   // not hit: out of reach, a miss
-                const int b_done = bb;
-                const float meas = ax.meas;
-                ++j;
-                bb += bstep;
-                if (j < n_side) {                                  // next beam's constants, in flight during the sink
-                    tn = beam_tan(tabs, bb);
-                    ax = beam_aux(tabs, bb);
-                    tn_f = (float)tn;
-                    gap = (float)(q_cur * tn - p_cur);
+            // gap = q tan - p cancels (both ~ the lateral distance, tens of metres; the difference is a fraction of a
+            // cell), but ONE float32 FMA forms the product exactly and rounds the small difference once: what is left
+            // is the rounding of its inputs (the float32 copies of the two accumulators and of tan, < 5e-6 m in gap),
+            // which the range sees scaled by slope / den -- grazing hits (den < kDenPrecise) go the float64 way.
+            // Two instantiations of the loop: on a segment whose slope cannot make any beam of this side graze
+            // (s <= s_lim, all of a smooth seabed) the float64 re-solve and its test are not compiled in.
+            auto resolve_beams = [&](auto may_graze) {
+                while (ba != ba_end) {
+                    const float den = fmaf(-s, ax.tn, 1.0f);
+                    const float gap = fmaf(q_f, ax.tn, -p_f);
+                    const bool hit = gap <= dp * den;
+                    if (!(hit || p_out_f > ax.reach)) break;
+                    // range = (q at the hit) / cos th.  float32 from the float32 copy of q_cur: three
+                    // roundings at <= 120 m, < 2e-5 m (tolerance 1e-4 m).  (gap < 0: the hit lies a rounding before
+                    // the segment, on the same plane.  den <= 0 with a hit is a grazing hit: whatever the division
+                    // makes of it is replaced.)
+                    float t = fmaf(s, fast_div(gap, den), q_f) * ax.sec;
+                    if (decltype(may_graze)::value) {
+                        if (hit && den < kDenPrecise) {
+                            const int bb = beam_index(tabs, ba);
+                            t = (float)(precise_hit(D, sgf, cx, cy, z00, z01, z10, z11, lower, T.tan_t[bb]) * T.sec_t[bb]);
+                        }
+                    }
+                    // not hit: out of reach, a miss; a hit beyond range_max is one as well
+                    const float range = fminf(fmaxf(hit ? t : kBigT, 0.f), rmax);
+                    sink(beam_index(tabs, ba), range, ax.meas);
+                    ba += bstep;
+                    if (ba != ba_end) ax = beam_aux(tabs, ba);         // the next beam's constants
                 }
-                sink(b_done, range, meas);
+            };
+            if (!fail) {
+                if (s <= s_lim) resolve_beams(std::false_type{});
+                else resolve_beams(std::true_type{});
             }
             // Lanes leave the beam loop after different trip counts; without this barrier each group
             // ran the code below on its own (ncu: 2.3 executions per step at 13 of 32 lanes).
@@ -984,19 +982,16 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             if (fail) {
                 ok = false;
                 running = false;
-            } else if (j >= n_side) {
+            } else if (ba == ba_end) {
                 // this side is done: start the other one from the anchor, or finish
                 if (side == 0 && T.B - T.n1 > 0) {
                     side = 1;
-                    n_side = T.B - T.n1;
-                    bb = T.n1;
-                    bstep = 1;
+                    ba = beam_addr(tabs, T.n1);
+                    bstep = 16u;
+                    ba_end = beam_addr(tabs, T.B);
+                    s_lim = T.s_lim[1];
                     sgf = -sgf;
-                    j = 0;
-                    tn = beam_tan(tabs, bb);
-                    ax = beam_aux(tabs, bb);
-                    tn_f = (float)tn;
-                    gap = (float)(S.q0 * tn);
+                    ax = beam_aux(tabs, ba);
                     cx = S.cx;
                     cy = S.cy;
                     zi = cy * m.pitch + cx;
@@ -1017,7 +1012,6 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             } else {
                 // advance to the exit point and step into the neighbour across that edge (selects, not
                 // branches: lanes leaving through different edges stay converged)
-                gap = fmaf(-dp, fmaf(-s, tn_f, 1.0f), gap);         // the current beam's lead at the new curve point
                 q_cur += (double)(s * dp);
                 p_cur += (double)dp;
                 q_f = (float)q_cur;
@@ -1040,10 +1034,10 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     if (kBorder) {
                         // the rest of this side is finished ray by ray AFTER the march loop (finish_side_by_rays);
                         // remember where it stopped
-                        ex_j[side] = j;
-                        ex_bb[side] = bb;
+                        ex_bb[side] = beam_index(tabs, ba);
+                        ex_j[side] = side == 0 ? T.n1 - 1 - ex_bb[side] : ex_bb[side] - T.n1;
                         ex_p[side] = p_f;
-                        j = n_side;                                // the side switch happens in the next step
+                        ba = ba_end;                               // the side switch happens in the next step
                         cx = S.cx;                                 // (any cell inside the map: the step's loads stay in bounds)
                         cy = S.cy;
                         zi = cy * m.pitch + cx;

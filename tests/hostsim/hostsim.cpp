@@ -140,7 +140,7 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
                 aux[b].sec = (float)plan.sec_t[b];
                 aux[b].reach = plan.s[b] * v.range_max;
                 aux[b].meas = 0.f;
-                aux[b].rmax = v.range_max;
+                aux[b].tn = (float)plan.tan_t[b];
             }
             T.tan_t = plan.tan_t.data();
             T.sec_t = plan.sec_t.data();
@@ -148,6 +148,8 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
             T.B = B;
             T.n1 = plan.n1;
             T.sgn1 = plan.sgn1;
+            T.s_lim[0] = plan.n1 > 0 ? (1.0f - kDenPrecise) / fmaxf(aux[0].tn, 1.0e-6f) : 0.f;
+            T.s_lim[1] = B > plan.n1 ? (1.0f - kDenPrecise) / fmaxf(aux[B - 1].tn, 1.0e-6f) : 0.f;
             for (int a = 0; a < 3; ++a) {
                 T.c0[a] = plan.c0[a];
                 T.a0[a] = plan.a0[a];
