@@ -877,14 +877,16 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     uint32_t bstep = side == 0 ? (uint32_t)-16 : 16u;
     float s_lim = T.s_lim[side];
     float sgf = (float)(side == 0 ? T.sgn1 : -T.sgn1);
+    float lgx = sgf * F0.agx, lgy = sgf * F0.agy, lz = sgf * F0.az;    // lateral unit vector of the side being marched
     BeamAux ax;                            // the current beam's float32 constants; reloaded only when the beam changes
     ax.sec = 1.f;
     ax.reach = ax.meas = ax.tn = 0.f;
     const float rmax = m.range_max;
     int cx = S.cx, cy = S.cy;
-    int zi = cy * m.pitch + cx;            // index of the cell's vertex (0, 0) in the padded DEM
-    float u = S.u, v = S.v;
-    bool lower = u >= v;
+    // position inside the triangle in CANONICAL coordinates a >= b: (a, b) = (u, v) in the lower half of the cell
+    // (u >= v), (v, u) in the upper half.  Edges: 0: a = 1, 1: b = 0, 2: a = b (the diagonal).
+    bool lower = S.u >= S.v;
+    float a = lower ? S.u : S.v, b = lower ? S.v : S.u;
     int entry = -1;                        // canonical edge the curve entered the triangle through
     double p_cur = 0.0, q_cur = S.q0;
     float p_f = 0.f, q_f = (float)S.q0;    // float32 copies of the two accumulators
@@ -895,10 +897,11 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     const int max_steps = 2 * (8 * (int)(m.range_max / m.res) + 256);
     float z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
     if (running) {
-        z00 = ldg_f(m.z + zi);
-        z01 = ldg_f(m.z + zi + 1);
-        z10 = ldg_f(m.z + zi + m.pitch);
-        z11 = ldg_f(m.z + zi + m.pitch + 1);
+        const float *zp = m.z + (cy * m.pitch + cx);       // the cell's vertex (0, 0) in the padded DEM
+        z00 = ldg_f(zp);
+        z01 = ldg_f(zp + 1);
+        z10 = ldg_f(zp + m.pitch);
+        z11 = ldg_f(zp + m.pitch + 1);
         ax = beam_aux(tabs, ba);
     }
     for (int step = 0; step < max_steps; ++step) {
@@ -911,12 +914,11 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             const float Dv = lower ? z11 - z01 : z10 - z00;
             const float gamma = F0.cz - F0.cgx * Du - F0.cgy * Dv;
             if (!(gamma < -kGammaMin) && fresh) { AUVPF_REASON(0); fail = true; }
-            const float beta = sgf * (F0.agx * Du + F0.agy * Dv - F0.az);
+            const float beta = lgx * Du + lgy * Dv - lz;
             const float s = fast_div(beta, gamma);                // profile slope dT/dp
-            const float X1 = fmaf(s, F0.cgx, sgf * F0.agx), Y1 = fmaf(s, F0.cgy, sgf * F0.agy);   // d(u,v)/dp
-            // canonical triangle a >= b: (a, b) = (u, v) in the lower half, (v, u) in the upper half.
-            // Edges: 0: a = 1 (reached when A1 > 0), 1: b = 0 (B1 < 0), 2: a = b (B1 > A1).
-            const float a = lower ? u : v, b = lower ? v : u;
+            const float X1 = fmaf(s, F0.cgx, lgx), Y1 = fmaf(s, F0.cgy, lgy);   // d(u,v)/dp
+            // the exit: edge 0 is reached when A1 > 0, edge 1 when B1 < 0, edge 2 when B1 > A1; the nearest wins
+            // (fractions compared by cross-multiplication)
             const float A1 = lower ? X1 : Y1, B1 = lower ? Y1 : X1;
             float bn = kBigT, bd = 1.f;                            // nearest exit = bn / bd
             int be = -1;
@@ -930,10 +932,12 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 bd = -B1;
                 be = 1;
             }
-            if (entry != 2 && B1 > A1 && (a - b) * bd < bn * (B1 - A1)) {
-                bn = a - b;
-                bd = B1 - A1;
-                be = 2;
+            {
+                const float wn = a - b, wd = B1 - A1;
+                const bool c2 = entry != 2 && wd > 0.f && wn * bd < bn * wd;
+                bn = c2 ? wn : bn;
+                bd = c2 ? wd : bd;
+                be = c2 ? 2 : be;
             }
             if (be < 0 && !fail && fresh) { AUVPF_REASON(1); fail = true; }   // curve turns back through its entry edge
             const float dp = fast_div(bn, bd);
@@ -991,22 +995,25 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     ba_end = beam_addr(tabs, T.B);
                     s_lim = T.s_lim[1];
                     sgf = -sgf;
+                    lgx = -lgx;
+                    lgy = -lgy;
+                    lz = -lz;
                     ax = beam_aux(tabs, ba);
                     cx = S.cx;
                     cy = S.cy;
-                    zi = cy * m.pitch + cx;
-                    u = S.u;
-                    v = S.v;
-                    lower = u >= v;
+                    lower = S.u >= S.v;
+                    a = lower ? S.u : S.v;
+                    b = lower ? S.v : S.u;
                     entry = -1;
                     p_cur = 0.0;
                     q_cur = S.q0;
                     p_f = 0.f;
                     q_f = (float)S.q0;
-                    z00 = ldg_f(m.z + zi);
-                    z01 = ldg_f(m.z + zi + 1);
-                    z10 = ldg_f(m.z + zi + m.pitch);
-                    z11 = ldg_f(m.z + zi + m.pitch + 1);
+                    const float *zp = m.z + (cy * m.pitch + cx);
+                    z00 = ldg_f(zp);
+                    z01 = ldg_f(zp + 1);
+                    z10 = ldg_f(zp + m.pitch);
+                    z11 = ldg_f(zp + m.pitch + 1);
                 } else
                     running = false;
             } else {
@@ -1016,19 +1023,20 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 p_cur += (double)dp;
                 q_f = (float)q_cur;
                 p_f = (float)p_cur;
-                u = fminf(fmaxf(fmaf(dp, X1, u), 0.f), 1.f);
-                v = fminf(fmaxf(fmaf(dp, Y1, v), 0.f), 1.f);
-                const bool diag = be == 2;                         // diagonal: same cell, other half
-                const bool uedge = !diag && ((be == 0) == lower);  // an x = const edge
-                const bool vedge = !diag && !uedge;
-                const int dir = be == 0 ? 1 : -1;                  // edge 0: coordinate reached 1, edge 1: reached 0
-                const float nc = be == 0 ? 0.f : 1.f;
-                const float mid = 0.5f * (u + v);
-                cx += uedge ? dir : 0;
-                cy += vedge ? dir : 0;
-                zi += uedge ? dir : (vedge ? dir * m.pitch : 0);
-                u = diag ? mid : (uedge ? nc : u);
-                v = diag ? mid : (vedge ? nc : v);
+                // In canonical coordinates the step across an edge does not depend on the half the curve is in:
+                // edge 0 (a = 1): (a, b) -> (b, 0); edge 1 (b = 0): (a, b) -> (1, a); the diagonal: both -> their mean.
+                // Which cell that is does: edge 0 leads to x + 1 from the lower half, y + 1 from the upper one,
+                // edge 1 to y - 1 / x - 1; the diagonal stays in the cell.  Every crossing changes the half.
+                const float a_adv = fminf(fmaxf(fmaf(dp, A1, a), 0.f), 1.f);
+                const float b_adv = fminf(fmaxf(fmaf(dp, B1, b), 0.f), 1.f);
+                const float mid = 0.5f * (a_adv + b_adv);
+                const bool diag = be == 2;
+                a = be == 0 ? b_adv : (diag ? mid : 1.f);
+                b = be == 0 ? 0.f : (diag ? mid : a_adv);
+                const bool xedge = (be == 0) == lower;             // (meaningless on the diagonal, masked below)
+                const int dir = diag ? 0 : (be == 0 ? 1 : -1);     // edge 0: coordinate reached 1, edge 1: reached 0
+                cx += xedge ? dir : 0;
+                cy += xedge ? 0 : dir;
                 if ((unsigned)cx > (unsigned)(m.W - 2) || (unsigned)cy > (unsigned)(m.H - 2)) {   // left the map
                     AUVPF_REASON(2);
                     if (kBorder) {
@@ -1040,16 +1048,16 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                         ba = ba_end;                               // the side switch happens in the next step
                         cx = S.cx;                                 // (any cell inside the map: the step's loads stay in bounds)
                         cy = S.cy;
-                        zi = cy * m.pitch + cx;
                     } else {
                         ok = false;
                         running = false;
                     }
                 } else if (!diag) {
-                    z00 = ldg_f(m.z + zi);
-                    z01 = ldg_f(m.z + zi + 1);
-                    z10 = ldg_f(m.z + zi + m.pitch);
-                    z11 = ldg_f(m.z + zi + m.pitch + 1);
+                    const float *zp = m.z + (cy * m.pitch + cx);
+                    z00 = ldg_f(zp);
+                    z01 = ldg_f(zp + 1);
+                    z10 = ldg_f(zp + m.pitch);
+                    z11 = ldg_f(zp + m.pitch + 1);
                 }
                 lower = !lower;
                 entry = be == 2 ? 2 : 1 - be;
