@@ -1346,9 +1346,10 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
             // ray); a SMALL grid strides over the list (usually empty: its blocks leave at once).  What even that
             // cannot certify (sensor outside the map, centre beam missed, a facet steeper than the fan tilt allows)
             // goes on list 2 ...
-            const int blocks2 = (int)std::min<int64_t>((h->M + kProfThreads - 1) / kProfThreads, std::max<int64_t>(1, (148 * kProfMinBlocks) / h->F));
-            k_update_mbes_profile<kProfThreads, kProfMinBlocks, true>
-                <<<dim3((unsigned)blocks2, (unsigned)h->F), kProfThreads, smp, h->stream>>>(
+            const int blocks2 = (int)std::min<int64_t>((h->M + kProfThreadsBorder - 1) / kProfThreadsBorder,
+                                                       std::max<int64_t>(1, (148 * kProfMinBlocksBorder) / h->F));
+            k_update_mbes_profile<kProfThreadsBorder, kProfMinBlocksBorder, true>
+                <<<dim3((unsigned)blocks2, (unsigned)h->F), kProfThreadsBorder, smp, h->stream>>>(
                     h->st[h->cur], h->M, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->meas, h->B,
                     (float)h->cfg.range_min, nhiv, lnb, h->logw, h->flagged, count1, h->flagged2, count2, h->wmax_f32);
             LAUNCHED(h, AUVPF_K_UPDATE_MBES, 2);

@@ -440,12 +440,20 @@ k_raycast_poses(const double *__restrict__ poses, int64_t n, FrameParams fp, Dem
 // footprint is shared in L1.  Particles that cannot be certified (near the map border, centre
 // beam missed, a triangle steeper than the fan tilt allows) are flagged and recast by the
 // per-ray kernel above.
-// Block shapes of the profile kernel, measured at C3 / C2 (ms): (128 thr, 5 blocks/SM, 96 regs) 4.60 / 0.142;
-// (128, 6, 80 regs) 4.23 / 0.142; (192, 3, 96 regs) 4.24 / 0.132; (256, 2, 109 regs, no spill) 4.44 / 0.118.
-// A saturated GPU wants the 24-warp or the 192-thread shape; a cloud that does not fill the machine
-// (fewer than ~4 warps per scheduler) runs fastest with all the registers it wants.
-constexpr int kProfThreads = 192, kProfMinBlocks = 3;
+// Block shapes of the profile kernel at C3 (ms per update, converged cloud).  Round 1, 245 instructions per march
+// step: (128 thr, 5 blocks/SM, 96 regs) 4.60; (128, 6, 80 regs) 4.23; (192, 3, 96 regs) 4.24; (256, 2, 109 regs)
+// 4.44.  Round 2, after the march step went to ~195 instructions: (192, 3, 96 regs) 3.62; (192, 4, 80 regs)
+// 3.29; (256, 3, 80) 3.29; (128, 6, 80) 3.30; (128, 7, 72 regs, 24 B of spills) 3.23; (128, 8, 64 regs) 3.31;
+// (256, 4, 64) 3.30 -- the leaner loop is a shorter dependent chain per warp, so warps per scheduler (7 instead of
+// 4.5) now buy more than registers do.  A cloud that does not fill the machine (fewer than ~4 warps per scheduler)
+// still runs fastest with all the registers it wants (C2: 0.118 ms at (256, 2) against 0.142 at (128, 6)).
+#ifndef AUVPF_PROF_T          // (kernel-tuning builds: make EXTRA="-DAUVPF_PROF_T=128 -DAUVPF_PROF_MINB=6" OUT=../lib_x.so)
+#define AUVPF_PROF_T 128
+#define AUVPF_PROF_MINB 7
+#endif
+constexpr int kProfThreads = AUVPF_PROF_T, kProfMinBlocks = AUVPF_PROF_MINB;
 constexpr int kProfThreadsSmall = 256, kProfMinBlocksSmall = 2;
+constexpr int kProfThreadsBorder = 192, kProfMinBlocksBorder = 3;   // the map-border variant wants its 96 registers
 constexpr int64_t kProfSmallLimit = 148 * 4 * 4 * 32;      // particles below which the small-cloud shape is used
 
 // shared memory: tan (double B) | sec (double B) | aux (BeamAux B: sec, reach, measured range)
