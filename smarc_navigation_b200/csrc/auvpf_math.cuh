@@ -885,8 +885,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     int cx = S.cx, cy = S.cy;
     // position inside the triangle in CANONICAL coordinates a >= b: (a, b) = (u, v) in the lower half of the cell
     // (u >= v), (v, u) in the upper half.  Edges: 0: a = 1, 1: b = 0, 2: a = b (the diagonal).
-    bool lower = S.u >= S.v;
-    float a = lower ? S.u : S.v, b = lower ? S.v : S.u;
+    bool lower_rt = S.u >= S.v;            // the half the curve is in; EVERY edge crossing changes it
+    float a = lower_rt ? S.u : S.v, b = lower_rt ? S.v : S.u;
     int entry = -1;                        // canonical edge the curve entered the triangle through
     double p_cur = 0.0, q_cur = S.q0;
     float p_f = 0.f, q_f = (float)S.q0;    // float32 copies of the two accumulators
@@ -904,10 +904,13 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
         z11 = ldg_f(zp + m.pitch + 1);
         ax = beam_aux(tabs, ba);
     }
-    for (int step = 0; step < max_steps; ++step) {
-        const unsigned act = AUVPF_WARP_BALLOT(running);
-        if (!act) break;
-        if (running) {
+    // One march step = one triangle.  Because every crossing changes the half, the loop below runs the steps in
+    // pairs -- a lower-half instantiation, then an upper-half one -- and `lower` is a compile-time constant in both
+    // (gradient, direction and neighbour selects fold away).  A lane whose triangle is of the other half sits a
+    // half-trip out; that happens once per side (at its start), after that the lane alternates with the loop.
+    auto march_step = [&](auto lower_c, const unsigned act) {
+        constexpr bool lower = decltype(lower_c)::value;
+        {
             bool fail = false;
             const bool fresh = !kBorder || ba != ba_end;     // false only in the step after a side ran off the map: nothing left to march
             const float Du = lower ? z01 - z00 : z11 - z10;      // dh/du, dh/dv of this triangle (per cell)
@@ -1001,9 +1004,9 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     ax = beam_aux(tabs, ba);
                     cx = S.cx;
                     cy = S.cy;
-                    lower = S.u >= S.v;
-                    a = lower ? S.u : S.v;
-                    b = lower ? S.v : S.u;
+                    lower_rt = S.u >= S.v;
+                    a = lower_rt ? S.u : S.v;
+                    b = lower_rt ? S.v : S.u;
                     entry = -1;
                     p_cur = 0.0;
                     q_cur = S.q0;
@@ -1059,11 +1062,25 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     z10 = ldg_f(zp + m.pitch);
                     z11 = ldg_f(zp + m.pitch + 1);
                 }
-                lower = !lower;
+                lower_rt = !lower;
                 entry = be == 2 ? 2 : 1 - be;
             }
         }
-        AUVPF_WARP_SYNC();      // (measured: relying on the next iteration's ballot alone is 1.2 % slower)
+    };
+    for (int step = 0; step < max_steps; step += 2) {
+        if (!AUVPF_WARP_BALLOT(running)) break;
+        {
+            const bool go = running && lower_rt;
+            const unsigned act = AUVPF_WARP_BALLOT(go);
+            if (go) march_step(std::true_type{}, act);
+            AUVPF_WARP_SYNC();      // (measured: relying on the next ballot alone is 1.2 % slower)
+        }
+        {
+            const bool go = running && !lower_rt;
+            const unsigned act = AUVPF_WARP_BALLOT(go);
+            if (go) march_step(std::false_type{}, act);
+            AUVPF_WARP_SYNC();
+        }
     }
     if (running) {                           // ran out of steps: not certified
         AUVPF_REASON(3);
