@@ -5,6 +5,7 @@ TAG=$1; WORLDS=${2:-2}; shift 2
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
 for W in $WORLDS; do
+  [ -n "$NOTEST" ] && continue
   AUVPF_TEST_WORLD=$W timeout 900 python -m pytest tests/test_gpu_sharded.py -m gpu -x -q -k "on_gpus" > gpurun_out/pytest_sharded_${TAG}_w$W.log 2>&1
   echo "world $W pytest rc=$?"; tail -4 gpurun_out/pytest_sharded_${TAG}_w$W.log
 done
