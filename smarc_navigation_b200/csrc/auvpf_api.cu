@@ -1331,7 +1331,7 @@ int auvpf_update_mbes(auvpf_handle *h, const float *ranges, float *logw_out)
         if (h->fan.planar && h->use_profile) {
             // profile merge, one thread per particle.  Pass 1: every particle, the lean interior variant; a sensor
             // closer to the border than its reach goes on list 1 ...
-            const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B;
+            const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B + 2 * sizeof(BeamAux);
             if (h->N <= kProfSmallLimit)
                 k_update_mbes_profile<kProfThreadsSmall, kProfMinBlocksSmall, false>
                     <<<grid1(h->M, kProfThreadsSmall, h->F), kProfThreadsSmall, smp, h->stream>>>(
@@ -1400,7 +1400,7 @@ int auvpf_raycast(auvpf_handle *h, const double *poses, int64_t n, float *ranges
         if (h->fan.planar && h->use_profile) {
             void *fl;
             if ((rc = slot_reserve(h, S_OUT1, (size_t)n, &fl))) return rc;
-            const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B;
+            const size_t smp = (2 * sizeof(double) + sizeof(BeamAux)) * h->B + 2 * sizeof(BeamAux);
             k_raycast_poses_profile<<<grid1(n, kProfThreads, 1), kProfThreads, smp, h->stream>>>(
                 pd, n, h->frame, h->dem, h->fan, h->beam_tan, h->beam_aux, h->B, od, static_cast<unsigned char *>(fl));
             only = static_cast<unsigned char *>(fl);

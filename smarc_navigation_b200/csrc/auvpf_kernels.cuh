@@ -456,7 +456,7 @@ constexpr int kProfThreadsSmall = 256, kProfMinBlocksSmall = 2;
 constexpr int kProfThreadsBorder = 192, kProfMinBlocksBorder = 3;   // the map-border variant wants its 96 registers
 constexpr int64_t kProfSmallLimit = 148 * 4 * 4 * 32;      // particles below which the small-cloud shape is used
 
-// shared memory: tan (double B) | sec (double B) | aux (BeamAux B: sec, reach, measured range)
+// shared memory: tan (double B) | sec (double B) | aux (BeamAux B + 2: sec, reach, measured range, tan; a sentinel at either end)
 // beam_tan = [tan | sec] (2B doubles), beam_aux[0..B) = |lateral component|
 __device__ __forceinline__ FanTables make_tables(const FanParams &fan, int B, const double *s_tan, const double *s_sec,
                                                  const BeamAux *s_aux)
@@ -493,7 +493,7 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
 {
     extern __shared__ double smd[];
     double *s_tan = smd, *s_sec = smd + B;
-    BeamAux *s_aux = reinterpret_cast<BeamAux *>(smd + 2 * B);
+    BeamAux *s_aux = reinterpret_cast<BeamAux *>(smd + 2 * B) + 1;        // entries -1 and B: the sentinels (beam_sentinel)
     __shared__ int s_valid;
     const int f = blockIdx.y;
     const int64_t n_work = kBorder ? (int64_t)(in_count[f] - (unsigned int)kWmaxReset) : M;
@@ -514,6 +514,7 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
         s_aux[b] = a;
         nv += ok ? 1 : 0;
     }
+    if (threadIdx.x == 0) s_aux[-1] = s_aux[B] = beam_sentinel();
     if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
     const FanTables T = make_tables(fan, B, s_tan, s_sec, s_aux);
@@ -555,7 +556,7 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
 {
     extern __shared__ double smd[];
     double *s_tan = smd, *s_sec = smd + B;
-    BeamAux *s_aux = reinterpret_cast<BeamAux *>(smd + 2 * B);
+    BeamAux *s_aux = reinterpret_cast<BeamAux *>(smd + 2 * B) + 1;        // entries -1 and B: the sentinels (beam_sentinel)
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         s_tan[b] = beam_tan[b];
         s_sec[b] = beam_tan[B + b];
@@ -566,6 +567,7 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
         a.tn = (float)beam_tan[b];
         s_aux[b] = a;
     }
+    if (threadIdx.x == 0) s_aux[-1] = s_aux[B] = beam_sentinel();
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
     const bool active = i < n;

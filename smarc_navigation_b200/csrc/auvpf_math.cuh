@@ -789,6 +789,16 @@ struct BeamTabs {
 #endif
 };
 
+// Table entries -1 and B: nothing compares true against a NaN, so the beam loop reads the entry past a side's last
+// beam like any other, finds neither a hit nor a miss and stops -- it needs no end-of-table test of its own.
+AUVPF_HD BeamAux beam_sentinel()
+{
+    BeamAux a;
+    a.sec = 0.f;
+    a.reach = a.meas = a.tn = nanf("");
+    return a;
+}
+
 AUVPF_HD uint32_t beam_addr(const BeamTabs &t, int b) { return t.base + 16u * (uint32_t)b; }
 AUVPF_HD int beam_index(const BeamTabs &t, uint32_t ba) { return (int)(ba - t.base) >> 4; }
 
@@ -799,7 +809,7 @@ AUVPF_HD BeamAux beam_aux(const BeamTabs &t, uint32_t ba)
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.sec), "=f"(a.reach), "=f"(a.meas), "=f"(a.tn) : "r"(ba));
     return a;
 #else
-    return t.aux[ba >> 4];
+    return t.aux[(int32_t)ba >> 4];      // (entry -1 is the lower sentinel)
 #endif
 }
 
@@ -961,7 +971,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             // Two instantiations of the loop: on a segment whose slope cannot make any beam of this side graze
             // (s <= s_lim, all of a smooth seabed) the float64 re-solve and its test are not compiled in.
             auto resolve_beams = [&](auto may_graze) {
-                while (ba != ba_end) {
+                for (;;) {                                 // ends at the side's sentinel entry at the latest
                     const float den = fmaf(-s, ax.tn, 1.0f);
                     const float gap = fmaf(q_f, ax.tn, -p_f);
                     const bool hit = gap <= dp * den;
@@ -981,7 +991,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     const float range = fminf(fmaxf(hit ? t : kBigT, 0.f), rmax);
                     sink(beam_index(tabs, ba), range, ax.meas);
                     ba += bstep;
-                    if (ba != ba_end) ax = beam_aux(tabs, ba);         // the next beam's constants
+                    ax = beam_aux(tabs, ba);               // the next beam's constants (or the sentinel's)
                 }
             };
             if (!fail) {
@@ -1054,6 +1064,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                         ex_j[side] = side == 0 ? T.n1 - 1 - ex_bb[side] : ex_bb[side] - T.n1;
                         ex_p[side] = p_f;
                         ba = ba_end;                               // the side switch happens in the next step
+                        ax = beam_aux(tabs, ba);                   // (the sentinel: the beam loop finds nothing)
                         cx = S.cx;                                 // (any cell inside the map: the step's loads stay in bounds)
                         cy = S.cy;
                     } else {

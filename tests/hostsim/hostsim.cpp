@@ -135,7 +135,8 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
         if (use_fan == 2) {
             // profile merge (k_update_mbes_profile): one march per side, generic fallback
             FanTables T;
-            std::vector<BeamAux> aux(B);
+            std::vector<BeamAux> aux_store(B + 2, beam_sentinel());      // entries -1 and B: the sentinels
+            BeamAux *aux = aux_store.data() + 1;
             for (int b = 0; b < B; ++b) {
                 aux[b].sec = (float)plan.sec_t[b];
                 aux[b].reach = plan.s[b] * v.range_max;
@@ -144,7 +145,7 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
             }
             T.tan_t = plan.tan_t.data();
             T.sec_t = plan.sec_t.data();
-            T.aux = aux.data();
+            T.aux = aux;
             T.B = B;
             T.n1 = plan.n1;
             T.sgn1 = plan.sgn1;
