@@ -1057,6 +1057,8 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
     DemView &d = h->dem;
     d.z = z00;
     d.W = W;
+    d.last_cx = W - 2;
+    d.last_cy = H - 2;
     d.H = H;
     d.pitch = pitch;
     d.mip[0] = lvl_lo;

@@ -514,7 +514,7 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
         s_aux[b] = a;
         nv += ok ? 1 : 0;
     }
-    if (threadIdx.x == 0) s_aux[-1] = s_aux[B] = beam_sentinel();
+    if (threadIdx.x == 0) s_aux[-1] = s_aux[B] = beam_sentinel(dem.range_max);
     if (nv) atomicAdd(&s_valid, nv);
     __syncthreads();
     const FanTables T = make_tables(fan, B, s_tan, s_sec, s_aux);
@@ -567,7 +567,7 @@ k_raycast_poses_profile(const double *__restrict__ poses, int64_t n, FrameParams
         a.tn = (float)beam_tan[b];
         s_aux[b] = a;
     }
-    if (threadIdx.x == 0) s_aux[-1] = s_aux[B] = beam_sentinel();
+    if (threadIdx.x == 0) s_aux[-1] = s_aux[B] = beam_sentinel(dem.range_max);
     __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * kProfThreads + threadIdx.x;
     const bool active = i < n;

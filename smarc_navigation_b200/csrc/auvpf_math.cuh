@@ -285,6 +285,7 @@ constexpr int kMaxLevels = 2;
 struct DemView {
     const float *z;      // vertex (0,0); row pitch `pitch` floats; rows/cols -1 .. H / W are readable
     int W, H, pitch;
+    int last_cx, last_cy;   // W - 2, H - 2: the last cell column / row (a kernel parameter the march compares against directly)
     const float *mip[kMaxLevels];   // mip[0] = finer block level, mip[1] = coarser (or unused)
     int mipW[kMaxLevels], mipH[kMaxLevels], shift[kMaxLevels];
     int n_levels;        // 1 or 2
@@ -791,10 +792,12 @@ struct BeamTabs {
 
 // Table entries -1 and B: nothing compares true against a NaN, so the beam loop reads the entry past a side's last
 // beam like any other, finds neither a hit nor a miss and stops -- it needs no end-of-table test of its own.
-AUVPF_HD BeamAux beam_sentinel()
+// (Its unused first word carries range_max: read back from shared memory the value is a plain register to the
+// compiler, which otherwise re-reads the kernel parameter from the constant bank in every trip of the beam loop.)
+AUVPF_HD BeamAux beam_sentinel(float range_max)
 {
     BeamAux a;
-    a.sec = 0.f;
+    a.sec = range_max;
     a.reach = a.meas = a.tn = nanf("");
     return a;
 }
@@ -892,10 +895,10 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     ax.sec = 1.f;
     ax.reach = ax.meas = ax.tn = 0.f;
 #if defined(__CUDA_ARCH__)
-    float rmax;                            // pinned in a register: left alone the compiler re-reads it from the constant
-    asm volatile("mov.f32 %0, %1;" : "=f"(rmax) : "f"(m.range_max));     // bank in every trip of the beam loop (0.7 %)
+    float rmax;                            // range_max from the sentinel entry (see beam_sentinel)
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rmax) : "r"((uint32_t)__cvta_generic_to_shared(T.aux) - 16u));
 #else
-    const float rmax = m.range_max;
+    const float rmax = T.aux[-1].sec;
 #endif
     int cx = S.cx, cy = S.cy;
     // position inside the triangle in CANONICAL coordinates a >= b: (a, b) = (u, v) in the lower half of the cell
@@ -988,7 +991,9 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                         }
                     }
                     // not hit: out of reach, a miss; a hit beyond range_max is one as well
-                    const float range = fminf(fmaxf(hit ? t : kBigT, 0.f), rmax);
+                    // (no clamp at zero on the no-graze path: the hit lies on a segment of the curve, in front of the sensor)
+                    if (decltype(may_graze)::value) t = fmaxf(t, 0.f);
+                    const float range = fminf(hit ? t : kBigT, rmax);
                     sink(beam_index(tabs, ba), range, ax.meas);
                     ba += bstep;
                     ax = beam_aux(tabs, ba);               // the next beam's constants (or the sentinel's)
@@ -1055,7 +1060,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 const int dir = diag ? 0 : (be == 0 ? 1 : -1);     // edge 0: coordinate reached 1, edge 1: reached 0
                 cx += xedge ? dir : 0;
                 cy += xedge ? 0 : dir;
-                if ((unsigned)cx > (unsigned)(m.W - 2) || (unsigned)cy > (unsigned)(m.H - 2)) {   // left the map
+                if ((unsigned)cx > (unsigned)m.last_cx || (unsigned)cy > (unsigned)m.last_cy) {   // left the map
                     AUVPF_REASON(2);
                     if (kBorder) {
                         // the rest of this side is finished ray by ray AFTER the march loop (finish_side_by_rays);

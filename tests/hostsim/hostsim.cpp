@@ -87,6 +87,8 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
     DemView &v = d.v;
     v.z = zp.data() + pitch + 1;
     v.W = W;
+    v.last_cx = W - 2;
+    v.last_cy = H - 2;
     v.H = H;
     v.pitch = pitch;
     v.mip[0] = d.mip.data();
@@ -135,7 +137,7 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
         if (use_fan == 2) {
             // profile merge (k_update_mbes_profile): one march per side, generic fallback
             FanTables T;
-            std::vector<BeamAux> aux_store(B + 2, beam_sentinel());      // entries -1 and B: the sentinels
+            std::vector<BeamAux> aux_store(B + 2, beam_sentinel(v.range_max));      // entries -1 and B: the sentinels
             BeamAux *aux = aux_store.data() + 1;
             for (int b = 0; b < B; ++b) {
                 aux[b].sec = (float)plan.sec_t[b];
