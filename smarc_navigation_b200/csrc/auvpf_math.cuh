@@ -991,9 +991,13 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                         }
                     }
                     // not hit: out of reach, a miss; a hit beyond range_max is one as well
-                    // (no clamp at zero on the no-graze path: the hit lies on a segment of the curve, in front of the sensor)
-                    if (decltype(may_graze)::value) t = fmaxf(t, 0.f);
-                    const float range = fminf(hit ? t : kBigT, rmax);
+                    // On the no-graze path den >= kDenPrecise > 0 for every beam, so (a) the hit lies on a segment of
+                    // the curve, in front of the sensor: no clamp at zero; (b) a beam resolved as a MISS (segment end
+                    // beyond its reach, no hit) meets the extended facet at a lateral distance > reach, i.e. its t
+                    // is >= range_max by itself: the clamp at range_max is all it needs.
+                    float range;
+                    if (decltype(may_graze)::value) range = fminf(hit ? fmaxf(t, 0.f) : kBigT, rmax);
+                    else range = fminf(t, rmax);
                     sink(beam_index(tabs, ba), range, ax.meas);
                     ba += bstep;
                     ax = beam_aux(tabs, ba);               // the next beam's constants (or the sentinel's)
