@@ -507,9 +507,11 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
         const float r = meas[(size_t)f * B + b];
         const bool ok = isfinite(r) && r >= range_min && r <= dem.range_max;
         BeamAux a;
-        a.sec = (float)beam_tan[B + b];
+        // a beam without a valid measurement: sec = 0 and meas = 0 -- its range comes out as 0 * (q at the hit) = 0,
+        // its error as 0 - 0, and the sum takes it like any other beam (no test per beam in the march's hot loop)
+        a.sec = ok ? (float)beam_tan[B + b] : 0.f;
         a.reach = beam_aux[b] * dem.range_max;
-        a.meas = ok ? r : __int_as_float(0x7fc00000);        // invalid measured beam: skipped in the sum
+        a.meas = ok ? r : 0.f;
         a.tn = (float)beam_tan[b];
         s_aux[b] = a;
         nv += ok ? 1 : 0;
@@ -533,11 +535,11 @@ k_update_mbes_profile(StateView s, int64_t M, FrameParams fp, DemView dem, FanPa
             dem, T, p, R, active,
             [&acc](int, float range, float rm) {
                 const float e = rm - range;
-                if (rm == rm) acc = fmaf(e, e, acc);
+                acc = fmaf(e, e, acc);
             },
             [&acc_exit](int, float range, float rm) {
                 const float e = rm - range;
-                if (rm == rm) acc_exit = fmaf(e, e, acc_exit);
+                acc_exit = fmaf(e, e, acc_exit);
             });
         if (kBorder) acc += acc_exit;
         const float lw = fmaf(neg_half_inv_var, acc, lognorm);

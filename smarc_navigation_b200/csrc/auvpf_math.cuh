@@ -772,7 +772,8 @@ double precise_hit(const ProfFrameD *D, float sgf, int cx, int cy, float z00, fl
 struct BeamAux {                             // one 16-byte load per beam: everything the beam loop reads
     float sec;                               // 1 / along-centre component (float32 copy)
     float reach;                             // |lateral component| * range_max: lateral distance the beam can cover
-    float meas;                              // measured range of the ping (NaN = beam not used); 0 for probes
+    float meas;                              // measured range of the ping; 0 for probes.  A beam of the ping without a
+                                             // valid measurement has sec = 0 AND meas = 0: range 0, error 0.
     float tn;                                // |lateral| / along-centre component (float32 copy of tan_t)
 };
 
@@ -858,6 +859,7 @@ void finish_side_by_rays(const DemView m, const FanTables T, const ProfFrameD *D
         r.dz = (float)(ct * D->cz + sg * st * D->az);
         const float t_lo = st > 0.0 ? sweep_bound(p_clear, (float)(1.0 / st)) : 0.f;
         const float range = raycast_from(m, r, t_lo, false);
+        if (T.aux[bb].sec == 0.f) continue;          // no valid measurement on this beam: nothing to add (see BeamAux)
         sink(bb, range, T.aux[bb].meas);
     }
 }
@@ -988,6 +990,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                         if (hit && den < kDenPrecise) {
                             const int bb = beam_index(tabs, ba);
                             t = (float)(precise_hit(D, sgf, cx, cy, z00, z01, z10, z11, lower, T.tan_t[bb]) * T.sec_t[bb]);
+                            if (ax.sec == 0.f) t = 0.f;
                         }
                     }
                     // not hit: out of reach, a miss; a hit beyond range_max is one as well
@@ -996,7 +999,8 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     // beyond its reach, no hit) meets the extended facet at a lateral distance > reach, i.e. its t
                     // is >= range_max by itself: the clamp at range_max is all it needs.
                     float range;
-                    if (decltype(may_graze)::value) range = fminf(hit ? fmaxf(t, 0.f) : kBigT, rmax);
+                    // (kBigT * sec: range_max for a miss, but 0 for a beam without a valid measurement, sec = 0)
+                    if (decltype(may_graze)::value) range = fminf(hit ? fmaxf(t, 0.f) : kBigT * ax.sec, rmax);
                     else range = fminf(t, rmax);
                     sink(beam_index(tabs, ba), range, ax.meas);
                     ba += bstep;
