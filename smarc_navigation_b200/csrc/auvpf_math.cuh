@@ -905,18 +905,22 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
     int cx = S.cx, cy = S.cy;
     // position inside the triangle in CANONICAL coordinates a >= b: (a, b) = (u, v) in the lower half of the cell
     // (u >= v), (v, u) in the upper half.  Edges: 0: a = 1, 1: b = 0, 2: a = b (the diagonal).
-    bool lower_rt = S.u >= S.v;            // the half the curve is in; EVERY edge crossing changes it
-    float a = lower_rt ? S.u : S.v, b = lower_rt ? S.v : S.u;
-    int entry = -1;                        // canonical edge the curve entered the triangle through
+    const bool lower0 = S.u >= S.v;        // the half the curve starts in (both sides); EVERY edge crossing changes it
+    float a = lower0 ? S.u : S.v, b = lower0 ? S.v : S.u;
+    int prev_be = -1;                      // edge the previous triangle was left through: this one was entered through
+                                           // edge 1 after an exit through 0, edge 0 after 1, the diagonal after the diagonal
     double p_cur = 0.0, q_cur = S.q0;
     float p_f = 0.f, q_f = (float)S.q0;    // float32 copies of the two accumulators
-    bool running = active && T.B > 0;
-    bool ok = true;
+    // one word of state: marching in the lower / the upper half of a cell, then kDone or kFail (not certified).
+    // (Three bools were kept byte-packed in one register by the compiler and cost half a dozen byte-insert and
+    // mask instructions per step.)
+    enum : int { kLower = 0, kUpper = 1, kDone = 2, kFail = 3 };
+    int state = active && T.B > 0 ? (lower0 ? kLower : kUpper) : kDone;
     int ex_j[2] = {-1, -1}, ex_bb[2] = {0, 0};     // a side whose curve ran off the map: first unresolved beam (count, index) ...
     float ex_p[2] = {0.f, 0.f};                    // ... and the lateral distance the curve was marched to
     const int max_steps = 2 * (8 * (int)(m.range_max / m.res) + 256);
     float z00 = 0.f, z01 = 0.f, z10 = 0.f, z11 = 0.f;
-    if (running) {
+    if (state < kDone) {
         const float *zp = m.z + (cy * m.pitch + cx);       // the cell's vertex (0, 0) in the padded DEM
         z00 = ldg_f(zp);
         z01 = ldg_f(zp + 1);
@@ -945,19 +949,19 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             const float A1 = lower ? X1 : Y1, B1 = lower ? Y1 : X1;
             float bn = kBigT, bd = 1.f;                            // nearest exit = bn / bd
             int be = -1;
-            if (entry != 0 && A1 > 0.f) {
+            if (prev_be != 1 && A1 > 0.f) {
                 bn = 1.f - a;
                 bd = A1;
                 be = 0;
             }
-            if (entry != 1 && B1 < 0.f && b * bd < bn * -B1) {
+            if (prev_be != 0 && B1 < 0.f && b * bd < bn * -B1) {
                 bn = b;
                 bd = -B1;
                 be = 1;
             }
             {
                 const float wn = a - b, wd = B1 - A1;
-                const bool c2 = entry != 2 && wd > 0.f && wn * bd < bn * wd;
+                const bool c2 = prev_be != 2 && wd > 0.f && wn * bd < bn * wd;
                 bn = c2 ? wn : bn;
                 bd = c2 ? wd : bd;
                 be = c2 ? 2 : be;
@@ -1016,8 +1020,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
             // lanes; with the loop in its present form the compiler brackets it with its own reconvergence barrier
             // (BSSY / BSYNC), and the explicit one, with the ballot that made its mask, measured 4.3 % slower.)
             if (fail) {
-                ok = false;
-                running = false;
+                state = kFail;
             } else if (ba == ba_end) {
                 // this side is done: start the other one from the anchor, or finish
                 if (side == 0 && T.B - T.n1 > 0) {
@@ -1033,10 +1036,10 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     ax = beam_aux(tabs, ba);
                     cx = S.cx;
                     cy = S.cy;
-                    lower_rt = S.u >= S.v;
-                    a = lower_rt ? S.u : S.v;
-                    b = lower_rt ? S.v : S.u;
-                    entry = -1;
+                    state = lower0 ? kLower : kUpper;
+                    a = lower0 ? S.u : S.v;
+                    b = lower0 ? S.v : S.u;
+                    prev_be = -1;
                     p_cur = 0.0;
                     q_cur = S.q0;
                     p_f = 0.f;
@@ -1047,10 +1050,11 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     z10 = ldg_f(zp + m.pitch);
                     z11 = ldg_f(zp + m.pitch + 1);
                 } else
-                    running = false;
+                    state = kDone;
             } else {
                 // advance to the exit point and step into the neighbour across that edge (selects, not
                 // branches: lanes leaving through different edges stay converged)
+                state = lower ? kUpper : kLower;
                 q_cur += (double)(s * dp);
                 p_cur += (double)dp;
                 q_f = (float)q_cur;
@@ -1065,10 +1069,13 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                 const bool diag = be == 2;
                 a = be == 0 ? b_adv : (diag ? mid : 1.f);
                 b = be == 0 ? 0.f : (diag ? mid : a_adv);
-                const bool xedge = (be == 0) == lower;             // (meaningless on the diagonal, masked below)
-                const int dir = diag ? 0 : (be == 0 ? 1 : -1);     // edge 0: coordinate reached 1, edge 1: reached 0
-                cx += xedge ? dir : 0;
-                cy += xedge ? 0 : dir;
+                if (lower) {                                       // (a compile-time constant)
+                    cx += be == 0 ? 1 : 0;
+                    cy -= be == 1 ? 1 : 0;
+                } else {
+                    cy += be == 0 ? 1 : 0;
+                    cx -= be == 1 ? 1 : 0;
+                }
                 if ((unsigned)cx > (unsigned)m.last_cx || (unsigned)cy > (unsigned)m.last_cy) {   // left the map
                     AUVPF_REASON(2);
                     if (kBorder) {
@@ -1082,8 +1089,7 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                         cx = S.cx;                                 // (any cell inside the map: the step's loads stay in bounds)
                         cy = S.cy;
                     } else {
-                        ok = false;
-                        running = false;
+                        state = kFail;
                     }
                 } else if (!diag) {
                     const float *zp = m.z + (cy * m.pitch + cx);
@@ -1092,20 +1098,20 @@ AUVPF_HD bool profile_march(const DemView &m, const FanTables &T, const ProfFram
                     z10 = ldg_f(zp + m.pitch);
                     z11 = ldg_f(zp + m.pitch + 1);
                 }
-                lower_rt = !lower;
-                entry = be == 2 ? 2 : 1 - be;
+                prev_be = be;
             }
         }
     };
     for (int step = 0; step < max_steps; step += 2) {
-        if (!AUVPF_WARP_BALLOT(running)) break;              // (also the point where the warp reconverges once per pair)
-        if (running && lower_rt) march_step(std::true_type{});
-        if (running && !lower_rt) march_step(std::false_type{});
+        if (!AUVPF_WARP_BALLOT(state < kDone)) break;        // (also the point where the warp reconverges once per pair)
+        if (state == kLower) march_step(std::true_type{});
+        if (state == kUpper) march_step(std::false_type{});
     }
-    if (running) {                           // ran out of steps: not certified
+    if (state < kDone) {                     // ran out of steps: not certified
         AUVPF_REASON(3);
-        ok = false;
+        state = kFail;
     }
+    const bool ok = state != kFail;
     if (kBorder && ok && (ex_j[0] >= 0 || ex_j[1] >= 0)) {
         for (int sd = 0; sd < 2; ++sd)
             if (ex_j[sd] >= 0)
