@@ -130,7 +130,7 @@ struct auvpf_handle {
     bool have_norm = false;
 
     // map / sensor
-    float *dem_z = nullptr, *mip = nullptr, *mip_hi = nullptr, *beams = nullptr, *meas = nullptr;
+    float *dem_z = nullptr, *mip = nullptr, *mip_hi = nullptr, *beams = nullptr, *meas = nullptr, *slope_blk = nullptr;
     float *beam_aux = nullptr;   // [3B]: |sin th|, 1/|sin th|, 1/cos th
     double *beam_tan = nullptr;  // [2B]: tan |th|, 1 / cos th (profile merge)
     int *flagged = nullptr, *flagged2 = nullptr;   // [N] each, per filter: particles for the map-border pass / for the per-ray kernel
@@ -930,7 +930,7 @@ int auvpf_destroy(auvpf_handle *h)
                     h->a_pre, h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
                     h->wmax_f32, h->done, h->scan3, h->skipped,
-                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->flagged2, h->probe_flags.p,
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->slope_blk, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->flagged2, h->probe_flags.p,
                     h->replay_params.p, h->replay_ranges.p, h->replay_u.p, h->replay_stats.p};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
@@ -1053,6 +1053,13 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
     CU(cudaStreamSynchronize(h->stream));
     float max_slope;
     memcpy(&max_slope, &mx, sizeof max_slope);
+    // ... and per block of 128 x 128 cells: what certifies a profile march (local_max_slope)
+    const int sbW = std::max(1, (W - 1 + kSlopeBlock - 1) / kSlopeBlock), sbH = std::max(1, (H - 1 + kSlopeBlock - 1) / kSlopeBlock);
+    if (h->slope_blk) cudaFree(h->slope_blk);
+    h->slope_blk = nullptr;
+    CU(cudaMalloc(&h->slope_blk, sizeof(float) * (size_t)sbW * sbH));
+    k_slope_blocks<<<dim3((unsigned)sbW, (unsigned)sbH), 256, 0, h->stream>>>(z00, pitch, H, W, (float)(1.0 / res), h->slope_blk, sbW);
+    CU(cudaGetLastError());
 
     DemView &d = h->dem;
     d.z = z00;
@@ -1073,6 +1080,9 @@ int auvpf_set_dem(auvpf_handle *h, const float *z, int32_t H, int32_t W, double 
     d.range_max = (float)h->cfg.range_max;
     d.zmax = zmax;
     d.max_slope = max_slope * 1.0001f + 1e-6f;
+    d.slope_blk = h->slope_blk;
+    d.sbW = sbW;
+    d.sbH = sbH;
     d.res = (float)res;
     d.x0 = x0;
     d.y0 = y0;

@@ -687,6 +687,28 @@ __global__ void k_max_slope(const float *z, int pitch, int H, int W, float inv_r
     if ((threadIdx.x & 31) == 0) atomicMax(out_ordered, float_to_ordered(m));
 }
 
+// the same per block of kSlopeBlock x kSlopeBlock cells (DemView::slope_blk): one thread block per slope block
+__global__ void k_slope_blocks(const float *z, int pitch, int H, int W, float inv_res, float *out, int sbW)
+{
+    __shared__ float s_m[8];
+    const int i0 = blockIdx.y * kSlopeBlock, j0 = blockIdx.x * kSlopeBlock;
+    float m = 0.f;
+    for (int c = threadIdx.x; c < kSlopeBlock * kSlopeBlock; c += blockDim.x) {
+        const int i = i0 + c / kSlopeBlock, j = j0 + c % kSlopeBlock;
+        if (i >= H - 1 || j >= W - 1) continue;
+        const float *p = z + (size_t)i * pitch + j;
+        const float z00 = p[0], z01 = p[1], z10 = p[pitch], z11 = p[pitch + 1];
+        m = fmaxf(m, fmaxf(hypotf(z01 - z00, z11 - z01), hypotf(z11 - z10, z10 - z00)) * inv_res);
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmaxf(m, s_m[k]);
+        out[(size_t)blockIdx.y * sbW + blockIdx.x] = m * 1.0001f + 1e-6f;       // (the margin max_slope carries)
+    }
+}
+
 __global__ void k_max_f32(const float *in, int64_t n, int *out_ordered)
 {
     float m = -INFINITY;

@@ -292,6 +292,8 @@ struct DemView {
     float range_max;
     float zmax;          // global maximum height
     float max_slope;     // largest triangle gradient norm |grad h| (Lipschitz constant of the surface)
+    const float *slope_blk;   // the same per block of kSlopeBlock x kSlopeBlock cells, [sbH][sbW] (local_max_slope)
+    int sbW, sbH;
     float res;           // cell size [m]
     double x0, y0, inv_res_d;
 };
@@ -336,6 +338,20 @@ AUVPF_HD float fast_div(float a, float b)
 }
 
 AUVPF_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+constexpr int kSlopeShift = 7, kSlopeBlock = 1 << kSlopeShift;     // 128 x 128 cells: a 120 m reach on a 0.5 m map touches 5 x 5 blocks
+
+// Largest triangle gradient norm among the cells within `radius` cells of the grid position (gx, gy).
+AUVPF_HD float local_max_slope(const DemView &m, double gx, double gy, double radius)
+{
+    const int j0 = clampi((int)floor(gx - radius) >> kSlopeShift, 0, m.sbW - 1), j1 = clampi((int)floor(gx + radius) >> kSlopeShift, 0, m.sbW - 1);
+    const int i0 = clampi((int)floor(gy - radius) >> kSlopeShift, 0, m.sbH - 1), i1 = clampi((int)floor(gy + radius) >> kSlopeShift, 0, m.sbH - 1);
+    float s = 0.f;
+    for (int i = i0; i <= i1; ++i)
+        for (int j = j0; j <= j1; ++j) s = fmaxf(s, ldg_f(m.slope_blk + (size_t)i * m.sbW + j));
+    return s;
+}
+
 
 constexpr float kBigT = 3.0e38f;
 constexpr float kSkipMargin = 2.0e-3f;   // [m] slack that keeps max skipping conservative in fp32
@@ -1172,6 +1188,19 @@ AUVPF_HD bool profile_particle(const DemView &m, const FanTables &T, const doubl
             cw[a] = R[3 * a] * T.c0[0] + R[3 * a + 1] * T.c0[1] + R[3 * a + 2] * T.c0[2];
         }
         if (!(aw[0] * aw[0] + aw[1] * aw[1] > 1.0e-6)) { ok = false; break; }   // fan plane (nearly) horizontal
+        // The march follows ONE curve -- the connected piece of (fan plane) x (surface) through the centre hit --
+        // and that is every beam's first hit only if the intersection is a single-valued profile q = T(p): if
+        // gamma < 0 on EVERY facet the fan plane crosses within reach, not just on those the curve meets.  (A
+        // sensor pitched 23 deg over 60 deg ridge faces sees crests as overhangs: a beam hit one at 29.35 m that
+        // the curve passes at 35 m; the march, stopped early by a short range_max, never met the facet whose
+        // gamma would have failed it.)  gamma = c_z - c_xy . grad h <= c_z + |c_xy| max|grad h|: certified from
+        // the largest facet gradient in the blocks the reach touches; otherwise the particle goes ray by ray.
+        {
+            const double cxy = sqrt(cw[0] * cw[0] + cw[1] * cw[1]);
+            const double radius = reach * (1.0 + cxy) * m.inv_res_d + 2.0;          // lateral reach + drift of the curve along c
+            const float slope = local_max_slope(m, (p[0] - m.x0) * m.inv_res_d, (p[1] - m.y0) * m.inv_res_d, radius);
+            if (!(cw[2] + cxy * (double)slope < -(double)kGammaMin)) { AUVPF_REASON(7); ok = false; break; }
+        }
         // anchor: the triangle under the centre hit, and the hit re-solved on its plane in float64
         const double gox = (p[0] - m.x0) * m.inv_res_d, goy = (p[1] - m.y0) * m.inv_res_d;   // sensor, grid units
         const double cgx = cw[0] * m.inv_res_d, cgy = cw[1] * m.inv_res_d;

@@ -24,7 +24,7 @@ long g_prof_reasons[8] = {0};
 
 namespace {
 struct HostDem {
-    std::vector<float> mip;
+    std::vector<float> mip, slope_blk;
     DemView v;
 };
 
@@ -112,6 +112,19 @@ void hs_raycast_poses(const float *z, int H, int W, double x0, double y0, double
                 ms = std::max(ms, std::max(std::hypot(z01 - z00, z11 - z01), std::hypot(z11 - z10, z10 - z00)) * (float)(1.0 / res));
             }
         v.max_slope = ms * 1.0001f + 1e-6f;
+        // per block of kSlopeBlock x kSlopeBlock cells (k_slope_blocks)
+        v.sbW = std::max(1, (W - 1 + kSlopeBlock - 1) / kSlopeBlock);
+        v.sbH = std::max(1, (H - 1 + kSlopeBlock - 1) / kSlopeBlock);
+        d.slope_blk.assign((size_t)v.sbW * v.sbH, 0.f);
+        for (int i = 0; i + 1 < H; ++i)
+            for (int j = 0; j + 1 < W; ++j) {
+                float z00 = z[(size_t)i * W + j], z01 = z[(size_t)i * W + j + 1], z10 = z[(size_t)(i + 1) * W + j],
+                      z11 = z[(size_t)(i + 1) * W + j + 1];
+                float &b = d.slope_blk[(size_t)(i >> kSlopeShift) * v.sbW + (j >> kSlopeShift)];
+                b = std::max(b, std::max(std::hypot(z01 - z00, z11 - z01), std::hypot(z11 - z10, z10 - z00)) * (float)(1.0 / res));
+            }
+        for (float &b : d.slope_blk) b = b * 1.0001f + 1e-6f;
+        v.slope_blk = d.slope_blk.data();
     }
     v.x0 = x0;
     v.y0 = y0;

@@ -319,6 +319,57 @@ def test_update_mbes_mixed_profile_and_per_ray_particles():
     pf.close()
 
 
+@pytest.mark.parametrize("rmax", [world.RANGE_MAX, 35.0])
+def test_update_mbes_unusable_beams_on_every_path(rmax):
+    """A ping whose beams are partly unusable (NaN, inf, below range_min, beyond range_max -- the nadir beam and the
+    outermost beam of either side among them) on ridged terrain: the march's no-graze and grazing beam loops, the
+    map-border variant with its ray-by-ray finish, and the per-ray fallback must all leave those beams out of the
+    sum exactly as the oracle does (the march carries no validity test per beam: an unusable beam is a table entry
+    whose range and error come out as zero).  With the short range_max the outer beams MISS as well."""
+    dem = _ridged_dem(700, 0.5)
+    ext = (dem["z"].shape[0] - 1) * dem["res"]
+    B = 256
+    beams = world.make_beams(B, 65.0).astype(np.float32).astype(np.float64)
+    rng = np.random.default_rng(123)
+    poses = np.concatenate([_cloud(rng, 400, (0.5 * ext, 0.5 * ext), 6.0, roll_pitch=0.03),          # interior
+                            _cloud(rng, 400, (0.5 * ext, 0.5 * ext), 6.0, roll_pitch=0.20),          # grazing beams / fallback
+                            _cloud(rng, 300, (0.04 * ext, 0.5 * ext), 5.0, roll_pitch=0.03),         # reach leaves the map
+                            _cloud(rng, 300, (0.95 * ext, 0.93 * ext), 5.0, roll_pitch=0.05)])       # ... in a corner
+    poses = poses[(poses[:, 0] > 0) & (poses[:, 0] < ext) & (poses[:, 1] > 0) & (poses[:, 1] < ext)]
+    truth = np.array([[0.5 * ext, 0.5 * ext, -5.0, 0.0, 0.0, 0.3]])
+    meas = (c_oracle.update_mbes(dem, truth, np.eye(4), beams, None, 1.0, 0.5, rmax, want_ranges=True)["ranges"][0]
+            + rng.normal(0, 0.05, B)).astype(np.float32)
+    bad = rng.choice(B, B // 4, replace=False)
+    meas[bad[0::4]] = np.nan
+    meas[bad[1::4]] = np.inf
+    meas[bad[2::4]] = 0.5 * world.RANGE_MIN
+    meas[bad[3::4]] = 2.0 * rmax
+    meas[[0, B - 1, B // 2]] = np.nan               # outermost beam of either side, and the nadir
+    pf = _pf(particle_count=len(poses), measurement_std=1.0, range_min=world.RANGE_MIN, range_max=rmax)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    pf.set_poses(poses)
+    pf.update_mbes(meas, return_weights=False)
+    got = pf.log_weights().astype(np.float64)
+    flagged = pf.mbes_flagged()
+    out = c_oracle.update_mbes(dem, poses, np.eye(4), beams, meas.astype(np.float64), 1.0, world.RANGE_MIN, rmax,
+                               want_ranges=True, want_diag=True)
+    extra, fr = fragile.logw_bound(dem, poses, np.eye(4), beams, meas, 1.0, world.RANGE_MIN, rmax, out)
+    n_valid = int(np.sum(np.isfinite(meas) & (meas >= world.RANGE_MIN) & (meas <= rmax)))
+    assert 0.4 * B < n_valid < 0.85 * B
+    lognorm = -n_valid * np.log(np.sqrt(2 * np.pi))
+    tol = LOGW_RTOL * (np.abs(out["logw"] - lognorm) + abs(lognorm)) + extra
+    d = np.abs(got - out["logw"])
+    assert np.all(d <= tol), np.max(d / tol)
+    assert int(flagged[:, 0].sum()) > 100 and int(flagged[:, 1].sum()) > 0          # every path was really taken
+    if rmax < world.RANGE_MAX:
+        assert (out["ranges"] >= rmax).mean() > 0.05                       # misses are present
+    fragile.report({"label": "unusable beams, rmax %g" % rmax, "particles": len(poses), "fragile_frac": float(fr.mean()),
+                    "border_pass": int(flagged[:, 0].sum()), "ray_by_ray": int(flagged[:, 1].sum()),
+                    "max_dlogw_over_tol": float(np.max(d / tol))})
+    pf.close()
+
+
 def test_quantised_dem_file_parity(tmp_path):
     """Map ingestion: a DEM file with uint16 heights.  The library and the oracle both see the
     dequantised float32 map, so ranges and log-weights keep the usual tolerances ON THAT MAP."""

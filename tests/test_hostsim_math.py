@@ -374,8 +374,12 @@ def test_profile_merge_vs_oracle(name):
     if name == "border":
         inside = (poses[:, 0] > 0.0).sum()
         assert n_prof == inside * r.shape[1]          # every sensor that stands over the map is certified by the march
-    elif name in ("tilted", "ridged_tilted"):
+    elif name == "tilted":
         assert n_prof >= 0.75 * r.size          # steep triangle x large tilt: some particles fall back
+    elif name == "ridged_tilted":
+        # 60-degree ridge faces: only sensors tilted less than ~14 degrees see a single-valued profile in their fan
+        # plane (the certificate of profile_particle); the others are recast ray by ray
+        assert 0.25 * r.size <= n_prof < 0.9 * r.size
     else:
         assert n_prof == r.size                 # every particle certified by the profile march
     if name == "short_range":
@@ -402,6 +406,31 @@ def test_profile_merge_near_every_border_and_corner(terrain):
     ro, err, fragile_ = _compare(dem, 2, poses, beams, np.eye(4), rmax, max_fragile_frac=frag, shift_hi=5, fan=2)
     assert n_prof >= (0.95 if terrain == "smooth" else 0.7) * r.size      # the march, not the per-ray fallback
     assert (ro >= rmax).mean() > 0.1 and (ro < rmax).mean() > 0.3       # misses beyond the border and hits before it
+
+
+def test_profile_merge_is_only_certified_where_the_profile_is_single_valued():
+    """Regression: a sensor pitched 23 degrees over 60-degree ridge faces sees crests as overhangs in its fan plane
+    -- the plane meets the surface in more than one piece, and a beam's first hit (29.35 m) lay on a piece the
+    marched curve does not contain (it passes there at 35 m).  With range_max = 35 m the march stopped before it
+    met the facet whose gamma would have failed it, and certified two wrong misses.  The certificate is now the
+    largest facet gradient within reach against the tilt; such sensors are recast ray by ray."""
+    rng = np.random.default_rng(123)
+    dem = _ridged_dem(n=700, res=0.5)
+    ext = (dem["z"].shape[0] - 1) * dem["res"]
+    beams = world.make_beams(256, 65.0)
+    poses = _cloud(rng, 600, (0.5 * ext, 0.5 * ext), 6.0, roll_pitch=0.20)
+    poses[0] = [169.579322, 174.228105, -5.0, 0.0849569291, 0.406004101, -2.71862006]      # the sensor it was found with
+    poses[1:40] = poses[0] + rng.normal(0, 1.0, (39, 6)) * np.array([0.3, 0.3, 0.0, 0.01, 0.01, 0.02])
+    for rmax in (35.0, 60.0):
+        out = c_oracle.update_mbes(dem, poses, np.eye(4), beams.astype(np.float32).astype(np.float64), None, 1.0, 0.5, rmax,
+                                   want_ranges=True, want_diag=True)
+        r, n_prof = hs.raycast_poses(dem, 2, rmax, np.eye(4), poses, beams.astype(np.float32), shift_hi=5, fan=2, want_swept=True)
+        ro, dg = out["ranges"], out["diag"]
+        sturdy = ~((dg[..., 0] < FRAGILE) | (dg[..., 1] < FRAGILE) | (dg[..., 2] < FRAGILE))
+        assert sturdy.mean() > 0.95
+        assert np.abs(r - ro)[sturdy].max() <= RANGE_TOL
+        assert 0.2 * r.size < n_prof < 0.95 * r.size          # the march still takes the sensors it can certify
+        assert (np.abs(np.diff(ro, axis=1)) > 2.0).sum() > 100   # occlusion jumps are what this scene is made of
 
 
 def test_profile_merge_random_fans():
