@@ -303,6 +303,9 @@ struct Ray {
     float lx0, ly0;      // origin in local grid units, in [0,1) when inside the map
     float oz;
     float dgx, dgy, dz;  // direction in grid units / metres
+    float oz_lo, dgx_lo, dgy_lo, dz_lo;   // what float32 dropped of oz and of the direction: read only by the float64
+                                          // re-solve of a grazing hit (precise_ray_hit), where 1e-6 m of sensor height
+                                          // is 2e-4 m of range
 };
 
 AUVPF_HD float ldg_f(const float *p)
@@ -494,11 +497,36 @@ AUVPF_HD float tri_height4(float z00, float z01, float z10, float z11, float u, 
     return (u >= v) ? z00 + u * (z01 - z00) + v * (z11 - z01) : z00 + u * (z11 - z10) + v * (z10 - z00);
 }
 
+// A ray that meets a facet at a grazing angle: the float32 evaluation of f at the two ends of the sub-segment
+// (~5e-6 m each: differences of heights of tens of metres, end points rounded to 1e-6 cells) is divided by the
+// closing rate, and 0.02 m/m turns that into 2.5e-4 m of range.  Such hits are re-solved on the facet's plane,
+//   o_z + t d_z = z00 + u(t) Du + v(t) Dv,  u(t) = lx0 - cxl + t dgx,  v(t) = ly0 - cyl + t dgy,
+// in float64 from the (exact) float32 ray and vertex heights.  (cxl, cyl) = the cell relative to the ray's origin cell.
+constexpr float kRayGraze = 0.25f;       // closing rate [m of height per m of range] below which the hit is re-solved
+
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+float precise_ray_hit(float z00, float z01, float z10, float z11, bool lower, float cxl, float cyl, const Ray *r, float t_lo,
+                      float t_hi)
+{
+    const double Du = lower ? (double)z01 - (double)z00 : (double)z11 - (double)z10;
+    const double Dv = lower ? (double)z11 - (double)z01 : (double)z10 - (double)z00;
+    const double num = (double)z00 + ((double)r->lx0 - (double)cxl) * Du + ((double)r->ly0 - (double)cyl) * Dv -
+                       ((double)r->oz + (double)r->oz_lo);
+    const double den = ((double)r->dz + (double)r->dz_lo) - ((double)r->dgx + (double)r->dgx_lo) * Du -
+                       ((double)r->dgy + (double)r->dgy_lo) * Dv;
+    const double t = num / den;
+    return (float)(t < (double)t_lo ? (double)t_lo : (t > (double)t_hi ? (double)t_hi : t));   // (NaN: den = 0 -> t_hi... see caller)
+}
+
 // Exact two-triangle test of one cell over the ray segment [ta, tb]; (ua,va), (ub,vb) are the
 // segment end points in cell coordinates.  Returns true and the range when f has its first
 // root in the segment (or f(ta) <= 0, spec: range = ta).
 AUVPF_HD bool exact_segment(float z00, float z01, float z10, float z11, float ua, float va, float ub, float vb,
-                            float ta, float tb, const Ray &r, float &range)
+                            float ta, float tb, const Ray &r, float &range, float cxl, float cyl)
 {
     const float fa = fmaf(ta, r.dz, r.oz) - tri_height4(z00, z01, z10, z11, ua, va);
     if (fa <= 0.f) {
@@ -525,7 +553,15 @@ AUVPF_HD bool exact_segment(float z00, float z01, float z10, float z11, float ua
         }
     } else
         hit = fb <= 0.f;
-    if (hit) range = t1 > t0 ? fmaf(t1 - t0, fast_div(f0, f0 - f1), t0) : t0;
+    if (hit) {
+        range = t1 > t0 ? fmaf(t1 - t0, fast_div(f0, f0 - f1), t0) : t0;
+        if (t1 > t0 && f0 - f1 < kRayGraze * (t1 - t0)) {
+            // which half the sub-segment [t0, t1] lies in: its middle decides (the diagonal, if crossed, is one of its ends)
+            const float wa = fmaf(0.5f * (t0 + t1) - ta, fast_div(ga - gb, ta - tb), ga);     // (u - v) at the middle
+            const float tp = precise_ray_hit(z00, z01, z10, z11, wa >= 0.f, cxl, cyl, &r, t0, t1);
+            if (tp == tp) range = tp;
+        }
+    }
     return hit;
 }
 
@@ -537,7 +573,7 @@ AUVPF_HD bool trav_exact(Trav &s, const DemView &m, const Ray &r, float &range)
     const float cxl = (float)(s.cx - r.ix0), cyl = (float)(s.cy - r.iy0);
     const float ua = fmaf(ta, r.dgx, r.lx0) - cxl, va = fmaf(ta, r.dgy, r.ly0) - cyl;
     const float ub = fmaf(tb, r.dgx, r.lx0) - cxl, vb = fmaf(tb, r.dgy, r.ly0) - cyl;
-    if (exact_segment(s.z00, s.z01, s.z10, s.z11, ua, va, ub, vb, ta, tb, r, range)) return true;
+    if (exact_segment(s.z00, s.z01, s.z10, s.z11, ua, va, ub, vb, ta, tb, r, range, cxl, cyl)) return true;
     if (tb >= s.te) {                // end of the ray: miss
         range = m.range_max;
         return true;
@@ -589,7 +625,7 @@ AUVPF_HD bool near_walk(Trav &s, const DemView &m, const Ray &r, float &range)
         if (!(zlow > zmax4 + kSkipMargin)) {
             const float ua = fmaf(t, r.dgx, r.lx0) - cxl, va = fmaf(t, r.dgy, r.ly0) - cyl;
             const float ub = fmaf(t_out, r.dgx, r.lx0) - cxl, vb = fmaf(t_out, r.dgy, r.ly0) - cyl;
-            if (exact_segment(z00, z01, z10, z11, ua, va, ub, vb, t, t_out, r, range)) return true;
+            if (exact_segment(z00, z01, z10, z11, ua, va, ub, vb, t, t_out, r, range, cxl, cyl)) return true;
         }
         if (t_out >= s.te) {
             range = m.range_max;
@@ -681,6 +717,10 @@ AUVPF_HD Ray make_ray(const DemView &m, const double p[3], int ix0, int iy0, flo
     r.dgx = (float)(dx * m.inv_res_d);
     r.dgy = (float)(dy * m.inv_res_d);
     r.dz = (float)dz;
+    r.oz_lo = (float)(p[2] - (double)r.oz);
+    r.dgx_lo = (float)(dx * m.inv_res_d - (double)r.dgx);
+    r.dgy_lo = (float)(dy * m.inv_res_d - (double)r.dgy);
+    r.dz_lo = (float)(dz - (double)r.dz);
     return r;
 }
 
@@ -867,12 +907,17 @@ void finish_side_by_rays(const DemView m, const FanTables T, const ProfFrameD *D
     r.lx0 = (float)(D->gox - fx);
     r.ly0 = (float)(D->goy - fy);
     r.oz = (float)D->oz;
+    r.oz_lo = (float)(D->oz - (double)r.oz);
     const double sg = (double)sgf;
     for (; j < n_side; ++j, bb += bstep) {
         const double tn = T.tan_t[bb], ct = 1.0 / T.sec_t[bb], st = tn * ct;
-        r.dgx = (float)(ct * D->cgx + sg * st * D->agx);
-        r.dgy = (float)(ct * D->cgy + sg * st * D->agy);
-        r.dz = (float)(ct * D->cz + sg * st * D->az);
+        const double dgx = ct * D->cgx + sg * st * D->agx, dgy = ct * D->cgy + sg * st * D->agy, dz = ct * D->cz + sg * st * D->az;
+        r.dgx = (float)dgx;
+        r.dgy = (float)dgy;
+        r.dz = (float)dz;
+        r.dgx_lo = (float)(dgx - (double)r.dgx);
+        r.dgy_lo = (float)(dgy - (double)r.dgy);
+        r.dz_lo = (float)(dz - (double)r.dz);
         const float t_lo = st > 0.0 ? sweep_bound(p_clear, (float)(1.0 / st)) : 0.f;
         const float range = raycast_from(m, r, t_lo, false);
         if (T.aux[bb].sec == 0.f) continue;          // no valid measurement on this beam: nothing to add (see BeamAux)
