@@ -809,19 +809,18 @@ double precise_hit(const ProfFrameD *D, float sgf, int cx, int cy, float z00, fl
 
 // Warp convergence.  With independent thread scheduling, lanes that leave a data-dependent
 // loop at different iterations are only reconverged where the compiler places a barrier; for the
-// march below it placed none inside the loop, so every lane ran its whole march ALONE (ncu:
-// 1.03 threads per instruction, 17x slower).  The march is therefore written as a warp-uniform
-// loop: every lane of the warp enters (lanes without work carry active = false), the loop runs
-// while ANY lane is still marching, and the warp is re-synchronised at the end of every step.
+// first version of the march it placed none inside the loop, so every lane ran its whole march ALONE
+// (ncu: 1.03 threads per instruction, 17x slower).  The march is therefore written as a warp-uniform
+// loop: every lane of the warp enters (lanes without work carry a finished state), the loop runs
+// while ANY lane is still marching, and the ballot at its head reconverges the warp once per pair of steps
+// (inside a step the compiler's own barriers around the beam loop do).
 // profile_particle must be called by all 32 lanes of a warp.
 #if defined(__CUDA_ARCH__)
 #define AUVPF_WARP_BALLOT(p) __ballot_sync(0xffffffffu, (p))
 #define AUVPF_WARP_SYNC() __syncwarp()
-#define AUVPF_WARP_SYNC_MASK(m) __syncwarp(m)
 #else
 #define AUVPF_WARP_BALLOT(p) ((p) ? 1u : 0u)
 #define AUVPF_WARP_SYNC() ((void)0)
-#define AUVPF_WARP_SYNC_MASK(m) ((void)(m))
 #endif
 
 // Beam tables of a planar fan as the profile merge needs them (device: shared memory).
