@@ -217,6 +217,14 @@ int auvpf_estimate(auvpf_handle *h, int32_t flags, double *mean, double *cov);
  * most max_poses.  (After a resample every particle has the same weight, so a stride IS a fair subsample; the
  * reference publishes all of them -- 48 MB per 10 Hz tick at 1 M particles.) */
 int auvpf_pose_array(auvpf_handle *h, int64_t stride, int64_t max_poses, double *poses7_out, int64_t *n_out);
+
+/* The k particles of LARGEST weight of every filter as Pose entries ("strided / top-k particle
+ * subsample" for the PoseArray of loc_loop, auv_pf.py:264-285): poses7_out [F][k][7] = x y z qx qy qz qw, optionally
+ * their log-weights [F][k] and particle indices [F][k].  Meaningful between an update and the resample that
+ * consumes its weights.  The SET is exact and deterministic -- larger log-weight first, lower index among equal
+ * weights, NaN counted as -inf (a radix select on the device, nothing but k rows comes back) -- the ORDER of the
+ * rows is not: sort by (log-weight descending, index ascending) if it matters (the Python facade does). */
+int auvpf_pose_array_topk(auvpf_handle *h, int64_t k, double *poses7_out, float *logw_out, int32_t *index_out);
 /* The same without leaving the device (a sharded filter reduces its ranks' sums with one collective and
  * reads them back once, sharded.py::combine_pose_sums): auvpf_pose_sums_dev enqueues the pass, the 16
  * float64 sums per filter land in the library buffer auvpf_pose_sums_buffer returns -- [sum d_xyz, sum roll,

@@ -70,6 +70,7 @@ SYMBOLS = [
     ("auvpf_mean_cov", C.c_int, [_vp, _vp, _vp]),
     ("auvpf_estimate", C.c_int, [_vp, _i32, _vp, _vp]),
     ("auvpf_pose_array", C.c_int, [_vp, _i64, _i64, _vp, C.POINTER(_i64)]),
+    ("auvpf_pose_array_topk", C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     ("auvpf_pose_sums_buffer", C.c_int, [_vp, C.POINTER(_vp)]),
     ("auvpf_pose_sums_dev", C.c_int, [_vp]),
     ("auvpf_resample_status", C.c_int, [_vp, _vp]),

@@ -1597,6 +1597,48 @@ int auvpf_pose_array(auvpf_handle *h, int64_t stride, int64_t max_poses, double 
     return finish_out(h, poses7_out, (const double *)od, (size_t)n * 7 * h->F);
 }
 
+int auvpf_pose_array_topk(auvpf_handle *h, int64_t k, double *poses7_out, float *logw_out, int32_t *index_out)
+{
+    if (!h || !poses7_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (k < 1 || k > h->M) return fail(AUVPF_ERR_BADARG, "k must be in [1, particle_count]");
+    if (h->M > 0xFFFFFFFFll) return fail(AUVPF_ERR_BADARG, "top-k: more than 2^32 particles per filter");
+    Guard g(h);
+    const int F = h->F;
+    // scratch: [F] states | [F][65536] histogram | [F][k] indices | [F][k] log-weights
+    const size_t off_hist = (sizeof(TopkState) * F + 255) / 256 * 256, off_idx = off_hist + sizeof(unsigned int) * 65536 * (size_t)F;
+    const size_t off_lw = off_idx + sizeof(int) * (size_t)k * F, total = off_lw + sizeof(float) * (size_t)k * F;
+    void *scratch;
+    int rc = slot_reserve(h, S_IN3, total, &scratch);
+    if (rc) return rc;
+    char *base = static_cast<char *>(scratch);
+    TopkState *st = reinterpret_cast<TopkState *>(base);
+    unsigned int *hist = reinterpret_cast<unsigned int *>(base + off_hist);
+    int *idx = reinterpret_cast<int *>(base + off_idx);
+    float *lw = reinterpret_cast<float *>(base + off_lw);
+    std::vector<TopkState> init((size_t)F);
+    for (auto &s : init) s = TopkState{0ull, (long long)k, 0u, 0u};
+    CU(cudaMemcpyAsync(st, init.data(), sizeof(TopkState) * F, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));                      // (init is a stack vector)
+    CU(cudaMemsetAsync(hist, 0, sizeof(unsigned int) * 65536 * (size_t)F, h->stream));
+    const int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 1184 / F));
+    for (int round = 0; round < 4; ++round) {
+        k_topk_hist<<<dim3(blocks, F), kThreads, 0, h->stream>>>(h->logw, h->M, st, round, hist);
+        k_topk_pick<<<F, 1024, 0, h->stream>>>(st, hist);
+    }
+    k_topk_emit<<<dim3(blocks, F), kThreads, 0, h->stream>>>(h->logw, h->M, st, k, idx);
+    LAUNCHED(h, AUVPF_K_OTHER, 9);
+    double *od;
+    if ((rc = stage_out(h, S_OUT0, poses7_out, (size_t)k * 7 * F, &od))) return rc;
+    k_pose_array_idx<<<grid1(k, kThreads, F), kThreads, 0, h->stream>>>(h->st[h->cur], h->logw, h->M, idx, k, od, lw);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    if ((rc = finish_out(h, poses7_out, (const double *)od, (size_t)k * 7 * F))) return rc;
+    if (logw_out) CU(cudaMemcpyAsync(logw_out, lw, sizeof(float) * (size_t)k * F, cudaMemcpyDeviceToHost, h->stream));
+    if (index_out) CU(cudaMemcpyAsync(index_out, idx, sizeof(int) * (size_t)k * F, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+
 int auvpf_pose_sums_buffer(auvpf_handle *h, void **sums_f64)
 {
     if (!h || !sums_f64) return fail(AUVPF_ERR_BADARG, "null argument");

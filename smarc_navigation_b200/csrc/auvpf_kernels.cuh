@@ -1250,6 +1250,114 @@ k_pose_array(StateView s, int64_t M, int64_t stride, int64_t n, double *__restri
     o[6] = cr * cp * cy + sr * sp * sy;
 }
 
+// ---- the k particles of largest weight ("strided / top-k particle subsample") ----------------------
+// Radix select on a 64-bit key that is unique per particle: (order-preserving code of the log-weight) << 32 |
+// (0xFFFFFFFF - index), so "larger key" = larger weight, lower index among equals; a NaN log-weight counts as
+// -inf.  Four rounds of one 16-bit digit each: histogram of the digit among the keys that match the digits
+// fixed so far (k_topk_hist), then one block picks the digit that holds the k-th largest (k_topk_pick).  What
+// is left in `prefix` after the fourth round IS the k-th largest key; k_topk_emit collects the k keys >= it.
+struct TopkState {
+    unsigned long long prefix;       // the digits fixed so far (right-aligned)
+    long long k_rem;                 // how many of the keys that match the prefix are still wanted
+    unsigned int count;              // k_topk_emit: slots handed out
+    unsigned int pad;
+};
+
+__device__ __forceinline__ unsigned long long topk_key(float lw, int64_t i)
+{
+    const float v = lw == lw ? lw : -INFINITY;
+    const unsigned int code = (unsigned int)float_to_ordered(v) ^ 0x80000000u;      // signed order -> unsigned order
+    return ((unsigned long long)code << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)i);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_topk_hist(const float *__restrict__ logw, int64_t M, const TopkState *__restrict__ st, int round, unsigned int *__restrict__ hist)
+{
+    const int f = blockIdx.y;
+    const unsigned long long prefix = st[f].prefix;
+    const int shift = 48 - 16 * round;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        const unsigned long long key = topk_key(logw[(int64_t)f * M + i], i);
+        if (round == 0 || (key >> (shift + 16)) == prefix) atomicAdd(hist + (size_t)f * 65536 + ((key >> shift) & 0xFFFFull), 1u);
+    }
+}
+
+// one block of 1024 threads per filter: the digit d with  #(digits > d) < k_rem <= #(digits >= d)
+__global__ void __launch_bounds__(1024) k_topk_pick(TopkState *st, unsigned int *hist)
+{
+    __shared__ unsigned long long s_sum[1024];
+    __shared__ int s_digit;
+    __shared__ unsigned long long s_above;
+    const int f = blockIdx.x, t = threadIdx.x;
+    unsigned int *h = hist + (size_t)f * 65536;
+    const long long k_rem = st[f].k_rem;
+    // thread t owns the 64 digits [65536 - 64 (t + 1), 65536 - 64 t): thread 0 the largest
+    unsigned long long mine = 0;
+    const int base = 65536 - 64 * (t + 1);
+    for (int j = 0; j < 64; ++j) mine += h[base + j];
+    s_sum[t] = mine;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {                  // inclusive scan over the threads (largest digits first)
+        const unsigned long long v = t >= o ? s_sum[t - o] : 0;
+        __syncthreads();
+        s_sum[t] += v;
+        __syncthreads();
+    }
+    const unsigned long long incl = s_sum[t], excl = incl - mine;
+    if ((long long)excl < k_rem && k_rem <= (long long)incl) {   // exactly one thread
+        unsigned long long above = excl;
+        int d = base + 63;
+        for (; d >= base; --d) {
+            if ((long long)(above + h[d]) >= k_rem) break;
+            above += h[d];
+        }
+        s_digit = d;
+        s_above = above;
+    }
+    __syncthreads();
+    for (int j = t; j < 65536; j += 1024) h[j] = 0;       // ready for the next round
+    if (t == 0) {
+        st[f].prefix = (st[f].prefix << 16) | (unsigned long long)s_digit;
+        st[f].k_rem = k_rem - (long long)s_above;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_topk_emit(const float *__restrict__ logw, int64_t M, TopkState *st, int64_t k, int *__restrict__ idx_out)
+{
+    const int f = blockIdx.y;
+    const unsigned long long kth = st[f].prefix;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads)
+        if (topk_key(logw[(int64_t)f * M + i], i) >= kth) {
+            const unsigned int slot = atomicAdd(&st[f].count, 1u);
+            if ((int64_t)slot < k) idx_out[(int64_t)f * k + slot] = (int)i;
+        }
+}
+
+// Pose entries [x y z qx qy qz qw] and log-weights of listed particles
+__global__ void __launch_bounds__(kThreads)
+k_pose_array_idx(StateView s, const float *__restrict__ logw, int64_t M, const int *__restrict__ idx, int64_t n,
+                 double *__restrict__ out, float *__restrict__ lw_out)
+{
+    const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (k >= n) return;
+    const int f = blockIdx.y;
+    const int64_t row = (int64_t)f * M + idx[(int64_t)f * n + k];
+    double sr, cr, sp, cp, sy, cy;
+    sincos(0.5 * (double)s.roll[row], &sr, &cr);
+    sincos(0.5 * (double)s.pitch[row], &sp, &cp);
+    sincos(0.5 * (double)s.yaw[row], &sy, &cy);
+    double *o = out + ((int64_t)f * n + k) * 7;
+    o[0] = s.x[row];
+    o[1] = s.y[row];
+    o[2] = (double)s.z[row];
+    o[3] = sr * cp * cy - cr * sp * sy;
+    o[4] = cr * sp * cy + sr * cp * sy;
+    o[5] = cr * cp * sy - sr * sp * cy;
+    o[6] = cr * cp * cy + sr * sp * sy;
+    lw_out[(int64_t)f * n + k] = logw[row];
+}
+
 // pack / unpack between the ABI's (n,6) float64 rows and the SoA state
 __global__ void __launch_bounds__(kThreads) k_set_poses(const double *poses, int64_t n, StateView s)
 {

@@ -417,6 +417,22 @@ class ParticleFilter(object):
             _lib.check(self._lib.auvpf_pose_array(self._h, int(stride), n_max, _ptr(out), C.byref(n)))
         return out.reshape(-1)[: self.n_filters * n.value * 7].reshape(self.n_filters, n.value, 7)
 
+    def pose_array_topk(self, k=2000):
+        """The ``k`` particles of largest weight per filter (between an update and its resample), selected on the
+        device: ``(poses (F, k, 7) [x y z qx qy qz qw], log_weights (F, k), indices (F, k))``, rows ordered by
+        weight descending, index ascending among equal weights."""
+        k = min(int(k), self.pc)
+        poses = np.empty((self.n_filters, k, 7), np.float64)
+        lw = np.empty((self.n_filters, k), np.float32)
+        idx = np.empty((self.n_filters, k), np.int32)
+        with self._lock:
+            _lib.check(self._lib.auvpf_pose_array_topk(self._h, k, _ptr(poses), _ptr(lw), _ptr(idx)))
+        for f in range(self.n_filters):
+            key = np.where(np.isnan(lw[f]), -np.inf, lw[f])
+            order = np.lexsort((idx[f], -key))
+            poses[f], lw[f], idx[f] = poses[f][order], lw[f][order], idx[f][order]
+        return poses, lw, idx
+
     def neff(self):
         out = np.empty(self.n_filters, np.float64)
         with self._lock:

@@ -876,6 +876,41 @@ def test_estimate_options_and_pose_array():
     pf.close()
 
 
+@pytest.mark.parametrize("M,F,k", [(20000, 2, 500), (1 << 20, 1, 2000), (70000, 3, 70000), (4097, 1, 1)])
+def test_pose_array_topk_is_the_exact_selection(M, F, k):
+    """SURVEY 8f-1, the top-k form of the PoseArray subsample: the k particles of largest weight per filter, chosen
+    on the device, against numpy's stable ordering (weight descending, index ascending among equals, NaN as -inf)
+    -- with heavy ties, -inf, NaN and +0 / -0 in the weights."""
+    rng = np.random.default_rng(M + k)
+    poses = np.column_stack([rng.normal(100, 30, F * M), rng.normal(-50, 30, F * M), rng.normal(-5, 1, F * M),
+                             rng.normal(0, 0.05, F * M), rng.normal(0, 0.05, F * M), rng.uniform(-3.1, 3.1, F * M)])
+    poses[:, 2:6] = poses[:, 2:6].astype(np.float32)
+    logw = np.round(rng.normal(0, 3.0, F * M), 1).astype(np.float32) - 100       # one decimal: thousands of exact ties
+    logw[rng.choice(F * M, F * M // 50, replace=False)] = -np.inf
+    logw[rng.choice(F * M, max(1, F * M // 200), replace=False)] = np.nan
+    logw[0:4] = [0.0, -0.0, 0.0, -0.0]                                          # the largest, equal under IEEE compare? (no: see below)
+    pf = _pf(particle_count=M, n_filters=F)
+    pf.set_poses(poses)
+    pf.set_log_weights(logw)
+    got_p, got_w, got_i = pf.pose_array_topk(k)
+    assert got_p.shape == (F, k, 7) and got_w.shape == (F, k) and got_i.shape == (F, k)
+    for f in range(F):
+        lw = logw[f * M:(f + 1) * M]
+        key = np.where(np.isnan(lw), -np.inf, lw).astype(np.float64)
+        # the device orders the weights by their bit pattern: +0 above -0 (a total order; IEEE compares them equal)
+        key = np.where((lw == 0) & np.signbit(lw), -1e-300, key)
+        want = np.lexsort((np.arange(M), -key))[:k]
+        np.testing.assert_array_equal(np.sort(got_i[f]), np.sort(want))                  # the exact set
+        kk = np.where(np.isnan(got_w[f]), -np.inf, got_w[f])
+        assert np.all(kk[:-1] >= kk[1:])                                                 # the facade's order
+        src = poses[f * M:(f + 1) * M][got_i[f]]
+        np.testing.assert_allclose(got_p[f, :, 0:3], src[:, 0:3], atol=1e-9)
+        np.testing.assert_array_equal(got_w[f][~np.isnan(got_w[f])], lw[got_i[f]][~np.isnan(got_w[f])])
+        q = np.array([tf_stub.quaternion_from_euler(r, p_, y) for r, p_, y in src[:40, 3:6]])
+        np.testing.assert_allclose(got_p[f, :40, 3:7], q, atol=1e-12)
+    pf.close()
+
+
 # --------------------------------------------------------------------------- full-size properties
 def test_c3_full_size_properties():
     """At BASELINE C3 size (1M x 512 on the 4000^2 DEM) the oracle is too slow for a full
