@@ -111,7 +111,8 @@ int auvpf_destroy(auvpf_handle *h);
 int auvpf_sync(auvpf_handle *h);
 /* the handle's cudaStream_t, for torch.cuda.ExternalStream interop */
 void *auvpf_stream(auvpf_handle *h);
-int64_t auvpf_particle_count(auvpf_handle *h); /* F*M rows held by this handle */
+int64_t auvpf_particle_count(auvpf_handle *h); /* F*M rows held by this handle (changes with auvpf_set_next_particle_count) */
+int64_t auvpf_particle_capacity(auvpf_handle *h); /* ... and what it was created with: the upper bound of the count */
 
 /* -- map and sensor model (no reference counterpart: SURVEY.md section 0) --- */
 /* H x W float32 vertex heights, row i at y0 + i*res, column j at x0 + j*res;
@@ -225,6 +226,22 @@ int auvpf_pose_array(auvpf_handle *h, int64_t stride, int64_t max_poses, double 
  * weights, NaN counted as -inf (a radix select on the device, nothing but k rows comes back) -- the ORDER of the
  * rows is not: sort by (log-weight descending, index ascending) if it matters (the Python facade does). */
 int auvpf_pose_array_topk(auvpf_handle *h, int64_t k, double *poses7_out, float *logw_out, int32_t *index_out);
+
+/* ---- KLD-style adaptation of the particle count (Fox, "Adapting the sample size in particle
+ * filters through KLD-sampling", IJRR 2003).  Not in the reference, whose particle_count is a launch parameter
+ * (auv_pf.py:27).
+ * auvpf_kld_bins: how many bins of bin_xy x bin_xy [m] x bin_yaw [rad] the current cloud of every filter occupies
+ *   (bin index = floor(coordinate * (1 / bin)), yaw shifted by +pi; a hash set on the device; bins_out [F]).
+ * auvpf_kld_target: the number of particles that keeps the KL divergence between the sample-based posterior and
+ *   the true one below eps with the confidence whose standard-normal quantile is z_quantile, clamped to
+ *   [n_min, n_max] (a pure function; same float64 operations as oracle/pf_oracle.py kld_target).
+ * auvpf_set_next_particle_count: the NEXT systematic, non-in-place resample of this handle draws n particles
+ *   -- positions (u + i) / n over the CDF of the current ones -- and the handle continues with n; 1 <= n <= the
+ *   count it was created with, one filter per handle, not particle-sharded.  A resample that is held back by the
+ *   N_eff gate, or fails on degenerate weights, leaves the count alone (the request stays pending).  0 cancels. */
+int auvpf_kld_bins(auvpf_handle *h, double bin_xy, double bin_yaw, int64_t *bins_out);
+int64_t auvpf_kld_target(int64_t bins, double eps, double z_quantile, int64_t n_min, int64_t n_max);
+int auvpf_set_next_particle_count(auvpf_handle *h, int64_t n);
 /* The same without leaving the device (a sharded filter reduces its ranks' sums with one collective and
  * reads them back once, sharded.py::combine_pose_sums): auvpf_pose_sums_dev enqueues the pass, the 16
  * float64 sums per filter land in the library buffer auvpf_pose_sums_buffer returns -- [sum d_xyz, sum roll,

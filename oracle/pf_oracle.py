@@ -333,6 +333,41 @@ def systematic_resample(weights, u):
     return idx.astype(np.int32)
 
 
+def systematic_resample_to(weights, u, n_out):
+    """``systematic_resample`` (resampling.py:135-168) generalised to ``n_out`` positions ``(u + i) / n_out`` over the
+    same cumulative sum: the resample that changes the particle count (KLD adaptation).  ``n_out =
+    len(weights)`` is the reference function."""
+    w = np.asarray(weights, np.float64)
+    positions = (u + np.arange(int(n_out))) / float(n_out)
+    idx = np.searchsorted(np.cumsum(w), positions, side='right')
+    if idx[-1] >= len(w):
+        raise IndexError("positions[-1] >= cumsum[-1]")
+    return idx.astype(np.int32)
+
+
+def kld_bins(poses, bin_xy, bin_yaw):
+    """Occupied bins of a cloud (n, 6) (KLD-sampling, Fox 2003): bin index = floor(coordinate * (1 / bin)) in x and y,
+    floor((yaw + pi) * (1 / bin_yaw)) in yaw, yaw as the float32 the state holds."""
+    p = np.asarray(poses, np.float64)
+    ix = np.floor(p[:, 0] * (1.0 / bin_xy)).astype(np.int64)
+    iy = np.floor(p[:, 1] * (1.0 / bin_xy)).astype(np.int64)
+    iw = np.floor((p[:, 5].astype(np.float32).astype(np.float64) + np.pi) * (1.0 / bin_yaw)).astype(np.int64)
+    return len(np.unique(np.stack([ix, iy, iw], axis=1), axis=0))
+
+
+def kld_target(bins, eps, z_quantile, n_min, n_max):
+    """n >= (k - 1) / (2 eps) (1 - 2 / (9 (k - 1)) + sqrt(2 / (9 (k - 1))) z)^3, clamped (Fox 2003, eq. 13); the same
+    float64 operations as auvpf_kld_target."""
+    n = n_min
+    if bins > 1 and eps > 0.0:
+        k1 = float(bins - 1)
+        a = 2.0 / (9.0 * k1)
+        t = 1.0 - a + math.sqrt(a) * z_quantile
+        v = k1 / (2.0 * eps) * (t * t * t)
+        n = n_max if v >= 9.0e18 else int(math.ceil(v))
+    return max(n_min, min(n_max, n))
+
+
 def stratified_resample(weights, uniforms):
     """``stratified_resample`` (resampling.py:80-114) with ``random(N)`` = uniforms."""
     w = np.asarray(weights, np.float64)

@@ -48,6 +48,10 @@ SYMBOLS = [
     ("auvpf_sync", C.c_int, [_vp]),
     ("auvpf_stream", _vp, [_vp]),
     ("auvpf_particle_count", _i64, [_vp]),
+    ("auvpf_particle_capacity", _i64, [_vp]),
+    ("auvpf_kld_bins", C.c_int, [_vp, C.c_double, C.c_double, _vp]),
+    ("auvpf_kld_target", _i64, [_i64, C.c_double, C.c_double, _i64, _i64]),
+    ("auvpf_set_next_particle_count", C.c_int, [_vp, _i64]),
     ("auvpf_set_dem", C.c_int, [_vp, _vp, _i32, _i32, _dbl, _dbl, _dbl]),
     ("auvpf_rasterise_mesh", C.c_int, [_vp, _vp, _i64, _vp, _i64, _i32, _i32, _dbl, _dbl, _dbl, C.c_float, _vp]),
     ("auvpf_set_beams", C.c_int, [_vp, _vp, _i32]),

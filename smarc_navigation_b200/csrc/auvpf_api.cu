@@ -67,6 +67,8 @@ struct auvpf_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     int64_t M = 0, N = 0;   // per filter, total rows
+    int64_t cap_M = 0, cap_N = 0;      // what the buffers were sized for at creation (M can shrink and grow below it)
+    int64_t next_count = 0;            // auvpf_set_next_particle_count: the next systematic resample draws this many
     int F = 1;
     int64_t global_offset = 0, global_count = 0;
 
@@ -534,6 +536,7 @@ SelArgs select_args(auvpf_handle *h, const WeightSrc &src)
     SelArgs a{};
     a.M = h->M;
     a.n_global = h->global_count;
+    a.n_src_total = h->global_count;
     a.out_lo = h->global_offset;
     a.n_out = h->M;
     a.tiles = h->tiles_per_filter;
@@ -572,11 +575,11 @@ int check_degenerate(auvpf_handle *h)
 int ensure_inplace_buffers(auvpf_handle *h)
 {
     if (h->first) return AUVPF_OK;
-    CU(cudaMalloc(&h->first, sizeof(int) * h->N));
-    CU(cudaMalloc(&h->scan2, sizeof(unsigned long long) * h->N));
+    CU(cudaMalloc(&h->first, sizeof(int) * h->cap_N));
+    CU(cudaMalloc(&h->scan2, sizeof(unsigned long long) * h->cap_N));
     CU(cudaMalloc(&h->totals2, sizeof(unsigned long long) * 2 * h->F));
-    CU(cudaMalloc(&h->lost, sizeof(int32_t) * h->N));
-    CU(cudaMalloc(&h->dupes, sizeof(int32_t) * h->N));
+    CU(cudaMalloc(&h->lost, sizeof(int32_t) * h->cap_N));
+    CU(cudaMalloc(&h->dupes, sizeof(int32_t) * h->cap_N));
     return AUVPF_OK;
 }
 
@@ -635,7 +638,7 @@ int host_neff_gate(auvpf_handle *h, bool *skip)
 int emit_identity_ancestors(auvpf_handle *h, int32_t *ancestors_out)
 {
     if (!ancestors_out) return AUVPF_OK;
-    if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
+    if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->cap_N));
     int32_t *dev = is_device_ptr(ancestors_out) ? ancestors_out : h->anc;
     k_identity_indices<<<grid1(h->M, kThreads, h->F), kThreads, 0, h->stream>>>(dev, h->M);
     CU(cudaGetLastError());
@@ -675,8 +678,8 @@ int do_resample_residual(auvpf_handle *h, const WeightSrc &src, int32_t flags, c
         if ((rc = run_exact_q(h, h->cdf, nullptr, h->A, nullptr))) return rc;
     }
     if ((rc = ensure_inplace_buffers(h))) return rc;
-    if (!h->scan3) CU(cudaMalloc(&h->scan3, sizeof(unsigned long long) * h->N));
-    if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
+    if (!h->scan3) CU(cudaMalloc(&h->scan3, sizeof(unsigned long long) * h->cap_N));
+    if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->cap_N));
     const double *ud = nullptr;
     if (u && (rc = stage_in(h, S_IN3, u, (size_t)h->N, &ud))) return rc;
     const float *rn = nullptr;
@@ -733,6 +736,53 @@ int do_resample_residual(auvpf_handle *h, const WeightSrc &src, int32_t flags, c
     return AUVPF_OK;
 }
 
+// everything that is derived from the particle count (one filter per handle, not sharded: auvpf_set_next_particle_count)
+void set_count(auvpf_handle *h, int64_t n)
+{
+    h->M = h->N = h->global_count = n;
+    h->tiles_per_filter = (int)((n + kScanTile - 1) / kScanTile);
+    h->have_norm = false;
+    h->wmax_valid = false;
+}
+
+// The systematic resample that CHANGES the particle count (KLD adaptation): n_new positions (u + i) / n_new
+// over the CDF of the M current particles.  Decided on the host, because a held-back or degenerate resample must leave
+// the count alone: one read-back, acceptable for a call that is made when the cloud has changed size, not every cycle.
+int do_resample_to_count(auvpf_handle *h, const WeightSrc &src, int64_t n_new, int32_t *ancestors_out, const double *rough_var)
+{
+    int rc;
+    if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
+    if ((rc = check_degenerate(h))) return rc;                   // (error: state, weights and count untouched)
+    bool skip;
+    if ((rc = host_neff_gate(h, &skip))) return rc;
+    if (skip) {                                                  // held back: the draws count as consumed, the count stays
+        if (rough_var) h->step_rough++;
+        return emit_identity_ancestors(h, ancestors_out);
+    }
+    if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->cap_N));
+    int32_t *anc_dev = ancestors_out ? ((is_device_ptr(ancestors_out)) ? ancestors_out : h->anc) : nullptr;
+    SelArgs sa = select_args(h, src);
+    sa.n_global = n_new;                    // positions
+    sa.n_out = n_new;                       // ... all of them emitted here
+    sa.gate_thresh = 0.0;                   // (decided above)
+    sa.rough = make_noise(h, rough_var, nullptr, rough_var ? 1 : 0, h->step_rough, kStreamRoughen);
+    sa.anc32 = anc_dev;
+    sa.dst = h->st[1 - h->cur];
+    {
+        Prof pr(h, AUVPF_K_SELECT_GATHER);
+        CU(launch_select<kSelLocal>(h, grid1(n_new, kSelTile, 1), sa));
+        LAUNCHED(h, AUVPF_K_SELECT_GATHER, 1);
+        CU(cudaGetLastError());
+    }
+    h->cur = 1 - h->cur;
+    if (rough_var) h->step_rough++;
+    if (ancestors_out && anc_dev != ancestors_out && (rc = finish_out(h, ancestors_out, (const int32_t *)anc_dev, (size_t)n_new))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    set_count(h, n_new);
+    h->next_count = 0;
+    return AUVPF_OK;
+}
+
 int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t flags, const double *u,
                 int32_t *ancestors_out, const double *rough_var, const float *rough_noise)
 {
@@ -756,12 +806,18 @@ int do_resample(auvpf_handle *h, const WeightSrc &src, int32_t mode, int32_t fla
     h->step_resample++;
 
     const bool inplace = (flags & AUVPF_RS_INPLACE_REF) != 0;
+    if (h->next_count > 0 && h->next_count != h->M) {
+        if (inplace || rough_noise)
+            return fail(AUVPF_ERR_BADARG, "a resample that changes the particle count is systematic, gathers into the other buffer and draws its own roughening noise");
+        return do_resample_to_count(h, src, h->next_count, ancestors_out, rough_var);
+    }
+    h->next_count = 0;
     const float *rn = nullptr;
     if (rough_noise && (rc = stage_in(h, S_IN1, rough_noise, (size_t)h->N * 6, &rn))) return rc;
     if ((rc = run_weights(h, src, /*use_mailbox=*/false))) return rc;
     int32_t *anc_dev = nullptr;
     if (ancestors_out || inplace) {
-        if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->N));
+        if (!h->anc) CU(cudaMalloc(&h->anc, sizeof(int32_t) * h->cap_N));
         anc_dev = h->anc;
         if (ancestors_out && is_device_ptr(ancestors_out) && !inplace) anc_dev = ancestors_out;
     }
@@ -841,6 +897,8 @@ int auvpf_create(const auvpf_config *cfg, auvpf_handle **out)
     h->M = cfg->particle_count;
     h->F = F;
     h->N = h->M * F;
+    h->cap_M = h->M;
+    h->cap_N = h->N;
     h->global_offset = cfg->global_offset;
     h->global_count = cfg->global_count > 0 ? cfg->global_count : h->M;
     Guard g(h);
@@ -1165,8 +1223,8 @@ int auvpf_set_beams(auvpf_handle *h, const float *dirs_xyz, int32_t B)
     CU(cudaMalloc(&h->beam_tan, sizeof(double) * 2 * B));
     CU(cudaMemcpy(h->beam_tan, plan.tan_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->beam_tan + B, plan.sec_t.data(), sizeof(double) * B, cudaMemcpyHostToDevice));
-    if (!h->flagged) CU(cudaMalloc(&h->flagged, sizeof(int) * (size_t)h->N));
-    if (!h->flagged2) CU(cudaMalloc(&h->flagged2, sizeof(int) * (size_t)h->N));
+    if (!h->flagged) CU(cudaMalloc(&h->flagged, sizeof(int) * (size_t)h->cap_N));
+    if (!h->flagged2) CU(cudaMalloc(&h->flagged2, sizeof(int) * (size_t)h->cap_N));
     CU(cudaMalloc(&h->beam_order, sizeof(int) * plan.order.size()));
     CU(cudaMemcpy(h->beams, host.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->beam_aux, aux.data(), sizeof(float) * 3 * B, cudaMemcpyHostToDevice));
@@ -1445,7 +1503,7 @@ int auvpf_resample_weights(auvpf_handle *h, const double *weights, int32_t mode,
     int rc = stage_in(h, S_IN2, weights, (size_t)h->N, &wd);
     if (rc) return rc;
     // float64 maximum, then a_i = floor(w_i / max * 2^60) into a scratch array: the resample kernels read integers
-    if (!h->a_pre) CU(cudaMalloc(&h->a_pre, sizeof(unsigned long long) * h->N));
+    if (!h->a_pre) CU(cudaMalloc(&h->a_pre, sizeof(unsigned long long) * h->cap_N));
     {
         Prof pr(h, AUVPF_K_NORMALISE);
         int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 1184);
@@ -1638,6 +1696,69 @@ int auvpf_pose_array_topk(auvpf_handle *h, int64_t k, double *poses7_out, float 
     CU(cudaStreamSynchronize(h->stream));
     return AUVPF_OK;
 }
+
+// ---- KLD-style adaptation of the particle count ---------------------------------------------------
+int auvpf_kld_bins(auvpf_handle *h, double bin_xy, double bin_yaw, int64_t *bins_out)
+{
+    if (!h || !bins_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    if (!(bin_xy > 0.0) || !(bin_yaw > 0.0)) return fail(AUVPF_ERR_BADARG, "bin sizes must be positive");
+    if (h->F > 256) return fail(AUVPF_ERR_BADARG, "kld_bins: at most 256 filters per handle");
+    Guard g(h);
+    size_t slots = 1024;
+    while (slots < 2 * (size_t)h->N) slots <<= 1;
+    const size_t off_tab = 256 * ((sizeof(unsigned long long) * (h->F + 1) + 255) / 256);
+    void *scratch;
+    int rc = slot_reserve(h, S_IN3, off_tab + sizeof(unsigned long long) * slots, &scratch);
+    if (rc) return rc;
+    unsigned long long *out = static_cast<unsigned long long *>(scratch);
+    unsigned long long *table = reinterpret_cast<unsigned long long *>(static_cast<char *>(scratch) + off_tab);
+    CU(cudaMemsetAsync(out, 0, sizeof(unsigned long long) * (h->F + 1), h->stream));
+    CU(cudaMemsetAsync(table, 0xFF, sizeof(unsigned long long) * slots, h->stream));
+    const int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, std::max(1, 1184 / h->F));
+    k_kld_bins<<<dim3(blocks, h->F), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, 1.0 / bin_xy, 1.0 / bin_yaw, table, slots - 1, out, h->F);
+    LAUNCHED(h, AUVPF_K_OTHER, 1);
+    CU(cudaGetLastError());
+    std::vector<unsigned long long> host((size_t)h->F + 1);
+    CU(cudaMemcpyAsync(host.data(), out, sizeof(unsigned long long) * (h->F + 1), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (host[h->F]) return fail(AUVPF_ERR_BADARG, "kld_bins: a particle lies outside +-2^21 bins in x or y, or +-2^11 in yaw (or is NaN)");
+    for (int f = 0; f < h->F; ++f) bins_out[f] = (int64_t)host[f];
+    return AUVPF_OK;
+}
+
+// Fox's bound: with probability 1 - delta the KL divergence between the sample-based estimate and the true posterior
+// stays below eps when n >= (k - 1) / (2 eps) (1 - 2 / (9 (k - 1)) + sqrt(2 / (9 (k - 1))) z)^3, z the 1 - delta
+// quantile of the standard normal, k the occupied bins.  Plain float64, no library power: the oracle gets the same bits.
+int64_t auvpf_kld_target(int64_t bins, double eps, double z_quantile, int64_t n_min, int64_t n_max)
+{
+    int64_t n = n_min;
+    if (bins > 1 && eps > 0.0) {
+        const double k1 = (double)(bins - 1), a = 2.0 / (9.0 * k1);
+        const double t = 1.0 - a + sqrt(a) * z_quantile;
+        const double v = k1 / (2.0 * eps) * (t * t * t);
+        n = v >= 9.0e18 ? n_max : (int64_t)ceil(v);
+    }
+    if (n < n_min) n = n_min;
+    if (n > n_max) n = n_max;
+    return n;
+}
+
+int auvpf_set_next_particle_count(auvpf_handle *h, int64_t n)
+{
+    if (!h) return fail(AUVPF_ERR_BADARG, "null handle");
+    Guard g(h);
+    if (n == 0) {
+        h->next_count = 0;
+        return AUVPF_OK;
+    }
+    if (h->F != 1 || h->global_count != h->M || h->n_peers > 1)
+        return fail(AUVPF_ERR_BADARG, "the particle count can change for one filter per handle on one GPU only");
+    if (n < 1 || n > h->cap_M) return fail(AUVPF_ERR_BADARG, "particle count %lld outside [1, %lld] (the count the handle was created with)", (long long)n, (long long)h->cap_M);
+    h->next_count = n;
+    return AUVPF_OK;
+}
+
+int64_t auvpf_particle_capacity(auvpf_handle *h) { return h ? h->cap_N : 0; }
 
 int auvpf_pose_sums_buffer(auvpf_handle *h, void **sums_f64)
 {

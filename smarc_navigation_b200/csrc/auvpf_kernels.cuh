@@ -1358,6 +1358,39 @@ k_pose_array_idx(StateView s, const float *__restrict__ logw, int64_t M, const i
     lw_out[(int64_t)f * n + k] = logw[row];
 }
 
+// ---- KLD-sampling (Fox 2003): how many bins of size (bin_xy, bin_xy, bin_yaw) the cloud occupies ------
+// One open-addressing hash set per call; a key is the bin triple and the filter packed into 64 bits (22 + 22 + 12 + 8).
+// The COUNT of distinct keys does not depend on the insertion order.  out[0..F) += newly occupied bins; out[F] != 0
+// when a bin index did not fit its field.
+__global__ void __launch_bounds__(kThreads)
+k_kld_bins(StateView s, int64_t M, double inv_bin_xy, double inv_bin_yaw, unsigned long long *table, unsigned long long mask,
+           unsigned long long *out, int F)
+{
+    const int f = blockIdx.y;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < M; i += (int64_t)gridDim.x * kThreads) {
+        const int64_t row = (int64_t)f * M + i;
+        const double bx = floor(s.x[row] * inv_bin_xy), by = floor(s.y[row] * inv_bin_xy);
+        const double bw = floor(((double)s.yaw[row] + kPi) * inv_bin_yaw);
+        if (!(fabs(bx) < 2097152.0 && fabs(by) < 2097152.0 && fabs(bw) < 2048.0)) {      // (NaN poses land here too)
+            out[F] = 1ull;
+            continue;
+        }
+        const unsigned long long key = ((unsigned long long)((long long)bx + 2097152ll) << 42) |
+                                       ((unsigned long long)((long long)by + 2097152ll) << 20) |
+                                       ((unsigned long long)((long long)bw + 2048ll) << 8) | (unsigned long long)f;
+        unsigned long long hsh = key * 0x9E3779B97F4A7C15ull;
+        hsh ^= hsh >> 29;
+        for (unsigned long long slot = hsh & mask;; slot = (slot + 1) & mask) {
+            const unsigned long long prev = atomicCAS(table + slot, ~0ull, key);
+            if (prev == ~0ull) {
+                atomicAdd(out + f, 1ull);
+                break;
+            }
+            if (prev == key) break;
+        }
+    }
+}
+
 // pack / unpack between the ABI's (n,6) float64 rows and the SoA state
 __global__ void __launch_bounds__(kThreads) k_set_poses(const double *poses, int64_t n, StateView s)
 {

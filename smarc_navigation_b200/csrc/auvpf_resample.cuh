@@ -379,6 +379,7 @@ struct SelShard {                       // what the select kernel reads of one s
 struct SelArgs {
     int64_t M;                          // sources per shard and filter
     int64_t n_global;                   // N of positions = (u + i) / N
+    int64_t n_src_total;                // sources of the whole filter (= n_global unless the resample changes the particle count)
     int64_t out_lo, n_out;              // this launch emits the outputs [out_lo, out_lo + n_out) of every filter
     int tiles;                          // tiles per shard and filter
     int G, rank, kind;
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(kSelThreads, AUVPF_SEL_MINB) k_select(SelArgs 
     // warp scan on top of the chunk's base (tile prefix + the tile's chunk sums below it) -- in float64 for the
     // closed-form run ends, in exact integers only for the few sources whose estimate lands within 1e-5 of an
     // integer.  No barrier inside the walk: the warps do not depend on each other.
-    const int64_t J_last = a.n_global - 1;             // the filter's last particle (see the note at its use)
+    const int64_t J_last = a.n_src_total - 1;          // the filter's last particle (see the note at its use)
     for (int T = T_lo; T <= T_hi; ++T) {
         const int g = kMode == kSelLocal ? 0 : T / tiles, t = T - g * tiles;
         const SelShard &S = shard(g);

@@ -316,15 +316,22 @@ class ParticleFilter(object):
         return out
 
     # -- resample: auv_pf.resample (auv_pf.py:169-192) ---------------------------------------
-    def resample(self, weights=None, u=None, noise=None, return_ancestors=False, roughen=True, wait=True):
+    def resample(self, weights=None, u=None, noise=None, return_ancestors=False, roughen=True, wait=True, new_count=None):
         """Normalise (:172), draw ancestors, reassign poses (:183-189,195-198) and add
         ``resampling_noise_covariance`` noise to every particle (:191-192).
         ``weights=None`` uses the device-resident log-weights of the last update;
         a float64 array reproduces the reference call ``resample(weights)``.
         ``u``: the ``random()`` of resampling.py:157 (one per filter) for the systematic
         resampler, the ``random(N - k)`` array of :74 (``(F, M)``; the first ``M - k`` of a row
-        are consumed) for the residual one; default Philox."""
-        anc = np.empty(self.n_rows, np.int32) if return_ancestors else None
+        are consumed) for the residual one; default Philox.
+        ``new_count`` (one filter, systematic, not in place): draw that many particles instead of ``particle_count``
+        -- positions ``(u + i) / new_count`` over the CDF of the current ones -- and continue with them (KLD
+        adaptation, ``kld_particle_count``); between 1 and the count the filter was created with.  A resample held
+        back by the N_eff gate leaves the count alone."""
+        if new_count is not None:
+            with self._lock:
+                _lib.check(self._lib.auvpf_set_next_particle_count(self._h, int(new_count)))
+        anc = np.empty(max(self.n_rows, int(new_count or 0)), np.int32) if return_ancestors else None
         if u is None:
             uu = None
         elif self.resampler == _lib.RESIDUAL:
@@ -348,7 +355,33 @@ class ParticleFilter(object):
                 rc = self._lib.auvpf_resample_weights(self._h, _ptr(w), self.resampler, flags, _ptr(uu),
                                                       _ptr(anc), rv, _ptr(nz))
             _lib.check(rc)
-        return anc
+            if new_count is not None:
+                self.n_rows = int(self._lib.auvpf_particle_count(self._h))
+                self.pc = self.n_rows // self.n_filters
+                self._lib.auvpf_set_next_particle_count(self._h, 0)        # (a held-back resample: no stale request left behind)
+        return anc if anc is None else anc[:self.n_rows]
+
+    # -- KLD-style adaptation of the particle count (not in the reference) ------------------------
+    @property
+    def capacity(self):
+        """The particle count the filter was created with: the upper bound of ``resample(new_count=...)``."""
+        return int(self._lib.auvpf_particle_capacity(self._h)) // self.n_filters
+
+    def kld_bins(self, bin_xy=0.5, bin_yaw=np.radians(5.0)):
+        """Occupied bins of size ``bin_xy`` x ``bin_xy`` [m] x ``bin_yaw`` [rad] per filter (counted on the device)."""
+        out = np.zeros(self.n_filters, np.int64)
+        with self._lock:
+            _lib.check(self._lib.auvpf_kld_bins(self._h, float(bin_xy), float(bin_yaw), _ptr(out)))
+        return out
+
+    def kld_particle_count(self, bin_xy=0.5, bin_yaw=np.radians(5.0), eps=0.05, z_quantile=2.3263478740408408,
+                           n_min=1000, n_max=None):
+        """Fox's KLD bound for the current cloud: the particle count that keeps the KL divergence of the sample-based
+        posterior below ``eps`` with the confidence of ``z_quantile`` (default 99 %), clamped to ``[n_min, n_max]``
+        (default: the capacity).  Feed it to ``resample(new_count=...)``."""
+        n_max = self.capacity if n_max is None else int(n_max)
+        k = self.kld_bins(bin_xy, bin_yaw)
+        return np.array([self._lib.auvpf_kld_target(int(b), float(eps), float(z_quantile), int(n_min), n_max) for b in k], np.int64)
 
     def resample_status(self):
         """Per-filter degenerate-weights flag of the last resample (synchronises)."""

@@ -911,6 +911,94 @@ def test_pose_array_topk_is_the_exact_selection(M, F, k):
     pf.close()
 
 
+def test_kld_bins_and_a_resample_that_changes_the_particle_count():
+    """SURVEY 8f-4, KLD-style adaptation: the occupied-bin count of the cloud (device hash set) against numpy's unique;
+    Fox's bound from the library against the oracle's; and the resample that applies it -- n_new positions over the CDF
+    of the current particles -- bit-exact against the oracle, down AND up again, with the cycle continuing at the new
+    count.  A held-back or degenerate resample leaves the count alone; batched filters refuse."""
+    M = 200000
+    rng = np.random.default_rng(31)
+    poses = np.column_stack([rng.normal(420.0, 1.5, M), rng.normal(-77.0, 0.8, M), np.full(M, -5.0), np.zeros(M), np.zeros(M),
+                             rng.normal(3.1, 0.1, M)])                  # yaw straddles +pi: bins on both sides of the shift
+    poses[:, 2:6] = poses[:, 2:6].astype(np.float32)
+    pf = _pf(particle_count=M, resampling_noise_covariance=[0.0] * 6, measurement_std=1.0, range_min=world.RANGE_MIN,
+             range_max=world.RANGE_MAX)
+    pf.set_poses(poses)
+    for bxy, byaw in ((0.5, np.radians(5.0)), (0.05, np.radians(1.0)), (7.0, 1.0)):
+        k = int(pf.kld_bins(bxy, byaw)[0])
+        assert k == o.kld_bins(poses, bxy, byaw)
+        for eps, z in ((0.05, 2.3263478740408408), (0.01, 1.6448536269514722)):
+            assert int(pf._lib.auvpf_kld_target(k, eps, z, 100, 10 ** 9)) == o.kld_target(k, eps, z, 100, 10 ** 9)
+    n1 = int(pf.kld_particle_count(0.5, np.radians(5.0), n_min=1000)[0])
+    assert 1000 <= n1 < M and pf.capacity == M
+    # ---- down to n1: ancestors, state, count
+    logw = (rng.normal(0, 3.0, M) - 200).astype(np.float32)
+    pf.set_log_weights(logw)
+    anc = pf.resample(u=0.37, return_ancestors=True, roughen=False, new_count=n1)
+    qq = o.quantise_logw(logw)[0]
+    want = o.systematic_resample_to(o.weights_from_q(qq), 0.37, n1)
+    assert pf.pc == n1 and len(anc) == n1
+    np.testing.assert_array_equal(anc, want)
+    p1 = pf.poses()
+    assert p1.shape == (n1, 6)
+    np.testing.assert_array_equal(p1, poses[want])
+    # ---- the filter goes on at n1: an MBES update on the smaller cloud ...
+    dem = _dem(500, 2.0)
+    beams = world.make_beams(64).astype(np.float32).astype(np.float64)
+    pf.set_dem(dem)
+    pf.set_beams(beams)
+    truth = np.array([[420.0, -77.0 + 500.0, -5.0, 0.0, 0.0, 0.3]])
+    shifted = p1.copy()
+    shifted[:, 1] += 500.0                                   # (the cloud was placed off this map: move it onto it)
+    pf.set_poses(shifted)
+    meas = c_oracle.update_mbes(dem, truth, np.eye(4), beams, None, 1.0, 0.5, world.RANGE_MAX, want_ranges=True)["ranges"][0].astype(np.float32)
+    pf.update_mbes(meas, return_weights=False)
+    got = pf.log_weights()
+    ref = c_oracle.update_mbes(dem, shifted[:4000], np.eye(4), beams, meas.astype(np.float64), 1.0, world.RANGE_MIN,
+                               world.RANGE_MAX)["logw"]
+    assert got.shape == (n1,)
+    lognorm = -len(beams) * np.log(np.sqrt(2 * np.pi))
+    tol = LOGW_RTOL * (np.abs(ref - lognorm) + abs(lognorm))
+    assert np.all(np.abs(got[:4000].astype(np.float64) - ref) <= tol)
+    pf.set_poses(p1)
+    # ---- ... weights, an ordinary resample, the estimate
+    logw1 = (rng.normal(0, 2.0, n1) - 50).astype(np.float32)
+    pf.set_log_weights(logw1)
+    anc1 = pf.resample(u=0.81, return_ancestors=True, roughen=False)
+    np.testing.assert_array_equal(anc1, o.systematic_resample(o.weights_from_q(o.quantise_logw(logw1)[0]), 0.81))
+    p2 = pf.poses()
+    em, ec, _ = o.estimate(p2)
+    m, c = pf.mean_cov()
+    np.testing.assert_allclose(m[0], em, atol=1e-9)
+    # ---- up again to the capacity, with the gate holding one attempt back first
+    logw2 = np.zeros(n1, np.float32)                       # uniform weights: N_eff = n1, the gate holds the resample back
+    pf.set_log_weights(logw2)
+    pf.set_neff_gate(0.5)
+    pf.resample(u=0.5, roughen=False, new_count=M)
+    assert pf.pc == n1 and pf.resample_skipped()[0]
+    np.testing.assert_array_equal(pf.poses(), p2)
+    pf.set_neff_gate(0.0)
+    logw2 = (rng.normal(0, 1.0, n1)).astype(np.float32)
+    pf.set_log_weights(logw2)
+    anc2 = pf.resample(u=0.12, return_ancestors=True, roughen=False, new_count=M)
+    assert pf.pc == M
+    want2 = o.systematic_resample_to(o.weights_from_q(o.quantise_logw(logw2)[0]), 0.12, M)
+    np.testing.assert_array_equal(anc2, want2)
+    np.testing.assert_array_equal(pf.poses(), p2[want2])
+    # ---- degenerate weights: error, nothing changes; more than the capacity: refused
+    pf.set_log_weights(np.full(M, -np.inf, np.float32))
+    with pytest.raises(Exception):
+        pf.resample(u=0.3, roughen=False, new_count=5000)
+    assert pf.pc == M
+    with pytest.raises(Exception):
+        pf.resample(u=0.3, roughen=False, new_count=M + 1)
+    pf.close()
+    pf2 = _pf(particle_count=1000, n_filters=2)
+    with pytest.raises(Exception):
+        pf2.resample(new_count=500)
+    pf2.close()
+
+
 # --------------------------------------------------------------------------- full-size properties
 def test_c3_full_size_properties():
     """At BASELINE C3 size (1M x 512 on the 4000^2 DEM) the oracle is too slow for a full

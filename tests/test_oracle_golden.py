@@ -199,3 +199,28 @@ def test_residual_quantised_golden(golden):
         if len(w) - len(head) > 200:
             pr = frac / frac.sum()
             assert abs(pr[fx[len(head):]].mean() - (pr * pr).sum()) < 5.0 * np.sqrt((pr ** 3).sum() / (len(w) - len(head)))
+
+
+def test_kld_oracle_and_library_bound():
+    """KLD adaptation: `systematic_resample_to` with n_out = N is the reference function (and the golden
+    weights' ancestors); Fox's bound from the library (a pure host function of the C ABI) equals the oracle's for a
+    sweep of bin counts; the bin count is numpy's unique over floor(coordinate / bin)."""
+    rng = np.random.default_rng(3)
+    w = rng.dirichlet(np.ones(500) * 0.3)
+    for u in (0.0, 0.25, 0.999):
+        np.testing.assert_array_equal(o.systematic_resample_to(w, u, 500), o.systematic_resample(w, u))
+    a = o.systematic_resample_to(w, 0.4, 123)
+    assert len(a) == 123 and np.all(np.diff(a) >= 0) and a[-1] <= 499
+    up = o.systematic_resample_to(w, 0.4, 5000)
+    counts = np.bincount(up, minlength=500)
+    assert np.all(np.abs(counts - 5000 * w) <= 1.0 + 1e-9)          # systematic: every count within one of N w
+    from smarc_navigation_b200 import _lib
+    L = _lib.load()
+    for k in (0, 1, 2, 3, 10, 499, 500, 12345, 10 ** 6, 10 ** 9):
+        for eps, z in ((0.05, 2.3263478740408408), (0.2, 0.0), (1e-4, 3.0)):
+            assert int(L.auvpf_kld_target(k, eps, z, 50, 10 ** 12)) == o.kld_target(k, eps, z, 50, 10 ** 12)
+    assert o.kld_target(500, 0.05, 2.3263478740408408, 1, 10 ** 9) == 5755            # Fox 2003, eq. 13 by hand
+    poses = np.zeros((6, 6))
+    poses[:, 0] = [0.1, 0.4, 0.6, -0.1, 0.1, 0.1]
+    poses[:, 5] = [0, 0, 0, 0, 0.2, -3.2]
+    assert o.kld_bins(poses, 0.5, 0.1) == 5

@@ -56,6 +56,7 @@ def main():
         pf.estimate(weighted=True, circular_yaw=True, full_cov=True)
         pf.pose_array(max_poses=100)
         pf.pose_array_topk(64)
+        pf.kld_bins()
         pf.close()
     # linear weights (resample(weights)) and a particle-sharded filter: 3 ranks on this device, peer-memory path
     import ctypes as C
