@@ -51,6 +51,12 @@ DEFAULTS = {
     "publish_max_particles": 2000,             # PoseArray size: a strided subsample built on the device (the reference
                                                # publishes every particle, :264-285; >= particle_count does the same)
     "estimate_circular_yaw": False,            # True: circular yaw mean instead of the mean of wrapped yaws (:229-231)
+    "kld_adaptive": False,                     # True: every MBES resample draws Fox's KLD bound of particles (the
+                                               # reference's particle_count, :27, is then the ceiling)
+    "kld_bin_xy": 0.5,                         # [m]
+    "kld_bin_yaw": 0.0873,                     # [rad] (5 degrees)
+    "kld_epsilon": 0.05,
+    "kld_min_particles": 1000,
 }
 
 
@@ -100,6 +106,9 @@ class AuvPfNode(object):
         self.updates = 0
         self.publish_max = int(param("publish_max_particles"))
         self.circular_yaw = bool(param("estimate_circular_yaw"))
+        self.kld = bool(param("kld_adaptive"))
+        self.kld_args = dict(bin_xy=float(param("kld_bin_xy")), bin_yaw=float(param("kld_bin_yaw")),
+                             eps=float(param("kld_epsilon")), n_min=int(param("kld_min_particles")))
 
     # -- map / sensor (GPU additions) ---------------------------------------------------------
     def set_map(self, z, x0=0.0, y0=0.0, res=1.0):
@@ -144,7 +153,10 @@ class AuvPfNode(object):
                 self.pf.set_scan_geometry(*geom)
                 self._scan_geometry = geom
             self.pf.update_mbes(np.asarray(scan.ranges, np.float32), return_weights=False)
-            self.pf.resample()
+            if self.kld:       # the cloud's occupied bins decide how many particles the resample draws (<= particle_count)
+                self.pf.resample(new_count=int(self.pf.kld_particle_count(**self.kld_args)[0]))
+            else:
+                self.pf.resample()
             self.updates += 1
 
     def loc_loop(self, event=None):                                              # :264-285

@@ -49,8 +49,12 @@ class FakeFilter(object):
         self.calls.append(("update_gps", tuple(xy)))
         return np.ones(self.kw["particle_count"])
 
-    def resample(self, weights=None):
-        self.calls.append(("resample", None if weights is None else len(weights)))
+    def resample(self, weights=None, new_count=None):
+        self.calls.append(("resample", None if weights is None else len(weights)) if new_count is None else ("resample_to", new_count))
+
+    def kld_particle_count(self, **kw):
+        self.calls.append(("kld", kw["bin_xy"], kw["n_min"]))
+        return np.array([4321])
 
     def poses(self):
         return np.zeros((self.kw["particle_count"], 6))
@@ -150,6 +154,14 @@ def test_mbes_callback_sets_geometry_once():
     n.mbes_cb(scan)
     n.mbes_cb(scan)
     assert [c[0] for c in n.pf.calls] == ["geometry", "update_mbes", "resample", "update_mbes", "resample"]
+
+
+def test_kld_adaptive_node_resamples_to_the_kld_bound():
+    params = dict(PARAMS, kld_adaptive=True, kld_bin_xy=0.25, kld_min_particles=500)
+    n = node_mod.AuvPfNode(lambda name, default=_REQUIRED: params[name] if name in params else get_param(name, default),
+                           np.eye(4), filter_factory=FakeFilter)
+    n.mbes_cb(_ns(ranges=[10.0] * 32, angle_min=-1.0, angle_increment=2.0 / 31))
+    assert n.pf.calls == [("geometry", 32), ("update_mbes", 32), ("kld", 0.25, 500), ("resample_to", 4321)]
 
 
 @pytest.mark.gpu
