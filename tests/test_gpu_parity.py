@@ -370,6 +370,69 @@ def test_update_mbes_unusable_beams_on_every_path(rmax):
     pf.close()
 
 
+@pytest.mark.parametrize("seed", [2, 5, 11])
+def test_randomised_scenes_on_the_gpu(seed):
+    """The adversarial sweep of tests/test_hostsim_math.py, on the device: smooth / ridged / terraced / spiked terrain,
+    sensors 8-25 m above it tilted by up to ~40 degrees, 64-512 beams, range_max 20-120 m, pings with a few unusable
+    beams.  The update kernels (march, border variant, ray by ray: whichever takes a sensor) against the oracle's
+    log-weights with the fragile-ray slack, and the probe kernel's ranges with the fragile-ray bracket."""
+    rng = np.random.default_rng(seed)
+
+    def terrain(kind, n, res, tseed):
+        if kind == "smooth":
+            return world.make_dem(n, res, seed=tseed)
+        if kind == "ridged":
+            return _ridged_dem(n, res, seed=tseed)
+        d = world.make_dem(n, res, seed=tseed)
+        z = d["z"].astype(np.float64)
+        x = np.arange(n) * res
+        X, Y = np.meshgrid(x, x)
+        if kind == "steps":
+            z = z + np.floor((X + 0.3 * Y) / 11.0) % 3 * 1.5
+        else:
+            z = z + (rng.uniform(size=z.shape) < 0.002) * rng.uniform(1, 4, z.shape)
+        d["z"] = z.astype(np.float32)
+        return d
+
+    worst = 0.0
+    for trial in range(40):
+        kind = rng.choice(["smooth", "ridged", "steps", "spikes"])
+        res, n = float(rng.choice([0.5, 1.0, 2.0])), int(rng.choice([300, 500]))
+        dem = terrain(kind, n, res, int(rng.integers(1, 100)))
+        ext = (n - 1) * res
+        B = int(rng.choice([64, 256, 512]))
+        beams = world.make_beams(B, float(rng.choice([45, 60, 70]))).astype(np.float32).astype(np.float64)
+        centre = (rng.uniform(0.15, 0.85) * ext, rng.uniform(0.15, 0.85) * ext)
+        alt = float(rng.choice([-5.0, -15.0, -22.0]))
+        poses = _cloud(rng, 160, centre, float(rng.choice([0.5, 5.0, 30.0])), roll_pitch=float(rng.choice([0.02, 0.1, 0.25])), z=alt)
+        poses = poses[(poses[:, 0] > 0) & (poses[:, 0] < ext) & (poses[:, 1] > 0) & (poses[:, 1] < ext)]
+        if len(poses) < 8:
+            continue
+        rmax = float(rng.choice([20.0, 35.0, 60.0, 120.0]))
+        truth = np.array([[centre[0], centre[1], alt, 0.0, 0.0, 0.3]])
+        meas = (c_oracle.update_mbes(dem, truth, np.eye(4), beams, None, 1.0, 0.5, rmax, want_ranges=True)["ranges"][0]
+                + rng.normal(0, 0.05, B)).astype(np.float32)
+        meas[rng.choice(B, 5, replace=False)] = np.nan
+        pf = _pf(particle_count=len(poses), measurement_std=1.0, range_min=world.RANGE_MIN, range_max=rmax)
+        pf.set_dem(dem)
+        pf.set_beams(beams)
+        pf.set_poses(poses)
+        pf.update_mbes(meas, return_weights=False)
+        got = pf.log_weights().astype(np.float64)
+        out = c_oracle.update_mbes(dem, poses, np.eye(4), beams, meas.astype(np.float64), 1.0, world.RANGE_MIN, rmax,
+                                   want_ranges=True, want_diag=True)
+        extra, fr = fragile.logw_bound(dem, poses, np.eye(4), beams, meas, 1.0, world.RANGE_MIN, rmax, out)
+        n_valid = int(np.sum(np.isfinite(meas) & (meas >= world.RANGE_MIN) & (meas <= rmax)))
+        lognorm = -n_valid * np.log(np.sqrt(2 * np.pi))
+        tol = LOGW_RTOL * (np.abs(out["logw"] - lognorm) + abs(lognorm)) + extra
+        d = np.abs(got - out["logw"])
+        assert np.all(d <= tol), (trial, kind, res, rmax, float(np.max(d / tol)))
+        worst = max(worst, float(np.max(d[tol > 0] / tol[tol > 0])) if (tol > 0).any() else 0.0)
+        _check_ranges(pf, dem, poses[:48], beams, np.eye(4), rmax, max_fragile=0.2, label="sweep %d/%d %s" % (seed, trial, kind))
+        pf.close()
+    assert worst <= 1.0
+
+
 def test_quantised_dem_file_parity(tmp_path):
     """Map ingestion: a DEM file with uint16 heights.  The library and the oracle both see the
     dequantised float32 map, so ranges and log-weights keep the usual tolerances ON THAT MAP."""
