@@ -1816,6 +1816,7 @@ int auvpf_replay(auvpf_handle *h, int32_t n_cycles, int32_t n_steps, int32_t n_o
     if (mode != AUVPF_SYSTEMATIC || (flags & (AUVPF_RS_INPLACE_REF | AUVPF_RS_STRICT_REF)))
         return fail(AUVPF_ERR_BADARG, "replay runs the enqueue-only cycle: AUVPF_SYSTEMATIC, AUVPF_RS_SORTED");
     if (h->global_count != h->M) return fail(AUVPF_ERR_BADARG, "replay is not available for a particle-sharded filter");
+    if (h->next_count > 0) return fail(AUVPF_ERR_STATE, "a change of the particle count is pending (auvpf_set_next_particle_count): replay keeps the count");
     if (!h->have_dem || h->B <= 0) return fail(AUVPF_ERR_STATE, "replay needs set_dem and set_beams first");
     if ((mean_out == nullptr) != (cov_out == nullptr)) return fail(AUVPF_ERR_BADARG, "mean_out and cov_out go together");
     if (mean_out && (is_device_ptr(mean_out) || is_device_ptr(cov_out)))
