@@ -10,6 +10,7 @@ for W in $WORLDS; do
   echo "world $W pytest rc=$?"; tail -4 gpurun_out/pytest_sharded_${TAG}_w$W.log
 done
 for W in $WORLDS; do
+  [ -n "$NOBENCH" ] && continue
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $W --steps 10 --warmup 3 "$@" > gpurun_out/bench_${TAG}_g$W.log 2>&1
   python - <<PY
 import json
