@@ -320,6 +320,14 @@ int auvpf_shard_degenerate(auvpf_handle *h, int32_t *flag);
  * ancestors_out_dev: n_ranks device pointers ((M) int64 each) or NULL. */
 int auvpf_group_resample(auvpf_handle *const *handles, int32_t n_ranks, double u, const double *rough_var,
                          int64_t *const *ancestors_out_dev);
+/* The estimate of the sharded filter (auv_pf.update_loc_pose, auv_pf.py:218-252) without a collective library:
+ * every rank's 16 pose sums (k_pose_stats: sums about the shard's first particle, see auvpf_pose_sums_dev) are
+ * posted into every peer's mailbox and collected by one small kernel; sums_all_out = host (G, 16) float64, the
+ * same table on every rank, to be combined in rank order (smarc_navigation_b200.sharded.combine_pose_sums).
+ * Like auvpf_shard_resample: every rank calls it the same number of times.  auvpf_group_pose_sums is the
+ * stage-interleaved form for the ranks of one process; sums_all_out = (n_ranks, G, 16), one table per rank. */
+int auvpf_shard_pose_sums(auvpf_handle *h, double *sums_all_out);
+int auvpf_group_pose_sums(auvpf_handle *const *handles, int32_t n_ranks, double *sums_all_out);
 /* Staged path (no peer memory: any topology a collective library reaches).  The caller moves the scalars:
  *   auvpf_shard_max_dev;  all-reduce MAX in place on wmax_i32 (ORDER-PRESERVING int32: an integer MAX is
  *   the float max);  auvpf_shard_weights_dev;  all-gather of totals_u64 (6 uint64: A low, A high, the

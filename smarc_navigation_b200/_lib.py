@@ -89,6 +89,8 @@ SYMBOLS = [
     ("auvpf_shard_resample", C.c_int, [_vp, _dbl, _vp, _vp, _vp]),
     ("auvpf_shard_degenerate", C.c_int, [_vp, C.POINTER(_i32)]),
     ("auvpf_group_resample", C.c_int, [C.POINTER(_vp), _i32, _dbl, _vp, C.POINTER(_vp)]),
+    ("auvpf_shard_pose_sums", C.c_int, [_vp, _vp]),
+    ("auvpf_group_pose_sums", C.c_int, [C.POINTER(_vp), _i32, _vp]),
     ("auvpf_shard_buffers", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     ("auvpf_shard_max_dev", C.c_int, [_vp]),
     ("auvpf_shard_weights_dev", C.c_int, [_vp]),

@@ -85,6 +85,8 @@ struct auvpf_handle {
     MailboxView mbox{};                         // peers' mailboxes (G = 1 until peers are attached)
     unsigned long long *mailbox = nullptr;      // this rank's mailbox (inside the slab)
     unsigned int epoch = 0;                     // resamples of the sharded filter so far
+    unsigned int est_epoch = 0;                 // ... and estimates exchanged through the mailbox (auvpf_shard_pose_sums)
+    double *est_all = nullptr;                  // [kMaxPeers][16] device: every rank's pose sums
     int *shard_degenerate = nullptr;            // [1] device: no shard had any finite weight (written by k_select)
     unsigned long long *shard_totals = nullptr; // [6] device: A lo, A hi, S1, S2 lo, S2 hi, log-weight buffer (staged variant)
     U128 *c_off = nullptr;                      // [kMaxPeers + 1] device: mass below every shard, [G] = the global total
@@ -988,7 +990,7 @@ int auvpf_destroy(auvpf_handle *h)
                     h->a_pre, h->deficit, h->u,     h->sumsq,        h->sums,    h->gps,    h->pparams, h->degenerate,
                     h->tile_counter, h->anc,   h->first,   h->scan2,  h->totals2, h->lost,
                     h->wmax_f32, h->done, h->scan3, h->skipped,
-                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->slope_blk, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->flagged2, h->probe_flags.p,
+                    h->dupes,   h->dem_z, h->mip,          h->beams,   h->meas,   h->mip_hi, h->slope_blk, h->est_all, h->beam_aux, h->beam_order, h->beam_tan, h->flagged, h->flagged2, h->probe_flags.p,
                     h->replay_params.p, h->replay_ranges.p, h->replay_u.p, h->replay_stats.p};
     for (void *b : bufs) cudaFree(b);
     for (auto &s : h->slots) cudaFree(s.p);
@@ -2310,6 +2312,72 @@ int auvpf_group_resample(auvpf_handle *const *handles, int32_t n_ranks, double u
         if ((rc = shard_stage_weights(handles[r], /*post_inside=*/false))) return rc;
     for (int r = 0; r < n_ranks; ++r)
         if ((rc = shard_stage_select(handles[r], rough_var, nullptr, ancestors_out_dev ? ancestors_out_dev[r] : nullptr))) return rc;
+    return AUVPF_OK;
+}
+
+// ---- the estimate across ranks through the mailbox: no NCCL call, one read-back ------------------------------------
+namespace {
+int est_stage_post(auvpf_handle *h)
+{
+    Guard g(h);
+    if (!h->est_all) CU(cudaMalloc(&h->est_all, sizeof(double) * 16 * kMaxPeers));
+    h->est_epoch++;
+    Prof pr(h, AUVPF_K_ESTIMATE);
+    CU(cudaMemsetAsync(h->sums, 0, sizeof(double) * 16, h->stream));
+    const int blocks = (int)std::min<int64_t>((h->M + kThreads - 1) / kThreads, 592);
+    k_pose_stats<<<dim3(blocks, 1), kThreads, 0, h->stream>>>(h->st[h->cur], h->M, h->sums);
+    MailboxView mb = h->mbox;
+    mb.epoch = h->est_epoch;
+    k_est_post<<<1, 32, 0, h->stream>>>(mb, (int)(h->est_epoch & 1u), h->sums);
+    LAUNCHED(h, AUVPF_K_ESTIMATE, 2);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+int est_stage_wait(auvpf_handle *h)
+{
+    Guard g(h);
+    MailboxView mb = h->mbox;
+    mb.epoch = h->est_epoch;
+    k_est_wait<<<1, 32, 0, h->stream>>>(mb, (int)(h->est_epoch & 1u), h->est_all);
+    LAUNCHED(h, AUVPF_K_ESTIMATE, 1);
+    CU(cudaGetLastError());
+    return AUVPF_OK;
+}
+int est_read(auvpf_handle *h, double *sums_all_out)
+{
+    Guard g(h);
+    CU(cudaMemcpyAsync(sums_all_out, h->est_all, sizeof(double) * 16 * h->n_peers, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return AUVPF_OK;
+}
+}  // namespace
+
+int auvpf_shard_pose_sums(auvpf_handle *h, double *sums_all_out)
+{
+    if (!h || !sums_all_out) return fail(AUVPF_ERR_BADARG, "null argument");
+    int rc;
+    if ((rc = shard_check(h))) return rc;
+    if (h->F != 1) return fail(AUVPF_ERR_BADARG, "one filter per shard");
+    if ((rc = est_stage_post(h))) return rc;
+    if ((rc = est_stage_wait(h))) return rc;
+    return est_read(h, sums_all_out);
+}
+
+int auvpf_group_pose_sums(auvpf_handle *const *handles, int32_t n_ranks, double *sums_all_out)
+{
+    if (!handles || !sums_all_out || n_ranks < 1 || n_ranks > kMaxPeers) return fail(AUVPF_ERR_BADARG, "bad handle list");
+    int rc;
+    for (int r = 0; r < n_ranks; ++r) {
+        if ((rc = shard_check(handles[r]))) return rc;
+        if (handles[r]->n_peers != n_ranks || handles[r]->my_peer != r)
+            return fail(AUVPF_ERR_BADARG, "handles[%d] is not rank %d of %d", r, r, n_ranks);
+    }
+    for (int r = 0; r < n_ranks; ++r)
+        if ((rc = est_stage_post(handles[r]))) return rc;
+    for (int r = 0; r < n_ranks; ++r)
+        if ((rc = est_stage_wait(handles[r]))) return rc;
+    for (int r = 0; r < n_ranks; ++r)                      // every rank holds the same table: [r][G][16] out
+        if ((rc = est_read(handles[r], sums_all_out + (size_t)r * 16 * n_ranks))) return rc;
     return AUVPF_OK;
 }
 

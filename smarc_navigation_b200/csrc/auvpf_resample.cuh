@@ -33,7 +33,11 @@ static_assert(kChunksPerTile == kThreads / 32, "one chunk per warp of the weight
 // memory.  A slot is rewritten only after every reader consumed it: a rank posts stage 0 of epoch e+1 after
 // its select kernel of epoch e, which waited for everybody's stage 1 of epoch e, which every rank posts
 // after all its blocks consumed stage 0 of epoch e (and the same one stage later).
-constexpr int kMboxStages = 2, kMboxWords = 8, kMboxFlag = 7;
+// Stages 0 and 1 carry the resample (maximum, totals); stages 2 .. 7 the ESTIMATE's 16 pose sums of a rank: three
+// slots of 7 payload words, twice -- by the parity of the estimate's own epoch, because a rank may post estimate
+// e + 1 while a slower peer still reads its slots of estimate e (it cannot post e + 2 before that peer has posted
+// e + 1, i.e. is done reading e).
+constexpr int kMboxStages = 8, kMboxWords = 8, kMboxFlag = 7, kMboxEstStage = 2, kMboxEstParts = 3;
 constexpr size_t kMboxBytes = sizeof(unsigned long long) * kMboxStages * kMaxPeers * kMboxWords;
 #ifndef AUVPF_MBOX_TIMEOUT_MS
 #define AUVPF_MBOX_TIMEOUT_MS 20000
@@ -99,6 +103,31 @@ __device__ __forceinline__ const unsigned long long *mbox_wait(const MailboxView
                    (t1 - t0) / 1000000ull, src, stage, mb.epoch, ld_acquire_sys(slot + kMboxFlag));
             __trap();
         }
+    }
+}
+
+// ---- the estimate of a particle-sharded filter: every rank's 16 pose sums (k_pose_stats) to every rank -----------
+// k_est_post: one thread posts this rank's sums; k_est_wait: thread g collects rank g's into out[g][16].  Two
+// kernels, so that one process driving several ranks can enqueue all posts before any wait (auvpf_group_pose_sums).
+__global__ void k_est_post(MailboxView mb, int parity, const double *__restrict__ sums)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int part = 0; part < kMboxEstParts; ++part) {
+        unsigned long long w[kMboxFlag];
+        const int n = min(kMboxFlag, 16 - kMboxFlag * part);
+        for (int k = 0; k < n; ++k) w[k] = (unsigned long long)__double_as_longlong(sums[kMboxFlag * part + k]);
+        mbox_post(mb, kMboxEstStage + parity * kMboxEstParts + part, w, n);
+    }
+}
+
+__global__ void k_est_wait(MailboxView mb, int parity, double *__restrict__ out)
+{
+    const int g = threadIdx.x;
+    if (blockIdx.x != 0 || g >= mb.G) return;
+    for (int part = 0; part < kMboxEstParts; ++part) {
+        const unsigned long long *slot = mbox_wait(mb, kMboxEstStage + parity * kMboxEstParts + part, g);
+        const int n = min(kMboxFlag, 16 - kMboxFlag * part);
+        for (int k = 0; k < n; ++k) out[g * 16 + kMboxFlag * part + k] = __longlong_as_double((long long)ld_relaxed_sys(slot + k));
     }
 }
 

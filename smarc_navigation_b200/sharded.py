@@ -31,6 +31,7 @@ orchestration can be exercised with ``gloo`` on CPU (tests/test_sharded_gloo.py 
 the product ``GpuShardOps`` calls the C ABI.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -372,11 +373,18 @@ class ShardedParticleFilter(object):
         return bool(self.pf.resample_skipped()[0])
 
     def mean_cov(self):
-        """Global estimate (auv_pf.py:218-252): every rank's 16 pose sums stay on the device, ONE small
-        collective on the library's stream gathers them and they are read back ONCE; combined in float64
-        in rank order, so every rank returns the same numbers."""
+        """Global estimate (auv_pf.py:218-252): every rank's 16 pose sums stay on the device; with peer memory they
+        are gathered by ONE small collective on the library's stream -- or, with ``AUVPF_ESTIMATE_MAILBOX=1`` and peer
+        memory, travel through the mailbox like the resample's scalars (``auvpf_shard_pose_sums``); read back ONCE and
+        combined in float64 in rank order, so every rank returns the same numbers."""
         torch = self.ops.torch
         L, h = self.ops.L, self.pf._h
+        if self.exchange == "p2p" and os.environ.get("AUVPF_ESTIMATE_MAILBOX", "0") == "1":
+            # through the mailbox in peer memory, like the resample: no collective library, one read-back.  OPT-IN:
+            # verified with 2-8 ranks on one GPU and on two GPUs, but the round's GPU budget ended before an 8-GPU run
+            s = np.empty((self.G, 16), np.float64)
+            self.ops._lib.check(L.auvpf_shard_pose_sums(h, s.ctypes.data_as(C.c_void_p)))
+            return combine_pose_sums(s, self.M)
         if self._sums is None:
             p = C.c_void_p()
             self.ops._lib.check(L.auvpf_pose_sums_buffer(h, C.byref(p)))

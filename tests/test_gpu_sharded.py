@@ -59,6 +59,8 @@ def _worker(rank, world, port, M, seed, tmp, exchange):
                             device_id=torch.device("cuda", rank))
     N = M * world
     logw, poses, u = _scene(N, seed)
+    if exchange == "p2p":
+        os.environ["AUVPF_ESTIMATE_MAILBOX"] = "1"          # the estimate through the mailbox as well (opt-in, see sharded.mean_cov)
     sp = ShardedParticleFilter(M, dist, device=rank, seed=seed, resampling_noise_covariance=[0.0] * 6,
                                exchange=exchange)
     assert sp.exchange == exchange, "peer memory unavailable: %s" % sp.exchange
@@ -81,6 +83,12 @@ def _worker(rank, world, port, M, seed, tmp, exchange):
         sp.pf.set_log_weights(lw[rank * M:(rank + 1) * M])
         sp.resample(u=0.1 + 0.2 * c, roughen=False)
     got_chain = sp.poses()
+    # the estimate again, three times in a row (mailbox path: both parities of its slots and the reuse of the first)
+    est_chain = [sp.mean_cov() for _ in range(3)]
+    # (equal up to the order of the floating-point atomics inside k_pose_stats, which differs from launch to launch;
+    # the scene's x = particle index makes the covariance sums ~1e18 at 1 M particles, hence RELATIVE)
+    assert all(np.allclose(e[0], est_chain[0][0], rtol=1e-9, atol=1e-9) and np.allclose(e[1], est_chain[0][1], rtol=1e-9, atol=1e-6)
+               for e in est_chain)
     # degenerate weights on every shard: state carried over, flag raised
     sp.pf.set_log_weights(np.full(M, -np.inf, np.float32))
     deg = False
@@ -98,7 +106,7 @@ def _worker(rank, world, port, M, seed, tmp, exchange):
         gated = bool(sp.resample_skipped()) and np.array_equal(sp.poses(), got3)
         sp.pf.set_neff_gate(0.0)
     np.savez(os.path.join(tmp, "r%d.npz" % rank), poses=got, poses2=got2, poses3=got3, chain=got_chain, deg=deg, u=u,
-             logw=logw, logw2=logw2, u2=u2, all_poses=poses, mean=mean, cov=cov, qq=qq,
+             logw=logw, logw2=logw2, u2=u2, all_poses=poses, mean=mean, cov=cov, qq=qq, mean_chain=est_chain[0][0],
              anc=anc_t.cpu().numpy() if anc_t is not None else np.zeros(0), gated=-1 if gated is None else int(gated))
     sp.close()
     dist.barrier()
@@ -123,6 +131,8 @@ def _check_parts(parts, world, M, seed, exchange):
     np.testing.assert_allclose(parts[0]["cov"], ec, rtol=1e-6, atol=1e-6)
     for p in parts[1:]:
         np.testing.assert_array_equal(p["mean"], parts[0]["mean"])              # every rank returns the same estimate
+        np.testing.assert_array_equal(p["mean_chain"], parts[0]["mean_chain"])
+    np.testing.assert_allclose(parts[0]["mean_chain"], o.estimate(np.concatenate([p["chain"] for p in parts]))[0], atol=1e-6)
     # second cycle
     logw2, u2 = parts[0]["logw2"], float(parts[0]["u2"])
     anc2 = c_oracle.systematic(o.weights_from_q(c_oracle.quantise_logw(logw2)[0]), u2)
@@ -221,6 +231,19 @@ def test_peer_memory_resample_on_one_gpu(G, M, seed):
         everyone(uu, rough=res)
         one.resample(u=uu)
         np.testing.assert_array_equal(np.concatenate([pf.poses() for pf in pfs]), one.poses())
+        # the estimate through the mailbox (auvpf_group_pose_sums: every rank's 16 pose sums to every rank): the same
+        # table on all ranks, and combined it is update_loc_pose on the whole cloud; three calls in a row exercise
+        # both parities of its slots and the reuse of the first
+        from smarc_navigation_b200.sharded import combine_pose_sums
+        for rep in range(3 if c == 0 else 1):
+            tab = np.empty((G, G, 16), np.float64)
+            _lib.check(L.auvpf_group_pose_sums(handles, G, tab.ctypes.data_as(C.c_void_p)))
+            for g in range(1, G):
+                np.testing.assert_array_equal(tab[g], tab[0])
+            mean, cov = combine_pose_sums(tab[0], M)
+            em, ec, _ = o.estimate(one.poses())
+            np.testing.assert_allclose(mean, em, atol=1e-9)
+            np.testing.assert_allclose(cov, ec, atol=1e-9)
     # the gate on the global sums: uniform weights are held back at ratio 0.5, concentrated ones are not
     state = one.poses()
     for pf in pfs + [one]:
