@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define AUVPF_VERSION 201 /* 201: + auvpf_pose_array_topk, auvpf_kld_bins, auvpf_kld_target, auvpf_set_next_particle_count, auvpf_particle_capacity */
+#define AUVPF_VERSION 202 /* 201: + auvpf_pose_array_topk, auvpf_kld_bins, auvpf_kld_target, auvpf_set_next_particle_count, auvpf_particle_capacity; 202: + auvpf_shard_pose_sums, auvpf_group_pose_sums */
 
 /* status codes */
 #define AUVPF_OK 0

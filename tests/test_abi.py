@@ -25,7 +25,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, n), "libauvpf.so does not export %s" % n
         assert n in bound, "%s declared in auvpf.h but not bound in _lib.SYMBOLS" % n
     assert bound <= set(names)
-    assert lib.auvpf_version() == 201
+    assert lib.auvpf_version() == 202
 
 
 def test_config_struct_matches_header():
