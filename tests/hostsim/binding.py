@@ -141,12 +141,14 @@ def neff_fixed(a):
     return float(fn(_p(q), C.c_long(len(q))))
 
 
-def select_source_side(a, u, G=1, want_stats=False):
+def select_source_side(a, u, G=1, want_stats=False, n_out=None):
     """Ancestors by the host twin of k_select (chunk tables, source-side run ends from the cdf estimate,
-    exact fix-up, run heads + max-scan) for ``G`` shards; ``a``: the integer weights of all G*M sources."""
+    exact fix-up, run heads + max-scan) for ``G`` shards; ``a``: the integer weights of all G*M sources.
+    ``n_out``: number of positions (default: as many as sources)."""
     a = np.ascontiguousarray(a, np.uint64)
     assert len(a) % G == 0
-    anc = np.zeros(len(a), np.int32)
+    n_out = len(a) if n_out is None else int(n_out)
+    anc = np.zeros(n_out, np.int32)
     stats = (C.c_long * 2)()
-    lib().hs_select_source_side(_p(a), C.c_long(len(a) // G), C.c_int(G), C.c_double(u), _p(anc), stats)
+    lib().hs_select_source_side_n(_p(a), C.c_long(len(a) // G), C.c_int(G), C.c_double(u), C.c_long(n_out), _p(anc), stats)
     return (anc, (int(stats[0]), int(stats[1]))) if want_stats else anc

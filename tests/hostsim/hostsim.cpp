@@ -390,10 +390,12 @@ float hs_wrap_pi(float a) { return wrap_pi(a); }
 // sums and the warp scan's order of additions, rel_end_fast, the exact fix-up (cdf_exact + rel_end_of) only where
 // the estimate cannot decide, run heads, inclusive max-scan.  a: the integer weights of all G*M sources.
 // stats (optional, 2 longs): sources evaluated by the fast path / by the exact path.
-void hs_select_source_side(const uint64_t *a, long M, int G, double u, int32_t *anc, long *stats)
+// n_out: positions (u + i) / n_out, i < n_out, over the CDF of the G*M sources (the resample that changes the particle
+// count; n_out = G*M: the ordinary one) -- SelArgs::n_global vs n_src_total.
+void hs_select_source_side_n(const uint64_t *a, long M, int G, double u, long n_out, int32_t *anc, long *stats)
 {
     const int kTile = 2048, kItems = 8, kOut = 1024, kCh = 256, kCpt = 8;
-    const long tiles = (M + kTile - 1) / kTile, n_tiles = G * tiles, N = (long)G * M;
+    const long tiles = (M + kTile - 1) / kTile, n_tiles = G * tiles, Ns = (long)G * M, N = n_out;
     std::vector<U128> chunk((size_t)n_tiles * kCpt), tprefix((size_t)n_tiles), coff(G + 1);
     {
         unsigned __int128 acc_all = 0;
@@ -464,7 +466,7 @@ void hs_select_source_side(const uint64_t *a, long M, int G, double u, int32_t *
                 const U128 C_before = tile_base + (warp > 0 ? incl[warp - 1] : u128(0)), C_after = tile_base + incl[warp];
                 const long jc = t * kTile + (long)warp * kCh;
                 if (jc >= M) continue;
-                const bool has_last = (long)g * M + std::min<long>(jc + kCh, M) - 1 == N - 1;
+                const bool has_last = (long)g * M + std::min<long>(jc + kCh, M) - 1 == Ns - 1;
                 if (C_after == C_before && !has_last) continue;
                 const int e_begin = rel_end(C_before);
                 if (e_begin == nblk) break;
@@ -522,7 +524,7 @@ void hs_select_source_side(const uint64_t *a, long M, int G, double u, int32_t *
                     }
                     Cint = Ck;
                     for (int k = 0; k < kItems; ++k)
-                        if ((long)g * M + jc + lane * kItems + k == N - 1) e[k] = nblk;
+                        if ((long)g * M + jc + lane * kItems + k == Ns - 1) e[k] = nblk;
                     int start = prev_last;
                     const int wbase = (int)((T - T_lo) * kTile + warp * kCh + lane * kItems);
                     for (int k = 0; k < kItems; ++k) {
@@ -548,6 +550,11 @@ void hs_select_source_side(const uint64_t *a, long M, int G, double u, int32_t *
         stats[0] = n_fast;
         stats[1] = n_exact;
     }
+}
+
+void hs_select_source_side(const uint64_t *a, long M, int G, double u, int32_t *anc, long *stats)
+{
+    hs_select_source_side_n(a, M, G, u, (long)G * M, anc, stats);
 }
 
 // the N_eff gate's integer sums over the integer weights, accumulated like k_weights does

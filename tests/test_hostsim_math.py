@@ -594,6 +594,21 @@ def test_source_side_select_over_shards(G, M):
         assert got[-1] == N - 1
 
 
+@pytest.mark.parametrize("M,n_out", [(5000, 700), (5000, 1), (700, 5000), (4097, 4096), (2048, 100000), (70001, 1025)])
+def test_source_side_select_with_a_different_number_of_positions(M, n_out):
+    """The resample that changes the particle count (KLD adaptation): n_out positions over the CDF of M
+    sources -- fewer and more outputs than sources, across the tile / chunk / output-block sizes -- against the
+    oracle's generalised systematic resample."""
+    rng = np.random.default_rng(M + n_out)
+    for logw in _cases(M, rng):
+        qq, a = _quantised(logw)
+        w = o.weights_from_q(qq)
+        for u in (float(rng.uniform()), 0.0, 1.0 - 2.0 ** -20):
+            np.testing.assert_array_equal(hs.select_source_side(a, u, n_out=n_out), o.systematic_resample_to(w, u, n_out))
+        got = hs.select_source_side(a, 1.0 - 2.0 ** -53, n_out=n_out)         # the last position rounds to 1.0: last SOURCE
+        assert got[-1] <= M - 1 and np.all(np.diff(got) >= 0)
+
+
 def test_source_side_select_exact_fixups_are_exercised():
     """Weights built so that many run ends land EXACTLY on an output position (cdf N 2^-52 - u integral):
     the estimate cannot decide those, the exact path must, and the result is still the reference's."""
